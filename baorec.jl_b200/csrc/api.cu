@@ -1,0 +1,250 @@
+// extern "C" entry points for the mesh set-up, iterative solver, read-back and the
+// host-buffer pipelines (run! / reconstructed_positions equivalents).
+#include "internal.cuh"
+
+using namespace baorec;
+
+namespace baorec {
+
+static int check_params(const baorec_params* p) {
+  BR_REQUIRE(p != nullptr, "params is NULL");
+  BR_REQUIRE(p->bias != 0.f, "bias must be non-zero");
+  BR_REQUIRE(p->mas == BAOREC_MAS_CIC || p->mas == BAOREC_MAS_TSC, "unknown mas");
+  BR_REQUIRE(p->n_iter >= 0 && p->jacobi_niterations >= 0 && p->vcycle_niterations >= 0, "negative iteration count");
+  return BAOREC_OK;
+}
+
+static int check_catalog(int64_t n, const void* x, const void* y, const void* z, const void* w, const char* what) {
+  if (n < 0) {
+    set_error("invalid argument: %s count < 0", what);
+    return BAOREC_ERR_INVALID;
+  }
+  if (n > 0 && !(x && y && z && w)) {
+    set_error("invalid argument: NULL %s array", what);
+    return BAOREC_ERR_INVALID;
+  }
+  return BAOREC_OK;
+}
+
+// Displacement meshes of `mesh` into RX/RY/RZ, then the fused gather + read_shifts epilogue.
+static int read_common(baorec_ctx* ctx, const baorec_params* p, int algorithm, const float* mesh, const float* x,
+                       const float* y, const float* z, int64_t n, int field, int positions, float* ox, float* oy,
+                       float* oz, cudaStream_t st) {
+  float *px, *py, *pz;
+  BR_TRY(need_t(ctx, BUF_RX, ctx->M, &px));
+  BR_TRY(need_t(ctx, BUF_RY, ctx->M, &py));
+  BR_TRY(need_t(ctx, BUF_RZ, ctx->M, &pz));
+  BR_TRY(displacement_meshes(ctx, mesh, algorithm, px, py, pz, st));
+  BR_CUDA(cudaEventRecord(ctx->ev[5], st));
+  BR_TRY(reset_oob(ctx, st));
+  BR_TRY(gather3(ctx, px, py, pz, x, y, z, n, ox, oy, oz, p->mas, field, p->f, p->has_los, p->los, positions, st));
+  return check_oob(ctx, st, "read_shifts");
+}
+
+}  // namespace baorec
+
+extern "C" {
+
+int baorec_smooth_f32(baorec_ctx* ctx, float* d_mesh, float smoothing_radius, baorec_stream stream) {
+  BR_NEED_PLAN(ctx);
+  BR_REQUIRE(d_mesh != nullptr, "mesh is NULL");
+  return smooth(ctx, d_mesh, smoothing_radius, (cudaStream_t)stream);
+}
+
+int baorec_setup_overdensity_f32(baorec_ctx* ctx, const baorec_params* p, float* d_mesh, float* d_x, float* d_y,
+                                 float* d_z, const float* d_w, int64_t n, float* d_rx, float* d_ry, float* d_rz,
+                                 const float* d_rw, int64_t n_ran, int wrap, baorec_stream stream) {
+  BR_NEED_PLAN(ctx);
+  BR_TRY(check_params(p));
+  BR_REQUIRE(d_mesh != nullptr, "mesh is NULL");
+  BR_TRY(check_catalog(n, d_x, d_y, d_z, d_w, "data"));
+  BR_TRY(check_catalog(n_ran, d_rx, d_ry, d_rz, d_rw, "randoms"));
+  return setup_overdensity(ctx, p, d_mesh, d_x, d_y, d_z, d_w, n, d_rx, d_ry, d_rz, d_rw, n_ran, wrap,
+                           (cudaStream_t)stream);
+}
+
+int baorec_iterate_f32(baorec_ctx* ctx, float* d_delta_r, const float* d_delta_s, int iter, float beta,
+                       const float* h_los, baorec_stream stream) {
+  BR_NEED_PLAN(ctx);
+  BR_REQUIRE(d_delta_r && d_delta_s && iter >= 1, "iterate arguments");
+  return iterate(ctx, d_delta_r, d_delta_s, iter, beta, h_los, (cudaStream_t)stream);
+}
+
+int baorec_reconstructed_overdensity_f32(baorec_ctx* ctx, const baorec_params* p, float* d_mesh, float* d_x,
+                                         float* d_y, float* d_z, const float* d_w, int64_t n, float* d_rx,
+                                         float* d_ry, float* d_rz, const float* d_rw, int64_t n_ran,
+                                         baorec_stream stream) {
+  BR_NEED_PLAN(ctx);
+  BR_TRY(check_params(p));
+  BR_REQUIRE(d_mesh != nullptr, "mesh is NULL");
+  BR_TRY(check_catalog(n, d_x, d_y, d_z, d_w, "data"));
+  BR_TRY(check_catalog(n_ran, d_rx, d_ry, d_rz, d_rw, "randoms"));
+  return reconstructed_overdensity(ctx, p, d_mesh, d_x, d_y, d_z, d_w, n, d_rx, d_ry, d_rz, d_rw, n_ran,
+                                   (cudaStream_t)stream);
+}
+
+int baorec_reconstructed_potential_f32(baorec_ctx* ctx, const baorec_params* p, float* d_phi, float* d_x, float* d_y,
+                                       float* d_z, const float* d_w, int64_t n, float* d_rx, float* d_ry, float* d_rz,
+                                       const float* d_rw, int64_t n_ran, baorec_stream stream) {
+  BR_NEED_PLAN(ctx);
+  BR_TRY(check_params(p));
+  BR_REQUIRE(d_phi != nullptr, "phi is NULL");
+  BR_TRY(check_catalog(n, d_x, d_y, d_z, d_w, "data"));
+  BR_TRY(check_catalog(n_ran, d_rx, d_ry, d_rz, d_rw, "randoms"));
+  return reconstructed_potential(ctx, p, d_phi, d_x, d_y, d_z, d_w, n, d_rx, d_ry, d_rz, d_rw, n_ran,
+                                 (cudaStream_t)stream);
+}
+
+int baorec_displacement_meshes_f32(baorec_ctx* ctx, const float* d_mesh, int algorithm, float* d_psix, float* d_psiy,
+                                   float* d_psiz, baorec_stream stream) {
+  BR_NEED_PLAN(ctx);
+  BR_REQUIRE(d_mesh && d_psix && d_psiy && d_psiz, "NULL mesh pointer");
+  BR_REQUIRE(algorithm == BAOREC_ITERATIVE || algorithm == BAOREC_MULTIGRID, "unknown algorithm");
+  return displacement_meshes(ctx, d_mesh, algorithm, d_psix, d_psiy, d_psiz, (cudaStream_t)stream);
+}
+
+int baorec_compute_displacements_f32(baorec_ctx* ctx, const float* d_mesh, int algorithm, const float* d_x,
+                                     const float* d_y, const float* d_z, int64_t n, float* d_px, float* d_py,
+                                     float* d_pz, int mas, baorec_stream stream) {
+  BR_NEED_PLAN(ctx);
+  BR_REQUIRE(d_mesh != nullptr, "mesh is NULL");
+  BR_REQUIRE(algorithm == BAOREC_ITERATIVE || algorithm == BAOREC_MULTIGRID, "unknown algorithm");
+  BR_REQUIRE(n >= 0 && (n == 0 || (d_x && d_y && d_z && d_px && d_py && d_pz)), "particle arrays");
+  baorec_params p = {};
+  p.bias = 1.f;
+  p.mas = mas;
+  p.has_los = 1;
+  return read_common(ctx, &p, algorithm, d_mesh, d_x, d_y, d_z, n, BAOREC_FIELD_DISP, 0, d_px, d_py, d_pz,
+                     (cudaStream_t)stream);
+}
+
+int baorec_read_shifts_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, const float* d_mesh,
+                           const float* d_x, const float* d_y, const float* d_z, int64_t n, int field, float* d_sx,
+                           float* d_sy, float* d_sz, baorec_stream stream) {
+  BR_NEED_PLAN(ctx);
+  BR_TRY(check_params(p));
+  BR_REQUIRE(d_mesh != nullptr, "mesh is NULL");
+  BR_REQUIRE(field >= BAOREC_FIELD_DISP && field <= BAOREC_FIELD_SUM, "unknown field");
+  BR_REQUIRE(n >= 0 && (n == 0 || (d_x && d_y && d_z && d_sx && d_sy && d_sz)), "particle arrays");
+  return read_common(ctx, p, algorithm, d_mesh, d_x, d_y, d_z, n, field, 0, d_sx, d_sy, d_sz, (cudaStream_t)stream);
+}
+
+int baorec_reconstructed_positions_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, const float* d_mesh,
+                                       const float* d_x, const float* d_y, const float* d_z, int64_t n, int field,
+                                       float* d_ox, float* d_oy, float* d_oz, baorec_stream stream) {
+  BR_NEED_PLAN(ctx);
+  BR_TRY(check_params(p));
+  BR_REQUIRE(d_mesh != nullptr, "mesh is NULL");
+  BR_REQUIRE(field >= BAOREC_FIELD_DISP && field <= BAOREC_FIELD_SUM, "unknown field");
+  BR_REQUIRE(n >= 0 && (n == 0 || (d_x && d_y && d_z && d_ox && d_oy && d_oz)), "particle arrays");
+  return read_common(ctx, p, algorithm, d_mesh, d_x, d_y, d_z, n, field, 1, d_ox, d_oy, d_oz, (cudaStream_t)stream);
+}
+
+// ---- host pipelines ---------------------------------------------------------------------------------
+int baorec_run_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, float* h_x, float* h_y, float* h_z,
+                        const float* h_w, int64_t n, const float* h_rx, const float* h_ry, const float* h_rz,
+                        const float* h_rw, int64_t n_ran, float* h_mesh_out, float box_size_out[3],
+                        float box_min_out[3]) {
+  BR_NEED_PLAN(ctx);
+  BR_TRY(check_params(p));
+  BR_REQUIRE(algorithm == BAOREC_ITERATIVE || algorithm == BAOREC_MULTIGRID, "unknown algorithm");
+  BR_TRY(check_catalog(n, h_x, h_y, h_z, h_w, "data"));
+  BR_TRY(check_catalog(n_ran, h_rx, h_ry, h_rz, h_rw, "randoms"));
+  cudaStream_t st = ctx->own_stream;
+  ctx->cache_valid = false;
+  float *dp, *dr = nullptr, *mesh;
+  BR_TRY(need_t(ctx, BUF_PART, (size_t)(n > 0 ? n : 1) * 4, &dp));
+  if (n_ran > 0) BR_TRY(need_t(ctx, BUF_PART2, (size_t)n_ran * 4, &dr));
+  BR_TRY(need_t(ctx, BUF_CACHE, ctx->M, &mesh));
+  BR_CUDA(cudaEventRecord(ctx->ev[0], st));
+  const float* hsrc[4] = {h_x, h_y, h_z, h_w};
+  for (int c = 0; c < 4 && n > 0; c++)
+    BR_CUDA(cudaMemcpyAsync(dp + (size_t)c * n, hsrc[c], (size_t)n * sizeof(float), cudaMemcpyHostToDevice, st));
+  const float* hrs[4] = {h_rx, h_ry, h_rz, h_rw};
+  for (int c = 0; c < 4 && n_ran > 0; c++)
+    BR_CUDA(cudaMemcpyAsync(dr + (size_t)c * n_ran, hrs[c], (size_t)n_ran * sizeof(float), cudaMemcpyHostToDevice, st));
+  BR_CUDA(cudaMemsetAsync(mesh, 0, ctx->M * sizeof(float), st));
+  if (n_ran > 0) {
+    // run! with randoms overrides the box: setup_box(rand..., 500)  (src/recon.jl:172, 253)
+    float L[3], mn[3];
+    BR_TRY(setup_box_dev(ctx, dr, dr + n_ran, dr + 2 * n_ran, n_ran, p->box_pad, L, mn, st));
+    BR_TRY(baorec_set_box(ctx, L, mn));
+  }
+  if (box_size_out && box_min_out)
+    for (int a = 0; a < 3; a++) {
+      box_size_out[a] = ctx->L[a];
+      box_min_out[a] = ctx->mn[a];
+    }
+  BR_CUDA(cudaEventRecord(ctx->ev[1], st));
+  float* rx = dr;
+  float* ry = dr ? dr + n_ran : nullptr;
+  float* rz = dr ? dr + 2 * n_ran : nullptr;
+  float* rw = dr ? dr + 3 * n_ran : nullptr;
+  int s;
+  if (algorithm == BAOREC_MULTIGRID)
+    s = reconstructed_potential(ctx, p, mesh, dp, dp + n, dp + 2 * n, dp + 3 * n, n, rx, ry, rz, rw, n_ran, st);
+  else
+    s = reconstructed_overdensity(ctx, p, mesh, dp, dp + n, dp + 2 * n, dp + 3 * n, n, rx, ry, rz, rw, n_ran, st);
+  if (s != BAOREC_OK) return s;
+  BR_CUDA(cudaEventRecord(ctx->ev[2], st));
+  if (n_ran == 0 && n > 0) {
+    // cic!(wrap = true) mutates the caller's positions (src/mas.jl:8-10): copy them back.
+    float* hdst[3] = {h_x, h_y, h_z};
+    for (int c = 0; c < 3; c++)
+      BR_CUDA(cudaMemcpyAsync(hdst[c], dp + (size_t)c * n, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  if (h_mesh_out) BR_CUDA(cudaMemcpyAsync(h_mesh_out, mesh, ctx->M * sizeof(float), cudaMemcpyDeviceToHost, st));
+  BR_CUDA(cudaEventRecord(ctx->ev[3], st));
+  BR_CUDA(cudaStreamSynchronize(st));
+  ctx->cache_valid = true;
+  ctx->n_stage = 3;
+  for (int i = 0; i < 3; i++) BR_CUDA(cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]));
+  return BAOREC_OK;
+}
+
+int baorec_read_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, const float* h_mesh_or_null,
+                         const float* h_x, const float* h_y, const float* h_z, int64_t n, int field, int shifts_only,
+                         float* h_ox, float* h_oy, float* h_oz) {
+  BR_NEED_PLAN(ctx);
+  BR_TRY(check_params(p));
+  BR_REQUIRE(algorithm == BAOREC_ITERATIVE || algorithm == BAOREC_MULTIGRID, "unknown algorithm");
+  BR_REQUIRE(field >= BAOREC_FIELD_DISP && field <= BAOREC_FIELD_SUM, "unknown field");
+  BR_REQUIRE(n >= 0 && (n == 0 || (h_x && h_y && h_z && h_ox && h_oy && h_oz)), "particle arrays");
+  cudaStream_t st = ctx->own_stream;
+  float *mesh, *dp, *dout;
+  BR_TRY(need_t(ctx, BUF_CACHE, ctx->M, &mesh));
+  if (h_mesh_or_null) {
+    BR_CUDA(cudaMemcpyAsync(mesh, h_mesh_or_null, ctx->M * sizeof(float), cudaMemcpyHostToDevice, st));
+    ctx->cache_valid = true;
+  }
+  if (!ctx->cache_valid) {
+    set_error("baorec_read_host_f32: no cached result mesh (call baorec_run_host_f32 first or pass a mesh)");
+    return BAOREC_ERR_INVALID;
+  }
+  size_t nn = (size_t)(n > 0 ? n : 1);
+  BR_TRY(need_t(ctx, BUF_OUT, nn * 6, &dout));
+  dp = dout + 3 * nn;
+  BR_CUDA(cudaEventRecord(ctx->ev[4], st));
+  const float* hsrc[3] = {h_x, h_y, h_z};
+  for (int c = 0; c < 3 && n > 0; c++)
+    BR_CUDA(cudaMemcpyAsync(dp + c * nn, hsrc[c], (size_t)n * sizeof(float), cudaMemcpyHostToDevice, st));
+  BR_TRY(read_common(ctx, p, algorithm, mesh, dp, dp + nn, dp + 2 * nn, n, field, shifts_only ? 0 : 1, dout, dout + nn,
+                     dout + 2 * nn, st));
+  BR_CUDA(cudaEventRecord(ctx->ev[6], st));
+  float* hdst[3] = {h_ox, h_oy, h_oz};
+  for (int c = 0; c < 3 && n > 0; c++)
+    BR_CUDA(cudaMemcpyAsync(hdst[c], dout + c * nn, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  BR_CUDA(cudaEventRecord(ctx->ev[7], st));
+  BR_CUDA(cudaStreamSynchronize(st));
+  float a = 0, b = 0, c2 = 0;
+  BR_CUDA(cudaEventElapsedTime(&a, ctx->ev[4], ctx->ev[5]));
+  BR_CUDA(cudaEventElapsedTime(&b, ctx->ev[5], ctx->ev[6]));
+  BR_CUDA(cudaEventElapsedTime(&c2, ctx->ev[6], ctx->ev[7]));
+  ctx->stage_ms[3] = a;
+  ctx->stage_ms[4] = b;
+  ctx->stage_ms[5] = c2;
+  ctx->n_stage = 6;
+  return BAOREC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,296 @@
+// Context lifecycle, planning (cuFFT plans, k/x tables), scratch arena, FFT wrappers.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "internal.cuh"
+
+namespace baorec {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int need(baorec_ctx* ctx, BufId id, size_t bytes, void** out) {
+  Buf& b = ctx->bufs[id];
+  if (b.bytes < bytes) {
+    if (b.p) {
+      BR_CUDA(cudaFree(b.p));
+      b.p = nullptr;
+      b.bytes = 0;
+    }
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc of %zu bytes for scratch buffer %d failed: %s", bytes, (int)id, cudaGetErrorString(e));
+      b.p = nullptr;
+      return BAOREC_ERR_NOMEM;
+    }
+    b.bytes = bytes;
+  }
+  *out = b.p;
+  return BAOREC_OK;
+}
+
+void release(baorec_ctx* ctx, BufId id) {
+  Buf& b = ctx->bufs[id];
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.bytes = 0;
+}
+
+int reset_oob(baorec_ctx* ctx, cudaStream_t st) {
+  BR_CUDA(cudaMemsetAsync(ctx->d_oob, 0, sizeof(unsigned long long), st));
+  return BAOREC_OK;
+}
+
+int check_oob(baorec_ctx* ctx, cudaStream_t st, const char* what) {
+  unsigned long long h = 0;
+  BR_CUDA(cudaMemcpyAsync(&h, ctx->d_oob, sizeof(h), cudaMemcpyDeviceToHost, st));
+  BR_CUDA(cudaStreamSynchronize(st));
+  if (h != 0) {
+    set_error("%s: %llu particle(s) outside the mesh (the reference would raise BoundsError / write out of bounds)",
+              what, h);
+    return BAOREC_ERR_OUT_OF_BOX;
+  }
+  return BAOREC_OK;
+}
+
+int fft_r2c(baorec_ctx* ctx, const float* in, float2* out, cudaStream_t st) {
+  BR_CUFFT(cufftSetStream(ctx->r2c, st));
+  BR_CUFFT(cufftExecR2C(ctx->r2c, (cufftReal*)in, (cufftComplex*)out));
+  ctx->n_fft++;
+  return BAOREC_OK;
+}
+
+int fft_c2r(baorec_ctx* ctx, float2* in, float* out, cudaStream_t st) {
+  BR_CUFFT(cufftSetStream(ctx->c2r, st));
+  BR_CUFFT(cufftExecC2R(ctx->c2r, (cufftComplex*)in, (cufftReal*)out));
+  ctx->n_fft++;
+  return BAOREC_OK;
+}
+
+// k_vec (src/utils.jl:3-10): fs = T(2pi n / L) from a Float64 product, multiplier fs/n in T,
+// value = T(integer) * multiplier.
+static void host_kvec(int n, float L, bool half, std::vector<float>& out) {
+  float fs = (float)(2.0 * M_PI * (double)n / (double)L);
+  float mult = fs / (float)n;
+  if (half) {
+    out.resize(n / 2 + 1);
+    for (int i = 0; i <= n / 2; i++) out[i] = (float)i * mult;
+  } else {
+    out.resize(n);
+    int nn = (n + 1) >> 1;
+    for (int i = 0; i < n; i++) {
+      int f = i < nn ? i : i - n;
+      out[i] = (float)f * mult;
+    }
+  }
+}
+
+// x_vec (src/utils.jl:21-25): cell = L/n in T; Float64 range min + 0.5 cell + i cell, rounded to T.
+void host_xvec(int n, float L, float mn, std::vector<float>& out) {
+  float cell = L / (float)n;
+  double start = (double)mn + 0.5 * (double)cell;
+  out.resize(n);
+  for (int i = 0; i < n; i++) out[i] = (float)(start + (double)i * (double)cell);
+}
+
+static int upload_tables(baorec_ctx* ctx) {
+  int n[3] = {ctx->nx, ctx->ny, ctx->nz};
+  for (int a = 0; a < 3; a++) {
+    std::vector<float> k, x;
+    host_kvec(n[a], ctx->L[a], a == 0, k);
+    host_xvec(n[a], ctx->L[a], ctx->mn[a], x);
+    BR_CUDA(cudaMemcpy(ctx->d_k[a], k.data(), k.size() * sizeof(float), cudaMemcpyHostToDevice));
+    BR_CUDA(cudaMemcpy(ctx->d_xv[a], x.data(), x.size() * sizeof(float), cudaMemcpyHostToDevice));
+    ctx->cell[a] = ctx->L[a] / (float)n[a];
+  }
+  ctx->mg_radial_tables = false;
+  return BAOREC_OK;
+}
+
+static void destroy_plans(baorec_ctx* ctx) {
+  if (ctx->have_plans) {
+    cufftDestroy(ctx->r2c);
+    cufftDestroy(ctx->c2r);
+    ctx->have_plans = false;
+  }
+  if (ctx->have_dist_plans) {
+    cufftDestroy(ctx->p2d_r2c);
+    cufftDestroy(ctx->p2d_c2r);
+    cufftDestroy(ctx->p1d);
+    ctx->have_dist_plans = false;
+  }
+}
+
+int plan_common(baorec_ctx* ctx, int nx, int ny, int nz, const float L[3], const float mn[3]) {
+  BR_REQUIRE(ctx != nullptr, "ctx is NULL");
+  BR_REQUIRE(nx >= 2 && ny >= 2 && nz >= 2, "mesh must be at least 2 cells per axis");
+  BR_REQUIRE(nx % 2 == 0, "nx must be even (R2C halves the x axis)");
+  BR_REQUIRE(nz <= 65535 && ny <= 65535, "ny, nz must be <= 65535");
+  BR_REQUIRE(L && mn, "box_size / box_min are NULL");
+  BR_REQUIRE(L[0] > 0 && L[1] > 0 && L[2] > 0, "box_size must be positive");
+  BR_CUDA(cudaSetDevice(ctx->device));
+  bool same = ctx->planned && ctx->nx == nx && ctx->ny == ny && ctx->nz == nz;
+  if (!same) {
+    destroy_plans(ctx);
+    for (int a = 0; a < 3; a++) {
+      if (ctx->d_k[a]) cudaFree(ctx->d_k[a]);
+      if (ctx->d_xv[a]) cudaFree(ctx->d_xv[a]);
+      ctx->d_k[a] = ctx->d_xv[a] = nullptr;
+    }
+    ctx->levels.clear();
+    ctx->nx = nx;
+    ctx->ny = ny;
+    ctx->nz = nz;
+    ctx->xh = nx / 2 + 1;
+    ctx->M = (size_t)nx * ny * nz;
+    ctx->Mc = (size_t)ctx->xh * ny * nz;
+    int n[3] = {nx, ny, nz};
+    for (int a = 0; a < 3; a++) {
+      BR_CUDA(cudaMalloc(&ctx->d_k[a], sizeof(float) * (a == 0 ? ctx->xh : n[a])));
+      BR_CUDA(cudaMalloc(&ctx->d_xv[a], sizeof(float) * n[a]));
+    }
+    ctx->cache_valid = false;
+  }
+  for (int a = 0; a < 3; a++) {
+    ctx->L[a] = L[a];
+    ctx->mn[a] = mn[a];
+  }
+  BR_TRY(upload_tables(ctx));
+  return same ? 1 : 0;
+}
+
+}  // namespace baorec
+
+using namespace baorec;
+
+extern "C" {
+
+int baorec_version(void) { return BAOREC_VERSION; }
+const char* baorec_last_error(void) { return g_err; }
+
+int baorec_create(int device, baorec_ctx** out) {
+  BR_REQUIRE(out != nullptr, "out is NULL");
+  int ndev = 0;
+  BR_CUDA(cudaGetDeviceCount(&ndev));
+  BR_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+  BR_CUDA(cudaSetDevice(device));
+  baorec_ctx* ctx = new baorec_ctx();
+  ctx->device = device;
+  BR_CUDA(cudaMalloc(&ctx->d_oob, sizeof(unsigned long long)));
+  BR_CUDA(cudaMemset(ctx->d_oob, 0, sizeof(unsigned long long)));
+  BR_CUDA(cudaMalloc(&ctx->d_scal, 16 * sizeof(double)));
+  BR_CUDA(cudaMalloc(&ctx->d_minmax, 8 * sizeof(float)));
+  BR_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 8; i++) BR_CUDA(cudaEventCreate(&ctx->ev[i]));
+  *out = ctx;
+  return BAOREC_OK;
+}
+
+int baorec_comm_destroy_internal(baorec_ctx* ctx);
+
+int baorec_destroy(baorec_ctx* ctx) {
+  if (!ctx) return BAOREC_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  baorec_comm_destroy_internal(ctx);
+  destroy_plans(ctx);
+  for (int i = 0; i < BUF_COUNT; i++) release(ctx, (BufId)i);
+  for (int a = 0; a < 3; a++) {
+    if (ctx->d_k[a]) cudaFree(ctx->d_k[a]);
+    if (ctx->d_xv[a]) cudaFree(ctx->d_xv[a]);
+  }
+  if (ctx->d_oob) cudaFree(ctx->d_oob);
+  if (ctx->d_scal) cudaFree(ctx->d_scal);
+  if (ctx->d_minmax) cudaFree(ctx->d_minmax);
+  for (int i = 0; i < 8; i++)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return BAOREC_OK;
+}
+
+int baorec_plan(baorec_ctx* ctx, int nx, int ny, int nz, const float box_size[3], const float box_min[3]) {
+  int s = plan_common(ctx, nx, ny, nz, box_size, box_min);
+  if (s < 0) return s;
+  ctx->dist = false;
+  if (!ctx->have_plans) {
+    size_t w1 = 0, w2 = 0;
+    BR_CUFFT(cufftCreate(&ctx->r2c));
+    BR_CUFFT(cufftCreate(&ctx->c2r));
+    ctx->have_plans = true;
+    BR_CUFFT(cufftSetAutoAllocation(ctx->r2c, 0));
+    BR_CUFFT(cufftSetAutoAllocation(ctx->c2r, 0));
+    BR_CUFFT(cufftMakePlan3d(ctx->r2c, nz, ny, nx, CUFFT_R2C, &w1));
+    BR_CUFFT(cufftMakePlan3d(ctx->c2r, nz, ny, nx, CUFFT_C2R, &w2));
+    ctx->work_bytes = w1 > w2 ? w1 : w2;
+    void* work = nullptr;
+    BR_TRY(need(ctx, BUF_WORK, ctx->work_bytes > 0 ? ctx->work_bytes : 16, &work));
+    BR_CUFFT(cufftSetWorkArea(ctx->r2c, work));
+    BR_CUFFT(cufftSetWorkArea(ctx->c2r, work));
+  }
+  ctx->planned = true;
+  return BAOREC_OK;
+}
+
+int baorec_set_box(baorec_ctx* ctx, const float box_size[3], const float box_min[3]) {
+  BR_REQUIRE(ctx != nullptr, "ctx is NULL");
+  if (!ctx->planned) {
+    set_error("baorec_set_box: call baorec_plan first");
+    return BAOREC_ERR_NOT_PLANNED;
+  }
+  BR_REQUIRE(box_size && box_min, "box_size / box_min are NULL");
+  BR_REQUIRE(box_size[0] > 0 && box_size[1] > 0 && box_size[2] > 0, "box_size must be positive");
+  BR_CUDA(cudaSetDevice(ctx->device));
+  BR_CUDA(cudaDeviceSynchronize());
+  for (int a = 0; a < 3; a++) {
+    ctx->L[a] = box_size[a];
+    ctx->mn[a] = box_min[a];
+  }
+  return upload_tables(ctx);
+}
+
+int64_t baorec_scratch_bytes(const baorec_ctx* ctx) {
+  if (!ctx) return 0;
+  int64_t t = 0;
+  for (int i = 0; i < BUF_COUNT; i++) t += (int64_t)ctx->bufs[i].bytes;
+  return t;
+}
+
+int baorec_launch_counts(const baorec_ctx* ctx, int64_t* kernels, int64_t* fft_execs) {
+  BR_REQUIRE(ctx != nullptr, "ctx is NULL");
+  if (kernels) *kernels = ctx->n_kernels;
+  if (fft_execs) *fft_execs = ctx->n_fft;
+  return BAOREC_OK;
+}
+
+int baorec_last_stage_ms(const baorec_ctx* ctx, float* out, int cap) {
+  if (!ctx || !out) return 0;
+  int n = ctx->n_stage < cap ? ctx->n_stage : cap;
+  for (int i = 0; i < n; i++) out[i] = ctx->stage_ms[i];
+  return n;
+}
+
+float* baorec_result_cache(baorec_ctx* ctx) {
+  if (!ctx || !ctx->cache_valid) return nullptr;
+  return (float*)ctx->bufs[BUF_CACHE].p;
+}
+
+int baorec_host_alloc(void** out, int64_t bytes) {
+  BR_REQUIRE(out != nullptr && bytes > 0, "baorec_host_alloc arguments");
+  BR_CUDA(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+  return BAOREC_OK;
+}
+
+int baorec_host_free(void* p) {
+  if (p) BR_CUDA(cudaFreeHost(p));
+  return BAOREC_OK;
+}
+
+}  // extern "C"

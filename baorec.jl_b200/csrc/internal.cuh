@@ -1,0 +1,202 @@
+// Internal definitions shared by the translation units of libbaorec_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "baorec_b200.h"
+
+namespace baorec {
+
+void set_error(const char* fmt, ...);
+
+#define BR_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      baorec::set_error("%s:%d CUDA error %s in %s", __FILE__, __LINE__,                   \
+                        cudaGetErrorString(_e), #expr);                                    \
+      return BAOREC_ERR_CUDA;                                                              \
+    }                                                                                      \
+  } while (0)
+
+#define BR_CUFFT(expr)                                                                     \
+  do {                                                                                     \
+    cufftResult _e = (expr);                                                               \
+    if (_e != CUFFT_SUCCESS) {                                                             \
+      baorec::set_error("%s:%d cuFFT error %d in %s", __FILE__, __LINE__, (int)_e, #expr); \
+      return BAOREC_ERR_CUFFT;                                                             \
+    }                                                                                      \
+  } while (0)
+
+#define BR_TRY(expr)             \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != BAOREC_OK) return _s; \
+  } while (0)
+
+#define BR_REQUIRE(cond, msg)                         \
+  do {                                                \
+    if (!(cond)) {                                    \
+      baorec::set_error("invalid argument: %s", msg); \
+      return BAOREC_ERR_INVALID;                      \
+    }                                                 \
+  } while (0)
+
+// Count + check a kernel launch.
+#define BR_LAUNCH(ctx, kernel, grid, block, smem, stream, ...)            \
+  do {                                                                    \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);           \
+    (ctx)->n_kernels++;                                                   \
+    BR_CUDA(cudaGetLastError());                                          \
+  } while (0)
+
+enum BufId {
+  BUF_CK0 = 0,  // complex half-mesh (R2C output / k-space work)
+  BUF_CK1,
+  BUF_CK2,
+  BUF_RS,       // real mesh: delta_s / multigrid right-hand side
+  BUF_RX,       // real mesh: C2R output / displacement x
+  BUF_RY,
+  BUF_RZ,
+  BUF_RAN,      // real mesh: randoms density
+  BUF_WORK,     // cuFFT work area (shared by all plans)
+  BUF_CACHE,    // result mesh of the host pipeline (recon.result_cache)
+  BUF_PART,     // particle staging for host pipelines
+  BUF_PART2,    // randoms staging
+  BUF_OUT,      // per-particle outputs for host pipelines
+  BUF_BINKEY,   // particle binning
+  BUF_BINIDX,
+  BUF_BINTMP,
+  BUF_MG,       // multigrid level hierarchy (one slab allocation)
+  BUF_A2A_SEND, // distributed FFT staging
+  BUF_A2A_RECV,
+  BUF_HALO,
+  BUF_COUNT
+};
+
+struct Buf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct MgLevel {
+  int nx = 0, ny = 0, nz = 0;
+  size_t cells = 0;
+  float* f = nullptr;   // right-hand side
+  float* va = nullptr;  // solution ping
+  float* vb = nullptr;  // solution pong / residual scratch
+  float* px = nullptr;  // radial tables x_centre/cell per axis (length nx, ny, nz)
+  float* py = nullptr;
+  float* pz = nullptr;
+  float cell[3];
+};
+
+}  // namespace baorec
+
+struct baorec_ctx {
+  int device = 0;
+  bool planned = false;
+  int nx = 0, ny = 0, nz = 0, xh = 0;
+  size_t M = 0, Mc = 0;
+  float L[3] = {0, 0, 0}, mn[3] = {0, 0, 0};
+  float cell[3] = {0, 0, 0};  // T(L/n), the gather's cell_size (src/mas.jl:221)
+  cufftHandle r2c = 0, c2r = 0;
+  bool have_plans = false;
+  size_t work_bytes = 0;
+  float* d_k[3] = {nullptr, nullptr, nullptr};  // k tables (xh, ny, nz)
+  float* d_xv[3] = {nullptr, nullptr, nullptr}; // cell-centre tables (nx, ny, nz)
+  baorec::Buf bufs[baorec::BUF_COUNT];
+  unsigned long long* d_oob = nullptr;  // out-of-box particle counter
+  double* d_scal = nullptr;             // small device scalars (DC modes, sums)
+  float* d_minmax = nullptr;            // 6 floats for setup_box
+  cudaStream_t own_stream = nullptr;    // used by host pipelines
+  cudaEvent_t ev[8] = {};
+  float stage_ms[8] = {};
+  int n_stage = 0;
+  int64_t n_kernels = 0, n_fft = 0;
+  bool cache_valid = false;
+  // multigrid
+  std::vector<baorec::MgLevel> levels;
+  bool mg_radial_tables = false;
+  // distributed
+  void* comm = nullptr;  // ncclComm_t
+  int rank = 0, nranks = 1;
+  bool dist = false;
+  int nz_loc = 0, z0 = 0, ny_loc = 0, y0 = 0;
+  cufftHandle p2d_r2c = 0, p2d_c2r = 0, p1d = 0;
+  bool have_dist_plans = false;
+};
+
+namespace baorec {
+
+int need(baorec_ctx* ctx, BufId id, size_t bytes, void** out);
+template <class T>
+inline int need_t(baorec_ctx* ctx, BufId id, size_t count, T** out) {
+  void* p = nullptr;
+  int s = need(ctx, id, count * sizeof(T), &p);
+  *out = (T*)p;
+  return s;
+}
+void release(baorec_ctx* ctx, BufId id);
+int check_oob(baorec_ctx* ctx, cudaStream_t st, const char* what);
+int reset_oob(baorec_ctx* ctx, cudaStream_t st);
+
+// FFT wrappers (count executions, bind stream).
+int fft_r2c(baorec_ctx* ctx, const float* in, float2* out, cudaStream_t st);
+int fft_c2r(baorec_ctx* ctx, float2* in, float* out, cudaStream_t st);
+
+// mas.cu
+int scatter(baorec_ctx* ctx, float* rho, float* x, float* y, float* z, const float* w, int64_t n, int wrap,
+            int mas, cudaStream_t st);
+// mode: 0 disp, 1 rsd, 2 sum ; positions: write pos - shift
+int gather3(baorec_ctx* ctx, const float* fx, const float* fy, const float* fz, const float* x, const float* y,
+            const float* z, int64_t n, float* ox, float* oy, float* oz, int mas, int field, float f, int has_los,
+            const float* los, int positions, cudaStream_t st);
+
+// kspace.cu
+int smooth(baorec_ctx* ctx, float* mesh, float R, cudaStream_t st);
+int setup_overdensity(baorec_ctx* ctx, const baorec_params* p, float* mesh, float* x, float* y, float* z,
+                      const float* w, int64_t n, float* rx, float* ry, float* rz, const float* rw, int64_t nr,
+                      int wrap, cudaStream_t st);
+int iterate(baorec_ctx* ctx, float* delta_r, const float* delta_s, int iter, float beta, const float* los,
+            cudaStream_t st);
+int displacement_meshes(baorec_ctx* ctx, const float* mesh, int algorithm, float* px, float* py, float* pz,
+                        cudaStream_t st);
+
+int setup_overdensity_into(baorec_ctx* ctx, const baorec_params* p, float* mesh, float* delta_out, float* x, float* y,
+                           float* z, const float* w, int64_t n, float* rx, float* ry, float* rz, const float* rw,
+                           int64_t nr, int wrap, cudaStream_t st);
+int reconstructed_overdensity(baorec_ctx* ctx, const baorec_params* p, float* mesh, float* x, float* y, float* z,
+                              const float* w, int64_t n, float* rx, float* ry, float* rz, const float* rw, int64_t nr,
+                              cudaStream_t st);
+int setup_box_dev(baorec_ctx* ctx, const float* x, const float* y, const float* z, int64_t n, float pad,
+                  float L_out[3], float mn_out[3], cudaStream_t st);
+// ctx.cu
+int plan_common(baorec_ctx* ctx, int nx, int ny, int nz, const float L[3], const float mn[3]);
+void host_xvec(int n, float L, float mn, std::vector<float>& out);
+
+// multigrid.cu
+int mg_setup_levels(baorec_ctx* ctx);
+int reconstructed_potential(baorec_ctx* ctx, const baorec_params* p, float* phi, float* x, float* y, float* z,
+                            const float* w, int64_t n, float* rx, float* ry, float* rz, const float* rw, int64_t nr,
+                            cudaStream_t st);
+int mg_fmg(baorec_ctx* ctx, const float* f, float* v, float beta, float damping, int n_jacobi, int n_vcycle,
+           const float* los, cudaStream_t st);
+
+#define BR_NEED_PLAN(ctx)                                        \
+  do {                                                           \
+    BR_REQUIRE((ctx) != nullptr, "ctx is NULL");                 \
+    if (!(ctx)->planned) {                                       \
+      baorec::set_error("call baorec_plan before using the context"); \
+      return BAOREC_ERR_NOT_PLANNED;                             \
+    }                                                            \
+    BR_CUDA(cudaSetDevice((ctx)->device));                       \
+  } while (0)
+
+inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+}  // namespace baorec

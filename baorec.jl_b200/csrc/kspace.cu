@@ -1,0 +1,368 @@
+// k-space and real-space mesh passes around the cuFFT R2C/C2R transforms:
+// Gaussian smoothing, overdensity set-up (box and randoms), the RSD iteration
+// (iterate!), and the displacement meshes.  Every pass is a single streaming
+// kernel (one read + one write of each operand); the 1/M normalisation of the
+// inverse transform (`ldiv!`) is folded into the k-space multiply.
+#include "internal.cuh"
+
+namespace baorec {
+
+struct KGeom {
+  const float* kx;
+  const float* ky;
+  const float* kz;
+  int xh, ny, nz;
+};
+
+static KGeom kgeom_of(const baorec_ctx* ctx) {
+  KGeom g;
+  g.kx = ctx->d_k[0];
+  g.ky = ctx->d_k[1];
+  g.kz = ctx->d_k[2];
+  g.xh = ctx->xh;
+  g.ny = ctx->ny;
+  g.nz = ctx->nz;
+  return g;
+}
+
+constexpr int KS_THREADS = 256;
+constexpr int KS_UNROLL = 4;
+
+// One thread handles KS_UNROLL complex values of one z-plane (loads issued back to back,
+// then the stores), blockIdx.y = iz.  Op::apply(idx, v, kx, ky, kz, dc) writes its outputs.
+template <class Op>
+__global__ void __launch_bounds__(KS_THREADS) kspace_kernel(KGeom g, const float2* __restrict__ in, Op op) {
+  const int iz = blockIdx.y;
+  const unsigned plane = (unsigned)g.xh * (unsigned)g.ny;
+  const float kz = __ldg(g.kz + iz);
+  const unsigned base = blockIdx.x * (KS_THREADS * KS_UNROLL) + threadIdx.x;
+  const size_t off = (size_t)iz * plane;
+  float2 v[KS_UNROLL];
+#pragma unroll
+  for (int u = 0; u < KS_UNROLL; u++) {
+    unsigned p = base + u * KS_THREADS;
+    if (p < plane) v[u] = in[off + p];
+  }
+#pragma unroll
+  for (int u = 0; u < KS_UNROLL; u++) {
+    unsigned p = base + u * KS_THREADS;
+    if (p < plane) {
+      unsigned iy = p / (unsigned)g.xh;
+      unsigned ix = p - iy * (unsigned)g.xh;
+      op.apply(off + p, v[u], __ldg(g.kx + ix), __ldg(g.ky + iy), kz, (ix | iy | (unsigned)iz) == 0u);
+    }
+  }
+}
+
+__device__ __forceinline__ float ksq(float kx, float ky, float kz) {
+  // k² = kx^2 + ky^2 + kz^2, left to right in Float32 (src/utils.jl:51)
+  return __fadd_rn(__fadd_rn(__fmul_rn(kx, kx), __fmul_rn(ky, ky)), __fmul_rn(kz, kz));
+}
+
+// exp(-0.5 R² k²) evaluated in Float64 like the reference (src/utils.jl:52, 81).
+__device__ __forceinline__ double gauss64(float R2, float k2) { return exp(-0.5 * (double)R2 * (double)k2); }
+
+struct GaussOp {  // smooth!: field_k *= exp(-0.5 R² k²), then /M
+  float2* out;
+  float R2;
+  double invM;
+  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool) const {
+    double s = gauss64(R2, ksq(kx, ky, kz)) * invM;
+    out[idx] = make_float2((float)((double)v.x * s), (float)((double)v.y * s));
+  }
+};
+
+struct SetupBoxOp {  // smooth + (rho/mean - 1)/bias in k-space: delta_k = rho_k g /(A0 bias), DC -> 0
+  float2* out;
+  float R2;
+  float bias;
+  const double* dc;  // Re A_k[0] = sum(rho)
+  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool is_dc) const {
+    double s = gauss64(R2, ksq(kx, ky, kz)) / (__ldg(dc) * (double)bias);
+    if (is_dc) s = 0.0;
+    out[idx] = make_float2((float)((double)v.x * s), (float)((double)v.y * s));
+  }
+};
+
+struct IterLosOp {  // fixed LOS: sum_a k_a² los_a delta_k / k² (src/iterative.jl:10-14, 53), then /M
+  float2* out;
+  float los[3];
+  float invM;
+  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool) const {
+    float k2 = ksq(kx, ky, kz);
+    float c = __fmul_rn(__fmul_rn(kx, kx), los[0]);
+    c = __fadd_rn(c, __fmul_rn(__fmul_rn(ky, ky), los[1]));
+    c = __fadd_rn(c, __fmul_rn(__fmul_rn(kz, kz), los[2]));
+    float2 o = make_float2(0.f, 0.f);
+    if (k2 > 0.f) {
+      o.x = __fmul_rn(__fmul_rn(__fdiv_rn(v.x, k2), c), invM);
+      o.y = __fmul_rn(__fmul_rn(__fdiv_rn(v.y, k2), c), invM);
+    }
+    out[idx] = o;
+  }
+};
+
+struct IterPairOp {  // radial: k_i k_j delta_k / k² (src/iterative.jl:27), then /M
+  float2* out;
+  int i, j;
+  float invM;
+  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool) const {
+    float k2 = ksq(kx, ky, kz);
+    float ki = i == 0 ? kx : (i == 1 ? ky : kz);
+    float kj = j == 0 ? kx : (j == 1 ? ky : kz);
+    float c = __fmul_rn(ki, kj);
+    float2 o = make_float2(0.f, 0.f);
+    if (k2 > 0.f) {
+      o.x = __fmul_rn(__fmul_rn(c, __fdiv_rn(v.x, k2)), invM);
+      o.y = __fmul_rn(__fmul_rn(c, __fdiv_rn(v.y, k2)), invM);
+    }
+    out[idx] = o;
+  }
+};
+
+template <bool POTENTIAL>
+struct DispOp {  // Psi_a = i k_a delta_k / k² (src/iterative.jl:268) or i k_a phi_k (src/multigrid.jl:767), /M
+  float2* o0;
+  float2* o1;
+  float2* o2;
+  float invM;
+  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool) const {
+    float s;
+    if (POTENTIAL) {
+      s = invM;
+    } else {
+      float k2 = ksq(kx, ky, kz);
+      s = k2 > 0.f ? __fdiv_rn(invM, k2) : 0.f;
+    }
+    float re = __fmul_rn(-v.y, s), im = __fmul_rn(v.x, s);  // i * v * s
+    o0[idx] = make_float2(__fmul_rn(re, kx), __fmul_rn(im, kx));
+    o1[idx] = make_float2(__fmul_rn(re, ky), __fmul_rn(im, ky));
+    o2[idx] = make_float2(__fmul_rn(re, kz), __fmul_rn(im, kz));
+  }
+};
+
+__global__ void stash_dc_kernel(const float2* __restrict__ ck, double* scal, int slot) {
+  scal[slot] = (double)ck[0].x;
+}
+
+template <class Op>
+static int run_kspace(baorec_ctx* ctx, const float2* in, Op op, cudaStream_t st) {
+  size_t plane = (size_t)ctx->xh * ctx->ny;
+  dim3 grid(cdiv(plane, KS_THREADS * KS_UNROLL), ctx->nz);
+  BR_LAUNCH(ctx, kspace_kernel<Op>, grid, KS_THREADS, 0, st, kgeom_of(ctx), in, op);
+  return BAOREC_OK;
+}
+
+// ---- real-space passes -------------------------------------------------------------------------
+// delta_r = src - fac * X    (src/iterative.jl:59), 4 cells per thread
+__global__ void __launch_bounds__(256)
+axpy4_kernel(float4* __restrict__ out, const float4* __restrict__ src, const float4* __restrict__ X, float fac,
+             size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 s = src[i], x = X[i];
+    out[i] = make_float4(__fsub_rn(s.x, __fmul_rn(fac, x.x)), __fsub_rn(s.y, __fmul_rn(fac, x.y)),
+                         __fsub_rn(s.z, __fmul_rn(fac, x.z)), __fsub_rn(s.w, __fmul_rn(fac, x.w)));
+  }
+}
+__global__ void axpy1_kernel(float* __restrict__ out, const float* __restrict__ src, const float* __restrict__ X,
+                             float fac, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = __fsub_rn(src[i], __fmul_rn(fac, X[i]));
+}
+
+// radial update (src/iterative.jl:32-35): delta_r = x²>0 ? src - fac X x_i x_j / x² : 0
+__global__ void __launch_bounds__(256)
+radial_update_kernel(float* out, const float* src, const float* __restrict__ X,
+                     const float* __restrict__ xv0, const float* __restrict__ xv1, const float* __restrict__ xv2,
+                     int nx, int ny, int ci, int cj, float fac) {
+  const int iz = blockIdx.y;
+  const unsigned plane = (unsigned)nx * (unsigned)ny;
+  const float zc = __ldg(xv2 + iz);
+  const size_t off = (size_t)iz * plane;
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < plane; p += gridDim.x * blockDim.x) {
+    unsigned iy = p / (unsigned)nx, ix = p - iy * (unsigned)nx;
+    float xc = __ldg(xv0 + ix), yc = __ldg(xv1 + iy);
+    float x2 = __fadd_rn(__fadd_rn(__fmul_rn(xc, xc), __fmul_rn(yc, yc)), __fmul_rn(zc, zc));
+    float a = ci == 0 ? xc : (ci == 1 ? yc : zc);
+    float b = cj == 0 ? xc : (cj == 1 ? yc : zc);
+    float s = src[off + p], x = X[off + p];
+    float t = __fdiv_rn(__fmul_rn(__fmul_rn(__fmul_rn(fac, x), a), b), x2);
+    out[off + p] = x2 > 0.f ? __fsub_rn(s, t) : 0.f;
+  }
+}
+
+// randoms combine (src/recon.jl:78-85)
+__global__ void __launch_bounds__(256)
+randoms_combine_kernel(float* __restrict__ out, const float* __restrict__ dat, const float* __restrict__ ran,
+                       const double* __restrict__ scal, float bias, double ran_min, double n_ran, size_t n) {
+  const float sd = (float)scal[0], sr = (float)scal[1];
+  const float alpha = __fdiv_rn(sd, sr);
+  const float thr = (float)(ran_min * (double)sr / n_ran);
+  const float ba = __fmul_rn(bias, alpha);
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float d = dat[i], r = ran[i];
+    float num = __fsub_rn(d, __fmul_rn(alpha, r));
+    out[i] = r > thr ? __fdiv_rn(num, __fmul_rn(ba, r)) : 0.f;
+  }
+}
+
+static unsigned stream_grid(size_t work_items, int threads) {
+  size_t g = (work_items + threads - 1) / threads;
+  size_t cap = (size_t)148 * 32;
+  return (unsigned)(g < cap ? (g ? g : 1) : cap);
+}
+
+static int axpy(baorec_ctx* ctx, float* out, const float* src, const float* X, float fac, cudaStream_t st) {
+  size_t n = ctx->M;
+  bool al = (((uintptr_t)out | (uintptr_t)src | (uintptr_t)X) & 15) == 0;
+  if (n % 4 == 0 && al) {
+    BR_LAUNCH(ctx, axpy4_kernel, stream_grid(n / 4, 256), 256, 0, st, (float4*)out, (const float4*)src,
+              (const float4*)X, fac, n / 4);
+  } else {
+    BR_LAUNCH(ctx, axpy1_kernel, stream_grid(n, 256), 256, 0, st, out, src, X, fac, n);
+  }
+  return BAOREC_OK;
+}
+
+// ---- drivers -------------------------------------------------------------------------------------
+int smooth(baorec_ctx* ctx, float* mesh, float R, cudaStream_t st) {
+  float2* ck0;
+  BR_TRY(need_t(ctx, BUF_CK0, ctx->Mc, &ck0));
+  BR_TRY(fft_r2c(ctx, mesh, ck0, st));
+  GaussOp op{ck0, R * R, 1.0 / (double)ctx->M};
+  BR_TRY(run_kspace(ctx, ck0, op, st));
+  BR_TRY(fft_c2r(ctx, ck0, mesh, st));
+  return BAOREC_OK;
+}
+
+// Scatters into `mesh` (zero-filled by the caller) and leaves delta in `delta_out`
+// (which may be `mesh` itself).
+int setup_overdensity_into(baorec_ctx* ctx, const baorec_params* p, float* mesh, float* delta_out, float* x, float* y,
+                           float* z, const float* w, int64_t n, float* rx, float* ry, float* rz, const float* rw,
+                           int64_t nr, int wrap, cudaStream_t st) {
+  float2* ck0;
+  BR_TRY(need_t(ctx, BUF_CK0, ctx->Mc, &ck0));
+  const float R2 = p->smoothing_radius * p->smoothing_radius;
+  BR_TRY(reset_oob(ctx, st));
+  if (nr == 0) {
+    BR_TRY(scatter(ctx, mesh, x, y, z, w, n, wrap, p->mas, st));
+    BR_TRY(fft_r2c(ctx, mesh, ck0, st));
+    BR_LAUNCH(ctx, stash_dc_kernel, 1, 1, 0, st, ck0, ctx->d_scal, 0);
+    SetupBoxOp op{ck0, R2, p->bias, ctx->d_scal};
+    BR_TRY(run_kspace(ctx, ck0, op, st));
+    BR_TRY(fft_c2r(ctx, ck0, delta_out, st));
+  } else {
+    float* ran;
+    BR_TRY(need_t(ctx, BUF_RAN, ctx->M, &ran));
+    BR_CUDA(cudaMemsetAsync(ran, 0, ctx->M * sizeof(float), st));
+    BR_TRY(scatter(ctx, mesh, x, y, z, w, n, 0, p->mas, st));
+    BR_TRY(scatter(ctx, ran, rx, ry, rz, rw, nr, 0, p->mas, st));
+    GaussOp op{ck0, R2, 1.0 / (double)ctx->M};
+    BR_TRY(fft_r2c(ctx, mesh, ck0, st));
+    BR_LAUNCH(ctx, stash_dc_kernel, 1, 1, 0, st, ck0, ctx->d_scal, 0);
+    BR_TRY(run_kspace(ctx, ck0, op, st));
+    BR_TRY(fft_c2r(ctx, ck0, mesh, st));
+    BR_TRY(fft_r2c(ctx, ran, ck0, st));
+    BR_LAUNCH(ctx, stash_dc_kernel, 1, 1, 0, st, ck0, ctx->d_scal, 1);
+    BR_TRY(run_kspace(ctx, ck0, op, st));
+    BR_TRY(fft_c2r(ctx, ck0, ran, st));
+    BR_LAUNCH(ctx, randoms_combine_kernel, stream_grid(ctx->M, 256), 256, 0, st, delta_out, mesh, ran, ctx->d_scal,
+              p->bias, (double)p->ran_min, (double)nr, ctx->M);
+  }
+  return check_oob(ctx, st, "setup_overdensity");
+}
+
+int setup_overdensity(baorec_ctx* ctx, const baorec_params* p, float* mesh, float* x, float* y, float* z,
+                      const float* w, int64_t n, float* rx, float* ry, float* rz, const float* rw, int64_t nr, int wrap,
+                      cudaStream_t st) {
+  return setup_overdensity_into(ctx, p, mesh, mesh, x, y, z, w, n, rx, ry, rz, rw, nr, wrap, st);
+}
+
+// One RSD iteration: delta_k from `fft_src` (the current delta_r), result into `delta_r`.
+// On iteration 1 the reference has delta_r == delta_s, so the driver passes fft_src = delta_s
+// and never materialises `copy(δ_r)` (src/recon.jl:101).
+static int iterate_impl(baorec_ctx* ctx, const float* fft_src, float* delta_r, const float* delta_s, int iter,
+                        float beta, const float* los, cudaStream_t st) {
+  float2* ck0;
+  float* X;
+  BR_TRY(need_t(ctx, BUF_CK0, ctx->Mc, &ck0));
+  BR_TRY(need_t(ctx, BUF_RX, ctx->M, &X));
+  const float invM = (float)(1.0 / (double)ctx->M);
+  BR_TRY(fft_r2c(ctx, fft_src, ck0, st));
+  if (los) {
+    float fac = beta;
+    if (iter == 1) fac = fac / (1.0f + beta);
+    IterLosOp op{ck0, {los[0], los[1], los[2]}, invM};
+    BR_TRY(run_kspace(ctx, ck0, op, st));
+    BR_TRY(fft_c2r(ctx, ck0, X, st));
+    BR_TRY(axpy(ctx, delta_r, delta_s, X, fac, st));
+  } else {
+    float2* ck1;
+    BR_TRY(need_t(ctx, BUF_CK1, ctx->Mc, &ck1));
+    bool first = true;
+    for (int i = 0; i < 3; i++)
+      for (int j = i; j < 3; j++) {
+        float fac = (float)((1.0 + (i != j ? 1.0 : 0.0)) * (double)beta);
+        if (iter == 1) fac = fac / (1.0f + beta);
+        IterPairOp op{ck1, i, j, invM};
+        BR_TRY(run_kspace(ctx, ck0, op, st));
+        BR_TRY(fft_c2r(ctx, ck1, X, st));
+        dim3 grid(stream_grid((size_t)ctx->nx * ctx->ny, 256) > 64 ? 64 : stream_grid((size_t)ctx->nx * ctx->ny, 256),
+                  ctx->nz);
+        BR_LAUNCH(ctx, radial_update_kernel, grid, 256, 0, st, delta_r, first ? delta_s : delta_r, X, ctx->d_xv[0],
+                  ctx->d_xv[1], ctx->d_xv[2], ctx->nx, ctx->ny, i, j, fac);
+        first = false;
+      }
+  }
+  return BAOREC_OK;
+}
+
+int iterate(baorec_ctx* ctx, float* delta_r, const float* delta_s, int iter, float beta, const float* los,
+            cudaStream_t st) {
+  return iterate_impl(ctx, delta_r, delta_r, delta_s, iter, beta, los, st);
+}
+
+int displacement_meshes(baorec_ctx* ctx, const float* mesh, int algorithm, float* px, float* py, float* pz,
+                        cudaStream_t st) {
+  float2 *ck0, *ck1, *ck2;
+  BR_TRY(need_t(ctx, BUF_CK0, ctx->Mc, &ck0));
+  BR_TRY(need_t(ctx, BUF_CK1, ctx->Mc, &ck1));
+  BR_TRY(need_t(ctx, BUF_CK2, ctx->Mc, &ck2));
+  const float invM = (float)(1.0 / (double)ctx->M);
+  BR_TRY(fft_r2c(ctx, mesh, ck0, st));
+  if (algorithm == BAOREC_MULTIGRID) {
+    DispOp<true> op{ck0, ck1, ck2, invM};
+    BR_TRY(run_kspace(ctx, ck0, op, st));
+  } else {
+    DispOp<false> op{ck0, ck1, ck2, invM};
+    BR_TRY(run_kspace(ctx, ck0, op, st));
+  }
+  BR_TRY(fft_c2r(ctx, ck0, px, st));
+  BR_TRY(fft_c2r(ctx, ck1, py, st));
+  BR_TRY(fft_c2r(ctx, ck2, pz, st));
+  return BAOREC_OK;
+}
+
+int reconstructed_overdensity(baorec_ctx* ctx, const baorec_params* p, float* mesh, float* x, float* y, float* z,
+                              const float* w, int64_t n, float* rx, float* ry, float* rz, const float* rw, int64_t nr,
+                              cudaStream_t st) {
+  float* ds;
+  BR_TRY(need_t(ctx, BUF_RS, ctx->M, &ds));
+  // delta_s lands in RS (no `copy(δ_r)`, src/recon.jl:101); the first iteration reads it directly.
+  BR_TRY(setup_overdensity_into(ctx, p, mesh, ds, x, y, z, w, n, rx, ry, rz, rw, nr, 1, st));
+  if (p->n_iter <= 0) {
+    BR_CUDA(cudaMemcpyAsync(mesh, ds, ctx->M * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return BAOREC_OK;
+  }
+  const float* los = p->has_los ? p->los : nullptr;
+  for (int it = 1; it <= p->n_iter; it++)
+    BR_TRY(iterate_impl(ctx, it == 1 ? ds : mesh, mesh, ds, it, p->beta, los, st));
+  return BAOREC_OK;
+}
+
+}  // namespace baorec

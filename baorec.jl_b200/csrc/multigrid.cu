@@ -1,0 +1,516 @@
+// Finite-difference multigrid solver (src/multigrid.jl): damped-Jacobi smoother on the
+// 19-point anisotropic operator, residual, full-weighting restriction, trilinear
+// prolongation, V-cycle and full-multigrid drivers.
+//
+// The operator solved is  -lap(phi) - beta div((grad(phi).r) r) = f  with r the line of
+// sight (constant, or radial from the origin), second-order central differences, periodic.
+//
+// Kernel layout: every thread owns MG_VX consecutive x cells of one row and marches along
+// z, keeping the three z-planes of its 3x(MG_VX+2) neighbourhood in registers, so each
+// value of v is fetched once per thread (through L1) per z step and HBM sees one read of
+// v, one of f and one write per cell.  Jacobi fuses the damping
+// v <- (1-w) v + w jac and ping-pongs between two buffers (the reference allocates `jac`
+// and runs a second broadcast pass per sweep: src/multigrid.jl:195,207).
+#include "internal.cuh"
+
+namespace baorec {
+
+struct MgGeom {
+  int nx, ny, nz;
+  float cell[3];
+  float c2[3];   // cell^2
+  float ic2[3];  // 1/cell^2
+  double start[3];  // box_min + 0.5 cell (Float64, as x_vec builds its range)
+  float beta;
+  int radial;
+  float lp[3];  // los / cell
+};
+
+static MgGeom mg_geom(const baorec_ctx* ctx, int nx, int ny, int nz, float beta, const float* los) {
+  MgGeom g;
+  g.nx = nx;
+  g.ny = ny;
+  g.nz = nz;
+  int n[3] = {nx, ny, nz};
+  for (int a = 0; a < 3; a++) {
+    g.cell[a] = ctx->L[a] / (float)n[a];  // map(T, box_size ./ size(v))  src/multigrid.jl:17
+    g.c2[a] = g.cell[a] * g.cell[a];
+    g.ic2[a] = 1.0f / g.c2[a];
+    g.start[a] = (double)ctx->mn[a] + 0.5 * (double)g.cell[a];
+    g.lp[a] = los ? los[a] / g.cell[a] : 0.f;
+  }
+  g.beta = beta;
+  g.radial = los ? 0 : 1;
+  return g;
+}
+
+// p = x_centre / cell with x_centre = T(start + i*cell) (src/utils.jl:24, src/multigrid.jl:55-57)
+__device__ __forceinline__ float mg_p(const MgGeom& g, int a, int i) {
+  float xc = (float)__dadd_rn(g.start[a], __dmul_rn((double)i, (double)g.cell[a]));
+  return __fdiv_rn(xc, g.cell[a]);
+}
+
+constexpr int MG_JACOBI = 0;
+constexpr int MG_RESIDUAL = 1;
+
+// ---- generic kernel: one thread per cell (any size; used for small levels) ---------------------
+template <int MODE>
+__global__ void __launch_bounds__(256)
+mg_stencil_generic(float* __restrict__ out, const float* __restrict__ v, const float* __restrict__ f, MgGeom g,
+                   float omega) {
+  size_t cells = (size_t)g.nx * g.ny * g.nz;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cells) return;
+  int ix = (int)(idx % g.nx);
+  size_t t = idx / g.nx;
+  int iy = (int)(t % g.ny);
+  int iz = (int)(t / g.ny);
+  int xp = ix + 1 == g.nx ? 0 : ix + 1, xm = ix == 0 ? g.nx - 1 : ix - 1;
+  int yp = iy + 1 == g.ny ? 0 : iy + 1, ym = iy == 0 ? g.ny - 1 : iy - 1;
+  int zp = iz + 1 == g.nz ? 0 : iz + 1, zm = iz == 0 ? g.nz - 1 : iz - 1;
+  auto V = [&](int x, int y, int z) { return __ldg(v + ((size_t)z * g.ny + y) * g.nx + x); };
+  float px, py, pz;
+  if (g.radial) {
+    px = mg_p(g, 0, ix);
+    py = mg_p(g, 1, iy);
+    pz = mg_p(g, 2, iz);
+  } else {
+    px = g.lp[0];
+    py = g.lp[1];
+    pz = g.lp[2];
+  }
+  float gg = g.beta / (g.c2[0] * px * px + g.c2[1] * py * py + g.c2[2] * pz * pz);
+  float gx = g.ic2[0] + gg * px * px, gy = g.ic2[1] + gg * py * py, gz = g.ic2[2] + gg * pz * pz;
+  float vxp = V(xp, iy, iz), vxm = V(xm, iy, iz), vyp = V(ix, yp, iz), vym = V(ix, ym, iz);
+  float vzp = V(ix, iy, zp), vzm = V(ix, iy, zm);
+  float off = gx * (vxp + vxm) + gy * (vyp + vym) + gz * (vzp + vzm) +
+              gg / 2 *
+                  (px * py * (V(xp, yp, iz) + V(xm, ym, iz) - V(xm, yp, iz) - V(xp, ym, iz)) +
+                   px * pz * (V(xp, iy, zp) + V(xm, iy, zm) - V(xm, iy, zp) - V(xp, iy, zm)) +
+                   py * pz * (V(ix, yp, zp) + V(ix, ym, zm) - V(ix, ym, zp) - V(ix, yp, zm)));
+  if (g.radial) off += gg * (px * (vxp - vxm) + py * (vyp - vym) + pz * (vzp - vzm));
+  float diag = 2 * (gx + gy + gz);
+  float vc = V(ix, iy, iz);
+  if (MODE == MG_JACOBI) {
+    float jac = (f[idx] + off) / diag;
+    out[idx] = (1 - omega) * vc + omega * jac;
+  } else {
+    out[idx] = f[idx] - (diag * vc - off);
+  }
+}
+
+// ---- fast kernel: MG_VX cells per thread along x, register z-march ------------------------------
+constexpr int MG_VX = 4;
+
+struct Row6 {
+  float m, a, b, c, d, p;  // x-1, x..x+3, x+4
+};
+
+__device__ __forceinline__ Row6 load_row(const float* __restrict__ row, int x0, int xm, int xp) {
+  Row6 r;
+  float4 q = __ldg(reinterpret_cast<const float4*>(row + x0));
+  r.m = __ldg(row + xm);
+  r.a = q.x;
+  r.b = q.y;
+  r.c = q.z;
+  r.d = q.w;
+  r.p = __ldg(row + xp);
+  return r;
+}
+
+// grid: x = row-chunks, y = iy (TY rows per block via threadIdx.y), z = z-chunks.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+mg_stencil_march(float* __restrict__ out, const float* __restrict__ v, const float* __restrict__ f, MgGeom g,
+                 float omega, int zchunk) {
+  const int nx = g.nx, ny = g.ny, nz = g.nz;
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * MG_VX;
+  const int iy = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x0 >= nx || iy >= ny) return;
+  const int zbeg = blockIdx.z * zchunk;
+  const int zend = min(nz, zbeg + zchunk);
+  const int xm = x0 == 0 ? nx - 1 : x0 - 1;
+  const int xp = x0 + MG_VX >= nx ? 0 : x0 + MG_VX;
+  const int ym = iy == 0 ? ny - 1 : iy - 1, yp = iy + 1 == ny ? 0 : iy + 1;
+  const size_t plane = (size_t)nx * ny;
+  const size_t rm = (size_t)ym * nx, r0 = (size_t)iy * nx, rp = (size_t)yp * nx;
+
+  float px[MG_VX], py, pz = 0.f;
+  if (g.radial) {
+#pragma unroll
+    for (int k = 0; k < MG_VX; k++) px[k] = mg_p(g, 0, x0 + k);
+    py = mg_p(g, 1, iy);
+  } else {
+#pragma unroll
+    for (int k = 0; k < MG_VX; k++) px[k] = g.lp[0];
+    py = g.lp[1];
+    pz = g.lp[2];
+  }
+
+  // planes: A = z-1, B = z, C = z+1; each holds rows y-1, y, y+1
+  Row6 Am, A0, Ap, Bm, B0, Bp, Cm, C0, Cp;
+  {
+    int za = zbeg == 0 ? nz - 1 : zbeg - 1;
+    const float* pa = v + (size_t)za * plane;
+    Am = load_row(pa + rm, x0, xm, xp);
+    A0 = load_row(pa + r0, x0, xm, xp);
+    Ap = load_row(pa + rp, x0, xm, xp);
+    const float* pb = v + (size_t)zbeg * plane;
+    Bm = load_row(pb + rm, x0, xm, xp);
+    B0 = load_row(pb + r0, x0, xm, xp);
+    Bp = load_row(pb + rp, x0, xm, xp);
+  }
+  for (int iz = zbeg; iz < zend; iz++) {
+    int zc = iz + 1 == nz ? 0 : iz + 1;
+    const float* pc = v + (size_t)zc * plane;
+    Cm = load_row(pc + rm, x0, xm, xp);
+    C0 = load_row(pc + r0, x0, xm, xp);
+    Cp = load_row(pc + rp, x0, xm, xp);
+    const size_t o = (size_t)iz * plane + r0 + x0;
+    float4 fv = __ldg(reinterpret_cast<const float4*>(f + o));
+    if (g.radial) pz = mg_p(g, 2, iz);
+
+    const float bm[6] = {Bm.m, Bm.a, Bm.b, Bm.c, Bm.d, Bm.p};
+    const float b0[6] = {B0.m, B0.a, B0.b, B0.c, B0.d, B0.p};
+    const float bp[6] = {Bp.m, Bp.a, Bp.b, Bp.c, Bp.d, Bp.p};
+    const float a0[6] = {A0.m, A0.a, A0.b, A0.c, A0.d, A0.p};
+    const float c0[6] = {C0.m, C0.a, C0.b, C0.c, C0.d, C0.p};
+    const float am[4] = {Am.a, Am.b, Am.c, Am.d}, ap[4] = {Ap.a, Ap.b, Ap.c, Ap.d};
+    const float cm[4] = {Cm.a, Cm.b, Cm.c, Cm.d}, cp[4] = {Cp.a, Cp.b, Cp.c, Cp.d};
+    const float ff[4] = {fv.x, fv.y, fv.z, fv.w};
+    float res[4];
+#pragma unroll
+    for (int k = 0; k < MG_VX; k++) {
+      float pxk = px[k];
+      float gg = g.beta / (g.c2[0] * pxk * pxk + g.c2[1] * py * py + g.c2[2] * pz * pz);
+      float gx = g.ic2[0] + gg * pxk * pxk, gy = g.ic2[1] + gg * py * py, gz = g.ic2[2] + gg * pz * pz;
+      float vxp = b0[k + 2], vxm = b0[k], vyp = bp[k + 1], vym = bm[k + 1], vzp = c0[k + 1], vzm = a0[k + 1];
+      float off = gx * (vxp + vxm) + gy * (vyp + vym) + gz * (vzp + vzm) +
+                  gg / 2 *
+                      (pxk * py * (bp[k + 2] + bm[k] - bp[k] - bm[k + 2]) +
+                       pxk * pz * (c0[k + 2] + a0[k] - c0[k] - a0[k + 2]) +
+                       py * pz * (cp[k] + am[k] - cm[k] - ap[k]));
+      if (g.radial) off += gg * (pxk * (vxp - vxm) + py * (vyp - vym) + pz * (vzp - vzm));
+      float diag = 2 * (gx + gy + gz);
+      float vc = b0[k + 1];
+      if (MODE == MG_JACOBI) res[k] = (1 - omega) * vc + omega * ((ff[k] + off) / diag);
+      else res[k] = ff[k] - (diag * vc - off);
+    }
+    *reinterpret_cast<float4*>(out + o) = make_float4(res[0], res[1], res[2], res[3]);
+    Am = Bm; A0 = B0; Ap = Bp;
+    Bm = Cm; B0 = C0; Bp = Cp;
+  }
+}
+
+// ---- restriction (reduce!, src/multigrid.jl:520-584): coarse c <- fine 2c+1, weights 8/4/2/1 /64
+__global__ void __launch_bounds__(256)
+mg_restrict_kernel(float* __restrict__ c, const float* __restrict__ fine, int nx, int ny, int nz) {
+  int cx = nx / 2, cy = ny / 2, cz = nz / 2;
+  size_t cells = (size_t)cx * cy * cz;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cells) return;
+  int ix = (int)(idx % cx);
+  size_t t = idx / cx;
+  int iy = (int)(t % cy), iz = (int)(t / cy);
+  int X[3], Y[3], Z[3];
+  int fx = 2 * ix + 1, fy = 2 * iy + 1, fz = 2 * iz + 1;
+  X[0] = fx - 1; X[1] = fx; X[2] = fx + 1 == nx ? 0 : fx + 1;
+  Y[0] = fy - 1; Y[1] = fy; Y[2] = fy + 1 == ny ? 0 : fy + 1;
+  Z[0] = fz - 1; Z[1] = fz; Z[2] = fz + 1 == nz ? 0 : fz + 1;
+  float s8 = 0.f, s4 = 0.f, s2 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int c3 = 0; c3 < 3; c3++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+      const float* row = fine + ((size_t)Z[c3] * ny + Y[b]) * nx;
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        float val = __ldg(row + X[a]);
+        int k = (a != 1) + (b != 1) + (c3 != 1);
+        if (k == 0) s8 += val;
+        else if (k == 1) s4 += val;
+        else if (k == 2) s2 += val;
+        else s1 += val;
+      }
+    }
+  c[idx] = (8 * s8 + 4 * s4 + 2 * s2 + s1) / 64.0f;
+}
+
+// ---- prolongation (prolong!, src/multigrid.jl:398-453), one thread per FINE cell -----------------
+// fine odd index 2c+1 <- coarse c ; fine even index e <- mean(coarse e/2-1 (wrapped), coarse e/2).
+// ADD: out = out + P(coarse) (the `v += v1h` of vcycle!, src/multigrid.jl:680), else out = P(coarse).
+template <bool ADD>
+__global__ void __launch_bounds__(256)
+mg_prolong_kernel(float* __restrict__ fine, const float* __restrict__ c, int nx, int ny, int nz) {
+  int cx = nx / 2, cy = ny / 2, cz = nz / 2;
+  size_t cells = (size_t)nx * ny * nz;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cells) return;
+  int ix = (int)(idx % nx);
+  size_t t = idx / nx;
+  int iy = (int)(t % ny), iz = (int)(t / ny);
+  int xa, xb, ya, yb, za, zb;
+  if (ix & 1) { xa = xb = (ix - 1) >> 1; } else { xb = ix >> 1; xa = xb == 0 ? cx - 1 : xb - 1; if (xb >= cx) xb = 0; }
+  if (iy & 1) { ya = yb = (iy - 1) >> 1; } else { yb = iy >> 1; ya = yb == 0 ? cy - 1 : yb - 1; if (yb >= cy) yb = 0; }
+  if (iz & 1) { za = zb = (iz - 1) >> 1; } else { zb = iz >> 1; za = zb == 0 ? cz - 1 : zb - 1; if (zb >= cz) zb = 0; }
+  auto C = [&](int x, int y, int z) { return __ldg(c + ((size_t)z * cy + y) * cx + x); };
+  float s = C(xa, ya, za) + C(xb, ya, za) + C(xa, yb, za) + C(xb, yb, za) + C(xa, ya, zb) + C(xb, ya, zb) +
+            C(xa, yb, zb) + C(xb, yb, zb);
+  float val = s * 0.125f;
+  fine[idx] = ADD ? fine[idx] + val : val;
+}
+
+// ---- launch helpers -------------------------------------------------------------------------------
+static bool march_ok(int nx, int ny, int nz, const void* a, const void* b, const void* c) {
+  return nx % MG_VX == 0 && nx >= 32 && nz >= 8 && ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0);
+}
+
+template <int MODE>
+static int launch_stencil(baorec_ctx* ctx, float* out, const float* v, const float* f, const MgGeom& g, float omega,
+                          cudaStream_t st) {
+  if (march_ok(g.nx, g.ny, g.nz, out, v, f)) {
+    int tx = g.nx / MG_VX;
+    if (tx > 64) tx = 64;
+    int ty = 256 / tx;
+    if (ty > g.ny) ty = g.ny;
+    // z chunk: enough blocks to fill 148 SMs several times over, but at least 8 planes per march
+    int zchunk = 32;
+    size_t blocks_xy = (size_t)cdiv(g.nx / MG_VX, tx) * cdiv(g.ny, ty);
+    while (zchunk > 8 && blocks_xy * cdiv(g.nz, zchunk) < 148 * 8) zchunk /= 2;
+    dim3 grid(cdiv(g.nx / MG_VX, tx), cdiv(g.ny, ty), cdiv(g.nz, zchunk));
+    dim3 block(tx, ty);
+    BR_LAUNCH(ctx, mg_stencil_march<MODE>, grid, block, 0, st, out, v, f, g, omega, zchunk);
+  } else {
+    size_t cells = (size_t)g.nx * g.ny * g.nz;
+    BR_LAUNCH(ctx, mg_stencil_generic<MODE>, cdiv(cells, 256), 256, 0, st, out, v, f, g, omega);
+  }
+  return BAOREC_OK;
+}
+
+// niter damped-Jacobi sweeps ping-ponging a <-> b; *result points at the buffer holding the result.
+static int jacobi_pp(baorec_ctx* ctx, float* a, float* b, const float* f, const MgGeom& g, float omega, int niter,
+                     float** result, cudaStream_t st) {
+  float* cur = a;
+  float* alt = b;
+  for (int i = 0; i < niter; i++) {
+    BR_TRY(launch_stencil<MG_JACOBI>(ctx, alt, cur, f, g, omega, st));
+    float* t = cur;
+    cur = alt;
+    alt = t;
+  }
+  *result = cur;
+  return BAOREC_OK;
+}
+
+static int restrict_to(baorec_ctx* ctx, float* coarse, const float* fine, int nx, int ny, int nz, cudaStream_t st) {
+  size_t cells = (size_t)(nx / 2) * (ny / 2) * (nz / 2);
+  BR_LAUNCH(ctx, mg_restrict_kernel, cdiv(cells, 256), 256, 0, st, coarse, fine, nx, ny, nz);
+  return BAOREC_OK;
+}
+
+static int prolong_to(baorec_ctx* ctx, float* fine, const float* coarse, int nx, int ny, int nz, bool add,
+                      cudaStream_t st) {
+  size_t cells = (size_t)nx * ny * nz;
+  if (add) BR_LAUNCH(ctx, mg_prolong_kernel<true>, cdiv(cells, 256), 256, 0, st, fine, coarse, nx, ny, nz);
+  else BR_LAUNCH(ctx, mg_prolong_kernel<false>, cdiv(cells, 256), 256, 0, st, fine, coarse, nx, ny, nz);
+  return BAOREC_OK;
+}
+
+static bool can_recurse(int nx, int ny, int nz) {
+  return nx > 4 && ny > 4 && nz > 4 && nx % 2 == 0 && ny % 2 == 0 && nz % 2 == 0;
+}
+
+int mg_setup_levels(baorec_ctx* ctx) {
+  if (!ctx->levels.empty()) return BAOREC_OK;
+  std::vector<MgLevel> lv;
+  int nx = ctx->nx, ny = ctx->ny, nz = ctx->nz;
+  for (;;) {
+    MgLevel l;
+    l.nx = nx;
+    l.ny = ny;
+    l.nz = nz;
+    l.cells = (size_t)nx * ny * nz;
+    lv.push_back(l);
+    if (!can_recurse(nx, ny, nz)) break;
+    nx /= 2;
+    ny /= 2;
+    nz /= 2;
+  }
+  // one slab: level 0 needs vb only (f and va are the caller's); deeper levels need f, va, vb
+  size_t total = 0;
+  auto pad = [](size_t c) { return (c + 63) & ~(size_t)63; };
+  for (size_t i = 0; i < lv.size(); i++) total += pad(lv[i].cells) * (i == 0 ? 1 : 3);
+  float* base;
+  BR_TRY(need_t(ctx, BUF_MG, total, &base));
+  size_t off = 0;
+  for (size_t i = 0; i < lv.size(); i++) {
+    if (i > 0) {
+      lv[i].f = base + off;
+      off += pad(lv[i].cells);
+      lv[i].va = base + off;
+      off += pad(lv[i].cells);
+    }
+    lv[i].vb = base + off;
+    off += pad(lv[i].cells);
+  }
+  ctx->levels = lv;
+  return BAOREC_OK;
+}
+
+struct MgRun {
+  baorec_ctx* ctx;
+  float beta, omega;
+  int nj;
+  const float* los;
+  cudaStream_t st;
+  std::vector<float*> cur;       // buffer currently holding v at each level
+  std::vector<const float*> f;   // right-hand side at each level
+};
+
+static float* other_buf(const MgLevel& l, float* cur) { return cur == l.va ? l.vb : l.va; }
+
+// vcycle! (src/multigrid.jl:654-687) at level l, operating on run.cur[l]
+static int vcycle_level(MgRun& r, size_t l) {
+  baorec_ctx* ctx = r.ctx;
+  MgLevel& L = ctx->levels[l];
+  MgGeom g = mg_geom(ctx, L.nx, L.ny, L.nz, r.beta, r.los);
+  float* res;
+  BR_TRY(jacobi_pp(ctx, r.cur[l], other_buf(L, r.cur[l]), r.f[l], g, r.omega, r.nj, &res, r.st));
+  r.cur[l] = res;
+  if (l + 1 < ctx->levels.size()) {
+    MgLevel& C = ctx->levels[l + 1];
+    float* rbuf = other_buf(L, r.cur[l]);
+    BR_TRY(launch_stencil<MG_RESIDUAL>(ctx, rbuf, r.cur[l], r.f[l], g, 0.f, r.st));
+    BR_TRY(restrict_to(ctx, C.f, rbuf, L.nx, L.ny, L.nz, r.st));
+    BR_CUDA(cudaMemsetAsync(C.va, 0, C.cells * sizeof(float), r.st));
+    r.cur[l + 1] = C.va;
+    r.f[l + 1] = C.f;
+    BR_TRY(vcycle_level(r, l + 1));
+    BR_TRY(prolong_to(ctx, r.cur[l], r.cur[l + 1], L.nx, L.ny, L.nz, true, r.st));
+  }
+  BR_TRY(jacobi_pp(ctx, r.cur[l], other_buf(L, r.cur[l]), r.f[l], g, r.omega, r.nj, &res, r.st));
+  r.cur[l] = res;
+  return BAOREC_OK;
+}
+
+int mg_vcycle(baorec_ctx* ctx, float* v, const float* f, float beta, float damping, int nj, const float* los,
+              cudaStream_t st) {
+  BR_TRY(mg_setup_levels(ctx));
+  ctx->levels[0].va = v;
+  MgRun r{ctx, beta, damping, nj, los, st, {}, {}};
+  r.cur.assign(ctx->levels.size(), nullptr);
+  r.f.assign(ctx->levels.size(), nullptr);
+  r.cur[0] = v;
+  r.f[0] = f;
+  BR_TRY(vcycle_level(r, 0));
+  if (r.cur[0] != v) BR_CUDA(cudaMemcpyAsync(v, r.cur[0], ctx->M * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return BAOREC_OK;
+}
+
+// fmg (src/multigrid.jl:722-752)
+int mg_fmg(baorec_ctx* ctx, const float* f, float* v, float beta, float damping, int n_jacobi, int n_vcycle,
+           const float* los, cudaStream_t st) {
+  BR_TRY(mg_setup_levels(ctx));
+  auto& lv = ctx->levels;
+  const size_t nl = lv.size();
+  lv[0].va = v;
+  MgRun r{ctx, beta, damping, n_jacobi, los, st, {}, {}};
+  r.cur.assign(nl, nullptr);
+  r.f.assign(nl, nullptr);
+  r.f[0] = f;
+  for (size_t l = 0; l + 1 < nl; l++) {
+    BR_TRY(restrict_to(ctx, lv[l + 1].f, r.f[l], lv[l].nx, lv[l].ny, lv[l].nz, st));
+    r.f[l + 1] = lv[l + 1].f;
+  }
+  // Stage li (coarse -> fine) runs V-cycles that overwrite the f/v buffers of levels > li only;
+  // those levels have finished their own stage by then, so one restriction chain suffices.
+  for (size_t li = nl; li-- > 0;) {
+    r.f[li] = li == 0 ? f : lv[li].f;
+    if (li + 1 < nl) {
+      // initial guess: prolong the coarser solution (overwrites every fine cell)
+      float* tgt = li == 0 ? v : lv[li].va;
+      BR_TRY(prolong_to(ctx, tgt, r.cur[li + 1], lv[li].nx, lv[li].ny, lv[li].nz, false, st));
+      r.cur[li] = tgt;
+    } else {
+      float* tgt = li == 0 ? v : lv[li].va;
+      if (li != 0) BR_CUDA(cudaMemsetAsync(tgt, 0, lv[li].cells * sizeof(float), st));
+      r.cur[li] = tgt;
+    }
+    for (int c = 0; c < n_vcycle; c++) BR_TRY(vcycle_level(r, li));
+  }
+  if (r.cur[0] != v) BR_CUDA(cudaMemcpyAsync(v, r.cur[0], ctx->M * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return BAOREC_OK;
+}
+
+int reconstructed_potential(baorec_ctx* ctx, const baorec_params* p, float* phi, float* x, float* y, float* z,
+                            const float* w, int64_t n, float* rx, float* ry, float* rz, const float* rw, int64_t nr,
+                            cudaStream_t st) {
+  float* delta;
+  BR_TRY(need_t(ctx, BUF_RS, ctx->M, &delta));
+  // phi (zero-filled by the caller) is the scatter target; delta lands in RS (δ = zero(ϕ), src/recon.jl:191)
+  BR_TRY(setup_overdensity_into(ctx, p, phi, delta, x, y, z, w, n, rx, ry, rz, rw, nr, 1, st));
+  BR_CUDA(cudaMemsetAsync(phi, 0, ctx->M * sizeof(float), st));
+  return mg_fmg(ctx, delta, phi, p->beta, p->jacobi_damping_factor, p->jacobi_niterations, p->vcycle_niterations,
+                p->has_los ? p->los : nullptr, st);
+}
+
+}  // namespace baorec
+
+using namespace baorec;
+
+extern "C" {
+
+int baorec_mg_jacobi_f32(baorec_ctx* ctx, float* d_v, const float* d_f, int nx, int ny, int nz, float beta,
+                         float damping, int niterations, const float* h_los, baorec_stream stream) {
+  BR_NEED_PLAN(ctx);
+  BR_REQUIRE(d_v && d_f && nx > 1 && ny > 1 && nz > 1 && niterations >= 0, "mg_jacobi arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t cells = (size_t)nx * ny * nz;
+  float* tmp;
+  BR_TRY(need_t(ctx, BUF_RX, cells > ctx->M ? cells : ctx->M, &tmp));
+  MgGeom g = mg_geom(ctx, nx, ny, nz, beta, h_los);
+  float* res;
+  BR_TRY(jacobi_pp(ctx, d_v, tmp, d_f, g, damping, niterations, &res, st));
+  if (res != d_v) BR_CUDA(cudaMemcpyAsync(d_v, res, cells * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return BAOREC_OK;
+}
+
+int baorec_mg_residual_f32(baorec_ctx* ctx, float* d_r, const float* d_v, const float* d_f, int nx, int ny, int nz,
+                           float beta, const float* h_los, baorec_stream stream) {
+  BR_NEED_PLAN(ctx);
+  BR_REQUIRE(d_r && d_v && d_f && nx > 1 && ny > 1 && nz > 1, "mg_residual arguments");
+  MgGeom g = mg_geom(ctx, nx, ny, nz, beta, h_los);
+  return launch_stencil<MG_RESIDUAL>(ctx, d_r, d_v, d_f, g, 0.f, (cudaStream_t)stream);
+}
+
+int baorec_mg_restrict_f32(baorec_ctx* ctx, float* d_v2h, const float* d_v1h, int nx, int ny, int nz,
+                           baorec_stream stream) {
+  BR_NEED_PLAN(ctx);
+  BR_REQUIRE(d_v2h && d_v1h && nx >= 2 && ny >= 2 && nz >= 2, "mg_restrict arguments");
+  BR_REQUIRE(nx % 2 == 0 && ny % 2 == 0 && nz % 2 == 0, "mg_restrict needs even fine dimensions");
+  return restrict_to(ctx, d_v2h, d_v1h, nx, ny, nz, (cudaStream_t)stream);
+}
+
+int baorec_mg_prolong_f32(baorec_ctx* ctx, float* d_v1h, const float* d_v2h, int nx, int ny, int nz,
+                          baorec_stream stream) {
+  BR_NEED_PLAN(ctx);
+  BR_REQUIRE(d_v2h && d_v1h && nx >= 2 && ny >= 2 && nz >= 2, "mg_prolong arguments");
+  BR_REQUIRE(nx % 2 == 0 && ny % 2 == 0 && nz % 2 == 0, "mg_prolong needs even fine dimensions");
+  return prolong_to(ctx, d_v1h, d_v2h, nx, ny, nz, false, (cudaStream_t)stream);
+}
+
+int baorec_mg_vcycle_f32(baorec_ctx* ctx, float* d_v, const float* d_f, float beta, float damping, int niterations,
+                         const float* h_los, baorec_stream stream) {
+  BR_NEED_PLAN(ctx);
+  BR_REQUIRE(d_v && d_f && niterations >= 0, "mg_vcycle arguments");
+  return mg_vcycle(ctx, d_v, d_f, beta, damping, niterations, h_los, (cudaStream_t)stream);
+}
+
+int baorec_mg_fmg_f32(baorec_ctx* ctx, const float* d_f, float* d_v, float beta, float damping, int n_jacobi,
+                      int n_vcycle, const float* h_los, baorec_stream stream) {
+  BR_NEED_PLAN(ctx);
+  BR_REQUIRE(d_v && d_f && n_jacobi >= 0 && n_vcycle >= 0, "mg_fmg arguments");
+  return mg_fmg(ctx, d_f, d_v, beta, damping, n_jacobi, n_vcycle, h_los, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,223 @@
+/* baorec_b200.h -- C ABI of libbaorec_b200.so, the B200 (sm_100a) engine behind
+ * BAOrec.jl's device hot path.
+ *
+ * The reference has no FFI today: its device boundary is Julia multiple
+ * dispatch on CuArray (cited per entry point below, paths relative to the
+ * reference checkout).  Each function here is what a `ccall` from the Julia
+ * shim (baorec.jl_b200/julia/BAOrecB200.jl) or the Python ctypes mirror
+ * (baorec.jl_b200/host.py) binds instead of that CuArray method.
+ *
+ * Conventions
+ *  - Every function returns 0 on success, a negative BAOREC_ERR_* otherwise;
+ *    the message is available from baorec_last_error() (thread-local).
+ *    No exception or longjmp ever crosses the boundary.
+ *  - Meshes are float32, C-order [iz][iy][ix] with x fastest == Julia
+ *    Array{Float32,3}(nx,ny,nz) memory.  Particle arrays are SoA float32.
+ *  - Pointers named d_* are device pointers owned by the caller; the library
+ *    never frees or retains them past the call.  Pointers named h_* are host
+ *    pointers (pinned memory makes the copies asynchronous, pageable works).
+ *  - `stream` is a cudaStream_t passed as void* (CUDA.stream().handle in
+ *    Julia, torch.cuda.current_stream().cuda_stream in Python); 0 = legacy
+ *    default stream.  Primitives enqueue work on it and return; those that
+ *    can detect out-of-box particles synchronise the stream before returning
+ *    so the error code is reliable (documented per function).
+ *  - A context is bound to one device, is not re-entrant, and owns all
+ *    scratch (FFT plans and work area, k/x tables, multigrid level buffers,
+ *    binning buffers, NCCL staging): no per-call cudaMalloc after warm-up.
+ */
+#ifndef BAOREC_B200_H
+#define BAOREC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BAOREC_VERSION 100
+
+enum {
+  BAOREC_OK = 0,
+  BAOREC_ERR_INVALID = -1,     /* bad argument */
+  BAOREC_ERR_CUDA = -2,        /* CUDA runtime failure */
+  BAOREC_ERR_CUFFT = -3,       /* cuFFT failure */
+  BAOREC_ERR_NCCL = -4,        /* NCCL failure */
+  BAOREC_ERR_OUT_OF_BOX = -5,  /* particle outside the mesh (reference: BoundsError /
+                                  out-of-bounds atomic, src/mas.jl:33-49, 82-97) */
+  BAOREC_ERR_NOT_PLANNED = -6, /* baorec_plan has not been called */
+  BAOREC_ERR_NOMEM = -7
+};
+
+enum { BAOREC_MAS_CIC = 0, BAOREC_MAS_TSC = 1 };             /* TSC is an extension */
+enum { BAOREC_FIELD_DISP = 0, BAOREC_FIELD_RSD = 1, BAOREC_FIELD_SUM = 2 }; /* :disp :rsd :sum */
+enum { BAOREC_ITERATIVE = 0, BAOREC_MULTIGRID = 1 };
+
+typedef struct baorec_ctx baorec_ctx;
+typedef void* baorec_stream;
+
+/* Mirrors the keyword fields of IterativeRecon / MultigridRecon
+ * (src/recon.jl:2-16, 18-33) plus the constants the reference hard-codes. */
+typedef struct baorec_params {
+  float bias;
+  float f;
+  float smoothing_radius;
+  float beta;                  /* f / bias unless overridden */
+  int32_t n_iter;              /* IterativeRecon.n_iter (default 3) */
+  int32_t has_los;             /* 0: los = nothing (radial, observer at origin) */
+  float los[3];
+  float jacobi_damping_factor; /* default 0.4 */
+  int32_t jacobi_niterations;  /* default 5 */
+  int32_t vcycle_niterations;  /* default 6 */
+  int32_t mas;                 /* BAOREC_MAS_* ; reference = CIC */
+  float ran_min;               /* 0.01, src/recon.jl:70 */
+  float box_pad;               /* 500,  src/recon.jl:172,253 */
+} baorec_params;
+
+/* ---- lifecycle ------------------------------------------------------------ */
+int baorec_version(void);
+const char* baorec_last_error(void);
+
+/* Create a context on CUDA device `device` (runtime API, primary context:
+ * shares the context CUDA.jl / torch already use). */
+int baorec_create(int device, baorec_ctx** out);
+int baorec_destroy(baorec_ctx* ctx);
+
+/* Replaces setup_fft! (src/recon.jl:35-37) and the per-call k_vec/x_vec uploads
+ * (src/iterative.jl:153,168; src/utils.jl:89): builds cuFFT R2C/C2R plans, the
+ * k and x tables and (lazily) all scratch for an (nx,ny,nz) mesh in the given box. */
+int baorec_plan(baorec_ctx* ctx, int nx, int ny, int nz, const float box_size[3], const float box_min[3]);
+/* Change the box without re-planning the FFTs (run! with randoms overrides it,
+ * src/recon.jl:172). */
+int baorec_set_box(baorec_ctx* ctx, const float box_size[3], const float box_min[3]);
+/* Bytes of device scratch currently owned by the context. */
+int64_t baorec_scratch_bytes(const baorec_ctx* ctx);
+/* Kernel launches issued by this library since creation (cuFFT launches are
+ * counted separately in *fft_execs). */
+int baorec_launch_counts(const baorec_ctx* ctx, int64_t* kernels, int64_t* fft_execs);
+/* Per-stage timing of the last pipeline call (CUDA events on the stream):
+ * writes up to `cap` floats of milliseconds in the order scatter, setup_fft+kspace,
+ * iterations/solve, displacement meshes, gather.  Returns the count written. */
+int baorec_last_stage_ms(const baorec_ctx* ctx, float* out, int cap);
+
+/* ---- multi-GPU (one process per GPU; slabs along z) ------------------------ */
+/* 128-byte NCCL unique id, created on rank 0 and broadcast by the host side
+ * (torch.distributed / MPI.jl). */
+int baorec_comm_unique_id(void* out128);
+int baorec_comm_init(baorec_ctx* ctx, int rank, int nranks, const void* unique_id128);
+/* Distributed plan: this rank owns z-planes [rank*nz/P, (rank+1)*nz/P). */
+int baorec_plan_dist(baorec_ctx* ctx, int nx, int ny, int nz, const float box_size[3], const float box_min[3]);
+
+/* ---- mass assignment (replaces cic!/read_cic! CuArray methods) ------------- */
+/* cic!(rho::CuArray, ...; wrap) src/mas.jl:53-107.  Accumulates into d_rho (caller
+ * zero-fills).  With wrap != 0 the wrapped positions are written back into
+ * d_x/d_y/d_z exactly as the reference does (src/mas.jl:56-60).  Synchronises
+ * `stream`; returns BAOREC_ERR_OUT_OF_BOX if any particle was outside the mesh
+ * (those particles are skipped). */
+int baorec_cic_scatter_f32(baorec_ctx* ctx, float* d_rho, float* d_x, float* d_y, float* d_z,
+                           const float* d_w, int64_t n, int wrap, int mas, baorec_stream stream);
+/* Parity probe: the cell indices (0-based) and interpolation weights the
+ * scatter uses, per particle, axis-major: i0/i1/w0/w1 are [3][n]. Does not
+ * modify positions. (src/mas.jl:7-35) */
+int baorec_cic_cells_f32(baorec_ctx* ctx, const float* d_x, const float* d_y, const float* d_z, int64_t n,
+                         int wrap, int32_t* d_i0, int32_t* d_i1, float* d_w0, float* d_w1, baorec_stream stream);
+/* Same for the gather (read_cic!, src/mas.jl:224-255 CPU formula when
+ * gpu_formula == 0, :274-306 GPU formula otherwise). */
+int baorec_gather_cells_f32(baorec_ctx* ctx, const float* d_x, const float* d_y, const float* d_z, int64_t n,
+                            int gpu_formula, int32_t* d_id, int32_t* d_iu, float* d_wd, float* d_wu,
+                            baorec_stream stream);
+/* read_cic!(out::CuArray, field::CuArray, ...) src/mas.jl:271-327 (always periodic). */
+int baorec_gather_f32(baorec_ctx* ctx, const float* d_field, const float* d_x, const float* d_y,
+                      const float* d_z, int64_t n, float* d_out, int mas, baorec_stream stream);
+
+/* setup_box (src/utils.jl:100-109) on device arrays. */
+int baorec_setup_box_f32(baorec_ctx* ctx, const float* d_x, const float* d_y, const float* d_z, int64_t n,
+                         float pad, float box_size_out[3], float box_min_out[3], baorec_stream stream);
+
+/* ---- mesh set-up ------------------------------------------------------------ */
+/* smooth!(field::CuArray, R, L, plan) src/utils.jl:85-96. In place. */
+int baorec_smooth_f32(baorec_ctx* ctx, float* d_mesh, float smoothing_radius, baorec_stream stream);
+/* setup_overdensity! src/recon.jl:42-57 (n_ran == 0: periodic box, wrap as given)
+ * and :60-91 (randoms; wrap ignored = false).  d_mesh is zero-filled by the
+ * caller (run! does it) and receives delta. Synchronises `stream`. */
+int baorec_setup_overdensity_f32(baorec_ctx* ctx, const baorec_params* p, float* d_mesh,
+                                 float* d_x, float* d_y, float* d_z, const float* d_w, int64_t n,
+                                 float* d_rx, float* d_ry, float* d_rz, const float* d_rw, int64_t n_ran,
+                                 int wrap, baorec_stream stream);
+
+/* ---- iterative solver --------------------------------------------------------- */
+/* iterate!(δ_r::CuArray, δ_s, k⃗, iter, β, plan; r̂, x⃗) src/iterative.jl:151-211;
+ * `iter` is 1-based; d_los == NULL means radial (uses the x table of the plan). */
+int baorec_iterate_f32(baorec_ctx* ctx, float* d_delta_r, const float* d_delta_s, int iter, float beta,
+                       const float* h_los_or_null, baorec_stream stream);
+/* reconstructed_overdensity! src/recon.jl:93-132 (set-up + n_iter iterations). */
+int baorec_reconstructed_overdensity_f32(baorec_ctx* ctx, const baorec_params* p, float* d_mesh,
+                                         float* d_x, float* d_y, float* d_z, const float* d_w, int64_t n,
+                                         float* d_rx, float* d_ry, float* d_rz, const float* d_rw, int64_t n_ran,
+                                         baorec_stream stream);
+
+/* ---- multigrid solver (src/multigrid.jl) ---------------------------------------- */
+/* All meshes are (nx,ny,nz) device arrays of the *given* size, which may be any
+ * level of the hierarchy; the box is the plan's.  h_los == NULL -> radial. */
+int baorec_mg_jacobi_f32(baorec_ctx* ctx, float* d_v, const float* d_f, int nx, int ny, int nz, float beta,
+                         float damping, int niterations, const float* h_los_or_null, baorec_stream stream); /* :193-210 */
+int baorec_mg_residual_f32(baorec_ctx* ctx, float* d_r, const float* d_v, const float* d_f, int nx, int ny, int nz,
+                           float beta, const float* h_los_or_null, baorec_stream stream);                /* :378-395 */
+int baorec_mg_restrict_f32(baorec_ctx* ctx, float* d_v2h, const float* d_v1h, int nx, int ny, int nz,
+                           baorec_stream stream); /* reduce! :641-651 ; (nx,ny,nz) = fine size */
+int baorec_mg_prolong_f32(baorec_ctx* ctx, float* d_v1h, const float* d_v2h, int nx, int ny, int nz,
+                          baorec_stream stream);  /* prolong! :511-518 ; (nx,ny,nz) = fine size */
+int baorec_mg_vcycle_f32(baorec_ctx* ctx, float* d_v, const float* d_f, float beta, float damping,
+                         int niterations, const float* h_los_or_null, baorec_stream stream);       /* :689-719, plan size */
+int baorec_mg_fmg_f32(baorec_ctx* ctx, const float* d_f, float* d_v, float beta, float damping, int n_jacobi,
+                      int n_vcycle, const float* h_los_or_null, baorec_stream stream);              /* :722-752, plan size */
+/* reconstructed_potential! src/recon.jl:184-212. */
+int baorec_reconstructed_potential_f32(baorec_ctx* ctx, const baorec_params* p, float* d_phi,
+                                       float* d_x, float* d_y, float* d_z, const float* d_w, int64_t n,
+                                       float* d_rx, float* d_ry, float* d_rz, const float* d_rw, int64_t n_ran,
+                                       baorec_stream stream);
+
+/* ---- read-back ------------------------------------------------------------------ */
+/* compute_displacements(mesh::CuArray, x,y,z, recon) src/iterative.jl:229-250
+ * (algorithm BAOREC_ITERATIVE: Psi = irfft(i k delta_k/k^2)) and
+ * src/multigrid.jl:781-799 (BAOREC_MULTIGRID: Psi = irfft(i k phi_k)). */
+int baorec_compute_displacements_f32(baorec_ctx* ctx, const float* d_mesh, int algorithm,
+                                     const float* d_x, const float* d_y, const float* d_z, int64_t n,
+                                     float* d_px, float* d_py, float* d_pz, int mas, baorec_stream stream);
+/* read_shifts(recon, x,y,z, mesh; field) src/recon.jl:333-364. */
+int baorec_read_shifts_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, const float* d_mesh,
+                           const float* d_x, const float* d_y, const float* d_z, int64_t n, int field,
+                           float* d_sx, float* d_sy, float* d_sz, baorec_stream stream);
+/* reconstructed_positions src/recon.jl:366-388: pos - shift, no re-wrap. */
+int baorec_reconstructed_positions_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, const float* d_mesh,
+                                       const float* d_x, const float* d_y, const float* d_z, int64_t n, int field,
+                                       float* d_ox, float* d_oy, float* d_oz, baorec_stream stream);
+/* The three real-space displacement meshes themselves (parity probe). */
+int baorec_displacement_meshes_f32(baorec_ctx* ctx, const float* d_mesh, int algorithm,
+                                   float* d_psix, float* d_psiy, float* d_psiz, baorec_stream stream);
+
+/* ---- whole pipeline, host buffers (what run! + reconstructed_positions do) ------- */
+/* run!(recon, grid_size, data..., [rand...]) src/recon.jl:134-180 / 215-261 with HOST
+ * catalogs: uploads them, (randoms: setup_box with p->box_pad and baorec_set_box,
+ * returned in box_*_out), zero-fills an internal result mesh (recon.result_cache),
+ * solves.  h_mesh_out may be NULL (mesh stays on the device as the cache).  When
+ * wrap applies, the wrapped positions are written back to h_x/h_y/h_z like cic!. */
+int baorec_run_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm,
+                        float* h_x, float* h_y, float* h_z, const float* h_w, int64_t n,
+                        const float* h_rx, const float* h_ry, const float* h_rz, const float* h_rw, int64_t n_ran,
+                        float* h_mesh_out, float box_size_out[3], float box_min_out[3]);
+/* reconstructed_positions / read_shifts on HOST catalogs against the cached mesh
+ * (or h_mesh_or_null uploaded first).  shifts_only != 0 -> read_shifts. */
+int baorec_read_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, const float* h_mesh_or_null,
+                         const float* h_x, const float* h_y, const float* h_z, int64_t n, int field,
+                         int shifts_only, float* h_ox, float* h_oy, float* h_oz);
+/* Device pointer of the cached result mesh (recon.result_cache), or NULL. */
+float* baorec_result_cache(baorec_ctx* ctx);
+
+/* Pinned host memory helpers for callers without their own (Julia: CUDA.Mem.alloc(HostBuffer)). */
+int baorec_host_alloc(void** out, int64_t bytes);
+int baorec_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAOREC_B200_H */
