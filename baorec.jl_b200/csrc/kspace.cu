@@ -200,14 +200,14 @@ randoms_combine_kernel(float* __restrict__ out, const float* __restrict__ dat, c
                        const double* __restrict__ scal, float bias, double ran_min, double n_ran, size_t n) {
   const float sd = (float)scal[0], sr = (float)scal[1];
   const float alpha = __fdiv_rn(sd, sr);
-  const float thr = (float)(ran_min * (double)sr / n_ran);
+  const double thr = ran_min * (double)sr / n_ran;  // Float64 like the reference (0.01 literal, src/recon.jl:70,81)
   const float ba = __fmul_rn(bias, alpha);
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     float d = dat[i], r = ran[i];
     float num = __fsub_rn(d, __fmul_rn(alpha, r));
-    out[i] = r > thr ? __fdiv_rn(num, __fmul_rn(ba, r)) : 0.f;
+    out[i] = (double)r > thr ? __fdiv_rn(num, __fmul_rn(ba, r)) : 0.f;
   }
 }
 

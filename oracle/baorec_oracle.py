@@ -378,8 +378,13 @@ def _scatter(recon, rho, x, y, z, w, wrap):
 
 
 def setup_overdensity(delta, recon, x, y, z, w, rx=None, ry=None, rz=None, rw=None,
-                      wrap=True, ran_min=0.01):
-    """src/recon.jl:42-57 (no randoms) and :60-91 (randoms)."""
+                      wrap=True, ran_min=0.01, force_mask=None, info=None):
+    """src/recon.jl:42-57 (no randoms) and :60-91 (randoms).
+
+    Test hooks (not in the reference): `force_mask` replaces the `ran > threshold` decision by a
+    given boolean mesh (the cut is a discontinuity: cells whose smoothed randoms density sits
+    within fp32 FFT noise of the threshold legitimately flip between implementations); `info`, if
+    a dict, receives the smoothed randoms mesh and the threshold."""
     T = _T(delta)
     if rx is None:
         _scatter(recon, delta, x, y, z, w, wrap)
@@ -395,11 +400,14 @@ def setup_overdensity(delta, recon, x, y, z, w, rx=None, ry=None, rz=None, rw=No
     sd = T(delta.sum(dtype=T))
     sr = T(ran.sum(dtype=T))
     alpha = T(sd / sr)
-    thr = T(np.float64(ran_min) * np.float64(sr) / len(rx))   # ran_min is a Float64 literal (:70)
+    thr = np.float64(ran_min) * np.float64(sr) / len(rx)      # Float64: ran_min is a Float64 literal (:70)
     delta -= (alpha * ran).astype(T)
     with np.errstate(divide="ignore", invalid="ignore"):
         q = (delta / ((T(recon.bias) * alpha).astype(T) * ran).astype(T)).astype(T)
-    delta[...] = np.where(ran > thr, q, T(0))
+    mask = (ran.astype(np.float64) > thr) if force_mask is None else force_mask
+    if info is not None:
+        info.update(ran=ran, threshold=thr, alpha=alpha)
+    delta[...] = np.where(mask, q, T(0))
     return delta
 
 
@@ -447,11 +455,11 @@ def iterate(delta_r, delta_s, kv, it, beta, los=None, xv=None):
     return delta_r
 
 
-def reconstructed_overdensity(delta, recon: IterativeRecon, x, y, z, w, rx=None, ry=None, rz=None, rw=None):
+def reconstructed_overdensity(delta, recon: IterativeRecon, x, y, z, w, rx=None, ry=None, rz=None, rw=None, force_mask=None):
     """src/recon.jl:93-132."""
     T = _T(delta)
     nz, ny, nx = delta.shape
-    setup_overdensity(delta, recon, x, y, z, w, rx, ry, rz, rw)
+    setup_overdensity(delta, recon, x, y, z, w, rx, ry, rz, rw, force_mask=force_mask)
     delta_s = delta.copy()
     kv = k_vec((nx, ny, nz), recon.box_size, T)
     xv = x_vec((nx, ny, nz), recon.box_size, recon.box_min, T) if recon.los is None else None
@@ -693,11 +701,11 @@ def fmg(f1h, v1h, box_size, box_min, beta, damping_factor, jacobi_niterations, v
     return v1h
 
 
-def reconstructed_potential(phi, recon: MultigridRecon, x, y, z, w, rx=None, ry=None, rz=None, rw=None):
+def reconstructed_potential(phi, recon: MultigridRecon, x, y, z, w, rx=None, ry=None, rz=None, rw=None, force_mask=None):
     """src/recon.jl:184-212."""
     T = _T(phi)
     delta = np.zeros_like(phi)
-    setup_overdensity(delta, recon, x, y, z, w, rx, ry, rz, rw)
+    setup_overdensity(delta, recon, x, y, z, w, rx, ry, rz, rw, force_mask=force_mask)
     fmg(delta, phi, recon.box_size, recon.box_min, T(recon.beta), T(recon.jacobi_damping_factor),
         recon.jacobi_niterations, recon.vcycle_niterations, recon.los)
     return phi
@@ -706,15 +714,15 @@ def reconstructed_potential(phi, recon: MultigridRecon, x, y, z, w, rx=None, ry=
 # --------------------------------------------------------------------------
 # run! (src/recon.jl:134-180, 215-261)
 # --------------------------------------------------------------------------
-def run(recon, grid_size_xyz, x, y, z, w, rx=None, ry=None, rz=None, rw=None):
+def run(recon, grid_size_xyz, x, y, z, w, rx=None, ry=None, rz=None, rw=None, force_mask=None):
     T = _T(x)
     nx, ny, nz = grid_size_xyz
     mesh = np.zeros((nz, ny, nx), dtype=T)
     if rx is not None:
         recon.box_size, recon.box_min = setup_box(rx, ry, rz, T(500))
     if isinstance(recon, MultigridRecon):
-        reconstructed_potential(mesh, recon, x, y, z, w, rx, ry, rz, rw)
+        reconstructed_potential(mesh, recon, x, y, z, w, rx, ry, rz, rw, force_mask)
     else:
-        reconstructed_overdensity(mesh, recon, x, y, z, w, rx, ry, rz, rw)
+        reconstructed_overdensity(mesh, recon, x, y, z, w, rx, ry, rz, rw, force_mask)
     recon.result_cache = mesh
     return mesh

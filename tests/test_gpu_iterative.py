@@ -11,6 +11,9 @@ pytestmark = pytest.mark.gpu
 
 TOL_RMS = 1e-4
 TOL_MAX_SHIFT = 1e-3
+# lightcone test geometry: shell sector whose padded box gives cell (12.2 Mpc/h) < smoothing radius at 96^3
+LC = dict(rmin=500.0, rmax=800.0, half_angle_deg=25.0)
+NLC = 96
 
 
 def dev(a):
@@ -49,20 +52,27 @@ def test_setup_overdensity_box(B, O, maker):
 
 
 def test_setup_overdensity_randoms(B, O):
-    n = 64
-    d, wd, r, wr = lightcone(60_000, 600_000, seed=5)
+    n = NLC
+    d, wd, r, wr = lightcone(60_000, 600_000, seed=5, **LC)
     bs, bm = O.setup_box(*r, np.float32(500))
     kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=bs, box_min=bm, los=None)
     ref = O.setup_overdensity(np.zeros((n, n, n), np.float32), O.IterativeRecon(**kw), *d, wd, *r, wr)
+    kw64 = dict(kw, box_size=bs.astype(np.float64), box_min=bm.astype(np.float64))
+    ref64 = O.setup_overdensity(np.zeros((n, n, n), np.float64), O.IterativeRecon(**kw64),
+                                *[p.astype(np.float64) for p in d], wd.astype(np.float64),
+                                *[p.astype(np.float64) for p in r], wr.astype(np.float64))
     rec = B.IterativeRecon(**kw)
     mesh = torch.zeros((n, n, n), dtype=torch.float32, device="cuda")
     B.setup_fft(rec, mesh)
     B.setup_overdensity(mesh, rec, *(dev(p) for p in d), dev(wd), *(dev(p) for p in r), dev(wr))
     got = mesh.cpu().numpy()
-    # cells right at the ran > threshold cut can flip with the summation order of the scatter
-    flips = (got == 0) != (ref == 0)
-    assert flips.mean() < 1e-4
-    assert rel_rms(got[~flips], ref[~flips]) < TOL_RMS
+    # (dat - a ran)/(b a ran) amplifies fp32 rounding where ran is barely above the threshold, and
+    # cells right at the cut can flip: the yardstick is the fp32 oracle's own distance to fp64.
+    keep = ((got == 0) == (ref64 == 0)) & ((ref == 0) == (ref64 == 0))
+    assert (~keep).mean() < 1e-4
+    err_gpu, err_o32 = rel_rms(got[keep], ref64[keep]), rel_rms(ref[keep], ref64[keep])
+    assert err_gpu < max(TOL_RMS, 2 * err_o32), (err_gpu, err_o32)
+    assert rel_rms(got[keep], ref[keep]) < 3e-4
 
 
 @pytest.mark.parametrize("los", [(0.0, 0.0, 1.0), (1.0, 0.0, 0.0), None])
@@ -118,27 +128,64 @@ def test_run_and_read_shifts_box(B, O, maker, los):
         assert np.array_equal(newpos[a].cpu().numpy(), (d[a] - s[a]).cpu().numpy())
 
 
+def check_flips_explained(mask_gpu, info, max_flips=40):
+    """The `ran > threshold` cut (src/recon.jl:85) is a discontinuity: cells whose smoothed randoms
+    density is within fp32 FFT/atomic noise of the threshold may legitimately fall on either side.
+    Every disagreement with the oracle must be such a cell."""
+    ran, thr = info["ran"].astype(np.float64), info["threshold"]
+    flips = mask_gpu != (ran > thr)
+    assert flips.sum() <= max_flips
+    assert (np.abs(ran[flips] / thr - 1.0) < 2e-3).all()
+    return int(flips.sum())
+
+
 def test_run_lightcone_radial_randoms(B, O):
-    n = 64
-    d, wd, r, wr = lightcone(80_000, 800_000, seed=9)
+    """IterativeRecon, lightcone: radial LOS + randoms (BASELINE config 2 at test scale)."""
+    n = NLC
+    d, wd, r, wr = lightcone(80_000, 800_000, seed=9, **LC)
     kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, los=None)
-    orec = O.IterativeRecon(**kw)
-    omesh = O.run(orec, (n, n, n), *d, wd, *r, wr)
-    rec = B.IterativeRecon(**kw)
     gd, gr = [dev(p) for p in d], [dev(p) for p in r]
-    mesh = B.run(rec, (n, n, n), *gd, dev(wd), *gr, dev(wr))
+    # --- stepwise through the primitives: set-up, then 3 x iterate! ---
+    rec = B.IterativeRecon(**kw)
+    rec.box_size, rec.box_min = B.setup_box(*gr, 500.0)
+    ds = torch.zeros((n, n, n), dtype=torch.float32, device="cuda")
+    B.setup_fft(rec, ds)
+    B.setup_overdensity(ds, rec, *gd, dev(wd), *gr, dev(wr))
+    mask = ds.cpu().numpy() != 0
+    orec = O.IterativeRecon(**kw)
+    orec.box_size, orec.box_min = O.setup_box(*r, np.float32(500))
     assert np.array_equal(rec.box_size, orec.box_size) and np.array_equal(rec.box_min, orec.box_min)
-    got = mesh.cpu().numpy()
-    # threshold flips (ran ~ thr) propagate through the iterations only locally: compare shifts
-    assert rel_rms(got, omesh) < 5e-3
-    for f in ("disp", "sum"):
-        so = O.read_shifts(orec, *d, omesh, f)
-        sg = B.read_shifts(rec, *gd, mesh, field=f)
-        so_r = O.read_shifts(orec, *r, omesh, f)
-        sg_r = B.read_shifts(rec, *gr, mesh, field=f)
-        for a in range(3):
-            assert maxabs(sg[a].cpu().numpy(), so[a]) < 5e-3
-            assert maxabs(sg_r[a].cpu().numpy(), so_r[a]) < 5e-3
+    info = {}
+    O.setup_overdensity(np.zeros((n, n, n), np.float32), orec, *d, wd, *r, wr, info=info)
+    check_flips_explained(mask, info)
+    omesh = O.run(O.IterativeRecon(**kw), (n, n, n), *d, wd, *r, wr, force_mask=mask)
+    # fp64 truth with the same mask: the fp32 oracle's own distance to it is the yardstick, because
+    # 1/(a ran) amplifies fp32 rounding in the sparse cells at the survey edge
+    d64, r64 = [p.astype(np.float64) for p in d], [p.astype(np.float64) for p in r]
+    orec64 = O.IterativeRecon(**kw)
+    omesh64 = O.run(orec64, (n, n, n), *d64, wd.astype(np.float64), *r64, wr.astype(np.float64), force_mask=mask)
+    dr = ds.clone()
+    for it in (1, 2, 3):
+        B.iterate(dr, ds, None, it, rec.beta, rec.fft_plan, r_hat=None, box_size=rec.box_size, box_min=rec.box_min)
+    assert rel_rms(dr.cpu().numpy(), omesh64) < max(TOL_RMS, 2 * rel_rms(omesh, omesh64))
+    for f in ("disp", "rsd", "sum"):
+        for cat, cat64, gcat in ((d, d64, gd), (r, r64, gr)):
+            so = O.read_shifts(orec, *cat, omesh, f)
+            so64 = O.read_shifts(orec64, *cat64, omesh64, f)
+            sg = B.read_shifts(rec, *gcat, dr, field=f)
+            for a in range(3):
+                g = sg[a].cpu().numpy()
+                assert rel_rms(g, so64[a]) < max(TOL_RMS, 2 * rel_rms(so[a], so64[a]))
+                assert maxabs(g, so64[a]) < max(TOL_MAX_SHIFT, 2 * maxabs(so[a], so64[a]))
+    # --- the one-call driver: same thing up to the (run-to-run) threshold flips ---
+    rec2 = B.IterativeRecon(**kw)
+    mesh = B.run(rec2, (n, n, n), *gd, dev(wd), *gr, dev(wr))
+    assert np.array_equal(rec2.box_size, orec.box_size) and np.array_equal(rec2.box_min, orec.box_min)
+    sg = B.read_shifts(rec2, *gd, mesh, field="sum")
+    so = O.read_shifts(orec, *d, omesh, "sum")
+    for a in range(3):
+        err = np.abs(sg[a].cpu().numpy() - so[a])
+        assert np.median(err) < 5e-4 and np.quantile(err, 0.9) < 2e-3
 
 
 def test_host_pipeline_matches_device_path(B):
@@ -154,4 +201,4 @@ def test_host_pipeline_matches_device_path(B):
     assert rel_rms(hmesh, mesh.cpu().numpy()) < 1e-5      # atomics order only
     s_host = B.reconstructed_positions(rec2, *pos, field="sum")
     for a in range(3):
-        assert maxabs(s_host[a], s_dev[a].cpu().numpy()) < 1e-4
+        assert maxabs(s_host[a], s_dev[a].cpu().numpy()) < 5e-4   # positions ~1e3: a few ulp
