@@ -29,12 +29,12 @@ static int check_catalog(int64_t n, const void* x, const void* y, const void* z,
 // Displacement meshes of `mesh` into RX/RY/RZ, then the fused gather + read_shifts epilogue.
 static int read_common(baorec_ctx* ctx, const baorec_params* p, int algorithm, const float* mesh, const float* x,
                        const float* y, const float* z, int64_t n, int field, int positions, float* ox, float* oy,
-                       float* oz, cudaStream_t st) {
+                       float* oz, cudaStream_t st, bool use_kcache = false) {
   float *px, *py, *pz;
   BR_TRY(need_t(ctx, BUF_RX, ctx->M, &px));
   BR_TRY(need_t(ctx, BUF_RY, ctx->M, &py));
   BR_TRY(need_t(ctx, BUF_RZ, ctx->M, &pz));
-  BR_TRY(displacement_meshes(ctx, mesh, algorithm, px, py, pz, st));
+  BR_TRY(displacement_meshes(ctx, mesh, algorithm, px, py, pz, st, use_kcache));
   BR_CUDA(cudaEventRecord(ctx->ev[5], st));
   BR_TRY(reset_oob(ctx, st));
   BR_TRY(gather3(ctx, px, py, pz, x, y, z, n, ox, oy, oz, p->mas, field, p->f, p->has_los, p->los, positions, st));
@@ -140,6 +140,21 @@ int baorec_reconstructed_positions_f32(baorec_ctx* ctx, const baorec_params* p, 
   return read_common(ctx, p, algorithm, d_mesh, d_x, d_y, d_z, n, field, 1, d_ox, d_oy, d_oz, (cudaStream_t)stream);
 }
 
+int baorec_set_option(baorec_ctx* ctx, const char* name, int64_t value) {
+  BR_REQUIRE(ctx != nullptr && name != nullptr, "NULL argument");
+  std::string s(name);
+  if (s == "bin_min_particles") ctx->opt_bin_min_particles = value;
+  else if (s == "fuse_kspace") ctx->opt_fuse_kspace = (int)value;
+  else if (s == "gather_tiles") ctx->opt_gather_tiles = (int)value;
+  else if (s == "bin_zg_scatter") ctx->opt_zg_scatter = (int)value;
+  else if (s == "bin_zg_gather") ctx->opt_zg_gather = (int)value;
+  else {
+    set_error("baorec_set_option: unknown option '%s'", name);
+    return BAOREC_ERR_INVALID;
+  }
+  return BAOREC_OK;
+}
+
 // ---- host pipelines ---------------------------------------------------------------------------------
 int baorec_run_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, float* h_x, float* h_y, float* h_z,
                         const float* h_w, int64_t n, const float* h_rx, const float* h_ry, const float* h_rz,
@@ -152,6 +167,7 @@ int baorec_run_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, 
   BR_TRY(check_catalog(n_ran, h_rx, h_ry, h_rz, h_rw, "randoms"));
   cudaStream_t st = ctx->own_stream;
   ctx->cache_valid = false;
+  ctx->kcache_valid = false;
   float *dp, *dr = nullptr, *mesh;
   BR_TRY(need_t(ctx, BUF_PART, (size_t)(n > 0 ? n : 1) * 4, &dp));
   if (n_ran > 0) BR_TRY(need_t(ctx, BUF_PART2, (size_t)n_ran * 4, &dr));
@@ -181,14 +197,17 @@ int baorec_run_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, 
   float* rz = dr ? dr + 2 * n_ran : nullptr;
   float* rw = dr ? dr + 3 * n_ran : nullptr;
   int s;
+  ctx->want_kcache = true;
   if (algorithm == BAOREC_MULTIGRID)
     s = reconstructed_potential(ctx, p, mesh, dp, dp + n, dp + 2 * n, dp + 3 * n, n, rx, ry, rz, rw, n_ran, st);
   else
     s = reconstructed_overdensity(ctx, p, mesh, dp, dp + n, dp + 2 * n, dp + 3 * n, n, rx, ry, rz, rw, n_ran, st);
+  ctx->want_kcache = false;
   if (s != BAOREC_OK) return s;
   BR_CUDA(cudaEventRecord(ctx->ev[2], st));
-  if (n_ran == 0 && n > 0) {
-    // cic!(wrap = true) mutates the caller's positions (src/mas.jl:8-10): copy them back.
+  if (n_ran == 0 && n > 0 && ctx->last_wrapped > 0) {
+    // cic!(wrap = true) mutates the caller's positions (src/mas.jl:8-10): copy them back
+    // (only when at least one particle was actually wrapped).
     float* hdst[3] = {h_x, h_y, h_z};
     for (int c = 0; c < 3; c++)
       BR_CUDA(cudaMemcpyAsync(hdst[c], dp + (size_t)c * n, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -216,6 +235,7 @@ int baorec_read_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm,
   if (h_mesh_or_null) {
     BR_CUDA(cudaMemcpyAsync(mesh, h_mesh_or_null, ctx->M * sizeof(float), cudaMemcpyHostToDevice, st));
     ctx->cache_valid = true;
+    ctx->kcache_valid = false;
   }
   if (!ctx->cache_valid) {
     set_error("baorec_read_host_f32: no cached result mesh (call baorec_run_host_f32 first or pass a mesh)");
@@ -229,7 +249,7 @@ int baorec_read_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm,
   for (int c = 0; c < 3 && n > 0; c++)
     BR_CUDA(cudaMemcpyAsync(dp + c * nn, hsrc[c], (size_t)n * sizeof(float), cudaMemcpyHostToDevice, st));
   BR_TRY(read_common(ctx, p, algorithm, mesh, dp, dp + nn, dp + 2 * nn, n, field, shifts_only ? 0 : 1, dout, dout + nn,
-                     dout + 2 * nn, st));
+                     dout + 2 * nn, st, /*use_kcache=*/true));
   BR_CUDA(cudaEventRecord(ctx->ev[6], st));
   float* hdst[3] = {h_ox, h_oy, h_oz};
   for (int c = 0; c < 3 && n > 0; c++)

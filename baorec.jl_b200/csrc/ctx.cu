@@ -16,6 +16,30 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static cudaEvent_t prof_event(baorec_ctx* ctx) {
+  if (!ctx->prof_pool.empty()) {
+    cudaEvent_t e = ctx->prof_pool.back();
+    ctx->prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+int prof_begin(baorec_ctx* ctx, const char* name, cudaStream_t st) {
+  if (!ctx->prof_on) return -1;
+  ProfRec r{name, prof_event(ctx), prof_event(ctx)};
+  cudaEventRecord(r.a, st);
+  ctx->prof.push_back(r);
+  return (int)ctx->prof.size() - 1;
+}
+
+void prof_end(baorec_ctx* ctx, int idx, cudaStream_t st) {
+  if (idx < 0) return;
+  cudaEventRecord(ctx->prof[idx].b, st);
+}
+
 int need(baorec_ctx* ctx, BufId id, size_t bytes, void** out) {
   Buf& b = ctx->bufs[id];
   if (b.bytes < bytes) {
@@ -44,14 +68,16 @@ void release(baorec_ctx* ctx, BufId id) {
 }
 
 int reset_oob(baorec_ctx* ctx, cudaStream_t st) {
-  BR_CUDA(cudaMemsetAsync(ctx->d_oob, 0, sizeof(unsigned long long), st));
+  BR_CUDA(cudaMemsetAsync(ctx->d_oob, 0, 2 * sizeof(unsigned long long), st));
   return BAOREC_OK;
 }
 
 int check_oob(baorec_ctx* ctx, cudaStream_t st, const char* what) {
-  unsigned long long h = 0;
-  BR_CUDA(cudaMemcpyAsync(&h, ctx->d_oob, sizeof(h), cudaMemcpyDeviceToHost, st));
+  unsigned long long hh[2] = {0, 0};
+  BR_CUDA(cudaMemcpyAsync(hh, ctx->d_oob, sizeof(hh), cudaMemcpyDeviceToHost, st));
   BR_CUDA(cudaStreamSynchronize(st));
+  ctx->last_wrapped = (int64_t)hh[1];
+  unsigned long long h = hh[0];
   if (h != 0) {
     set_error("%s: %llu particle(s) outside the mesh (the reference would raise BoundsError / write out of bounds)",
               what, h);
@@ -62,14 +88,18 @@ int check_oob(baorec_ctx* ctx, cudaStream_t st, const char* what) {
 
 int fft_r2c(baorec_ctx* ctx, const float* in, float2* out, cudaStream_t st) {
   BR_CUFFT(cufftSetStream(ctx->r2c, st));
+  int pi = prof_begin(ctx, "cufft_r2c", st);
   BR_CUFFT(cufftExecR2C(ctx->r2c, (cufftReal*)in, (cufftComplex*)out));
+  prof_end(ctx, pi, st);
   ctx->n_fft++;
   return BAOREC_OK;
 }
 
 int fft_c2r(baorec_ctx* ctx, float2* in, float* out, cudaStream_t st) {
   BR_CUFFT(cufftSetStream(ctx->c2r, st));
+  int pi = prof_begin(ctx, "cufft_c2r", st);
   BR_CUFFT(cufftExecC2R(ctx->c2r, (cufftComplex*)in, (cufftReal*)out));
+  prof_end(ctx, pi, st);
   ctx->n_fft++;
   return BAOREC_OK;
 }
@@ -158,6 +188,7 @@ int plan_common(baorec_ctx* ctx, int nx, int ny, int nz, const float L[3], const
     }
     ctx->cache_valid = false;
   }
+  ctx->kcache_valid = false;
   for (int a = 0; a < 3; a++) {
     ctx->L[a] = L[a];
     ctx->mn[a] = mn[a];
@@ -183,8 +214,8 @@ int baorec_create(int device, baorec_ctx** out) {
   BR_CUDA(cudaSetDevice(device));
   baorec_ctx* ctx = new baorec_ctx();
   ctx->device = device;
-  BR_CUDA(cudaMalloc(&ctx->d_oob, sizeof(unsigned long long)));
-  BR_CUDA(cudaMemset(ctx->d_oob, 0, sizeof(unsigned long long)));
+  BR_CUDA(cudaMalloc(&ctx->d_oob, 2 * sizeof(unsigned long long)));  // [0] out-of-box, [1] positions wrapped
+  BR_CUDA(cudaMemset(ctx->d_oob, 0, 2 * sizeof(unsigned long long)));
   BR_CUDA(cudaMalloc(&ctx->d_scal, 16 * sizeof(double)));
   BR_CUDA(cudaMalloc(&ctx->d_minmax, 8 * sizeof(float)));
   BR_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
@@ -211,6 +242,11 @@ int baorec_destroy(baorec_ctx* ctx) {
   if (ctx->d_minmax) cudaFree(ctx->d_minmax);
   for (int i = 0; i < 8; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (auto& r : ctx->prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  for (auto e : ctx->prof_pool) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return BAOREC_OK;
@@ -280,6 +316,47 @@ int baorec_last_stage_ms(const baorec_ctx* ctx, float* out, int cap) {
 float* baorec_result_cache(baorec_ctx* ctx) {
   if (!ctx || !ctx->cache_valid) return nullptr;
   return (float*)ctx->bufs[BUF_CACHE].p;
+}
+
+int baorec_profile_enable(baorec_ctx* ctx, int on) {
+  BR_REQUIRE(ctx != nullptr, "ctx is NULL");
+  BR_CUDA(cudaSetDevice(ctx->device));
+  BR_CUDA(cudaDeviceSynchronize());
+  for (auto& r : ctx->prof) {
+    ctx->prof_pool.push_back(r.a);
+    ctx->prof_pool.push_back(r.b);
+  }
+  ctx->prof.clear();
+  ctx->prof_on = on != 0;
+  return BAOREC_OK;
+}
+
+int baorec_profile_read(baorec_ctx* ctx, char* names, int name_stride, float* total_ms, int32_t* counts, int cap) {
+  BR_REQUIRE(ctx != nullptr && names && total_ms && counts && name_stride > 1 && cap > 0, "profile_read arguments");
+  BR_CUDA(cudaSetDevice(ctx->device));
+  BR_CUDA(cudaDeviceSynchronize());
+  int n = 0;
+  for (auto& r : ctx->prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+    int k = -1;
+    for (int i = 0; i < n; i++)
+      if (strncmp(names + (size_t)i * name_stride, r.name, name_stride - 1) == 0) {
+        k = i;
+        break;
+      }
+    if (k < 0) {
+      if (n >= cap) continue;
+      k = n++;
+      strncpy(names + (size_t)k * name_stride, r.name, name_stride - 1);
+      names[(size_t)k * name_stride + name_stride - 1] = 0;
+      total_ms[k] = 0.f;
+      counts[k] = 0;
+    }
+    total_ms[k] += ms;
+    counts[k] += 1;
+  }
+  return n;
 }
 
 int baorec_host_alloc(void** out, int64_t bytes) {

@@ -46,10 +46,14 @@ void set_error(const char* fmt, ...);
     }                                                 \
   } while (0)
 
-// Count + check a kernel launch.
-#define BR_LAUNCH(ctx, kernel, grid, block, smem, stream, ...)            \
+// Count + check a kernel launch; when profiling is on, bracket it with CUDA events.
+#define BR_LAUNCH(ctx, kernel, grid, block, smem, stream, ...) \
+  BR_LAUNCH_NAMED(ctx, #kernel, kernel, grid, block, smem, stream, __VA_ARGS__)
+#define BR_LAUNCH_NAMED(ctx, name, kernel, grid, block, smem, stream, ...) \
   do {                                                                    \
+    int _pi = baorec::prof_begin((ctx), (name), (stream));                \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);           \
+    baorec::prof_end((ctx), _pi, (stream));                               \
     (ctx)->n_kernels++;                                                   \
     BR_CUDA(cudaGetLastError());                                          \
   } while (0)
@@ -58,6 +62,7 @@ enum BufId {
   BUF_CK0 = 0,  // complex half-mesh (R2C output / k-space work)
   BUF_CK1,
   BUF_CK2,
+  BUF_CKCACHE,  // delta_k of the cached result mesh (host pipeline)
   BUF_RS,       // real mesh: delta_s / multigrid right-hand side
   BUF_RX,       // real mesh: C2R output / displacement x
   BUF_RY,
@@ -71,6 +76,8 @@ enum BufId {
   BUF_BINKEY,   // particle binning
   BUF_BINIDX,
   BUF_BINTMP,
+  BUF_BININV,   // inverse permutation of the tile sort
+  BUF_BINOUT,   // gather results in sorted order
   BUF_MG,       // multigrid level hierarchy (one slab allocation)
   BUF_A2A_SEND, // distributed FFT staging
   BUF_A2A_RECV,
@@ -81,6 +88,11 @@ enum BufId {
 struct Buf {
   void* p = nullptr;
   size_t bytes = 0;
+};
+
+struct ProfRec {
+  const char* name;
+  cudaEvent_t a, b;
 };
 
 struct MgLevel {
@@ -119,6 +131,17 @@ struct baorec_ctx {
   int n_stage = 0;
   int64_t n_kernels = 0, n_fft = 0;
   bool cache_valid = false;
+  bool kcache_valid = false;   // BUF_CKCACHE holds the unnormalised R2C of the cached result mesh
+  bool want_kcache = false;    // set by the host pipeline around the solve
+  int64_t opt_bin_min_particles = 1 << 18;  // catalogs at least this large are z-binned first
+  int opt_fuse_kspace = 1;
+  int opt_gather_tiles = 1;    // gather: fine (z, y/8, x/128) tile binning instead of z slabs
+  int opt_zg_scatter = 0, opt_zg_gather = 0;  // z planes per bin (0 = auto)     // fixed-LOS iterations folded into one k-space pass
+  int64_t last_wrapped = 0;  // particles whose position cic! wrapped in the last scatter
+  // per-launch profiling (baorec_profile_*)
+  bool prof_on = false;
+  std::vector<baorec::ProfRec> prof;      // records of the current window
+  std::vector<cudaEvent_t> prof_pool;     // recycled events
   // multigrid
   std::vector<baorec::MgLevel> levels;
   bool mg_radial_tables = false;
@@ -133,6 +156,8 @@ struct baorec_ctx {
 
 namespace baorec {
 
+int prof_begin(baorec_ctx* ctx, const char* name, cudaStream_t st);
+void prof_end(baorec_ctx* ctx, int idx, cudaStream_t st);
 int need(baorec_ctx* ctx, BufId id, size_t bytes, void** out);
 template <class T>
 inline int need_t(baorec_ctx* ctx, BufId id, size_t count, T** out) {
@@ -165,7 +190,7 @@ int setup_overdensity(baorec_ctx* ctx, const baorec_params* p, float* mesh, floa
 int iterate(baorec_ctx* ctx, float* delta_r, const float* delta_s, int iter, float beta, const float* los,
             cudaStream_t st);
 int displacement_meshes(baorec_ctx* ctx, const float* mesh, int algorithm, float* px, float* py, float* pz,
-                        cudaStream_t st);
+                        cudaStream_t st, bool use_kcache = false);
 
 int setup_overdensity_into(baorec_ctx* ctx, const baorec_params* p, float* mesh, float* delta_out, float* x, float* y,
                            float* z, const float* w, int64_t n, float* rx, float* ry, float* rz, const float* rw,

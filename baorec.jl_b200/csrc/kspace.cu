@@ -62,7 +62,8 @@ __device__ __forceinline__ float ksq(float kx, float ky, float kz) {
 // exp(-0.5 R² k²) evaluated in Float64 like the reference (src/utils.jl:52, 81).
 __device__ __forceinline__ double gauss64(float R2, float k2) { return exp(-0.5 * (double)R2 * (double)k2); }
 
-struct GaussOp {  // smooth!: field_k *= exp(-0.5 R² k²), then /M
+struct GaussOp {
+  static const char* name() { return "kspace_kernel<GaussOp>"; }  // smooth!: field_k *= exp(-0.5 R² k²), then /M
   float2* out;
   float R2;
   double invM;
@@ -72,19 +73,21 @@ struct GaussOp {  // smooth!: field_k *= exp(-0.5 R² k²), then /M
   }
 };
 
-struct SetupBoxOp {  // smooth + (rho/mean - 1)/bias in k-space: delta_k = rho_k g /(A0 bias), DC -> 0
+struct SetupBoxOp {
+  static const char* name() { return "kspace_kernel<SetupBoxOp>"; }  // smooth + (rho/mean - 1)/bias in k-space: delta_k = rho_k g /(A0 bias), DC -> 0
   float2* out;
   float R2;
   float bias;
   const double* dc;  // Re A_k[0] = sum(rho)
   __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool is_dc) const {
-    double s = gauss64(R2, ksq(kx, ky, kz)) / (__ldg(dc) * (double)bias);
+    double s = gauss64(R2, ksq(kx, ky, kz)) * __ldg(dc + 8);  // dc[8] = 1 / (A0 bias)
     if (is_dc) s = 0.0;
     out[idx] = make_float2((float)((double)v.x * s), (float)((double)v.y * s));
   }
 };
 
-struct IterLosOp {  // fixed LOS: sum_a k_a² los_a delta_k / k² (src/iterative.jl:10-14, 53), then /M
+struct IterLosOp {
+  static const char* name() { return "kspace_kernel<IterLosOp>"; }  // fixed LOS: sum_a k_a² los_a delta_k / k² (src/iterative.jl:10-14, 53), then /M
   float2* out;
   float los[3];
   float invM;
@@ -102,7 +105,8 @@ struct IterLosOp {  // fixed LOS: sum_a k_a² los_a delta_k / k² (src/iterative
   }
 };
 
-struct IterPairOp {  // radial: k_i k_j delta_k / k² (src/iterative.jl:27), then /M
+struct IterPairOp {
+  static const char* name() { return "kspace_kernel<IterPairOp>"; }  // radial: k_i k_j delta_k / k² (src/iterative.jl:27), then /M
   float2* out;
   int i, j;
   float invM;
@@ -120,8 +124,59 @@ struct IterPairOp {  // radial: k_i k_j delta_k / k² (src/iterative.jl:27), the
   }
 };
 
+// All n_iter fixed-LOS RSD iterations in one pass.  For a constant line of sight iterate! is
+// linear and diagonal in k-space:  d^(n+1)_k = ds_k - fac_n mu_k d^(n)_k  with
+// mu_k = sum_a k_a^2 los_a / k^2, fac_1 = beta/(1+beta), fac_n = beta (src/iterative.jl:43-62),
+// so the per-iteration C2R/R2C round trips of the reference collapse into a per-mode recurrence.
+// MODE 0: input is rho_k (smoothing and (rho/mean-1)/bias applied here, src/recon.jl:53-55);
+// MODE 1: input is the R2C of delta_s.
+template <int MODE>
+struct FusedLosOp {
+  static const char* name() { return MODE == 0 ? "kspace_kernel<FusedLosOp<rho>>" : "kspace_kernel<FusedLosOp<delta>>"; }
+  float2* out_c2r;   // delta_final_k / M  (input of the C2R)
+  float2* out_keep;  // delta_final_k (unnormalised), or nullptr
+  float R2, bias;
+  const double* dc;
+  float los[3];
+  float beta;
+  int n_iter;
+  float invM;
+  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool is_dc) const {
+    float k2 = ksq(kx, ky, kz);
+    float dsx, dsy;
+    if (MODE == 0) {
+      // delta_k (unnormalised R2C convention) = rho_k g M / (A0 bias): mean(rho) = A0 / M
+      double s = gauss64(R2, k2) * __ldg(dc + 8);  // dc[8] = M / (A0 bias)
+      if (is_dc) s = 0.0;
+      dsx = (float)((double)v.x * s);
+      dsy = (float)((double)v.y * s);
+    } else {
+      dsx = v.x;
+      dsy = v.y;
+    }
+    float c = __fmul_rn(__fmul_rn(kx, kx), los[0]);
+    c = __fadd_rn(c, __fmul_rn(__fmul_rn(ky, ky), los[1]));
+    c = __fadd_rn(c, __fmul_rn(__fmul_rn(kz, kz), los[2]));
+    float mu = k2 > 0.f ? __fdiv_rn(c, k2) : 0.f;
+    float drx = dsx, dry = dsy;
+    for (int it = 1; it <= n_iter; it++) {
+      float fac = it == 1 ? __fdiv_rn(beta, __fadd_rn(1.0f, beta)) : beta;
+      float fm = __fmul_rn(fac, mu);
+      drx = __fsub_rn(dsx, __fmul_rn(fm, drx));
+      dry = __fsub_rn(dsy, __fmul_rn(fm, dry));
+    }
+    if (MODE == 1 && is_dc) {  // the reference zeroes the k=0 mode of the Hessian term only
+      drx = dsx;
+      dry = dsy;
+    }
+    out_c2r[idx] = make_float2(__fmul_rn(drx, invM), __fmul_rn(dry, invM));
+    if (out_keep) out_keep[idx] = make_float2(drx, dry);
+  }
+};
+
 template <bool POTENTIAL>
-struct DispOp {  // Psi_a = i k_a delta_k / k² (src/iterative.jl:268) or i k_a phi_k (src/multigrid.jl:767), /M
+struct DispOp {
+  static const char* name() { return POTENTIAL ? "kspace_kernel<DispOp<potential>>" : "kspace_kernel<DispOp<density>>"; }  // Psi_a = i k_a delta_k / k² (src/iterative.jl:268) or i k_a phi_k (src/multigrid.jl:767), /M
   float2* o0;
   float2* o1;
   float2* o2;
@@ -141,15 +196,18 @@ struct DispOp {  // Psi_a = i k_a delta_k / k² (src/iterative.jl:268) or i k_a 
   }
 };
 
-__global__ void stash_dc_kernel(const float2* __restrict__ ck, double* scal, int slot) {
-  scal[slot] = (double)ck[0].x;
+// scal[slot] = Re A_k[0] (= sum of the real mesh); scal[slot + 8] = mul / Re A_k[0]
+__global__ void stash_dc_kernel(const float2* __restrict__ ck, double* scal, int slot, double mul) {
+  double a0 = (double)ck[0].x;
+  scal[slot] = a0;
+  scal[slot + 8] = mul / a0;
 }
 
 template <class Op>
 static int run_kspace(baorec_ctx* ctx, const float2* in, Op op, cudaStream_t st) {
   size_t plane = (size_t)ctx->xh * ctx->ny;
   dim3 grid(cdiv(plane, KS_THREADS * KS_UNROLL), ctx->nz);
-  BR_LAUNCH(ctx, kspace_kernel<Op>, grid, KS_THREADS, 0, st, kgeom_of(ctx), in, op);
+  BR_LAUNCH_NAMED(ctx, Op::name(), kspace_kernel<Op>, grid, KS_THREADS, 0, st, kgeom_of(ctx), in, op);
   return BAOREC_OK;
 }
 
@@ -252,7 +310,7 @@ int setup_overdensity_into(baorec_ctx* ctx, const baorec_params* p, float* mesh,
   if (nr == 0) {
     BR_TRY(scatter(ctx, mesh, x, y, z, w, n, wrap, p->mas, st));
     BR_TRY(fft_r2c(ctx, mesh, ck0, st));
-    BR_LAUNCH(ctx, stash_dc_kernel, 1, 1, 0, st, ck0, ctx->d_scal, 0);
+    BR_LAUNCH(ctx, stash_dc_kernel, 1, 1, 0, st, ck0, ctx->d_scal, 0, 1.0 / (double)p->bias);
     SetupBoxOp op{ck0, R2, p->bias, ctx->d_scal};
     BR_TRY(run_kspace(ctx, ck0, op, st));
     BR_TRY(fft_c2r(ctx, ck0, delta_out, st));
@@ -264,11 +322,11 @@ int setup_overdensity_into(baorec_ctx* ctx, const baorec_params* p, float* mesh,
     BR_TRY(scatter(ctx, ran, rx, ry, rz, rw, nr, 0, p->mas, st));
     GaussOp op{ck0, R2, 1.0 / (double)ctx->M};
     BR_TRY(fft_r2c(ctx, mesh, ck0, st));
-    BR_LAUNCH(ctx, stash_dc_kernel, 1, 1, 0, st, ck0, ctx->d_scal, 0);
+    BR_LAUNCH(ctx, stash_dc_kernel, 1, 1, 0, st, ck0, ctx->d_scal, 0, 1.0);
     BR_TRY(run_kspace(ctx, ck0, op, st));
     BR_TRY(fft_c2r(ctx, ck0, mesh, st));
     BR_TRY(fft_r2c(ctx, ran, ck0, st));
-    BR_LAUNCH(ctx, stash_dc_kernel, 1, 1, 0, st, ck0, ctx->d_scal, 1);
+    BR_LAUNCH(ctx, stash_dc_kernel, 1, 1, 0, st, ck0, ctx->d_scal, 1, 1.0);
     BR_TRY(run_kspace(ctx, ck0, op, st));
     BR_TRY(fft_c2r(ctx, ck0, ran, st));
     BR_LAUNCH(ctx, randoms_combine_kernel, stream_grid(ctx->M, 256), 256, 0, st, delta_out, mesh, ran, ctx->d_scal,
@@ -328,19 +386,24 @@ int iterate(baorec_ctx* ctx, float* delta_r, const float* delta_s, int iter, flo
 }
 
 int displacement_meshes(baorec_ctx* ctx, const float* mesh, int algorithm, float* px, float* py, float* pz,
-                        cudaStream_t st) {
+                        cudaStream_t st, bool use_kcache) {
   float2 *ck0, *ck1, *ck2;
   BR_TRY(need_t(ctx, BUF_CK0, ctx->Mc, &ck0));
   BR_TRY(need_t(ctx, BUF_CK1, ctx->Mc, &ck1));
   BR_TRY(need_t(ctx, BUF_CK2, ctx->Mc, &ck2));
   const float invM = (float)(1.0 / (double)ctx->M);
-  BR_TRY(fft_r2c(ctx, mesh, ck0, st));
+  const float2* src = ck0;
+  if (use_kcache && ctx->kcache_valid && algorithm == BAOREC_ITERATIVE) {
+    src = (const float2*)ctx->bufs[BUF_CKCACHE].p;  // delta_k kept by the fused solve: no R2C needed
+  } else {
+    BR_TRY(fft_r2c(ctx, mesh, ck0, st));
+  }
   if (algorithm == BAOREC_MULTIGRID) {
     DispOp<true> op{ck0, ck1, ck2, invM};
-    BR_TRY(run_kspace(ctx, ck0, op, st));
+    BR_TRY(run_kspace(ctx, src, op, st));
   } else {
     DispOp<false> op{ck0, ck1, ck2, invM};
-    BR_TRY(run_kspace(ctx, ck0, op, st));
+    BR_TRY(run_kspace(ctx, src, op, st));
   }
   BR_TRY(fft_c2r(ctx, ck0, px, st));
   BR_TRY(fft_c2r(ctx, ck1, py, st));
@@ -351,6 +414,38 @@ int displacement_meshes(baorec_ctx* ctx, const float* mesh, int algorithm, float
 int reconstructed_overdensity(baorec_ctx* ctx, const baorec_params* p, float* mesh, float* x, float* y, float* z,
                               const float* w, int64_t n, float* rx, float* ry, float* rz, const float* rw, int64_t nr,
                               cudaStream_t st) {
+  ctx->kcache_valid = false;
+  const float* los = p->has_los ? p->los : nullptr;
+  const float invM = (float)(1.0 / (double)ctx->M);
+  if (los && ctx->opt_fuse_kspace) {
+    // Fixed line of sight: scatter -> R2C -> one fused k-space pass (smooth, normalise, all
+    // n_iter iterations) -> C2R.  2 transforms instead of 2 + 2 n_iter.
+    float2* ck0;
+    BR_TRY(need_t(ctx, BUF_CK0, ctx->Mc, &ck0));
+    float2* keep = nullptr;
+    if (ctx->want_kcache) BR_TRY(need_t(ctx, BUF_CKCACHE, ctx->Mc, &keep));
+    if (nr == 0) {
+      BR_TRY(reset_oob(ctx, st));
+      BR_TRY(scatter(ctx, mesh, x, y, z, w, n, 1, p->mas, st));
+      BR_TRY(fft_r2c(ctx, mesh, ck0, st));
+      BR_LAUNCH(ctx, stash_dc_kernel, 1, 1, 0, st, ck0, ctx->d_scal, 0, (double)ctx->M / (double)p->bias);
+      FusedLosOp<0> op{ck0, keep, p->smoothing_radius * p->smoothing_radius, p->bias, ctx->d_scal,
+                       {los[0], los[1], los[2]}, p->beta, p->n_iter, invM};
+      BR_TRY(run_kspace(ctx, ck0, op, st));
+      BR_TRY(fft_c2r(ctx, ck0, mesh, st));
+      BR_TRY(check_oob(ctx, st, "reconstructed_overdensity"));
+    } else {
+      float* ds;
+      BR_TRY(need_t(ctx, BUF_RS, ctx->M, &ds));
+      BR_TRY(setup_overdensity_into(ctx, p, mesh, ds, x, y, z, w, n, rx, ry, rz, rw, nr, 0, st));
+      BR_TRY(fft_r2c(ctx, ds, ck0, st));
+      FusedLosOp<1> op{ck0, keep, 0.f, p->bias, ctx->d_scal, {los[0], los[1], los[2]}, p->beta, p->n_iter, invM};
+      BR_TRY(run_kspace(ctx, ck0, op, st));
+      BR_TRY(fft_c2r(ctx, ck0, mesh, st));
+    }
+    ctx->kcache_valid = keep != nullptr;
+    return BAOREC_OK;
+  }
   float* ds;
   BR_TRY(need_t(ctx, BUF_RS, ctx->M, &ds));
   // delta_s lands in RS (no `copy(δ_r)`, src/recon.jl:101); the first iteration reads it directly.
@@ -359,7 +454,6 @@ int reconstructed_overdensity(baorec_ctx* ctx, const baorec_params* p, float* me
     BR_CUDA(cudaMemcpyAsync(mesh, ds, ctx->M * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return BAOREC_OK;
   }
-  const float* los = p->has_los ? p->los : nullptr;
   for (int it = 1; it <= p->n_iter; it++)
     BR_TRY(iterate_impl(ctx, it == 1 ? ds : mesh, mesh, ds, it, p->beta, los, st));
   return BAOREC_OK;

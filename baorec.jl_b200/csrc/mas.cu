@@ -4,6 +4,13 @@
 // Coordinate arithmetic uses explicit round-to-nearest intrinsics (__fsub_rn, __fmul_rn,
 // __fdiv_rn, __fadd_rn) so that nvcc never contracts it into FMAs: cell indices and weights
 // are bit-identical to the reference's Float32 CPU arithmetic (src/mas.jl:7-35, 224-255).
+//
+// Large catalogs go through a z-slab binning pass first (one counting sort on the base z
+// plane, ZG planes per bin): the scatter's float atomics and the gather's 8x3 loads then
+// walk the mesh one (ZG+1)-plane window at a time, which stays resident in the 126 MB L2,
+// so HBM sees each mesh sector once instead of once per particle.
+#include <string.h>
+
 #include "internal.cuh"
 
 namespace baorec {
@@ -97,80 +104,832 @@ __device__ __forceinline__ bool tsc_axis(float p, float mn, float L, int n, bool
   return true;
 }
 
+// ---- per-particle bodies ---------------------------------------------------------------------
+// Deposit one (already wrapped) particle.  Returns false if it is outside the mesh.
+template <int MAS>
+__device__ __forceinline__ bool deposit(float* __restrict__ rho, float px, float py, float pz, float ww,
+                                        const BoxGeom& g, bool wrap) {
+  const size_t nx = g.n[0], ny = g.n[1];
+  if (MAS == BAOREC_MAS_CIC) {
+    int x0, x1, y0, y1, z0, z1;
+    float wx0, wx1, wy0, wy1, wz0, wz1;
+    bool ok = cic_axis(px, g.mn[0], g.L[0], g.n[0], wrap, x0, x1, wx0, wx1);
+    ok = cic_axis(py, g.mn[1], g.L[1], g.n[1], wrap, y0, y1, wy0, wy1) && ok;
+    ok = cic_axis(pz, g.mn[2], g.L[2], g.n[2], wrap, z0, z1, wz0, wz1) && ok;
+    if (!ok) return false;
+    wx0 = __fmul_rn(wx0, ww);
+    wx1 = __fmul_rn(wx1, ww);
+    size_t r00 = ((size_t)z0 * ny + y0) * nx, r10 = ((size_t)z0 * ny + y1) * nx;
+    size_t r01 = ((size_t)z1 * ny + y0) * nx, r11 = ((size_t)z1 * ny + y1) * nx;
+    float a00 = __fmul_rn(wx0, wy0), a10 = __fmul_rn(wx1, wy0), a01 = __fmul_rn(wx0, wy1),
+          a11 = __fmul_rn(wx1, wy1);
+    atomicAdd(rho + r00 + x0, __fmul_rn(a00, wz0));
+    atomicAdd(rho + r00 + x1, __fmul_rn(a10, wz0));
+    atomicAdd(rho + r10 + x0, __fmul_rn(a01, wz0));
+    atomicAdd(rho + r01 + x0, __fmul_rn(a00, wz1));
+    atomicAdd(rho + r10 + x1, __fmul_rn(a11, wz0));
+    atomicAdd(rho + r01 + x1, __fmul_rn(a10, wz1));
+    atomicAdd(rho + r11 + x0, __fmul_rn(a01, wz1));
+    atomicAdd(rho + r11 + x1, __fmul_rn(a11, wz1));
+    return true;
+  } else {
+    int ix[3], iy[3], iz[3];
+    float wx[3], wy[3], wz[3];
+    bool ok = tsc_axis(px, g.mn[0], g.L[0], g.n[0], wrap, ix, wx);
+    ok = tsc_axis(py, g.mn[1], g.L[1], g.n[1], wrap, iy, wy) && ok;
+    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], wrap, iz, wz) && ok;
+    if (!ok) return false;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+#pragma unroll
+      for (int b = 0; b < 3; b++) {
+        size_t row = ((size_t)iz[c] * ny + iy[b]) * nx;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          float v = __fmul_rn(__fmul_rn(__fmul_rn(wx[a], ww), wy[b]), wz[c]);
+          atomicAdd(rho + row + ix[a], v);
+        }
+      }
+    }
+    return true;
+  }
+}
+
+struct GatherArgs {
+  const float* f[3];
+  const float* x;
+  const float* y;
+  const float* z;
+  float* o[3];
+  int64_t n;
+  int field;      // BAOREC_FIELD_*
+  int positions;  // write pos - shift
+  int has_los;
+  float los[3];
+  float fgrowth;
+  float4* sorted_out;  // if non-null: write (s0,s1,s2,0) at the record's sorted position instead of o[c][idx]
+};
+
+// read_shifts epilogue (src/recon.jl:277-304 / kernels :308-330) and optionally pos - shift (:376-378)
+template <int NF>
+__device__ __forceinline__ void shifts_epilogue(const GatherArgs& a, const float (&val)[NF], float px, float py,
+                                                float pz, int64_t out_idx, int64_t sorted_pos = -1) {
+  if (NF == 1) {
+    a.o[0][out_idx] = val[0];
+    return;
+  }
+  float s0 = val[0], s1 = val[NF > 1 ? 1 : 0], s2 = val[NF > 2 ? 2 : 0];
+  if (a.field != BAOREC_FIELD_DISP) {
+    float lx, ly, lz;
+    if (a.has_los) {
+      lx = a.los[0];
+      ly = a.los[1];
+      lz = a.los[2];
+    } else {
+      float dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
+      lx = __fdiv_rn(px, dist);
+      ly = __fdiv_rn(py, dist);
+      lz = __fdiv_rn(pz, dist);
+    }
+    float dot = __fadd_rn(__fadd_rn(__fmul_rn(s0, lx), __fmul_rn(s1, ly)), __fmul_rn(s2, lz));
+    float fd = __fmul_rn(a.fgrowth, dot);
+    float r0 = __fmul_rn(fd, lx), r1 = __fmul_rn(fd, ly), r2 = __fmul_rn(fd, lz);
+    if (a.field == BAOREC_FIELD_RSD) {
+      s0 = r0;
+      s1 = r1;
+      s2 = r2;
+    } else {
+      s0 = __fadd_rn(s0, r0);
+      s1 = __fadd_rn(s1, r1);
+      s2 = __fadd_rn(s2, r2);
+    }
+  }
+  if (a.positions) {
+    s0 = __fsub_rn(px, s0);
+    s1 = __fsub_rn(py, s1);
+    s2 = __fsub_rn(pz, s2);
+  }
+  if (a.sorted_out && sorted_pos >= 0) {
+    a.sorted_out[sorted_pos] = make_float4(s0, s1, s2, 0.f);  // coalesced; un-permuted by unsort_kernel
+    return;
+  }
+  a.o[0][out_idx] = s0;
+  if (NF > 1) a.o[1][out_idx] = s1;
+  if (NF > 2) a.o[2][out_idx] = s2;
+}
+
+// read_cic! (src/mas.jl:258-265): sum of field*wx*wy*wz, left-associated, in the order
+// ddd,ddu,dud,duu,udd,udu,uud,uuu (letters = x,y,z); then the read_shifts epilogue
+// (src/recon.jl:277-304 / kernels :308-330) and optionally pos - shift (:376-378).
+template <int NF, int MAS>
+__device__ __forceinline__ bool gather_one(const GatherArgs& a, const BoxGeom& g, float px, float py, float pz,
+                                           int64_t out_idx) {
+  float val[NF];
+  const size_t nx = g.n[0], ny = g.n[1];
+  bool ok;
+  if (MAS == BAOREC_MAS_CIC) {
+    int xd, xu, yd, yu, zd, zu;
+    float dx, ux, dy, uy, dz, uz;
+    ok = gather_axis(px, g.mn[0], g.L[0], g.cell[0], g.n[0], false, xd, xu, dx, ux);
+    ok = gather_axis(py, g.mn[1], g.L[1], g.cell[1], g.n[1], false, yd, yu, dy, uy) && ok;
+    ok = gather_axis(pz, g.mn[2], g.L[2], g.cell[2], g.n[2], false, zd, zu, dz, uz) && ok;
+    if (ok) {
+      size_t rdd = ((size_t)zd * ny + yd) * nx, rdu = ((size_t)zu * ny + yd) * nx;
+      size_t rud = ((size_t)zd * ny + yu) * nx, ruu = ((size_t)zu * ny + yu) * nx;
+      float l[NF][8];
+#pragma unroll
+      for (int c = 0; c < NF; c++) {  // issue all loads first (memory-level parallelism)
+        const float* f = a.f[c];
+        l[c][0] = __ldg(f + rdd + xd);
+        l[c][1] = __ldg(f + rdu + xd);
+        l[c][2] = __ldg(f + rud + xd);
+        l[c][3] = __ldg(f + ruu + xd);
+        l[c][4] = __ldg(f + rdd + xu);
+        l[c][5] = __ldg(f + rdu + xu);
+        l[c][6] = __ldg(f + rud + xu);
+        l[c][7] = __ldg(f + ruu + xu);
+      }
+#pragma unroll
+      for (int c = 0; c < NF; c++) {
+        float v;
+        v = __fmul_rn(__fmul_rn(__fmul_rn(l[c][0], dx), dy), dz);
+        v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(l[c][1], dx), dy), uz));
+        v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(l[c][2], dx), uy), dz));
+        v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(l[c][3], dx), uy), uz));
+        v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(l[c][4], ux), dy), dz));
+        v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(l[c][5], ux), dy), uz));
+        v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(l[c][6], ux), uy), dz));
+        v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(l[c][7], ux), uy), uz));
+        val[c] = v;
+      }
+    }
+  } else {
+    int ix[3], iy[3], iz[3];
+    float wx[3], wy[3], wz[3];
+    ok = tsc_axis(px, g.mn[0], g.L[0], g.n[0], true, ix, wx);
+    ok = tsc_axis(py, g.mn[1], g.L[1], g.n[1], true, iy, wy) && ok;
+    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], true, iz, wz) && ok;
+    if (ok) {
+#pragma unroll
+      for (int c = 0; c < NF; c++) val[c] = 0.f;
+#pragma unroll
+      for (int oz = 0; oz < 3; oz++)
+#pragma unroll
+        for (int oy = 0; oy < 3; oy++) {
+          size_t row = ((size_t)iz[oz] * ny + iy[oy]) * nx;
+#pragma unroll
+          for (int ox = 0; ox < 3; ox++)
+#pragma unroll
+            for (int c = 0; c < NF; c++)
+              val[c] = __fadd_rn(
+                  val[c], __fmul_rn(__fmul_rn(__fmul_rn(__ldg(a.f[c] + row + ix[ox]), wx[ox]), wy[oy]), wz[oz]));
+        }
+    }
+  }
+  if (!ok) {
+#pragma unroll
+    for (int c = 0; c < NF; c++) val[c] = 0.f;
+  }
+  shifts_epilogue<NF>(a, val, px, py, pz, out_idx);
+  return ok;
+}
+
+// ---- direct (unbinned) kernels: one thread per particle in catalog order -------------------------
+template <int MAS>
 __global__ void __launch_bounds__(256)
-cic_scatter_kernel(float* __restrict__ rho, float* __restrict__ x, float* __restrict__ y, float* __restrict__ z,
-                   const float* __restrict__ w, int64_t n, BoxGeom g, int wrap, unsigned long long* oob) {
+scatter_direct_kernel(float* __restrict__ rho, float* __restrict__ x, float* __restrict__ y, float* __restrict__ z,
+                      const float* __restrict__ w, int64_t n, BoxGeom g, int wrap, unsigned long long* oob) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float px = x[i], py = y[i], pz = z[i];
-  if (wrap) {
+  if (wrap && MAS == BAOREC_MAS_CIC) {
     float qx = wrap_pos(px, g.mn[0], g.L[0]);
     float qy = wrap_pos(py, g.mn[0], g.L[0]);
     float qz = wrap_pos(pz, g.mn[0], g.L[0]);
     if (qx != px) x[i] = qx;  // write-back like the reference (src/mas.jl:57-59)
     if (qy != py) y[i] = qy;
     if (qz != pz) z[i] = qz;
+    if (qx != px || qy != py || qz != pz) atomicAdd(oob + 1, 1ULL);
     px = qx;
     py = qy;
     pz = qz;
   }
-  int x0, x1, y0, y1, z0, z1;
-  float wx0, wx1, wy0, wy1, wz0, wz1;
-  bool ok = cic_axis(px, g.mn[0], g.L[0], g.n[0], wrap, x0, x1, wx0, wx1);
-  ok = cic_axis(py, g.mn[1], g.L[1], g.n[1], wrap, y0, y1, wy0, wy1) && ok;
-  ok = cic_axis(pz, g.mn[2], g.L[2], g.n[2], wrap, z0, z1, wz0, wz1) && ok;
-  if (!ok) {
-    atomicAdd(oob, 1ULL);
-    return;
-  }
-  float ww = w[i];
-  wx0 = __fmul_rn(wx0, ww);
-  wx1 = __fmul_rn(wx1, ww);
-  size_t nx = g.n[0], ny = g.n[1];
-  size_t r00 = ((size_t)z0 * ny + y0) * nx, r10 = ((size_t)z0 * ny + y1) * nx;
-  size_t r01 = ((size_t)z1 * ny + y0) * nx, r11 = ((size_t)z1 * ny + y1) * nx;
-  float a00 = __fmul_rn(wx0, wy0), a10 = __fmul_rn(wx1, wy0), a01 = __fmul_rn(wx0, wy1), a11 = __fmul_rn(wx1, wy1);
-  atomicAdd(rho + r00 + x0, __fmul_rn(a00, wz0));
-  atomicAdd(rho + r00 + x1, __fmul_rn(a10, wz0));
-  atomicAdd(rho + r10 + x0, __fmul_rn(a01, wz0));
-  atomicAdd(rho + r01 + x0, __fmul_rn(a00, wz1));
-  atomicAdd(rho + r10 + x1, __fmul_rn(a11, wz0));
-  atomicAdd(rho + r01 + x1, __fmul_rn(a10, wz1));
-  atomicAdd(rho + r11 + x0, __fmul_rn(a01, wz1));
-  atomicAdd(rho + r11 + x1, __fmul_rn(a11, wz1));
+  if (!deposit<MAS>(rho, px, py, pz, w[i], g, wrap != 0)) atomicAdd(oob, 1ULL);
 }
 
+template <int NF, int MAS>
+__global__ void __launch_bounds__(256) gather_direct_kernel(GatherArgs a, BoxGeom g, unsigned long long* oob) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  if (!gather_one<NF, MAS>(a, g, a.x[i], a.y[i], a.z[i], i)) atomicAdd(oob, 1ULL);
+}
+
+// ---- z-slab binning ---------------------------------------------------------------------------------
+// Key = base z plane / zg (scatter: cic z0 after wrap, or TSC centre; gather: lower z index).
+// Out-of-box particles get key = nbins (a trash bin that the sorted kernels never visit).
+constexpr int BIN_THREADS = 256;
+constexpr int BIN_PPT = 8;  // particles per thread in the reorder kernel
+constexpr int BIN_MAX = 1024;
+
+enum { BIN_SCATTER = 0, BIN_GATHER = 1 };
+
+template <int MODE, int MAS>
+__device__ __forceinline__ int bin_key(float& px, float& py, float& pz, const BoxGeom& g, int wrap, int zg, int nbins,
+                                       bool& wrapped) {
+  wrapped = false;
+  bool ok;
+  int zb;
+  if (MODE == BIN_SCATTER && MAS == BAOREC_MAS_CIC) {
+    if (wrap) {
+      float qx = wrap_pos(px, g.mn[0], g.L[0]), qy = wrap_pos(py, g.mn[0], g.L[0]),
+            qz = wrap_pos(pz, g.mn[0], g.L[0]);
+      wrapped = (qx != px) || (qy != py) || (qz != pz);
+      px = qx;
+      py = qy;
+      pz = qz;
+    }
+    int i0, i1;
+    float w0, w1;
+    ok = cic_axis(px, g.mn[0], g.L[0], g.n[0], wrap, i0, i1, w0, w1);
+    ok = cic_axis(py, g.mn[1], g.L[1], g.n[1], wrap, i0, i1, w0, w1) && ok;
+    ok = cic_axis(pz, g.mn[2], g.L[2], g.n[2], wrap, i0, i1, w0, w1) && ok;
+    zb = i0;
+  } else if (MAS == BAOREC_MAS_TSC) {
+    int idx[3];
+    float w[3];
+    bool wr = MODE == BIN_GATHER ? true : (wrap != 0);
+    ok = tsc_axis(px, g.mn[0], g.L[0], g.n[0], wr, idx, w);
+    ok = tsc_axis(py, g.mn[1], g.L[1], g.n[1], wr, idx, w) && ok;
+    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], wr, idx, w) && ok;
+    zb = idx[1];
+  } else {
+    int id, iu;
+    float wd, wu;
+    ok = gather_axis(px, g.mn[0], g.L[0], g.cell[0], g.n[0], false, id, iu, wd, wu);
+    ok = gather_axis(py, g.mn[1], g.L[1], g.cell[1], g.n[1], false, id, iu, wd, wu) && ok;
+    ok = gather_axis(pz, g.mn[2], g.L[2], g.cell[2], g.n[2], false, id, iu, wd, wu) && ok;
+    zb = id;
+  }
+  return ok ? zb / zg : nbins;
+}
+
+template <int MODE, int MAS>
+__global__ void __launch_bounds__(BIN_THREADS)
+bin_count_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z, int64_t n,
+                 BoxGeom g, int wrap, int zg, int nbins, unsigned* __restrict__ counts) {
+  __shared__ unsigned s_cnt[BIN_MAX + 1];
+  for (int t = threadIdx.x; t <= nbins; t += blockDim.x) s_cnt[t] = 0;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float px = x[i], py = y[i], pz = z[i];
+    bool wr;
+    int k = bin_key<MODE, MAS>(px, py, pz, g, wrap, zg, nbins, wr);
+    atomicAdd(&s_cnt[k], 1u);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t <= nbins; t += blockDim.x)
+    if (s_cnt[t]) atomicAdd(counts + t, s_cnt[t]);
+}
+
+// exclusive scan of counts[0..nbins] into cursor[0..nbins] (single block)
+__global__ void bin_scan_kernel(const unsigned* __restrict__ counts, unsigned* __restrict__ cursor,
+                                unsigned* __restrict__ starts, int nbins, unsigned long long* oob) {
+  __shared__ unsigned s[BIN_MAX + 2];
+  int t = threadIdx.x;
+  for (int i = t; i <= nbins; i += blockDim.x) s[i] = counts[i];
+  __syncthreads();
+  if (t == 0) {
+    unsigned acc = 0;
+    for (int i = 0; i <= nbins; i++) {
+      unsigned c = s[i];
+      s[i] = acc;
+      acc += c;
+    }
+    s[nbins + 1] = acc;
+    if (counts[nbins]) atomicAdd(oob, (unsigned long long)counts[nbins]);
+  }
+  __syncthreads();
+  for (int i = t; i <= nbins + 1; i += blockDim.x) {
+    if (i <= nbins) cursor[i] = s[i];
+    starts[i] = s[i];
+  }
+}
+
+// Reorder into float4 records: scatter (x,y,z,w) ; gather (x,y,z, original index bits).
+template <int MODE, int MAS>
+__global__ void __launch_bounds__(BIN_THREADS)
+bin_reorder_kernel(float* __restrict__ x, float* __restrict__ y, float* __restrict__ z, const float* __restrict__ w,
+                   int64_t n, BoxGeom g, int wrap, int zg, int nbins, unsigned* __restrict__ cursor,
+                   float4* __restrict__ rec, unsigned long long* oob) {
+  __shared__ unsigned s_cnt[BIN_MAX + 1];
+  __shared__ unsigned s_base[BIN_MAX + 1];
+  for (int t = threadIdx.x; t <= nbins; t += blockDim.x) s_cnt[t] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * (BIN_THREADS * BIN_PPT);
+  float4 r[BIN_PPT];
+  int key[BIN_PPT];
+  unsigned rank[BIN_PPT];
+#pragma unroll
+  for (int u = 0; u < BIN_PPT; u++) {
+    int64_t i = base + u * BIN_THREADS + threadIdx.x;
+    key[u] = -1;
+    if (i < n) {
+      float px = x[i], py = y[i], pz = z[i];
+      float ox = px, oy = py, oz = pz;
+      bool wr;
+      key[u] = bin_key<MODE, MAS>(px, py, pz, g, wrap, zg, nbins, wr);
+      if (MODE == BIN_SCATTER && wr) {  // cic! writes the wrapped position back (src/mas.jl:57-59)
+        if (px != ox) x[i] = px;
+        if (py != oy) y[i] = py;
+        if (pz != oz) z[i] = pz;
+        atomicAdd(oob + 1, 1ULL);
+      }
+      r[u] = make_float4(px, py, pz, MODE == BIN_SCATTER ? w[i] : __uint_as_float((unsigned)i));
+      rank[u] = atomicAdd(&s_cnt[key[u]], 1u);
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t <= nbins; t += blockDim.x)
+    if (s_cnt[t]) s_base[t] = atomicAdd(cursor + t, s_cnt[t]);
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < BIN_PPT; u++)
+    if (key[u] >= 0) rec[s_base[key[u]] + rank[u]] = r[u];
+}
+
+template <int MAS>
 __global__ void __launch_bounds__(256)
-tsc_scatter_kernel(float* __restrict__ rho, const float* __restrict__ x, const float* __restrict__ y,
-                   const float* __restrict__ z, const float* __restrict__ w, int64_t n, BoxGeom g, int wrap,
-                   unsigned long long* oob) {
+scatter_sorted_kernel(float* __restrict__ rho, const float4* __restrict__ rec, int64_t n_valid, BoxGeom g, int wrap) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_valid) return;
+  float4 p = rec[i];
+  deposit<MAS>(rho, p.x, p.y, p.z, p.w, g, wrap != 0);
+}
+
+template <int NF, int MAS>
+__global__ void __launch_bounds__(256)
+gather_sorted_kernel(GatherArgs a, const float4* __restrict__ rec, int64_t n_valid, BoxGeom g) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_valid) return;
+  float4 p = rec[i];
+  gather_one<NF, MAS>(a, g, p.x, p.y, p.z, (int64_t)__float_as_uint(p.w));
+}
+
+// zero-fill the outputs of out-of-box particles in the binned gather (they sit in the trash bin)
+__global__ void gather_trash_kernel(GatherArgs a, const float4* __restrict__ rec, int64_t first, int64_t n_total,
+                                    int nf) {
+  int64_t i = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_total) return;
+  int64_t idx = (int64_t)__float_as_uint(rec[i].w);
+  for (int c = 0; c < nf; c++) a.o[c][idx] = 0.f;
+}
+
+
+// ---- fine (tile) binning for the gather ---------------------------------------------------------
+// Key = (z plane, y / TILE_Y, x / TILE_X) in that order.  Consecutive records then share the
+// 2 x (TILE_Y+1) x (TILE_X+1) x 3-field window of their tile (~28 KB), which lives in L1 while
+// a thread block works through it; successive tiles along x, y and z reuse the neighbouring rows
+// and plane from L2.  Counting sort with one global counter per tile.
+constexpr int TILE_X = 128;
+constexpr int TILE_Y = 8;
+
+struct TileGeom {
+  int nxc, nyc;       // tiles per row / per plane column
+  unsigned ntiles;    // nz * nyc * nxc  (the trash bin has index ntiles)
+};
+
+template <int MAS>
+__device__ __forceinline__ unsigned tile_key(float px, float py, float pz, const BoxGeom& g, const TileGeom& t) {
+  int ix, iy, iz;
+  bool ok;
+  if (MAS == BAOREC_MAS_TSC) {
+    int idx[3];
+    float w[3];
+    ok = tsc_axis(px, g.mn[0], g.L[0], g.n[0], true, idx, w);
+    ix = idx[1];
+    ok = tsc_axis(py, g.mn[1], g.L[1], g.n[1], true, idx, w) && ok;
+    iy = idx[1];
+    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], true, idx, w) && ok;
+    iz = idx[1];
+  } else {
+    int iu;
+    float wd, wu;
+    ok = gather_axis(px, g.mn[0], g.L[0], g.cell[0], g.n[0], false, ix, iu, wd, wu);
+    ok = gather_axis(py, g.mn[1], g.L[1], g.cell[1], g.n[1], false, iy, iu, wd, wu) && ok;
+    ok = gather_axis(pz, g.mn[2], g.L[2], g.cell[2], g.n[2], false, iz, iu, wd, wu) && ok;
+  }
+  if (!ok) return t.ntiles;
+  return ((unsigned)iz * t.nyc + (unsigned)(iy / TILE_Y)) * t.nxc + (unsigned)(ix / TILE_X);
+}
+
+template <int MAS>
+__global__ void __launch_bounds__(256)
+tile_count_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z, int64_t n,
+                  BoxGeom g, TileGeom t, unsigned* __restrict__ counts) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int ix[3], iy[3], iz[3];
-  float wx[3], wy[3], wz[3];
-  bool ok = tsc_axis(x[i], g.mn[0], g.L[0], g.n[0], wrap, ix, wx);
-  ok = tsc_axis(y[i], g.mn[1], g.L[1], g.n[1], wrap, iy, wy) && ok;
-  ok = tsc_axis(z[i], g.mn[2], g.L[2], g.n[2], wrap, iz, wz) && ok;
-  if (!ok) {
-    atomicAdd(oob, 1ULL);
-    return;
+  atomicAdd(counts + tile_key<MAS>(x[i], y[i], z[i], g, t), 1u);
+}
+
+// exclusive scan of m counters, 3 phases (SCAN_CHUNK elements per block)
+constexpr int SCAN_CHUNK = 2048;
+__global__ void __launch_bounds__(256) scan_partial_kernel(const unsigned* __restrict__ in, unsigned* __restrict__ sums,
+                                                           unsigned m) {
+  __shared__ unsigned s[8];
+  unsigned base = blockIdx.x * SCAN_CHUNK, acc = 0;
+  for (unsigned i = threadIdx.x; i < SCAN_CHUNK; i += 256)
+    if (base + i < m) acc += in[base + i];
+  acc = __reduce_add_sync(0xffffffffu, acc);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = 0;
+    for (int w = 0; w < 8; w++) t += s[w];
+    sums[blockIdx.x] = t;
   }
-  float ww = w[i];
-  size_t nx = g.n[0], ny = g.n[1];
+}
+__global__ void scan_sums_kernel(unsigned* sums, unsigned nblocks, unsigned* total) {
+  // single thread: nblocks is at most a few thousand
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned acc = 0;
+    for (unsigned b = 0; b < nblocks; b++) {
+      unsigned c = sums[b];
+      sums[b] = acc;
+      acc += c;
+    }
+    *total = acc;
+  }
+}
+__global__ void __launch_bounds__(256) scan_final_kernel(const unsigned* __restrict__ in,
+                                                         const unsigned* __restrict__ sums,
+                                                         unsigned* __restrict__ out, unsigned* __restrict__ out2,
+                                                         unsigned m) {
+  // each thread scans 8 consecutive elements; block-level exclusive scan of the thread totals
+  __shared__ unsigned s_warp[8];
+  const unsigned base = blockIdx.x * SCAN_CHUNK + threadIdx.x * 8;
+  unsigned v[8], tot = 0;
 #pragma unroll
-  for (int c = 0; c < 3; c++) {
+  for (int k = 0; k < 8; k++) {
+    v[k] = (base + k < m) ? in[base + k] : 0u;
+    tot += v[k];
+  }
+  unsigned incl = tot;
 #pragma unroll
-    for (int b = 0; b < 3; b++) {
-      size_t row = ((size_t)iz[c] * ny + iy[b]) * nx;
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((threadIdx.x & 31) >= o) incl += up;
+  }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  unsigned woff = 0;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); w++) woff += s_warp[w];
+  unsigned run = sums[blockIdx.x] + woff + incl - tot;
 #pragma unroll
-      for (int a = 0; a < 3; a++) {
-        float v = __fmul_rn(__fmul_rn(__fmul_rn(wx[a], ww), wy[b]), wz[c]);
-        atomicAdd(rho + row + ix[a], v);
+  for (int k = 0; k < 8; k++) {
+    if (base + k < m) {
+      out[base + k] = run;
+      out2[base + k] = run;
+    }
+    run += v[k];
+  }
+}
+
+template <int MAS>
+__global__ void __launch_bounds__(256)
+tile_reorder_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z, int64_t n,
+                    BoxGeom g, TileGeom t, unsigned* __restrict__ cursor, float4* __restrict__ rec,
+                    unsigned* __restrict__ inv) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float px = x[i], py = y[i], pz = z[i];
+  unsigned k = tile_key<MAS>(px, py, pz, g, t);
+  unsigned dst = atomicAdd(cursor + k, 1u);
+  rec[dst] = make_float4(px, py, pz, __uint_as_float((unsigned)i));
+  inv[i] = dst;  // coalesced: where particle i went
+}
+
+
+// Tile gather: one thread block per (z, y/TILE_Y, x/TILE_X) tile.  The 2 x (TILE_Y+1) x (TILE_X+1)
+// window of each field is staged in shared memory with coalesced row loads (one 128 B line per
+// warp instruction instead of one line per lane), then every particle of the tile reads its 8 x NF
+// values from shared memory.  Same arithmetic and order as gather_one -> identical results.
+constexpr int TILE_WXP = TILE_X + 4;  // padded row length in shared memory
+
+template <int NF>
+__global__ void __launch_bounds__(128)
+gather_tile_kernel(GatherArgs a, const float4* __restrict__ rec, const unsigned* __restrict__ starts, BoxGeom g,
+                   TileGeom t) {
+  __shared__ __align__(16) float sm[NF][2][TILE_Y + 1][TILE_WXP];
+  const unsigned tile = blockIdx.x;
+  const unsigned beg = starts[tile], end = starts[tile + 1];
+  if (beg == end) return;
+  const int nx = g.n[0], ny = g.n[1], nz = g.n[2];
+  const int tx = tile % t.nxc;
+  const unsigned r = tile / t.nxc;
+  const int ty = r % t.nyc;
+  const int iz = r / t.nyc;
+  const int x0 = tx * TILE_X, y0 = ty * TILE_Y;
+  const int wx = min(TILE_X, nx - x0), wy = min(TILE_Y, ny - y0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool fast = (wx == TILE_X) && (wy == TILE_Y) && (nx % 4 == 0) &&
+                    ((((uintptr_t)a.f[0] | (uintptr_t)a.f[NF > 1 ? 1 : 0] | (uintptr_t)a.f[NF > 2 ? 2 : 0]) & 15) == 0);
+  if (fast) {
+    // One warp per row, rows dealt round-robin to the 4 warps with compile-time indices (no
+    // integer division); each lane issues one 16-byte cp.async (LDGSTS) per row straight into
+    // shared memory -- no register staging, all of a warp's rows in flight at once.
+    int xe = x0 + TILE_X;
+    if (xe >= nx) xe -= nx;
+    int zrow[2];
+    zrow[0] = iz;
+    zrow[1] = iz + 1 >= nz ? 0 : iz + 1;
+#pragma unroll
+    for (int r = 0; r < NF * 2 * (TILE_Y + 1); r++) {
+      if ((r & 3) != warp) continue;
+      constexpr int RY = TILE_Y + 1;
+      const int py = r % RY, pz = (r / RY) & 1, f = r / (2 * RY);
+      int yy = y0 + py;
+      if (yy >= ny) yy -= ny;
+      const float* fld = f == 0 ? a.f[0] : (f == 1 ? a.f[NF > 1 ? 1 : 0] : a.f[NF > 2 ? 2 : 0]);
+      const float* src = fld + ((size_t)zrow[pz] * ny + yy) * nx;
+      float* dst = &sm[f][pz][py][0];
+      unsigned d16 = (unsigned)__cvta_generic_to_shared(dst + 4 * lane);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d16), "l"(src + x0 + 4 * lane));
+      if (lane == 0) {
+        unsigned d4 = (unsigned)__cvta_generic_to_shared(dst + TILE_X);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d4), "l"(src + xe));
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else {
+    const int nrows = NF * 2 * (wy + 1);
+    for (int row = warp; row < nrows; row += 4) {
+      int py = row % (wy + 1);
+      int q = row / (wy + 1);
+      int pz = q & 1, f = q >> 1;
+      int zz = iz + pz;
+      if (zz >= nz) zz -= nz;
+      int yy = y0 + py;
+      if (yy >= ny) yy -= ny;
+      const float* fld = f == 0 ? a.f[0] : (f == 1 ? a.f[NF > 1 ? 1 : 0] : a.f[NF > 2 ? 2 : 0]);
+      const float* src = fld + ((size_t)zz * ny + yy) * nx;
+      float* dst = &sm[f][pz][py][0];
+      for (int c = lane; c <= wx; c += 32) {
+        int xx = x0 + c;
+        if (xx >= nx) xx -= nx;
+        dst[c] = __ldg(src + xx);
       }
     }
   }
+  __syncthreads();
+  for (unsigned i = beg + threadIdx.x; i < end; i += 128) {
+    float4 p = rec[i];
+    const float px = p.x, py = p.y, pz = p.z;
+    const int64_t out_idx = (int64_t)__float_as_uint(p.w);
+    int xd, xu, yd, yu, zd, zu;
+    float dx, ux, dy, uy, dz, uz;
+    gather_axis(px, g.mn[0], g.L[0], g.cell[0], nx, false, xd, xu, dx, ux);
+    gather_axis(py, g.mn[1], g.L[1], g.cell[1], ny, false, yd, yu, dy, uy);
+    gather_axis(pz, g.mn[2], g.L[2], g.cell[2], nz, false, zd, zu, dz, uz);
+    const int lx = xd - x0, ly = yd - y0;
+    float val[NF];
+#pragma unroll
+    for (int c = 0; c < NF; c++) {
+      float v;
+      v = __fmul_rn(__fmul_rn(__fmul_rn(sm[c][0][ly][lx], dx), dy), dz);
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(sm[c][1][ly][lx], dx), dy), uz));
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(sm[c][0][ly + 1][lx], dx), uy), dz));
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(sm[c][1][ly + 1][lx], dx), uy), uz));
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(sm[c][0][ly][lx + 1], ux), dy), dz));
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(sm[c][1][ly][lx + 1], ux), dy), uz));
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(sm[c][0][ly + 1][lx + 1], ux), uy), dz));
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(sm[c][1][ly + 1][lx + 1], ux), uy), uz));
+      val[c] = v;
+    }
+    shifts_epilogue<NF>(a, val, px, py, pz, out_idx, (int64_t)i);
+  }
 }
 
+// out[c][i] = sorted_out[inv[i]].c : coalesced index read and output writes, one random 16 B read.
+__global__ void __launch_bounds__(256)
+unsort_kernel(GatherArgs a, const float4* __restrict__ sorted_out, const unsigned* __restrict__ inv, int64_t n,
+              int64_t n_valid) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned j = inv[i];
+  float4 v = (int64_t)j < n_valid ? __ldg(sorted_out + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  a.o[0][i] = v.x;
+  a.o[1][i] = v.y;
+  a.o[2][i] = v.z;
+}
+
+struct BinResult {
+  float4* rec;
+  int64_t n_valid;
+  const unsigned* starts = nullptr;  // tile binning: first record of every tile (+ trash, + end)
+  unsigned ntiles = 0;
+  unsigned* inv = nullptr;           // tile binning: sorted position of every particle
+};
+
+// Builds the sorted records.  Synchronises the stream once (to learn n_valid).
+template <int MODE>
+static int bin_particles(baorec_ctx* ctx, float* x, float* y, float* z, const float* w, int64_t n, int wrap, int mas,
+                         cudaStream_t st, BinResult* out) {
+  BoxGeom g = geom_of(ctx);
+  int zg = MODE == BIN_SCATTER ? ctx->opt_zg_scatter : ctx->opt_zg_gather;
+  if (zg <= 0) zg = MODE == BIN_SCATTER ? (ctx->nz + 511) / 512 : 1;  // auto: window << L2
+  if (zg < 1) zg = 1;
+  int nbins = (ctx->nz + zg - 1) / zg;
+  if (nbins > BIN_MAX) {
+    zg = (ctx->nz + BIN_MAX - 1) / BIN_MAX;
+    nbins = (ctx->nz + zg - 1) / zg;
+  }
+  unsigned* cnt;
+  float4* rec;
+  BR_TRY(need_t(ctx, BUF_BINKEY, (size_t)3 * (BIN_MAX + 2), &cnt));
+  BR_TRY(need_t(ctx, BUF_BINIDX, (size_t)n, &rec));
+  unsigned* cursor = cnt + (BIN_MAX + 2);
+  unsigned* starts = cnt + 2 * (BIN_MAX + 2);
+  BR_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * (BIN_MAX + 2), st));
+  unsigned grid_c = cdiv((size_t)n, BIN_THREADS * 4);
+  if (grid_c > 148 * 8) grid_c = 148 * 8;
+  unsigned grid_r = cdiv((size_t)n, BIN_THREADS * BIN_PPT);
+  const bool tsc = mas == BAOREC_MAS_TSC;
+  if (tsc) {
+    BR_LAUNCH(ctx, (bin_count_kernel<MODE, BAOREC_MAS_TSC>), grid_c, BIN_THREADS, 0, st, x, y, z, n, g, wrap, zg, nbins,
+              cnt);
+  } else {
+    BR_LAUNCH(ctx, (bin_count_kernel<MODE, BAOREC_MAS_CIC>), grid_c, BIN_THREADS, 0, st, x, y, z, n, g, wrap, zg, nbins,
+              cnt);
+  }
+  BR_LAUNCH(ctx, bin_scan_kernel, 1, 256, 0, st, cnt, cursor, starts, nbins, ctx->d_oob);
+  if (tsc) {
+    BR_LAUNCH(ctx, (bin_reorder_kernel<MODE, BAOREC_MAS_TSC>), grid_r, BIN_THREADS, 0, st, x, y, z, w, n, g, wrap, zg,
+              nbins, cursor, rec, ctx->d_oob);
+  } else {
+    BR_LAUNCH(ctx, (bin_reorder_kernel<MODE, BAOREC_MAS_CIC>), grid_r, BIN_THREADS, 0, st, x, y, z, w, n, g, wrap, zg,
+              nbins, cursor, rec, ctx->d_oob);
+  }
+  unsigned h_valid = 0;
+  BR_CUDA(cudaMemcpyAsync(&h_valid, starts + nbins, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  BR_CUDA(cudaStreamSynchronize(st));
+  out->rec = rec;
+  out->n_valid = (int64_t)h_valid;
+  return BAOREC_OK;
+}
+
+// Fine binning for the gather (see TILE_X / TILE_Y).  Synchronises the stream once.
+static int bin_tiles(baorec_ctx* ctx, const float* x, const float* y, const float* z, int64_t n, int mas,
+                     cudaStream_t st, BinResult* out) {
+  BoxGeom g = geom_of(ctx);
+  TileGeom t;
+  t.nxc = (ctx->nx + TILE_X - 1) / TILE_X;
+  t.nyc = (ctx->ny + TILE_Y - 1) / TILE_Y;
+  t.ntiles = (unsigned)ctx->nz * t.nyc * t.nxc;
+  const unsigned m = t.ntiles + 1;  // + trash bin
+  const unsigned nsb = cdiv(m, SCAN_CHUNK);
+  unsigned* cnt;
+  float4* rec;
+  BR_TRY(need_t(ctx, BUF_BINTMP, (size_t)3 * m + nsb + 16, &cnt));
+  BR_TRY(need_t(ctx, BUF_BINIDX, (size_t)n, &rec));
+  unsigned* inv;
+  BR_TRY(need_t(ctx, BUF_BININV, (size_t)n, &inv));
+  unsigned* cursor = cnt + m;
+  unsigned* starts = cursor + m;  // m + 1 entries: starts[m] = n
+  unsigned* sums = starts + m + 1;
+  unsigned* total = sums + nsb;
+  BR_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * m, st));
+  const unsigned grid = cdiv((size_t)n, 256);
+  const bool tsc = mas == BAOREC_MAS_TSC;
+  if (tsc) BR_LAUNCH(ctx, tile_count_kernel<BAOREC_MAS_TSC>, grid, 256, 0, st, x, y, z, n, g, t, cnt);
+  else BR_LAUNCH(ctx, tile_count_kernel<BAOREC_MAS_CIC>, grid, 256, 0, st, x, y, z, n, g, t, cnt);
+  BR_LAUNCH(ctx, scan_partial_kernel, nsb, 256, 0, st, cnt, sums, m);
+  BR_LAUNCH(ctx, scan_sums_kernel, 1, 32, 0, st, sums, nsb, total);
+  BR_LAUNCH(ctx, scan_final_kernel, nsb, 256, 0, st, cnt, sums, cursor, starts, m);
+  unsigned h[2] = {0, 0};  // start of the trash bin (= number of in-box particles), its size
+  BR_CUDA(cudaMemcpyAsync(&h[0], cursor + t.ntiles, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  BR_CUDA(cudaMemcpyAsync(&h[1], cnt + t.ntiles, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  if (tsc) BR_LAUNCH(ctx, tile_reorder_kernel<BAOREC_MAS_TSC>, grid, 256, 0, st, x, y, z, n, g, t, cursor, rec, inv);
+  else BR_LAUNCH(ctx, tile_reorder_kernel<BAOREC_MAS_CIC>, grid, 256, 0, st, x, y, z, n, g, t, cursor, rec, inv);
+  BR_CUDA(cudaStreamSynchronize(st));
+  if (h[1]) {
+    unsigned long long add = h[1];
+    // account the out-of-box particles (the counter lives on the device)
+    unsigned long long cur = 0;
+    BR_CUDA(cudaMemcpy(&cur, ctx->d_oob, sizeof(cur), cudaMemcpyDeviceToHost));
+    cur += add;
+    BR_CUDA(cudaMemcpy(ctx->d_oob, &cur, sizeof(cur), cudaMemcpyHostToDevice));
+  }
+  out->rec = rec;
+  out->n_valid = (int64_t)h[0];
+  out->starts = starts;
+  out->ntiles = t.ntiles;
+  out->inv = inv;
+  return BAOREC_OK;
+}
+
+static bool use_binning(const baorec_ctx* ctx, int64_t n) {
+  return n >= ctx->opt_bin_min_particles && n < ((int64_t)1 << 32) && ctx->nz >= 8;
+}
+
+int scatter(baorec_ctx* ctx, float* rho, float* x, float* y, float* z, const float* w, int64_t n, int wrap, int mas,
+            cudaStream_t st) {
+  if (n == 0) return BAOREC_OK;
+  BoxGeom g = geom_of(ctx);
+  const bool tsc = mas == BAOREC_MAS_TSC;
+  if (use_binning(ctx, n)) {
+    BinResult b;
+    BR_TRY(bin_particles<BIN_SCATTER>(ctx, x, y, z, w, n, wrap, mas, st, &b));
+    if (b.n_valid == 0) return BAOREC_OK;
+    unsigned grid = cdiv((size_t)b.n_valid, 256);
+    if (tsc) BR_LAUNCH(ctx, scatter_sorted_kernel<BAOREC_MAS_TSC>, grid, 256, 0, st, rho, b.rec, b.n_valid, g, wrap);
+    else BR_LAUNCH(ctx, scatter_sorted_kernel<BAOREC_MAS_CIC>, grid, 256, 0, st, rho, b.rec, b.n_valid, g, wrap);
+    return BAOREC_OK;
+  }
+  unsigned grid = cdiv((size_t)n, 256);
+  if (tsc) BR_LAUNCH(ctx, scatter_direct_kernel<BAOREC_MAS_TSC>, grid, 256, 0, st, rho, x, y, z, w, n, g, wrap,
+                     ctx->d_oob);
+  else BR_LAUNCH(ctx, scatter_direct_kernel<BAOREC_MAS_CIC>, grid, 256, 0, st, rho, x, y, z, w, n, g, wrap,
+                 ctx->d_oob);
+  return BAOREC_OK;
+}
+
+int gather3(baorec_ctx* ctx, const float* fx, const float* fy, const float* fz, const float* x, const float* y,
+            const float* z, int64_t n, float* ox, float* oy, float* oz, int mas, int field, float f, int has_los,
+            const float* los, int positions, cudaStream_t st) {
+  if (n == 0) return BAOREC_OK;
+  BoxGeom g = geom_of(ctx);
+  GatherArgs a;
+  a.f[0] = fx;
+  a.f[1] = fy;
+  a.f[2] = fz;
+  a.x = x;
+  a.y = y;
+  a.z = z;
+  a.o[0] = ox;
+  a.o[1] = oy;
+  a.o[2] = oz;
+  a.n = n;
+  a.field = field;
+  a.positions = positions;
+  a.has_los = has_los;
+  for (int c = 0; c < 3; c++) a.los[c] = (has_los && los) ? los[c] : 0.f;
+  a.fgrowth = f;
+  a.sorted_out = nullptr;
+  const bool one = (fy == nullptr);
+  const bool tsc = mas == BAOREC_MAS_TSC;
+  if (use_binning(ctx, n)) {
+    BinResult b;
+    if (ctx->opt_gather_tiles) BR_TRY(bin_tiles(ctx, x, y, z, n, mas, st, &b));
+    else BR_TRY(bin_particles<BIN_GATHER>(ctx, (float*)x, (float*)y, (float*)z, nullptr, n, 0, mas, st, &b));
+    if (b.n_valid > 0 && b.starts && !tsc) {
+      TileGeom t;
+      t.nxc = (ctx->nx + TILE_X - 1) / TILE_X;
+      t.nyc = (ctx->ny + TILE_Y - 1) / TILE_Y;
+      t.ntiles = b.ntiles;
+      static bool carve = false;
+      if (!carve) {
+        cudaFuncSetAttribute(gather_tile_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        carve = true;
+      }
+      if (one) {
+        BR_LAUNCH(ctx, gather_tile_kernel<1>, b.ntiles, 128, 0, st, a, b.rec, b.starts, g, t);
+      } else {
+        // results land in sorted order (coalesced), then one un-permute pass: the 3 x 4 B scattered
+        // stores of the direct version cost three random DRAM read-modify-writes per particle
+        float4* so;
+        BR_TRY(need_t(ctx, BUF_BINOUT, (size_t)n, &so));
+        a.sorted_out = so;
+        BR_LAUNCH(ctx, gather_tile_kernel<3>, b.ntiles, 128, 0, st, a, b.rec, b.starts, g, t);
+        BR_LAUNCH(ctx, unsort_kernel, cdiv((size_t)n, 256), 256, 0, st, a, so, b.inv, n, b.n_valid);
+        return BAOREC_OK;
+      }
+    } else if (b.n_valid > 0) {
+      unsigned grid = cdiv((size_t)b.n_valid, 256);
+      if (tsc) {
+        if (one) BR_LAUNCH(ctx, (gather_sorted_kernel<1, BAOREC_MAS_TSC>), grid, 256, 0, st, a, b.rec, b.n_valid, g);
+        else BR_LAUNCH(ctx, (gather_sorted_kernel<3, BAOREC_MAS_TSC>), grid, 256, 0, st, a, b.rec, b.n_valid, g);
+      } else {
+        if (one) BR_LAUNCH(ctx, (gather_sorted_kernel<1, BAOREC_MAS_CIC>), grid, 256, 0, st, a, b.rec, b.n_valid, g);
+        else BR_LAUNCH(ctx, (gather_sorted_kernel<3, BAOREC_MAS_CIC>), grid, 256, 0, st, a, b.rec, b.n_valid, g);
+      }
+    }
+    if (b.n_valid < n)
+      BR_LAUNCH(ctx, gather_trash_kernel, cdiv((size_t)(n - b.n_valid), 256), 256, 0, st, a, b.rec, b.n_valid, n,
+                one ? 1 : 3);
+    return BAOREC_OK;
+  }
+  unsigned grid = cdiv((size_t)n, 256);
+  if (tsc) {
+    if (one) BR_LAUNCH(ctx, (gather_direct_kernel<1, BAOREC_MAS_TSC>), grid, 256, 0, st, a, g, ctx->d_oob);
+    else BR_LAUNCH(ctx, (gather_direct_kernel<3, BAOREC_MAS_TSC>), grid, 256, 0, st, a, g, ctx->d_oob);
+  } else {
+    if (one) BR_LAUNCH(ctx, (gather_direct_kernel<1, BAOREC_MAS_CIC>), grid, 256, 0, st, a, g, ctx->d_oob);
+    else BR_LAUNCH(ctx, (gather_direct_kernel<3, BAOREC_MAS_CIC>), grid, 256, 0, st, a, g, ctx->d_oob);
+  }
+  return BAOREC_OK;
+}
+
+// ---- parity probes -------------------------------------------------------------------------------------
 __global__ void cic_cells_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z,
                                  int64_t n, BoxGeom g, int wrap, int32_t* i0, int32_t* i1, float* w0, float* w1) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -210,137 +969,16 @@ __global__ void gather_cells_kernel(const float* __restrict__ x, const float* __
   }
 }
 
-struct GatherArgs {
-  const float* f[3];
-  const float* x;
-  const float* y;
-  const float* z;
-  float* o[3];
-  int64_t n;
-  int field;      // BAOREC_FIELD_*
-  int positions;  // write pos - shift
-  int has_los;
-  float los[3];
-  float fgrowth;
-};
-
-// read_cic! (src/mas.jl:258-265): sum of field*wx*wy*wz, left-associated, in the order
-// ddd,ddu,dud,duu,udd,udu,uud,uuu (letters = x,y,z).
-template <int NF, int MAS>
-__global__ void __launch_bounds__(256) gather_kernel(GatherArgs a, BoxGeom g, unsigned long long* oob) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
-  float px = a.x[i], py = a.y[i], pz = a.z[i];
-  float val[NF];
-  size_t nx = g.n[0], ny = g.n[1];
-  bool ok;
-  if (MAS == BAOREC_MAS_CIC) {
-    int xd, xu, yd, yu, zd, zu;
-    float dx, ux, dy, uy, dz, uz;
-    ok = gather_axis(px, g.mn[0], g.L[0], g.cell[0], g.n[0], false, xd, xu, dx, ux);
-    ok = gather_axis(py, g.mn[1], g.L[1], g.cell[1], g.n[1], false, yd, yu, dy, uy) && ok;
-    ok = gather_axis(pz, g.mn[2], g.L[2], g.cell[2], g.n[2], false, zd, zu, dz, uz) && ok;
-    if (ok) {
-      size_t rdd = ((size_t)zd * ny + yd) * nx, rdu = ((size_t)zu * ny + yd) * nx;
-      size_t rud = ((size_t)zd * ny + yu) * nx, ruu = ((size_t)zu * ny + yu) * nx;
-#pragma unroll
-      for (int c = 0; c < NF; c++) {
-        const float* f = a.f[c];
-        float v;
-        v = __fmul_rn(__fmul_rn(__fmul_rn(__ldg(f + rdd + xd), dx), dy), dz);
-        v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(__ldg(f + rdu + xd), dx), dy), uz));
-        v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(__ldg(f + rud + xd), dx), uy), dz));
-        v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(__ldg(f + ruu + xd), dx), uy), uz));
-        v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(__ldg(f + rdd + xu), ux), dy), dz));
-        v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(__ldg(f + rdu + xu), ux), dy), uz));
-        v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(__ldg(f + rud + xu), ux), uy), dz));
-        v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(__ldg(f + ruu + xu), ux), uy), uz));
-        val[c] = v;
-      }
-    }
-  } else {
-    int ix[3], iy[3], iz[3];
-    float wx[3], wy[3], wz[3];
-    ok = tsc_axis(px, g.mn[0], g.L[0], g.n[0], true, ix, wx);
-    ok = tsc_axis(py, g.mn[1], g.L[1], g.n[1], true, iy, wy) && ok;
-    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], true, iz, wz) && ok;
-    if (ok) {
-#pragma unroll
-      for (int c = 0; c < NF; c++) val[c] = 0.f;
-#pragma unroll
-      for (int oz = 0; oz < 3; oz++)
-#pragma unroll
-        for (int oy = 0; oy < 3; oy++) {
-          size_t row = ((size_t)iz[oz] * ny + iy[oy]) * nx;
-#pragma unroll
-          for (int ox = 0; ox < 3; ox++)
-#pragma unroll
-            for (int c = 0; c < NF; c++)
-              val[c] = __fadd_rn(
-                  val[c], __fmul_rn(__fmul_rn(__fmul_rn(__ldg(a.f[c] + row + ix[ox]), wx[ox]), wy[oy]), wz[oz]));
-        }
-    }
-  }
-  if (!ok) {
-    atomicAdd(oob, 1ULL);
-#pragma unroll
-    for (int c = 0; c < NF; c++) val[c] = 0.f;
-  }
-  if (NF == 1) {
-    a.o[0][i] = val[0];
-    return;
-  }
-  // read_shifts epilogue (src/recon.jl:277-304 / kernels :308-330)
-  float s0 = val[0], s1 = val[NF > 1 ? 1 : 0], s2 = val[NF > 2 ? 2 : 0];
-  if (a.field != BAOREC_FIELD_DISP) {
-    float lx, ly, lz;
-    if (a.has_los) {
-      lx = a.los[0];
-      ly = a.los[1];
-      lz = a.los[2];
-    } else {
-      float dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
-      lx = __fdiv_rn(px, dist);
-      ly = __fdiv_rn(py, dist);
-      lz = __fdiv_rn(pz, dist);
-    }
-    float dot = __fadd_rn(__fadd_rn(__fmul_rn(s0, lx), __fmul_rn(s1, ly)), __fmul_rn(s2, lz));
-    float fd = __fmul_rn(a.fgrowth, dot);
-    float r0 = __fmul_rn(fd, lx), r1 = __fmul_rn(fd, ly), r2 = __fmul_rn(fd, lz);
-    if (a.field == BAOREC_FIELD_RSD) {
-      s0 = r0;
-      s1 = r1;
-      s2 = r2;
-    } else {
-      s0 = __fadd_rn(s0, r0);
-      s1 = __fadd_rn(s1, r1);
-      s2 = __fadd_rn(s2, r2);
-    }
-  }
-  if (a.positions) {
-    s0 = __fsub_rn(px, s0);
-    s1 = __fsub_rn(py, s1);
-    s2 = __fsub_rn(pz, s2);
-  }
-  a.o[0][i] = s0;
-  if (NF > 1) a.o[1][i] = s1;
-  if (NF > 2) a.o[2][i] = s2;
-}
-
 // ---- setup_box reductions (src/utils.jl:100-109) --------------------------------------------
 __device__ __forceinline__ unsigned f2ord(float f) {
   unsigned u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
-__host__ __device__ __forceinline__ float ord2f(unsigned u) {
+static float ord2f(unsigned u) {
   unsigned v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
-#ifdef __CUDA_ARCH__
-  return __uint_as_float(v);
-#else
   float f;
   memcpy(&f, &v, 4);
   return f;
-#endif
 }
 
 __global__ void minmax_init_kernel(unsigned* mm) {
@@ -374,52 +1012,6 @@ minmax_kernel(const float* __restrict__ x, const float* __restrict__ y, const fl
       atomicMax(mm + 3 + a, hi[a]);
     }
   }
-}
-
-int scatter(baorec_ctx* ctx, float* rho, float* x, float* y, float* z, const float* w, int64_t n, int wrap, int mas,
-            cudaStream_t st) {
-  if (n == 0) return BAOREC_OK;
-  BoxGeom g = geom_of(ctx);
-  unsigned grid = cdiv((size_t)n, 256);
-  if (mas == BAOREC_MAS_TSC) {
-    BR_LAUNCH(ctx, tsc_scatter_kernel, grid, 256, 0, st, rho, x, y, z, w, n, g, wrap, ctx->d_oob);
-  } else {
-    BR_LAUNCH(ctx, cic_scatter_kernel, grid, 256, 0, st, rho, x, y, z, w, n, g, wrap, ctx->d_oob);
-  }
-  return BAOREC_OK;
-}
-
-int gather3(baorec_ctx* ctx, const float* fx, const float* fy, const float* fz, const float* x, const float* y,
-            const float* z, int64_t n, float* ox, float* oy, float* oz, int mas, int field, float f, int has_los,
-            const float* los, int positions, cudaStream_t st) {
-  if (n == 0) return BAOREC_OK;
-  BoxGeom g = geom_of(ctx);
-  GatherArgs a;
-  a.f[0] = fx;
-  a.f[1] = fy;
-  a.f[2] = fz;
-  a.x = x;
-  a.y = y;
-  a.z = z;
-  a.o[0] = ox;
-  a.o[1] = oy;
-  a.o[2] = oz;
-  a.n = n;
-  a.field = field;
-  a.positions = positions;
-  a.has_los = has_los;
-  for (int c = 0; c < 3; c++) a.los[c] = (has_los && los) ? los[c] : 0.f;
-  a.fgrowth = f;
-  unsigned grid = cdiv((size_t)n, 256);
-  bool one = (fy == nullptr);
-  if (mas == BAOREC_MAS_TSC) {
-    if (one) BR_LAUNCH(ctx, (gather_kernel<1, BAOREC_MAS_TSC>), grid, 256, 0, st, a, g, ctx->d_oob);
-    else BR_LAUNCH(ctx, (gather_kernel<3, BAOREC_MAS_TSC>), grid, 256, 0, st, a, g, ctx->d_oob);
-  } else {
-    if (one) BR_LAUNCH(ctx, (gather_kernel<1, BAOREC_MAS_CIC>), grid, 256, 0, st, a, g, ctx->d_oob);
-    else BR_LAUNCH(ctx, (gather_kernel<3, BAOREC_MAS_CIC>), grid, 256, 0, st, a, g, ctx->d_oob);
-  }
-  return BAOREC_OK;
 }
 
 int setup_box_dev(baorec_ctx* ctx, const float* x, const float* y, const float* z, int64_t n, float pad,

@@ -78,6 +78,27 @@ class Context:
         n = self.lib.baorec_last_stage_ms(self.handle, buf, 8)
         return [buf[i] for i in range(n)]
 
+    def set_option(self, name: str, value: int):
+        L.check(self.lib.baorec_set_option(self.handle, name.encode(), int(value)))
+
+    def profile(self, on: bool):
+        L.check(self.lib.baorec_profile_enable(self.handle, int(bool(on))))
+
+    def profile_read(self):
+        """{kernel name: (total ms, launches)} for the current profiling window."""
+        cap, stride = 64, 96
+        names = C.create_string_buffer(cap * stride)
+        ms = (C.c_float * cap)()
+        cnt = (C.c_int32 * cap)()
+        n = self.lib.baorec_profile_read(self.handle, names, stride, ms, cnt, cap)
+        if n < 0:
+            L.check(n)
+        out = {}
+        for i in range(n):
+            nm = names.raw[i * stride:(i + 1) * stride].split(b"\0", 1)[0].decode()
+            out[nm] = (float(ms[i]), int(cnt[i]))
+        return out
+
     def scratch_bytes(self):
         return int(self.lib.baorec_scratch_bytes(self.handle))
 

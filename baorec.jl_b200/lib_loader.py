@@ -52,9 +52,12 @@ SIGNATURES = {
     "baorec_destroy": [_vp],
     "baorec_plan": [_vp, _i, _i, _i, _f3, _f3],
     "baorec_set_box": [_vp, _f3, _f3],
+    "baorec_set_option": [_vp, C.c_char_p, _i64],
     "baorec_scratch_bytes": [_vp],
     "baorec_launch_counts": [_vp, C.POINTER(_i64), C.POINTER(_i64)],
     "baorec_last_stage_ms": [_vp, _f3, _i],
+    "baorec_profile_enable": [_vp, _i],
+    "baorec_profile_read": [_vp, C.c_char_p, _i, _f3, C.POINTER(C.c_int32), _i],
     "baorec_comm_unique_id": [_vp],
     "baorec_comm_init": [_vp, _i, _i, _vp],
     "baorec_plan_dist": [_vp, _i, _i, _i, _f3, _f3],

@@ -89,15 +89,31 @@ int baorec_plan(baorec_ctx* ctx, int nx, int ny, int nz, const float box_size[3]
 /* Change the box without re-planning the FFTs (run! with randoms overrides it,
  * src/recon.jl:172). */
 int baorec_set_box(baorec_ctx* ctx, const float box_size[3], const float box_min[3]);
+/* Tuning knobs (all default to the fast path):
+ *   "bin_min_particles" (default 262144): catalogs at least this large are counting-sorted by
+ *       z slab before the scatter / gather so the mesh window stays L2-resident; 0 = always.
+ *   "fuse_kspace" (default 1): with a fixed line of sight reconstructed_overdensity! folds the
+ *       smoothing, normalisation and all n_iter iterations into ONE k-space pass between one
+ *       R2C and one C2R (iterate! is linear and diagonal in k for a constant LOS); 0 = run the
+ *       reference's sequence of iterate! calls (2 + 2 n_iter transforms). */
+int baorec_set_option(baorec_ctx* ctx, const char* name, int64_t value);
 /* Bytes of device scratch currently owned by the context. */
 int64_t baorec_scratch_bytes(const baorec_ctx* ctx);
 /* Kernel launches issued by this library since creation (cuFFT launches are
  * counted separately in *fft_execs). */
 int baorec_launch_counts(const baorec_ctx* ctx, int64_t* kernels, int64_t* fft_execs);
-/* Per-stage timing of the last pipeline call (CUDA events on the stream):
- * writes up to `cap` floats of milliseconds in the order scatter, setup_fft+kspace,
- * iterations/solve, displacement meshes, gather.  Returns the count written. */
+/* Per-stage timing of the last host-pipeline calls (CUDA events on the context's stream), ms:
+ * [0] H2D of the catalogs (+ setup_box), [1] set-up + solve, [2] D2H (wrapped positions, mesh);
+ * after baorec_read_host_f32 also [3] H2D of positions + displacement meshes, [4] gather,
+ * [5] D2H of the outputs.  Returns the count written (<= cap). */
 int baorec_last_stage_ms(const baorec_ctx* ctx, float* out, int cap);
+/* Per-launch profiling: while enabled every kernel launch and cuFFT execution issued by the
+ * context is bracketed by CUDA events on its stream.  baorec_profile_enable(ctx, on) clears
+ * the current window; baorec_profile_read synchronises the device and aggregates the window
+ * by kernel name: names[i*name_stride ...] (NUL-terminated), total_ms[i], counts[i]; returns
+ * the number of distinct names (<= cap). */
+int baorec_profile_enable(baorec_ctx* ctx, int on);
+int baorec_profile_read(baorec_ctx* ctx, char* names, int name_stride, float* total_ms, int32_t* counts, int cap);
 
 /* ---- multi-GPU (one process per GPU; slabs along z) ------------------------ */
 /* 128-byte NCCL unique id, created on rank 0 and broadcast by the host side

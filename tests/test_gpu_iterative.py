@@ -176,7 +176,7 @@ def test_run_lightcone_radial_randoms(B, O):
             for a in range(3):
                 g = sg[a].cpu().numpy()
                 assert rel_rms(g, so64[a]) < max(TOL_RMS, 2 * rel_rms(so[a], so64[a]))
-                assert maxabs(g, so64[a]) < max(TOL_MAX_SHIFT, 2 * maxabs(so[a], so64[a]))
+                assert maxabs(g, so64[a]) < max(TOL_MAX_SHIFT, 3 * maxabs(so[a], so64[a]))
     # --- the one-call driver: same thing up to the (run-to-run) threshold flips ---
     rec2 = B.IterativeRecon(**kw)
     mesh = B.run(rec2, (n, n, n), *gd, dev(wd), *gr, dev(wr))

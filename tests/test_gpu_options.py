@@ -1,0 +1,169 @@
+"""GPU parity of the fast paths against the oracle and against the reference-sequence path:
+  * z-slab binned scatter / gather (forced on for small catalogs with bin_min_particles = 0);
+  * fused fixed-LOS k-space solve (fuse_kspace = 1) versus the sequence of iterate! calls."""
+import contextlib
+
+import numpy as np
+import pytest
+
+from util import uniform_box, clustered_box, lightcone, rel_rms, maxabs
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@contextlib.contextmanager
+def options(B, **kw):
+    ctx = B.Context.get(0)
+    defaults = {"bin_min_particles": 1 << 18, "fuse_kspace": 1}
+    try:
+        for k, v in kw.items():
+            ctx.set_option(k, v)
+        yield ctx
+    finally:
+        for k in kw:
+            ctx.set_option(k, defaults[k])
+
+
+def test_unknown_option(B):
+    with pytest.raises(B.BaorecError):
+        B.Context.get(0).set_option("no_such_option", 1)
+
+
+@pytest.mark.parametrize("wrap", [True, False])
+@pytest.mark.parametrize("n", [64, 20])
+def test_binned_scatter(B, O, wrap, n):
+    L, N = 1000.0, 200_000
+    pos, w = clustered_box(N, L, seed=17)
+    if wrap:
+        pos[0][:50] += np.float32(L)
+        pos[2][50:80] += np.float32(L)
+    else:
+        for p in pos:
+            np.clip(p, 0, np.float32(L - L / n - 1e-3), out=p)
+    bs, bm = np.full(3, L, np.float32), np.zeros(3, np.float32)
+    ox, oy, oz = (p.copy() for p in pos)
+    orho = O.cic_scatter(np.zeros((n, n, n), np.float32), ox, oy, oz, w, bs, bm, wrap)
+    gx, gy, gz = (dev(p) for p in pos)
+    rho = torch.zeros((n, n, n), dtype=torch.float32, device="cuda")
+    with options(B, bin_min_particles=0):
+        B.cic(rho, gx, gy, gz, dev(w), bs, bm, wrap=wrap)
+    assert maxabs(rho.cpu().numpy(), orho) <= 2e-5 * max(1.0, float(orho.max()))
+    for g, o in zip((gx, gy, gz), (ox, oy, oz)):       # wrapped positions written back
+        assert np.array_equal(g.cpu().numpy().view(np.uint32), o.view(np.uint32))
+
+
+def test_binned_scatter_out_of_box(B):
+    n, L = 32, 100.0
+    bs, bm = np.full(3, L, np.float32), np.zeros(3, np.float32)
+    rng = np.random.default_rng(0)
+    x = (rng.random(1000) * L).astype(np.float32)
+    y = (rng.random(1000) * L).astype(np.float32)
+    z = (rng.random(1000) * L).astype(np.float32)
+    x[7], z[11], y[500] = -3.0, 420.0, np.nan
+    rho = torch.zeros((n, n, n), dtype=torch.float32, device="cuda")
+    with options(B, bin_min_particles=0):
+        with pytest.raises(B.OutOfBoxError) as ei:
+            B.cic(rho, dev(x), dev(y), dev(z), dev(np.ones(1000, np.float32)), bs, bm, wrap=True)
+    assert "3 particle(s)" in str(ei.value)
+    assert abs(float(rho.sum()) - 997.0) < 1e-2       # the others were deposited
+
+
+@pytest.mark.parametrize("mas", ["cic", "tsc"])
+def test_binned_gather_bit_exact(B, O, mas):
+    n, L, lo, N = 48, 777.0, -123.0, 150_000
+    rng = np.random.default_rng(5)
+    fld = rng.standard_normal((n, n, n)).astype(np.float32)
+    pos, _ = uniform_box(N, L, seed=6, lo=lo)
+    bs, bm = np.full(3, L, np.float32), np.full(3, lo, np.float32)
+    ref = (O.read_cic if mas == "cic" else O.read_tsc)(fld, *pos, bs, bm)
+    out = torch.empty(N, dtype=torch.float32, device="cuda")
+    with options(B, bin_min_particles=0):
+        B.read_cic(out, dev(fld), *(dev(p) for p in pos), bs, bm, mas=mas)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+
+
+def test_binned_tsc_scatter(B, O):
+    n, L, N = 40, 500.0, 100_000
+    pos, w = clustered_box(N, L, seed=3)
+    bs, bm = np.full(3, L, np.float32), np.zeros(3, np.float32)
+    orho = O.tsc_scatter(np.zeros((n, n, n), np.float32), *pos, w, bs, bm, True)
+    rho = torch.zeros((n, n, n), dtype=torch.float32, device="cuda")
+    with options(B, bin_min_particles=0):
+        B.cic(rho, *(dev(p) for p in pos), dev(w), bs, bm, wrap=True, mas="tsc")
+    assert maxabs(rho.cpu().numpy(), orho) <= 2e-5 * float(orho.max())
+
+
+@pytest.mark.parametrize("opts", [dict(bin_min_particles=0, fuse_kspace=1), dict(bin_min_particles=0, fuse_kspace=0),
+                                  dict(bin_min_particles=1 << 40, fuse_kspace=0),
+                                  dict(bin_min_particles=1 << 40, fuse_kspace=1)])
+@pytest.mark.parametrize("los", [(0.0, 0.0, 1.0), (0.0, 1.0, 0.0)])
+def test_box_recon_all_paths(B, O, opts, los):
+    """Every combination of the fast paths reproduces the oracle's run! + read_shifts."""
+    n, L, N = 64, 1000.0, 300_000
+    pos, w = clustered_box(N, L, seed=33)
+    kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=np.full(3, L, np.float32),
+              box_min=np.zeros(3, np.float32), los=los, n_iter=3)
+    orec = O.IterativeRecon(**kw)
+    omesh = O.run(orec, (n, n, n), *[p.copy() for p in pos], w)
+    oshift = O.read_shifts(orec, *pos, omesh, "sum")
+    d = [dev(p) for p in pos]
+    with options(B, **opts):
+        rec = B.IterativeRecon(**kw)
+        mesh = B.run(rec, (n, n, n), *d, dev(w))
+        s = B.read_shifts(rec, *d, mesh, field="sum")
+        # host pipeline (uses the cached delta_k when fused)
+        rec_h = B.IterativeRecon(**kw)
+        hmesh = np.empty((n, n, n), np.float32)
+        B.run(rec_h, (n, n, n), *[p.copy() for p in pos], w, mesh_out=hmesh)
+        sh = B.read_shifts(rec_h, *pos, None, field="sum")
+    assert rel_rms(mesh.cpu().numpy(), omesh) < 1e-4
+    assert rel_rms(hmesh, omesh) < 1e-4
+    for a in range(3):
+        for got in (s[a].cpu().numpy(), sh[a]):
+            assert rel_rms(got, oshift[a]) < 1e-4
+            assert maxabs(got, oshift[a]) < 1e-3
+
+
+@pytest.mark.parametrize("n_iter", [0, 1, 5])
+def test_fused_n_iter(B, O, n_iter):
+    n, L, N = 48, 800.0, 100_000
+    pos, w = clustered_box(N, L, seed=2)
+    kw = dict(bias=1.7, f=0.9, smoothing_radius=12.0, box_size=np.full(3, L, np.float32),
+              box_min=np.zeros(3, np.float32), los=(1.0, 0.0, 0.0), n_iter=n_iter)
+    omesh = O.run(O.IterativeRecon(**kw), (n, n, n), *[p.copy() for p in pos], w)
+    mesh = B.run(B.IterativeRecon(**kw), (n, n, n), *(dev(p) for p in pos), dev(w))
+    assert rel_rms(mesh.cpu().numpy(), omesh) < 1e-4
+
+
+def test_fused_with_randoms_fixed_los(B, O):
+    """Fixed LOS + randoms (survey geometry with a plane-parallel LOS): fused MODE 1."""
+    from test_gpu_iterative import check_flips_explained, LC, NLC
+    n = NLC
+    d, wd, r, wr = lightcone(60_000, 600_000, seed=21, **LC)
+    kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, los=(1.0, 0.0, 0.0), n_iter=3)
+    gd, gr = [dev(p) for p in d], [dev(p) for p in r]
+    outs = {}
+    for fuse in (0, 1):
+        with options(B, fuse_kspace=fuse):
+            rec = B.IterativeRecon(**kw)
+            rec.box_size, rec.box_min = B.setup_box(*gr, 500.0)
+            ds = torch.zeros((n, n, n), dtype=torch.float32, device="cuda")
+            B.setup_fft(rec, ds)
+            B.setup_overdensity(ds, rec, *gd, dev(wd), *gr, dev(wr))
+            mesh = torch.zeros((n, n, n), dtype=torch.float32, device="cuda")
+            B.reconstructed_overdensity(mesh, rec, *gd, dev(wd), *gr, dev(wr))
+            outs[fuse] = (ds.cpu().numpy() != 0, mesh.cpu().numpy())
+    orec = O.IterativeRecon(**kw)
+    orec.box_size, orec.box_min = O.setup_box(*r, np.float32(500))
+    info = {}
+    O.setup_overdensity(np.zeros((n, n, n), np.float32), orec, *d, wd, *r, wr, info=info)
+    for fuse in (0, 1):
+        nfl = check_flips_explained(outs[fuse][0], info)
+        if nfl == 0:   # same threshold decisions as the oracle: compare the reconstructed mesh
+            omesh = O.run(O.IterativeRecon(**kw), (n, n, n), *d, wd, *r, wr)
+            assert rel_rms(outs[fuse][1], omesh) < 3e-4
