@@ -15,4 +15,6 @@ from .host import (Context, FFTPlan, IterativeRecon, MultigridRecon, setup_fft, 
                    reconstructed_potential, run, compute_displacements, displacement_meshes, read_shifts,
                    reconstructed_positions, jacobi, residual, reduce, prolong, vcycle, fmg)
 
+from . import dist
+
 lib_loader.load()   # no library -> ImportError; there is no fallback path

@@ -1,5 +1,13 @@
-// Multi-GPU plumbing: one process per GPU, NCCL communicator created from a unique id that the
-// host side (torch.distributed / MPI.jl) broadcasts.  Slabs along z.
+// Multi-GPU path: one process per GPU, the mesh decomposed into z slabs.
+//
+//  real space : rank r owns planes [r nz/P, (r+1) nz/P)            slab[zl][y][x]
+//  k space    : rank r owns rows   [r ny/P, (r+1) ny/P), z contiguous   T[yl][ix][iz]
+//
+//  forward FFT = batched 2-D R2C over the local planes -> pack (row copy) -> all-to-all
+//                -> unpack with an (x,z) tile transpose -> batched 1-D C2C along z
+//  inverse FFT = mirror image.  The all-to-all is grouped ncclSend/ncclRecv over NVLink.
+//  Particles are owned by the slab of their base cell: the scatter writes one ghost plane that
+//  is sent to the next rank and added; the gather reads three halo planes.
 #include <nccl.h>
 #include <string.h>
 
@@ -16,6 +24,198 @@ using namespace baorec;
     }                                                                                              \
   } while (0)
 
+namespace baorec {
+
+// ---- pack / unpack kernels ---------------------------------------------------------------------------
+// Row copy between A[zl][y][x] and the per-peer blocks B[peer][zl][yl][x]  (y = peer*nyl + yl).
+template <bool TO_BLOCKS>
+__global__ void __launch_bounds__(128)
+rows_kernel(float2* __restrict__ dst, const float2* __restrict__ src, int nzl, int ny, int nyl, int xh) {
+  const unsigned row = blockIdx.x;  // zl * ny + y
+  const int zl = row / ny, y = row - zl * ny;
+  const int peer = y / nyl, yl = y - peer * nyl;
+  const size_t a = (size_t)row * xh;
+  const size_t b = (((size_t)peer * nzl + zl) * nyl + yl) * xh;
+  const float2* s = src + (TO_BLOCKS ? a : b);
+  float2* d = dst + (TO_BLOCKS ? b : a);
+  for (int x = threadIdx.x; x < xh; x += blockDim.x) d[x] = s[x];
+}
+
+// Batched strided 2-D transpose through shared memory: dst[c][r] = src[r][c].
+struct TrGeom {
+  int rows, cols;
+  size_t src_row_stride, dst_row_stride;
+  int nb1;  // batch index b -> (b0 = b / nb1, b1 = b % nb1)
+  size_t src_b0, src_b1, dst_b0, dst_b1;
+};
+
+__global__ void __launch_bounds__(256) transpose_kernel(float2* __restrict__ dst, const float2* __restrict__ src, TrGeom t) {
+  __shared__ float2 tile[32][33];
+  const int b = blockIdx.z, b0 = b / t.nb1, b1 = b - b0 * t.nb1;
+  const float2* s = src + b0 * t.src_b0 + b1 * t.src_b1;
+  float2* d = dst + b0 * t.dst_b0 + b1 * t.dst_b1;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    int r = r0 + ty + 8 * k, c = c0 + tx;
+    if (r < t.rows && c < t.cols) tile[ty + 8 * k][tx] = s[(size_t)r * t.src_row_stride + c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    int c = c0 + ty + 8 * k, r = r0 + tx;
+    if (r < t.rows && c < t.cols) d[(size_t)c * t.dst_row_stride + r] = tile[tx][ty + 8 * k];
+  }
+}
+
+__global__ void add_plane_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
+__global__ void slab_owner_kernel(const float* __restrict__ z, int64_t n, float mn, float L, int nz, int nzl,
+                                  int32_t* __restrict__ owner) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // base plane of cic! (src/mas.jl:15,19,30) after the upper-face wrap (:10)
+  float p = z[i];
+  if (__fsub_rn(p, mn) > L) p = __fsub_rn(p, L);
+  float g = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(p, mn), (float)nz), L), 1.0f);
+  int c0 = (int)floorf(g);
+  if (c0 == nz + 1) c0 = 1;
+  owner[i] = (g >= 1.0f && c0 >= 1 && c0 <= nz) ? (c0 - 1) / nzl : -1;
+}
+
+static ncclComm_t comm_of(baorec_ctx* ctx) { return (ncclComm_t)ctx->comm; }
+
+// blocks of `blk` complex values per peer: S[peer] -> R[peer]
+static int all_to_all(baorec_ctx* ctx, const float2* S, float2* R, size_t blk, cudaStream_t st) {
+  const int P = ctx->nranks;
+  if (P == 1) {
+    BR_CUDA(cudaMemcpyAsync(R, S, blk * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    return BAOREC_OK;
+  }
+  int pi = prof_begin(ctx, "nccl_all_to_all", st);
+  BR_NCCL(ncclGroupStart());
+  for (int peer = 0; peer < P; peer++) {
+    BR_NCCL(ncclSend(S + (size_t)peer * blk, blk * 2, ncclFloat, peer, comm_of(ctx), st));
+    BR_NCCL(ncclRecv(R + (size_t)peer * blk, blk * 2, ncclFloat, peer, comm_of(ctx), st));
+  }
+  BR_NCCL(ncclGroupEnd());
+  prof_end(ctx, pi, st);
+  return BAOREC_OK;
+}
+
+// send `count` floats to rank `to`, receive as many from rank `from`
+static int ring_exchange(baorec_ctx* ctx, const float* send, int to, float* recv, int from, size_t count,
+                         cudaStream_t st) {
+  if (ctx->nranks == 1) {
+    BR_CUDA(cudaMemcpyAsync(recv, send, count * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return BAOREC_OK;
+  }
+  int pi = prof_begin(ctx, "nccl_halo", st);
+  BR_NCCL(ncclGroupStart());
+  BR_NCCL(ncclSend(send, count, ncclFloat, to, comm_of(ctx), st));
+  BR_NCCL(ncclRecv(recv, count, ncclFloat, from, comm_of(ctx), st));
+  BR_NCCL(ncclGroupEnd());
+  prof_end(ctx, pi, st);
+  return BAOREC_OK;
+}
+
+struct DistBufs {
+  float2 *A, *S, *R, *T;
+};
+
+static int dist_bufs(baorec_ctx* ctx, DistBufs* b) {
+  const size_t slab_c = (size_t)ctx->nz_loc * ctx->ny * ctx->xh;  // == ny_loc * xh * nz
+  BR_TRY(need_t(ctx, BUF_CK0, slab_c, &b->A));
+  BR_TRY(need_t(ctx, BUF_CK1, slab_c, &b->T));
+  BR_TRY(need_t(ctx, BUF_A2A_SEND, slab_c, &b->S));
+  BR_TRY(need_t(ctx, BUF_A2A_RECV, slab_c, &b->R));
+  return BAOREC_OK;
+}
+
+// slab[nz_loc][ny][nx] (real) -> T[ny_loc][xh][nz] (unnormalised forward transform)
+static int dist_r2c(baorec_ctx* ctx, const float* slab, float2* T, cudaStream_t st) {
+  DistBufs b;
+  BR_TRY(dist_bufs(ctx, &b));
+  const int P = ctx->nranks, nzl = ctx->nz_loc, nyl = ctx->ny_loc, ny = ctx->ny, xh = ctx->xh, nz = ctx->nz;
+  BR_CUFFT(cufftSetStream(ctx->p2d_r2c, st));
+  int pi = prof_begin(ctx, "cufft_2d_r2c", st);
+  BR_CUFFT(cufftExecR2C(ctx->p2d_r2c, (cufftReal*)slab, (cufftComplex*)b.A));
+  prof_end(ctx, pi, st);
+  ctx->n_fft++;
+  BR_LAUNCH(ctx, rows_kernel<true>, (unsigned)(nzl * ny), 128, 0, st, b.S, b.A, nzl, ny, nyl, xh);
+  const size_t blk = (size_t)nzl * nyl * xh;
+  BR_TRY(all_to_all(ctx, b.S, b.R, blk, st));
+  // T[yl][x][s*nzl + zl] = R[s][zl][yl][x]
+  TrGeom t;
+  t.rows = nzl;
+  t.cols = xh;
+  t.src_row_stride = (size_t)nyl * xh;
+  t.dst_row_stride = nz;
+  t.nb1 = nyl;
+  t.src_b0 = blk;
+  t.src_b1 = xh;
+  t.dst_b0 = nzl;
+  t.dst_b1 = (size_t)xh * nz;
+  dim3 grid(cdiv(xh, 32), cdiv(nzl, 32), P * nyl);
+  BR_LAUNCH(ctx, transpose_kernel, grid, 256, 0, st, T, b.R, t);
+  BR_CUFFT(cufftSetStream(ctx->p1d, st));
+  pi = prof_begin(ctx, "cufft_1d_z", st);
+  BR_CUFFT(cufftExecC2C(ctx->p1d, (cufftComplex*)T, (cufftComplex*)T, CUFFT_FORWARD));
+  prof_end(ctx, pi, st);
+  ctx->n_fft++;
+  return BAOREC_OK;
+}
+
+// T[ny_loc][xh][nz] (destroyed) -> slab[nz_loc][ny][nx]; unnormalised inverse
+static int dist_c2r(baorec_ctx* ctx, float2* T, float* slab, cudaStream_t st) {
+  DistBufs b;
+  BR_TRY(dist_bufs(ctx, &b));
+  const int P = ctx->nranks, nzl = ctx->nz_loc, nyl = ctx->ny_loc, ny = ctx->ny, xh = ctx->xh, nz = ctx->nz;
+  BR_CUFFT(cufftSetStream(ctx->p1d, st));
+  int pi = prof_begin(ctx, "cufft_1d_z", st);
+  BR_CUFFT(cufftExecC2C(ctx->p1d, (cufftComplex*)T, (cufftComplex*)T, CUFFT_INVERSE));
+  prof_end(ctx, pi, st);
+  ctx->n_fft++;
+  const size_t blk = (size_t)nzl * nyl * xh;
+  // S[d][zl][yl][x] = T[yl][x][d*nzl + zl]
+  TrGeom t;
+  t.rows = xh;
+  t.cols = nzl;
+  t.src_row_stride = nz;
+  t.dst_row_stride = (size_t)nyl * xh;
+  t.nb1 = nyl;
+  t.src_b0 = nzl;
+  t.src_b1 = (size_t)xh * nz;
+  t.dst_b0 = blk;
+  t.dst_b1 = xh;
+  dim3 grid(cdiv(nzl, 32), cdiv(xh, 32), P * nyl);
+  BR_LAUNCH(ctx, transpose_kernel, grid, 256, 0, st, b.S, T, t);
+  BR_TRY(all_to_all(ctx, b.S, b.R, blk, st));
+  BR_LAUNCH(ctx, rows_kernel<false>, (unsigned)(nzl * ny), 128, 0, st, b.A, b.R, nzl, ny, nyl, xh);
+  BR_CUFFT(cufftSetStream(ctx->p2d_c2r, st));
+  pi = prof_begin(ctx, "cufft_2d_c2r", st);
+  BR_CUFFT(cufftExecC2R(ctx->p2d_c2r, (cufftComplex*)b.A, (cufftReal*)slab));
+  prof_end(ctx, pi, st);
+  ctx->n_fft++;
+  return BAOREC_OK;
+}
+
+}  // namespace baorec
+
+#define BR_NEED_DIST(ctx)                                                     \
+  do {                                                                        \
+    BR_REQUIRE((ctx) != nullptr, "ctx is NULL");                              \
+    if (!(ctx)->planned || !(ctx)->dist) {                                    \
+      baorec::set_error("call baorec_plan_dist before the *_dist entry points"); \
+      return BAOREC_ERR_NOT_PLANNED;                                          \
+    }                                                                         \
+    BR_CUDA(cudaSetDevice((ctx)->device));                                    \
+  } while (0)
+
 extern "C" {
 
 int baorec_comm_unique_id(void* out128) {
@@ -28,20 +228,22 @@ int baorec_comm_unique_id(void* out128) {
 }
 
 int baorec_comm_init(baorec_ctx* ctx, int rank, int nranks, const void* unique_id128) {
-  BR_REQUIRE(ctx != nullptr && unique_id128 != nullptr, "NULL argument");
+  BR_REQUIRE(ctx != nullptr, "ctx is NULL");
   BR_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "rank / nranks");
   BR_CUDA(cudaSetDevice(ctx->device));
   if (ctx->comm) {
     ncclCommDestroy((ncclComm_t)ctx->comm);
     ctx->comm = nullptr;
   }
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  if (nranks == 1) return BAOREC_OK;  // single rank: no communicator needed
+  BR_REQUIRE(unique_id128 != nullptr, "unique id is NULL");
   ncclUniqueId id;
   memcpy(&id, unique_id128, sizeof(id));
   ncclComm_t comm;
   BR_NCCL(ncclCommInitRank(&comm, nranks, id, rank));
   ctx->comm = comm;
-  ctx->rank = rank;
-  ctx->nranks = nranks;
   return BAOREC_OK;
 }
 
@@ -54,10 +256,164 @@ int baorec_comm_destroy_internal(baorec_ctx* ctx) {
 }
 
 int baorec_plan_dist(baorec_ctx* ctx, int nx, int ny, int nz, const float box_size[3], const float box_min[3]) {
-  (void)nx; (void)ny; (void)nz; (void)box_size; (void)box_min;
   BR_REQUIRE(ctx != nullptr, "ctx is NULL");
-  set_error("baorec_plan_dist: slab-decomposed plan is not available in this build");
-  return BAOREC_ERR_INVALID;
+  const int P = ctx->nranks;
+  BR_REQUIRE(P == 1 || ctx->comm != nullptr, "call baorec_comm_init first");
+  BR_REQUIRE(nz % P == 0 && ny % P == 0, "nz and ny must be divisible by the number of ranks");
+  BR_REQUIRE(nz / P >= 2, "each slab needs at least two planes");
+  int s = plan_common(ctx, nx, ny, nz, box_size, box_min);
+  if (s < 0) return s;
+  const int nzl = nz / P, nyl = ny / P;
+  if (!ctx->have_dist_plans || s == 0 || ctx->nz_loc != nzl) {
+    if (ctx->have_dist_plans) {
+      cufftDestroy(ctx->p2d_r2c);
+      cufftDestroy(ctx->p2d_c2r);
+      cufftDestroy(ctx->p1d);
+      ctx->have_dist_plans = false;
+    }
+    size_t w[3] = {0, 0, 0};
+    int n2[2] = {ny, nx};
+    int n1[1] = {nz};
+    BR_CUFFT(cufftCreate(&ctx->p2d_r2c));
+    BR_CUFFT(cufftCreate(&ctx->p2d_c2r));
+    BR_CUFFT(cufftCreate(&ctx->p1d));
+    ctx->have_dist_plans = true;
+    BR_CUFFT(cufftSetAutoAllocation(ctx->p2d_r2c, 0));
+    BR_CUFFT(cufftSetAutoAllocation(ctx->p2d_c2r, 0));
+    BR_CUFFT(cufftSetAutoAllocation(ctx->p1d, 0));
+    BR_CUFFT(cufftMakePlanMany(ctx->p2d_r2c, 2, n2, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, nzl, &w[0]));
+    BR_CUFFT(cufftMakePlanMany(ctx->p2d_c2r, 2, n2, nullptr, 1, 0, nullptr, 1, 0, CUFFT_C2R, nzl, &w[1]));
+    BR_CUFFT(cufftMakePlanMany(ctx->p1d, 1, n1, nullptr, 1, 0, nullptr, 1, 0, CUFFT_C2C, nyl * (nx / 2 + 1), &w[2]));
+    size_t wmax = w[0] > w[1] ? w[0] : w[1];
+    if (w[2] > wmax) wmax = w[2];
+    if (wmax < 16) wmax = 16;
+    if (ctx->bufs[BUF_WORK].bytes > wmax) wmax = ctx->bufs[BUF_WORK].bytes;
+    void* work = nullptr;
+    BR_TRY(need(ctx, BUF_WORK, wmax, &work));
+    BR_CUFFT(cufftSetWorkArea(ctx->p2d_r2c, work));
+    BR_CUFFT(cufftSetWorkArea(ctx->p2d_c2r, work));
+    BR_CUFFT(cufftSetWorkArea(ctx->p1d, work));
+    if (ctx->have_plans) {  // the single-GPU plans share the (possibly re-allocated) work area
+      BR_CUFFT(cufftSetWorkArea(ctx->r2c, work));
+      BR_CUFFT(cufftSetWorkArea(ctx->c2r, work));
+    }
+  }
+  ctx->nz_loc = nzl;
+  ctx->z0 = ctx->rank * nzl;
+  ctx->ny_loc = nyl;
+  ctx->y0 = ctx->rank * nyl;
+  ctx->dist = true;
+  ctx->planned = true;
+  ctx->kcache_valid = false;
+  return BAOREC_OK;
+}
+
+int baorec_slab_range(const baorec_ctx* ctx, int* z_lo, int* nz_loc) {
+  BR_REQUIRE(ctx != nullptr && ctx->dist, "not a distributed plan");
+  if (z_lo) *z_lo = ctx->z0;
+  if (nz_loc) *nz_loc = ctx->nz_loc;
+  return BAOREC_OK;
+}
+
+int baorec_slab_owner_f32(baorec_ctx* ctx, const float* d_z, int64_t n, int32_t* d_owner, baorec_stream stream) {
+  BR_NEED_DIST(ctx);
+  BR_REQUIRE(n >= 0 && (n == 0 || (d_z && d_owner)), "slab_owner arguments");
+  if (n == 0) return BAOREC_OK;
+  // note: the wrap of cic! uses the axis-1 box for every axis (src/mas.jl:8-10)
+  BR_LAUNCH(ctx, slab_owner_kernel, cdiv((size_t)n, 256), 256, 0, (cudaStream_t)stream, d_z, n, ctx->mn[2], ctx->L[2],
+            ctx->nz, ctx->nz_loc, d_owner);
+  return BAOREC_OK;
+}
+
+int baorec_dist_r2c_f32(baorec_ctx* ctx, const float* d_slab, float* d_kslab_t, baorec_stream stream) {
+  BR_NEED_DIST(ctx);
+  BR_REQUIRE(d_slab && d_kslab_t, "NULL pointer");
+  return dist_r2c(ctx, d_slab, (float2*)d_kslab_t, (cudaStream_t)stream);
+}
+
+int baorec_dist_c2r_f32(baorec_ctx* ctx, float* d_kslab_t, float* d_slab, baorec_stream stream) {
+  BR_NEED_DIST(ctx);
+  BR_REQUIRE(d_slab && d_kslab_t, "NULL pointer");
+  return dist_c2r(ctx, (float2*)d_kslab_t, d_slab, (cudaStream_t)stream);
+}
+
+int baorec_run_dist_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, float* d_x, float* d_y, float* d_z,
+                        const float* d_w, int64_t n_local, float* d_mesh_slab, baorec_stream stream) {
+  BR_NEED_DIST(ctx);
+  BR_REQUIRE(p != nullptr && d_mesh_slab != nullptr, "NULL argument");
+  BR_REQUIRE(n_local >= 0 && (n_local == 0 || (d_x && d_y && d_z && d_w)), "particle arrays");
+  if (algorithm != BAOREC_ITERATIVE || !p->has_los || p->mas != BAOREC_MAS_CIC) {
+    set_error("baorec_run_dist_f32: this build distributes IterativeRecon with a fixed line of sight and CIC "
+              "(periodic box); radial/randoms and MultigridRecon run on one GPU");
+    return BAOREC_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = ctx->nranks, nzl = ctx->nz_loc;
+  const size_t plane = (size_t)ctx->ny * ctx->nx;
+  ctx->kcache_valid = false;
+  float *loc, *halo;
+  BR_TRY(need_t(ctx, BUF_RS, (size_t)(nzl + 1) * plane, &loc));
+  BR_TRY(need_t(ctx, BUF_HALO, plane, &halo));
+  BR_CUDA(cudaMemsetAsync(loc, 0, (size_t)(nzl + 1) * plane * sizeof(float), st));
+  BR_TRY(reset_oob(ctx, st));
+  ctx->slab_mode = 1;
+  int s = scatter(ctx, loc, d_x, d_y, d_z, d_w, n_local, 1, p->mas, st);
+  ctx->slab_mode = 0;
+  if (s != BAOREC_OK) return s;
+  // ghost plane (global plane z_lo + nzl) belongs to the next rank: send it, add what arrives
+  BR_TRY(ring_exchange(ctx, loc + (size_t)nzl * plane, (ctx->rank + 1) % P, halo, (ctx->rank + P - 1) % P, plane, st));
+  BR_LAUNCH(ctx, add_plane_kernel, cdiv(plane, 256), 256, 0, st, loc, halo, plane);
+  DistBufs b;
+  BR_TRY(dist_bufs(ctx, &b));
+  BR_TRY(dist_r2c(ctx, loc, b.T, st));
+  // sum(rho) = DC mode, held by rank 0: broadcast it with the derived scale
+  if (ctx->rank == 0) BR_TRY(stash_dc(ctx, b.T, 0, (double)ctx->M / (double)p->bias, st));
+  if (P > 1) BR_NCCL(ncclBroadcast(ctx->d_scal, ctx->d_scal, 16, ncclDouble, 0, comm_of(ctx), st));
+  float2* keep;
+  BR_TRY(need_t(ctx, BUF_CKCACHE, (size_t)ctx->ny_loc * ctx->xh * ctx->nz, &keep));
+  BR_TRY(kpass_fused_T(ctx, b.T, b.T, keep, p, st));
+  BR_TRY(dist_c2r(ctx, b.T, d_mesh_slab, st));
+  BR_TRY(check_oob(ctx, st, "run_dist (particles must lie in this rank's slab)"));
+  ctx->kcache_valid = true;
+  return BAOREC_OK;
+}
+
+int baorec_read_shifts_dist_f32(baorec_ctx* ctx, const baorec_params* p, const float* d_x, const float* d_y,
+                                const float* d_z, int64_t n_local, int field, int positions, float* d_sx,
+                                float* d_sy, float* d_sz, baorec_stream stream) {
+  BR_NEED_DIST(ctx);
+  BR_REQUIRE(p != nullptr, "params is NULL");
+  BR_REQUIRE(field >= BAOREC_FIELD_DISP && field <= BAOREC_FIELD_SUM, "unknown field");
+  BR_REQUIRE(n_local >= 0 && (n_local == 0 || (d_x && d_y && d_z && d_sx && d_sy && d_sz)), "particle arrays");
+  if (!ctx->kcache_valid) {
+    set_error("baorec_read_shifts_dist_f32: call baorec_run_dist_f32 first (no cached delta_k)");
+    return BAOREC_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = ctx->nranks, nzl = ctx->nz_loc;
+  const size_t plane = (size_t)ctx->ny * ctx->nx;
+  const int next = (ctx->rank + 1) % P, prev = (ctx->rank + P - 1) % P;
+  DistBufs b;
+  BR_TRY(dist_bufs(ctx, &b));
+  const float2* keep = (const float2*)ctx->bufs[BUF_CKCACHE].p;
+  float* psi[3];
+  BR_TRY(need_t(ctx, BUF_RX, (size_t)(nzl + 3) * plane, &psi[0]));
+  BR_TRY(need_t(ctx, BUF_RY, (size_t)(nzl + 3) * plane, &psi[1]));
+  BR_TRY(need_t(ctx, BUF_RZ, (size_t)(nzl + 3) * plane, &psi[2]));
+  for (int c = 0; c < 3; c++) {
+    BR_TRY(kpass_disp_T(ctx, keep, b.T, c, st));
+    BR_TRY(dist_c2r(ctx, b.T, psi[c] + plane, st));  // own planes at local index 1 .. nzl
+    // halo: plane 0 <- previous rank's last plane; planes nzl+1, nzl+2 <- next rank's first two
+    BR_TRY(ring_exchange(ctx, psi[c] + (size_t)nzl * plane, next, psi[c], prev, plane, st));
+    BR_TRY(ring_exchange(ctx, psi[c] + plane, prev, psi[c] + (size_t)(nzl + 1) * plane, next, 2 * plane, st));
+  }
+  BR_TRY(reset_oob(ctx, st));
+  ctx->slab_mode = 2;
+  int s = gather3(ctx, psi[0], psi[1], psi[2], d_x, d_y, d_z, n_local, d_sx, d_sy, d_sz, p->mas, field, p->f,
+                  p->has_los, p->los, positions, st);
+  ctx->slab_mode = 0;
+  if (s != BAOREC_OK) return s;
+  return check_oob(ctx, st, "read_shifts_dist (particles must lie in this rank's slab)");
 }
 
 }  // extern "C"

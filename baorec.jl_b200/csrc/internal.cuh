@@ -150,6 +150,7 @@ struct baorec_ctx {
   int rank = 0, nranks = 1;
   bool dist = false;
   int nz_loc = 0, z0 = 0, ny_loc = 0, y0 = 0;
+  int slab_mode = 0;  // 0: whole mesh; 1: scatter into a slab (+1 ghost plane); 2: gather from a slab (+3 halo planes)
   cufftHandle p2d_r2c = 0, p2d_c2r = 0, p1d = 0;
   bool have_dist_plans = false;
 };
@@ -203,6 +204,11 @@ int setup_box_dev(baorec_ctx* ctx, const float* x, const float* y, const float* 
 // ctx.cu
 int plan_common(baorec_ctx* ctx, int nx, int ny, int nz, const float L[3], const float mn[3]);
 void host_xvec(int n, float L, float mn, std::vector<float>& out);
+
+int stash_dc(baorec_ctx* ctx, const float2* ck, int slot, double mul, cudaStream_t st);
+int kpass_fused_T(baorec_ctx* ctx, const float2* in, float2* out_c2r, float2* keep, const baorec_params* p,
+                  cudaStream_t st);
+int kpass_disp_T(baorec_ctx* ctx, const float2* in, float2* out, int comp, cudaStream_t st);
 
 // multigrid.cu
 int mg_setup_levels(baorec_ctx* ctx);

@@ -459,4 +459,71 @@ int reconstructed_overdensity(baorec_ctx* ctx, const baorec_params* p, float* me
   return BAOREC_OK;
 }
 
+// ---- transposed (distributed) layout -----------------------------------------------------------
+// After the slab transpose rank r holds T[yl][ix][iz] (z contiguous) for global rows
+// y = y0 + yl.  Same Ops, different index decode.
+template <class Op>
+__global__ void __launch_bounds__(KS_THREADS)
+kspace_kernel_t(KGeom g, int y0, const float2* __restrict__ in, Op op) {
+  const int yl = blockIdx.y;
+  const unsigned plane = (unsigned)g.xh * (unsigned)g.nz;
+  const float ky = __ldg(g.ky + y0 + yl);
+  const unsigned base = blockIdx.x * (KS_THREADS * KS_UNROLL) + threadIdx.x;
+  const size_t off = (size_t)yl * plane;
+  float2 v[KS_UNROLL];
+#pragma unroll
+  for (int u = 0; u < KS_UNROLL; u++) {
+    unsigned p = base + u * KS_THREADS;
+    if (p < plane) v[u] = in[off + p];
+  }
+#pragma unroll
+  for (int u = 0; u < KS_UNROLL; u++) {
+    unsigned p = base + u * KS_THREADS;
+    if (p < plane) {
+      unsigned ix = p / (unsigned)g.nz;
+      unsigned iz = p - ix * (unsigned)g.nz;
+      op.apply(off + p, v[u], __ldg(g.kx + ix), ky, __ldg(g.kz + iz), (ix | (unsigned)(y0 + yl) | iz) == 0u);
+    }
+  }
+}
+
+template <class Op>
+static int run_kspace_t(baorec_ctx* ctx, const float2* in, Op op, cudaStream_t st) {
+  size_t plane = (size_t)ctx->xh * ctx->nz;
+  dim3 grid(cdiv(plane, KS_THREADS * KS_UNROLL), ctx->ny_loc);
+  BR_LAUNCH_NAMED(ctx, Op::name(), kspace_kernel_t<Op>, grid, KS_THREADS, 0, st, kgeom_of(ctx), ctx->y0, in, op);
+  return BAOREC_OK;
+}
+
+struct DispCompOp {  // one component of Psi = i k delta_k / k^2, /M (src/iterative.jl:268)
+  static const char* name() { return "kspace_kernel_t<DispCompOp>"; }
+  float2* out;
+  int comp;
+  float invM;
+  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool) const {
+    float k2 = ksq(kx, ky, kz);
+    float s = k2 > 0.f ? __fdiv_rn(invM, k2) : 0.f;
+    float kc = comp == 0 ? kx : (comp == 1 ? ky : kz);
+    out[idx] = make_float2(__fmul_rn(__fmul_rn(-v.y, s), kc), __fmul_rn(__fmul_rn(v.x, s), kc));
+  }
+};
+
+int stash_dc(baorec_ctx* ctx, const float2* ck, int slot, double mul, cudaStream_t st) {
+  BR_LAUNCH(ctx, stash_dc_kernel, 1, 1, 0, st, ck, ctx->d_scal, slot, mul);
+  return BAOREC_OK;
+}
+
+int kpass_fused_T(baorec_ctx* ctx, const float2* in, float2* out_c2r, float2* keep, const baorec_params* p,
+                  cudaStream_t st) {
+  const float invM = (float)(1.0 / (double)ctx->M);
+  FusedLosOp<0> op{out_c2r, keep, p->smoothing_radius * p->smoothing_radius, p->bias, ctx->d_scal,
+                   {p->los[0], p->los[1], p->los[2]}, p->beta, p->n_iter, invM};
+  return run_kspace_t(ctx, in, op, st);
+}
+
+int kpass_disp_T(baorec_ctx* ctx, const float2* in, float2* out, int comp, cudaStream_t st) {
+  DispCompOp op{out, comp, (float)(1.0 / (double)ctx->M)};
+  return run_kspace_t(ctx, in, op, st);
+}
+
 }  // namespace baorec

@@ -20,6 +20,9 @@ struct BoxGeom {
   float L[3];
   float cell[3];
   int n[3];
+  // slab decomposition (multi-GPU): the mesh buffer holds nzp planes; global plane z maps to local
+  // plane (z - z_lo + zoff) (periodic); slab == 0 -> the whole mesh, planes wrap at n[2]
+  int slab, z_lo, zoff, nzp;
 };
 
 static BoxGeom geom_of(const baorec_ctx* ctx) {
@@ -32,6 +35,10 @@ static BoxGeom geom_of(const baorec_ctx* ctx) {
   g.n[0] = ctx->nx;
   g.n[1] = ctx->ny;
   g.n[2] = ctx->nz;
+  g.slab = ctx->slab_mode != 0;
+  g.z_lo = g.slab ? ctx->z0 : 0;
+  g.zoff = ctx->slab_mode == 2 ? 1 : 0;  // gather slabs carry one halo plane below and two above
+  g.nzp = ctx->slab_mode == 1 ? ctx->nz_loc + 1 : (ctx->slab_mode == 2 ? ctx->nz_loc + 3 : ctx->nz);
   return g;
 }
 
@@ -104,6 +111,22 @@ __device__ __forceinline__ bool tsc_axis(float p, float mn, float L, int n, bool
   return true;
 }
 
+// Global plane indices (lower, upper-wrapped) -> plane indices in the local buffer.
+__device__ __forceinline__ bool local_planes(const BoxGeom& g, int z0, int z1, int& l0, int& l1) {
+  if (!g.slab) {
+    l0 = z0;
+    l1 = z1;
+    return true;
+  }
+  const int nz = g.n[2];
+  int dz = z0 - g.z_lo;          // in (-nz, nz)
+  if (dz < 0) dz += nz;          // periodic distance above the slab base, in [0, nz)
+  if (dz + g.zoff > g.nzp - 2) dz -= nz;  // not reachable from below: it is a plane under the slab
+  l0 = dz + g.zoff;
+  l1 = l0 + 1;
+  return l0 >= 0 && l1 < g.nzp;
+}
+
 // ---- per-particle bodies ---------------------------------------------------------------------
 // Deposit one (already wrapped) particle.  Returns false if it is outside the mesh.
 template <int MAS>
@@ -116,7 +139,7 @@ __device__ __forceinline__ bool deposit(float* __restrict__ rho, float px, float
     bool ok = cic_axis(px, g.mn[0], g.L[0], g.n[0], wrap, x0, x1, wx0, wx1);
     ok = cic_axis(py, g.mn[1], g.L[1], g.n[1], wrap, y0, y1, wy0, wy1) && ok;
     ok = cic_axis(pz, g.mn[2], g.L[2], g.n[2], wrap, z0, z1, wz0, wz1) && ok;
-    if (!ok) return false;
+    if (!ok || !local_planes(g, z0, z1, z0, z1)) return false;
     wx0 = __fmul_rn(wx0, ww);
     wx1 = __fmul_rn(wx1, ww);
     size_t r00 = ((size_t)z0 * ny + y0) * nx, r10 = ((size_t)z0 * ny + y1) * nx;
@@ -138,7 +161,7 @@ __device__ __forceinline__ bool deposit(float* __restrict__ rho, float px, float
     bool ok = tsc_axis(px, g.mn[0], g.L[0], g.n[0], wrap, ix, wx);
     ok = tsc_axis(py, g.mn[1], g.L[1], g.n[1], wrap, iy, wy) && ok;
     ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], wrap, iz, wz) && ok;
-    if (!ok) return false;
+    if (!ok || g.slab) return false;  // TSC slabs (two ghost planes) are not implemented
 #pragma unroll
     for (int c = 0; c < 3; c++) {
 #pragma unroll
@@ -233,6 +256,7 @@ __device__ __forceinline__ bool gather_one(const GatherArgs& a, const BoxGeom& g
     ok = gather_axis(px, g.mn[0], g.L[0], g.cell[0], g.n[0], false, xd, xu, dx, ux);
     ok = gather_axis(py, g.mn[1], g.L[1], g.cell[1], g.n[1], false, yd, yu, dy, uy) && ok;
     ok = gather_axis(pz, g.mn[2], g.L[2], g.cell[2], g.n[2], false, zd, zu, dz, uz) && ok;
+    ok = ok && local_planes(g, zd, zu, zd, zu);
     if (ok) {
       size_t rdd = ((size_t)zd * ny + yd) * nx, rdu = ((size_t)zu * ny + yd) * nx;
       size_t rud = ((size_t)zd * ny + yu) * nx, ruu = ((size_t)zu * ny + yu) * nx;
@@ -268,7 +292,7 @@ __device__ __forceinline__ bool gather_one(const GatherArgs& a, const BoxGeom& g
     float wx[3], wy[3], wz[3];
     ok = tsc_axis(px, g.mn[0], g.L[0], g.n[0], true, ix, wx);
     ok = tsc_axis(py, g.mn[1], g.L[1], g.n[1], true, iy, wy) && ok;
-    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], true, iz, wz) && ok;
+    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], true, iz, wz) && ok && !g.slab;
     if (ok) {
 #pragma unroll
       for (int c = 0; c < NF; c++) val[c] = 0.f;
@@ -353,6 +377,7 @@ __device__ __forceinline__ int bin_key(float& px, float& py, float& pz, const Bo
     ok = cic_axis(px, g.mn[0], g.L[0], g.n[0], wrap, i0, i1, w0, w1);
     ok = cic_axis(py, g.mn[1], g.L[1], g.n[1], wrap, i0, i1, w0, w1) && ok;
     ok = cic_axis(pz, g.mn[2], g.L[2], g.n[2], wrap, i0, i1, w0, w1) && ok;
+    ok = ok && local_planes(g, i0, i1, i0, i1);
     zb = i0;
   } else if (MAS == BAOREC_MAS_TSC) {
     int idx[3];
@@ -360,7 +385,7 @@ __device__ __forceinline__ int bin_key(float& px, float& py, float& pz, const Bo
     bool wr = MODE == BIN_GATHER ? true : (wrap != 0);
     ok = tsc_axis(px, g.mn[0], g.L[0], g.n[0], wr, idx, w);
     ok = tsc_axis(py, g.mn[1], g.L[1], g.n[1], wr, idx, w) && ok;
-    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], wr, idx, w) && ok;
+    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], wr, idx, w) && ok && !g.slab;
     zb = idx[1];
   } else {
     int id, iu;
@@ -368,6 +393,7 @@ __device__ __forceinline__ int bin_key(float& px, float& py, float& pz, const Bo
     ok = gather_axis(px, g.mn[0], g.L[0], g.cell[0], g.n[0], false, id, iu, wd, wu);
     ok = gather_axis(py, g.mn[1], g.L[1], g.cell[1], g.n[1], false, id, iu, wd, wu) && ok;
     ok = gather_axis(pz, g.mn[2], g.L[2], g.cell[2], g.n[2], false, id, iu, wd, wu) && ok;
+    ok = ok && local_planes(g, id, iu, id, iu);
     zb = id;
   }
   return ok ? zb / zg : nbins;
@@ -509,7 +535,7 @@ __device__ __forceinline__ unsigned tile_key(float px, float py, float pz, const
     ix = idx[1];
     ok = tsc_axis(py, g.mn[1], g.L[1], g.n[1], true, idx, w) && ok;
     iy = idx[1];
-    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], true, idx, w) && ok;
+    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], true, idx, w) && ok && !g.slab;
     iz = idx[1];
   } else {
     int iu;
@@ -517,6 +543,7 @@ __device__ __forceinline__ unsigned tile_key(float px, float py, float pz, const
     ok = gather_axis(px, g.mn[0], g.L[0], g.cell[0], g.n[0], false, ix, iu, wd, wu);
     ok = gather_axis(py, g.mn[1], g.L[1], g.cell[1], g.n[1], false, iy, iu, wd, wu) && ok;
     ok = gather_axis(pz, g.mn[2], g.L[2], g.cell[2], g.n[2], false, iz, iu, wd, wu) && ok;
+    ok = ok && local_planes(g, iz, iu, iz, iu);
   }
   if (!ok) return t.ntiles;
   return ((unsigned)iz * t.nyc + (unsigned)(iy / TILE_Y)) * t.nxc + (unsigned)(ix / TILE_X);
@@ -641,7 +668,7 @@ gather_tile_kernel(GatherArgs a, const float4* __restrict__ rec, const unsigned*
     if (xe >= nx) xe -= nx;
     int zrow[2];
     zrow[0] = iz;
-    zrow[1] = iz + 1 >= nz ? 0 : iz + 1;
+    zrow[1] = g.slab ? iz + 1 : (iz + 1 >= nz ? 0 : iz + 1);
 #pragma unroll
     for (int r = 0; r < NF * 2 * (TILE_Y + 1); r++) {
       if ((r & 3) != warp) continue;
@@ -667,7 +694,7 @@ gather_tile_kernel(GatherArgs a, const float4* __restrict__ rec, const unsigned*
       int q = row / (wy + 1);
       int pz = q & 1, f = q >> 1;
       int zz = iz + pz;
-      if (zz >= nz) zz -= nz;
+      if (!g.slab && zz >= nz) zz -= nz;
       int yy = y0 + py;
       if (yy >= ny) yy -= ny;
       const float* fld = f == 0 ? a.f[0] : (f == 1 ? a.f[NF > 1 ? 1 : 0] : a.f[NF > 2 ? 2 : 0]);
@@ -736,12 +763,13 @@ static int bin_particles(baorec_ctx* ctx, float* x, float* y, float* z, const fl
                          cudaStream_t st, BinResult* out) {
   BoxGeom g = geom_of(ctx);
   int zg = MODE == BIN_SCATTER ? ctx->opt_zg_scatter : ctx->opt_zg_gather;
+  const int nzp = g.nzp;
   if (zg <= 0) zg = MODE == BIN_SCATTER ? (ctx->nz + 511) / 512 : 1;  // auto: window << L2
   if (zg < 1) zg = 1;
-  int nbins = (ctx->nz + zg - 1) / zg;
+  int nbins = (nzp + zg - 1) / zg;
   if (nbins > BIN_MAX) {
-    zg = (ctx->nz + BIN_MAX - 1) / BIN_MAX;
-    nbins = (ctx->nz + zg - 1) / zg;
+    zg = (nzp + BIN_MAX - 1) / BIN_MAX;
+    nbins = (nzp + zg - 1) / zg;
   }
   unsigned* cnt;
   float4* rec;
@@ -784,7 +812,7 @@ static int bin_tiles(baorec_ctx* ctx, const float* x, const float* y, const floa
   TileGeom t;
   t.nxc = (ctx->nx + TILE_X - 1) / TILE_X;
   t.nyc = (ctx->ny + TILE_Y - 1) / TILE_Y;
-  t.ntiles = (unsigned)ctx->nz * t.nyc * t.nxc;
+  t.ntiles = (unsigned)g.nzp * t.nyc * t.nxc;
   const unsigned m = t.ntiles + 1;  // + trash bin
   const unsigned nsb = cdiv(m, SCAN_CHUNK);
   unsigned* cnt;

@@ -1,0 +1,149 @@
+"""Multi-GPU host side: one process per GPU (torchrun), z-slab decomposition.
+
+torch.distributed is the plumbing (rendezvous, the NCCL unique id broadcast and the particle
+redistribution); the data path -- slab FFT transposes, ghost/halo planes -- runs inside the
+library over its own NCCL communicator."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib_loader as L
+from .host import Context, FFTPlan, _chk_vec, _ptr, _stream
+
+
+# ---- host logic (pure numpy / torch.distributed; runs on CPU with gloo) --------------------------
+def owner_of_z(z, box_min_z, box_size_z, nz, world, box_min_0=None, box_size_0=None):
+    """Owner rank of each particle = slab of the base plane cic! deposits into (src/mas.jl:8-30),
+    evaluated with the reference's Float32 arithmetic; -1 for out-of-box particles."""
+    z = np.asarray(z, np.float32)
+    mn, Lz = np.float32(box_min_z), np.float32(box_size_z)
+    mn0 = mn if box_min_0 is None else np.float32(box_min_0)
+    L0 = Lz if box_size_0 is None else np.float32(box_size_0)
+    zw = np.where((z - mn0) > L0, (z - L0).astype(np.float32), z).astype(np.float32)   # upper-face wrap (quirk: axis-1 box)
+    g = (((zw - mn) * np.float32(nz)).astype(np.float32) / Lz).astype(np.float32) + np.float32(1)
+    c0 = np.floor(g).astype(np.int64)
+    c0 = np.where(c0 == nz + 1, 1, c0)
+    ok = (g >= 1) & (c0 >= 1) & (c0 <= nz)
+    return np.where(ok, (c0 - 1) // (nz // world), -1).astype(np.int32)
+
+
+def shard_catalog(x, y, z, w, box_size, box_min, nz, world):
+    """Splits host arrays into per-rank lists by slab ownership (used before the upload)."""
+    own = owner_of_z(z, box_min[2], box_size[2], nz, world, box_min[0], box_size[0])
+    if (own < 0).any():
+        raise L.OutOfBoxError(L.ERR_OUT_OF_BOX, f"{int((own < 0).sum())} particle(s) outside the box")
+    return [tuple(a[own == r] for a in (x, y, z, w)) for r in range(world)]
+
+
+def exchange_catalog(x, y, z, w, box_size, box_min, nz, group=None):
+    """Every rank holds an arbitrary part of the catalog (torch tensors on CPU or GPU); after the
+    call it holds exactly the particles of its own slab.  One all_to_all_single per column."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    own = torch.from_numpy(owner_of_z(z.cpu().numpy(), box_min[2], box_size[2], nz, world, box_min[0], box_size[0]))
+    if (own < 0).any():
+        raise L.OutOfBoxError(L.ERR_OUT_OF_BOX, "particle(s) outside the box")
+    order = torch.argsort(own, stable=True).to(x.device)
+    counts = torch.bincount(own, minlength=world).to(torch.int64)
+    recv_counts = torch.empty_like(counts)
+    cdev = counts.to(x.device)
+    rdev = torch.empty_like(cdev)
+    dist.all_to_all_single(rdev, cdev, group=group)
+    recv_counts = rdev.cpu()
+    outs = []
+    for col in (x, y, z, w):
+        send = col[order].contiguous()
+        recv = torch.empty(int(recv_counts.sum()), dtype=col.dtype, device=col.device)
+        dist.all_to_all_single(recv, send, output_split_sizes=recv_counts.tolist(),
+                               input_split_sizes=counts.tolist(), group=group)
+        outs.append(recv)
+    return tuple(outs)
+
+
+# ---- library side ---------------------------------------------------------------------------------
+def init_comm(ctx: Context = None):
+    """Creates the library's NCCL communicator from torch.distributed's ranks."""
+    import torch.distributed as dist
+    ctx = ctx or Context.get()
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        L.check(ctx.lib.baorec_comm_init(ctx.handle, 0, 1, None))
+        return ctx
+    rank, world = dist.get_rank(), dist.get_world_size()
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = (C.c_ubyte * 128)()
+        L.check(ctx.lib.baorec_comm_unique_id(buf))
+        uid = torch.tensor(list(buf), dtype=torch.uint8)
+    dev = torch.device("cuda", ctx.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+    uid = uid.to(dev)
+    dist.broadcast(uid, 0)
+    raw = bytes(uid.cpu().tolist())
+    L.check(ctx.lib.baorec_comm_init(ctx.handle, rank, world, C.create_string_buffer(raw, 128)))
+    return ctx
+
+
+def plan(ctx: Context, grid_size, box_size, box_min):
+    nx, ny, nz = (int(v) for v in grid_size)
+    L.check(ctx.lib.baorec_plan_dist(ctx.handle, nx, ny, nz, L.f3(box_size), L.f3(box_min)))
+    ctx.plan_key = ("dist", nx, ny, nz, tuple(float(np.float32(v)) for v in box_size),
+                    tuple(float(np.float32(v)) for v in box_min))
+    return ctx
+
+
+def slab_range(ctx: Context):
+    a, b = C.c_int(), C.c_int()
+    L.check(ctx.lib.baorec_slab_range(ctx.handle, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def slab_owner(ctx: Context, z):
+    n = _chk_vec(z)
+    out = torch.empty(n, dtype=torch.int32, device=z.device)
+    L.check(ctx.lib.baorec_slab_owner_f32(ctx.handle, _ptr(z), n, _ptr(out), _stream()))
+    return out
+
+
+def dist_r2c(ctx: Context, slab):
+    nzl, ny, nx = slab.shape
+    z_lo, nz_loc = slab_range(ctx)
+    assert nzl == nz_loc
+    world = ctx.plan_key[3] // nz_loc
+    out = torch.empty((ny // world, nx // 2 + 1, ctx.plan_key[3]), dtype=torch.complex64, device=slab.device)
+    L.check(ctx.lib.baorec_dist_r2c_f32(ctx.handle, _ptr(slab), _ptr(out), _stream()))
+    return out
+
+
+def dist_c2r(ctx: Context, kslab_t, out_slab):
+    L.check(ctx.lib.baorec_dist_c2r_f32(ctx.handle, _ptr(kslab_t), _ptr(out_slab), _stream()))
+    return out_slab
+
+
+def run_dist(recon, grid_size, data_x, data_y, data_z, data_w, ctx: Context = None):
+    """run!(recon, grid_size, data...) over all ranks: pass this rank's slab particles, get this
+    rank's slab of the reconstructed mesh, shape (nz_loc, ny, nx)."""
+    n = _chk_vec(data_x, data_y, data_z, data_w)
+    ctx = ctx or Context.get(data_x.device.index)
+    plan(ctx, grid_size, recon.box_size, recon.box_min)
+    recon.fft_plan = FFTPlan(ctx, tuple(int(v) for v in grid_size))
+    _, nzl = slab_range(ctx)
+    nx, ny, nz = (int(v) for v in grid_size)
+    mesh = torch.empty((nzl, ny, nx), dtype=torch.float32, device=data_x.device)
+    p = recon._params()
+    L.check(ctx.lib.baorec_run_dist_f32(ctx.handle, C.byref(p), recon.algorithm, _ptr(data_x), _ptr(data_y),
+                                        _ptr(data_z), _ptr(data_w), n, _ptr(mesh), _stream()))
+    recon.result_cache = mesh
+    return mesh
+
+
+def read_shifts_dist(recon, data_x, data_y, data_z, field="disp", positions=False):
+    n = _chk_vec(data_x, data_y, data_z)
+    ctx = recon.fft_plan.ctx
+    p = recon._params()
+    out = tuple(torch.empty_like(data_x) for _ in range(3))
+    L.check(ctx.lib.baorec_read_shifts_dist_f32(ctx.handle, C.byref(p), _ptr(data_x), _ptr(data_y), _ptr(data_z), n,
+                                                L.FIELDS[field], int(bool(positions)), _ptr(out[0]), _ptr(out[1]),
+                                                _ptr(out[2]), _stream()))
+    return out

@@ -120,8 +120,31 @@ int baorec_profile_read(baorec_ctx* ctx, char* names, int name_stride, float* to
  * (torch.distributed / MPI.jl). */
 int baorec_comm_unique_id(void* out128);
 int baorec_comm_init(baorec_ctx* ctx, int rank, int nranks, const void* unique_id128);
-/* Distributed plan: this rank owns z-planes [rank*nz/P, (rank+1)*nz/P). */
+/* Distributed plan: this rank owns z-planes [rank*nz/P, (rank+1)*nz/P) in real space and the
+ * rows y in [rank*ny/P, (rank+1)*ny/P) in k space (nz, ny divisible by P).  With nranks == 1 no
+ * communicator is needed (baorec_comm_init(ctx, 0, 1, NULL)). */
 int baorec_plan_dist(baorec_ctx* ctx, int nx, int ny, int nz, const float box_size[3], const float box_min[3]);
+int baorec_slab_range(const baorec_ctx* ctx, int* z_lo, int* nz_loc);
+/* Owner rank of every particle = slab of its cic! base plane (src/mas.jl:15-30), -1 if out of box. */
+int baorec_slab_owner_f32(baorec_ctx* ctx, const float* d_z, int64_t n, int32_t* d_owner, baorec_stream stream);
+/* Slab-decomposed transforms (unnormalised): real slab [nz_loc][ny][nx] <-> transposed k slab
+ * [ny_loc][nx/2+1][nz] (complex, z contiguous).  2-D cuFFT over the local planes, hand-written
+ * pack / tile-transpose kernels, grouped ncclSend/ncclRecv all-to-all, 1-D cuFFT along z. */
+int baorec_dist_r2c_f32(baorec_ctx* ctx, const float* d_slab, float* d_kslab_t, baorec_stream stream);
+int baorec_dist_c2r_f32(baorec_ctx* ctx, float* d_kslab_t /* destroyed */, float* d_slab, baorec_stream stream);
+/* run! (src/recon.jl:134-153) across the ranks: every rank passes the particles whose base plane
+ * lies in its slab (baorec_slab_owner_f32) and receives its slab of the reconstructed mesh.
+ * Scatter into slab + ghost plane, ghost sent to the next rank and added, distributed R2C, fused
+ * k-space solve in the transposed layout (DC broadcast from rank 0), distributed C2R.  delta_k is
+ * kept (transposed) for baorec_read_shifts_dist_f32.  This build distributes IterativeRecon with
+ * a fixed line of sight and CIC; other modes return BAOREC_ERR_INVALID. */
+int baorec_run_dist_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, float* d_x, float* d_y, float* d_z,
+                        const float* d_w, int64_t n_local, float* d_mesh_slab, baorec_stream stream);
+/* read_shifts / reconstructed_positions (positions != 0) for this rank's particles: three
+ * distributed C2R of i k delta_k / k^2, halo planes exchanged with both neighbours, gather. */
+int baorec_read_shifts_dist_f32(baorec_ctx* ctx, const baorec_params* p, const float* d_x, const float* d_y,
+                                const float* d_z, int64_t n_local, int field, int positions, float* d_sx,
+                                float* d_sy, float* d_sz, baorec_stream stream);
 
 /* ---- mass assignment (replaces cic!/read_cic! CuArray methods) ------------- */
 /* cic!(rho::CuArray, ...; wrap) src/mas.jl:53-107.  Accumulates into d_rho (caller
