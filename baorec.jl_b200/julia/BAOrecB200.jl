@@ -1,0 +1,291 @@
+# BAOrecB200.jl -- drop-in device back end for BAOrec.jl on NVIDIA B200 (sm_100a).
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: neither Julia nor CUDA.jl is installed in the build
+# image.  The identical C ABI is exercised end to end by the Python ctypes mirror
+# (baorec.jl_b200/host.py) and the GPU parity tests; this file is the binding a BAOrec.jl
+# maintainer adds.  It re-defines the CuArray methods of the reference (same names, same
+# positional signatures, same in-place semantics) as thin `ccall`s into libbaorec_b200.so:
+#
+#   reference method (file:line)                         -> C entry point
+#   setup_fft!(recon, ::CuArray)        src/recon.jl:35   -> baorec_plan
+#   cic!(ρ::CuArray, ...)               src/mas.jl:100    -> baorec_cic_scatter_f32
+#   read_cic!(out::CuArray, ...)        src/mas.jl:320    -> baorec_gather_f32
+#   smooth!(::CuArray, ...)             src/utils.jl:85   -> baorec_smooth_f32
+#   setup_overdensity!(::CuArray, ...)  src/recon.jl:42,60-> baorec_setup_overdensity_f32
+#   iterate!(::CuArray, ...)            src/iterative.jl:151 -> baorec_iterate_f32
+#   reconstructed_overdensity!          src/recon.jl:93,111  -> baorec_reconstructed_overdensity_f32
+#   jacobi!/residual!/reduce!/prolong!/vcycle!/fmg  src/multigrid.jl:193,378,641,511,689,722
+#                                                        -> baorec_mg_*_f32
+#   reconstructed_potential!            src/recon.jl:184,198 -> baorec_reconstructed_potential_f32
+#   compute_displacements(::CuArray..)  src/iterative.jl:229, src/multigrid.jl:781
+#                                                        -> baorec_compute_displacements_f32
+#   read_shifts(...::CuVector...)       src/recon.jl:333  -> baorec_read_shifts_f32
+#   reconstructed_positions             src/recon.jl:366  -> baorec_reconstructed_positions_f32
+#   setup_box                           src/utils.jl:100  -> baorec_setup_box_f32
+#
+# Usage inside BAOrec.jl:  include("BAOrecB200.jl") after the other includes; every method
+# below is more specific than the generic AbstractArray ones, so CuArray inputs dispatch here.
+
+module BAOrecB200
+
+using CUDA
+using StaticArrays
+import ..BAOrec: AbstractRecon, IterativeRecon, MultigridRecon, setup_fft!, cic!, read_cic!, smooth!,
+                 setup_overdensity!, iterate!, reconstructed_overdensity!, reconstructed_potential!,
+                 jacobi!, residual!, reduce!, prolong!, vcycle!, fmg, compute_displacements,
+                 read_shifts, reconstructed_positions, setup_box
+
+const libbaorec = get(ENV, "BAOREC_B200_LIB", "libbaorec_b200.so")
+
+# struct baorec_params (include/baorec_b200.h) -- field order and types must match exactly
+struct Params
+    bias::Cfloat
+    f::Cfloat
+    smoothing_radius::Cfloat
+    beta::Cfloat
+    n_iter::Int32
+    has_los::Int32
+    los::NTuple{3,Cfloat}
+    jacobi_damping_factor::Cfloat
+    jacobi_niterations::Int32
+    vcycle_niterations::Int32
+    mas::Int32
+    ran_min::Cfloat
+    box_pad::Cfloat
+end
+
+const ITERATIVE = Cint(0)
+const MULTIGRID = Cint(1)
+const FIELD = Dict(:disp => Cint(0), :rsd => Cint(1), :sum => Cint(2))
+
+algorithm(::IterativeRecon) = ITERATIVE
+algorithm(::MultigridRecon) = MULTIGRID
+
+function Params(r::AbstractRecon)
+    los = r.los === nothing ? (0f0, 0f0, 0f0) : (Float32(r.los[1]), Float32(r.los[2]), Float32(r.los[3]))
+    Params(Float32(r.bias), Float32(r.f), Float32(r.smoothing_radius), Float32(r.β),
+           Int32(r isa IterativeRecon ? r.n_iter : 0), Int32(r.los === nothing ? 0 : 1), los,
+           Float32(r isa MultigridRecon ? r.jacobi_damping_factor : 0.4f0),
+           Int32(r isa MultigridRecon ? r.jacobi_niterations : 5),
+           Int32(r isa MultigridRecon ? r.vcycle_niterations : 6),
+           Int32(0), 0.01f0, 500f0)
+end
+
+struct BaorecError <: Exception
+    code::Cint
+    msg::String
+end
+
+function check(code::Cint)
+    code == 0 && return nothing
+    msg = unsafe_string(ccall((:baorec_last_error, libbaorec), Cstring, ()))
+    throw(BaorecError(code, msg))     # -5 = particle outside the mesh (reference: BoundsError)
+end
+
+# One context per device, created lazily; it owns plans and all scratch memory.
+const CTX = Dict{Int,Ptr{Cvoid}}()
+function context()
+    dev = CUDA.deviceid(CUDA.device())
+    get!(CTX, dev) do
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:baorec_create, libbaorec), Cint, (Cint, Ptr{Ptr{Cvoid}}), dev, h))
+        h[]
+    end
+end
+
+stream() = CUDA.stream().handle            # the caller's task-local stream
+f3(v) = Ref((Float32(v[1]), Float32(v[2]), Float32(v[3])))
+ptr(a::CuArray{Float32}) = reinterpret(Ptr{Cvoid}, pointer(a))
+ptr(::Nothing) = C_NULL
+
+function plan!(mesh::CuArray{Float32,3}, box_size, box_min)
+    ctx = context()
+    nx, ny, nz = size(mesh)
+    check(ccall((:baorec_plan, libbaorec), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cfloat}, Ptr{Cfloat}),
+                ctx, nx, ny, nz, f3(box_size), f3(box_min)))
+    ctx
+end
+
+# setup_fft! -- the plan object the reference stores in recon.fft_plan is the context handle here
+function setup_fft!(recon::AbstractRecon, field::CuArray{Float32,3})
+    recon.fft_plan = context()
+end
+
+function cic!(ρ::CuArray{Float32,3}, x::CuArray{Float32}, y::CuArray{Float32}, z::CuArray{Float32},
+              w::CuArray{Float32}, box_size::SVector{3,Float32}, box_min::SVector{3,Float32}; wrap::Bool = true)
+    ctx = plan!(ρ, box_size, box_min)
+    check(ccall((:baorec_cic_scatter_f32, libbaorec), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint, Cint, Ptr{Cvoid}),
+                ctx, ptr(ρ), ptr(x), ptr(y), ptr(z), ptr(w), length(x), wrap, 0, stream()))
+    ρ
+end
+
+function read_cic!(out::CuArray{Float32}, field::CuArray{Float32,3}, x::CuArray{Float32}, y::CuArray{Float32},
+                   z::CuArray{Float32}, box_size::SVector{3,Float32}, box_min::SVector{3,Float32}; wrap = true)
+    ctx = plan!(field, box_size, box_min)
+    check(ccall((:baorec_gather_f32, libbaorec), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+                ctx, ptr(field), ptr(x), ptr(y), ptr(z), length(x), ptr(out), 0, stream()))
+    out
+end
+
+function smooth!(field::CuArray{Float32,3}, smoothing_radius::Float32, box_size::SVector{3,Float32}, fft_plan)
+    ctx = plan!(field, box_size, SVector(0f0, 0f0, 0f0))
+    check(ccall((:baorec_smooth_f32, libbaorec), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cfloat, Ptr{Cvoid}),
+                ctx, ptr(field), smoothing_radius, stream()))
+    field
+end
+
+function _catalog_call(sym::Symbol, mesh, recon, d, r; extra = ())
+    ctx = plan!(mesh, recon.box_size, recon.box_min)
+    p = Ref(Params(recon))
+    nr = r === nothing ? 0 : length(r[1])
+    rp = r === nothing ? (C_NULL, C_NULL, C_NULL, C_NULL) : map(ptr, r)
+    ctx, p, nr, rp
+end
+
+function setup_overdensity!(δ::CuArray{Float32,3}, recon::AbstractRecon, x::CuArray{Float32}, y::CuArray{Float32},
+                            z::CuArray{Float32}, w::CuArray{Float32}, wrap = true)
+    ctx, p, _, rp = _catalog_call(:setup, δ, recon, (x, y, z, w), nothing)
+    check(ccall((:baorec_setup_overdensity_f32, libbaorec), Cint,
+                (Ptr{Cvoid}, Ptr{Params}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64,
+                 Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint, Ptr{Cvoid}),
+                ctx, p, ptr(δ), ptr(x), ptr(y), ptr(z), ptr(w), length(x), rp..., 0, wrap, stream()))
+    δ
+end
+
+function setup_overdensity!(δ::CuArray{Float32,3}, recon::AbstractRecon, x::CuArray{Float32}, y::CuArray{Float32},
+                            z::CuArray{Float32}, w::CuArray{Float32}, rx::CuArray{Float32}, ry::CuArray{Float32},
+                            rz::CuArray{Float32}, rw::CuArray{Float32}, ran_min = 0.01)
+    ctx, p, nr, rp = _catalog_call(:setup, δ, recon, (x, y, z, w), (rx, ry, rz, rw))
+    check(ccall((:baorec_setup_overdensity_f32, libbaorec), Cint,
+                (Ptr{Cvoid}, Ptr{Params}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64,
+                 Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint, Ptr{Cvoid}),
+                ctx, p, ptr(δ), ptr(x), ptr(y), ptr(z), ptr(w), length(x), rp..., nr, false, stream()))
+    δ
+end
+
+function iterate!(δ_r::CuArray{Float32,3}, δ_s::CuArray{Float32,3}, k⃗, iter::Int, β::Float32, fft_plan;
+                  r̂ = nothing, x⃗ = nothing)
+    # k⃗ / x⃗ are accepted for signature parity; the plan holds the same tables on the device
+    los = r̂ === nothing ? C_NULL : f3(r̂)
+    check(ccall((:baorec_iterate_f32, libbaorec), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cfloat, Ptr{Cfloat}, Ptr{Cvoid}),
+                context(), ptr(δ_r), ptr(δ_s), iter, β, los, stream()))
+    δ_r
+end
+
+for (fn, sym) in ((:reconstructed_overdensity!, :baorec_reconstructed_overdensity_f32),
+                  (:reconstructed_potential!, :baorec_reconstructed_potential_f32))
+    R = fn === :reconstructed_overdensity! ? :IterativeRecon : :MultigridRecon
+    @eval function $fn(mesh::CuArray{Float32,3}, recon::$R, x::CuArray{Float32}, y::CuArray{Float32},
+                       z::CuArray{Float32}, w::CuArray{Float32}, r::CuArray{Float32}...)
+        rr = length(r) == 4 ? r : nothing
+        ctx, p, nr, rp = _catalog_call($(QuoteNode(fn)), mesh, recon, (x, y, z, w), rr)
+        check(ccall(($(QuoteNode(sym)), libbaorec), Cint,
+                    (Ptr{Cvoid}, Ptr{Params}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64,
+                     Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}),
+                    ctx, p, ptr(mesh), ptr(x), ptr(y), ptr(z), ptr(w), length(x), rp..., nr, stream()))
+        mesh
+    end
+end
+
+function compute_displacements(mesh::CuArray{Float32,3}, x::CuVector{Float32}, y::CuVector{Float32},
+                               z::CuVector{Float32}, recon::AbstractRecon)
+    ctx = plan!(mesh, recon.box_size, recon.box_min)
+    out = Tuple(similar(x) for _ in 1:3)
+    check(ccall((:baorec_compute_displacements_f32, libbaorec), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid},
+                 Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+                ctx, ptr(mesh), algorithm(recon), ptr(x), ptr(y), ptr(z), length(x), ptr(out[1]), ptr(out[2]),
+                ptr(out[3]), 0, stream()))
+    out
+end
+
+function _read(sym::Symbol, recon, x, y, z, mesh, field)
+    ctx = plan!(mesh, recon.box_size, recon.box_min)
+    out = Tuple(similar(x) for _ in 1:3)
+    p = Ref(Params(recon))
+    check(ccall((sym, libbaorec), Cint,
+                (Ptr{Cvoid}, Ptr{Params}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint,
+                 Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                ctx, p, algorithm(recon), ptr(mesh), ptr(x), ptr(y), ptr(z), length(x), FIELD[field],
+                ptr(out[1]), ptr(out[2]), ptr(out[3]), stream()))
+    out
+end
+
+read_shifts(recon::AbstractRecon, x::CuVector{Float32}, y::CuVector{Float32}, z::CuVector{Float32},
+            mesh::CuArray{Float32,3}; field = :disp) = _read(:baorec_read_shifts_f32, recon, x, y, z, mesh, field)
+
+reconstructed_positions(recon::AbstractRecon, x::CuVector{Float32}, y::CuVector{Float32}, z::CuVector{Float32},
+                        mesh::CuArray{Float32,3}; field = :disp) =
+    _read(:baorec_reconstructed_positions_f32, recon, x, y, z, mesh, field)
+
+function setup_box(x::CuVector{Float32}, y::CuVector{Float32}, z::CuVector{Float32}, box_pad)
+    bs = Ref((0f0, 0f0, 0f0)); bm = Ref((0f0, 0f0, 0f0))
+    check(ccall((:baorec_setup_box_f32, libbaorec), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cfloat, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cvoid}),
+                context(), ptr(x), ptr(y), ptr(z), length(x), Float32(box_pad), bs, bm, stream()))
+    SVector(bs[]...), SVector(bm[]...)
+end
+
+# ---- multigrid primitives (src/multigrid.jl) -------------------------------------------------
+_los(los) = los === nothing ? C_NULL : f3(los)
+
+function jacobi!(v::CuArray{Float32,3}, f::CuArray{Float32,3}, x_vec, box_size, box_min, β::Float32,
+                 damping_factor::Float32, niterations::Int; los = nothing)
+    ctx = plan!(v, box_size, box_min)
+    check(ccall((:baorec_mg_jacobi_f32, libbaorec), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Cfloat, Cfloat, Cint, Ptr{Cfloat}, Ptr{Cvoid}),
+                ctx, ptr(v), ptr(f), size(v)..., β, damping_factor, niterations, _los(los), stream()))
+    v
+end
+
+function residual!(r::CuArray{Float32,3}, v::CuArray{Float32,3}, f::CuArray{Float32,3}, x_vec, box_size, box_min,
+                   β::Float32, damping_factor::Float32, niterations::Int; los = nothing)
+    ctx = plan!(v, box_size, box_min)
+    check(ccall((:baorec_mg_residual_f32, libbaorec), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Cfloat, Ptr{Cfloat}, Ptr{Cvoid}),
+                ctx, ptr(r), ptr(v), ptr(f), size(v)..., β, _los(los), stream()))
+    r
+end
+
+function reduce!(v2h::CuArray{Float32,3}, v1h::CuArray{Float32,3})
+    check(ccall((:baorec_mg_restrict_f32, libbaorec), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cvoid}),
+                context(), ptr(v2h), ptr(v1h), size(v1h)..., stream()))
+    v2h
+end
+
+function prolong!(v1h::CuArray{Float32,3}, v2h::CuArray{Float32,3})
+    check(ccall((:baorec_mg_prolong_f32, libbaorec), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cvoid}),
+                context(), ptr(v1h), ptr(v2h), size(v1h)..., stream()))
+    v1h
+end
+
+function vcycle!(v::CuArray{Float32,3}, f::CuArray{Float32,3}, box_size, box_min, β::Float32,
+                 damping_factor::Float32, niterations::Int; los = nothing)
+    ctx = plan!(v, box_size, box_min)
+    check(ccall((:baorec_mg_vcycle_f32, libbaorec), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cfloat, Cfloat, Cint, Ptr{Cfloat}, Ptr{Cvoid}),
+                ctx, ptr(v), ptr(f), β, damping_factor, niterations, _los(los), stream()))
+    v
+end
+
+function fmg(f1h::CuArray{Float32,3}, v1h::Union{CuArray{Float32,3},Nothing}, box_size, box_min, β::Float32,
+             jacobi_damping_factor::Float32, jacobi_niterations::Int, vcycle_niterations::Int; los = nothing)
+    v1h === nothing && (v1h = CUDA.zeros(Float32, size(f1h)...))
+    ctx = plan!(v1h, box_size, box_min)
+    check(ccall((:baorec_mg_fmg_f32, libbaorec), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cfloat, Cfloat, Cint, Cint, Ptr{Cfloat}, Ptr{Cvoid}),
+                ctx, ptr(f1h), ptr(v1h), β, jacobi_damping_factor, jacobi_niterations, vcycle_niterations,
+                _los(los), stream()))
+    v1h
+end
+
+# run! needs no override: the reference's run! (src/recon.jl:134-261) allocates a CuArray mesh when
+# data_x isa CuArray and calls setup_fft!, setup_box and reconstructed_*! -- all of which dispatch
+# to the methods above.
+
+end # module
