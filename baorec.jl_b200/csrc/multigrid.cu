@@ -58,13 +58,9 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 mg_stencil_generic(float* __restrict__ out, const float* __restrict__ v, const float* __restrict__ f, MgGeom g,
                    float omega) {
-  size_t cells = (size_t)g.nx * g.ny * g.nz;
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= cells) return;
-  int ix = (int)(idx % g.nx);
-  size_t t = idx / g.nx;
-  int iy = (int)(t % g.ny);
-  int iz = (int)(t / g.ny);
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y * blockDim.y + threadIdx.y, iz = blockIdx.z;
+  if (ix >= g.nx || iy >= g.ny) return;
+  const size_t idx = ((size_t)iz * g.ny + iy) * g.nx + ix;
   int xp = ix + 1 == g.nx ? 0 : ix + 1, xm = ix == 0 ? g.nx - 1 : ix - 1;
   int yp = iy + 1 == g.ny ? 0 : iy + 1, ym = iy == 0 ? g.ny - 1 : iy - 1;
   int zp = iz + 1 == g.nz ? 0 : iz + 1, zm = iz == 0 ? g.nz - 1 : iz - 1;
@@ -119,7 +115,7 @@ __device__ __forceinline__ Row6 load_row(const float* __restrict__ row, int x0, 
 }
 
 // grid: x = row-chunks, y = iy (TY rows per block via threadIdx.y), z = z-chunks.
-template <int MODE>
+template <int MODE, bool RADIAL>
 __global__ void __launch_bounds__(256)
 mg_stencil_march(float* __restrict__ out, const float* __restrict__ v, const float* __restrict__ f, MgGeom g,
                  float omega, int zchunk) {
@@ -136,7 +132,7 @@ mg_stencil_march(float* __restrict__ out, const float* __restrict__ v, const flo
   const size_t rm = (size_t)ym * nx, r0 = (size_t)iy * nx, rp = (size_t)yp * nx;
 
   float px[MG_VX], py, pz = 0.f;
-  if (g.radial) {
+  if (RADIAL) {
 #pragma unroll
     for (int k = 0; k < MG_VX; k++) px[k] = mg_p(g, 0, x0 + k);
     py = mg_p(g, 1, iy);
@@ -146,6 +142,10 @@ mg_stencil_march(float* __restrict__ out, const float* __restrict__ v, const flo
     py = g.lp[1];
     pz = g.lp[2];
   }
+  float ax2[MG_VX];
+#pragma unroll
+  for (int k = 0; k < MG_VX; k++) ax2[k] = g.c2[0] * px[k] * px[k];
+  const float by2 = g.c2[1] * py * py;
 
   // planes: A = z-1, B = z, C = z+1; each holds rows y-1, y, y+1
   Row6 Am, A0, Ap, Bm, B0, Bp, Cm, C0, Cp;
@@ -160,6 +160,7 @@ mg_stencil_march(float* __restrict__ out, const float* __restrict__ v, const flo
     B0 = load_row(pb + r0, x0, xm, xp);
     Bp = load_row(pb + rp, x0, xm, xp);
   }
+#pragma unroll 3
   for (int iz = zbeg; iz < zend; iz++) {
     int zc = iz + 1 == nz ? 0 : iz + 1;
     const float* pc = v + (size_t)zc * plane;
@@ -168,7 +169,8 @@ mg_stencil_march(float* __restrict__ out, const float* __restrict__ v, const flo
     Cp = load_row(pc + rp, x0, xm, xp);
     const size_t o = (size_t)iz * plane + r0 + x0;
     float4 fv = __ldg(reinterpret_cast<const float4*>(f + o));
-    if (g.radial) pz = mg_p(g, 2, iz);
+    if (RADIAL) pz = mg_p(g, 2, iz);
+    const float cz2 = g.c2[2] * pz * pz, byz = by2 + cz2;
 
     const float bm[6] = {Bm.m, Bm.a, Bm.b, Bm.c, Bm.d, Bm.p};
     const float b0[6] = {B0.m, B0.a, B0.b, B0.c, B0.d, B0.p};
@@ -182,7 +184,8 @@ mg_stencil_march(float* __restrict__ out, const float* __restrict__ v, const flo
 #pragma unroll
     for (int k = 0; k < MG_VX; k++) {
       float pxk = px[k];
-      float gg = g.beta / (g.c2[0] * pxk * pxk + g.c2[1] * py * py + g.c2[2] * pz * pz);
+      // g = beta / (cell^2 . p^2): fast reciprocal (<= 2 ulp); the reference's @tturbo is not IEEE-exact either
+      float gg = __fdividef(g.beta, ax2[k] + byz);
       float gx = g.ic2[0] + gg * pxk * pxk, gy = g.ic2[1] + gg * py * py, gz = g.ic2[2] + gg * pz * pz;
       float vxp = b0[k + 2], vxm = b0[k], vyp = bp[k + 1], vym = bm[k + 1], vzp = c0[k + 1], vzm = a0[k + 1];
       float off = gx * (vxp + vxm) + gy * (vyp + vym) + gz * (vzp + vzm) +
@@ -190,10 +193,10 @@ mg_stencil_march(float* __restrict__ out, const float* __restrict__ v, const flo
                       (pxk * py * (bp[k + 2] + bm[k] - bp[k] - bm[k + 2]) +
                        pxk * pz * (c0[k + 2] + a0[k] - c0[k] - a0[k + 2]) +
                        py * pz * (cp[k] + am[k] - cm[k] - ap[k]));
-      if (g.radial) off += gg * (pxk * (vxp - vxm) + py * (vyp - vym) + pz * (vzp - vzm));
+      if (RADIAL) off += gg * (pxk * (vxp - vxm) + py * (vyp - vym) + pz * (vzp - vzm));
       float diag = 2 * (gx + gy + gz);
       float vc = b0[k + 1];
-      if (MODE == MG_JACOBI) res[k] = (1 - omega) * vc + omega * ((ff[k] + off) / diag);
+      if (MODE == MG_JACOBI) res[k] = (1 - omega) * vc + omega * __fdividef(ff[k] + off, diag);
       else res[k] = ff[k] - (diag * vc - off);
     }
     *reinterpret_cast<float4*>(out + o) = make_float4(res[0], res[1], res[2], res[3]);
@@ -206,12 +209,9 @@ mg_stencil_march(float* __restrict__ out, const float* __restrict__ v, const flo
 __global__ void __launch_bounds__(256)
 mg_restrict_kernel(float* __restrict__ c, const float* __restrict__ fine, int nx, int ny, int nz) {
   int cx = nx / 2, cy = ny / 2, cz = nz / 2;
-  size_t cells = (size_t)cx * cy * cz;
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= cells) return;
-  int ix = (int)(idx % cx);
-  size_t t = idx / cx;
-  int iy = (int)(t % cy), iz = (int)(t / cy);
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y * blockDim.y + threadIdx.y, iz = blockIdx.z;
+  if (ix >= cx || iy >= cy || iz >= cz) return;
+  const size_t idx = ((size_t)iz * cy + iy) * cx + ix;
   int X[3], Y[3], Z[3];
   int fx = 2 * ix + 1, fy = 2 * iy + 1, fz = 2 * iz + 1;
   X[0] = fx - 1; X[1] = fx; X[2] = fx + 1 == nx ? 0 : fx + 1;
@@ -242,22 +242,43 @@ mg_restrict_kernel(float* __restrict__ c, const float* __restrict__ fine, int nx
 template <bool ADD>
 __global__ void __launch_bounds__(256)
 mg_prolong_kernel(float* __restrict__ fine, const float* __restrict__ c, int nx, int ny, int nz) {
-  int cx = nx / 2, cy = ny / 2, cz = nz / 2;
-  size_t cells = (size_t)nx * ny * nz;
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= cells) return;
-  int ix = (int)(idx % nx);
-  size_t t = idx / nx;
-  int iy = (int)(t % ny), iz = (int)(t / ny);
-  int xa, xb, ya, yb, za, zb;
-  if (ix & 1) { xa = xb = (ix - 1) >> 1; } else { xb = ix >> 1; xa = xb == 0 ? cx - 1 : xb - 1; if (xb >= cx) xb = 0; }
-  if (iy & 1) { ya = yb = (iy - 1) >> 1; } else { yb = iy >> 1; ya = yb == 0 ? cy - 1 : yb - 1; if (yb >= cy) yb = 0; }
-  if (iz & 1) { za = zb = (iz - 1) >> 1; } else { zb = iz >> 1; za = zb == 0 ? cz - 1 : zb - 1; if (zb >= cz) zb = 0; }
-  auto C = [&](int x, int y, int z) { return __ldg(c + ((size_t)z * cy + y) * cx + x); };
-  float s = C(xa, ya, za) + C(xb, ya, za) + C(xa, yb, za) + C(xb, yb, za) + C(xa, ya, zb) + C(xb, ya, zb) +
-            C(xa, yb, zb) + C(xb, yb, zb);
-  float val = s * 0.125f;
-  fine[idx] = ADD ? fine[idx] + val : val;
+  // one thread per coarse cell (cx,cy,cz): writes the 2x2x2 fine cells (2c, 2c+1) per axis from the
+  // coarse cells {c-1, c} per axis (8 loads, 4 aligned float2 stores)
+  const int cx = nx / 2, cy = ny / 2, cz = nz / 2;
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y * blockDim.y + threadIdx.y, iz = blockIdx.z;
+  if (ix >= cx || iy >= cy) return;
+  const int xm = ix == 0 ? cx - 1 : ix - 1, ym = iy == 0 ? cy - 1 : iy - 1, zm = iz == 0 ? cz - 1 : iz - 1;
+  const int X[2] = {xm, ix}, Y[2] = {ym, iy}, Z[2] = {zm, iz};
+  float xe[2][2], xo[2][2];  // [dz][dy]: even / odd fine x
+#pragma unroll
+  for (int dz = 0; dz < 2; dz++)
+#pragma unroll
+    for (int dy = 0; dy < 2; dy++) {
+      const float* row = c + ((size_t)Z[dz] * cy + Y[dy]) * cx;
+      float a = __ldg(row + X[0]), b = __ldg(row + X[1]);
+      xe[dz][dy] = 0.5f * (a + b);
+      xo[dz][dy] = b;
+    }
+#pragma unroll
+  for (int pz = 0; pz < 2; pz++)
+#pragma unroll
+    for (int py = 0; py < 2; py++) {
+      float e[2], o[2];  // after the y reduction, per dz
+#pragma unroll
+      for (int dz = 0; dz < 2; dz++) {
+        e[dz] = py ? xe[dz][1] : 0.5f * (xe[dz][0] + xe[dz][1]);
+        o[dz] = py ? xo[dz][1] : 0.5f * (xo[dz][0] + xo[dz][1]);
+      }
+      float ve = pz ? e[1] : 0.5f * (e[0] + e[1]);
+      float vo = pz ? o[1] : 0.5f * (o[0] + o[1]);
+      float2* dst = reinterpret_cast<float2*>(fine + ((size_t)(2 * iz + pz) * ny + (2 * iy + py)) * nx + 2 * ix);
+      if (ADD) {
+        float2 cur = *dst;
+        ve += cur.x;
+        vo += cur.y;
+      }
+      *dst = make_float2(ve, vo);
+    }
 }
 
 // ---- launch helpers -------------------------------------------------------------------------------
@@ -279,10 +300,11 @@ static int launch_stencil(baorec_ctx* ctx, float* out, const float* v, const flo
     while (zchunk > 8 && blocks_xy * cdiv(g.nz, zchunk) < 148 * 8) zchunk /= 2;
     dim3 grid(cdiv(g.nx / MG_VX, tx), cdiv(g.ny, ty), cdiv(g.nz, zchunk));
     dim3 block(tx, ty);
-    BR_LAUNCH(ctx, mg_stencil_march<MODE>, grid, block, 0, st, out, v, f, g, omega, zchunk);
+    if (g.radial) BR_LAUNCH(ctx, (mg_stencil_march<MODE, true>), grid, block, 0, st, out, v, f, g, omega, zchunk);
+    else BR_LAUNCH(ctx, (mg_stencil_march<MODE, false>), grid, block, 0, st, out, v, f, g, omega, zchunk);
   } else {
-    size_t cells = (size_t)g.nx * g.ny * g.nz;
-    BR_LAUNCH(ctx, mg_stencil_generic<MODE>, cdiv(cells, 256), 256, 0, st, out, v, f, g, omega);
+    dim3 block(32, 8), grid(cdiv(g.nx, 32), cdiv(g.ny, 8), g.nz);
+    BR_LAUNCH(ctx, mg_stencil_generic<MODE>, grid, block, 0, st, out, v, f, g, omega);
   }
   return BAOREC_OK;
 }
@@ -303,16 +325,16 @@ static int jacobi_pp(baorec_ctx* ctx, float* a, float* b, const float* f, const 
 }
 
 static int restrict_to(baorec_ctx* ctx, float* coarse, const float* fine, int nx, int ny, int nz, cudaStream_t st) {
-  size_t cells = (size_t)(nx / 2) * (ny / 2) * (nz / 2);
-  BR_LAUNCH(ctx, mg_restrict_kernel, cdiv(cells, 256), 256, 0, st, coarse, fine, nx, ny, nz);
+  dim3 block(32, 8), grid(cdiv(nx / 2, 32), cdiv(ny / 2, 8), nz / 2);
+  BR_LAUNCH(ctx, mg_restrict_kernel, grid, block, 0, st, coarse, fine, nx, ny, nz);
   return BAOREC_OK;
 }
 
 static int prolong_to(baorec_ctx* ctx, float* fine, const float* coarse, int nx, int ny, int nz, bool add,
                       cudaStream_t st) {
-  size_t cells = (size_t)nx * ny * nz;
-  if (add) BR_LAUNCH(ctx, mg_prolong_kernel<true>, cdiv(cells, 256), 256, 0, st, fine, coarse, nx, ny, nz);
-  else BR_LAUNCH(ctx, mg_prolong_kernel<false>, cdiv(cells, 256), 256, 0, st, fine, coarse, nx, ny, nz);
+  dim3 block(32, 8), grid(cdiv(nx / 2, 32), cdiv(ny / 2, 8), nz / 2);
+  if (add) BR_LAUNCH(ctx, mg_prolong_kernel<true>, grid, block, 0, st, fine, coarse, nx, ny, nz);
+  else BR_LAUNCH(ctx, mg_prolong_kernel<false>, grid, block, 0, st, fine, coarse, nx, ny, nz);
   return BAOREC_OK;
 }
 
