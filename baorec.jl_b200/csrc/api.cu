@@ -145,6 +145,7 @@ int baorec_set_option(baorec_ctx* ctx, const char* name, int64_t value) {
   std::string s(name);
   if (s == "bin_min_particles") ctx->opt_bin_min_particles = value;
   else if (s == "fuse_kspace") ctx->opt_fuse_kspace = (int)value;
+  else if (s == "own_fft") ctx->opt_own_fft = (int)value;
   else if (s == "gather_tiles") ctx->opt_gather_tiles = (int)value;
   else if (s == "bin_zg_scatter") ctx->opt_zg_scatter = (int)value;
   else if (s == "bin_zg_gather") ctx->opt_zg_gather = (int)value;

@@ -87,6 +87,7 @@ int check_oob(baorec_ctx* ctx, cudaStream_t st, const char* what) {
 }
 
 int fft_r2c(baorec_ctx* ctx, const float* in, float2* out, cudaStream_t st) {
+  if (own_fft_available(ctx)) return own_r2c(ctx, in, out, st);
   BR_CUFFT(cufftSetStream(ctx->r2c, st));
   int pi = prof_begin(ctx, "cufft_r2c", st);
   BR_CUFFT(cufftExecR2C(ctx->r2c, (cufftReal*)in, (cufftComplex*)out));
@@ -96,6 +97,7 @@ int fft_r2c(baorec_ctx* ctx, const float* in, float2* out, cudaStream_t st) {
 }
 
 int fft_c2r(baorec_ctx* ctx, float2* in, float* out, cudaStream_t st) {
+  if (own_fft_available(ctx)) return own_c2r(ctx, in, out, st);
   BR_CUFFT(cufftSetStream(ctx->c2r, st));
   int pi = prof_begin(ctx, "cufft_c2r", st);
   BR_CUFFT(cufftExecC2R(ctx->c2r, (cufftComplex*)in, (cufftReal*)out));
@@ -145,6 +147,11 @@ static int upload_tables(baorec_ctx* ctx) {
 }
 
 static void destroy_plans(baorec_ctx* ctx) {
+  if (ctx->have_x_plans) {
+    cufftDestroy(ctx->px_r2c);
+    cufftDestroy(ctx->px_c2r);
+    ctx->have_x_plans = false;
+  }
   if (ctx->have_plans) {
     cufftDestroy(ctx->r2c);
     cufftDestroy(ctx->c2r);
@@ -237,6 +244,8 @@ int baorec_destroy(baorec_ctx* ctx) {
     if (ctx->d_k[a]) cudaFree(ctx->d_k[a]);
     if (ctx->d_xv[a]) cudaFree(ctx->d_xv[a]);
   }
+  for (int a = 0; a < 2; a++)
+    if (ctx->d_tw[a]) cudaFree(ctx->d_tw[a]);
   if (ctx->d_oob) cudaFree(ctx->d_oob);
   if (ctx->d_scal) cudaFree(ctx->d_scal);
   if (ctx->d_minmax) cudaFree(ctx->d_minmax);
@@ -266,10 +275,25 @@ int baorec_plan(baorec_ctx* ctx, int nx, int ny, int nz, const float box_size[3]
     BR_CUFFT(cufftMakePlan3d(ctx->r2c, nz, ny, nx, CUFFT_R2C, &w1));
     BR_CUFFT(cufftMakePlan3d(ctx->c2r, nz, ny, nx, CUFFT_C2R, &w2));
     ctx->work_bytes = w1 > w2 ? w1 : w2;
+    // batched contiguous 1-D transforms along x for the own-FFT path
+    size_t w3 = 0, w4 = 0;
+    int n1[1] = {nx};
+    BR_CUFFT(cufftCreate(&ctx->px_r2c));
+    BR_CUFFT(cufftCreate(&ctx->px_c2r));
+    ctx->have_x_plans = true;
+    BR_CUFFT(cufftSetAutoAllocation(ctx->px_r2c, 0));
+    BR_CUFFT(cufftSetAutoAllocation(ctx->px_c2r, 0));
+    BR_CUFFT(cufftMakePlanMany(ctx->px_r2c, 1, n1, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, ny * nz, &w3));
+    BR_CUFFT(cufftMakePlanMany(ctx->px_c2r, 1, n1, nullptr, 1, 0, nullptr, 1, 0, CUFFT_C2R, ny * nz, &w4));
+    if (w3 > ctx->work_bytes) ctx->work_bytes = w3;
+    if (w4 > ctx->work_bytes) ctx->work_bytes = w4;
     void* work = nullptr;
     BR_TRY(need(ctx, BUF_WORK, ctx->work_bytes > 0 ? ctx->work_bytes : 16, &work));
     BR_CUFFT(cufftSetWorkArea(ctx->r2c, work));
     BR_CUFFT(cufftSetWorkArea(ctx->c2r, work));
+    BR_CUFFT(cufftSetWorkArea(ctx->px_r2c, work));
+    BR_CUFFT(cufftSetWorkArea(ctx->px_c2r, work));
+    BR_TRY(own_fft_setup(ctx));
   }
   ctx->planned = true;
   return BAOREC_OK;

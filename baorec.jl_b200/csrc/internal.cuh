@@ -118,6 +118,11 @@ struct baorec_ctx {
   float cell[3] = {0, 0, 0};  // T(L/n), the gather's cell_size (src/mas.jl:221)
   cufftHandle r2c = 0, c2r = 0;
   bool have_plans = false;
+  // own FFT path: batched 1-D cuFFT along x + our column kernels along y and z (fft.cu)
+  cufftHandle px_r2c = 0, px_c2r = 0;
+  bool have_x_plans = false;
+  float2* d_tw[2] = {nullptr, nullptr};  // twiddle tables for the y and z axes
+  int opt_own_fft = 0;  // experimental: correct, but slower than cuFFT's strided passes today
   size_t work_bytes = 0;
   float* d_k[3] = {nullptr, nullptr, nullptr};  // k tables (xh, ny, nz)
   float* d_xv[3] = {nullptr, nullptr, nullptr}; // cell-centre tables (nx, ny, nz)
@@ -209,6 +214,16 @@ int stash_dc(baorec_ctx* ctx, const float2* ck, int slot, double mul, cudaStream
 int kpass_fused_T(baorec_ctx* ctx, const float2* in, float2* out_c2r, float2* keep, const baorec_params* p,
                   cudaStream_t st);
 int kpass_disp_T(baorec_ctx* ctx, const float2* in, float2* out, int comp, cudaStream_t st);
+
+// fft.cu
+bool own_fft_available(const baorec_ctx* ctx);
+int own_fft_setup(baorec_ctx* ctx);
+int own_r2c(baorec_ctx* ctx, const float* in, float2* out, cudaStream_t st);
+int own_c2r(baorec_ctx* ctx, float2* in, float* out, cudaStream_t st);
+int own_fused_los_solve(baorec_ctx* ctx, const baorec_params* p, float* mesh, float2* work, float2* keep,
+                        cudaStream_t st);
+int own_displacements(baorec_ctx* ctx, const float* mesh, const float2* from_k, int algorithm, float2* w0, float2* w1,
+                      float2* w2, float* px, float* py, float* pz, cudaStream_t st);
 
 // multigrid.cu
 int mg_setup_levels(baorec_ctx* ctx);

@@ -392,6 +392,11 @@ int displacement_meshes(baorec_ctx* ctx, const float* mesh, int algorithm, float
   BR_TRY(need_t(ctx, BUF_CK1, ctx->Mc, &ck1));
   BR_TRY(need_t(ctx, BUF_CK2, ctx->Mc, &ck2));
   const float invM = (float)(1.0 / (double)ctx->M);
+  if (own_fft_available(ctx)) {
+    const float2* from_k = (use_kcache && ctx->kcache_valid && algorithm == BAOREC_ITERATIVE)
+                               ? (const float2*)ctx->bufs[BUF_CKCACHE].p : nullptr;
+    return own_displacements(ctx, mesh, from_k, algorithm, ck0, ck1, ck2, px, py, pz, st);
+  }
   const float2* src = ck0;
   if (use_kcache && ctx->kcache_valid && algorithm == BAOREC_ITERATIVE) {
     src = (const float2*)ctx->bufs[BUF_CKCACHE].p;  // delta_k kept by the fused solve: no R2C needed
@@ -424,7 +429,13 @@ int reconstructed_overdensity(baorec_ctx* ctx, const baorec_params* p, float* me
     BR_TRY(need_t(ctx, BUF_CK0, ctx->Mc, &ck0));
     float2* keep = nullptr;
     if (ctx->want_kcache) BR_TRY(need_t(ctx, BUF_CKCACHE, ctx->Mc, &keep));
-    if (nr == 0) {
+    if (nr == 0 && own_fft_available(ctx)) {
+      // x: cuFFT 1-D; y: column kernel; z: forward + solve + inverse in one kernel; y; x
+      BR_TRY(reset_oob(ctx, st));
+      BR_TRY(scatter(ctx, mesh, x, y, z, w, n, 1, p->mas, st));
+      BR_TRY(own_fused_los_solve(ctx, p, mesh, ck0, keep, st));
+      BR_TRY(check_oob(ctx, st, "reconstructed_overdensity"));
+    } else if (nr == 0) {
       BR_TRY(reset_oob(ctx, st));
       BR_TRY(scatter(ctx, mesh, x, y, z, w, n, 1, p->mas, st));
       BR_TRY(fft_r2c(ctx, mesh, ck0, st));

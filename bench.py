@@ -76,7 +76,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -141,8 +141,16 @@ def algorithmic_bytes(name, M, Mc, N):
         return 16 * Mc
     if name.startswith("axpy") or name.startswith("radial_update") or name.startswith("randoms_combine"):
         return 12 * M
+    if name.startswith("cufft_1d_x"):
+        return 4 * M + 8 * Mc
     if name.startswith("cufft_1d"):
         return 16 * Mc
+    if name.startswith("fft_cols_kernel"):
+        return 16 * Mc
+    if name.startswith("fft_z_solve"):
+        return 16 * Mc                      # (+ 8 Mc when delta_k is kept for the read-back)
+    if name.startswith("fft_z_disp"):
+        return 8 * Mc + 24 * Mc
     if name.startswith("cufft"):
         return 4 * M + 8 * Mc              # single-pass lower bound (a 3-axis-pass FFT moves ~3x this)
     if name.startswith("rows_kernel") or name.startswith("transpose_kernel"):
