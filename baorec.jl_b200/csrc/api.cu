@@ -247,10 +247,24 @@ int baorec_read_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm,
   dp = dout + 3 * nn;
   BR_CUDA(cudaEventRecord(ctx->ev[4], st));
   const float* hsrc[3] = {h_x, h_y, h_z};
+  // the upload of the positions (copy stream) overlaps the displacement-mesh transforms (main stream)
   for (int c = 0; c < 3 && n > 0; c++)
-    BR_CUDA(cudaMemcpyAsync(dp + c * nn, hsrc[c], (size_t)n * sizeof(float), cudaMemcpyHostToDevice, st));
-  BR_TRY(read_common(ctx, p, algorithm, mesh, dp, dp + nn, dp + 2 * nn, n, field, shifts_only ? 0 : 1, dout, dout + nn,
-                     dout + 2 * nn, st, /*use_kcache=*/true));
+    BR_CUDA(cudaMemcpyAsync(dp + c * nn, hsrc[c], (size_t)n * sizeof(float), cudaMemcpyHostToDevice,
+                            ctx->copy_stream));
+  BR_CUDA(cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+  {
+    float *px, *py, *pz;
+    BR_TRY(need_t(ctx, BUF_RX, ctx->M, &px));
+    BR_TRY(need_t(ctx, BUF_RY, ctx->M, &py));
+    BR_TRY(need_t(ctx, BUF_RZ, ctx->M, &pz));
+    BR_TRY(displacement_meshes(ctx, mesh, algorithm, px, py, pz, st, /*use_kcache=*/true));
+    BR_CUDA(cudaEventRecord(ctx->ev[5], st));
+    BR_CUDA(cudaStreamWaitEvent(st, ctx->ev_copy, 0));
+    BR_TRY(reset_oob(ctx, st));
+    BR_TRY(gather3(ctx, px, py, pz, dp, dp + nn, dp + 2 * nn, n, dout, dout + nn, dout + 2 * nn, p->mas, field, p->f,
+                   p->has_los, p->los, shifts_only ? 0 : 1, st));
+    BR_TRY(check_oob(ctx, st, "read_shifts"));
+  }
   BR_CUDA(cudaEventRecord(ctx->ev[6], st));
   float* hdst[3] = {h_ox, h_oy, h_oz};
   for (int c = 0; c < 3 && n > 0; c++)

@@ -226,6 +226,8 @@ int baorec_create(int device, baorec_ctx** out) {
   BR_CUDA(cudaMalloc(&ctx->d_scal, 16 * sizeof(double)));
   BR_CUDA(cudaMalloc(&ctx->d_minmax, 8 * sizeof(float)));
   BR_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  BR_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  BR_CUDA(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
   for (int i = 0; i < 8; i++) BR_CUDA(cudaEventCreate(&ctx->ev[i]));
   *out = ctx;
   return BAOREC_OK;
@@ -257,6 +259,8 @@ int baorec_destroy(baorec_ctx* ctx) {
   }
   for (auto e : ctx->prof_pool) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
   delete ctx;
   return BAOREC_OK;
 }

@@ -131,6 +131,8 @@ struct baorec_ctx {
   double* d_scal = nullptr;             // small device scalars (DC modes, sums)
   float* d_minmax = nullptr;            // 6 floats for setup_box
   cudaStream_t own_stream = nullptr;    // used by host pipelines
+  cudaStream_t copy_stream = nullptr;   // H2D uploads that overlap compute
+  cudaEvent_t ev_copy = nullptr;
   cudaEvent_t ev[8] = {};
   float stage_ms[8] = {};
   int n_stage = 0;

@@ -485,27 +485,34 @@ bin_reorder_kernel(float* __restrict__ x, float* __restrict__ y, float* __restri
 
 template <int MAS>
 __global__ void __launch_bounds__(256)
-scatter_sorted_kernel(float* __restrict__ rho, const float4* __restrict__ rec, int64_t n_valid, BoxGeom g, int wrap) {
+scatter_sorted_kernel(float* __restrict__ rho, const float4* __restrict__ rec, const unsigned* __restrict__ n_valid,
+                      BoxGeom g, int wrap) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_valid) return;
+  if (i >= (int64_t)__ldg(n_valid)) return;  // records beyond this are the out-of-box trash bin
   float4 p = rec[i];
   deposit<MAS>(rho, p.x, p.y, p.z, p.w, g, wrap != 0);
 }
 
 template <int NF, int MAS>
 __global__ void __launch_bounds__(256)
-gather_sorted_kernel(GatherArgs a, const float4* __restrict__ rec, int64_t n_valid, BoxGeom g) {
+gather_sorted_kernel(GatherArgs a, const float4* __restrict__ rec, const unsigned* __restrict__ n_valid, int64_t n,
+                     BoxGeom g) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_valid) return;
+  if (i >= n) return;
   float4 p = rec[i];
-  gather_one<NF, MAS>(a, g, p.x, p.y, p.z, (int64_t)__float_as_uint(p.w));
+  const int64_t idx = (int64_t)__float_as_uint(p.w);
+  if (i >= (int64_t)__ldg(n_valid)) {  // out-of-box particle (trash bin): zero outputs
+    for (int c = 0; c < NF; c++) a.o[c][idx] = 0.f;
+    return;
+  }
+  gather_one<NF, MAS>(a, g, p.x, p.y, p.z, idx);
 }
 
 // zero-fill the outputs of out-of-box particles in the binned gather (they sit in the trash bin)
-__global__ void gather_trash_kernel(GatherArgs a, const float4* __restrict__ rec, int64_t first, int64_t n_total,
-                                    int nf) {
-  int64_t i = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_total) return;
+__global__ void gather_trash_kernel(GatherArgs a, const float4* __restrict__ rec, const unsigned* __restrict__ first,
+                                    int64_t n_total, int nf) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_total || i < (int64_t)__ldg(first)) return;
   int64_t idx = (int64_t)__float_as_uint(rec[i].w);
   for (int c = 0; c < nf; c++) a.o[c][idx] = 0.f;
 }
@@ -736,14 +743,18 @@ gather_tile_kernel(GatherArgs a, const float4* __restrict__ rec, const unsigned*
   }
 }
 
+__global__ void add_oob_kernel(const unsigned* __restrict__ count, unsigned long long* oob) {
+  if (*count) atomicAdd(oob, (unsigned long long)*count);
+}
+
 // out[c][i] = sorted_out[inv[i]].c : coalesced index read and output writes, one random 16 B read.
 __global__ void __launch_bounds__(256)
 unsort_kernel(GatherArgs a, const float4* __restrict__ sorted_out, const unsigned* __restrict__ inv, int64_t n,
-              int64_t n_valid) {
+              const unsigned* __restrict__ n_valid) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   unsigned j = inv[i];
-  float4 v = (int64_t)j < n_valid ? __ldg(sorted_out + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 v = j < __ldg(n_valid) ? __ldg(sorted_out + j) : make_float4(0.f, 0.f, 0.f, 0.f);
   a.o[0][i] = v.x;
   a.o[1][i] = v.y;
   a.o[2][i] = v.z;
@@ -751,13 +762,13 @@ unsort_kernel(GatherArgs a, const float4* __restrict__ sorted_out, const unsigne
 
 struct BinResult {
   float4* rec;
-  int64_t n_valid;
+  const unsigned* n_valid;  // device: number of in-box records (start of the trash bin)
   const unsigned* starts = nullptr;  // tile binning: first record of every tile (+ trash, + end)
   unsigned ntiles = 0;
   unsigned* inv = nullptr;           // tile binning: sorted position of every particle
 };
 
-// Builds the sorted records.  Synchronises the stream once (to learn n_valid).
+// Builds the sorted records (asynchronous: the number of in-box records stays on the device).
 template <int MODE>
 static int bin_particles(baorec_ctx* ctx, float* x, float* y, float* z, const float* w, int64_t n, int wrap, int mas,
                          cudaStream_t st, BinResult* out) {
@@ -797,15 +808,12 @@ static int bin_particles(baorec_ctx* ctx, float* x, float* y, float* z, const fl
     BR_LAUNCH(ctx, (bin_reorder_kernel<MODE, BAOREC_MAS_CIC>), grid_r, BIN_THREADS, 0, st, x, y, z, w, n, g, wrap, zg,
               nbins, cursor, rec, ctx->d_oob);
   }
-  unsigned h_valid = 0;
-  BR_CUDA(cudaMemcpyAsync(&h_valid, starts + nbins, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-  BR_CUDA(cudaStreamSynchronize(st));
   out->rec = rec;
-  out->n_valid = (int64_t)h_valid;
+  out->n_valid = starts + nbins;  // stays on the device: no host round trip
   return BAOREC_OK;
 }
 
-// Fine binning for the gather (see TILE_X / TILE_Y).  Synchronises the stream once.
+// Fine binning for the gather (see TILE_X / TILE_Y).  Asynchronous.
 static int bin_tiles(baorec_ctx* ctx, const float* x, const float* y, const float* z, int64_t n, int mas,
                      cudaStream_t st, BinResult* out) {
   BoxGeom g = geom_of(ctx);
@@ -833,22 +841,11 @@ static int bin_tiles(baorec_ctx* ctx, const float* x, const float* y, const floa
   BR_LAUNCH(ctx, scan_partial_kernel, nsb, 256, 0, st, cnt, sums, m);
   BR_LAUNCH(ctx, scan_sums_kernel, 1, 32, 0, st, sums, nsb, total);
   BR_LAUNCH(ctx, scan_final_kernel, nsb, 256, 0, st, cnt, sums, cursor, starts, m);
-  unsigned h[2] = {0, 0};  // start of the trash bin (= number of in-box particles), its size
-  BR_CUDA(cudaMemcpyAsync(&h[0], cursor + t.ntiles, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-  BR_CUDA(cudaMemcpyAsync(&h[1], cnt + t.ntiles, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  BR_LAUNCH(ctx, add_oob_kernel, 1, 1, 0, st, cnt + t.ntiles, ctx->d_oob);  // trash-bin size -> out-of-box counter
   if (tsc) BR_LAUNCH(ctx, tile_reorder_kernel<BAOREC_MAS_TSC>, grid, 256, 0, st, x, y, z, n, g, t, cursor, rec, inv);
   else BR_LAUNCH(ctx, tile_reorder_kernel<BAOREC_MAS_CIC>, grid, 256, 0, st, x, y, z, n, g, t, cursor, rec, inv);
-  BR_CUDA(cudaStreamSynchronize(st));
-  if (h[1]) {
-    unsigned long long add = h[1];
-    // account the out-of-box particles (the counter lives on the device)
-    unsigned long long cur = 0;
-    BR_CUDA(cudaMemcpy(&cur, ctx->d_oob, sizeof(cur), cudaMemcpyDeviceToHost));
-    cur += add;
-    BR_CUDA(cudaMemcpy(ctx->d_oob, &cur, sizeof(cur), cudaMemcpyHostToDevice));
-  }
   out->rec = rec;
-  out->n_valid = (int64_t)h[0];
+  out->n_valid = starts + t.ntiles;
   out->starts = starts;
   out->ntiles = t.ntiles;
   out->inv = inv;
@@ -867,8 +864,7 @@ int scatter(baorec_ctx* ctx, float* rho, float* x, float* y, float* z, const flo
   if (use_binning(ctx, n)) {
     BinResult b;
     BR_TRY(bin_particles<BIN_SCATTER>(ctx, x, y, z, w, n, wrap, mas, st, &b));
-    if (b.n_valid == 0) return BAOREC_OK;
-    unsigned grid = cdiv((size_t)b.n_valid, 256);
+    unsigned grid = cdiv((size_t)n, 256);
     if (tsc) BR_LAUNCH(ctx, scatter_sorted_kernel<BAOREC_MAS_TSC>, grid, 256, 0, st, rho, b.rec, b.n_valid, g, wrap);
     else BR_LAUNCH(ctx, scatter_sorted_kernel<BAOREC_MAS_CIC>, grid, 256, 0, st, rho, b.rec, b.n_valid, g, wrap);
     return BAOREC_OK;
@@ -909,7 +905,7 @@ int gather3(baorec_ctx* ctx, const float* fx, const float* fy, const float* fz, 
     BinResult b;
     if (ctx->opt_gather_tiles) BR_TRY(bin_tiles(ctx, x, y, z, n, mas, st, &b));
     else BR_TRY(bin_particles<BIN_GATHER>(ctx, (float*)x, (float*)y, (float*)z, nullptr, n, 0, mas, st, &b));
-    if (b.n_valid > 0 && b.starts && !tsc) {
+    if (b.starts && !tsc) {
       TileGeom t;
       t.nxc = (ctx->nx + TILE_X - 1) / TILE_X;
       t.nyc = (ctx->ny + TILE_Y - 1) / TILE_Y;
@@ -931,19 +927,18 @@ int gather3(baorec_ctx* ctx, const float* fx, const float* fy, const float* fz, 
         BR_LAUNCH(ctx, unsort_kernel, cdiv((size_t)n, 256), 256, 0, st, a, so, b.inv, n, b.n_valid);
         return BAOREC_OK;
       }
-    } else if (b.n_valid > 0) {
-      unsigned grid = cdiv((size_t)b.n_valid, 256);
+      // single-field tile gather wrote in place; out-of-box outputs are zeroed below
+      BR_LAUNCH(ctx, gather_trash_kernel, cdiv((size_t)n, 256), 256, 0, st, a, b.rec, b.n_valid, n, 1);
+    } else {
+      unsigned grid = cdiv((size_t)n, 256);
       if (tsc) {
-        if (one) BR_LAUNCH(ctx, (gather_sorted_kernel<1, BAOREC_MAS_TSC>), grid, 256, 0, st, a, b.rec, b.n_valid, g);
-        else BR_LAUNCH(ctx, (gather_sorted_kernel<3, BAOREC_MAS_TSC>), grid, 256, 0, st, a, b.rec, b.n_valid, g);
+        if (one) BR_LAUNCH(ctx, (gather_sorted_kernel<1, BAOREC_MAS_TSC>), grid, 256, 0, st, a, b.rec, b.n_valid, n, g);
+        else BR_LAUNCH(ctx, (gather_sorted_kernel<3, BAOREC_MAS_TSC>), grid, 256, 0, st, a, b.rec, b.n_valid, n, g);
       } else {
-        if (one) BR_LAUNCH(ctx, (gather_sorted_kernel<1, BAOREC_MAS_CIC>), grid, 256, 0, st, a, b.rec, b.n_valid, g);
-        else BR_LAUNCH(ctx, (gather_sorted_kernel<3, BAOREC_MAS_CIC>), grid, 256, 0, st, a, b.rec, b.n_valid, g);
+        if (one) BR_LAUNCH(ctx, (gather_sorted_kernel<1, BAOREC_MAS_CIC>), grid, 256, 0, st, a, b.rec, b.n_valid, n, g);
+        else BR_LAUNCH(ctx, (gather_sorted_kernel<3, BAOREC_MAS_CIC>), grid, 256, 0, st, a, b.rec, b.n_valid, n, g);
       }
     }
-    if (b.n_valid < n)
-      BR_LAUNCH(ctx, gather_trash_kernel, cdiv((size_t)(n - b.n_valid), 256), 256, 0, st, a, b.rec, b.n_valid, n,
-                one ? 1 : 3);
     return BAOREC_OK;
   }
   unsigned grid = cdiv((size_t)n, 256);
