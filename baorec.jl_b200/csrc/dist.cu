@@ -41,6 +41,21 @@ rows_kernel(float2* __restrict__ dst, const float2* __restrict__ src, int nzl, i
   for (int x = threadIdx.x; x < xh; x += blockDim.x) d[x] = s[x];
 }
 
+// Fused pack + exchange: the same row copy, but every per-peer block is stored straight into that
+// peer's receive buffer (mapped through CUDA IPC, NVLink stores), at the slot of the sending rank.
+struct PeerTab {
+  float2* p[16];
+};
+__global__ void __launch_bounds__(128)
+rows_p2p_kernel(PeerTab dst, const float2* __restrict__ src, int nzl, int ny, int nyl, int xh, int rank) {
+  const unsigned row = blockIdx.x;  // zl * ny + y
+  const int zl = row / ny, y = row - zl * ny;
+  const int peer = y / nyl, yl = y - peer * nyl;
+  const float2* s = src + (size_t)row * xh;
+  float2* d = dst.p[peer] + (((size_t)rank * nzl + zl) * nyl + yl) * xh;
+  for (int x = threadIdx.x; x < xh; x += blockDim.x) d[x] = s[x];
+}
+
 // Batched strided 2-D transpose through shared memory: dst[c][r] = src[r][c].
 struct TrGeom {
   int rows, cols;
@@ -49,11 +64,15 @@ struct TrGeom {
   size_t src_b0, src_b1, dst_b0, dst_b1;
 };
 
-__global__ void __launch_bounds__(256) transpose_kernel(float2* __restrict__ dst, const float2* __restrict__ src, TrGeom t) {
+// If `tab` is given, batch b0 (= destination peer) is written into tab.p[b0] + tab_off instead of
+// dst + b0 * dst_b0 (fused transpose + exchange over peer memory).
+__global__ void __launch_bounds__(256)
+transpose_kernel(float2* __restrict__ dst, const float2* __restrict__ src, TrGeom t, PeerTab tab, int use_tab,
+                 size_t tab_off) {
   __shared__ float2 tile[32][33];
   const int b = blockIdx.z, b0 = b / t.nb1, b1 = b - b0 * t.nb1;
   const float2* s = src + b0 * t.src_b0 + b1 * t.src_b1;
-  float2* d = dst + b0 * t.dst_b0 + b1 * t.dst_b1;
+  float2* d = (use_tab ? tab.p[b0] + tab_off : dst + b0 * t.dst_b0) + b1 * t.dst_b1;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
 #pragma unroll
@@ -123,6 +142,23 @@ static int ring_exchange(baorec_ctx* ctx, const float* send, int to, float* recv
   return BAOREC_OK;
 }
 
+__global__ void barrier_touch_kernel(int* p) { *p = 1; }
+
+// all ranks' preceding work on `st` is complete once this returns on every rank's stream
+static int stream_barrier(baorec_ctx* ctx, cudaStream_t st) {
+  if (ctx->nranks == 1) return BAOREC_OK;
+  int pi = prof_begin(ctx, "nccl_barrier", st);
+  BR_NCCL(ncclAllReduce(ctx->d_barrier, ctx->d_barrier, 1, ncclInt, ncclMax, comm_of(ctx), st));
+  prof_end(ctx, pi, st);
+  return BAOREC_OK;
+}
+
+static PeerTab peer_tab(const baorec_ctx* ctx, int parity) {
+  PeerTab t;
+  for (int i = 0; i < 16; i++) t.p[i] = ctx->peer_recv[parity][i];
+  return t;
+}
+
 struct DistBufs {
   float2 *A, *S, *R, *T;
 };
@@ -146,9 +182,20 @@ static int dist_r2c(baorec_ctx* ctx, const float* slab, float2* T, cudaStream_t 
   BR_CUFFT(cufftExecR2C(ctx->p2d_r2c, (cufftReal*)slab, (cufftComplex*)b.A));
   prof_end(ctx, pi, st);
   ctx->n_fft++;
-  BR_LAUNCH(ctx, rows_kernel<true>, (unsigned)(nzl * ny), 128, 0, st, b.S, b.A, nzl, ny, nyl, xh);
   const size_t blk = (size_t)nzl * nyl * xh;
-  BR_TRY(all_to_all(ctx, b.S, b.R, blk, st));
+  const float2* Rsrc = b.R;
+  if (ctx->p2p) {
+    // pack + exchange in one kernel: blocks go straight into the peers' receive buffers
+    const int par = ctx->a2a_parity;
+    ctx->a2a_parity ^= 1;
+    BR_LAUNCH(ctx, rows_p2p_kernel, (unsigned)(nzl * ny), 128, 0, st, peer_tab(ctx, par), b.A, nzl, ny, nyl, xh,
+              ctx->rank);
+    BR_TRY(stream_barrier(ctx, st));
+    Rsrc = ctx->own_recv[par];
+  } else {
+    BR_LAUNCH(ctx, rows_kernel<true>, (unsigned)(nzl * ny), 128, 0, st, b.S, b.A, nzl, ny, nyl, xh);
+    BR_TRY(all_to_all(ctx, b.S, b.R, blk, st));
+  }
   // T[yl][x][s*nzl + zl] = R[s][zl][yl][x]
   TrGeom t;
   t.rows = nzl;
@@ -161,7 +208,7 @@ static int dist_r2c(baorec_ctx* ctx, const float* slab, float2* T, cudaStream_t 
   t.dst_b0 = nzl;
   t.dst_b1 = (size_t)xh * nz;
   dim3 grid(cdiv(xh, 32), cdiv(nzl, 32), P * nyl);
-  BR_LAUNCH(ctx, transpose_kernel, grid, 256, 0, st, T, b.R, t);
+  BR_LAUNCH(ctx, transpose_kernel, grid, 256, 0, st, T, Rsrc, t, PeerTab{}, 0, (size_t)0);
   BR_CUFFT(cufftSetStream(ctx->p1d, st));
   pi = prof_begin(ctx, "cufft_1d_z", st);
   BR_CUFFT(cufftExecC2C(ctx->p1d, (cufftComplex*)T, (cufftComplex*)T, CUFFT_FORWARD));
@@ -193,9 +240,29 @@ static int dist_c2r(baorec_ctx* ctx, float2* T, float* slab, cudaStream_t st) {
   t.dst_b0 = blk;
   t.dst_b1 = xh;
   dim3 grid(cdiv(nzl, 32), cdiv(xh, 32), P * nyl);
-  BR_LAUNCH(ctx, transpose_kernel, grid, 256, 0, st, b.S, T, t);
-  BR_TRY(all_to_all(ctx, b.S, b.R, blk, st));
-  BR_LAUNCH(ctx, rows_kernel<false>, (unsigned)(nzl * ny), 128, 0, st, b.A, b.R, nzl, ny, nyl, xh);
+  const float2* Rsrc = b.R;
+  if (ctx->p2p) {
+    // transpose + exchange in one kernel: tile (d, yl) is written into peer d's receive buffer
+    const int par = ctx->a2a_parity;
+    ctx->a2a_parity ^= 1;
+    // tile transpose into per-peer blocks (local), then every block goes to its peer's receive
+    // buffer as ONE contiguous copy over NVLink (256-byte transposed segments stored remotely
+    // reach only ~350 GB/s; contiguous blocks run at link speed)
+    BR_LAUNCH(ctx, transpose_kernel, grid, 256, 0, st, b.S, T, t, PeerTab{}, 0, (size_t)0);
+    int pi = prof_begin(ctx, "p2p_block_copies", st);
+    for (int k = 0; k < P; k++) {
+      const int d = (ctx->rank + k) % P;  // stagger the targets
+      BR_CUDA(cudaMemcpyAsync(ctx->peer_recv[par][d] + (size_t)ctx->rank * blk, b.S + (size_t)d * blk,
+                              blk * sizeof(float2), cudaMemcpyDefault, st));
+    }
+    prof_end(ctx, pi, st);
+    BR_TRY(stream_barrier(ctx, st));
+    Rsrc = ctx->own_recv[par];
+  } else {
+    BR_LAUNCH(ctx, transpose_kernel, grid, 256, 0, st, b.S, T, t, PeerTab{}, 0, (size_t)0);
+    BR_TRY(all_to_all(ctx, b.S, b.R, blk, st));
+  }
+  BR_LAUNCH(ctx, rows_kernel<false>, (unsigned)(nzl * ny), 128, 0, st, b.A, Rsrc, nzl, ny, nyl, xh);
   BR_CUFFT(cufftSetStream(ctx->p2d_c2r, st));
   pi = prof_begin(ctx, "cufft_2d_c2r", st);
   BR_CUFFT(cufftExecC2R(ctx->p2d_c2r, (cufftComplex*)b.A, (cufftReal*)slab));
@@ -247,7 +314,22 @@ int baorec_comm_init(baorec_ctx* ctx, int rank, int nranks, const void* unique_i
   return BAOREC_OK;
 }
 
+static void close_ipc(baorec_ctx* ctx) {
+  for (int k = 0; k < 2; k++)
+    for (int r = 0; r < 16; r++) {
+      if (ctx->peer_recv[k][r] && ctx->peer_recv[k][r] != ctx->own_recv[k]) cudaIpcCloseMemHandle(ctx->peer_recv[k][r]);
+      ctx->peer_recv[k][r] = nullptr;
+    }
+  ctx->p2p = false;
+  cudaGetLastError();  // a peer that already exited makes the close fail; nothing to do about it
+}
+
 int baorec_comm_destroy_internal(baorec_ctx* ctx) {
+  if (ctx) {
+    close_ipc(ctx);
+    if (ctx->d_barrier) cudaFree(ctx->d_barrier);
+    ctx->d_barrier = nullptr;
+  }
   if (ctx && ctx->comm) {
     ncclCommDestroy((ncclComm_t)ctx->comm);
     ctx->comm = nullptr;
@@ -298,6 +380,19 @@ int baorec_plan_dist(baorec_ctx* ctx, int nx, int ny, int nz, const float box_si
       BR_CUFFT(cufftSetWorkArea(ctx->c2r, work));
     }
   }
+  {
+    // receive buffers are allocated here at their final size: their addresses are exported via IPC
+    const size_t slab_c = (size_t)nzl * ny * (nx / 2 + 1);
+    void* r0 = ctx->bufs[BUF_A2A_RECV].p;
+    void* r1 = ctx->bufs[BUF_A2A_RECV2].p;
+    BR_TRY(need_t(ctx, BUF_A2A_RECV, slab_c, &ctx->own_recv[0]));
+    BR_TRY(need_t(ctx, BUF_A2A_RECV2, slab_c, &ctx->own_recv[1]));
+    if (r0 != ctx->own_recv[0] || r1 != ctx->own_recv[1]) ctx->p2p = false;  // re-export needed
+    if (!ctx->d_barrier) {
+      BR_CUDA(cudaMalloc(&ctx->d_barrier, sizeof(int)));
+      BR_CUDA(cudaMemset(ctx->d_barrier, 0, sizeof(int)));
+    }
+  }
   ctx->nz_loc = nzl;
   ctx->z0 = ctx->rank * nzl;
   ctx->ny_loc = nyl;
@@ -305,6 +400,45 @@ int baorec_plan_dist(baorec_ctx* ctx, int nx, int ny, int nz, const float box_si
   ctx->dist = true;
   ctx->planned = true;
   ctx->kcache_valid = false;
+  return BAOREC_OK;
+}
+
+int baorec_dist_ipc_close(baorec_ctx* ctx) {
+  BR_REQUIRE(ctx != nullptr, "ctx is NULL");
+  BR_CUDA(cudaSetDevice(ctx->device));
+  BR_CUDA(cudaDeviceSynchronize());
+  close_ipc(ctx);
+  return BAOREC_OK;
+}
+
+int baorec_dist_ipc_export(baorec_ctx* ctx, void* out128) {
+  BR_NEED_DIST(ctx);
+  BR_REQUIRE(out128 != nullptr, "out128 is NULL");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+  cudaIpcMemHandle_t h[2];
+  BR_CUDA(cudaIpcGetMemHandle(&h[0], ctx->own_recv[0]));
+  BR_CUDA(cudaIpcGetMemHandle(&h[1], ctx->own_recv[1]));
+  memcpy(out128, h, sizeof(h));
+  return BAOREC_OK;
+}
+
+int baorec_dist_ipc_open(baorec_ctx* ctx, const void* all_handles, int nranks) {
+  BR_NEED_DIST(ctx);
+  BR_REQUIRE(all_handles != nullptr && nranks == ctx->nranks && nranks <= 16, "ipc_open arguments");
+  const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)all_handles;
+  close_ipc(ctx);
+  for (int r = 0; r < nranks; r++)
+    for (int k = 0; k < 2; k++) {
+      if (r == ctx->rank) {
+        ctx->peer_recv[k][r] = ctx->own_recv[k];
+        continue;
+      }
+      void* p = nullptr;
+      BR_CUDA(cudaIpcOpenMemHandle(&p, h[2 * r + k], cudaIpcMemLazyEnablePeerAccess));
+      ctx->peer_recv[k][r] = (float2*)p;
+    }
+  ctx->a2a_parity = 0;
+  ctx->p2p = true;
   return BAOREC_OK;
 }
 

@@ -81,6 +81,7 @@ enum BufId {
   BUF_MG,       // multigrid level hierarchy (one slab allocation)
   BUF_A2A_SEND, // distributed FFT staging
   BUF_A2A_RECV,
+  BUF_A2A_RECV2,
   BUF_HALO,
   BUF_COUNT
 };
@@ -157,6 +158,12 @@ struct baorec_ctx {
   int rank = 0, nranks = 1;
   bool dist = false;
   int nz_loc = 0, z0 = 0, ny_loc = 0, y0 = 0;
+  // peer-to-peer transposes: recv buffers of every rank mapped through CUDA IPC (double-buffered)
+  bool p2p = false;
+  float2* peer_recv[2][16] = {};
+  float2* own_recv[2] = {nullptr, nullptr};
+  int a2a_parity = 0;
+  int* d_barrier = nullptr;
   int slab_mode = 0;  // 0: whole mesh; 1: scatter into a slab (+1 ghost plane); 2: gather from a slab (+3 halo planes)
   cufftHandle p2d_r2c = 0, p2d_c2r = 0, p1d = 0;
   bool have_dist_plans = false;

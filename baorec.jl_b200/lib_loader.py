@@ -61,6 +61,9 @@ SIGNATURES = {
     "baorec_comm_unique_id": [_vp],
     "baorec_comm_init": [_vp, _i, _i, _vp],
     "baorec_plan_dist": [_vp, _i, _i, _i, _f3, _f3],
+    "baorec_dist_ipc_close": [_vp],
+    "baorec_dist_ipc_export": [_vp, _vp],
+    "baorec_dist_ipc_open": [_vp, _vp, _i],
     "baorec_slab_range": [_vp, C.POINTER(_i), C.POINTER(_i)],
     "baorec_slab_owner_f32": [_vp, _vp, _i64, _vp, _vp],
     "baorec_dist_r2c_f32": [_vp, _vp, _vp, _vp],

@@ -244,7 +244,7 @@ def main():
     N = int(args.particles)
     M = n ** 3
     Mc = (n // 2 + 1) * n * n
-    L = BOX_L * n / 1024.0 if n != 1024 else BOX_L
+    L = BOX_L * n / 1024.0   # same 2.44 Mpc/h cells at every mesh size
     grid = (n, n, n)
     kw = dict(box_size=np.full(3, L, np.float32), box_min=np.zeros(3, np.float32), **PARAMS)
 

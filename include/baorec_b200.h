@@ -125,6 +125,14 @@ int baorec_comm_init(baorec_ctx* ctx, int rank, int nranks, const void* unique_i
  * communicator is needed (baorec_comm_init(ctx, 0, 1, NULL)). */
 int baorec_plan_dist(baorec_ctx* ctx, int nx, int ny, int nz, const float box_size[3], const float box_min[3]);
 int baorec_slab_range(const baorec_ctx* ctx, int* z_lo, int* nz_loc);
+/* Peer-to-peer transposes (optional, after baorec_plan_dist): every rank exports the CUDA IPC
+ * handles of its two receive buffers (2 x 64 bytes), the host side all-gathers them, and each rank
+ * opens the others'.  From then on the pack / tile-transpose kernels store their per-peer blocks
+ * straight into the peers' receive buffers over NVLink (one fused kernel + a one-int NCCL barrier
+ * instead of pack + grouped ncclSend/ncclRecv). */
+int baorec_dist_ipc_close(baorec_ctx* ctx);  /* drop the mappings (before a re-plan frees the buffers) */
+int baorec_dist_ipc_export(baorec_ctx* ctx, void* out128);
+int baorec_dist_ipc_open(baorec_ctx* ctx, const void* all_handles /* nranks x 128 bytes */, int nranks);
 /* Owner rank of every particle = slab of its cic! base plane (src/mas.jl:15-30), -1 if out of box. */
 int baorec_slab_owner_f32(baorec_ctx* ctx, const float* d_z, int64_t n, int32_t* d_owner, baorec_stream stream);
 /* Slab-decomposed transforms (unnormalised): real slab [nz_loc][ny][nx] <-> transposed k slab
