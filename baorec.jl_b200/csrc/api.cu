@@ -129,6 +129,22 @@ int baorec_read_shifts_f32(baorec_ctx* ctx, const baorec_params* p, int algorith
   return read_common(ctx, p, algorithm, d_mesh, d_x, d_y, d_z, n, field, 0, d_sx, d_sy, d_sz, (cudaStream_t)stream);
 }
 
+// read_shifts / reconstructed_positions against recon.result_cache: the caller asserts that d_mesh
+// is the (unmodified) mesh returned by the last reconstructed_overdensity! on this context, so the
+// delta_k kept by that solve is used and the forward transform of the mesh is skipped.
+int baorec_read_result_cache_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, const float* d_mesh,
+                                 const float* d_x, const float* d_y, const float* d_z, int64_t n, int field,
+                                 int positions, float* d_ox, float* d_oy, float* d_oz, baorec_stream stream) {
+  BR_NEED_PLAN(ctx);
+  BR_TRY(check_params(p));
+  BR_REQUIRE(d_mesh != nullptr, "mesh is NULL");
+  BR_REQUIRE(field >= BAOREC_FIELD_DISP && field <= BAOREC_FIELD_SUM, "unknown field");
+  BR_REQUIRE(n >= 0 && (n == 0 || (d_x && d_y && d_z && d_ox && d_oy && d_oz)), "particle arrays");
+  const bool hit = ctx->kcache_valid && ctx->kcache_mesh == d_mesh && algorithm == BAOREC_ITERATIVE;
+  return read_common(ctx, p, algorithm, d_mesh, d_x, d_y, d_z, n, field, positions, d_ox, d_oy, d_oz,
+                     (cudaStream_t)stream, hit);
+}
+
 int baorec_reconstructed_positions_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, const float* d_mesh,
                                        const float* d_x, const float* d_y, const float* d_z, int64_t n, int field,
                                        float* d_ox, float* d_oy, float* d_oz, baorec_stream stream) {
@@ -145,6 +161,7 @@ int baorec_set_option(baorec_ctx* ctx, const char* name, int64_t value) {
   std::string s(name);
   if (s == "bin_min_particles") ctx->opt_bin_min_particles = value;
   else if (s == "fuse_kspace") ctx->opt_fuse_kspace = (int)value;
+  else if (s == "keep_delta_k") ctx->opt_keep_delta_k = (int)value;
   else if (s == "own_fft") ctx->opt_own_fft = (int)value;
   else if (s == "gather_tiles") ctx->opt_gather_tiles = (int)value;
   else if (s == "bin_zg_scatter") ctx->opt_zg_scatter = (int)value;

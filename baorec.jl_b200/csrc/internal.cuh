@@ -140,7 +140,9 @@ struct baorec_ctx {
   int64_t n_kernels = 0, n_fft = 0;
   bool cache_valid = false;
   bool kcache_valid = false;   // BUF_CKCACHE holds the unnormalised R2C of the cached result mesh
-  bool want_kcache = false;    // set by the host pipeline around the solve
+  bool want_kcache = false;
+  const float* kcache_mesh = nullptr;  // the result mesh delta_k belongs to
+  int opt_keep_delta_k = 1;    // device API: keep delta_k of the last reconstructed_overdensity! result    // set by the host pipeline around the solve
   int64_t opt_bin_min_particles = 1 << 18;  // catalogs at least this large are z-binned first
   int opt_fuse_kspace = 1;
   int opt_gather_tiles = 1;    // gather: fine (z, y/8, x/128) tile binning instead of z slabs

@@ -428,7 +428,7 @@ int reconstructed_overdensity(baorec_ctx* ctx, const baorec_params* p, float* me
     float2* ck0;
     BR_TRY(need_t(ctx, BUF_CK0, ctx->Mc, &ck0));
     float2* keep = nullptr;
-    if (ctx->want_kcache) BR_TRY(need_t(ctx, BUF_CKCACHE, ctx->Mc, &keep));
+    if (ctx->want_kcache || ctx->opt_keep_delta_k) BR_TRY(need_t(ctx, BUF_CKCACHE, ctx->Mc, &keep));
     if (nr == 0 && own_fft_available(ctx)) {
       // x: cuFFT 1-D; y: column kernel; z: forward + solve + inverse in one kernel; y; x
       BR_TRY(reset_oob(ctx, st));
@@ -455,6 +455,7 @@ int reconstructed_overdensity(baorec_ctx* ctx, const baorec_params* p, float* me
       BR_TRY(fft_c2r(ctx, ck0, mesh, st));
     }
     ctx->kcache_valid = keep != nullptr;
+    ctx->kcache_mesh = mesh;
     return BAOREC_OK;
   }
   float* ds;

@@ -433,7 +433,11 @@ def run(recon: AbstractRecon, grid_size, data_x, data_y, data_z, data_w, *rand, 
     nx, ny, nz = (int(v) for v in grid_size)
     has_rand = len(rand) >= 4
     if _is_dev(data_x):
-        mesh = torch.zeros((nz, ny, nx), dtype=torch.float32, device=data_x.device)
+        if mesh_out is not None:      # reuse a caller-provided device mesh (zero-filled here, like run!)
+            assert _chk_mesh(mesh_out) == (nx, ny, nz)
+            mesh = mesh_out.zero_()
+        else:
+            mesh = torch.zeros((nz, ny, nx), dtype=torch.float32, device=data_x.device)
         if has_rand:
             recon.box_size, recon.box_min = setup_box(rand[0], rand[1], rand[2], 500.0)
         setup_fft(recon, mesh)
@@ -442,6 +446,7 @@ def run(recon: AbstractRecon, grid_size, data_x, data_y, data_z, data_w, *rand, 
         else:
             reconstructed_overdensity(mesh, recon, data_x, data_y, data_z, data_w, *rand[:4])
         recon.result_cache = mesh
+        recon._cache_version = mesh._version
         return mesh
     # host arrays: whole pipeline inside the library
     n = _chk_np(data_x, data_y, data_z, data_w)
@@ -487,14 +492,25 @@ def displacement_meshes(mesh, recon: AbstractRecon):
     return out
 
 
-def _read(recon, data_x, data_y, data_z, mesh, field, positions):
+def _read(recon, data_x, data_y, data_z, mesh, field, positions, out=None):
     fld = L.FIELDS[field]
     if _is_dev(data_x):
         n = _chk_vec(data_x, data_y, data_z)
         _chk_mesh(mesh)
         ctx = recon._ctx(mesh)
         p = recon._params()
-        out = tuple(torch.empty_like(data_x) for _ in range(3))
+        if out is None:
+            out = tuple(torch.empty_like(data_x) for _ in range(3))
+        else:
+            assert _chk_vec(*out) == n
+        # recon.result_cache semantics (src/recon.jl:380-388): when the caller hands back the very mesh
+        # run!/reconstructed_overdensity! produced, untouched (torch's in-place version counter), the
+        # library reuses the delta_k it kept and skips the forward transform
+        if mesh is recon.result_cache and getattr(recon, "_cache_version", None) == mesh._version:
+            L.check(ctx.lib.baorec_read_result_cache_f32(
+                ctx.handle, C.byref(p), recon.algorithm, _ptr(mesh), _ptr(data_x), _ptr(data_y), _ptr(data_z), n,
+                fld, int(bool(positions)), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _stream()))
+            return out
         fn = ctx.lib.baorec_reconstructed_positions_f32 if positions else ctx.lib.baorec_read_shifts_f32
         L.check(fn(ctx.handle, C.byref(p), recon.algorithm, _ptr(mesh), _ptr(data_x), _ptr(data_y), _ptr(data_z), n,
                    fld, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _stream()))
@@ -510,16 +526,17 @@ def _read(recon, data_x, data_y, data_z, mesh, field, positions):
     return out
 
 
-def read_shifts(recon, data_x, data_y, data_z, mesh, field="disp"):
-    """read_shifts src/recon.jl:333-364; field in {"disp","rsd","sum"}."""
-    return _read(recon, data_x, data_y, data_z, mesh, field, False)
+def read_shifts(recon, data_x, data_y, data_z, mesh, field="disp", out=None):
+    """read_shifts src/recon.jl:333-364; field in {"disp","rsd","sum"}.  `out` (3 device vectors)
+    optionally receives the result instead of freshly allocated arrays."""
+    return _read(recon, data_x, data_y, data_z, mesh, field, False, out)
 
 
-def reconstructed_positions(recon, data_x, data_y, data_z, mesh=None, field="disp"):
+def reconstructed_positions(recon, data_x, data_y, data_z, mesh=None, field="disp", out=None):
     """reconstructed_positions src/recon.jl:366-388 (mesh defaults to recon.result_cache)."""
     if mesh is None:
         mesh = recon.result_cache
-    return _read(recon, data_x, data_y, data_z, mesh, field, True)
+    return _read(recon, data_x, data_y, data_z, mesh, field, True, out)
 
 
 # --------------------------------------------------------------------------------------------

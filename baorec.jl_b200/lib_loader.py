@@ -89,6 +89,7 @@ SIGNATURES = {
     "baorec_compute_displacements_f32": [_vp, _vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _vp],
     "baorec_read_shifts_f32": [_vp, _pp, _i, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp],
     "baorec_reconstructed_positions_f32": [_vp, _pp, _i, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp],
+    "baorec_read_result_cache_f32": [_vp, _pp, _i, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp],
     "baorec_displacement_meshes_f32": [_vp, _vp, _i, _vp, _vp, _vp, _vp],
     "baorec_run_host_f32": [_vp, _pp, _i, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _f3, _f3],
     "baorec_read_host_f32": [_vp, _pp, _i, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp],

@@ -238,6 +238,15 @@ int baorec_read_shifts_f32(baorec_ctx* ctx, const baorec_params* p, int algorith
 int baorec_reconstructed_positions_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, const float* d_mesh,
                                        const float* d_x, const float* d_y, const float* d_z, int64_t n, int field,
                                        float* d_ox, float* d_oy, float* d_oz, baorec_stream stream);
+/* read_shifts / reconstructed_positions (positions != 0) against recon.result_cache
+ * (src/recon.jl:380-388 passes recon.result_cache as the mesh): the caller asserts that d_mesh is
+ * the unmodified mesh produced by the last reconstructed_overdensity! on this context.  The library
+ * keeps delta_k of that result (option "keep_delta_k", default 1), so the forward transform the
+ * reference repeats on every call (src/iterative.jl:236) is skipped; if the pointer does not match
+ * or no delta_k is held the call behaves exactly like baorec_read_shifts_f32. */
+int baorec_read_result_cache_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, const float* d_mesh,
+                                 const float* d_x, const float* d_y, const float* d_z, int64_t n, int field,
+                                 int positions, float* d_ox, float* d_oy, float* d_oz, baorec_stream stream);
 /* The three real-space displacement meshes themselves (parity probe). */
 int baorec_displacement_meshes_f32(baorec_ctx* ctx, const float* d_mesh, int algorithm,
                                    float* d_psix, float* d_psiy, float* d_psiz, baorec_stream stream);

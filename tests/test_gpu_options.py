@@ -196,3 +196,34 @@ def test_own_fft_smooth_and_displacements_match_cufft_and_oracle(B, O, shape):
         # path drops the offending imaginary parts like FFTW/pocketfft (= the oracle); cuFFT's C2R
         # does not, so the library path is only compared on the smoothed field above
         assert rel_rms(out[1][1][a], opsi[a]) < 5e-6
+
+
+def test_result_cache_read_skips_forward_transform_and_matches(B, O):
+    """read_shifts(recon, x,y,z, recon.result_cache) reuses the delta_k kept by run!; a copy of the mesh
+    (or a mesh modified in place) goes through the forward transform like the reference."""
+    n, L, N = 64, 1000.0, 200_000
+    pos, w = clustered_box(N, L, seed=8)
+    kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=np.full(3, L, np.float32),
+              box_min=np.zeros(3, np.float32), los=(0.0, 0.0, 1.0), n_iter=3)
+    d = [dev(p) for p in pos]
+    rec = B.IterativeRecon(**kw)
+    mesh = B.run(rec, (n, n, n), *d, dev(w))
+    ctx = rec.fft_plan.ctx
+    _, f0 = ctx.launch_counts()
+    s_cached = B.read_shifts(rec, *d, mesh, field="sum")
+    _, f1 = ctx.launch_counts()
+    s_plain = B.read_shifts(rec, *d, mesh.clone(), field="sum")
+    _, f2 = ctx.launch_counts()
+    assert f1 - f0 == 3 and f2 - f1 == 4            # 3 C2R vs R2C + 3 C2R
+    for a in range(3):
+        assert maxabs(s_cached[a].cpu().numpy(), s_plain[a].cpu().numpy()) < 1e-4   # one C2R/R2C round trip of rounding
+    orec = O.IterativeRecon(**kw)
+    omesh = O.run(orec, (n, n, n), *[p.copy() for p in pos], w)
+    oshift = O.read_shifts(orec, *pos, omesh, "sum")
+    for a in range(3):
+        assert maxabs(s_cached[a].cpu().numpy(), oshift[a]) < 1e-3
+    mesh.mul_(2.0)                                     # in-place edit: the cache must not be used
+    s_mod = B.read_shifts(rec, *d, mesh, field="disp")
+    s_ref = B.read_shifts(rec, *d, mesh.clone(), field="disp")
+    for a in range(3):
+        assert maxabs(s_mod[a].cpu().numpy(), s_ref[a].cpu().numpy()) < 1e-6
