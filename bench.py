@@ -160,6 +160,26 @@ def algorithmic_bytes(name, M, Mc, N):
     return None
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of THIS workload
+# (1024^3, 1e8 particles, one GPU; profiles/r1_ncu_full_final_own_kernels.csv, r1_ncu_full_prof_r1_a.csv)
+NCU_TRAFFIC_BYTES_C4 = {
+    "gather_tile_kernel<3>": 14.502e9 + 1.598e9,
+    "scatter_sorted_kernel": 5.851e9 + 4.100e9,
+    "tile_reorder_kernel": 3.090e9 + 3.300e9,
+    "bin_reorder_kernel": 1.645e9 + 1.587e9,
+    "unsort_kernel": 7.531e9 + 1.195e9,
+}
+
+
+def ncu_traffic(name, n, N, world):
+    if n != 1024 or N != 100_000_000 or world != 1:
+        return None
+    for key, val in NCU_TRAFFIC_BYTES_C4.items():
+        if key in name:
+            return val
+    return None
+
+
 def cpu_reference(mesh_n, n_part, reps, warm):
     """BAOrec.jl's CPU path, restated (oracle/baorec_oracle.py; NOT the Julia binary): run! +
     read_shifts(:sum) on a bounded sample: a (mesh_n)^3 sub-volume with the same cell size and
@@ -195,7 +215,9 @@ def run_reference_arm(args, rank, world):
     value = ms_sample * scale
     cores = os.cpu_count() or 1
     sample = (f"{mesh_n}^3 mesh / {n_part} particles sub-volume (same cell size and density), "
-              f"{ms_sample:.0f} ms per sample reconstruction, scaled x{scale} (linear) to 1024^3 / 1e8")
+              f"{ms_sample:.0f} ms per sample reconstruction, scaled x{scale} (linear) to 1024^3 / 1e8; numpy port of "
+              "the reference's CPU methods: scipy.fft on all host threads, scatter serial like the reference "
+              "(src/mas.jl:5), gather/k-space loops single-threaded numpy")
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_sample, "higher_is_better": False,
@@ -386,7 +408,8 @@ def main():
     roofline = None
     if top and kernels[top]["alg_GBs"]:
         roofline = {"kernel": top, "bound": "hbm", "achieved": kernels[top]["alg_GBs"], "peak": peak,
-                    "unit": "GB/s", "frac": kernels[top]["frac_of_peak"], "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": kernels[top]["frac_of_peak"], "traffic": ncu_traffic(top, n, N, world),
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": algorithmic_bytes(top, M // world, Mc // world, N // world)}
     fft_ms = sum(v["ms_per_step"] for k, v in kernels.items() if k.startswith("cufft"))
     own_ms = sum(v["ms_per_step"] for k, v in own.items())
@@ -399,7 +422,9 @@ def main():
         ms_sample = 1e3 * float(np.mean(times))
         cpu_baseline = {"value": ms_sample * scale, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                         "sample": f"{mesh_n}^3 mesh / {N // scale} particles sub-volume (same cell size and density): "
-                                  f"{ms_sample:.0f} ms per sample reconstruction on the host cores, scaled x{scale}"}
+                                  f"{ms_sample:.0f} ms per sample reconstruction, scaled x{scale}; numpy port of the "
+                                  "reference's CPU methods: scipy.fft on all host threads, scatter serial like the "
+                                  "reference (src/mas.jl:5), gather/k-space loops single-threaded numpy"}
 
     out = {
         "metric": METRIC, "value": ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
