@@ -206,6 +206,16 @@ function _read(sym::Symbol, recon, x, y, z, mesh, field)
     ctx = plan!(mesh, recon.box_size, recon.box_min)
     out = Tuple(similar(x) for _ in 1:3)
     p = Ref(Params(recon))
+    if mesh === recon.result_cache
+        # the mesh run! produced: the library kept its delta_k, the forward transform is skipped
+        positions = sym === :baorec_reconstructed_positions_f32
+        check(ccall((:baorec_read_result_cache_f32, libbaorec), Cint,
+                    (Ptr{Cvoid}, Ptr{Params}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint, Cint,
+                     Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                    ctx, p, algorithm(recon), ptr(mesh), ptr(x), ptr(y), ptr(z), length(x), FIELD[field],
+                    positions, ptr(out[1]), ptr(out[2]), ptr(out[3]), stream()))
+        return out
+    end
     check(ccall((sym, libbaorec), Cint,
                 (Ptr{Cvoid}, Ptr{Params}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint,
                  Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
