@@ -163,9 +163,14 @@ int baorec_set_option(baorec_ctx* ctx, const char* name, int64_t value) {
   else if (s == "fuse_kspace") ctx->opt_fuse_kspace = (int)value;
   else if (s == "keep_delta_k") ctx->opt_keep_delta_k = (int)value;
   else if (s == "own_fft") ctx->opt_own_fft = (int)value;
+  else if (s == "fft_split_planes") ctx->opt_fft_split = (int)value;
   else if (s == "gather_tiles") ctx->opt_gather_tiles = (int)value;
   else if (s == "bin_zg_scatter") ctx->opt_zg_scatter = (int)value;
   else if (s == "bin_zg_gather") ctx->opt_zg_gather = (int)value;
+  else if (s == "mg_slab_min_cells") {
+    ctx->opt_mg_slab_min_cells = value;
+    ctx->dlevels.clear();
+  }
   else {
     set_error("baorec_set_option: unknown option '%s'", name);
     return BAOREC_ERR_INVALID;

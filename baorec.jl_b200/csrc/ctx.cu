@@ -86,8 +86,101 @@ int check_oob(baorec_ctx* ctx, cudaStream_t st, const char* what) {
   return BAOREC_OK;
 }
 
+static void destroy_split_plans(baorec_ctx* ctx) {
+  if (ctx->split_planes_planned) {
+    cufftDestroy(ctx->ps_r2c);
+    cufftDestroy(ctx->ps_c2r);
+    cufftDestroy(ctx->ps_z);
+    ctx->split_planes_planned = 0;
+  }
+}
+
+// Plans of the split path: 2-D R2C/C2R over C planes, strided 1-D C2C along z (in place).
+static int split_setup(baorec_ctx* ctx) {
+  int C = ctx->opt_fft_split;
+  if (C > ctx->nz) C = ctx->nz;
+  while (ctx->nz % C) C--;
+  if (ctx->split_planes_planned == C) return BAOREC_OK;
+  destroy_split_plans(ctx);
+  size_t w[3] = {0, 0, 0};
+  int n2[2] = {ctx->ny, ctx->nx};
+  int n1[1] = {ctx->nz};
+  const int stride = ctx->ny * ctx->xh;
+  BR_CUFFT(cufftCreate(&ctx->ps_r2c));
+  BR_CUFFT(cufftCreate(&ctx->ps_c2r));
+  BR_CUFFT(cufftCreate(&ctx->ps_z));
+  ctx->split_planes_planned = C;
+  BR_CUFFT(cufftSetAutoAllocation(ctx->ps_r2c, 0));
+  BR_CUFFT(cufftSetAutoAllocation(ctx->ps_c2r, 0));
+  BR_CUFFT(cufftSetAutoAllocation(ctx->ps_z, 0));
+  BR_CUFFT(cufftMakePlanMany(ctx->ps_r2c, 2, n2, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, C, &w[0]));
+  BR_CUFFT(cufftMakePlanMany(ctx->ps_c2r, 2, n2, nullptr, 1, 0, nullptr, 1, 0, CUFFT_C2R, C, &w[1]));
+  BR_CUFFT(cufftMakePlanMany(ctx->ps_z, 1, n1, n1, stride, 1, n1, stride, 1, CUFFT_C2C, stride, &w[2]));
+  size_t wmax = w[0] > w[1] ? w[0] : w[1];
+  if (w[2] > wmax) wmax = w[2];
+  if (wmax > ctx->bufs[BUF_WORK].bytes) {
+    // the shared work area is about to move: rebind every plan that uses it
+    BR_CUDA(cudaDeviceSynchronize());
+    void* work = nullptr;
+    BR_TRY(need(ctx, BUF_WORK, wmax, &work));
+    if (ctx->have_plans) {
+      BR_CUFFT(cufftSetWorkArea(ctx->r2c, work));
+      BR_CUFFT(cufftSetWorkArea(ctx->c2r, work));
+    }
+    if (ctx->have_x_plans) {
+      BR_CUFFT(cufftSetWorkArea(ctx->px_r2c, work));
+      BR_CUFFT(cufftSetWorkArea(ctx->px_c2r, work));
+    }
+    if (ctx->have_dist_plans) {
+      BR_CUFFT(cufftSetWorkArea(ctx->p2d_r2c, work));
+      BR_CUFFT(cufftSetWorkArea(ctx->p2d_c2r, work));
+      BR_CUFFT(cufftSetWorkArea(ctx->p1d, work));
+    }
+  }
+  void* work = ctx->bufs[BUF_WORK].p;
+  BR_CUFFT(cufftSetWorkArea(ctx->ps_r2c, work));
+  BR_CUFFT(cufftSetWorkArea(ctx->ps_c2r, work));
+  BR_CUFFT(cufftSetWorkArea(ctx->ps_z, work));
+  return BAOREC_OK;
+}
+
+static int split_r2c(baorec_ctx* ctx, const float* in, float2* out, cudaStream_t st) {
+  BR_TRY(split_setup(ctx));
+  const int C = ctx->split_planes_planned;
+  const size_t rplane = (size_t)ctx->nx * ctx->ny, cplane = (size_t)ctx->xh * ctx->ny;
+  BR_CUFFT(cufftSetStream(ctx->ps_r2c, st));
+  BR_CUFFT(cufftSetStream(ctx->ps_z, st));
+  int pi = prof_begin(ctx, "cufft_split_2d_r2c", st);
+  for (int z = 0; z < ctx->nz; z += C)
+    BR_CUFFT(cufftExecR2C(ctx->ps_r2c, (cufftReal*)(in + (size_t)z * rplane), (cufftComplex*)(out + (size_t)z * cplane)));
+  prof_end(ctx, pi, st);
+  pi = prof_begin(ctx, "cufft_split_z", st);
+  BR_CUFFT(cufftExecC2C(ctx->ps_z, (cufftComplex*)out, (cufftComplex*)out, CUFFT_FORWARD));
+  prof_end(ctx, pi, st);
+  ctx->n_fft++;
+  return BAOREC_OK;
+}
+
+static int split_c2r(baorec_ctx* ctx, float2* in, float* out, cudaStream_t st) {
+  BR_TRY(split_setup(ctx));
+  const int C = ctx->split_planes_planned;
+  const size_t rplane = (size_t)ctx->nx * ctx->ny, cplane = (size_t)ctx->xh * ctx->ny;
+  BR_CUFFT(cufftSetStream(ctx->ps_c2r, st));
+  BR_CUFFT(cufftSetStream(ctx->ps_z, st));
+  int pi = prof_begin(ctx, "cufft_split_z", st);
+  BR_CUFFT(cufftExecC2C(ctx->ps_z, (cufftComplex*)in, (cufftComplex*)in, CUFFT_INVERSE));
+  prof_end(ctx, pi, st);
+  pi = prof_begin(ctx, "cufft_split_2d_c2r", st);
+  for (int z = 0; z < ctx->nz; z += C)
+    BR_CUFFT(cufftExecC2R(ctx->ps_c2r, (cufftComplex*)(in + (size_t)z * cplane), (cufftReal*)(out + (size_t)z * rplane)));
+  prof_end(ctx, pi, st);
+  ctx->n_fft++;
+  return BAOREC_OK;
+}
+
 int fft_r2c(baorec_ctx* ctx, const float* in, float2* out, cudaStream_t st) {
   if (own_fft_available(ctx)) return own_r2c(ctx, in, out, st);
+  if (ctx->opt_fft_split > 0) return split_r2c(ctx, in, out, st);
   BR_CUFFT(cufftSetStream(ctx->r2c, st));
   int pi = prof_begin(ctx, "cufft_r2c", st);
   BR_CUFFT(cufftExecR2C(ctx->r2c, (cufftReal*)in, (cufftComplex*)out));
@@ -98,6 +191,7 @@ int fft_r2c(baorec_ctx* ctx, const float* in, float2* out, cudaStream_t st) {
 
 int fft_c2r(baorec_ctx* ctx, float2* in, float* out, cudaStream_t st) {
   if (own_fft_available(ctx)) return own_c2r(ctx, in, out, st);
+  if (ctx->opt_fft_split > 0) return split_c2r(ctx, in, out, st);
   BR_CUFFT(cufftSetStream(ctx->c2r, st));
   int pi = prof_begin(ctx, "cufft_c2r", st);
   BR_CUFFT(cufftExecC2R(ctx->c2r, (cufftComplex*)in, (cufftReal*)out));
@@ -147,6 +241,7 @@ static int upload_tables(baorec_ctx* ctx) {
 }
 
 static void destroy_plans(baorec_ctx* ctx) {
+  destroy_split_plans(ctx);
   if (ctx->have_x_plans) {
     cufftDestroy(ctx->px_r2c);
     cufftDestroy(ctx->px_c2r);
@@ -182,6 +277,7 @@ int plan_common(baorec_ctx* ctx, int nx, int ny, int nz, const float L[3], const
       ctx->d_k[a] = ctx->d_xv[a] = nullptr;
     }
     ctx->levels.clear();
+    ctx->dlevels.clear();
     ctx->nx = nx;
     ctx->ny = ny;
     ctx->nz = nz;

@@ -142,6 +142,47 @@ static int ring_exchange(baorec_ctx* ctx, const float* send, int to, float* recv
   return BAOREC_OK;
 }
 
+// Both halo planes of a slab-layout buffer ((nzl+2) planes, real planes at 1..nzl): plane 0 <- last
+// real plane of the previous rank, plane nzl+1 <- first real plane of the next rank (periodic ring).
+// One NCCL group of two sends and two receives; with two ranks both neighbours are the same peer
+// and the in-order matching of NCCL pairs (last plane -> plane 0) and (first plane -> plane nzl+1).
+int mg_halo_exchange(baorec_ctx* ctx, float* buf, size_t plane, int nzl, cudaStream_t st) {
+  float* lo = buf;
+  float* first = buf + plane;
+  float* last = buf + (size_t)nzl * plane;
+  float* hi = buf + (size_t)(nzl + 1) * plane;
+  const int P = ctx->nranks;
+  if (P == 1) {
+    BR_CUDA(cudaMemcpyAsync(lo, last, plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    BR_CUDA(cudaMemcpyAsync(hi, first, plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return BAOREC_OK;
+  }
+  const int next = (ctx->rank + 1) % P, prev = (ctx->rank + P - 1) % P;
+  int pi = prof_begin(ctx, "nccl_mg_halo", st);
+  BR_NCCL(ncclGroupStart());
+  BR_NCCL(ncclSend(last, plane, ncclFloat, next, comm_of(ctx), st));
+  BR_NCCL(ncclSend(first, plane, ncclFloat, prev, comm_of(ctx), st));
+  BR_NCCL(ncclRecv(lo, plane, ncclFloat, prev, comm_of(ctx), st));
+  BR_NCCL(ncclRecv(hi, plane, ncclFloat, next, comm_of(ctx), st));
+  BR_NCCL(ncclGroupEnd());
+  prof_end(ctx, pi, st);
+  return BAOREC_OK;
+}
+
+// recv[r * count ...] = rank r's send[0 .. count)
+int mg_allgather(baorec_ctx* ctx, const float* send, float* recv, size_t count, cudaStream_t st) {
+  if (ctx->nranks == 1) {
+    BR_CUDA(cudaMemcpyAsync(recv, send, count * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return BAOREC_OK;
+  }
+  int pi = prof_begin(ctx, "nccl_mg_allgather", st);
+  BR_NCCL(ncclAllGather(send, recv, count, ncclFloat, comm_of(ctx), st));
+  prof_end(ctx, pi, st);
+  return BAOREC_OK;
+}
+
+__global__ void set_scalar_kernel(double* p, double v) { *p = v; }
+
 __global__ void barrier_touch_kernel(int* p) { *p = 1; }
 
 // all ranks' preceding work on `st` is complete once this returns on every rank's stream
@@ -347,6 +388,7 @@ int baorec_plan_dist(baorec_ctx* ctx, int nx, int ny, int nz, const float box_si
   if (s < 0) return s;
   const int nzl = nz / P, nyl = ny / P;
   if (!ctx->have_dist_plans || s == 0 || ctx->nz_loc != nzl) {
+    ctx->dlevels.clear();
     if (ctx->have_dist_plans) {
       cufftDestroy(ctx->p2d_r2c);
       cufftDestroy(ctx->p2d_c2r);
@@ -471,42 +513,175 @@ int baorec_dist_c2r_f32(baorec_ctx* ctx, float* d_kslab_t, float* d_slab, baorec
   return dist_c2r(ctx, (float2*)d_kslab_t, d_slab, (cudaStream_t)stream);
 }
 
+// Scatter this rank's particles into `loc` ((nz_loc+1) planes, zero-filled here); the ghost plane
+// (global plane z_lo + nz_loc) belongs to the next rank: send it, add what arrives from below.
+static int dist_scatter(baorec_ctx* ctx, float* loc, float* x, float* y, float* z, const float* w, int64_t n,
+                        int wrap, int mas, cudaStream_t st) {
+  const int P = ctx->nranks, nzl = ctx->nz_loc;
+  const size_t plane = (size_t)ctx->ny * ctx->nx;
+  float* halo;
+  BR_TRY(need_t(ctx, BUF_HALO, plane, &halo));
+  BR_CUDA(cudaMemsetAsync(loc, 0, (size_t)(nzl + 1) * plane * sizeof(float), st));
+  ctx->slab_mode = 1;
+  int s = scatter(ctx, loc, x, y, z, w, n, wrap, mas, st);
+  ctx->slab_mode = 0;
+  if (s != BAOREC_OK) return s;
+  BR_TRY(ring_exchange(ctx, loc + (size_t)nzl * plane, (ctx->rank + 1) % P, halo, (ctx->rank + P - 1) % P, plane, st));
+  BR_LAUNCH(ctx, add_plane_kernel, cdiv(plane, 256), 256, 0, st, loc, halo, plane);
+  return BAOREC_OK;
+}
+
+// rank 0 holds the DC mode of a transposed k slab: scal[slot] = sum(mesh), scal[slot+8] = mul / sum
+static int dist_stash_dc(baorec_ctx* ctx, const float2* T, int slot, double mul, cudaStream_t st) {
+  if (ctx->rank == 0) BR_TRY(stash_dc(ctx, T, slot, mul, st));
+  return BAOREC_OK;
+}
+
+static int dist_bcast_scal(baorec_ctx* ctx, cudaStream_t st) {
+  if (ctx->nranks > 1) BR_NCCL(ncclBroadcast(ctx->d_scal, ctx->d_scal, 16, ncclDouble, 0, comm_of(ctx), st));
+  return BAOREC_OK;
+}
+
+// setup_overdensity! (src/recon.jl:42-57 box, :60-91 randoms) on slabs: delta lands in `delta_out`
+// (nz_loc planes; must not alias BUF_RS plane 0.. when randoms are used -> see callers).
+static int dist_setup_overdensity(baorec_ctx* ctx, const baorec_params* p, float* delta_out, float* x, float* y,
+                                  float* z, const float* w, int64_t n, float* rx, float* ry, float* rz,
+                                  const float* rw, int64_t nr, bool has_randoms, cudaStream_t st) {
+  const int nzl = ctx->nz_loc;
+  const size_t plane = (size_t)ctx->ny * ctx->nx;
+  DistBufs b;
+  BR_TRY(dist_bufs(ctx, &b));
+  float* loc;
+  BR_TRY(need_t(ctx, BUF_RS, (size_t)(nzl + 2) * plane, &loc));
+  if (!has_randoms) {
+    BR_TRY(dist_scatter(ctx, loc, x, y, z, w, n, 1, p->mas, st));
+    BR_TRY(dist_r2c(ctx, loc, b.T, st));
+    BR_TRY(dist_stash_dc(ctx, b.T, 0, 1.0 / (double)p->bias, st));
+    BR_TRY(dist_bcast_scal(ctx, st));
+    BR_TRY(kpass_setup_box_T(ctx, b.T, b.T, p, st));
+    BR_TRY(dist_c2r(ctx, b.T, delta_out, st));
+    return BAOREC_OK;
+  }
+  float *ran, *dat;
+  BR_TRY(need_t(ctx, BUF_RAN, (size_t)(nzl + 1) * plane, &ran));
+  BR_TRY(need_t(ctx, BUF_RX, (size_t)(nzl + 3) * plane, &dat));
+  BR_TRY(dist_scatter(ctx, loc, x, y, z, w, n, 0, p->mas, st));
+  BR_TRY(dist_scatter(ctx, ran, rx, ry, rz, rw, nr, 0, p->mas, st));
+  BR_TRY(dist_r2c(ctx, loc, b.T, st));
+  BR_TRY(dist_stash_dc(ctx, b.T, 0, 1.0, st));
+  BR_TRY(kpass_gauss_T(ctx, b.T, b.T, p->smoothing_radius, st));
+  BR_TRY(dist_c2r(ctx, b.T, dat, st));
+  BR_TRY(dist_r2c(ctx, ran, b.T, st));
+  BR_TRY(dist_stash_dc(ctx, b.T, 1, 1.0, st));
+  BR_TRY(kpass_gauss_T(ctx, b.T, b.T, p->smoothing_radius, st));
+  BR_TRY(dist_c2r(ctx, b.T, ran, st));
+  BR_TRY(dist_bcast_scal(ctx, st));
+  // global randoms count for the threshold (src/recon.jl:81)
+  BR_LAUNCH(ctx, set_scalar_kernel, 1, 1, 0, st, ctx->d_scal + 2, (double)nr);
+  if (ctx->nranks > 1)
+    BR_NCCL(ncclAllReduce(ctx->d_scal + 2, ctx->d_scal + 2, 1, ncclDouble, ncclSum, comm_of(ctx), st));
+  BR_TRY(randoms_combine(ctx, delta_out, dat, ran, p->bias, p->ran_min, -1.0, (size_t)nzl * plane, st));
+  return BAOREC_OK;
+}
+
 int baorec_run_dist_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, float* d_x, float* d_y, float* d_z,
-                        const float* d_w, int64_t n_local, float* d_mesh_slab, baorec_stream stream) {
+                        const float* d_w, int64_t n_local, float* d_rx, float* d_ry, float* d_rz, const float* d_rw,
+                        int64_t n_ran_local, int has_randoms, float* d_mesh_slab, baorec_stream stream) {
   BR_NEED_DIST(ctx);
   BR_REQUIRE(p != nullptr && d_mesh_slab != nullptr, "NULL argument");
+  BR_REQUIRE(algorithm == BAOREC_ITERATIVE || algorithm == BAOREC_MULTIGRID, "unknown algorithm");
   BR_REQUIRE(n_local >= 0 && (n_local == 0 || (d_x && d_y && d_z && d_w)), "particle arrays");
-  if (algorithm != BAOREC_ITERATIVE || !p->has_los || p->mas != BAOREC_MAS_CIC) {
-    set_error("baorec_run_dist_f32: this build distributes IterativeRecon with a fixed line of sight and CIC "
-              "(periodic box); radial/randoms and MultigridRecon run on one GPU");
+  BR_REQUIRE(n_ran_local >= 0 && (n_ran_local == 0 || (d_rx && d_ry && d_rz && d_rw)), "randoms arrays");
+  BR_REQUIRE(has_randoms || n_ran_local == 0, "randoms passed with has_randoms == 0");
+  if (p->mas != BAOREC_MAS_CIC) {
+    set_error("baorec_run_dist_f32: the slab-decomposed path supports CIC only (TSC needs two ghost planes)");
     return BAOREC_ERR_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const int P = ctx->nranks, nzl = ctx->nz_loc;
+  const int nzl = ctx->nz_loc;
   const size_t plane = (size_t)ctx->ny * ctx->nx;
+  const size_t slab_r = (size_t)nzl * plane;
+  const size_t slab_c = (size_t)ctx->ny_loc * ctx->xh * ctx->nz;
+  const float* los = p->has_los ? p->los : nullptr;
   ctx->kcache_valid = false;
-  float *loc, *halo;
-  BR_TRY(need_t(ctx, BUF_RS, (size_t)(nzl + 1) * plane, &loc));
-  BR_TRY(need_t(ctx, BUF_HALO, plane, &halo));
-  BR_CUDA(cudaMemsetAsync(loc, 0, (size_t)(nzl + 1) * plane * sizeof(float), st));
+  ctx->kcache_potential = false;
   BR_TRY(reset_oob(ctx, st));
-  ctx->slab_mode = 1;
-  int s = scatter(ctx, loc, d_x, d_y, d_z, d_w, n_local, 1, p->mas, st);
-  ctx->slab_mode = 0;
-  if (s != BAOREC_OK) return s;
-  // ghost plane (global plane z_lo + nzl) belongs to the next rank: send it, add what arrives
-  BR_TRY(ring_exchange(ctx, loc + (size_t)nzl * plane, (ctx->rank + 1) % P, halo, (ctx->rank + P - 1) % P, plane, st));
-  BR_LAUNCH(ctx, add_plane_kernel, cdiv(plane, 256), 256, 0, st, loc, halo, plane);
   DistBufs b;
   BR_TRY(dist_bufs(ctx, &b));
-  BR_TRY(dist_r2c(ctx, loc, b.T, st));
-  // sum(rho) = DC mode, held by rank 0: broadcast it with the derived scale
-  if (ctx->rank == 0) BR_TRY(stash_dc(ctx, b.T, 0, (double)ctx->M / (double)p->bias, st));
-  if (P > 1) BR_NCCL(ncclBroadcast(ctx->d_scal, ctx->d_scal, 16, ncclDouble, 0, comm_of(ctx), st));
   float2* keep;
-  BR_TRY(need_t(ctx, BUF_CKCACHE, (size_t)ctx->ny_loc * ctx->xh * ctx->nz, &keep));
-  BR_TRY(kpass_fused_T(ctx, b.T, b.T, keep, p, st));
-  BR_TRY(dist_c2r(ctx, b.T, d_mesh_slab, st));
+  BR_TRY(need_t(ctx, BUF_CKCACHE, slab_c, &keep));
+  float* rs;
+  BR_TRY(need_t(ctx, BUF_RS, (size_t)(nzl + 2) * plane, &rs));
+
+  if (algorithm == BAOREC_MULTIGRID) {
+    // reconstructed_potential! (src/recon.jl:184-212): delta -> planes 1..nzl of the slab-layout rhs
+    float* f_slab;
+    if (has_randoms) {
+      f_slab = rs;
+      BR_TRY(dist_setup_overdensity(ctx, p, d_mesh_slab, d_x, d_y, d_z, d_w, n_local, d_rx, d_ry, d_rz, d_rw,
+                                    n_ran_local, true, st));
+      BR_CUDA(cudaMemcpyAsync(f_slab + plane, d_mesh_slab, slab_r * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else {
+      // the C2R output goes straight to plane 1 (the scatter target at plane 0.. is dead by then)
+      f_slab = rs;
+      BR_TRY(dist_setup_overdensity(ctx, p, rs + plane, d_x, d_y, d_z, d_w, n_local, nullptr, nullptr, nullptr,
+                                    nullptr, 0, false, st));
+    }
+    float* phi;
+    BR_TRY(mg_fmg_dist(ctx, f_slab, &phi, p->beta, p->jacobi_damping_factor, p->jacobi_niterations,
+                       p->vcycle_niterations, los, st));
+    BR_CUDA(cudaMemcpyAsync(d_mesh_slab, phi + plane, slab_r * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // phi_k for read_shifts (the reference transforms phi in every compute_displacements call,
+    // src/multigrid.jl:787)
+    BR_TRY(dist_r2c(ctx, d_mesh_slab, keep, st));
+    ctx->kcache_potential = true;
+  } else if (los && !has_randoms) {
+    // fixed line of sight, periodic box: smoothing, normalisation and all iterations in one pass
+    BR_TRY(dist_scatter(ctx, rs, d_x, d_y, d_z, d_w, n_local, 1, p->mas, st));
+    BR_TRY(dist_r2c(ctx, rs, b.T, st));
+    // sum(rho) = DC mode, held by rank 0: broadcast it with the derived scale
+    BR_TRY(dist_stash_dc(ctx, b.T, 0, (double)ctx->M / (double)p->bias, st));
+    BR_TRY(dist_bcast_scal(ctx, st));
+    BR_TRY(kpass_fused_T(ctx, b.T, b.T, keep, p, st));
+    BR_TRY(dist_c2r(ctx, b.T, d_mesh_slab, st));
+  } else {
+    // delta_s in planes 1..nzl of RS (kept for the whole iteration)
+    float* ds = rs + plane;
+    if (has_randoms) {
+      BR_TRY(dist_setup_overdensity(ctx, p, d_mesh_slab, d_x, d_y, d_z, d_w, n_local, d_rx, d_ry, d_rz, d_rw,
+                                    n_ran_local, true, st));
+      BR_CUDA(cudaMemcpyAsync(ds, d_mesh_slab, slab_r * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else {
+      BR_TRY(dist_setup_overdensity(ctx, p, ds, d_x, d_y, d_z, d_w, n_local, nullptr, nullptr, nullptr, nullptr, 0,
+                                    false, st));
+    }
+    if (los) {
+      BR_TRY(dist_r2c(ctx, ds, b.T, st));
+      BR_TRY(kpass_fused_delta_T(ctx, b.T, b.T, keep, p, st));
+      BR_TRY(dist_c2r(ctx, b.T, d_mesh_slab, st));
+    } else {
+      // radial line of sight: iterate! (src/iterative.jl:151-211) on slabs, 1 R2C + 6 C2R per iteration
+      float2* pair;
+      float* X;
+      BR_TRY(need_t(ctx, BUF_CK2, slab_c, &pair));
+      BR_TRY(need_t(ctx, BUF_RX, (size_t)(nzl + 3) * plane, &X));
+      if (p->n_iter <= 0) BR_CUDA(cudaMemcpyAsync(d_mesh_slab, ds, slab_r * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      for (int it = 1; it <= p->n_iter; it++) {
+        BR_TRY(dist_r2c(ctx, it == 1 ? ds : d_mesh_slab, b.T, st));
+        bool first = true;
+        for (int i = 0; i < 3; i++)
+          for (int j = i; j < 3; j++) {
+            float fac = (float)((1.0 + (i != j ? 1.0 : 0.0)) * (double)p->beta);
+            if (it == 1) fac = fac / (1.0f + p->beta);
+            BR_TRY(kpass_iter_pair_T(ctx, b.T, pair, i, j, st));
+            BR_TRY(dist_c2r(ctx, pair, X, st));
+            BR_TRY(radial_update_slab(ctx, d_mesh_slab, first ? ds : d_mesh_slab, X, nzl, ctx->z0, i, j, fac, st));
+            first = false;
+          }
+      }
+      BR_TRY(dist_r2c(ctx, d_mesh_slab, keep, st));  // delta_k of the result for read_shifts
+    }
+  }
   BR_TRY(check_oob(ctx, st, "run_dist (particles must lie in this rank's slab)"));
   ctx->kcache_valid = true;
   return BAOREC_OK;
@@ -520,7 +695,7 @@ int baorec_read_shifts_dist_f32(baorec_ctx* ctx, const baorec_params* p, const f
   BR_REQUIRE(field >= BAOREC_FIELD_DISP && field <= BAOREC_FIELD_SUM, "unknown field");
   BR_REQUIRE(n_local >= 0 && (n_local == 0 || (d_x && d_y && d_z && d_sx && d_sy && d_sz)), "particle arrays");
   if (!ctx->kcache_valid) {
-    set_error("baorec_read_shifts_dist_f32: call baorec_run_dist_f32 first (no cached delta_k)");
+    set_error("baorec_read_shifts_dist_f32: call baorec_run_dist_f32 first (no cached delta_k / phi_k)");
     return BAOREC_ERR_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream;
@@ -535,7 +710,7 @@ int baorec_read_shifts_dist_f32(baorec_ctx* ctx, const baorec_params* p, const f
   BR_TRY(need_t(ctx, BUF_RY, (size_t)(nzl + 3) * plane, &psi[1]));
   BR_TRY(need_t(ctx, BUF_RZ, (size_t)(nzl + 3) * plane, &psi[2]));
   for (int c = 0; c < 3; c++) {
-    BR_TRY(kpass_disp_T(ctx, keep, b.T, c, st));
+    BR_TRY(kpass_disp_T(ctx, keep, b.T, c, ctx->kcache_potential, st));
     BR_TRY(dist_c2r(ctx, b.T, psi[c] + plane, st));  // own planes at local index 1 .. nzl
     // halo: plane 0 <- previous rank's last plane; planes nzl+1, nzl+2 <- next rank's first two
     BR_TRY(ring_exchange(ctx, psi[c] + (size_t)nzl * plane, next, psi[c], prev, plane, st));

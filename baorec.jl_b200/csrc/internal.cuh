@@ -83,6 +83,7 @@ enum BufId {
   BUF_A2A_RECV,
   BUF_A2A_RECV2,
   BUF_HALO,
+  BUF_MGD,      // multigrid level hierarchy of the slab-decomposed solver
   BUF_COUNT
 };
 
@@ -106,6 +107,11 @@ struct MgLevel {
   float* py = nullptr;
   float* pz = nullptr;
   float cell[3];
+  // slab-decomposed hierarchy (multi-GPU): slab != 0 -> this rank stores nzl real planes at plane
+  // index 1..nzl of an (nzl+2)-plane buffer (planes 0 and nzl+1 are halos); slab == 0 -> the level
+  // is replicated on every rank.  tmp: slab-layout window of the first replicated level.
+  int nzl = 0, slab = 0;
+  float* tmp = nullptr;
 };
 
 }  // namespace baorec
@@ -123,6 +129,11 @@ struct baorec_ctx {
   cufftHandle px_r2c = 0, px_c2r = 0;
   bool have_x_plans = false;
   float2* d_tw[2] = {nullptr, nullptr};  // twiddle tables for the y and z axes
+  // split FFT path (option "fft_split_planes" = C > 0): batched 2-D transforms over chunks of C planes
+  // (the intermediate of cuFFT's x and y passes stays L2-resident) + one strided 1-D pass along z
+  cufftHandle ps_r2c = 0, ps_c2r = 0, ps_z = 0;
+  int split_planes_planned = 0;
+  int opt_fft_split = 0;
   int opt_own_fft = 0;  // experimental: correct, but slower than cuFFT's strided passes today
   size_t work_bytes = 0;
   float* d_k[3] = {nullptr, nullptr, nullptr};  // k tables (xh, ny, nz)
@@ -154,6 +165,8 @@ struct baorec_ctx {
   std::vector<cudaEvent_t> prof_pool;     // recycled events
   // multigrid
   std::vector<baorec::MgLevel> levels;
+  std::vector<baorec::MgLevel> dlevels;  // slab-decomposed hierarchy (baorec_plan_dist)
+  int64_t opt_mg_slab_min_cells = 1 << 21;  // levels with fewer cells are replicated, not slab-decomposed
   bool mg_radial_tables = false;
   // distributed
   void* comm = nullptr;  // ncclComm_t
@@ -166,6 +179,7 @@ struct baorec_ctx {
   float2* own_recv[2] = {nullptr, nullptr};
   int a2a_parity = 0;
   int* d_barrier = nullptr;
+  bool kcache_potential = false;  // BUF_CKCACHE holds phi_k (MultigridRecon) instead of delta_k
   int slab_mode = 0;  // 0: whole mesh; 1: scatter into a slab (+1 ghost plane); 2: gather from a slab (+3 halo planes)
   cufftHandle p2d_r2c = 0, p2d_c2r = 0, p1d = 0;
   bool have_dist_plans = false;
@@ -224,7 +238,18 @@ void host_xvec(int n, float L, float mn, std::vector<float>& out);
 int stash_dc(baorec_ctx* ctx, const float2* ck, int slot, double mul, cudaStream_t st);
 int kpass_fused_T(baorec_ctx* ctx, const float2* in, float2* out_c2r, float2* keep, const baorec_params* p,
                   cudaStream_t st);
-int kpass_disp_T(baorec_ctx* ctx, const float2* in, float2* out, int comp, cudaStream_t st);
+int kpass_fused_delta_T(baorec_ctx* ctx, const float2* in, float2* out_c2r, float2* keep, const baorec_params* p,
+                        cudaStream_t st);
+int kpass_disp_T(baorec_ctx* ctx, const float2* in, float2* out, int comp, bool potential, cudaStream_t st);
+int kpass_setup_box_T(baorec_ctx* ctx, const float2* in, float2* out, const baorec_params* p, cudaStream_t st);
+int kpass_gauss_T(baorec_ctx* ctx, const float2* in, float2* out, float R, cudaStream_t st);
+int kpass_iter_pair_T(baorec_ctx* ctx, const float2* in, float2* out, int i, int j, cudaStream_t st);
+// real-space passes on a slab of `nzl` planes starting at global plane z_lo
+int radial_update_slab(baorec_ctx* ctx, float* out, const float* src, const float* X, int nzl, int z_lo, int ci,
+                       int cj, float fac, cudaStream_t st);
+// n_ran < 0: the randoms count is read from d_scal[2]
+int randoms_combine(baorec_ctx* ctx, float* out, const float* dat, const float* ran, float bias, float ran_min,
+                    double n_ran, size_t cells, cudaStream_t st);
 
 // fft.cu
 bool own_fft_available(const baorec_ctx* ctx);
@@ -243,6 +268,13 @@ int reconstructed_potential(baorec_ctx* ctx, const baorec_params* p, float* phi,
                             cudaStream_t st);
 int mg_fmg(baorec_ctx* ctx, const float* f, float* v, float beta, float damping, int n_jacobi, int n_vcycle,
            const float* los, cudaStream_t st);
+// Slab-decomposed fmg: f_slab is an (nz_loc+2)-plane buffer with this rank's right-hand side at
+// planes 1..nz_loc; *result is the library buffer (same layout) holding the solution.
+int mg_fmg_dist(baorec_ctx* ctx, float* f_slab, float** result, float beta, float damping, int n_jacobi,
+                int n_vcycle, const float* los, cudaStream_t st);
+// dist.cu: both halo planes of a slab-layout buffer (ring neighbours, periodic); all-gather of slabs
+int mg_halo_exchange(baorec_ctx* ctx, float* buf, size_t plane, int nzl, cudaStream_t st);
+int mg_allgather(baorec_ctx* ctx, const float* send, float* recv, size_t count, cudaStream_t st);
 
 #define BR_NEED_PLAN(ctx)                                        \
   do {                                                           \

@@ -258,6 +258,7 @@ randoms_combine_kernel(float* __restrict__ out, const float* __restrict__ dat, c
                        const double* __restrict__ scal, float bias, double ran_min, double n_ran, size_t n) {
   const float sd = (float)scal[0], sr = (float)scal[1];
   const float alpha = __fdiv_rn(sd, sr);
+  if (n_ran < 0.0) n_ran = scal[2];  // distributed: global randoms count, all-reduced into scal[2]
   const double thr = ran_min * (double)sr / n_ran;  // Float64 like the reference (0.01 literal, src/recon.jl:70,81)
   const float ba = __fmul_rn(bias, alpha);
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -507,14 +508,20 @@ static int run_kspace_t(baorec_ctx* ctx, const float2* in, Op op, cudaStream_t s
   return BAOREC_OK;
 }
 
-struct DispCompOp {  // one component of Psi = i k delta_k / k^2, /M (src/iterative.jl:268)
-  static const char* name() { return "kspace_kernel_t<DispCompOp>"; }
+template <bool POTENTIAL>
+struct DispCompOp {  // one component of Psi = i k delta_k / k^2 (src/iterative.jl:268) or i k phi_k (src/multigrid.jl:767), /M
+  static const char* name() { return POTENTIAL ? "kspace_kernel_t<DispCompOp<potential>>" : "kspace_kernel_t<DispCompOp<density>>"; }
   float2* out;
   int comp;
   float invM;
   __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool) const {
-    float k2 = ksq(kx, ky, kz);
-    float s = k2 > 0.f ? __fdiv_rn(invM, k2) : 0.f;
+    float s;
+    if (POTENTIAL) {
+      s = invM;
+    } else {
+      float k2 = ksq(kx, ky, kz);
+      s = k2 > 0.f ? __fdiv_rn(invM, k2) : 0.f;
+    }
     float kc = comp == 0 ? kx : (comp == 1 ? ky : kz);
     out[idx] = make_float2(__fmul_rn(__fmul_rn(-v.y, s), kc), __fmul_rn(__fmul_rn(v.x, s), kc));
   }
@@ -533,9 +540,55 @@ int kpass_fused_T(baorec_ctx* ctx, const float2* in, float2* out_c2r, float2* ke
   return run_kspace_t(ctx, in, op, st);
 }
 
-int kpass_disp_T(baorec_ctx* ctx, const float2* in, float2* out, int comp, cudaStream_t st) {
-  DispCompOp op{out, comp, (float)(1.0 / (double)ctx->M)};
+// same recurrence on the R2C of delta_s (randoms set-up done in real space)
+int kpass_fused_delta_T(baorec_ctx* ctx, const float2* in, float2* out_c2r, float2* keep, const baorec_params* p,
+                        cudaStream_t st) {
+  const float invM = (float)(1.0 / (double)ctx->M);
+  FusedLosOp<1> op{out_c2r, keep, 0.f, p->bias, ctx->d_scal, {p->los[0], p->los[1], p->los[2]}, p->beta, p->n_iter,
+                   invM};
   return run_kspace_t(ctx, in, op, st);
+}
+
+int kpass_disp_T(baorec_ctx* ctx, const float2* in, float2* out, int comp, bool potential, cudaStream_t st) {
+  const float invM = (float)(1.0 / (double)ctx->M);
+  if (potential) {
+    DispCompOp<true> op{out, comp, invM};
+    return run_kspace_t(ctx, in, op, st);
+  }
+  DispCompOp<false> op{out, comp, invM};
+  return run_kspace_t(ctx, in, op, st);
+}
+
+// dc[8] must hold 1 / (A0 bias) (stash_dc with mul = 1/bias)
+int kpass_setup_box_T(baorec_ctx* ctx, const float2* in, float2* out, const baorec_params* p, cudaStream_t st) {
+  SetupBoxOp op{out, p->smoothing_radius * p->smoothing_radius, p->bias, ctx->d_scal};
+  return run_kspace_t(ctx, in, op, st);
+}
+
+int kpass_gauss_T(baorec_ctx* ctx, const float2* in, float2* out, float R, cudaStream_t st) {
+  GaussOp op{out, R * R, 1.0 / (double)ctx->M};
+  return run_kspace_t(ctx, in, op, st);
+}
+
+int kpass_iter_pair_T(baorec_ctx* ctx, const float2* in, float2* out, int i, int j, cudaStream_t st) {
+  IterPairOp op{out, i, j, (float)(1.0 / (double)ctx->M)};
+  return run_kspace_t(ctx, in, op, st);
+}
+
+int radial_update_slab(baorec_ctx* ctx, float* out, const float* src, const float* X, int nzl, int z_lo, int ci,
+                       int cj, float fac, cudaStream_t st) {
+  unsigned gx = stream_grid((size_t)ctx->nx * ctx->ny, 256);
+  dim3 grid(gx > 64 ? 64 : gx, nzl);
+  BR_LAUNCH(ctx, radial_update_kernel, grid, 256, 0, st, out, src, X, ctx->d_xv[0], ctx->d_xv[1], ctx->d_xv[2] + z_lo,
+            ctx->nx, ctx->ny, ci, cj, fac);
+  return BAOREC_OK;
+}
+
+int randoms_combine(baorec_ctx* ctx, float* out, const float* dat, const float* ran, float bias, float ran_min,
+                    double n_ran, size_t cells, cudaStream_t st) {
+  BR_LAUNCH(ctx, randoms_combine_kernel, stream_grid(cells, 256), 256, 0, st, out, dat, ran, ctx->d_scal, bias,
+            (double)ran_min, n_ran, cells);
+  return BAOREC_OK;
 }
 
 }  // namespace baorec

@@ -24,6 +24,9 @@ struct MgGeom {
   float beta;
   int radial;
   float lp[3];  // los / cell
+  // slab mode (multi-GPU): nz = local real planes, stored at plane index 1..nz of an (nz+2)-plane
+  // buffer whose planes 0 and nz+1 are halos; zlo = global index of the first real plane
+  int slab, zlo;
 };
 
 static MgGeom mg_geom(const baorec_ctx* ctx, int nx, int ny, int nz, float beta, const float* los) {
@@ -41,6 +44,8 @@ static MgGeom mg_geom(const baorec_ctx* ctx, int nx, int ny, int nz, float beta,
   }
   g.beta = beta;
   g.radial = los ? 0 : 1;
+  g.slab = 0;
+  g.zlo = 0;
   return g;
 }
 
@@ -60,16 +65,17 @@ mg_stencil_generic(float* __restrict__ out, const float* __restrict__ v, const f
                    float omega) {
   const int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y * blockDim.y + threadIdx.y, iz = blockIdx.z;
   if (ix >= g.nx || iy >= g.ny) return;
-  const size_t idx = ((size_t)iz * g.ny + iy) * g.nx + ix;
+  const int pl = iz + g.slab;  // storage plane
+  const size_t idx = ((size_t)pl * g.ny + iy) * g.nx + ix;
   int xp = ix + 1 == g.nx ? 0 : ix + 1, xm = ix == 0 ? g.nx - 1 : ix - 1;
   int yp = iy + 1 == g.ny ? 0 : iy + 1, ym = iy == 0 ? g.ny - 1 : iy - 1;
-  int zp = iz + 1 == g.nz ? 0 : iz + 1, zm = iz == 0 ? g.nz - 1 : iz - 1;
+  int zp = g.slab ? pl + 1 : (iz + 1 == g.nz ? 0 : iz + 1), zm = g.slab ? pl - 1 : (iz == 0 ? g.nz - 1 : iz - 1);
   auto V = [&](int x, int y, int z) { return __ldg(v + ((size_t)z * g.ny + y) * g.nx + x); };
   float px, py, pz;
   if (g.radial) {
     px = mg_p(g, 0, ix);
     py = mg_p(g, 1, iy);
-    pz = mg_p(g, 2, iz);
+    pz = mg_p(g, 2, g.zlo + iz);
   } else {
     px = g.lp[0];
     py = g.lp[1];
@@ -77,16 +83,16 @@ mg_stencil_generic(float* __restrict__ out, const float* __restrict__ v, const f
   }
   float gg = g.beta / (g.c2[0] * px * px + g.c2[1] * py * py + g.c2[2] * pz * pz);
   float gx = g.ic2[0] + gg * px * px, gy = g.ic2[1] + gg * py * py, gz = g.ic2[2] + gg * pz * pz;
-  float vxp = V(xp, iy, iz), vxm = V(xm, iy, iz), vyp = V(ix, yp, iz), vym = V(ix, ym, iz);
+  float vxp = V(xp, iy, pl), vxm = V(xm, iy, pl), vyp = V(ix, yp, pl), vym = V(ix, ym, pl);
   float vzp = V(ix, iy, zp), vzm = V(ix, iy, zm);
   float off = gx * (vxp + vxm) + gy * (vyp + vym) + gz * (vzp + vzm) +
               gg / 2 *
-                  (px * py * (V(xp, yp, iz) + V(xm, ym, iz) - V(xm, yp, iz) - V(xp, ym, iz)) +
+                  (px * py * (V(xp, yp, pl) + V(xm, ym, pl) - V(xm, yp, pl) - V(xp, ym, pl)) +
                    px * pz * (V(xp, iy, zp) + V(xm, iy, zm) - V(xm, iy, zp) - V(xp, iy, zm)) +
                    py * pz * (V(ix, yp, zp) + V(ix, ym, zm) - V(ix, ym, zp) - V(ix, yp, zm)));
   if (g.radial) off += gg * (px * (vxp - vxm) + py * (vyp - vym) + pz * (vzp - vzm));
   float diag = 2 * (gx + gy + gz);
-  float vc = V(ix, iy, iz);
+  float vc = V(ix, iy, pl);
   if (MODE == MG_JACOBI) {
     float jac = (f[idx] + off) / diag;
     out[idx] = (1 - omega) * vc + omega * jac;
@@ -150,26 +156,26 @@ mg_stencil_march(float* __restrict__ out, const float* __restrict__ v, const flo
   // planes: A = z-1, B = z, C = z+1; each holds rows y-1, y, y+1
   Row6 Am, A0, Ap, Bm, B0, Bp, Cm, C0, Cp;
   {
-    int za = zbeg == 0 ? nz - 1 : zbeg - 1;
+    int za = g.slab ? zbeg : (zbeg == 0 ? nz - 1 : zbeg - 1);  // storage plane of real plane zbeg-1
     const float* pa = v + (size_t)za * plane;
     Am = load_row(pa + rm, x0, xm, xp);
     A0 = load_row(pa + r0, x0, xm, xp);
     Ap = load_row(pa + rp, x0, xm, xp);
-    const float* pb = v + (size_t)zbeg * plane;
+    const float* pb = v + (size_t)(zbeg + g.slab) * plane;
     Bm = load_row(pb + rm, x0, xm, xp);
     B0 = load_row(pb + r0, x0, xm, xp);
     Bp = load_row(pb + rp, x0, xm, xp);
   }
 #pragma unroll 3
   for (int iz = zbeg; iz < zend; iz++) {
-    int zc = iz + 1 == nz ? 0 : iz + 1;
+    int zc = g.slab ? iz + 2 : (iz + 1 == nz ? 0 : iz + 1);
     const float* pc = v + (size_t)zc * plane;
     Cm = load_row(pc + rm, x0, xm, xp);
     C0 = load_row(pc + r0, x0, xm, xp);
     Cp = load_row(pc + rp, x0, xm, xp);
-    const size_t o = (size_t)iz * plane + r0 + x0;
+    const size_t o = (size_t)(iz + g.slab) * plane + r0 + x0;
     float4 fv = __ldg(reinterpret_cast<const float4*>(f + o));
-    if (RADIAL) pz = mg_p(g, 2, iz);
+    if (RADIAL) pz = mg_p(g, 2, g.zlo + iz);
     const float cz2 = g.c2[2] * pz * pz, byz = by2 + cz2;
 
     const float bm[6] = {Bm.m, Bm.a, Bm.b, Bm.c, Bm.d, Bm.p};
@@ -207,16 +213,16 @@ mg_stencil_march(float* __restrict__ out, const float* __restrict__ v, const flo
 
 // ---- restriction (reduce!, src/multigrid.jl:520-584): coarse c <- fine 2c+1, weights 8/4/2/1 /64
 __global__ void __launch_bounds__(256)
-mg_restrict_kernel(float* __restrict__ c, const float* __restrict__ fine, int nx, int ny, int nz) {
+mg_restrict_kernel(float* __restrict__ c, const float* __restrict__ fine, int nx, int ny, int nz, int slab) {
   int cx = nx / 2, cy = ny / 2, cz = nz / 2;
   const int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y * blockDim.y + threadIdx.y, iz = blockIdx.z;
   if (ix >= cx || iy >= cy || iz >= cz) return;
-  const size_t idx = ((size_t)iz * cy + iy) * cx + ix;
+  const size_t idx = ((size_t)(iz + slab) * cy + iy) * cx + ix;
   int X[3], Y[3], Z[3];
-  int fx = 2 * ix + 1, fy = 2 * iy + 1, fz = 2 * iz + 1;
+  int fx = 2 * ix + 1, fy = 2 * iy + 1, fz = 2 * iz + 1 + slab;
   X[0] = fx - 1; X[1] = fx; X[2] = fx + 1 == nx ? 0 : fx + 1;
   Y[0] = fy - 1; Y[1] = fy; Y[2] = fy + 1 == ny ? 0 : fy + 1;
-  Z[0] = fz - 1; Z[1] = fz; Z[2] = fz + 1 == nz ? 0 : fz + 1;
+  Z[0] = fz - 1; Z[1] = fz; Z[2] = slab ? fz + 1 : (fz + 1 == nz ? 0 : fz + 1);
   float s8 = 0.f, s4 = 0.f, s2 = 0.f, s1 = 0.f;
 #pragma unroll
   for (int c3 = 0; c3 < 3; c3++)
@@ -241,14 +247,15 @@ mg_restrict_kernel(float* __restrict__ c, const float* __restrict__ fine, int nx
 // ADD: out = out + P(coarse) (the `v += v1h` of vcycle!, src/multigrid.jl:680), else out = P(coarse).
 template <bool ADD>
 __global__ void __launch_bounds__(256)
-mg_prolong_kernel(float* __restrict__ fine, const float* __restrict__ c, int nx, int ny, int nz) {
+mg_prolong_kernel(float* __restrict__ fine, const float* __restrict__ c, int nx, int ny, int nz, int slab) {
   // one thread per coarse cell (cx,cy,cz): writes the 2x2x2 fine cells (2c, 2c+1) per axis from the
   // coarse cells {c-1, c} per axis (8 loads, 4 aligned float2 stores)
   const int cx = nx / 2, cy = ny / 2, cz = nz / 2;
   const int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y * blockDim.y + threadIdx.y, iz = blockIdx.z;
   if (ix >= cx || iy >= cy) return;
-  const int xm = ix == 0 ? cx - 1 : ix - 1, ym = iy == 0 ? cy - 1 : iy - 1, zm = iz == 0 ? cz - 1 : iz - 1;
-  const int X[2] = {xm, ix}, Y[2] = {ym, iy}, Z[2] = {zm, iz};
+  const int xm = ix == 0 ? cx - 1 : ix - 1, ym = iy == 0 ? cy - 1 : iy - 1;
+  const int zm = slab ? iz : (iz == 0 ? cz - 1 : iz - 1);  // storage plane of coarse plane iz-1
+  const int X[2] = {xm, ix}, Y[2] = {ym, iy}, Z[2] = {zm, iz + slab};
   float xe[2][2], xo[2][2];  // [dz][dy]: even / odd fine x
 #pragma unroll
   for (int dz = 0; dz < 2; dz++)
@@ -271,7 +278,7 @@ mg_prolong_kernel(float* __restrict__ fine, const float* __restrict__ c, int nx,
       }
       float ve = pz ? e[1] : 0.5f * (e[0] + e[1]);
       float vo = pz ? o[1] : 0.5f * (o[0] + o[1]);
-      float2* dst = reinterpret_cast<float2*>(fine + ((size_t)(2 * iz + pz) * ny + (2 * iy + py)) * nx + 2 * ix);
+      float2* dst = reinterpret_cast<float2*>(fine + ((size_t)(2 * iz + pz + slab) * ny + (2 * iy + py)) * nx + 2 * ix);
       if (ADD) {
         float2 cur = *dst;
         ve += cur.x;
@@ -309,13 +316,21 @@ static int launch_stencil(baorec_ctx* ctx, float* out, const float* v, const flo
   return BAOREC_OK;
 }
 
+// Slab levels (multi-GPU): refresh both halo planes of `buf` from the ring neighbours.
+static int level_halo(baorec_ctx* ctx, const MgLevel* L, float* buf, cudaStream_t st) {
+  if (!L || !L->slab) return BAOREC_OK;
+  return mg_halo_exchange(ctx, buf, (size_t)L->nx * L->ny, L->nzl, st);
+}
+
 // niter damped-Jacobi sweeps ping-ponging a <-> b; *result points at the buffer holding the result.
+// On a slab level the halos of the new iterate are exchanged after every sweep.
 static int jacobi_pp(baorec_ctx* ctx, float* a, float* b, const float* f, const MgGeom& g, float omega, int niter,
-                     float** result, cudaStream_t st) {
+                     float** result, cudaStream_t st, const MgLevel* L = nullptr) {
   float* cur = a;
   float* alt = b;
   for (int i = 0; i < niter; i++) {
     BR_TRY(launch_stencil<MG_JACOBI>(ctx, alt, cur, f, g, omega, st));
+    BR_TRY(level_halo(ctx, L, alt, st));
     float* t = cur;
     cur = alt;
     alt = t;
@@ -324,23 +339,28 @@ static int jacobi_pp(baorec_ctx* ctx, float* a, float* b, const float* f, const 
   return BAOREC_OK;
 }
 
-static int restrict_to(baorec_ctx* ctx, float* coarse, const float* fine, int nx, int ny, int nz, cudaStream_t st) {
+static int restrict_to(baorec_ctx* ctx, float* coarse, const float* fine, int nx, int ny, int nz, cudaStream_t st,
+                       int slab = 0) {
   dim3 block(32, 8), grid(cdiv(nx / 2, 32), cdiv(ny / 2, 8), nz / 2);
-  BR_LAUNCH(ctx, mg_restrict_kernel, grid, block, 0, st, coarse, fine, nx, ny, nz);
+  BR_LAUNCH(ctx, mg_restrict_kernel, grid, block, 0, st, coarse, fine, nx, ny, nz, slab);
   return BAOREC_OK;
 }
 
 static int prolong_to(baorec_ctx* ctx, float* fine, const float* coarse, int nx, int ny, int nz, bool add,
-                      cudaStream_t st) {
+                      cudaStream_t st, int slab = 0) {
   dim3 block(32, 8), grid(cdiv(nx / 2, 32), cdiv(ny / 2, 8), nz / 2);
-  if (add) BR_LAUNCH(ctx, mg_prolong_kernel<true>, grid, block, 0, st, fine, coarse, nx, ny, nz);
-  else BR_LAUNCH(ctx, mg_prolong_kernel<false>, grid, block, 0, st, fine, coarse, nx, ny, nz);
+  if (add) BR_LAUNCH(ctx, mg_prolong_kernel<true>, grid, block, 0, st, fine, coarse, nx, ny, nz, slab);
+  else BR_LAUNCH(ctx, mg_prolong_kernel<false>, grid, block, 0, st, fine, coarse, nx, ny, nz, slab);
   return BAOREC_OK;
 }
 
 static bool can_recurse(int nx, int ny, int nz) {
   return nx > 4 && ny > 4 && nz > 4 && nx % 2 == 0 && ny % 2 == 0 && nz % 2 == 0;
 }
+
+static size_t pad64(size_t c) { return (c + 63) & ~(size_t)63; }
+// floats a level buffer holds: slab levels carry two halo planes
+static size_t level_elems(const MgLevel& l) { return l.slab ? (size_t)(l.nzl + 2) * l.nx * l.ny : l.cells; }
 
 int mg_setup_levels(baorec_ctx* ctx) {
   if (!ctx->levels.empty()) return BAOREC_OK;
@@ -360,27 +380,89 @@ int mg_setup_levels(baorec_ctx* ctx) {
   }
   // one slab: level 0 needs vb only (f and va are the caller's); deeper levels need f, va, vb
   size_t total = 0;
-  auto pad = [](size_t c) { return (c + 63) & ~(size_t)63; };
-  for (size_t i = 0; i < lv.size(); i++) total += pad(lv[i].cells) * (i == 0 ? 1 : 3);
+  for (size_t i = 0; i < lv.size(); i++) total += pad64(lv[i].cells) * (i == 0 ? 1 : 3);
   float* base;
   BR_TRY(need_t(ctx, BUF_MG, total, &base));
   size_t off = 0;
   for (size_t i = 0; i < lv.size(); i++) {
     if (i > 0) {
       lv[i].f = base + off;
-      off += pad(lv[i].cells);
+      off += pad64(lv[i].cells);
       lv[i].va = base + off;
-      off += pad(lv[i].cells);
+      off += pad64(lv[i].cells);
     }
     lv[i].vb = base + off;
-    off += pad(lv[i].cells);
+    off += pad64(lv[i].cells);
   }
   ctx->levels = lv;
   return BAOREC_OK;
 }
 
+// Hierarchy of the slab-decomposed solver.  Level 0 is this rank's z slab; a coarser level stays
+// slab-decomposed while every rank keeps an even number (>= 2) of planes and the level has at
+// least opt_mg_slab_min_cells cells; below that the level is replicated: the restricted residual
+// is all-gathered and every rank runs the (tiny, launch-bound) coarse V-cycle redundantly.
+static int mg_setup_dist_levels(baorec_ctx* ctx) {
+  if (!ctx->dlevels.empty()) return BAOREC_OK;
+  std::vector<MgLevel> lv;
+  int nx = ctx->nx, ny = ctx->ny, nz = ctx->nz;
+  MgLevel l0;
+  l0.nx = nx;
+  l0.ny = ny;
+  l0.nz = nz;
+  l0.cells = (size_t)nx * ny * nz;
+  l0.slab = 1;
+  l0.nzl = ctx->nz_loc;
+  lv.push_back(l0);
+  while (can_recurse(nx, ny, nz)) {
+    const MgLevel par = lv.back();
+    if (par.slab && par.nzl % 2 != 0) {
+      set_error("slab-decomposed multigrid needs an even number of planes per rank (nz/P = %d)", par.nzl);
+      return BAOREC_ERR_INVALID;
+    }
+    nx /= 2;
+    ny /= 2;
+    nz /= 2;
+    MgLevel l;
+    l.nx = nx;
+    l.ny = ny;
+    l.nz = nz;
+    l.cells = (size_t)nx * ny * nz;
+    const int half = par.nzl / 2;
+    l.slab = par.slab && half >= 2 && half % 2 == 0 && (int64_t)l.cells >= ctx->opt_mg_slab_min_cells;
+    l.nzl = l.slab ? half : 0;
+    lv.push_back(l);
+  }
+  size_t total = 0;
+  for (size_t i = 0; i < lv.size(); i++) {
+    total += pad64(level_elems(lv[i])) * (i == 0 ? 2 : 3);
+    if (i > 0 && lv[i - 1].slab && !lv[i].slab) total += pad64((size_t)(lv[i - 1].nzl / 2 + 2) * lv[i].nx * lv[i].ny);
+  }
+  float* base;
+  BR_TRY(need_t(ctx, BUF_MGD, total, &base));
+  size_t off = 0;
+  for (size_t i = 0; i < lv.size(); i++) {
+    const size_t e = pad64(level_elems(lv[i]));
+    if (i > 0) {
+      lv[i].f = base + off;
+      off += e;
+    }
+    lv[i].va = base + off;
+    off += e;
+    lv[i].vb = base + off;
+    off += e;
+    if (i > 0 && lv[i - 1].slab && !lv[i].slab) {
+      lv[i].tmp = base + off;
+      off += pad64((size_t)(lv[i - 1].nzl / 2 + 2) * lv[i].nx * lv[i].ny);
+    }
+  }
+  ctx->dlevels = lv;
+  return BAOREC_OK;
+}
+
 struct MgRun {
   baorec_ctx* ctx;
+  std::vector<MgLevel>* lv;
   float beta, omega;
   int nj;
   const float* los;
@@ -391,26 +473,72 @@ struct MgRun {
 
 static float* other_buf(const MgLevel& l, float* cur) { return cur == l.va ? l.vb : l.va; }
 
+static MgGeom level_geom(const baorec_ctx* ctx, const MgLevel& L, float beta, const float* los) {
+  MgGeom g = mg_geom(ctx, L.nx, L.ny, L.nz, beta, los);  // cell sizes from the global level size
+  if (L.slab) {
+    g.nz = L.nzl;
+    g.slab = 1;
+    g.zlo = ctx->rank * L.nzl;
+  }
+  return g;
+}
+
+// reduce! from level l to l+1.  Slab fine levels read their upper halo plane (fine 2c+2 of the last
+// local coarse plane), so `fine` must have current halos.
+static int restrict_level(MgRun& r, size_t l, const float* fine, float* coarse) {
+  baorec_ctx* ctx = r.ctx;
+  const MgLevel& F = (*r.lv)[l];
+  const MgLevel& C = (*r.lv)[l + 1];
+  if (!F.slab) return restrict_to(ctx, coarse, fine, F.nx, F.ny, F.nz, r.st, 0);
+  if (C.slab) return restrict_to(ctx, coarse, fine, F.nx, F.ny, F.nzl, r.st, 1);
+  // transition: restrict this rank's planes, then all-gather them into the replicated coarse level
+  const size_t cplane = (size_t)C.nx * C.ny;
+  BR_TRY(restrict_to(ctx, C.tmp, fine, F.nx, F.ny, F.nzl, r.st, 1));
+  return mg_allgather(ctx, C.tmp + cplane, coarse, (size_t)(F.nzl / 2) * cplane, r.st);
+}
+
+// prolong! from level l+1 to l (add: v += P(coarse)).  Slab coarse levels are read at planes c-1, c:
+// their lower halo must be current.
+static int prolong_level(MgRun& r, size_t l, const float* coarse, float* fine, bool add) {
+  baorec_ctx* ctx = r.ctx;
+  const MgLevel& F = (*r.lv)[l];
+  const MgLevel& C = (*r.lv)[l + 1];
+  if (!F.slab) return prolong_to(ctx, fine, coarse, F.nx, F.ny, F.nz, add, r.st, 0);
+  if (C.slab) return prolong_to(ctx, fine, coarse, F.nx, F.ny, F.nzl, add, r.st, 1);
+  // transition: slab-layout window (plane below + own planes) of the replicated coarse level
+  const size_t cplane = (size_t)C.nx * C.ny;
+  const int nzc = F.nzl / 2, zlo = ctx->rank * nzc;
+  const int below = (zlo - 1 + C.nz) % C.nz;
+  BR_CUDA(cudaMemcpyAsync(C.tmp, coarse + (size_t)below * cplane, cplane * sizeof(float), cudaMemcpyDeviceToDevice,
+                          r.st));
+  BR_CUDA(cudaMemcpyAsync(C.tmp + cplane, coarse + (size_t)zlo * cplane, (size_t)nzc * cplane * sizeof(float),
+                          cudaMemcpyDeviceToDevice, r.st));
+  return prolong_to(ctx, fine, C.tmp, F.nx, F.ny, F.nzl, add, r.st, 1);
+}
+
 // vcycle! (src/multigrid.jl:654-687) at level l, operating on run.cur[l]
 static int vcycle_level(MgRun& r, size_t l) {
   baorec_ctx* ctx = r.ctx;
-  MgLevel& L = ctx->levels[l];
-  MgGeom g = mg_geom(ctx, L.nx, L.ny, L.nz, r.beta, r.los);
+  std::vector<MgLevel>& lv = *r.lv;
+  MgLevel& L = lv[l];
+  MgGeom g = level_geom(ctx, L, r.beta, r.los);
   float* res;
-  BR_TRY(jacobi_pp(ctx, r.cur[l], other_buf(L, r.cur[l]), r.f[l], g, r.omega, r.nj, &res, r.st));
+  BR_TRY(jacobi_pp(ctx, r.cur[l], other_buf(L, r.cur[l]), r.f[l], g, r.omega, r.nj, &res, r.st, &L));
   r.cur[l] = res;
-  if (l + 1 < ctx->levels.size()) {
-    MgLevel& C = ctx->levels[l + 1];
+  if (l + 1 < lv.size()) {
+    MgLevel& C = lv[l + 1];
     float* rbuf = other_buf(L, r.cur[l]);
     BR_TRY(launch_stencil<MG_RESIDUAL>(ctx, rbuf, r.cur[l], r.f[l], g, 0.f, r.st));
-    BR_TRY(restrict_to(ctx, C.f, rbuf, L.nx, L.ny, L.nz, r.st));
-    BR_CUDA(cudaMemsetAsync(C.va, 0, C.cells * sizeof(float), r.st));
+    BR_TRY(level_halo(ctx, &L, rbuf, r.st));
+    BR_TRY(restrict_level(r, l, rbuf, C.f));
+    BR_CUDA(cudaMemsetAsync(C.va, 0, level_elems(C) * sizeof(float), r.st));
     r.cur[l + 1] = C.va;
     r.f[l + 1] = C.f;
     BR_TRY(vcycle_level(r, l + 1));
-    BR_TRY(prolong_to(ctx, r.cur[l], r.cur[l + 1], L.nx, L.ny, L.nz, true, r.st));
+    BR_TRY(prolong_level(r, l, r.cur[l + 1], r.cur[l], true));
+    BR_TRY(level_halo(ctx, &L, r.cur[l], r.st));
   }
-  BR_TRY(jacobi_pp(ctx, r.cur[l], other_buf(L, r.cur[l]), r.f[l], g, r.omega, r.nj, &res, r.st));
+  BR_TRY(jacobi_pp(ctx, r.cur[l], other_buf(L, r.cur[l]), r.f[l], g, r.omega, r.nj, &res, r.st, &L));
   r.cur[l] = res;
   return BAOREC_OK;
 }
@@ -419,7 +547,7 @@ int mg_vcycle(baorec_ctx* ctx, float* v, const float* f, float beta, float dampi
               cudaStream_t st) {
   BR_TRY(mg_setup_levels(ctx));
   ctx->levels[0].va = v;
-  MgRun r{ctx, beta, damping, nj, los, st, {}, {}};
+  MgRun r{ctx, &ctx->levels, beta, damping, nj, los, st, {}, {}};
   r.cur.assign(ctx->levels.size(), nullptr);
   r.f.assign(ctx->levels.size(), nullptr);
   r.cur[0] = v;
@@ -429,38 +557,60 @@ int mg_vcycle(baorec_ctx* ctx, float* v, const float* f, float beta, float dampi
   return BAOREC_OK;
 }
 
-// fmg (src/multigrid.jl:722-752)
-int mg_fmg(baorec_ctx* ctx, const float* f, float* v, float beta, float damping, int n_jacobi, int n_vcycle,
-           const float* los, cudaStream_t st) {
-  BR_TRY(mg_setup_levels(ctx));
-  auto& lv = ctx->levels;
+// fmg (src/multigrid.jl:722-752) over the hierarchy *r.lv; lv[0].va / r.f[0] are set by the caller.
+static int fmg_levels(MgRun& r, int n_vcycle) {
+  baorec_ctx* ctx = r.ctx;
+  std::vector<MgLevel>& lv = *r.lv;
   const size_t nl = lv.size();
-  lv[0].va = v;
-  MgRun r{ctx, beta, damping, n_jacobi, los, st, {}, {}};
-  r.cur.assign(nl, nullptr);
-  r.f.assign(nl, nullptr);
-  r.f[0] = f;
+  cudaStream_t st = r.st;
+  const float* f0 = r.f[0];
   for (size_t l = 0; l + 1 < nl; l++) {
-    BR_TRY(restrict_to(ctx, lv[l + 1].f, r.f[l], lv[l].nx, lv[l].ny, lv[l].nz, st));
+    BR_TRY(level_halo(ctx, &lv[l], const_cast<float*>(r.f[l]), st));
+    BR_TRY(restrict_level(r, l, r.f[l], lv[l + 1].f));
     r.f[l + 1] = lv[l + 1].f;
   }
   // Stage li (coarse -> fine) runs V-cycles that overwrite the f/v buffers of levels > li only;
   // those levels have finished their own stage by then, so one restriction chain suffices.
   for (size_t li = nl; li-- > 0;) {
-    r.f[li] = li == 0 ? f : lv[li].f;
+    r.f[li] = li == 0 ? f0 : lv[li].f;
+    float* tgt = lv[li].va;
     if (li + 1 < nl) {
       // initial guess: prolong the coarser solution (overwrites every fine cell)
-      float* tgt = li == 0 ? v : lv[li].va;
-      BR_TRY(prolong_to(ctx, tgt, r.cur[li + 1], lv[li].nx, lv[li].ny, lv[li].nz, false, st));
-      r.cur[li] = tgt;
-    } else {
-      float* tgt = li == 0 ? v : lv[li].va;
-      if (li != 0) BR_CUDA(cudaMemsetAsync(tgt, 0, lv[li].cells * sizeof(float), st));
-      r.cur[li] = tgt;
+      BR_TRY(prolong_level(r, li, r.cur[li + 1], tgt, false));
+      BR_TRY(level_halo(ctx, &lv[li], tgt, st));
+    } else if (li != 0 || lv[li].slab) {
+      BR_CUDA(cudaMemsetAsync(tgt, 0, level_elems(lv[li]) * sizeof(float), st));
     }
+    r.cur[li] = tgt;
     for (int c = 0; c < n_vcycle; c++) BR_TRY(vcycle_level(r, li));
   }
+  return BAOREC_OK;
+}
+
+int mg_fmg(baorec_ctx* ctx, const float* f, float* v, float beta, float damping, int n_jacobi, int n_vcycle,
+           const float* los, cudaStream_t st) {
+  BR_TRY(mg_setup_levels(ctx));
+  auto& lv = ctx->levels;
+  lv[0].va = v;
+  MgRun r{ctx, &lv, beta, damping, n_jacobi, los, st, {}, {}};
+  r.cur.assign(lv.size(), nullptr);
+  r.f.assign(lv.size(), nullptr);
+  r.f[0] = f;
+  BR_TRY(fmg_levels(r, n_vcycle));
   if (r.cur[0] != v) BR_CUDA(cudaMemcpyAsync(v, r.cur[0], ctx->M * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return BAOREC_OK;
+}
+
+int mg_fmg_dist(baorec_ctx* ctx, float* f_slab, float** result, float beta, float damping, int n_jacobi,
+                int n_vcycle, const float* los, cudaStream_t st) {
+  BR_TRY(mg_setup_dist_levels(ctx));
+  auto& lv = ctx->dlevels;
+  MgRun r{ctx, &lv, beta, damping, n_jacobi, los, st, {}, {}};
+  r.cur.assign(lv.size(), nullptr);
+  r.f.assign(lv.size(), nullptr);
+  r.f[0] = f_slab;
+  BR_TRY(fmg_levels(r, n_vcycle));
+  *result = r.cur[0];
   return BAOREC_OK;
 }
 

@@ -153,10 +153,32 @@ def dist_c2r(ctx: Context, kslab_t, out_slab):
     return out_slab
 
 
-def run_dist(recon, grid_size, data_x, data_y, data_z, data_w, ctx: Context = None):
-    """run!(recon, grid_size, data...) over all ranks: pass this rank's slab particles, get this
-    rank's slab of the reconstructed mesh, shape (nz_loc, ny, nx)."""
+def setup_box_dist(pos_x, pos_y, pos_z, box_pad, group=None):
+    """setup_box (src/utils.jl:100-109) of a catalog spread over the ranks: local min/max per axis,
+    all-reduced, then the reference's Float32 arithmetic.  Works on CPU (gloo) and CUDA tensors."""
+    import torch.distributed as dist
+    big = torch.finfo(torch.float32).max
+    lo = torch.stack([p.min() if p.numel() else p.new_tensor(big) for p in (pos_x, pos_y, pos_z)])
+    hi = torch.stack([p.max() if p.numel() else p.new_tensor(-big) for p in (pos_x, pos_y, pos_z)])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    half = np.float32(box_pad) / np.float32(2)
+    mn = lo.cpu().numpy().astype(np.float32) - half
+    mx = hi.cpu().numpy().astype(np.float32) + half
+    return np.full(3, (mx - mn).max(), dtype=np.float32), mn.astype(np.float32)
+
+
+def run_dist(recon, grid_size, data_x, data_y, data_z, data_w, rand_x=None, rand_y=None, rand_z=None, rand_w=None,
+             ctx: Context = None):
+    """run!(recon, grid_size, data...[, rand...]) over all ranks: pass this rank's slab particles
+    (exchange_catalog / shard_catalog), get this rank's slab of the result mesh, shape
+    (nz_loc, ny, nx): delta_r for IterativeRecon, phi for MultigridRecon.  With randoms the caller
+    sets recon.box_size / box_min from setup_box_dist(rand..., 500) BEFORE sharding (run! does it
+    from the full randoms catalog, src/recon.jl:172,253)."""
     n = _chk_vec(data_x, data_y, data_z, data_w)
+    has_ran = rand_x is not None
+    nr = _chk_vec(rand_x, rand_y, rand_z, rand_w) if has_ran else 0
     ctx = ctx or Context.get(data_x.device.index)
     plan(ctx, grid_size, recon.box_size, recon.box_min)
     recon.fft_plan = FFTPlan(ctx, tuple(int(v) for v in grid_size))
@@ -165,12 +187,15 @@ def run_dist(recon, grid_size, data_x, data_y, data_z, data_w, ctx: Context = No
     mesh = torch.empty((nzl, ny, nx), dtype=torch.float32, device=data_x.device)
     p = recon._params()
     L.check(ctx.lib.baorec_run_dist_f32(ctx.handle, C.byref(p), recon.algorithm, _ptr(data_x), _ptr(data_y),
-                                        _ptr(data_z), _ptr(data_w), n, _ptr(mesh), _stream()))
+                                        _ptr(data_z), _ptr(data_w), n, _ptr(rand_x), _ptr(rand_y), _ptr(rand_z),
+                                        _ptr(rand_w), nr, int(has_ran), _ptr(mesh), _stream()))
     recon.result_cache = mesh
     return mesh
 
 
 def read_shifts_dist(recon, data_x, data_y, data_z, field="disp", positions=False):
+    """read_shifts / reconstructed_positions for this rank's slab particles against the result of
+    the last run_dist (IterativeRecon: delta_k; MultigridRecon: phi_k kept by the library)."""
     n = _chk_vec(data_x, data_y, data_z)
     ctx = recon.fft_plan.ctx
     p = recon._params()

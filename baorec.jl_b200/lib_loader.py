@@ -68,7 +68,7 @@ SIGNATURES = {
     "baorec_slab_owner_f32": [_vp, _vp, _i64, _vp, _vp],
     "baorec_dist_r2c_f32": [_vp, _vp, _vp, _vp],
     "baorec_dist_c2r_f32": [_vp, _vp, _vp, _vp],
-    "baorec_run_dist_f32": [_vp, _pp, _i, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
+    "baorec_run_dist_f32": [_vp, _pp, _i, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp],
     "baorec_read_shifts_dist_f32": [_vp, _pp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp],
     "baorec_cic_scatter_f32": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
     "baorec_cic_cells_f32": [_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp],

@@ -95,7 +95,9 @@ int baorec_set_box(baorec_ctx* ctx, const float box_size[3], const float box_min
  *   "fuse_kspace" (default 1): with a fixed line of sight reconstructed_overdensity! folds the
  *       smoothing, normalisation and all n_iter iterations into ONE k-space pass between one
  *       R2C and one C2R (iterate! is linear and diagonal in k for a constant LOS); 0 = run the
- *       reference's sequence of iterate! calls (2 + 2 n_iter transforms). */
+ *       reference's sequence of iterate! calls (2 + 2 n_iter transforms).
+ *   "mg_slab_min_cells" (default 2097152): slab-decomposed multigrid levels with fewer cells are
+ *       replicated on every rank instead of exchanging halos. */
 int baorec_set_option(baorec_ctx* ctx, const char* name, int64_t value);
 /* Bytes of device scratch currently owned by the context. */
 int64_t baorec_scratch_bytes(const baorec_ctx* ctx);
@@ -140,16 +142,25 @@ int baorec_slab_owner_f32(baorec_ctx* ctx, const float* d_z, int64_t n, int32_t*
  * pack / tile-transpose kernels, grouped ncclSend/ncclRecv all-to-all, 1-D cuFFT along z. */
 int baorec_dist_r2c_f32(baorec_ctx* ctx, const float* d_slab, float* d_kslab_t, baorec_stream stream);
 int baorec_dist_c2r_f32(baorec_ctx* ctx, float* d_kslab_t /* destroyed */, float* d_slab, baorec_stream stream);
-/* run! (src/recon.jl:134-153) across the ranks: every rank passes the particles whose base plane
- * lies in its slab (baorec_slab_owner_f32) and receives its slab of the reconstructed mesh.
- * Scatter into slab + ghost plane, ghost sent to the next rank and added, distributed R2C, fused
- * k-space solve in the transposed layout (DC broadcast from rank 0), distributed C2R.  delta_k is
- * kept (transposed) for baorec_read_shifts_dist_f32.  This build distributes IterativeRecon with
- * a fixed line of sight and CIC; other modes return BAOREC_ERR_INVALID. */
+/* run! (src/recon.jl:134-180 box, :215-261 randoms) across the ranks: every rank passes the
+ * particles (data and, with has_randoms != 0, randoms) whose base plane lies in its slab
+ * (baorec_slab_owner_f32) and receives its slab of the result mesh (delta_r for BAOREC_ITERATIVE,
+ * phi for BAOREC_MULTIGRID).  The box is the plan's: with randoms the host side all-reduces
+ * setup_box (src/utils.jl:100-109) over the ranks before planning.
+ *   scatter into slab + ghost plane (sent to the next rank and added), distributed R2C, k-space
+ *   passes in the transposed layout (DC modes broadcast from rank 0), distributed C2R;
+ *   IterativeRecon, fixed LOS: all iterations in one k-space pass; radial LOS: iterate!
+ *   (src/iterative.jl:151-211) on slabs with 1 R2C + 6 C2R per iteration;
+ *   MultigridRecon: fmg (src/multigrid.jl:722-752) on slabs, one halo-plane exchange with both
+ *   ring neighbours after every Jacobi sweep / residual / prolongation; levels smaller than
+ *   option "mg_slab_min_cells" (default 2^21 cells) are all-gathered and solved on every rank.
+ * delta_k (phi_k) is kept, transposed, for baorec_read_shifts_dist_f32.  CIC only. */
 int baorec_run_dist_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, float* d_x, float* d_y, float* d_z,
-                        const float* d_w, int64_t n_local, float* d_mesh_slab, baorec_stream stream);
-/* read_shifts / reconstructed_positions (positions != 0) for this rank's particles: three
- * distributed C2R of i k delta_k / k^2, halo planes exchanged with both neighbours, gather. */
+                        const float* d_w, int64_t n_local, float* d_rx, float* d_ry, float* d_rz, const float* d_rw,
+                        int64_t n_ran_local, int has_randoms, float* d_mesh_slab, baorec_stream stream);
+/* read_shifts / reconstructed_positions (positions != 0) for this rank's particles against the
+ * result of the last baorec_run_dist_f32: three distributed C2R of i k delta_k / k^2 (i k phi_k
+ * for MultigridRecon), halo planes exchanged with both neighbours, gather. */
 int baorec_read_shifts_dist_f32(baorec_ctx* ctx, const baorec_params* p, const float* d_x, const float* d_y,
                                 const float* d_z, int64_t n_local, int field, int positions, float* d_sx,
                                 float* d_sy, float* d_sz, baorec_stream stream);

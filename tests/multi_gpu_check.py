@@ -24,6 +24,81 @@ import baorec_oracle as O  # noqa: E402
 from util import clustered_box, rel_rms, maxabs  # noqa: E402
 
 
+def more_modes(B, ctx, rank, world):
+    """MultigridRecon on slabs (halo exchange per sweep, slab restriction / prolongation, all-gathered
+    coarse levels), radial line of sight and the randoms set-up, all against the oracle."""
+    ok = True
+    n, L = 64, 1000.0
+    if n % (2 * world):
+        return ok
+
+    def put(a, mine):
+        return torch.from_numpy(np.ascontiguousarray(a[mine])).cuda()
+
+    def report(tag, e_mesh, e_rms, e_max):
+        good = e_mesh < 1e-4 and e_rms < 1e-4 and e_max < 1e-3
+        print(f"[rank {rank}/{world}] {tag}: mesh rel.rms={e_mesh:.2e} shift rel.rms={e_rms:.2e} "
+              f"max={e_max:.2e} {'OK' if good else 'FAIL'}", flush=True)
+        return good
+
+    # 1. MultigridRecon, periodic box, fixed and radial LOS; all levels on slabs / coarse levels replicated
+    for los, lo, min_cells in (((0.0, 0.0, 1.0), 0.0, 0), (None, 700.0, 16 ** 3), ((0.0, 1.0, 0.0), 0.0, 1 << 21)):
+        pos, w = clustered_box(200_000, L, seed=21, lo=lo)
+        kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=np.full(3, L, np.float32),
+                  box_min=np.full(3, lo, np.float32), los=los)
+        orec = O.MultigridRecon(**kw)
+        ophi = O.run(orec, (n, n, n), *[p.copy() for p in pos], w)
+        oshift = O.read_shifts(orec, *pos, ophi, "sum")
+        mine = B.dist.owner_of_z(pos[2], lo, L, n, world) == rank
+        d = [put(p, mine) for p in pos]
+        ctx.set_option("mg_slab_min_cells", min_cells)
+        rec = B.MultigridRecon(**kw)
+        phi = B.dist.run_dist(rec, (n, n, n), *d, put(w, mine), ctx=ctx)
+        z_lo, nzl = B.dist.slab_range(ctx)
+        s = B.dist.read_shifts_dist(rec, *d, field="sum")
+        ok &= report(f"multigrid box los={los} min_cells={min_cells}",
+                     rel_rms(phi.cpu().numpy(), ophi[z_lo:z_lo + nzl]),
+                     max(rel_rms(s[a].cpu().numpy(), oshift[a][mine]) for a in range(3)),
+                     max(maxabs(s[a].cpu().numpy(), oshift[a][mine]) for a in range(3)))
+    ctx.set_option("mg_slab_min_cells", 16 ** 3)
+
+    # 2. randoms set-up (box filled by the randoms: no cell on the ran > threshold discontinuity)
+    lo = 700.0
+    span = L * (1.0 - 2.0 / n)
+    dd, wd = clustered_box(60_000, span, seed=31, lo=lo)
+    rr, wr = clustered_box(600_000, span, seed=32, lo=lo, nclump=1, sigma=10.0)
+    md = B.dist.owner_of_z(dd[2], lo, L, n, world) == rank
+    mr = B.dist.owner_of_z(rr[2], lo, L, n, world) == rank
+    for algo in ("iterative", "multigrid"):
+        for los in (None, (0.0, 0.0, 1.0)):
+            kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=np.full(3, L, np.float32),
+                      box_min=np.full(3, lo, np.float32), los=los)
+            if algo == "iterative":
+                orec, rec = O.IterativeRecon(**kw), B.IterativeRecon(**kw)
+                omesh = O.reconstructed_overdensity(np.zeros((n, n, n), np.float32), orec, *dd, wd, *rr, wr)
+            else:
+                orec, rec = O.MultigridRecon(**kw), B.MultigridRecon(**kw)
+                omesh = O.reconstructed_potential(np.zeros((n, n, n), np.float32), orec, *dd, wd, *rr, wr)
+            oshift = O.read_shifts(orec, *dd, omesh, "sum")
+            gd = [put(p, md) for p in dd]
+            mesh = B.dist.run_dist(rec, (n, n, n), *gd, put(wd, md), *[put(p, mr) for p in rr], put(wr, mr), ctx=ctx)
+            z_lo, nzl = B.dist.slab_range(ctx)
+            g, o = mesh.cpu().numpy().astype(np.float64), omesh[z_lo:z_lo + nzl].astype(np.float64)
+            if algo == "multigrid":   # potential: defined up to a constant (global mean)
+                gm = torch.tensor([g.sum()], dtype=torch.float64, device="cuda")
+                dist.all_reduce(gm)
+                g, o = g - gm.item() / n ** 3, o - omesh.astype(np.float64).mean()
+                e_mesh = float(np.sqrt(np.mean((g - o) ** 2)) / (omesh.astype(np.float64) - omesh.astype(np.float64).mean()).std())
+            else:
+                e_mesh = rel_rms(g, o)
+            s = B.dist.read_shifts_dist(rec, *gd, field="sum")
+            ok &= report(f"{algo} randoms los={los}", e_mesh,
+                         max(rel_rms(s[a].cpu().numpy(), oshift[a][md]) for a in range(3)),
+                         max(maxabs(s[a].cpu().numpy(), oshift[a][md]) for a in range(3)))
+    ctx.set_option("mg_slab_min_cells", 1 << 21)
+    return ok
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -59,6 +134,7 @@ def main():
         print(f"[rank {rank}/{world}] n={n} los={los} particles={int(mine.sum())} slab=[{z_lo},{z_lo + nzl}) "
               f"mesh rel.rms={e_mesh:.2e} shift rel.rms={e_rms:.2e} max={e_max:.2e} {'OK' if good else 'FAIL'}",
               flush=True)
+    ok &= more_modes(B, ctx, rank, world)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

@@ -50,6 +50,7 @@ def test_shard_catalog_partitions_everything(B):
 def _worker(rank, world, port, q):
     try:
         sys.path.insert(0, str(ROOT))
+        sys.path.insert(0, str(ROOT / "oracle"))
         import torch
         import torch.distributed as dist
         import __graft_entry__ as G
@@ -72,6 +73,15 @@ def _worker(rank, world, port, q):
         expect = sum(float((np.arange(3000 + 500 * r) + 10000 * r).sum()) for r in range(world))
         ok = bool((own == rank).all()) and int(total) == sum(3000 + 500 * r for r in range(world)) \
             and abs(float(chk) - expect) < 1e-3 and len(x) == len(y) == len(z) == len(w)
+        # setup_box over the ranks == setup_box of the concatenated catalog (src/utils.jl:100-109)
+        import baorec_oracle as O
+        rngs = [np.random.default_rng(100 + r) for r in range(world)]
+        allc = [[(g.random(3000 + 500 * r) * L).astype(np.float32) for _ in range(3)] for r, g in enumerate(rngs)]
+        full = [np.concatenate([allc[r][a] for r in range(world)]) for a in range(3)]
+        obs, obm = O.setup_box(*full, np.float32(500))
+        gbs, gbm = B.dist.setup_box_dist(*cols, 500.0)
+        ok = ok and np.array_equal(obs.view(np.uint32), gbs.view(np.uint32)) \
+            and np.array_equal(obm.view(np.uint32), gbm.view(np.uint32))
         dist.destroy_process_group()
         q.put((rank, ok, ""))
     except Exception as e:  # pragma: no cover

@@ -83,6 +83,78 @@ def test_run_dist_rejects_unsupported_modes(B, dctx):
     n, L = 32, 100.0
     e = torch.zeros(4, dtype=torch.float32, device="cuda") + 5
     rec = B.IterativeRecon(bias=2.0, f=0.5, smoothing_radius=5.0, box_size=np.full(3, L, np.float32),
-                           box_min=np.zeros(3, np.float32), los=None)
+                           box_min=np.zeros(3, np.float32), los=(0.0, 0.0, 1.0), mas="tsc")
     with pytest.raises(B.BaorecError):
         B.dist.run_dist(rec, (n, n, n), e, e, e, e, ctx=dctx)
+
+
+def filled_box(n_data, n_rand, L, lo, n, seed):
+    """Data (clumpy) and randoms (uniform) covering the whole box except its last two cells per axis
+    (the scatter without wrap rejects the last cell, src/mas.jl:33-35): the smoothed randoms density
+    stays far above the ran_min threshold everywhere, so no cell sits on the `ran > threshold`
+    discontinuity and the comparison with the oracle is clean."""
+    span = L * (1.0 - 2.0 / n)
+    d, wd = clustered_box(n_data, span, seed=seed, lo=lo)
+    r, wr = clustered_box(n_rand, span, seed=seed + 1, lo=lo, nclump=1, sigma=10.0)   # ~uniform
+    return d, wd, r, wr
+
+
+@pytest.mark.parametrize("min_cells", [0, 16 ** 3])
+@pytest.mark.parametrize("los,lo", [((0.0, 0.0, 1.0), 0.0), (None, 700.0)])
+def test_multigrid_dist_box(B, O, dctx, min_cells, los, lo):
+    """MultigridRecon on slabs (halo planes, slab restriction / prolongation, replicated coarse
+    levels below `mg_slab_min_cells`) against the oracle."""
+    n, L, N = 64, 1000.0, 200_000
+    pos, w = clustered_box(N, L, seed=21, lo=lo)
+    kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=np.full(3, L, np.float32),
+              box_min=np.full(3, lo, np.float32), los=los)
+    orec = O.MultigridRecon(**kw)
+    opos = [p.copy() for p in pos]
+    ophi = O.run(orec, (n, n, n), *opos, w)
+    dctx.set_option("mg_slab_min_cells", min_cells)
+    try:
+        rec = B.MultigridRecon(**kw)
+        d = [dev(p) for p in pos]
+        phi = B.dist.run_dist(rec, (n, n, n), *d, dev(w), ctx=dctx)
+        assert rel_rms(phi.cpu().numpy(), ophi) < 1e-4
+        for f in ("disp", "sum"):
+            s = B.dist.read_shifts_dist(rec, *d, field=f)
+            ref = O.read_shifts(orec, *opos, ophi, f)
+            for a in range(3):
+                assert rel_rms(s[a].cpu().numpy(), ref[a]) < 1e-4
+                assert maxabs(s[a].cpu().numpy(), ref[a]) < 1e-3
+    finally:
+        dctx.set_option("mg_slab_min_cells", 1 << 21)
+
+
+@pytest.mark.parametrize("algo", ["iterative", "multigrid"])
+@pytest.mark.parametrize("los,lo", [(None, 700.0), ((0.0, 0.0, 1.0), 700.0)])
+def test_run_dist_with_randoms(B, O, dctx, algo, los, lo):
+    """Randoms set-up (two smoothed meshes, DC sums, global randoms count, threshold) on slabs;
+    IterativeRecon radial LOS = iterate! on slabs, fixed LOS = fused pass on delta_s."""
+    n, L = 64, 1000.0
+    d, wd, r, wr = filled_box(60_000, 600_000, L, lo, n, seed=31)
+    kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=np.full(3, L, np.float32),
+              box_min=np.full(3, lo, np.float32), los=los)
+    if algo == "iterative":
+        orec, rec = O.IterativeRecon(**kw), B.IterativeRecon(**kw)
+        omesh = O.reconstructed_overdensity(np.zeros((n, n, n), np.float32), orec, *d, wd, *r, wr)
+    else:
+        orec, rec = O.MultigridRecon(**kw), B.MultigridRecon(**kw)
+        omesh = O.reconstructed_potential(np.zeros((n, n, n), np.float32), orec, *d, wd, *r, wr)
+    gd, gr = [dev(p) for p in d], [dev(p) for p in r]
+    dctx.set_option("mg_slab_min_cells", 16 ** 3)
+    try:
+        mesh = B.dist.run_dist(rec, (n, n, n), *gd, dev(wd), *gr, dev(wr), ctx=dctx)
+    finally:
+        dctx.set_option("mg_slab_min_cells", 1 << 21)
+    g = mesh.cpu().numpy()
+    if algo == "multigrid":   # the potential is defined up to a constant
+        assert rel_rms(g - g.mean(), omesh - omesh.mean()) < 1e-4
+    else:
+        assert rel_rms(g, omesh) < 1e-4
+    s = B.dist.read_shifts_dist(rec, *gd, field="sum")
+    ref = O.read_shifts(orec, *d, omesh, "sum")
+    for a in range(3):
+        assert rel_rms(s[a].cpu().numpy(), ref[a]) < 1e-4
+        assert maxabs(s[a].cpu().numpy(), ref[a]) < 1e-3

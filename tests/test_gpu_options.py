@@ -19,7 +19,8 @@ def dev(a):
 @contextlib.contextmanager
 def options(B, **kw):
     ctx = B.Context.get(0)
-    defaults = {"bin_min_particles": 1 << 18, "fuse_kspace": 1, "own_fft": 0, "gather_tiles": 1}
+    defaults = {"bin_min_particles": 1 << 18, "fuse_kspace": 1, "own_fft": 0, "gather_tiles": 1,
+                "fft_split_planes": 0}
     try:
         for k, v in kw.items():
             ctx.set_option(k, v)
@@ -100,6 +101,8 @@ def test_binned_tsc_scatter(B, O):
 
 @pytest.mark.parametrize("opts", [dict(bin_min_particles=0, fuse_kspace=1), dict(bin_min_particles=0, fuse_kspace=0),
                                   dict(bin_min_particles=0, fuse_kspace=1, own_fft=1),
+                                  dict(bin_min_particles=0, fuse_kspace=1, fft_split_planes=8),
+                                  dict(bin_min_particles=0, fuse_kspace=0, fft_split_planes=24),
                                   dict(bin_min_particles=0, fuse_kspace=0, own_fft=1, gather_tiles=0),
                                   dict(bin_min_particles=1 << 40, fuse_kspace=0),
                                   dict(bin_min_particles=1 << 40, fuse_kspace=1)])
