@@ -29,12 +29,24 @@ static int check_catalog(int64_t n, const void* x, const void* y, const void* z,
 // Displacement meshes of `mesh` into RX/RY/RZ, then the fused gather + read_shifts epilogue.
 static int read_common(baorec_ctx* ctx, const baorec_params* p, int algorithm, const float* mesh, const float* x,
                        const float* y, const float* z, int64_t n, int field, int positions, float* ox, float* oy,
-                       float* oz, cudaStream_t st, bool use_kcache = false) {
+                       float* oz, cudaStream_t st, bool use_kcache = false, bool trusted = false) {
   float *px, *py, *pz;
   BR_TRY(need_t(ctx, BUF_RX, ctx->M, &px));
   BR_TRY(need_t(ctx, BUF_RY, ctx->M, &py));
   BR_TRY(need_t(ctx, BUF_RZ, ctx->M, &pz));
-  BR_TRY(displacement_meshes(ctx, mesh, algorithm, px, py, pz, st, use_kcache));
+  // `trusted`: the caller asserts that `mesh` is the unmodified cached result, so displacement
+  // meshes computed from it by an earlier call are still its displacement meshes
+  const bool reuse = trusted && ctx->disp_valid && ctx->disp_algo == algorithm && ctx->disp_mesh == mesh &&
+                     !own_fft_available(ctx);
+  if (!reuse) {
+    ctx->disp_valid = false;
+    BR_TRY(displacement_meshes(ctx, mesh, algorithm, px, py, pz, st, use_kcache));
+    if (trusted) {
+      ctx->disp_valid = true;
+      ctx->disp_algo = algorithm;
+      ctx->disp_mesh = mesh;
+    }
+  }
   BR_CUDA(cudaEventRecord(ctx->ev[5], st));
   BR_TRY(reset_oob(ctx, st));
   BR_TRY(gather3(ctx, px, py, pz, x, y, z, n, ox, oy, oz, p->mas, field, p->f, p->has_los, p->los, positions, st));
@@ -141,8 +153,10 @@ int baorec_read_result_cache_f32(baorec_ctx* ctx, const baorec_params* p, int al
   BR_REQUIRE(field >= BAOREC_FIELD_DISP && field <= BAOREC_FIELD_SUM, "unknown field");
   BR_REQUIRE(n >= 0 && (n == 0 || (d_x && d_y && d_z && d_ox && d_oy && d_oz)), "particle arrays");
   const bool hit = ctx->kcache_valid && ctx->kcache_mesh == d_mesh && algorithm == BAOREC_ITERATIVE;
+  // MultigridRecon keeps no phi_k, but the displacement meshes of the asserted-unmodified mesh are reusable
+  const bool trusted = hit || (algorithm == BAOREC_MULTIGRID && ctx->mg_result_mesh == d_mesh);
   return read_common(ctx, p, algorithm, d_mesh, d_x, d_y, d_z, n, field, positions, d_ox, d_oy, d_oz,
-                     (cudaStream_t)stream, hit);
+                     (cudaStream_t)stream, hit, trusted);
 }
 
 int baorec_reconstructed_positions_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, const float* d_mesh,
@@ -167,6 +181,8 @@ int baorec_set_option(baorec_ctx* ctx, const char* name, int64_t value) {
   else if (s == "gather_tiles") ctx->opt_gather_tiles = (int)value;
   else if (s == "bin_zg_scatter") ctx->opt_zg_scatter = (int)value;
   else if (s == "bin_zg_gather") ctx->opt_zg_gather = (int)value;
+  else if (s == "mg_kernel") ctx->opt_mg_kernel = (int)value;
+  else if (s == "mg_ring") ctx->opt_mg_ring = (int)value;
   else if (s == "mg_slab_min_cells") {
     ctx->opt_mg_slab_min_cells = value;
     ctx->dlevels.clear();
@@ -191,6 +207,7 @@ int baorec_run_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, 
   cudaStream_t st = ctx->own_stream;
   ctx->cache_valid = false;
   ctx->kcache_valid = false;
+  ctx->disp_valid = false;
   float *dp, *dr = nullptr, *mesh;
   BR_TRY(need_t(ctx, BUF_PART, (size_t)(n > 0 ? n : 1) * 4, &dp));
   if (n_ran > 0) BR_TRY(need_t(ctx, BUF_PART2, (size_t)n_ran * 4, &dr));
@@ -259,6 +276,7 @@ int baorec_read_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm,
     BR_CUDA(cudaMemcpyAsync(mesh, h_mesh_or_null, ctx->M * sizeof(float), cudaMemcpyHostToDevice, st));
     ctx->cache_valid = true;
     ctx->kcache_valid = false;
+    ctx->disp_valid = false;
   }
   if (!ctx->cache_valid) {
     set_error("baorec_read_host_f32: no cached result mesh (call baorec_run_host_f32 first or pass a mesh)");
@@ -279,7 +297,14 @@ int baorec_read_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm,
     BR_TRY(need_t(ctx, BUF_RX, ctx->M, &px));
     BR_TRY(need_t(ctx, BUF_RY, ctx->M, &py));
     BR_TRY(need_t(ctx, BUF_RZ, ctx->M, &pz));
-    BR_TRY(displacement_meshes(ctx, mesh, algorithm, px, py, pz, st, /*use_kcache=*/true));
+    // the cached mesh is library-owned: displacement meshes of an earlier read are still valid
+    if (!(ctx->disp_valid && ctx->disp_algo == algorithm && ctx->disp_mesh == mesh && !own_fft_available(ctx))) {
+      ctx->disp_valid = false;
+      BR_TRY(displacement_meshes(ctx, mesh, algorithm, px, py, pz, st, /*use_kcache=*/true));
+      ctx->disp_valid = true;
+      ctx->disp_algo = algorithm;
+      ctx->disp_mesh = mesh;
+    }
     BR_CUDA(cudaEventRecord(ctx->ev[5], st));
     BR_CUDA(cudaStreamWaitEvent(st, ctx->ev_copy, 0));
     BR_TRY(reset_oob(ctx, st));

@@ -43,6 +43,7 @@ void prof_end(baorec_ctx* ctx, int idx, cudaStream_t st) {
 int need(baorec_ctx* ctx, BufId id, size_t bytes, void** out) {
   Buf& b = ctx->bufs[id];
   if (b.bytes < bytes) {
+    if (id == BUF_RX || id == BUF_RY || id == BUF_RZ) ctx->disp_valid = false;
     if (b.p) {
       BR_CUDA(cudaFree(b.p));
       b.p = nullptr;
@@ -226,7 +227,36 @@ void host_xvec(int n, float L, float mn, std::vector<float>& out) {
   for (int i = 0; i < n; i++) out[i] = (float)(start + (double)i * (double)cell);
 }
 
+int gauss_tables(baorec_ctx* ctx, float R, const double** gx, const double** gy, const double** gz, cudaStream_t st) {
+  const int len[3] = {ctx->xh, ctx->ny, ctx->nz};
+  const int n[3] = {ctx->nx, ctx->ny, ctx->nz};
+  if (!ctx->d_gauss) BR_CUDA(cudaMalloc(&ctx->d_gauss, sizeof(double) * (size_t)(len[0] + len[1] + len[2])));
+  if (!ctx->gauss_valid || ctx->gauss_R != R) {
+    const float R2 = R * R;  // T(R)^2 in Float32, promoted (src/utils.jl:52)
+    std::vector<double> h;
+    h.reserve((size_t)len[0] + len[1] + len[2]);
+    for (int a = 0; a < 3; a++) {
+      std::vector<float> k;
+      host_kvec(n[a], ctx->L[a], a == 0, k);
+      for (int i = 0; i < len[a]; i++) {
+        const float k2 = k[i] * k[i];
+        h.push_back(exp(-0.5 * (double)R2 * (double)k2));
+      }
+    }
+    // earlier passes on `st` may still read the old tables: the copy is ordered after them
+    BR_CUDA(cudaMemcpyAsync(ctx->d_gauss, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    BR_CUDA(cudaStreamSynchronize(st));  // h is pageable and local
+    ctx->gauss_R = R;
+    ctx->gauss_valid = true;
+  }
+  *gx = ctx->d_gauss;
+  *gy = ctx->d_gauss + len[0];
+  *gz = ctx->d_gauss + len[0] + len[1];
+  return BAOREC_OK;
+}
+
 static int upload_tables(baorec_ctx* ctx) {
+  ctx->gauss_valid = false;
   int n[3] = {ctx->nx, ctx->ny, ctx->nz};
   for (int a = 0; a < 3; a++) {
     std::vector<float> k, x;
@@ -278,6 +308,9 @@ int plan_common(baorec_ctx* ctx, int nx, int ny, int nz, const float L[3], const
     }
     ctx->levels.clear();
     ctx->dlevels.clear();
+    if (ctx->d_gauss) cudaFree(ctx->d_gauss);
+    ctx->d_gauss = nullptr;
+    ctx->gauss_valid = false;
     ctx->nx = nx;
     ctx->ny = ny;
     ctx->nz = nz;
@@ -292,6 +325,8 @@ int plan_common(baorec_ctx* ctx, int nx, int ny, int nz, const float L[3], const
     ctx->cache_valid = false;
   }
   ctx->kcache_valid = false;
+  ctx->disp_valid = false;
+  ctx->mg_result_mesh = nullptr;
   for (int a = 0; a < 3; a++) {
     ctx->L[a] = L[a];
     ctx->mn[a] = mn[a];
@@ -344,6 +379,7 @@ int baorec_destroy(baorec_ctx* ctx) {
   }
   for (int a = 0; a < 2; a++)
     if (ctx->d_tw[a]) cudaFree(ctx->d_tw[a]);
+  if (ctx->d_gauss) cudaFree(ctx->d_gauss);
   if (ctx->d_oob) cudaFree(ctx->d_oob);
   if (ctx->d_scal) cudaFree(ctx->d_scal);
   if (ctx->d_minmax) cudaFree(ctx->d_minmax);
@@ -409,6 +445,7 @@ int baorec_set_box(baorec_ctx* ctx, const float box_size[3], const float box_min
   BR_REQUIRE(box_size[0] > 0 && box_size[1] > 0 && box_size[2] > 0, "box_size must be positive");
   BR_CUDA(cudaSetDevice(ctx->device));
   BR_CUDA(cudaDeviceSynchronize());
+  ctx->disp_valid = false;
   for (int a = 0; a < 3; a++) {
     ctx->L[a] = box_size[a];
     ctx->mn[a] = box_min[a];

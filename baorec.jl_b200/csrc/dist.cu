@@ -605,6 +605,7 @@ int baorec_run_dist_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, 
   const float* los = p->has_los ? p->los : nullptr;
   ctx->kcache_valid = false;
   ctx->kcache_potential = false;
+  ctx->disp_valid = false;
   BR_TRY(reset_oob(ctx, st));
   DistBufs b;
   BR_TRY(dist_bufs(ctx, &b));
@@ -709,7 +710,10 @@ int baorec_read_shifts_dist_f32(baorec_ctx* ctx, const baorec_params* p, const f
   BR_TRY(need_t(ctx, BUF_RX, (size_t)(nzl + 3) * plane, &psi[0]));
   BR_TRY(need_t(ctx, BUF_RY, (size_t)(nzl + 3) * plane, &psi[1]));
   BR_TRY(need_t(ctx, BUF_RZ, (size_t)(nzl + 3) * plane, &psi[2]));
-  for (int c = 0; c < 3; c++) {
+  // the displacement slabs (+ halos) of the last run are kept across calls (data, then randoms, ...)
+  const bool reuse = ctx->disp_valid && ctx->disp_algo == -1;
+  ctx->disp_valid = false;
+  for (int c = 0; c < 3 && !reuse; c++) {
     BR_TRY(kpass_disp_T(ctx, keep, b.T, c, ctx->kcache_potential, st));
     BR_TRY(dist_c2r(ctx, b.T, psi[c] + plane, st));  // own planes at local index 1 .. nzl
     // halo: plane 0 <- previous rank's last plane; planes nzl+1, nzl+2 <- next rank's first two
@@ -722,6 +726,8 @@ int baorec_read_shifts_dist_f32(baorec_ctx* ctx, const baorec_params* p, const f
                   p->has_los, p->los, positions, st);
   ctx->slab_mode = 0;
   if (s != BAOREC_OK) return s;
+  ctx->disp_valid = true;
+  ctx->disp_algo = -1;  // marks slab-layout displacement meshes
   return check_oob(ctx, st, "read_shifts_dist (particles must lie in this rank's slab)");
 }
 

@@ -138,6 +138,10 @@ struct baorec_ctx {
   size_t work_bytes = 0;
   float* d_k[3] = {nullptr, nullptr, nullptr};  // k tables (xh, ny, nz)
   float* d_xv[3] = {nullptr, nullptr, nullptr}; // cell-centre tables (nx, ny, nz)
+  // per-axis Gaussian factors exp(-0.5 R^2 k_a^2) in Float64 (xh + ny + nz doubles) for radius gauss_R
+  double* d_gauss = nullptr;
+  float gauss_R = 0.f;
+  bool gauss_valid = false;
   baorec::Buf bufs[baorec::BUF_COUNT];
   unsigned long long* d_oob = nullptr;  // out-of-box particle counter
   double* d_scal = nullptr;             // small device scalars (DC modes, sums)
@@ -166,6 +170,8 @@ struct baorec_ctx {
   // multigrid
   std::vector<baorec::MgLevel> levels;
   std::vector<baorec::MgLevel> dlevels;  // slab-decomposed hierarchy (baorec_plan_dist)
+  int opt_mg_ring = 6;    // planes in the staged kernel's shared-memory ring (3 or 6)
+  int opt_mg_kernel = 0;  // 0: staged shared-memory kernel where it applies; 1: register march; 2: generic
   int64_t opt_mg_slab_min_cells = 1 << 21;  // levels with fewer cells are replicated, not slab-decomposed
   bool mg_radial_tables = false;
   // distributed
@@ -179,6 +185,13 @@ struct baorec_ctx {
   float2* own_recv[2] = {nullptr, nullptr};
   int a2a_parity = 0;
   int* d_barrier = nullptr;
+  // displacement meshes (BUF_RX/RY/RZ) of the cached result, kept across read_shifts /
+  // reconstructed_positions calls (the examples read data, randoms-sym and randoms-iso back from
+  // one reconstruction: examples/simulation.jl:32-35) so that only the first call pays for the transforms
+  bool disp_valid = false;
+  int disp_algo = 0;
+  const float* disp_mesh = nullptr;
+  const float* mg_result_mesh = nullptr;  // phi produced by the last reconstructed_potential! on this context
   bool kcache_potential = false;  // BUF_CKCACHE holds phi_k (MultigridRecon) instead of delta_k
   int slab_mode = 0;  // 0: whole mesh; 1: scatter into a slab (+1 ghost plane); 2: gather from a slab (+3 halo planes)
   cufftHandle p2d_r2c = 0, p2d_c2r = 0, p1d = 0;
@@ -232,6 +245,8 @@ int reconstructed_overdensity(baorec_ctx* ctx, const baorec_params* p, float* me
 int setup_box_dev(baorec_ctx* ctx, const float* x, const float* y, const float* z, int64_t n, float pad,
                   float L_out[3], float mn_out[3], cudaStream_t st);
 // ctx.cu
+// device tables of the separable Gaussian for smoothing radius R (rebuilt when R or the box changes)
+int gauss_tables(baorec_ctx* ctx, float R, const double** gx, const double** gy, const double** gz, cudaStream_t st);
 int plan_common(baorec_ctx* ctx, int nx, int ny, int nz, const float L[3], const float mn[3]);
 void host_xvec(int n, float L, float mn, std::vector<float>& out);
 

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(KS_THREADS) kspace_kernel(KGeom g, const float
     if (p < plane) {
       unsigned iy = p / (unsigned)g.xh;
       unsigned ix = p - iy * (unsigned)g.xh;
-      op.apply(off + p, v[u], __ldg(g.kx + ix), __ldg(g.ky + iy), kz, (ix | iy | (unsigned)iz) == 0u);
+      op.apply(off + p, v[u], __ldg(g.kx + ix), __ldg(g.ky + iy), kz, (ix | iy | (unsigned)iz) == 0u, (int)ix, (int)iy, iz);
     }
   }
 }
@@ -59,16 +59,26 @@ __device__ __forceinline__ float ksq(float kx, float ky, float kz) {
   return __fadd_rn(__fadd_rn(__fmul_rn(kx, kx), __fmul_rn(ky, ky)), __fmul_rn(kz, kz));
 }
 
-// exp(-0.5 R² k²) evaluated in Float64 like the reference (src/utils.jl:52, 81).
-__device__ __forceinline__ double gauss64(float R2, float k2) { return exp(-0.5 * (double)R2 * (double)k2); }
+// exp(-0.5 R² k²) in Float64 like the reference (src/utils.jl:52, 81), as the product of three
+// per-axis factors exp(-0.5 R² k_a²) tabulated in Float64 at plan time (gauss_tables): the Float64
+// `exp` per mode made the pass compute-bound.  k_a² is the Float32 square the reference forms; only
+// the two Float32 roundings of its k² sum are not reproduced (<= 1.2e-7 relative in the exponent).
+struct GaussTab {
+  const double* gx;
+  const double* gy;
+  const double* gz;
+  __device__ __forceinline__ double at(int ix, int iy, int iz) const {
+    return __ldg(gx + ix) * __ldg(gy + iy) * __ldg(gz + iz);
+  }
+};
 
 struct GaussOp {
   static const char* name() { return "kspace_kernel<GaussOp>"; }  // smooth!: field_k *= exp(-0.5 R² k²), then /M
   float2* out;
-  float R2;
+  GaussTab gt;
   double invM;
-  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool) const {
-    double s = gauss64(R2, ksq(kx, ky, kz)) * invM;
+  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool, int ix, int iy, int iz) const {
+    double s = gt.at(ix, iy, iz) * invM;
     out[idx] = make_float2((float)((double)v.x * s), (float)((double)v.y * s));
   }
 };
@@ -76,11 +86,11 @@ struct GaussOp {
 struct SetupBoxOp {
   static const char* name() { return "kspace_kernel<SetupBoxOp>"; }  // smooth + (rho/mean - 1)/bias in k-space: delta_k = rho_k g /(A0 bias), DC -> 0
   float2* out;
-  float R2;
+  GaussTab gt;
   float bias;
   const double* dc;  // Re A_k[0] = sum(rho)
-  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool is_dc) const {
-    double s = gauss64(R2, ksq(kx, ky, kz)) * __ldg(dc + 8);  // dc[8] = 1 / (A0 bias)
+  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool is_dc, int ix, int iy, int iz) const {
+    double s = gt.at(ix, iy, iz) * __ldg(dc + 8);  // dc[8] = 1 / (A0 bias)
     if (is_dc) s = 0.0;
     out[idx] = make_float2((float)((double)v.x * s), (float)((double)v.y * s));
   }
@@ -91,7 +101,7 @@ struct IterLosOp {
   float2* out;
   float los[3];
   float invM;
-  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool) const {
+  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool, int, int, int) const {
     float k2 = ksq(kx, ky, kz);
     float c = __fmul_rn(__fmul_rn(kx, kx), los[0]);
     c = __fadd_rn(c, __fmul_rn(__fmul_rn(ky, ky), los[1]));
@@ -110,7 +120,7 @@ struct IterPairOp {
   float2* out;
   int i, j;
   float invM;
-  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool) const {
+  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool, int, int, int) const {
     float k2 = ksq(kx, ky, kz);
     float ki = i == 0 ? kx : (i == 1 ? ky : kz);
     float kj = j == 0 ? kx : (j == 1 ? ky : kz);
@@ -135,18 +145,19 @@ struct FusedLosOp {
   static const char* name() { return MODE == 0 ? "kspace_kernel<FusedLosOp<rho>>" : "kspace_kernel<FusedLosOp<delta>>"; }
   float2* out_c2r;   // delta_final_k / M  (input of the C2R)
   float2* out_keep;  // delta_final_k (unnormalised), or nullptr
-  float R2, bias;
+  GaussTab gt;
+  float bias;
   const double* dc;
   float los[3];
   float beta;
   int n_iter;
   float invM;
-  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool is_dc) const {
+  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool is_dc, int ix, int iy, int iz) const {
     float k2 = ksq(kx, ky, kz);
     float dsx, dsy;
     if (MODE == 0) {
       // delta_k (unnormalised R2C convention) = rho_k g M / (A0 bias): mean(rho) = A0 / M
-      double s = gauss64(R2, k2) * __ldg(dc + 8);  // dc[8] = M / (A0 bias)
+      double s = gt.at(ix, iy, iz) * __ldg(dc + 8);  // dc[8] = M / (A0 bias)
       if (is_dc) s = 0.0;
       dsx = (float)((double)v.x * s);
       dsy = (float)((double)v.y * s);
@@ -181,7 +192,7 @@ struct DispOp {
   float2* o1;
   float2* o2;
   float invM;
-  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool) const {
+  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool, int, int, int) const {
     float s;
     if (POTENTIAL) {
       s = invM;
@@ -201,6 +212,10 @@ __global__ void stash_dc_kernel(const float2* __restrict__ ck, double* scal, int
   double a0 = (double)ck[0].x;
   scal[slot] = a0;
   scal[slot + 8] = mul / a0;
+}
+
+static int gauss_tab(baorec_ctx* ctx, float R, GaussTab* t, cudaStream_t st) {
+  return gauss_tables(ctx, R, &t->gx, &t->gy, &t->gz, st);
 }
 
 template <class Op>
@@ -293,7 +308,9 @@ int smooth(baorec_ctx* ctx, float* mesh, float R, cudaStream_t st) {
   float2* ck0;
   BR_TRY(need_t(ctx, BUF_CK0, ctx->Mc, &ck0));
   BR_TRY(fft_r2c(ctx, mesh, ck0, st));
-  GaussOp op{ck0, R * R, 1.0 / (double)ctx->M};
+  GaussTab gt;
+  BR_TRY(gauss_tab(ctx, R, &gt, st));
+  GaussOp op{ck0, gt, 1.0 / (double)ctx->M};
   BR_TRY(run_kspace(ctx, ck0, op, st));
   BR_TRY(fft_c2r(ctx, ck0, mesh, st));
   return BAOREC_OK;
@@ -306,13 +323,14 @@ int setup_overdensity_into(baorec_ctx* ctx, const baorec_params* p, float* mesh,
                            int64_t nr, int wrap, cudaStream_t st) {
   float2* ck0;
   BR_TRY(need_t(ctx, BUF_CK0, ctx->Mc, &ck0));
-  const float R2 = p->smoothing_radius * p->smoothing_radius;
+  GaussTab gt;
+  BR_TRY(gauss_tab(ctx, p->smoothing_radius, &gt, st));
   BR_TRY(reset_oob(ctx, st));
   if (nr == 0) {
     BR_TRY(scatter(ctx, mesh, x, y, z, w, n, wrap, p->mas, st));
     BR_TRY(fft_r2c(ctx, mesh, ck0, st));
     BR_LAUNCH(ctx, stash_dc_kernel, 1, 1, 0, st, ck0, ctx->d_scal, 0, 1.0 / (double)p->bias);
-    SetupBoxOp op{ck0, R2, p->bias, ctx->d_scal};
+    SetupBoxOp op{ck0, gt, p->bias, ctx->d_scal};
     BR_TRY(run_kspace(ctx, ck0, op, st));
     BR_TRY(fft_c2r(ctx, ck0, delta_out, st));
   } else {
@@ -321,7 +339,7 @@ int setup_overdensity_into(baorec_ctx* ctx, const baorec_params* p, float* mesh,
     BR_CUDA(cudaMemsetAsync(ran, 0, ctx->M * sizeof(float), st));
     BR_TRY(scatter(ctx, mesh, x, y, z, w, n, 0, p->mas, st));
     BR_TRY(scatter(ctx, ran, rx, ry, rz, rw, nr, 0, p->mas, st));
-    GaussOp op{ck0, R2, 1.0 / (double)ctx->M};
+    GaussOp op{ck0, gt, 1.0 / (double)ctx->M};
     BR_TRY(fft_r2c(ctx, mesh, ck0, st));
     BR_LAUNCH(ctx, stash_dc_kernel, 1, 1, 0, st, ck0, ctx->d_scal, 0, 1.0);
     BR_TRY(run_kspace(ctx, ck0, op, st));
@@ -351,6 +369,7 @@ static int iterate_impl(baorec_ctx* ctx, const float* fft_src, float* delta_r, c
   float* X;
   BR_TRY(need_t(ctx, BUF_CK0, ctx->Mc, &ck0));
   BR_TRY(need_t(ctx, BUF_RX, ctx->M, &X));
+  ctx->disp_valid = false;
   const float invM = (float)(1.0 / (double)ctx->M);
   BR_TRY(fft_r2c(ctx, fft_src, ck0, st));
   if (los) {
@@ -421,6 +440,8 @@ int reconstructed_overdensity(baorec_ctx* ctx, const baorec_params* p, float* me
                               const float* w, int64_t n, float* rx, float* ry, float* rz, const float* rw, int64_t nr,
                               cudaStream_t st) {
   ctx->kcache_valid = false;
+  ctx->disp_valid = false;
+  ctx->mg_result_mesh = nullptr;
   const float* los = p->has_los ? p->los : nullptr;
   const float invM = (float)(1.0 / (double)ctx->M);
   if (los && ctx->opt_fuse_kspace) {
@@ -441,7 +462,9 @@ int reconstructed_overdensity(baorec_ctx* ctx, const baorec_params* p, float* me
       BR_TRY(scatter(ctx, mesh, x, y, z, w, n, 1, p->mas, st));
       BR_TRY(fft_r2c(ctx, mesh, ck0, st));
       BR_LAUNCH(ctx, stash_dc_kernel, 1, 1, 0, st, ck0, ctx->d_scal, 0, (double)ctx->M / (double)p->bias);
-      FusedLosOp<0> op{ck0, keep, p->smoothing_radius * p->smoothing_radius, p->bias, ctx->d_scal,
+      GaussTab gt;
+      BR_TRY(gauss_tab(ctx, p->smoothing_radius, &gt, st));
+      FusedLosOp<0> op{ck0, keep, gt, p->bias, ctx->d_scal,
                        {los[0], los[1], los[2]}, p->beta, p->n_iter, invM};
       BR_TRY(run_kspace(ctx, ck0, op, st));
       BR_TRY(fft_c2r(ctx, ck0, mesh, st));
@@ -451,7 +474,7 @@ int reconstructed_overdensity(baorec_ctx* ctx, const baorec_params* p, float* me
       BR_TRY(need_t(ctx, BUF_RS, ctx->M, &ds));
       BR_TRY(setup_overdensity_into(ctx, p, mesh, ds, x, y, z, w, n, rx, ry, rz, rw, nr, 0, st));
       BR_TRY(fft_r2c(ctx, ds, ck0, st));
-      FusedLosOp<1> op{ck0, keep, 0.f, p->bias, ctx->d_scal, {los[0], los[1], los[2]}, p->beta, p->n_iter, invM};
+      FusedLosOp<1> op{ck0, keep, GaussTab{}, p->bias, ctx->d_scal, {los[0], los[1], los[2]}, p->beta, p->n_iter, invM};
       BR_TRY(run_kspace(ctx, ck0, op, st));
       BR_TRY(fft_c2r(ctx, ck0, mesh, st));
     }
@@ -495,7 +518,7 @@ kspace_kernel_t(KGeom g, int y0, const float2* __restrict__ in, Op op) {
     if (p < plane) {
       unsigned ix = p / (unsigned)g.nz;
       unsigned iz = p - ix * (unsigned)g.nz;
-      op.apply(off + p, v[u], __ldg(g.kx + ix), ky, __ldg(g.kz + iz), (ix | (unsigned)(y0 + yl) | iz) == 0u);
+      op.apply(off + p, v[u], __ldg(g.kx + ix), ky, __ldg(g.kz + iz), (ix | (unsigned)(y0 + yl) | iz) == 0u, (int)ix, y0 + yl, (int)iz);
     }
   }
 }
@@ -514,7 +537,7 @@ struct DispCompOp {  // one component of Psi = i k delta_k / k^2 (src/iterative.
   float2* out;
   int comp;
   float invM;
-  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool) const {
+  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool, int, int, int) const {
     float s;
     if (POTENTIAL) {
       s = invM;
@@ -535,7 +558,9 @@ int stash_dc(baorec_ctx* ctx, const float2* ck, int slot, double mul, cudaStream
 int kpass_fused_T(baorec_ctx* ctx, const float2* in, float2* out_c2r, float2* keep, const baorec_params* p,
                   cudaStream_t st) {
   const float invM = (float)(1.0 / (double)ctx->M);
-  FusedLosOp<0> op{out_c2r, keep, p->smoothing_radius * p->smoothing_radius, p->bias, ctx->d_scal,
+  GaussTab gt;
+  BR_TRY(gauss_tab(ctx, p->smoothing_radius, &gt, st));
+  FusedLosOp<0> op{out_c2r, keep, gt, p->bias, ctx->d_scal,
                    {p->los[0], p->los[1], p->los[2]}, p->beta, p->n_iter, invM};
   return run_kspace_t(ctx, in, op, st);
 }
@@ -544,7 +569,7 @@ int kpass_fused_T(baorec_ctx* ctx, const float2* in, float2* out_c2r, float2* ke
 int kpass_fused_delta_T(baorec_ctx* ctx, const float2* in, float2* out_c2r, float2* keep, const baorec_params* p,
                         cudaStream_t st) {
   const float invM = (float)(1.0 / (double)ctx->M);
-  FusedLosOp<1> op{out_c2r, keep, 0.f, p->bias, ctx->d_scal, {p->los[0], p->los[1], p->los[2]}, p->beta, p->n_iter,
+  FusedLosOp<1> op{out_c2r, keep, GaussTab{}, p->bias, ctx->d_scal, {p->los[0], p->los[1], p->los[2]}, p->beta, p->n_iter,
                    invM};
   return run_kspace_t(ctx, in, op, st);
 }
@@ -561,12 +586,16 @@ int kpass_disp_T(baorec_ctx* ctx, const float2* in, float2* out, int comp, bool 
 
 // dc[8] must hold 1 / (A0 bias) (stash_dc with mul = 1/bias)
 int kpass_setup_box_T(baorec_ctx* ctx, const float2* in, float2* out, const baorec_params* p, cudaStream_t st) {
-  SetupBoxOp op{out, p->smoothing_radius * p->smoothing_radius, p->bias, ctx->d_scal};
+  GaussTab gt;
+  BR_TRY(gauss_tab(ctx, p->smoothing_radius, &gt, st));
+  SetupBoxOp op{out, gt, p->bias, ctx->d_scal};
   return run_kspace_t(ctx, in, op, st);
 }
 
 int kpass_gauss_T(baorec_ctx* ctx, const float2* in, float2* out, float R, cudaStream_t st) {
-  GaussOp op{out, R * R, 1.0 / (double)ctx->M};
+  GaussTab gt;
+  BR_TRY(gauss_tab(ctx, R, &gt, st));
+  GaussOp op{out, gt, 1.0 / (double)ctx->M};
   return run_kspace_t(ctx, in, op, st);
 }
 

@@ -211,6 +211,253 @@ mg_stencil_march(float* __restrict__ out, const float* __restrict__ v, const flo
   }
 }
 
+// ---- staged kernel: cp.async plane ring in shared memory + register z-march ----------------------
+// Block = TX x TY threads, tile = 4 TX cells in x by TY rows; every thread owns 4 consecutive x
+// cells and marches along z.  The (TY+2) x (4 TX + 2) window of each plane is copied global ->
+// shared memory with 16-byte cp.async (LDGSTS: no register staging, no L1 re-reads by the three
+// threads that need each row) into a ring of three planes, two planes ahead of the arithmetic,
+// so HBM latency is covered by the copies in flight rather than by occupancy.  Planes z-1 and z
+// stay in registers from the previous steps (the march is unrolled by three so the rotation is
+// free); only plane z+1 is read from shared memory (one LDS.128 per row; the x-1 / x+4
+// neighbours come from the adjacent lanes by shuffle, the tile edges from the staged halo
+// columns).  Coefficients are factored into per-thread (x, y) and per-plane (z) invariants and
+// the mixed differences share their partial differences between neighbouring cells.
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+struct Rows3 {
+  Row6 m, c, p;  // rows y-1, y, y+1 of one plane
+};
+
+// x-1, x..x+3, x+4 of one staged row (row points at the row's first float; x-1 of the tile is at
+// index 3, the body starts at index 4, x+4TX at index 4+4TX)
+__device__ __forceinline__ Row6 smem_row6(const float* row, int tx, int TX) {
+  Row6 r;
+  const float4 q = *reinterpret_cast<const float4*>(row + 4 + 4 * tx);
+  float l = __shfl_up_sync(0xffffffffu, q.w, 1), rr = __shfl_down_sync(0xffffffffu, q.x, 1);
+  if (tx == 0) l = row[3];
+  if (tx == TX - 1) rr = row[4 + 4 * TX];
+  r.m = l;
+  r.a = q.x;
+  r.b = q.y;
+  r.c = q.z;
+  r.d = q.w;
+  r.p = rr;
+  return r;
+}
+__device__ __forceinline__ Rows3 smem_rows3(const float* base, int RS, int tx, int TX) {
+  Rows3 r;
+  r.m = smem_row6(base, tx, TX);
+  r.c = smem_row6(base + RS, tx, TX);
+  r.p = smem_row6(base + 2 * RS, tx, TX);
+  return r;
+}
+
+constexpr int MG_ZCHUNK_MAX = 64;
+
+// NS = planes in the shared-memory ring: NS-1 planes (v window + f tile each) are in flight ahead
+// of the arithmetic.  At ~1 us of loaded HBM latency a B200 needs ~45 KB in flight per SM to
+// stream at full bandwidth; with two resident blocks (register-limited) NS = 3 keeps only
+// 2 x 2 x 5.4 KB in flight and the kernel sits at half the bandwidth (measured), NS = 6 keeps
+// 2 x 5 x 9.5 KB.
+template <int MODE, bool RADIAL, int NS>
+__global__ void __launch_bounds__(256, 2)
+mg_stencil_smem(float* __restrict__ out, const float* __restrict__ v, const float* __restrict__ f, MgGeom g,
+                float omega, int zchunk) {
+  extern __shared__ __align__(16) float sm[];
+  const int TX = blockDim.x, TY = blockDim.y;
+  const int RS = 4 * TX + 8, PS = (TY + 2) * RS;
+  const int FS = TY * 4 * TX;              // f tile of one plane
+  float* const fsm = sm + NS * PS;         // f ring
+  float* const pz_tab = fsm + NS * FS;     // p_z of the planes of this chunk (radial)
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int nx = g.nx, ny = g.ny, nz = g.nz;
+  const int xb = blockIdx.x * 4 * TX, yb = blockIdx.y * TY;
+  const int x0 = xb + 4 * tx, iy = yb + ty;
+  const int zbeg = blockIdx.z * zchunk, zend = min(nz, zbeg + zchunk);
+  const size_t plane = (size_t)nx * ny;
+  const int xl = xb == 0 ? nx - 1 : xb - 1, xr = xb + 4 * TX >= nx ? 0 : xb + 4 * TX;
+  const int yl = yb == 0 ? ny - 1 : yb - 1, yr = yb + TY >= ny ? 0 : yb + TY;
+
+  // staging plan of this thread: its own row, plus a halo row for the threads of rows 0 and 1;
+  // left / right halo columns by the first / last thread of the row
+  const bool has_halo_row = ty < 2;
+  const int hy = ty == 0 ? yl : yr;
+  const unsigned src_own = (unsigned)iy * nx, src_halo = (unsigned)hy * nx;  // row offsets inside a plane
+  float* const d_own = sm + (ty + 1) * RS;
+  float* const d_halo = sm + (ty == 0 ? 0 : TY + 1) * RS;
+  float* const d_f = fsm + (ty * TX + tx) * 4;
+  // real plane z (-1 .. nz) -> plane index in the buffer
+  auto storage = [&](int z) { return g.slab ? z + 1 : (z < 0 ? z + nz : (z >= nz ? z - nz : z)); };
+  // one copy group: the v window of plane z and the f tile of plane z-1 (what the step that reads
+  // plane z as its upper plane needs); planes past zend are never read
+  auto stage = [&](int z, int slot) {
+    if (z <= zend) {
+      const float* pl = v + (size_t)storage(z) * plane;
+      const int so = slot * PS;
+      {
+        const float* srow = pl + src_own;
+        float* drow = d_own + so;
+        cp_async16(drow + 4 + 4 * tx, srow + x0);
+        if (tx == 0) cp_async4(drow + 3, srow + xl);
+        if (tx == TX - 1) cp_async4(drow + 4 + 4 * TX, srow + xr);
+      }
+      if (has_halo_row) {
+        const float* srow = pl + src_halo;
+        float* drow = d_halo + so;
+        cp_async16(drow + 4 + 4 * tx, srow + x0);
+        if (tx == 0) cp_async4(drow + 3, srow + xl);
+        if (tx == TX - 1) cp_async4(drow + 4 + 4 * TX, srow + xr);
+      }
+      if (z > zbeg) cp_async16(d_f + slot * FS, f + (size_t)(z - 1 + g.slab) * plane + src_own + x0);
+    }
+    cp_async_commit();
+  };
+  // plane z lives in slot (z - zbeg + 1) % NS
+#pragma unroll
+  for (int j = 0; j < NS; j++) stage(zbeg - 1 + j, j);
+
+  // per-thread invariants
+  float px[MG_VX], pxx2[MG_VX];
+  float py, pz = 0.f;
+  if (RADIAL) {
+#pragma unroll
+    for (int k = 0; k < MG_VX; k++) px[k] = mg_p(g, 0, x0 + k);
+    py = mg_p(g, 1, iy);
+    for (int t = ty * TX + tx; t < zend - zbeg; t += TX * TY) pz_tab[t] = mg_p(g, 2, g.zlo + zbeg + t);
+  } else {
+#pragma unroll
+    for (int k = 0; k < MG_VX; k++) px[k] = g.lp[0];
+    py = g.lp[1];
+    pz = g.lp[2];
+  }
+  const float pyy = py * py, by2 = g.c2[1] * pyy, hpy = 0.5f * py, hc2x = 0.5f * g.c2[0];
+#pragma unroll
+  for (int k = 0; k < MG_VX; k++) pxx2[k] = 2.f * px[k] * px[k];
+  const float d0 = 2.f * (g.ic2[0] + g.ic2[1] + g.ic2[2]);
+  const float om1 = 1.f - omega;
+  const float icx = g.ic2[0], icy = g.ic2[1], icz = g.ic2[2];
+  // constant line of sight: every coefficient is a per-thread constant
+  float gg_c = 0.f, diag_c = 0.f, idiag_c = 0.f;
+  if (!RADIAL) {
+    gg_c = g.beta / (hc2x * pxx2[0] + by2 + g.c2[2] * pz * pz);
+    diag_c = d0 + gg_c * (pxx2[0] + 2.f * (pyy + pz * pz));
+    idiag_c = 1.f / diag_c;
+  }
+
+  cp_async_wait<NS - 2>();
+  __syncthreads();
+  Rows3 R0 = smem_rows3(sm + ty * RS, RS, tx, TX);       // plane zbeg-1 (slot 0)
+  Rows3 R1 = smem_rows3(sm + PS + ty * RS, RS, tx, TX);  // plane zbeg   (slot 1)
+  Rows3 R2;
+  __syncthreads();
+  stage(zbeg + NS - 1, 0);
+  const size_t rowoff = (size_t)iy * nx + x0;
+  int cslot = 2 % NS;  // slot of plane iz+1
+  int fslot = 1;       // slot of plane iz (free once this step's barrier is passed)
+
+  // one z step: A = plane iz-1, B = plane iz (registers); C = plane iz+1 is read from cslot;
+  // plane iz+NS is staged into fslot
+  auto step = [&](int iz, const Rows3& A, const Rows3& B, Rows3& C) {
+    cp_async_wait<NS - 2>();
+    __syncthreads();
+    stage(iz + NS, fslot);
+    C = smem_rows3(sm + cslot * PS + ty * RS, RS, tx, TX);
+    const float4 fcur = *reinterpret_cast<const float4*>(d_f + cslot * FS);
+    fslot = cslot;
+    cslot = cslot + 1 == NS ? 0 : cslot + 1;
+    const size_t o = (size_t)(iz + g.slab) * plane + rowoff;
+    float pzz2 = 0.f, hpyz, byz = 0.f, s_yz2 = 0.f;
+    if (RADIAL) {
+      pz = pz_tab[iz - zbeg];
+      const float pzz = pz * pz;
+      byz = fmaf(g.c2[2], pzz, by2);
+      s_yz2 = 2.f * (pyy + pzz);
+      pzz2 = pzz;
+    } else {
+      pzz2 = pz * pz;
+    }
+    hpyz = 0.5f * py * pz;
+    const float hpz = 0.5f * pz;
+    const float bm[6] = {B.m.m, B.m.a, B.m.b, B.m.c, B.m.d, B.m.p};
+    const float b0[6] = {B.c.m, B.c.a, B.c.b, B.c.c, B.c.d, B.c.p};
+    const float bp[6] = {B.p.m, B.p.a, B.p.b, B.p.c, B.p.d, B.p.p};
+    const float a0[6] = {A.c.m, A.c.a, A.c.b, A.c.c, A.c.d, A.c.p};
+    const float c0[6] = {C.c.m, C.c.a, C.c.b, C.c.c, C.c.d, C.c.p};
+    const float am[4] = {A.m.a, A.m.b, A.m.c, A.m.d}, ap[4] = {A.p.a, A.p.b, A.p.c, A.p.d};
+    const float cm[4] = {C.m.a, C.m.b, C.m.c, C.m.d}, cp[4] = {C.p.a, C.p.b, C.p.c, C.p.d};
+    const float ff[4] = {fcur.x, fcur.y, fcur.z, fcur.w};
+    // D[j] = v(y+1) - v(y-1), E[j] = v(z+1) - v(z-1) at x-1 .. x+4: the mixed differences are
+    // D[k+2]-D[k] and E[k+2]-E[k]; D[k+1], E[k+1] are the first differences of the radial term
+    float D[6], E[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      D[j] = bp[j] - bm[j];
+      E[j] = c0[j] - a0[j];
+    }
+    float res[4];
+#pragma unroll
+    for (int k = 0; k < MG_VX; k++) {
+      const float vxp = b0[k + 2], vxm = b0[k], vc = b0[k + 1];
+      const float sx = vxp + vxm, sy = bp[k + 1] + bm[k + 1], sz = c0[k + 1] + a0[k + 1];
+      const float dxy = D[k + 2] - D[k], dxz = E[k + 2] - E[k];
+      const float dyz = (cp[k] - cm[k]) - (ap[k] - am[k]);
+      float gg, diag, idiag;
+      if (RADIAL) {
+        gg = g.beta * rcp_approx(fmaf(hc2x, pxx2[k], byz));
+        diag = fmaf(gg, pxx2[k] + s_yz2, d0);
+        idiag = rcp_approx(diag);
+      } else {
+        gg = gg_c;
+        diag = diag_c;
+        idiag = idiag_c;
+      }
+      // off = sum_a ic2_a s_a + gg [ sum_a p_a^2 s_a + (1/2) sum_{a<b} p_a p_b d_ab + (radial) sum_a p_a e_a ]
+      float in = 0.5f * pxx2[k] * sx;
+      in = fmaf(pyy, sy, in);
+      in = fmaf(pzz2, sz, in);
+      in = fmaf(px[k] * hpy, dxy, in);
+      in = fmaf(px[k] * hpz, dxz, in);
+      in = fmaf(hpyz, dyz, in);
+      if (RADIAL) {
+        in = fmaf(px[k], vxp - vxm, in);
+        in = fmaf(py, D[k + 1], in);
+        in = fmaf(pz, E[k + 1], in);
+      }
+      float off = icx * sx;
+      off = fmaf(icy, sy, off);
+      off = fmaf(icz, sz, off);
+      off = fmaf(gg, in, off);
+      if (MODE == MG_JACOBI) res[k] = fmaf(omega, (ff[k] + off) * idiag, om1 * vc);
+      else res[k] = ff[k] - fmaf(diag, vc, -off);
+    }
+    *reinterpret_cast<float4*>(out + o) = make_float4(res[0], res[1], res[2], res[3]);
+  };
+
+  for (int iz = zbeg; iz < zend; iz += 3) {
+    step(iz, R0, R1, R2);
+    if (iz + 1 < zend) step(iz + 1, R1, R2, R0);
+    if (iz + 2 < zend) step(iz + 2, R2, R0, R1);
+  }
+  cp_async_wait<0>();
+}
+
 // ---- restriction (reduce!, src/multigrid.jl:520-584): coarse c <- fine 2c+1, weights 8/4/2/1 /64
 __global__ void __launch_bounds__(256)
 mg_restrict_kernel(float* __restrict__ c, const float* __restrict__ fine, int nx, int ny, int nz, int slab) {
@@ -293,10 +540,53 @@ static bool march_ok(int nx, int ny, int nz, const void* a, const void* b, const
   return nx % MG_VX == 0 && nx >= 32 && nz >= 8 && ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0);
 }
 
+// staged kernel: whole tiles only (4 TX | nx, TY | ny), full warps, 16-byte aligned rows
+static bool smem_ok(const MgGeom& g, const void* a, const void* b, const void* c, int* tx_out, int* ty_out) {
+  if (g.nx % 4 != 0 || g.nx < 16 || g.nz < 4) return false;
+  if ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) != 0) return false;
+  int tx = g.nx / 4;
+  if (tx > 32) tx = 32;
+  if ((tx & (tx - 1)) != 0 || g.nx % (4 * tx) != 0) return false;
+  int ty = 256 / tx;
+  while (ty > 2 && g.ny % ty != 0) ty /= 2;
+  if (ty < 2 || g.ny % ty != 0 || (tx * ty) % 32 != 0) return false;
+  *tx_out = tx;
+  *ty_out = ty;
+  return true;
+}
+
 template <int MODE>
 static int launch_stencil(baorec_ctx* ctx, float* out, const float* v, const float* f, const MgGeom& g, float omega,
                           cudaStream_t st) {
-  if (march_ok(g.nx, g.ny, g.nz, out, v, f)) {
+  int stx = 0, sty = 0;
+  if (ctx->opt_mg_kernel == 0 && smem_ok(g, out, v, f, &stx, &sty)) {
+    int zchunk = MG_ZCHUNK_MAX;
+    const size_t blocks_xy = (size_t)(g.nx / (4 * stx)) * (g.ny / sty);
+    while (zchunk > 8 && blocks_xy * cdiv(g.nz, zchunk) < 148 * 6) zchunk /= 2;
+    dim3 grid(g.nx / (4 * stx), g.ny / sty, cdiv(g.nz, zchunk));
+    dim3 block(stx, sty);
+    const int NS = ctx->opt_mg_ring == 3 ? 3 : 6;
+    const size_t smem =
+        ((size_t)NS * ((sty + 2) * (4 * stx + 8) + sty * 4 * stx) + MG_ZCHUNK_MAX) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+      const int big = 100 * 1024;
+      cudaFuncSetAttribute(mg_stencil_smem<MG_JACOBI, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      cudaFuncSetAttribute(mg_stencil_smem<MG_JACOBI, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      cudaFuncSetAttribute(mg_stencil_smem<MG_RESIDUAL, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      cudaFuncSetAttribute(mg_stencil_smem<MG_RESIDUAL, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      attr = true;
+    }
+    if (NS == 3) {
+      if (g.radial) BR_LAUNCH(ctx, (mg_stencil_smem<MODE, true, 3>), grid, block, smem, st, out, v, f, g, omega, zchunk);
+      else BR_LAUNCH(ctx, (mg_stencil_smem<MODE, false, 3>), grid, block, smem, st, out, v, f, g, omega, zchunk);
+    } else {
+      if (g.radial) BR_LAUNCH(ctx, (mg_stencil_smem<MODE, true, 6>), grid, block, smem, st, out, v, f, g, omega, zchunk);
+      else BR_LAUNCH(ctx, (mg_stencil_smem<MODE, false, 6>), grid, block, smem, st, out, v, f, g, omega, zchunk);
+    }
+    return BAOREC_OK;
+  }
+  if (ctx->opt_mg_kernel <= 1 && march_ok(g.nx, g.ny, g.nz, out, v, f)) {
     int tx = g.nx / MG_VX;
     if (tx > 64) tx = 64;
     int ty = 256 / tx;
@@ -618,12 +908,16 @@ int reconstructed_potential(baorec_ctx* ctx, const baorec_params* p, float* phi,
                             const float* w, int64_t n, float* rx, float* ry, float* rz, const float* rw, int64_t nr,
                             cudaStream_t st) {
   float* delta;
+  ctx->disp_valid = false;
+  ctx->mg_result_mesh = nullptr;
   BR_TRY(need_t(ctx, BUF_RS, ctx->M, &delta));
   // phi (zero-filled by the caller) is the scatter target; delta lands in RS (δ = zero(ϕ), src/recon.jl:191)
   BR_TRY(setup_overdensity_into(ctx, p, phi, delta, x, y, z, w, n, rx, ry, rz, rw, nr, 1, st));
   BR_CUDA(cudaMemsetAsync(phi, 0, ctx->M * sizeof(float), st));
-  return mg_fmg(ctx, delta, phi, p->beta, p->jacobi_damping_factor, p->jacobi_niterations, p->vcycle_niterations,
-                p->has_los ? p->los : nullptr, st);
+  BR_TRY(mg_fmg(ctx, delta, phi, p->beta, p->jacobi_damping_factor, p->jacobi_niterations, p->vcycle_niterations,
+                p->has_los ? p->los : nullptr, st));
+  ctx->mg_result_mesh = phi;
+  return BAOREC_OK;
 }
 
 }  // namespace baorec
@@ -640,6 +934,7 @@ int baorec_mg_jacobi_f32(baorec_ctx* ctx, float* d_v, const float* d_f, int nx, 
   size_t cells = (size_t)nx * ny * nz;
   float* tmp;
   BR_TRY(need_t(ctx, BUF_RX, cells > ctx->M ? cells : ctx->M, &tmp));
+  ctx->disp_valid = false;
   MgGeom g = mg_geom(ctx, nx, ny, nz, beta, h_los);
   float* res;
   BR_TRY(jacobi_pp(ctx, d_v, tmp, d_f, g, damping, niterations, &res, st));

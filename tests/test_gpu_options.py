@@ -230,3 +230,51 @@ def test_result_cache_read_skips_forward_transform_and_matches(B, O):
     s_ref = B.read_shifts(rec, *d, mesh.clone(), field="disp")
     for a in range(3):
         assert maxabs(s_mod[a].cpu().numpy(), s_ref[a].cpu().numpy()) < 1e-6
+
+
+@pytest.mark.parametrize("algo", ["iterative", "multigrid"])
+def test_displacement_meshes_are_reused_across_catalogs(B, O, algo):
+    """reconstructed_positions for data, then for two other catalogs against the same
+    recon.result_cache (examples/simulation.jl:32-35): only the first call pays for the transforms;
+    a new run! or an edited mesh invalidates the kept displacement meshes."""
+    n, L = 64, 1000.0
+    pos, w = clustered_box(200_000, L, seed=9)
+    rnd, _ = clustered_box(300_000, L, seed=10, nclump=1, sigma=10.0)
+    kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=np.full(3, L, np.float32),
+              box_min=np.zeros(3, np.float32), los=(0.0, 0.0, 1.0))
+    Rec, ORec = (B.IterativeRecon, O.IterativeRecon) if algo == "iterative" else (B.MultigridRecon, O.MultigridRecon)
+    d, r = [dev(p) for p in pos], [dev(p) for p in rnd]
+    rec = Rec(**kw)
+    mesh = B.run(rec, (n, n, n), *d, dev(w))
+    ctx = rec.fft_plan.ctx
+    _, f0 = ctx.launch_counts()
+    pd = B.reconstructed_positions(rec, *d, field="sum")
+    _, f1 = ctx.launch_counts()
+    pr_sym = B.reconstructed_positions(rec, *r, field="sum")
+    pr_iso = B.reconstructed_positions(rec, *r, field="disp")
+    _, f2 = ctx.launch_counts()
+    assert f1 - f0 == (3 if algo == "iterative" else 4) and f2 == f1
+    orec = ORec(**kw)
+    omesh = O.run(orec, (n, n, n), *[p.copy() for p in pos], w)
+    for got, cat, f in ((pd, pos, "sum"), (pr_sym, rnd, "sum"), (pr_iso, rnd, "disp")):
+        sh = O.read_shifts(orec, *cat, omesh, f)
+        for a in range(3):
+            assert maxabs(got[a].cpu().numpy(), cat[a] - sh[a]) < 1e-3
+    # host pipeline: same reuse against the library-owned cached mesh
+    rec_h = Rec(**kw)
+    B.run(rec_h, (n, n, n), *[p.copy() for p in pos], w)
+    _, f3 = ctx.launch_counts()
+    hd = B.read_shifts(rec_h, *pos, None, field="sum")
+    _, f4 = ctx.launch_counts()
+    hr = B.read_shifts(rec_h, *rnd, None, field="sum")
+    _, f5 = ctx.launch_counts()
+    assert f4 > f3 and f5 == f4
+    sh = O.read_shifts(orec, *rnd, omesh, "sum")
+    for a in range(3):
+        assert maxabs(hr[a], sh[a]) < 1e-3
+    # a new reconstruction on the context invalidates the kept meshes
+    mesh2 = B.run(rec, (n, n, n), *r, dev(np.ones(len(rnd[0]), np.float32)))
+    _, f6 = ctx.launch_counts()
+    B.reconstructed_positions(rec, *d, field="sum")
+    _, f7 = ctx.launch_counts()
+    assert f7 - f6 >= 3
