@@ -183,6 +183,7 @@ int baorec_set_option(baorec_ctx* ctx, const char* name, int64_t value) {
   else if (s == "bin_zg_gather") ctx->opt_zg_gather = (int)value;
   else if (s == "mg_kernel") ctx->opt_mg_kernel = (int)value;
   else if (s == "mg_ring") ctx->opt_mg_ring = (int)value;
+  else if (s == "mg_coarse") ctx->opt_mg_coarse = (int)value;
   else if (s == "mg_slab_min_cells") {
     ctx->opt_mg_slab_min_cells = value;
     ctx->dlevels.clear();

@@ -535,6 +535,192 @@ mg_prolong_kernel(float* __restrict__ fine, const float* __restrict__ c, int nx,
     }
 }
 
+// ---- coarse levels: one thread block runs the whole bottom of the V-cycle in shared memory ------
+// Levels of at most MG_COARSE_CELLS cells (16^3 and below) are launch-bound: a V-cycle visits them
+// with 10 sweeps + residual + restriction + prolongation each, ~37 launches of a few microseconds
+// for 16^3 -> 8^3 -> 4^3, and full multigrid visits them hundreds of times.  This kernel keeps v, its
+// ping-pong copy and f of every such level in shared memory and runs `ncycles` V-cycles
+// (src/multigrid.jl:654-687) from level 0 of `a` downwards with block-wide barriers between the
+// steps: same operator, same restriction / prolongation weights, same order of sweeps.
+constexpr int MG_COARSE_CELLS = 4096;
+constexpr int MG_COARSE_LEVELS = 6;
+constexpr int MG_COARSE_THREADS = 1024;
+
+struct CoarseArgs {
+  MgGeom g[MG_COARSE_LEVELS];
+  int nlev, nj, ncycles;
+  float omega;
+};
+
+struct CoarseLevel {
+  float *v, *w, *f;       // solution, ping-pong / residual scratch, right-hand side
+  float *px, *py, *pz;    // p tables (radial)
+};
+
+template <int MODE>
+__device__ __forceinline__ void coarse_stencil(float* __restrict__ out, const float* __restrict__ v,
+                                               const float* __restrict__ f, const MgGeom& g, const CoarseLevel& L,
+                                               float omega) {
+  const int nx = g.nx, ny = g.ny, nz = g.nz, cells = nx * ny * nz;
+  for (int c = threadIdx.x; c < cells; c += MG_COARSE_THREADS) {
+    const int iz = c / (nx * ny), rem = c - iz * nx * ny, iy = rem / nx, ix = rem - iy * nx;
+    const int xp = ix + 1 == nx ? 0 : ix + 1, xm = ix == 0 ? nx - 1 : ix - 1;
+    const int yp = iy + 1 == ny ? 0 : iy + 1, ym = iy == 0 ? ny - 1 : iy - 1;
+    const int zp = iz + 1 == nz ? 0 : iz + 1, zm = iz == 0 ? nz - 1 : iz - 1;
+    auto V = [&](int x, int y, int z) { return v[(z * ny + y) * nx + x]; };
+    float px, py, pz;
+    if (g.radial) {
+      px = L.px[ix];
+      py = L.py[iy];
+      pz = L.pz[iz];
+    } else {
+      px = g.lp[0];
+      py = g.lp[1];
+      pz = g.lp[2];
+    }
+    float gg = g.beta / (g.c2[0] * px * px + g.c2[1] * py * py + g.c2[2] * pz * pz);
+    float gx = g.ic2[0] + gg * px * px, gy = g.ic2[1] + gg * py * py, gz = g.ic2[2] + gg * pz * pz;
+    float vxp = V(xp, iy, iz), vxm = V(xm, iy, iz), vyp = V(ix, yp, iz), vym = V(ix, ym, iz);
+    float vzp = V(ix, iy, zp), vzm = V(ix, iy, zm);
+    float off = gx * (vxp + vxm) + gy * (vyp + vym) + gz * (vzp + vzm) +
+                gg / 2 *
+                    (px * py * (V(xp, yp, iz) + V(xm, ym, iz) - V(xm, yp, iz) - V(xp, ym, iz)) +
+                     px * pz * (V(xp, iy, zp) + V(xm, iy, zm) - V(xm, iy, zp) - V(xp, iy, zm)) +
+                     py * pz * (V(ix, yp, zp) + V(ix, ym, zm) - V(ix, ym, zp) - V(ix, yp, zm)));
+    if (g.radial) off += gg * (px * (vxp - vxm) + py * (vyp - vym) + pz * (vzp - vzm));
+    float diag = 2 * (gx + gy + gz);
+    float vc = v[c];
+    if (MODE == MG_JACOBI) out[c] = (1 - omega) * vc + omega * ((f[c] + off) / diag);
+    else out[c] = f[c] - (diag * vc - off);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(MG_COARSE_THREADS)
+mg_coarse_kernel(float* __restrict__ v_io, const float* __restrict__ f_in, CoarseArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  CoarseLevel L[MG_COARSE_LEVELS];
+  {
+    float* p = sm;
+    for (int l = 0; l < a.nlev; l++) {
+      const int cells = a.g[l].nx * a.g[l].ny * a.g[l].nz;
+      L[l].v = p;
+      L[l].w = p + cells;
+      L[l].f = p + 2 * cells;
+      p += 3 * cells;
+      L[l].px = p;
+      L[l].py = p + a.g[l].nx;
+      L[l].pz = L[l].py + a.g[l].ny;
+      p += a.g[l].nx + a.g[l].ny + a.g[l].nz;
+    }
+  }
+  const int tid = threadIdx.x;
+  for (int l = 0; l < a.nlev; l++) {
+    const MgGeom& g = a.g[l];
+    if (g.radial) {
+      for (int i = tid; i < g.nx; i += MG_COARSE_THREADS) L[l].px[i] = mg_p(g, 0, i);
+      for (int i = tid; i < g.ny; i += MG_COARSE_THREADS) L[l].py[i] = mg_p(g, 1, i);
+      for (int i = tid; i < g.nz; i += MG_COARSE_THREADS) L[l].pz[i] = mg_p(g, 2, i);
+    }
+  }
+  {
+    const int cells = a.g[0].nx * a.g[0].ny * a.g[0].nz;
+    for (int c = tid; c < cells; c += MG_COARSE_THREADS) {
+      L[0].v[c] = v_io[c];
+      L[0].f[c] = f_in[c];
+    }
+  }
+  __syncthreads();
+  auto smooth = [&](int l) {
+    for (int i = 0; i < a.nj; i++) {
+      coarse_stencil<MG_JACOBI>(L[l].w, L[l].v, L[l].f, a.g[l], L[l], a.omega);
+      float* t = L[l].v;
+      L[l].v = L[l].w;
+      L[l].w = t;
+    }
+  };
+  for (int cyc = 0; cyc < a.ncycles; cyc++) {
+    for (int l = 0; l < a.nlev; l++) {
+      smooth(l);
+      if (l + 1 == a.nlev) {
+        smooth(l);  // the coarsest level smooths twice per V-cycle (pre + post, nothing in between)
+        break;
+      }
+      coarse_stencil<MG_RESIDUAL>(L[l].w, L[l].v, L[l].f, a.g[l], L[l], 0.f);
+      // reduce!: coarse c <- fine 2c+1, weights 8/4/2/1 / 64; the coarse solution starts from zero
+      const int nx = a.g[l].nx, ny = a.g[l].ny, nz = a.g[l].nz, cx = nx / 2, cy = ny / 2, cz = nz / 2;
+      const float* fine = L[l].w;
+      for (int c = tid; c < cx * cy * cz; c += MG_COARSE_THREADS) {
+        const int iz = c / (cx * cy), rem = c - iz * cx * cy, iy = rem / cx, ix = rem - iy * cx;
+        const int fx = 2 * ix + 1, fy = 2 * iy + 1, fz = 2 * iz + 1;
+        const int X[3] = {fx - 1, fx, fx + 1 == nx ? 0 : fx + 1};
+        const int Y[3] = {fy - 1, fy, fy + 1 == ny ? 0 : fy + 1};
+        const int Z[3] = {fz - 1, fz, fz + 1 == nz ? 0 : fz + 1};
+        float s8 = 0.f, s4 = 0.f, s2 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int c3 = 0; c3 < 3; c3++)
+#pragma unroll
+          for (int b = 0; b < 3; b++)
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+              const float val = fine[(Z[c3] * ny + Y[b]) * nx + X[q]];
+              const int k = (q != 1) + (b != 1) + (c3 != 1);
+              if (k == 0) s8 += val;
+              else if (k == 1) s4 += val;
+              else if (k == 2) s2 += val;
+              else s1 += val;
+            }
+        L[l + 1].f[c] = (8 * s8 + 4 * s4 + 2 * s2 + s1) / 64.0f;
+        L[l + 1].v[c] = 0.f;
+      }
+      __syncthreads();
+    }
+    for (int l = a.nlev - 2; l >= 0; l--) {
+      // v += prolong!(coarse): one thread per coarse cell writes its 2x2x2 fine cells
+      const int nx = a.g[l].nx, ny = a.g[l].ny, cx = nx / 2, cy = ny / 2, cz = a.g[l].nz / 2;
+      const float* cs = L[l + 1].v;
+      float* fine = L[l].v;
+      for (int c = tid; c < cx * cy * cz; c += MG_COARSE_THREADS) {
+        const int iz = c / (cx * cy), rem = c - iz * cx * cy, iy = rem / cx, ix = rem - iy * cx;
+        const int X[2] = {ix == 0 ? cx - 1 : ix - 1, ix}, Y[2] = {iy == 0 ? cy - 1 : iy - 1, iy};
+        const int Z[2] = {iz == 0 ? cz - 1 : iz - 1, iz};
+        float xe[2][2], xo[2][2];
+#pragma unroll
+        for (int dz = 0; dz < 2; dz++)
+#pragma unroll
+          for (int dy = 0; dy < 2; dy++) {
+            const float* row = cs + (Z[dz] * cy + Y[dy]) * cx;
+            const float p0 = row[X[0]], p1 = row[X[1]];
+            xe[dz][dy] = 0.5f * (p0 + p1);
+            xo[dz][dy] = p1;
+          }
+#pragma unroll
+        for (int pz = 0; pz < 2; pz++)
+#pragma unroll
+          for (int py = 0; py < 2; py++) {
+            float e[2], o[2];
+#pragma unroll
+            for (int dz = 0; dz < 2; dz++) {
+              e[dz] = py ? xe[dz][1] : 0.5f * (xe[dz][0] + xe[dz][1]);
+              o[dz] = py ? xo[dz][1] : 0.5f * (xo[dz][0] + xo[dz][1]);
+            }
+            const float ve = pz ? e[1] : 0.5f * (e[0] + e[1]);
+            const float vo = pz ? o[1] : 0.5f * (o[0] + o[1]);
+            float* dst = fine + ((2 * iz + pz) * ny + (2 * iy + py)) * nx + 2 * ix;
+            dst[0] += ve;
+            dst[1] += vo;
+          }
+      }
+      __syncthreads();
+      smooth(l);
+    }
+  }
+  {
+    const int cells = a.g[0].nx * a.g[0].ny * a.g[0].nz;
+    for (int c = tid; c < cells; c += MG_COARSE_THREADS) v_io[c] = L[0].v[c];
+  }
+}
+
 // ---- launch helpers -------------------------------------------------------------------------------
 static bool march_ok(int nx, int ny, int nz, const void* a, const void* b, const void* c) {
   return nx % MG_VX == 0 && nx >= 32 && nz >= 8 && ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0);
@@ -806,10 +992,42 @@ static int prolong_level(MgRun& r, size_t l, const float* coarse, float* fine, b
   return prolong_to(ctx, fine, C.tmp, F.nx, F.ny, F.nzl, add, r.st, 1);
 }
 
+// Levels small enough for the single-block kernel (and everything below them).
+static bool coarse_ok(const MgRun& r, size_t l) {
+  const std::vector<MgLevel>& lv = *r.lv;
+  return r.ctx->opt_mg_coarse && !lv[l].slab && lv[l].cells <= (size_t)MG_COARSE_CELLS &&
+         lv.size() - l <= (size_t)MG_COARSE_LEVELS;
+}
+
+// `ncycles` V-cycles at level l (and below) in one launch, in place on r.cur[l]
+static int coarse_cycles(MgRun& r, size_t l, int ncycles) {
+  baorec_ctx* ctx = r.ctx;
+  const std::vector<MgLevel>& lv = *r.lv;
+  CoarseArgs a;
+  a.nlev = (int)(lv.size() - l);
+  a.nj = r.nj;
+  a.ncycles = ncycles;
+  a.omega = r.omega;
+  size_t floats = 0;
+  for (int i = 0; i < a.nlev; i++) {
+    const MgLevel& L = lv[l + i];
+    a.g[i] = level_geom(ctx, L, r.beta, r.los);
+    floats += 3 * L.cells + L.nx + L.ny + L.nz;
+  }
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(mg_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr = true;
+  }
+  BR_LAUNCH(ctx, mg_coarse_kernel, 1, MG_COARSE_THREADS, floats * sizeof(float), r.st, r.cur[l], r.f[l], a);
+  return BAOREC_OK;
+}
+
 // vcycle! (src/multigrid.jl:654-687) at level l, operating on run.cur[l]
 static int vcycle_level(MgRun& r, size_t l) {
   baorec_ctx* ctx = r.ctx;
   std::vector<MgLevel>& lv = *r.lv;
+  if (coarse_ok(r, l)) return coarse_cycles(r, l, 1);
   MgLevel& L = lv[l];
   MgGeom g = level_geom(ctx, L, r.beta, r.los);
   float* res;
@@ -872,6 +1090,10 @@ static int fmg_levels(MgRun& r, int n_vcycle) {
       BR_CUDA(cudaMemsetAsync(tgt, 0, level_elems(lv[li]) * sizeof(float), st));
     }
     r.cur[li] = tgt;
+    if (coarse_ok(r, li)) {
+      if (n_vcycle > 0) BR_TRY(coarse_cycles(r, li, n_vcycle));
+      continue;
+    }
     for (int c = 0; c < n_vcycle; c++) BR_TRY(vcycle_level(r, li));
   }
   return BAOREC_OK;

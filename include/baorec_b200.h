@@ -96,7 +96,7 @@ int baorec_set_box(baorec_ctx* ctx, const float box_size[3], const float box_min
  *       smoothing, normalisation and all n_iter iterations into ONE k-space pass between one
  *       R2C and one C2R (iterate! is linear and diagonal in k for a constant LOS); 0 = run the
  *       reference's sequence of iterate! calls (2 + 2 n_iter transforms).
- *   "mg_slab_min_cells" (default 2097152): slab-decomposed multigrid levels with fewer cells are
+ *   "mg_slab_min_cells" (default 4194304): slab-decomposed multigrid levels with fewer cells are
  *       replicated on every rank instead of exchanging halos. */
 int baorec_set_option(baorec_ctx* ctx, const char* name, int64_t value);
 /* Bytes of device scratch currently owned by the context. */
@@ -153,7 +153,7 @@ int baorec_dist_c2r_f32(baorec_ctx* ctx, float* d_kslab_t /* destroyed */, float
  *   (src/iterative.jl:151-211) on slabs with 1 R2C + 6 C2R per iteration;
  *   MultigridRecon: fmg (src/multigrid.jl:722-752) on slabs, one halo-plane exchange with both
  *   ring neighbours after every Jacobi sweep / residual / prolongation; levels smaller than
- *   option "mg_slab_min_cells" (default 2^21 cells) are all-gathered and solved on every rank.
+ *   option "mg_slab_min_cells" (default 2^22 cells: 128^3 and below) are all-gathered and solved on every rank.
  * delta_k (phi_k) is kept, transposed, for baorec_read_shifts_dist_f32.  CIC only. */
 int baorec_run_dist_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, float* d_x, float* d_y, float* d_z,
                         const float* d_w, int64_t n_local, float* d_rx, float* d_ry, float* d_rz, const float* d_rw,

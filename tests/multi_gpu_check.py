@@ -24,7 +24,7 @@ import baorec_oracle as O  # noqa: E402
 from util import clustered_box, rel_rms, maxabs  # noqa: E402
 
 
-def more_modes(B, ctx, rank, world):
+def more_modes(B, ctx, rank, world, quick=False):
     """MultigridRecon on slabs (halo exchange per sweep, slab restriction / prolongation, all-gathered
     coarse levels), radial line of sight and the randoms set-up, all against the oracle."""
     ok = True
@@ -42,7 +42,7 @@ def more_modes(B, ctx, rank, world):
         return good
 
     # 1. MultigridRecon, periodic box, fixed and radial LOS; all levels on slabs / coarse levels replicated
-    for los, lo, min_cells in (((0.0, 0.0, 1.0), 0.0, 0), (None, 700.0, 16 ** 3), ((0.0, 1.0, 0.0), 0.0, 1 << 21)):
+    for los, lo, min_cells in (((0.0, 0.0, 1.0), 0.0, 0), (None, 700.0, 16 ** 3), ((0.0, 1.0, 0.0), 0.0, 1 << 22)):
         pos, w = clustered_box(200_000, L, seed=21, lo=lo)
         kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=np.full(3, L, np.float32),
                   box_min=np.full(3, lo, np.float32), los=los)
@@ -61,6 +61,9 @@ def more_modes(B, ctx, rank, world):
                      max(rel_rms(s[a].cpu().numpy(), oshift[a][mine]) for a in range(3)),
                      max(maxabs(s[a].cpu().numpy(), oshift[a][mine]) for a in range(3)))
     ctx.set_option("mg_slab_min_cells", 16 ** 3)
+    if quick:
+        ctx.set_option("mg_slab_min_cells", 1 << 22)
+        return ok
 
     # 2. randoms set-up (box filled by the randoms: no cell on the ran > threshold discontinuity)
     lo = 700.0
@@ -95,7 +98,7 @@ def more_modes(B, ctx, rank, world):
             ok &= report(f"{algo} randoms los={los}", e_mesh,
                          max(rel_rms(s[a].cpu().numpy(), oshift[a][md]) for a in range(3)),
                          max(maxabs(s[a].cpu().numpy(), oshift[a][md]) for a in range(3)))
-    ctx.set_option("mg_slab_min_cells", 1 << 21)
+    ctx.set_option("mg_slab_min_cells", 1 << 22)
     return ok
 
 
@@ -108,8 +111,9 @@ def main():
     ctx = B.Context.get(local)
     B.dist.init_comm(ctx)
     ok = True
+    quick = os.environ.get("MGC_QUICK") == "1"       # multigrid cases only (8-rank runs are charged 8x)
     for n, los in ((64, (0.0, 0.0, 1.0)), (96, (0.0, 1.0, 0.0))):
-        if n % world:
+        if n % world or quick:
             continue
         L, N = 1000.0, 400_000
         pos, w = clustered_box(N, L, seed=11)
@@ -134,7 +138,7 @@ def main():
         print(f"[rank {rank}/{world}] n={n} los={los} particles={int(mine.sum())} slab=[{z_lo},{z_lo + nzl}) "
               f"mesh rel.rms={e_mesh:.2e} shift rel.rms={e_rms:.2e} max={e_max:.2e} {'OK' if good else 'FAIL'}",
               flush=True)
-    ok &= more_modes(B, ctx, rank, world)
+    ok &= more_modes(B, ctx, rank, world, quick)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

@@ -124,7 +124,7 @@ def test_multigrid_dist_box(B, O, dctx, min_cells, los, lo):
                 assert rel_rms(s[a].cpu().numpy(), ref[a]) < 1e-4
                 assert maxabs(s[a].cpu().numpy(), ref[a]) < 1e-3
     finally:
-        dctx.set_option("mg_slab_min_cells", 1 << 21)
+        dctx.set_option("mg_slab_min_cells", 1 << 22)
 
 
 @pytest.mark.parametrize("algo", ["iterative", "multigrid"])
@@ -147,7 +147,7 @@ def test_run_dist_with_randoms(B, O, dctx, algo, los, lo):
     try:
         mesh = B.dist.run_dist(rec, (n, n, n), *gd, dev(wd), *gr, dev(wr), ctx=dctx)
     finally:
-        dctx.set_option("mg_slab_min_cells", 1 << 21)
+        dctx.set_option("mg_slab_min_cells", 1 << 22)
     g = mesh.cpu().numpy()
     if algo == "multigrid":   # the potential is defined up to a constant
         assert rel_rms(g - g.mean(), omesh - omesh.mean()) < 1e-4
