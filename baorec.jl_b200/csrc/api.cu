@@ -38,6 +38,8 @@ static int read_common(baorec_ctx* ctx, const baorec_params* p, int algorithm, c
   // meshes computed from it by an earlier call are still its displacement meshes
   const bool reuse = trusted && ctx->disp_valid && ctx->disp_algo == algorithm && ctx->disp_mesh == mesh &&
                      !own_fft_available(ctx);
+  BR_TRY(reset_oob(ctx, st));
+  if (!reuse) BR_TRY(gather_prebin(ctx, x, y, z, n, p->mas, st));  // the sort overlaps the transforms
   if (!reuse) {
     ctx->disp_valid = false;
     BR_TRY(displacement_meshes(ctx, mesh, algorithm, px, py, pz, st, use_kcache));
@@ -48,7 +50,6 @@ static int read_common(baorec_ctx* ctx, const baorec_params* p, int algorithm, c
     }
   }
   BR_CUDA(cudaEventRecord(ctx->ev[5], st));
-  BR_TRY(reset_oob(ctx, st));
   BR_TRY(gather3(ctx, px, py, pz, x, y, z, n, ox, oy, oz, p->mas, field, p->f, p->has_los, p->los, positions, st));
   return check_oob(ctx, st, "read_shifts");
 }
@@ -183,6 +184,8 @@ int baorec_set_option(baorec_ctx* ctx, const char* name, int64_t value) {
   else if (s == "bin_zg_gather") ctx->opt_zg_gather = (int)value;
   else if (s == "mg_kernel") ctx->opt_mg_kernel = (int)value;
   else if (s == "mg_ring") ctx->opt_mg_ring = (int)value;
+  else if (s == "overlap_sort") ctx->opt_overlap_sort = (int)value;
+  else if (s == "a2a_chunks") ctx->opt_a2a_chunks = (int)value;
   else if (s == "mg_coarse") ctx->opt_mg_coarse = (int)value;
   else if (s == "mg_slab_min_cells") {
     ctx->opt_mg_slab_min_cells = value;
@@ -292,7 +295,10 @@ int baorec_read_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm,
   for (int c = 0; c < 3 && n > 0; c++)
     BR_CUDA(cudaMemcpyAsync(dp + c * nn, hsrc[c], (size_t)n * sizeof(float), cudaMemcpyHostToDevice,
                             ctx->copy_stream));
+  BR_TRY(reset_oob(ctx, ctx->copy_stream));
   BR_CUDA(cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+  // ... and so does the tile sort of the uploaded positions (side stream, ordered after the copies)
+  BR_TRY(gather_prebin(ctx, dp, dp + nn, dp + 2 * nn, n, p->mas, ctx->copy_stream));
   {
     float *px, *py, *pz;
     BR_TRY(need_t(ctx, BUF_RX, ctx->M, &px));
@@ -308,7 +314,6 @@ int baorec_read_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm,
     }
     BR_CUDA(cudaEventRecord(ctx->ev[5], st));
     BR_CUDA(cudaStreamWaitEvent(st, ctx->ev_copy, 0));
-    BR_TRY(reset_oob(ctx, st));
     BR_TRY(gather3(ctx, px, py, pz, dp, dp + nn, dp + 2 * nn, n, dout, dout + nn, dout + 2 * nn, p->mas, field, p->f,
                    p->has_los, p->los, shifts_only ? 0 : 1, st));
     BR_TRY(check_oob(ctx, st, "read_shifts"));

@@ -288,6 +288,11 @@ static void destroy_plans(baorec_ctx* ctx) {
     cufftDestroy(ctx->p1d);
     ctx->have_dist_plans = false;
   }
+  if (ctx->chunk_planes) {
+    cufftDestroy(ctx->pc_r2c);
+    cufftDestroy(ctx->pc_c2r);
+    ctx->chunk_planes = 0;
+  }
 }
 
 int plan_common(baorec_ctx* ctx, int nx, int ny, int nz, const float L[3], const float mn[3]) {
@@ -358,6 +363,14 @@ int baorec_create(int device, baorec_ctx** out) {
   BR_CUDA(cudaMalloc(&ctx->d_minmax, 8 * sizeof(float)));
   BR_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   BR_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  BR_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+  BR_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 8; i++) {
+    BR_CUDA(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
+    BR_CUDA(cudaEventCreateWithFlags(&ctx->ev_a2a[i], cudaEventDisableTiming));
+  }
+  BR_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  BR_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   BR_CUDA(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
   for (int i = 0; i < 8; i++) BR_CUDA(cudaEventCreate(&ctx->ev[i]));
   *out = ctx;
@@ -392,6 +405,14 @@ int baorec_destroy(baorec_ctx* ctx) {
   for (auto e : ctx->prof_pool) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+  for (int i = 0; i < 8; i++) {
+    if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
+    if (ctx->ev_a2a[i]) cudaEventDestroy(ctx->ev_a2a[i]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
   delete ctx;
   return BAOREC_OK;

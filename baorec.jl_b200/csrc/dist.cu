@@ -30,8 +30,9 @@ namespace baorec {
 // Row copy between A[zl][y][x] and the per-peer blocks B[peer][zl][yl][x]  (y = peer*nyl + yl).
 template <bool TO_BLOCKS>
 __global__ void __launch_bounds__(128)
-rows_kernel(float2* __restrict__ dst, const float2* __restrict__ src, int nzl, int ny, int nyl, int xh) {
-  const unsigned row = blockIdx.x;  // zl * ny + y
+rows_kernel(float2* __restrict__ dst, const float2* __restrict__ src, int nzl, int ny, int nyl, int xh,
+            unsigned row0) {
+  const unsigned row = row0 + blockIdx.x;  // zl * ny + y
   const int zl = row / ny, y = row - zl * ny;
   const int peer = y / nyl, yl = y - peer * nyl;
   const size_t a = (size_t)row * xh;
@@ -213,8 +214,162 @@ static int dist_bufs(baorec_ctx* ctx, DistBufs* b) {
   return BAOREC_OK;
 }
 
+// ---- pipelined variants ------------------------------------------------------------------------------
+// chunk c of the all-to-all: planes [c nzc, (c+1) nzc) of every per-peer block (contiguous inside the block)
+static int all_to_all_chunk(baorec_ctx* ctx, const float2* S, float2* R, size_t blk, size_t off, size_t cnt,
+                            cudaStream_t st) {
+  const int P = ctx->nranks;
+  if (P == 1) {
+    BR_CUDA(cudaMemcpyAsync(R + off, S + off, cnt * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    return BAOREC_OK;
+  }
+  int pi = prof_begin(ctx, "nccl_all_to_all", st);
+  BR_NCCL(ncclGroupStart());
+  for (int peer = 0; peer < P; peer++) {
+    BR_NCCL(ncclSend(S + (size_t)peer * blk + off, cnt * 2, ncclFloat, peer, comm_of(ctx), st));
+    BR_NCCL(ncclRecv(R + (size_t)peer * blk + off, cnt * 2, ncclFloat, peer, comm_of(ctx), st));
+  }
+  BR_NCCL(ncclGroupEnd());
+  prof_end(ctx, pi, st);
+  return BAOREC_OK;
+}
+
+// number of chunks (0 = not pipelined) and the 2-D plans for nzl / chunks planes
+static int chunk_setup(baorec_ctx* ctx, int* chunks_out) {
+  *chunks_out = 0;
+  int C = ctx->opt_a2a_chunks;
+  if (ctx->p2p || C < 2) return BAOREC_OK;
+  if (C > 8) C = 8;
+  while (C > 1 && (ctx->nz_loc % C != 0)) C--;
+  if (C < 2) return BAOREC_OK;
+  const int nzc = ctx->nz_loc / C;
+  if (ctx->chunk_planes != nzc) {
+    if (ctx->chunk_planes) {
+      cufftDestroy(ctx->pc_r2c);
+      cufftDestroy(ctx->pc_c2r);
+      ctx->chunk_planes = 0;
+    }
+    size_t w[2] = {0, 0};
+    int n2[2] = {ctx->ny, ctx->nx};
+    BR_CUFFT(cufftCreate(&ctx->pc_r2c));
+    BR_CUFFT(cufftCreate(&ctx->pc_c2r));
+    ctx->chunk_planes = nzc;
+    BR_CUFFT(cufftSetAutoAllocation(ctx->pc_r2c, 0));
+    BR_CUFFT(cufftSetAutoAllocation(ctx->pc_c2r, 0));
+    BR_CUFFT(cufftMakePlanMany(ctx->pc_r2c, 2, n2, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, nzc, &w[0]));
+    BR_CUFFT(cufftMakePlanMany(ctx->pc_c2r, 2, n2, nullptr, 1, 0, nullptr, 1, 0, CUFFT_C2R, nzc, &w[1]));
+    const size_t wmax = w[0] > w[1] ? w[0] : w[1];
+    if (wmax > ctx->bufs[BUF_WORK].bytes) {
+      set_error("chunk plans need a larger cuFFT work area than the slab plans (%zu > %zu bytes)", wmax,
+                ctx->bufs[BUF_WORK].bytes);
+      return BAOREC_ERR_CUFFT;
+    }
+    BR_CUFFT(cufftSetWorkArea(ctx->pc_r2c, ctx->bufs[BUF_WORK].p));
+    BR_CUFFT(cufftSetWorkArea(ctx->pc_c2r, ctx->bufs[BUF_WORK].p));
+  }
+  *chunks_out = C;
+  return BAOREC_OK;
+}
+
+static int dist_r2c_pipelined(baorec_ctx* ctx, const float* slab, float2* T, int C, cudaStream_t st) {
+  DistBufs b;
+  BR_TRY(dist_bufs(ctx, &b));
+  const int P = ctx->nranks, nzl = ctx->nz_loc, nyl = ctx->ny_loc, ny = ctx->ny, xh = ctx->xh, nz = ctx->nz;
+  const int nzc = nzl / C;
+  const size_t rplane = (size_t)ny * ctx->nx, cplane = (size_t)ny * xh;
+  const size_t blk = (size_t)nzl * nyl * xh, cblk = (size_t)nzc * nyl * xh;
+  cudaStream_t cs = ctx->comm_stream;
+  BR_CUFFT(cufftSetStream(ctx->pc_r2c, st));
+  for (int c = 0; c < C; c++) {
+    int pi = prof_begin(ctx, "cufft_2d_r2c", st);
+    BR_CUFFT(cufftExecR2C(ctx->pc_r2c, (cufftReal*)(slab + (size_t)c * nzc * rplane),
+                          (cufftComplex*)(b.A + (size_t)c * nzc * cplane)));
+    prof_end(ctx, pi, st);
+    BR_LAUNCH(ctx, rows_kernel<true>, (unsigned)(nzc * ny), 128, 0, st, b.S, b.A, nzl, ny, nyl, xh,
+              (unsigned)(c * nzc * ny));
+    BR_CUDA(cudaEventRecord(ctx->ev_chunk[c], st));
+    BR_CUDA(cudaStreamWaitEvent(cs, ctx->ev_chunk[c], 0));
+    BR_TRY(all_to_all_chunk(ctx, b.S, b.R, blk, (size_t)c * cblk, cblk, cs));
+    BR_CUDA(cudaEventRecord(ctx->ev_a2a[c], cs));
+  }
+  ctx->n_fft++;
+  for (int c = 0; c < C; c++) {
+    BR_CUDA(cudaStreamWaitEvent(st, ctx->ev_a2a[c], 0));
+    // T[yl][x][s*nzl + zl] = R[s][zl][yl][x] for the planes zl of chunk c
+    TrGeom t;
+    t.rows = nzc;
+    t.cols = xh;
+    t.src_row_stride = (size_t)nyl * xh;
+    t.dst_row_stride = nz;
+    t.nb1 = nyl;
+    t.src_b0 = blk;
+    t.src_b1 = xh;
+    t.dst_b0 = nzl;
+    t.dst_b1 = (size_t)xh * nz;
+    dim3 grid(cdiv(xh, 32), cdiv(nzc, 32), P * nyl);
+    BR_LAUNCH(ctx, transpose_kernel, grid, 256, 0, st, T + (size_t)c * nzc, b.R + (size_t)c * cblk, t, PeerTab{}, 0,
+              (size_t)0);
+  }
+  BR_CUFFT(cufftSetStream(ctx->p1d, st));
+  int pi = prof_begin(ctx, "cufft_1d_z", st);
+  BR_CUFFT(cufftExecC2C(ctx->p1d, (cufftComplex*)T, (cufftComplex*)T, CUFFT_FORWARD));
+  prof_end(ctx, pi, st);
+  ctx->n_fft++;
+  return BAOREC_OK;
+}
+
+static int dist_c2r_pipelined(baorec_ctx* ctx, float2* T, float* slab, int C, cudaStream_t st) {
+  DistBufs b;
+  BR_TRY(dist_bufs(ctx, &b));
+  const int P = ctx->nranks, nzl = ctx->nz_loc, nyl = ctx->ny_loc, ny = ctx->ny, xh = ctx->xh, nz = ctx->nz;
+  const int nzc = nzl / C;
+  const size_t rplane = (size_t)ny * ctx->nx, cplane = (size_t)ny * xh;
+  const size_t blk = (size_t)nzl * nyl * xh, cblk = (size_t)nzc * nyl * xh;
+  cudaStream_t cs = ctx->comm_stream;
+  BR_CUFFT(cufftSetStream(ctx->p1d, st));
+  int pi = prof_begin(ctx, "cufft_1d_z", st);
+  BR_CUFFT(cufftExecC2C(ctx->p1d, (cufftComplex*)T, (cufftComplex*)T, CUFFT_INVERSE));
+  prof_end(ctx, pi, st);
+  ctx->n_fft++;
+  for (int c = 0; c < C; c++) {
+    // S[d][zl][yl][x] = T[yl][x][d*nzl + zl] for the planes zl of chunk c
+    TrGeom t;
+    t.rows = xh;
+    t.cols = nzc;
+    t.src_row_stride = nz;
+    t.dst_row_stride = (size_t)nyl * xh;
+    t.nb1 = nyl;
+    t.src_b0 = nzl;
+    t.src_b1 = (size_t)xh * nz;
+    t.dst_b0 = blk;
+    t.dst_b1 = xh;
+    dim3 grid(cdiv(nzc, 32), cdiv(xh, 32), P * nyl);
+    BR_LAUNCH(ctx, transpose_kernel, grid, 256, 0, st, b.S + (size_t)c * cblk, T + (size_t)c * nzc, t, PeerTab{}, 0,
+              (size_t)0);
+    BR_CUDA(cudaEventRecord(ctx->ev_chunk[c], st));
+    BR_CUDA(cudaStreamWaitEvent(cs, ctx->ev_chunk[c], 0));
+    BR_TRY(all_to_all_chunk(ctx, b.S, b.R, blk, (size_t)c * cblk, cblk, cs));
+    BR_CUDA(cudaEventRecord(ctx->ev_a2a[c], cs));
+  }
+  BR_CUFFT(cufftSetStream(ctx->pc_c2r, st));
+  for (int c = 0; c < C; c++) {
+    BR_CUDA(cudaStreamWaitEvent(st, ctx->ev_a2a[c], 0));
+    BR_LAUNCH(ctx, rows_kernel<false>, (unsigned)(nzc * ny), 128, 0, st, b.A, b.R, nzl, ny, nyl, xh,
+              (unsigned)(c * nzc * ny));
+    pi = prof_begin(ctx, "cufft_2d_c2r", st);
+    BR_CUFFT(cufftExecC2R(ctx->pc_c2r, (cufftComplex*)(b.A + (size_t)c * nzc * cplane),
+                          (cufftReal*)(slab + (size_t)c * nzc * rplane)));
+    prof_end(ctx, pi, st);
+  }
+  ctx->n_fft++;
+  return BAOREC_OK;
+}
+
 // slab[nz_loc][ny][nx] (real) -> T[ny_loc][xh][nz] (unnormalised forward transform)
 static int dist_r2c(baorec_ctx* ctx, const float* slab, float2* T, cudaStream_t st) {
+  int chunks = 0;
+  BR_TRY(chunk_setup(ctx, &chunks));
+  if (chunks >= 2) return dist_r2c_pipelined(ctx, slab, T, chunks, st);
   DistBufs b;
   BR_TRY(dist_bufs(ctx, &b));
   const int P = ctx->nranks, nzl = ctx->nz_loc, nyl = ctx->ny_loc, ny = ctx->ny, xh = ctx->xh, nz = ctx->nz;
@@ -234,7 +389,7 @@ static int dist_r2c(baorec_ctx* ctx, const float* slab, float2* T, cudaStream_t 
     BR_TRY(stream_barrier(ctx, st));
     Rsrc = ctx->own_recv[par];
   } else {
-    BR_LAUNCH(ctx, rows_kernel<true>, (unsigned)(nzl * ny), 128, 0, st, b.S, b.A, nzl, ny, nyl, xh);
+    BR_LAUNCH(ctx, rows_kernel<true>, (unsigned)(nzl * ny), 128, 0, st, b.S, b.A, nzl, ny, nyl, xh, 0u);
     BR_TRY(all_to_all(ctx, b.S, b.R, blk, st));
   }
   // T[yl][x][s*nzl + zl] = R[s][zl][yl][x]
@@ -260,6 +415,9 @@ static int dist_r2c(baorec_ctx* ctx, const float* slab, float2* T, cudaStream_t 
 
 // T[ny_loc][xh][nz] (destroyed) -> slab[nz_loc][ny][nx]; unnormalised inverse
 static int dist_c2r(baorec_ctx* ctx, float2* T, float* slab, cudaStream_t st) {
+  int chunks = 0;
+  BR_TRY(chunk_setup(ctx, &chunks));
+  if (chunks >= 2) return dist_c2r_pipelined(ctx, T, slab, chunks, st);
   DistBufs b;
   BR_TRY(dist_bufs(ctx, &b));
   const int P = ctx->nranks, nzl = ctx->nz_loc, nyl = ctx->ny_loc, ny = ctx->ny, xh = ctx->xh, nz = ctx->nz;
@@ -303,7 +461,7 @@ static int dist_c2r(baorec_ctx* ctx, float2* T, float* slab, cudaStream_t st) {
     BR_LAUNCH(ctx, transpose_kernel, grid, 256, 0, st, b.S, T, t, PeerTab{}, 0, (size_t)0);
     BR_TRY(all_to_all(ctx, b.S, b.R, blk, st));
   }
-  BR_LAUNCH(ctx, rows_kernel<false>, (unsigned)(nzl * ny), 128, 0, st, b.A, Rsrc, nzl, ny, nyl, xh);
+  BR_LAUNCH(ctx, rows_kernel<false>, (unsigned)(nzl * ny), 128, 0, st, b.A, Rsrc, nzl, ny, nyl, xh, 0u);
   BR_CUFFT(cufftSetStream(ctx->p2d_c2r, st));
   pi = prof_begin(ctx, "cufft_2d_c2r", st);
   BR_CUFFT(cufftExecC2R(ctx->p2d_c2r, (cufftComplex*)b.A, (cufftReal*)slab));
@@ -389,6 +547,11 @@ int baorec_plan_dist(baorec_ctx* ctx, int nx, int ny, int nz, const float box_si
   const int nzl = nz / P, nyl = ny / P;
   if (!ctx->have_dist_plans || s == 0 || ctx->nz_loc != nzl) {
     ctx->dlevels.clear();
+    if (ctx->chunk_planes) {
+      cufftDestroy(ctx->pc_r2c);
+      cufftDestroy(ctx->pc_c2r);
+      ctx->chunk_planes = 0;
+    }
     if (ctx->have_dist_plans) {
       cufftDestroy(ctx->p2d_r2c);
       cufftDestroy(ctx->p2d_c2r);
@@ -713,6 +876,13 @@ int baorec_read_shifts_dist_f32(baorec_ctx* ctx, const baorec_params* p, const f
   // the displacement slabs (+ halos) of the last run are kept across calls (data, then randoms, ...)
   const bool reuse = ctx->disp_valid && ctx->disp_algo == -1;
   ctx->disp_valid = false;
+  BR_TRY(reset_oob(ctx, st));
+  if (!reuse) {  // the tile sort of the catalog overlaps the three distributed transforms
+    ctx->slab_mode = 2;
+    int sp = gather_prebin(ctx, d_x, d_y, d_z, n_local, p->mas, st);
+    ctx->slab_mode = 0;
+    if (sp != BAOREC_OK) return sp;
+  }
   for (int c = 0; c < 3 && !reuse; c++) {
     BR_TRY(kpass_disp_T(ctx, keep, b.T, c, ctx->kcache_potential, st));
     BR_TRY(dist_c2r(ctx, b.T, psi[c] + plane, st));  // own planes at local index 1 .. nzl
@@ -720,7 +890,6 @@ int baorec_read_shifts_dist_f32(baorec_ctx* ctx, const baorec_params* p, const f
     BR_TRY(ring_exchange(ctx, psi[c] + (size_t)nzl * plane, next, psi[c], prev, plane, st));
     BR_TRY(ring_exchange(ctx, psi[c] + plane, prev, psi[c] + (size_t)(nzl + 1) * plane, next, 2 * plane, st));
   }
-  BR_TRY(reset_oob(ctx, st));
   ctx->slab_mode = 2;
   int s = gather3(ctx, psi[0], psi[1], psi[2], d_x, d_y, d_z, n_local, d_sx, d_sy, d_sz, p->mas, field, p->f,
                   p->has_los, p->los, positions, st);

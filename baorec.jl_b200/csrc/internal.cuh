@@ -148,6 +148,20 @@ struct baorec_ctx {
   float* d_minmax = nullptr;            // 6 floats for setup_box
   cudaStream_t own_stream = nullptr;    // used by host pipelines
   cudaStream_t copy_stream = nullptr;   // H2D uploads that overlap compute
+  // tile sort of the read-back catalog, forked onto side_stream so that it overlaps the
+  // displacement transforms (gather_prebin / gather3 in mas.cu)
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool prebin_valid = false;
+  const float *prebin_x = nullptr, *prebin_y = nullptr, *prebin_z = nullptr;
+  int64_t prebin_n = 0;
+  int prebin_mas = 0, prebin_slab_mode = 0;
+  void* prebin_rec = nullptr;
+  const unsigned* prebin_nvalid = nullptr;
+  const unsigned* prebin_starts = nullptr;
+  unsigned prebin_ntiles = 0;
+  unsigned* prebin_inv = nullptr;
+  int opt_overlap_sort = 0;  // measured: no gain on one GPU (the transforms already saturate HBM), off by default
   cudaEvent_t ev_copy = nullptr;
   cudaEvent_t ev[8] = {};
   float stage_ms[8] = {};
@@ -197,6 +211,13 @@ struct baorec_ctx {
   int slab_mode = 0;  // 0: whole mesh; 1: scatter into a slab (+1 ghost plane); 2: gather from a slab (+3 halo planes)
   cufftHandle p2d_r2c = 0, p2d_c2r = 0, p1d = 0;
   bool have_dist_plans = false;
+  // pipelined slab transposes: the local planes are processed in opt_a2a_chunks chunks so that the
+  // all-to-all of chunk c (comm_stream) overlaps the 2-D transforms / pack / unpack of its neighbours
+  cufftHandle pc_r2c = 0, pc_c2r = 0;
+  int chunk_planes = 0;  // planes per chunk the chunk plans were made for (0 = none)
+  int opt_a2a_chunks = 4;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_chunk[8] = {}, ev_a2a[8] = {};
 };
 
 namespace baorec {
@@ -222,6 +243,11 @@ int fft_c2r(baorec_ctx* ctx, float2* in, float* out, cudaStream_t st);
 // mas.cu
 int scatter(baorec_ctx* ctx, float* rho, float* x, float* y, float* z, const float* w, int64_t n, int wrap,
             int mas, cudaStream_t st);
+// Starts the tile sort of a read-back catalog on the side stream (ordered after everything already
+// queued on `st`); the next gather3 on the same arrays joins it instead of sorting.  A no-op for
+// catalogs / modes that do not use the tile gather.
+int gather_prebin(baorec_ctx* ctx, const float* x, const float* y, const float* z, int64_t n, int mas,
+                  cudaStream_t st);
 // mode: 0 disp, 1 rsd, 2 sum ; positions: write pos - shift
 int gather3(baorec_ctx* ctx, const float* fx, const float* fy, const float* fz, const float* x, const float* y,
             const float* z, int64_t n, float* ox, float* oy, float* oz, int mas, int field, float f, int has_los,

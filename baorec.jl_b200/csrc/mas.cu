@@ -858,6 +858,10 @@ static bool use_binning(const baorec_ctx* ctx, int64_t n) {
 
 int scatter(baorec_ctx* ctx, float* rho, float* x, float* y, float* z, const float* w, int64_t n, int wrap, int mas,
             cudaStream_t st) {
+  if (ctx->prebin_valid) {  // a forked read-back sort that was never joined (error path) owns the binning buffers
+    BR_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    ctx->prebin_valid = false;
+  }
   if (n == 0) return BAOREC_OK;
   BoxGeom g = geom_of(ctx);
   const bool tsc = mas == BAOREC_MAS_TSC;
@@ -877,9 +881,41 @@ int scatter(baorec_ctx* ctx, float* rho, float* x, float* y, float* z, const flo
   return BAOREC_OK;
 }
 
+int gather_prebin(baorec_ctx* ctx, const float* x, const float* y, const float* z, int64_t n, int mas,
+                  cudaStream_t st) {
+  ctx->prebin_valid = false;
+  if (!ctx->opt_overlap_sort || n == 0 || !use_binning(ctx, n) || !ctx->opt_gather_tiles || mas == BAOREC_MAS_TSC)
+    return BAOREC_OK;
+  BR_CUDA(cudaEventRecord(ctx->ev_fork, st));
+  BR_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+  BinResult b;
+  BR_TRY(bin_tiles(ctx, x, y, z, n, mas, ctx->side_stream, &b));
+  BR_CUDA(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+  ctx->prebin_x = x;
+  ctx->prebin_y = y;
+  ctx->prebin_z = z;
+  ctx->prebin_n = n;
+  ctx->prebin_mas = mas;
+  ctx->prebin_slab_mode = ctx->slab_mode;
+  ctx->prebin_rec = b.rec;
+  ctx->prebin_nvalid = b.n_valid;
+  ctx->prebin_starts = b.starts;
+  ctx->prebin_ntiles = b.ntiles;
+  ctx->prebin_inv = b.inv;
+  ctx->prebin_valid = true;
+  return BAOREC_OK;
+}
+
 int gather3(baorec_ctx* ctx, const float* fx, const float* fy, const float* fz, const float* x, const float* y,
             const float* z, int64_t n, float* ox, float* oy, float* oz, int mas, int field, float f, int has_los,
             const float* los, int positions, cudaStream_t st) {
+  const bool joined = ctx->prebin_valid && ctx->prebin_x == x && ctx->prebin_y == y && ctx->prebin_z == z &&
+                      ctx->prebin_n == n && ctx->prebin_mas == mas && ctx->prebin_slab_mode == ctx->slab_mode;
+  if (ctx->prebin_valid) {
+    // whatever happens next must be ordered after the forked sort (it owns the binning buffers)
+    BR_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    ctx->prebin_valid = false;
+  }
   if (n == 0) return BAOREC_OK;
   BoxGeom g = geom_of(ctx);
   GatherArgs a;
@@ -903,7 +939,13 @@ int gather3(baorec_ctx* ctx, const float* fx, const float* fy, const float* fz, 
   const bool tsc = mas == BAOREC_MAS_TSC;
   if (use_binning(ctx, n)) {
     BinResult b;
-    if (ctx->opt_gather_tiles) BR_TRY(bin_tiles(ctx, x, y, z, n, mas, st, &b));
+    if (joined) {
+      b.rec = (float4*)ctx->prebin_rec;
+      b.n_valid = ctx->prebin_nvalid;
+      b.starts = ctx->prebin_starts;
+      b.ntiles = ctx->prebin_ntiles;
+      b.inv = ctx->prebin_inv;
+    } else if (ctx->opt_gather_tiles) BR_TRY(bin_tiles(ctx, x, y, z, n, mas, st, &b));
     else BR_TRY(bin_particles<BIN_GATHER>(ctx, (float*)x, (float*)y, (float*)z, nullptr, n, 0, mas, st, &b));
     if (b.starts && !tsc) {
       TileGeom t;

@@ -136,7 +136,7 @@ def algorithmic_bytes(name, M, Mc, N):
     if "DispOp" in name:
         return 8 * Mc + 24 * Mc
     if "FusedLosOp" in name:
-        return 16 * Mc
+        return 24 * Mc                      # rho_k in, delta_k/M out for the C2R, delta_k kept for the read-back
     if name.startswith("kspace_kernel"):
         return 16 * Mc
     if name.startswith("axpy") or name.startswith("radial_update") or name.startswith("randoms_combine"):
@@ -279,6 +279,8 @@ def main():
         # strong scaling: the same 1e8-particle workload, sharded by z slab (each rank draws its
         # N/P particles inside its own slab; ownership re-checked with the library's own rule)
         B.dist.init_comm(ctx)
+        if os.environ.get("BAOREC_A2A_CHUNKS"):      # A/B knob: 1 = unpipelined slab transposes
+            ctx.set_option("a2a_chunks", int(os.environ["BAOREC_A2A_CHUNKS"]))
         B.dist.plan(ctx, grid, kw["box_size"], kw["box_min"])
         z_lo, nzl = B.dist.slab_range(ctx)
         cell = L / n
