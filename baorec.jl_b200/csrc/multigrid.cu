@@ -230,6 +230,14 @@ __device__ __forceinline__ void cp_async4(float* dst, const float* src) {
   unsigned d = (unsigned)__cvta_generic_to_shared(dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
 }
+// shared-space byte address + global byte pointer (the callers precompute per-thread offsets so that a
+// copy costs one 64-bit add and one 32-bit add instead of re-deriving both addresses from indices)
+__device__ __forceinline__ void cp_async16_raw(unsigned saddr, const char* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4_raw(unsigned saddr, const char* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -295,37 +303,41 @@ mg_stencil_smem(float* __restrict__ out, const float* __restrict__ v, const floa
   const int xl = xb == 0 ? nx - 1 : xb - 1, xr = xb + 4 * TX >= nx ? 0 : xb + 4 * TX;
   const int yl = yb == 0 ? ny - 1 : yb - 1, yr = yb + TY >= ny ? 0 : yb + TY;
 
-  // staging plan of this thread: its own row, plus a halo row for the threads of rows 0 and 1;
-  // left / right halo columns by the first / last thread of the row
+  // staging plan of this thread: the body of its own row, plus the body of a halo row for the
+  // threads of rows 0 and 1; the first / last thread of a row also copies the left / right halo
+  // column.  All offsets are precomputed as bytes: per copy one 64-bit add (global) and one
+  // 32-bit add (shared).
   const bool has_halo_row = ty < 2;
+  const bool is_edge = tx == 0 || tx == TX - 1;
   const int hy = ty == 0 ? yl : yr;
-  const unsigned src_own = (unsigned)iy * nx, src_halo = (unsigned)hy * nx;  // row offsets inside a plane
-  float* const d_own = sm + (ty + 1) * RS;
-  float* const d_halo = sm + (ty == 0 ? 0 : TY + 1) * RS;
-  float* const d_f = fsm + (ty * TX + tx) * 4;
+  const int xe = tx == 0 ? xl : xr;                       // global column of this thread's halo column
+  const int se = tx == 0 ? 3 : 4 + 4 * TX;                // its index in the staged row
+  const int hrow = ty == 0 ? 0 : TY + 1;
+  const unsigned g_own = ((unsigned)iy * nx + x0) * 4u, g_halo = ((unsigned)hy * nx + x0) * 4u;
+  const unsigned g_own_e = ((unsigned)iy * nx + xe) * 4u, g_halo_e = ((unsigned)hy * nx + xe) * 4u;
+  const unsigned s_base = (unsigned)__cvta_generic_to_shared(sm);
+  const unsigned s_own = s_base + ((ty + 1) * RS + 4 + 4 * tx) * 4u, s_halo = s_base + (hrow * RS + 4 + 4 * tx) * 4u;
+  const unsigned s_own_e = s_base + ((ty + 1) * RS + se) * 4u, s_halo_e = s_base + (hrow * RS + se) * 4u;
+  const unsigned s_f = s_base + (NS * PS + (ty * TX + tx) * 4) * 4u;
+  const unsigned PS4 = PS * 4u, FS4 = FS * 4u;
+  const size_t plane_bytes = plane * sizeof(float);
+  const float* const d_f = fsm + (ty * TX + tx) * 4;
   // real plane z (-1 .. nz) -> plane index in the buffer
   auto storage = [&](int z) { return g.slab ? z + 1 : (z < 0 ? z + nz : (z >= nz ? z - nz : z)); };
   // one copy group: the v window of plane z and the f tile of plane z-1 (what the step that reads
   // plane z as its upper plane needs); planes past zend are never read
   auto stage = [&](int z, int slot) {
     if (z <= zend) {
-      const float* pl = v + (size_t)storage(z) * plane;
-      const int so = slot * PS;
-      {
-        const float* srow = pl + src_own;
-        float* drow = d_own + so;
-        cp_async16(drow + 4 + 4 * tx, srow + x0);
-        if (tx == 0) cp_async4(drow + 3, srow + xl);
-        if (tx == TX - 1) cp_async4(drow + 4 + 4 * TX, srow + xr);
-      }
+      const char* pl = reinterpret_cast<const char*>(v) + (size_t)storage(z) * plane_bytes;
+      const unsigned so = slot * PS4;
+      cp_async16_raw(s_own + so, pl + g_own);
+      if (is_edge) cp_async4_raw(s_own_e + so, pl + g_own_e);
       if (has_halo_row) {
-        const float* srow = pl + src_halo;
-        float* drow = d_halo + so;
-        cp_async16(drow + 4 + 4 * tx, srow + x0);
-        if (tx == 0) cp_async4(drow + 3, srow + xl);
-        if (tx == TX - 1) cp_async4(drow + 4 + 4 * TX, srow + xr);
+        cp_async16_raw(s_halo + so, pl + g_halo);
+        if (is_edge) cp_async4_raw(s_halo_e + so, pl + g_halo_e);
       }
-      if (z > zbeg) cp_async16(d_f + slot * FS, f + (size_t)(z - 1 + g.slab) * plane + src_own + x0);
+      if (z > zbeg)
+        cp_async16_raw(s_f + slot * FS4, reinterpret_cast<const char*>(f) + (size_t)(z - 1 + g.slab) * plane_bytes + g_own);
     }
     cp_async_commit();
   };
