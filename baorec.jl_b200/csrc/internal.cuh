@@ -185,6 +185,7 @@ struct baorec_ctx {
   std::vector<baorec::MgLevel> levels;
   std::vector<baorec::MgLevel> dlevels;  // slab-decomposed hierarchy (baorec_plan_dist)
   int opt_mg_coarse = 1;  // levels of <= 4096 cells: the bottom of the V-cycle in one thread block
+  int opt_mg_bulk = 0;    // staged kernel: row bodies by TMA bulk copies; measured SLOWER than cp.async staging (554 vs 355 us), off
   int opt_mg_ring = 6;    // planes in the staged kernel's shared-memory ring (3 or 6)
   int opt_mg_kernel = 0;  // 0: staged shared-memory kernel where it applies; 1: register march; 2: generic
   int64_t opt_mg_slab_min_cells = 1 << 22;  // levels with fewer cells (128^3 and below) are replicated, not slab-decomposed

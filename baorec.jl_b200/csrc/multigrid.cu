@@ -243,6 +243,35 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+// ---- TMA bulk copies (cp.async.bulk, the 1-D mode of the copy engine: no tensor map) + mbarrier ----
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// one contiguous run of `bytes` (multiple of 16, both addresses 16-byte aligned) global -> shared,
+// completion reported to the mbarrier as transferred bytes
+__device__ __forceinline__ void bulk_g2s(unsigned saddr, const char* src, unsigned bytes, unsigned mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(saddr),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival when this thread's earlier cp.async copies have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(unsigned mbar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(mbar) : "memory");
+}
+
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -284,7 +313,16 @@ constexpr int MG_ZCHUNK_MAX = 64;
 // stream at full bandwidth; with two resident blocks (register-limited) NS = 3 keeps only
 // 2 x 2 x 5.4 KB in flight and the kernel sits at half the bandwidth (measured), NS = 6 keeps
 // 2 x 5 x 9.5 KB.
-template <int MODE, bool RADIAL, int NS>
+// BULK (tiles of 128 x 8 cells, i.e. levels with nx >= 128): the row bodies (512 B each: 10 rows of
+// v, 8 rows of f per plane) are copied by the TMA engine -- ONE cp.async.bulk warp instruction of
+// warp 0, one row per lane -- and the 20 halo-column scalars by one cp.async instruction of warp 1;
+// completion is tracked by one mbarrier per ring slot (transaction bytes + pre-counted cp.async
+// arrivals).  The other six warps issue no staging instructions at all (with per-thread cp.async
+// staging ~40 of ~270 issue slots per warp and z step go into copies, their addresses and the
+// LDGSTS scheduling bubbles).  MEASURED: correct, but slower than the cp.async path on B200
+// (512^3 radial sweep 554 vs 355 us, fixed LOS 490 vs 276 us): 18 bulk copies of 512 B per plane and
+// 256 threads polling an mbarrier cost more than they save.  Kept as option "mg_bulk", off.
+template <int MODE, bool RADIAL, int NS, bool BULK>
 __global__ void __launch_bounds__(256, 2)
 mg_stencil_smem(float* __restrict__ out, const float* __restrict__ v, const float* __restrict__ f, MgGeom g,
                 float omega, int zchunk) {
@@ -326,7 +364,57 @@ mg_stencil_smem(float* __restrict__ out, const float* __restrict__ v, const floa
   auto storage = [&](int z) { return g.slab ? z + 1 : (z < 0 ? z + nz : (z >= nz ? z - nz : z)); };
   // one copy group: the v window of plane z and the f tile of plane z-1 (what the step that reads
   // plane z as its upper plane needs); planes past zend are never read
+  // BULK staging plan (TX == 32, TY == 8): warp 0, lane l < TY+2 copies row l of the v window
+  // (0: halo row yl, 1..TY: rows yb.., TY+1: halo row yr), lanes TY+2 .. 2TY+1 the rows of f;
+  // warp 1, lane l < 2(TY+2) copies halo column (l & 1) of window row l >> 1
+  __shared__ __align__(8) unsigned long long mbar_store[BULK ? NS : 1];
+  const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(mbar_store);
+  const int tid = ty * TX + tx, lane = tid & 31, warp = tid >> 5;
+  const char* b_src = nullptr;   // warp 0: global row start at plane 0 of v (or f); warp 1: halo column element
+  unsigned b_dst = 0, b_stride = 0;
+  bool b_isf = false, b_on = false;
+  if (BULK) {
+    if (warp == 0 && lane < 2 * TY + 2) {
+      b_on = true;
+      b_isf = lane >= TY + 2;
+      const int r = b_isf ? lane - (TY + 2) : lane;
+      const int gy = b_isf ? yb + r : (r == 0 ? yl : (r == TY + 1 ? yr : yb + r - 1));
+      b_src = reinterpret_cast<const char*>(b_isf ? f : v) + ((size_t)gy * nx + xb) * 4u;
+      b_dst = b_isf ? s_base + (NS * PS + r * 4 * TX) * 4u : s_base + (r * RS + 4) * 4u;
+      b_stride = b_isf ? FS4 : PS4;
+    } else if (warp == 1 && lane < 2 * (TY + 2)) {
+      b_on = true;
+      const int r = lane >> 1, right = lane & 1;
+      const int gy = r == 0 ? yl : (r == TY + 1 ? yr : yb + r - 1);
+      b_src = reinterpret_cast<const char*>(v) + ((size_t)gy * nx + (right ? xr : xl)) * 4u;
+      b_dst = s_base + (r * RS + (right ? 4 + 4 * TX : 3)) * 4u;
+      b_stride = PS4;
+    }
+    if (tid == 0) {
+      for (int i = 0; i < NS; i++) mbar_init(mbar0 + 8 * i, 1 + 2 * (TY + 2));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
   auto stage = [&](int z, int slot) {
+    if (BULK) {
+      if (z <= zend && warp < 2) {
+        const unsigned mb = mbar0 + 8 * slot;
+        const bool with_f = z > zbeg;
+        if (warp == 0) {
+          if (lane == 0) mbar_expect_tx(mb, (unsigned)((TY + 2) + (with_f ? TY : 0)) * 4u * TX * 4u);
+          __syncwarp();
+          if (b_on && (with_f || !b_isf)) {
+            const size_t pidx = b_isf ? (size_t)(z - 1 + g.slab) : (size_t)storage(z);
+            bulk_g2s(b_dst + slot * b_stride, b_src + pidx * plane_bytes, 4u * TX * 4u, mb);
+          }
+        } else if (b_on) {
+          cp_async4_raw(b_dst + slot * b_stride, b_src + (size_t)storage(z) * plane_bytes);
+          cp_async_arrive_noinc(mb);
+        }
+      }
+      return;
+    }
     if (z <= zend) {
       const char* pl = reinterpret_cast<const char*>(v) + (size_t)storage(z) * plane_bytes;
       const unsigned so = slot * PS4;
@@ -373,7 +461,12 @@ mg_stencil_smem(float* __restrict__ out, const float* __restrict__ v, const floa
     idiag_c = 1.f / diag_c;
   }
 
-  cp_async_wait<NS - 2>();
+  if (BULK) {
+    mbar_wait(mbar0, 0);
+    mbar_wait(mbar0 + 8, 0);
+  } else {
+    cp_async_wait<NS - 2>();
+  }
   __syncthreads();
   Rows3 R0 = smem_rows3(sm + ty * RS, RS, tx, TX);       // plane zbeg-1 (slot 0)
   Rows3 R1 = smem_rows3(sm + PS + ty * RS, RS, tx, TX);  // plane zbeg   (slot 1)
@@ -383,17 +476,24 @@ mg_stencil_smem(float* __restrict__ out, const float* __restrict__ v, const floa
   const size_t rowoff = (size_t)iy * nx + x0;
   int cslot = 2 % NS;  // slot of plane iz+1
   int fslot = 1;       // slot of plane iz (free once this step's barrier is passed)
+  unsigned cpar = NS == 2 ? 1u : 0u;  // BULK: phase parity of the mbarrier of cslot (flips at every ring wrap)
 
   // one z step: A = plane iz-1, B = plane iz (registers); C = plane iz+1 is read from cslot;
   // plane iz+NS is staged into fslot
   auto step = [&](int iz, const Rows3& A, const Rows3& B, Rows3& C) {
-    cp_async_wait<NS - 2>();
+    if (BULK) mbar_wait(mbar0 + 8 * cslot, cpar);
+    else cp_async_wait<NS - 2>();
     __syncthreads();
     stage(iz + NS, fslot);
     C = smem_rows3(sm + cslot * PS + ty * RS, RS, tx, TX);
     const float4 fcur = *reinterpret_cast<const float4*>(d_f + cslot * FS);
     fslot = cslot;
-    cslot = cslot + 1 == NS ? 0 : cslot + 1;
+    if (cslot + 1 == NS) {
+      cslot = 0;
+      cpar ^= 1u;
+    } else {
+      cslot = cslot + 1;
+    }
     const size_t o = (size_t)(iz + g.slab) * plane + rowoff;
     float pzz2 = 0.f, hpyz, byz = 0.f, s_yz2 = 0.f;
     if (RADIAL) {
@@ -467,7 +567,7 @@ mg_stencil_smem(float* __restrict__ out, const float* __restrict__ v, const floa
     if (iz + 1 < zend) step(iz + 1, R1, R2, R0);
     if (iz + 2 < zend) step(iz + 2, R2, R0, R1);
   }
-  cp_async_wait<0>();
+  if (!BULK) cp_async_wait<0>();
 }
 
 // ---- restriction (reduce!, src/multigrid.jl:520-584): coarse c <- fine 2c+1, weights 8/4/2/1 /64
@@ -764,23 +864,31 @@ static int launch_stencil(baorec_ctx* ctx, float* out, const float* v, const flo
     dim3 grid(g.nx / (4 * stx), g.ny / sty, cdiv(g.nz, zchunk));
     dim3 block(stx, sty);
     const int NS = ctx->opt_mg_ring == 3 ? 3 : 6;
+    const bool bulk = ctx->opt_mg_bulk && NS == 6 && stx == 32 && sty == 8;
     const size_t smem =
         ((size_t)NS * ((sty + 2) * (4 * stx + 8) + sty * 4 * stx) + MG_ZCHUNK_MAX) * sizeof(float);
     static bool attr = false;
     if (!attr) {
       const int big = 100 * 1024;
-      cudaFuncSetAttribute(mg_stencil_smem<MG_JACOBI, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-      cudaFuncSetAttribute(mg_stencil_smem<MG_JACOBI, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-      cudaFuncSetAttribute(mg_stencil_smem<MG_RESIDUAL, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-      cudaFuncSetAttribute(mg_stencil_smem<MG_RESIDUAL, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      cudaFuncSetAttribute(mg_stencil_smem<MG_JACOBI, true, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      cudaFuncSetAttribute(mg_stencil_smem<MG_JACOBI, false, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      cudaFuncSetAttribute(mg_stencil_smem<MG_RESIDUAL, true, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      cudaFuncSetAttribute(mg_stencil_smem<MG_RESIDUAL, false, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      cudaFuncSetAttribute(mg_stencil_smem<MG_JACOBI, true, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      cudaFuncSetAttribute(mg_stencil_smem<MG_JACOBI, false, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      cudaFuncSetAttribute(mg_stencil_smem<MG_RESIDUAL, true, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      cudaFuncSetAttribute(mg_stencil_smem<MG_RESIDUAL, false, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
       attr = true;
     }
     if (NS == 3) {
-      if (g.radial) BR_LAUNCH(ctx, (mg_stencil_smem<MODE, true, 3>), grid, block, smem, st, out, v, f, g, omega, zchunk);
-      else BR_LAUNCH(ctx, (mg_stencil_smem<MODE, false, 3>), grid, block, smem, st, out, v, f, g, omega, zchunk);
+      if (g.radial) BR_LAUNCH(ctx, (mg_stencil_smem<MODE, true, 3, false>), grid, block, smem, st, out, v, f, g, omega, zchunk);
+      else BR_LAUNCH(ctx, (mg_stencil_smem<MODE, false, 3, false>), grid, block, smem, st, out, v, f, g, omega, zchunk);
+    } else if (bulk) {
+      if (g.radial) BR_LAUNCH(ctx, (mg_stencil_smem<MODE, true, 6, true>), grid, block, smem, st, out, v, f, g, omega, zchunk);
+      else BR_LAUNCH(ctx, (mg_stencil_smem<MODE, false, 6, true>), grid, block, smem, st, out, v, f, g, omega, zchunk);
     } else {
-      if (g.radial) BR_LAUNCH(ctx, (mg_stencil_smem<MODE, true, 6>), grid, block, smem, st, out, v, f, g, omega, zchunk);
-      else BR_LAUNCH(ctx, (mg_stencil_smem<MODE, false, 6>), grid, block, smem, st, out, v, f, g, omega, zchunk);
+      if (g.radial) BR_LAUNCH(ctx, (mg_stencil_smem<MODE, true, 6, false>), grid, block, smem, st, out, v, f, g, omega, zchunk);
+      else BR_LAUNCH(ctx, (mg_stencil_smem<MODE, false, 6, false>), grid, block, smem, st, out, v, f, g, omega, zchunk);
     }
     return BAOREC_OK;
   }
