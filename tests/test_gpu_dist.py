@@ -23,9 +23,13 @@ def dctx(B):
     ctx.plan_key = None       # force a fresh single-GPU plan for whoever comes next
 
 
-@pytest.mark.parametrize("shape", [(32, 32, 32), (48, 32, 16), (64, 64, 64)])
-def test_dist_fft_roundtrip_and_matches_rfftn(B, dctx, shape):
+@pytest.mark.parametrize("chunks", [4, 1, 3])
+@pytest.mark.parametrize("shape", [(32, 32, 32), (48, 32, 16), (64, 64, 64), (64, 32, 48)])
+def test_dist_fft_roundtrip_and_matches_rfftn(B, dctx, shape, chunks):
+    """Slab transforms, pipelined in `chunks` plane chunks (1 = unpipelined; a chunk count that does
+    not divide the local planes falls back to the next smaller one)."""
     nx, ny, nz = shape
+    dctx.set_option("a2a_chunks", chunks)
     B.dist.plan(dctx, shape, np.full(3, 100.0, np.float32), np.zeros(3, np.float32))
     rng = np.random.default_rng(0)
     a = rng.standard_normal((nz, ny, nx)).astype(np.float32)
@@ -35,6 +39,7 @@ def test_dist_fft_roundtrip_and_matches_rfftn(B, dctx, shape):
     assert rel_rms(got.real, ref.real) < 1e-5 and rel_rms(got.imag, ref.imag) < 1e-5
     back = torch.empty((nz, ny, nx), dtype=torch.float32, device="cuda")
     B.dist.dist_c2r(dctx, T, back)
+    dctx.set_option("a2a_chunks", 4)
     assert rel_rms(back.cpu().numpy() / a.size, a) < 1e-5
 
 
