@@ -180,6 +180,11 @@ int baorec_set_option(baorec_ctx* ctx, const char* name, int64_t value) {
   else if (s == "own_fft") ctx->opt_own_fft = (int)value;
   else if (s == "fft_split_planes") ctx->opt_fft_split = (int)value;
   else if (s == "gather_tiles") ctx->opt_gather_tiles = (int)value;
+  else if (s == "scatter_tiles") ctx->opt_scatter_tiles = (int)value;
+  else if (s == "unified_sort") {
+    ctx->opt_unified_sort = (int)value;
+    ctx->sortc_valid = false;
+  }
   else if (s == "bin_zg_scatter") ctx->opt_zg_scatter = (int)value;
   else if (s == "bin_zg_gather") ctx->opt_zg_gather = (int)value;
   else if (s == "mg_kernel") ctx->opt_mg_kernel = (int)value;
@@ -290,6 +295,14 @@ int baorec_read_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm,
   size_t nn = (size_t)(n > 0 ? n : 1);
   BR_TRY(need_t(ctx, BUF_OUT, nn * 6, &dout));
   dp = dout + 3 * nn;
+  // A catalog of the size run! scattered is uploaded to the very device arrays run! used (x, y, z at
+  // stride n in BUF_PART): if it is the same catalog -- decided by the content hash in gather3 --
+  // the tile sort made for the scatter is reused instead of sorting again.
+  if (ctx->sortc_valid && ctx->sortc_n == n && n > 0 && ctx->sortc_x == (const float*)ctx->bufs[BUF_PART].p &&
+      ctx->bufs[BUF_PART].bytes >= (size_t)n * 4 * sizeof(float)) {
+    dp = (float*)ctx->bufs[BUF_PART].p;
+    nn = (size_t)n;
+  }
   BR_CUDA(cudaEventRecord(ctx->ev[4], st));
   const float* hsrc[3] = {h_x, h_y, h_z};
   // the upload of the positions (copy stream) overlaps the displacement-mesh transforms (main stream)

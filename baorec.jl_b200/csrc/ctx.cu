@@ -257,6 +257,7 @@ int gauss_tables(baorec_ctx* ctx, float R, const double** gx, const double** gy,
 
 static int upload_tables(baorec_ctx* ctx) {
   ctx->gauss_valid = false;
+  ctx->sortc_valid = false;  // tile keys depend on the box
   int n[3] = {ctx->nx, ctx->ny, ctx->nz};
   for (int a = 0; a < 3; a++) {
     std::vector<float> k, x;
@@ -360,6 +361,7 @@ int baorec_create(int device, baorec_ctx** out) {
   BR_CUDA(cudaMalloc(&ctx->d_oob, 2 * sizeof(unsigned long long)));  // [0] out-of-box, [1] positions wrapped
   BR_CUDA(cudaMemset(ctx->d_oob, 0, 2 * sizeof(unsigned long long)));
   BR_CUDA(cudaMalloc(&ctx->d_scal, 16 * sizeof(double)));
+  BR_CUDA(cudaMalloc(&ctx->d_hash, 4 * sizeof(unsigned long long)));
   BR_CUDA(cudaMalloc(&ctx->d_minmax, 8 * sizeof(float)));
   BR_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   BR_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -395,6 +397,7 @@ int baorec_destroy(baorec_ctx* ctx) {
   if (ctx->d_gauss) cudaFree(ctx->d_gauss);
   if (ctx->d_oob) cudaFree(ctx->d_oob);
   if (ctx->d_scal) cudaFree(ctx->d_scal);
+  if (ctx->d_hash) cudaFree(ctx->d_hash);
   if (ctx->d_minmax) cudaFree(ctx->d_minmax);
   for (int i = 0; i < 8; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -480,6 +483,8 @@ int64_t baorec_scratch_bytes(const baorec_ctx* ctx) {
   for (int i = 0; i < BUF_COUNT; i++) t += (int64_t)ctx->bufs[i].bytes;
   return t;
 }
+
+int64_t baorec_sort_reuse_count(const baorec_ctx* ctx) { return ctx ? ctx->n_sort_reuse : 0; }
 
 int baorec_launch_counts(const baorec_ctx* ctx, int64_t* kernels, int64_t* fft_execs) {
   BR_REQUIRE(ctx != nullptr, "ctx is NULL");

@@ -174,6 +174,18 @@ struct baorec_ctx {
   int opt_keep_delta_k = 1;    // device API: keep delta_k of the last reconstructed_overdensity! result    // set by the host pipeline around the solve
   int64_t opt_bin_min_particles = 1 << 18;  // catalogs at least this large are z-binned first
   int opt_fuse_kspace = 1;
+  int opt_scatter_tiles = 0;   // scatter: (z, y/8, x/128) tile order instead of z slabs
+  // Unified sort: run! sorts the catalog ONCE into the gather's tile order (records x,y,z,w + inverse
+  // permutation + a 64-bit content hash of the wrapped positions); the scatter deposits in that order
+  // and a read-back of the same, unmodified position arrays (same pointers, same count, same hash --
+  // recomputed from the arrays on every read) reuses it instead of sorting again.
+  int opt_unified_sort = 1;
+  bool sortc_valid = false;
+  const float *sortc_x = nullptr, *sortc_y = nullptr, *sortc_z = nullptr;
+  int64_t sortc_n = 0;
+  unsigned sortc_ntiles = 0;
+  unsigned long long* d_hash = nullptr;  // [0] hash at sort time, [1] hash at read time, [2] match flag
+  int64_t n_sort_reuse = 0;              // read-backs that reused the run!'s sort (diagnostics)
   int opt_gather_tiles = 1;    // gather: fine (z, y/8, x/128) tile binning instead of z slabs
   int opt_zg_scatter = 0, opt_zg_gather = 0;  // z planes per bin (0 = auto)     // fixed-LOS iterations folded into one k-space pass
   int64_t last_wrapped = 0;  // particles whose position cic! wrapped in the last scatter

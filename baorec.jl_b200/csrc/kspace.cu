@@ -337,8 +337,9 @@ int setup_overdensity_into(baorec_ctx* ctx, const baorec_params* p, float* mesh,
     float* ran;
     BR_TRY(need_t(ctx, BUF_RAN, ctx->M, &ran));
     BR_CUDA(cudaMemsetAsync(ran, 0, ctx->M * sizeof(float), st));
-    BR_TRY(scatter(ctx, mesh, x, y, z, w, n, 0, p->mas, st));
+    // randoms first: the sort kept for the read-back is then the data catalog's (unified sort)
     BR_TRY(scatter(ctx, ran, rx, ry, rz, rw, nr, 0, p->mas, st));
+    BR_TRY(scatter(ctx, mesh, x, y, z, w, n, 0, p->mas, st));
     GaussOp op{ck0, gt, 1.0 / (double)ctx->M};
     BR_TRY(fft_r2c(ctx, mesh, ck0, st));
     BR_LAUNCH(ctx, stash_dc_kernel, 1, 1, 0, st, ck0, ctx->d_scal, 0, 1.0);

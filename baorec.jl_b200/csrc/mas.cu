@@ -531,6 +531,60 @@ struct TileGeom {
   unsigned ntiles;    // nz * nyc * nxc  (the trash bin has index ntiles)
 };
 
+// Scatter flavour (option "scatter_tiles"): the same tile order for the deposit -- the 8 atomics of
+// a warp's particles then fall into one 2 x 9 x 129-cell window instead of anywhere in a 2-plane
+// slab.  Key from cic!'s own cell (src/mas.jl:13-35) of the wrapped position, which is returned.
+__device__ __forceinline__ unsigned tile_key_scatter(float& px, float& py, float& pz, const BoxGeom& g,
+                                                     const TileGeom& t, int wrap, bool& wrapped) {
+  wrapped = false;
+  if (wrap) {
+    float qx = wrap_pos(px, g.mn[0], g.L[0]), qy = wrap_pos(py, g.mn[0], g.L[0]), qz = wrap_pos(pz, g.mn[0], g.L[0]);
+    wrapped = (qx != px) || (qy != py) || (qz != pz);
+    px = qx;
+    py = qy;
+    pz = qz;
+  }
+  int ix, iy, iz, i1;
+  float w0, w1;
+  bool ok = cic_axis(px, g.mn[0], g.L[0], g.n[0], wrap, ix, i1, w0, w1);
+  ok = cic_axis(py, g.mn[1], g.L[1], g.n[1], wrap, iy, i1, w0, w1) && ok;
+  ok = cic_axis(pz, g.mn[2], g.L[2], g.n[2], wrap, iz, i1, w0, w1) && ok;
+  ok = ok && local_planes(g, iz, i1, iz, i1);
+  if (!ok) return t.ntiles;
+  return ((unsigned)iz * t.nyc + (unsigned)(iy / TILE_Y)) * t.nxc + (unsigned)(ix / TILE_X);
+}
+
+__global__ void __launch_bounds__(256)
+tile_count_scatter_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z,
+                          int64_t n, BoxGeom g, TileGeom t, int wrap, unsigned* __restrict__ counts) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float px = x[i], py = y[i], pz = z[i];
+  bool wr;
+  atomicAdd(counts + tile_key_scatter(px, py, pz, g, t, wrap, wr), 1u);
+}
+
+// records (x, y, z, w) in tile order; wrapped positions are written back like cic! does (src/mas.jl:57-59)
+__global__ void __launch_bounds__(256)
+tile_reorder_scatter_kernel(float* __restrict__ x, float* __restrict__ y, float* __restrict__ z,
+                            const float* __restrict__ w, int64_t n, BoxGeom g, TileGeom t, int wrap,
+                            unsigned* __restrict__ cursor, float4* __restrict__ rec, unsigned long long* oob) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float px = x[i], py = y[i], pz = z[i];
+  const float ox = px, oy = py, oz = pz;
+  bool wr;
+  unsigned k = tile_key_scatter(px, py, pz, g, t, wrap, wr);
+  if (wr) {
+    if (px != ox) x[i] = px;
+    if (py != oy) y[i] = py;
+    if (pz != oz) z[i] = pz;
+    atomicAdd(oob + 1, 1ULL);
+  }
+  unsigned dst = atomicAdd(cursor + k, 1u);
+  rec[dst] = make_float4(px, py, pz, w[i]);
+}
+
 template <int MAS>
 __device__ __forceinline__ unsigned tile_key(float px, float py, float pz, const BoxGeom& g, const TileGeom& t) {
   int ix, iy, iz;
@@ -554,6 +608,90 @@ __device__ __forceinline__ unsigned tile_key(float px, float py, float pz, const
   }
   if (!ok) return t.ntiles;
   return ((unsigned)iz * t.nyc + (unsigned)(iy / TILE_Y)) * t.nxc + (unsigned)(ix / TILE_X);
+}
+
+// ---- unified sort (run! sorts once, the read-back of the same catalog reuses it) -----------------
+// Order-independent 64-bit content hash of a catalog: sum over particles of a mixed (index, x, y, z).
+__device__ __forceinline__ unsigned long long mix64(unsigned long long v) {  // splitmix64 finaliser
+  v ^= v >> 30;
+  v *= 0xbf58476d1ce4e5b9ULL;
+  v ^= v >> 27;
+  v *= 0x94d049bb133111ebULL;
+  v ^= v >> 31;
+  return v;
+}
+__device__ __forceinline__ unsigned long long particle_hash(int64_t i, float px, float py, float pz) {
+  unsigned long long a = (unsigned long long)__float_as_uint(px) | ((unsigned long long)__float_as_uint(py) << 32);
+  unsigned long long b = (unsigned long long)__float_as_uint(pz) ^ ((unsigned long long)(i + 1) * 0x9e3779b97f4a7c15ULL);
+  return mix64(a ^ mix64(b));
+}
+__device__ __forceinline__ void hash_accumulate(unsigned long long h, unsigned long long* __restrict__ dst) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) h += __shfl_down_sync(0xffffffffu, h, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(dst, h);
+}
+
+__global__ void __launch_bounds__(256)
+usort_count_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z, int64_t n,
+                   BoxGeom g, TileGeom t, int wrap, unsigned* __restrict__ counts) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float px = x[i], py = y[i], pz = z[i];
+  if (wrap) {  // cic!'s upper-face wrap (src/mas.jl:8-10); the key is the gather's tile of the wrapped position
+    px = wrap_pos(px, g.mn[0], g.L[0]);
+    py = wrap_pos(py, g.mn[0], g.L[0]);
+    pz = wrap_pos(pz, g.mn[0], g.L[0]);
+  }
+  atomicAdd(counts + tile_key<BAOREC_MAS_CIC>(px, py, pz, g, t), 1u);
+}
+
+// records (x, y, z, w) in the gather's tile order + inverse permutation + content hash of the
+// (wrapped, written-back) positions
+__global__ void __launch_bounds__(256)
+usort_reorder_kernel(float* __restrict__ x, float* __restrict__ y, float* __restrict__ z, const float* __restrict__ w,
+                     int64_t n, BoxGeom g, TileGeom t, int wrap, unsigned* __restrict__ cursor,
+                     float4* __restrict__ rec, unsigned* __restrict__ inv, unsigned long long* __restrict__ oob,
+                     unsigned long long* __restrict__ hash) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long h = 0;
+  if (i < n) {
+    float px = x[i], py = y[i], pz = z[i];
+    if (wrap) {
+      const float ox = px, oy = py, oz = pz;
+      px = wrap_pos(px, g.mn[0], g.L[0]);
+      py = wrap_pos(py, g.mn[0], g.L[0]);
+      pz = wrap_pos(pz, g.mn[0], g.L[0]);
+      if (px != ox) x[i] = px;  // write-back like the reference (src/mas.jl:57-59)
+      if (py != oy) y[i] = py;
+      if (pz != oz) z[i] = pz;
+      if (px != ox || py != oy || pz != oz) atomicAdd(oob + 1, 1ULL);
+    }
+    unsigned dst = atomicAdd(cursor + tile_key<BAOREC_MAS_CIC>(px, py, pz, g, t), 1u);
+    rec[dst] = make_float4(px, py, pz, w[i]);
+    inv[i] = dst;
+    h = particle_hash(i, px, py, pz);
+  }
+  hash_accumulate(h, hash);
+}
+
+__global__ void __launch_bounds__(256)
+hash_positions_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z, int64_t n,
+                      unsigned long long* __restrict__ hash) {
+  unsigned long long h = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    h += particle_hash(i, x[i], y[i], z[i]);
+  hash_accumulate(h, hash);
+}
+__global__ void hash_compare_kernel(unsigned long long* h) { h[2] = h[0] == h[1] ? 1ULL : 0ULL; }
+
+// deposit every record (the order is the gather's; validity is cic!'s own: src/mas.jl:33-35)
+__global__ void __launch_bounds__(256)
+scatter_records_kernel(float* __restrict__ rho, const float4* __restrict__ rec, int64_t n, BoxGeom g, int wrap,
+                       unsigned long long* __restrict__ oob) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = rec[i];
+  if (!deposit<BAOREC_MAS_CIC>(rho, p.x, p.y, p.z, p.w, g, wrap != 0)) atomicAdd(oob, 1ULL);
 }
 
 template <int MAS>
@@ -852,6 +990,109 @@ static int bin_tiles(baorec_ctx* ctx, const float* x, const float* y, const floa
   return BAOREC_OK;
 }
 
+// Tile order for the scatter (CIC).  Asynchronous.
+static int bin_tiles_scatter(baorec_ctx* ctx, float* x, float* y, float* z, const float* w, int64_t n, int wrap,
+                             cudaStream_t st, BinResult* out) {
+  BoxGeom g = geom_of(ctx);
+  TileGeom t;
+  t.nxc = (ctx->nx + TILE_X - 1) / TILE_X;
+  t.nyc = (ctx->ny + TILE_Y - 1) / TILE_Y;
+  t.ntiles = (unsigned)g.nzp * t.nyc * t.nxc;
+  const unsigned m = t.ntiles + 1;  // + trash bin
+  const unsigned nsb = cdiv(m, SCAN_CHUNK);
+  unsigned* cnt;
+  float4* rec;
+  BR_TRY(need_t(ctx, BUF_BINTMP, (size_t)3 * m + nsb + 16, &cnt));
+  BR_TRY(need_t(ctx, BUF_BINIDX, (size_t)n, &rec));
+  unsigned* cursor = cnt + m;
+  unsigned* starts = cursor + m;
+  unsigned* sums = starts + m + 1;
+  unsigned* total = sums + nsb;
+  BR_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * m, st));
+  const unsigned grid = cdiv((size_t)n, 256);
+  BR_LAUNCH(ctx, tile_count_scatter_kernel, grid, 256, 0, st, x, y, z, n, g, t, wrap, cnt);
+  BR_LAUNCH(ctx, scan_partial_kernel, nsb, 256, 0, st, cnt, sums, m);
+  BR_LAUNCH(ctx, scan_sums_kernel, 1, 32, 0, st, sums, nsb, total);
+  BR_LAUNCH(ctx, scan_final_kernel, nsb, 256, 0, st, cnt, sums, cursor, starts, m);
+  BR_LAUNCH(ctx, add_oob_kernel, 1, 1, 0, st, cnt + t.ntiles, ctx->d_oob);
+  BR_LAUNCH(ctx, tile_reorder_scatter_kernel, grid, 256, 0, st, x, y, z, w, n, g, t, wrap, cursor, rec, ctx->d_oob);
+  out->rec = rec;
+  out->n_valid = starts + t.ntiles;
+  return BAOREC_OK;
+}
+
+struct TileScratch {
+  unsigned *cnt, *cursor, *starts, *sums, *total;
+  unsigned m, nsb;
+};
+static int tile_scratch(baorec_ctx* ctx, const TileGeom& t, TileScratch* s) {
+  s->m = t.ntiles + 1;  // + trash bin
+  s->nsb = cdiv(s->m, SCAN_CHUNK);
+  BR_TRY(need_t(ctx, BUF_BINTMP, (size_t)3 * s->m + s->nsb + 16, &s->cnt));
+  s->cursor = s->cnt + s->m;
+  s->starts = s->cursor + s->m;  // m + 1 entries: starts[m] = n
+  s->sums = s->starts + s->m + 1;
+  s->total = s->sums + s->nsb;
+  return BAOREC_OK;
+}
+
+// run!'s sort: the catalog into the gather's tile order, once (see opt_unified_sort).  Asynchronous.
+static int unified_sort(baorec_ctx* ctx, float* x, float* y, float* z, const float* w, int64_t n, int wrap,
+                        cudaStream_t st, BinResult* out) {
+  ctx->sortc_valid = false;
+  BoxGeom g = geom_of(ctx);
+  TileGeom t;
+  t.nxc = (ctx->nx + TILE_X - 1) / TILE_X;
+  t.nyc = (ctx->ny + TILE_Y - 1) / TILE_Y;
+  t.ntiles = (unsigned)g.nzp * t.nyc * t.nxc;
+  TileScratch sc;
+  BR_TRY(tile_scratch(ctx, t, &sc));
+  float4* rec;
+  unsigned* inv;
+  BR_TRY(need_t(ctx, BUF_BINIDX, (size_t)n, &rec));
+  BR_TRY(need_t(ctx, BUF_BININV, (size_t)n, &inv));
+  BR_CUDA(cudaMemsetAsync(sc.cnt, 0, sizeof(unsigned) * sc.m, st));
+  BR_CUDA(cudaMemsetAsync(ctx->d_hash, 0, sizeof(unsigned long long), st));
+  const unsigned grid = cdiv((size_t)n, 256);
+  BR_LAUNCH(ctx, usort_count_kernel, grid, 256, 0, st, x, y, z, n, g, t, wrap, sc.cnt);
+  BR_LAUNCH(ctx, scan_partial_kernel, sc.nsb, 256, 0, st, sc.cnt, sc.sums, sc.m);
+  BR_LAUNCH(ctx, scan_sums_kernel, 1, 32, 0, st, sc.sums, sc.nsb, sc.total);
+  BR_LAUNCH(ctx, scan_final_kernel, sc.nsb, 256, 0, st, sc.cnt, sc.sums, sc.cursor, sc.starts, sc.m);
+  BR_LAUNCH(ctx, usort_reorder_kernel, grid, 256, 0, st, x, y, z, w, n, g, t, wrap, sc.cursor, rec, inv, ctx->d_oob,
+            ctx->d_hash);
+  out->rec = rec;
+  out->n_valid = sc.starts + t.ntiles;
+  out->starts = sc.starts;
+  out->ntiles = t.ntiles;
+  out->inv = inv;
+  ctx->sortc_x = x;
+  ctx->sortc_y = y;
+  ctx->sortc_z = z;
+  ctx->sortc_n = n;
+  ctx->sortc_ntiles = t.ntiles;
+  ctx->sortc_valid = true;
+  return BAOREC_OK;
+}
+
+// Does the sort kept by the last scatter describe exactly these arrays?  Pointers, count and a content
+// hash recomputed from the arrays (one 12 B/particle streaming pass + a 4-byte read-back).
+static int sort_cache_hit(baorec_ctx* ctx, const float* x, const float* y, const float* z, int64_t n, cudaStream_t st,
+                          bool* hit) {
+  *hit = false;
+  if (!ctx->sortc_valid || ctx->slab_mode != 0 || ctx->sortc_x != x || ctx->sortc_y != y || ctx->sortc_z != z ||
+      ctx->sortc_n != n)
+    return BAOREC_OK;
+  BR_CUDA(cudaMemsetAsync(ctx->d_hash + 1, 0, sizeof(unsigned long long), st));
+  unsigned grid = cdiv((size_t)n, 256 * 8);
+  BR_LAUNCH(ctx, hash_positions_kernel, grid, 256, 0, st, x, y, z, n, ctx->d_hash + 1);
+  BR_LAUNCH(ctx, hash_compare_kernel, 1, 1, 0, st, ctx->d_hash);
+  unsigned long long flag = 0;
+  BR_CUDA(cudaMemcpyAsync(&flag, ctx->d_hash + 2, sizeof(flag), cudaMemcpyDeviceToHost, st));
+  BR_CUDA(cudaStreamSynchronize(st));
+  *hit = flag != 0;
+  return BAOREC_OK;
+}
+
 static bool use_binning(const baorec_ctx* ctx, int64_t n) {
   return n >= ctx->opt_bin_min_particles && n < ((int64_t)1 << 32) && ctx->nz >= 8;
 }
@@ -865,9 +1106,17 @@ int scatter(baorec_ctx* ctx, float* rho, float* x, float* y, float* z, const flo
   if (n == 0) return BAOREC_OK;
   BoxGeom g = geom_of(ctx);
   const bool tsc = mas == BAOREC_MAS_TSC;
+  if (use_binning(ctx, n) && ctx->opt_unified_sort && !tsc && ctx->slab_mode == 0 && ctx->opt_gather_tiles) {
+    BinResult b;
+    BR_TRY(unified_sort(ctx, x, y, z, w, n, wrap, st, &b));
+    BR_LAUNCH(ctx, scatter_records_kernel, cdiv((size_t)n, 256), 256, 0, st, rho, b.rec, n, g, wrap, ctx->d_oob);
+    return BAOREC_OK;
+  }
+  ctx->sortc_valid = false;  // the paths below reuse the binning buffers
   if (use_binning(ctx, n)) {
     BinResult b;
-    BR_TRY(bin_particles<BIN_SCATTER>(ctx, x, y, z, w, n, wrap, mas, st, &b));
+    if (ctx->opt_scatter_tiles && !tsc) BR_TRY(bin_tiles_scatter(ctx, x, y, z, w, n, wrap, st, &b));
+    else BR_TRY(bin_particles<BIN_SCATTER>(ctx, x, y, z, w, n, wrap, mas, st, &b));
     unsigned grid = cdiv((size_t)n, 256);
     if (tsc) BR_LAUNCH(ctx, scatter_sorted_kernel<BAOREC_MAS_TSC>, grid, 256, 0, st, rho, b.rec, b.n_valid, g, wrap);
     else BR_LAUNCH(ctx, scatter_sorted_kernel<BAOREC_MAS_CIC>, grid, 256, 0, st, rho, b.rec, b.n_valid, g, wrap);
@@ -886,6 +1135,10 @@ int gather_prebin(baorec_ctx* ctx, const float* x, const float* y, const float* 
   ctx->prebin_valid = false;
   if (!ctx->opt_overlap_sort || n == 0 || !use_binning(ctx, n) || !ctx->opt_gather_tiles || mas == BAOREC_MAS_TSC)
     return BAOREC_OK;
+  if (ctx->sortc_valid && ctx->slab_mode == 0 && ctx->sortc_x == x && ctx->sortc_y == y && ctx->sortc_z == z &&
+      ctx->sortc_n == n)
+    return BAOREC_OK;  // candidate for the sort run! kept: gather3 validates and reuses it
+  ctx->sortc_valid = false;
   BR_CUDA(cudaEventRecord(ctx->ev_fork, st));
   BR_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
   BinResult b;
@@ -939,14 +1192,36 @@ int gather3(baorec_ctx* ctx, const float* fx, const float* fy, const float* fz, 
   const bool tsc = mas == BAOREC_MAS_TSC;
   if (use_binning(ctx, n)) {
     BinResult b;
-    if (joined) {
+    bool reuse = false;
+    if (!one && !tsc && !joined && ctx->opt_gather_tiles) BR_TRY(sort_cache_hit(ctx, x, y, z, n, st, &reuse));
+    if (reuse) {
+      // the sort run! made for the scatter is this catalog's sort: records, tile starts, inverse permutation
+      TileGeom t;
+      t.nxc = (ctx->nx + TILE_X - 1) / TILE_X;
+      t.nyc = (ctx->ny + TILE_Y - 1) / TILE_Y;
+      t.ntiles = ctx->sortc_ntiles;
+      TileScratch sc;
+      BR_TRY(tile_scratch(ctx, t, &sc));
+      b.rec = (float4*)ctx->bufs[BUF_BINIDX].p;
+      b.n_valid = sc.starts + t.ntiles;
+      b.starts = sc.starts;
+      b.ntiles = t.ntiles;
+      b.inv = (unsigned*)ctx->bufs[BUF_BININV].p;
+      BR_LAUNCH(ctx, add_oob_kernel, 1, 1, 0, st, sc.cnt + t.ntiles, ctx->d_oob);  // trash-bin size -> out-of-box counter
+      ctx->n_sort_reuse++;
+    } else if (joined) {
       b.rec = (float4*)ctx->prebin_rec;
       b.n_valid = ctx->prebin_nvalid;
       b.starts = ctx->prebin_starts;
       b.ntiles = ctx->prebin_ntiles;
       b.inv = ctx->prebin_inv;
-    } else if (ctx->opt_gather_tiles) BR_TRY(bin_tiles(ctx, x, y, z, n, mas, st, &b));
-    else BR_TRY(bin_particles<BIN_GATHER>(ctx, (float*)x, (float*)y, (float*)z, nullptr, n, 0, mas, st, &b));
+    } else if (ctx->opt_gather_tiles) {
+      ctx->sortc_valid = false;
+      BR_TRY(bin_tiles(ctx, x, y, z, n, mas, st, &b));
+    } else {
+      ctx->sortc_valid = false;
+      BR_TRY(bin_particles<BIN_GATHER>(ctx, (float*)x, (float*)y, (float*)z, nullptr, n, 0, mas, st, &b));
+    }
     if (b.starts && !tsc) {
       TileGeom t;
       t.nxc = (ctx->nx + TILE_X - 1) / TILE_X;

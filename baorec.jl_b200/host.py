@@ -102,6 +102,10 @@ class Context:
     def scratch_bytes(self):
         return int(self.lib.baorec_scratch_bytes(self.handle))
 
+    def sort_reuse_count(self):
+        """Read-backs that reused the tile sort of the preceding run! (same unmodified position arrays)."""
+        return int(self.lib.baorec_sort_reuse_count(self.handle))
+
     def close(self):
         if self.handle:
             self.lib.baorec_destroy(self.handle)

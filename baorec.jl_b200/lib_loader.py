@@ -54,6 +54,7 @@ SIGNATURES = {
     "baorec_set_box": [_vp, _f3, _f3],
     "baorec_set_option": [_vp, C.c_char_p, _i64],
     "baorec_scratch_bytes": [_vp],
+    "baorec_sort_reuse_count": [_vp],
     "baorec_launch_counts": [_vp, C.POINTER(_i64), C.POINTER(_i64)],
     "baorec_last_stage_ms": [_vp, _f3, _i],
     "baorec_profile_enable": [_vp, _i],
@@ -97,7 +98,7 @@ SIGNATURES = {
     "baorec_host_alloc": [C.POINTER(_vp), _i64],
     "baorec_host_free": [_vp],
 }
-_RESTYPES = {"baorec_last_error": C.c_char_p, "baorec_scratch_bytes": C.c_int64, "baorec_result_cache": C.c_void_p}
+_RESTYPES = {"baorec_last_error": C.c_char_p, "baorec_scratch_bytes": C.c_int64, "baorec_sort_reuse_count": C.c_int64, "baorec_result_cache": C.c_void_p}
 
 _lib = None
 

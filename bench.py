@@ -117,7 +117,11 @@ class ClockSampler:
 def algorithmic_bytes(name, M, Mc, N):
     """Compulsory HBM traffic per launch ('kernels'): every operand read once, every
     result written once."""
-    if "scatter_sorted" in name or "scatter_direct" in name:
+    if "usort_count" in name or "hash_positions" in name:
+        return 12 * N                       # positions in
+    if "usort_reorder" in name:
+        return 16 * N + 16 * N + 4 * N      # x, y, z, w in; float4 records + inverse permutation out
+    if "scatter_sorted" in name or "scatter_direct" in name or "scatter_records" in name:
         return 16 * N + 4 * M              # records/SoA in, every mesh cell written once
     if "gather_sorted_kernel<3" in name or "gather_direct_kernel<3" in name:
         return 16 * N + 12 * N + 12 * M    # positions(+index) in, 3 outputs, 3 displacement meshes once
@@ -164,7 +168,7 @@ def algorithmic_bytes(name, M, Mc, N):
 # (1024^3, 1e8 particles, one GPU; profiles/r1_ncu_full_final_own_kernels.csv, r1_ncu_full_prof_r1_a.csv)
 NCU_TRAFFIC_BYTES_C4 = {
     "gather_tile_kernel<3>": 14.502e9 + 1.598e9,
-    "scatter_sorted_kernel": 5.851e9 + 4.100e9,
+    "scatter_sorted_kernel": 5.851e9 + 4.100e9,      # z-slab order (option unified_sort=0)
     "tile_reorder_kernel": 3.090e9 + 3.300e9,
     "bin_reorder_kernel": 1.645e9 + 1.587e9,
     "unsort_kernel": 7.531e9 + 1.195e9,

@@ -101,6 +101,10 @@ int baorec_set_box(baorec_ctx* ctx, const float box_size[3], const float box_min
 int baorec_set_option(baorec_ctx* ctx, const char* name, int64_t value);
 /* Bytes of device scratch currently owned by the context. */
 int64_t baorec_scratch_bytes(const baorec_ctx* ctx);
+/* Read-backs that reused the tile sort of the preceding run! (option "unified_sort", default 1: the
+ * catalog is sorted once per reconstruction when read_shifts / reconstructed_positions is given the
+ * same, unmodified position arrays; validated by a 64-bit content hash on every read). */
+int64_t baorec_sort_reuse_count(const baorec_ctx* ctx);
 /* Kernel launches issued by this library since creation (cuFFT launches are
  * counted separately in *fft_execs). */
 int baorec_launch_counts(const baorec_ctx* ctx, int64_t* kernels, int64_t* fft_execs);

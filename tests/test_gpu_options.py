@@ -20,7 +20,8 @@ def dev(a):
 def options(B, **kw):
     ctx = B.Context.get(0)
     defaults = {"bin_min_particles": 1 << 18, "fuse_kspace": 1, "own_fft": 0, "gather_tiles": 1,
-                "fft_split_planes": 0}
+                "fft_split_planes": 0, "scatter_tiles": 0,
+                "unified_sort": 1}
     try:
         for k, v in kw.items():
             ctx.set_option(k, v)
@@ -35,9 +36,10 @@ def test_unknown_option(B):
         B.Context.get(0).set_option("no_such_option", 1)
 
 
+@pytest.mark.parametrize("tiles", [0, 1, 2])      # z-slab bins, scatter tiles, unified sort (default)
 @pytest.mark.parametrize("wrap", [True, False])
 @pytest.mark.parametrize("n", [64, 20])
-def test_binned_scatter(B, O, wrap, n):
+def test_binned_scatter(B, O, wrap, n, tiles):
     L, N = 1000.0, 200_000
     pos, w = clustered_box(N, L, seed=17)
     if wrap:
@@ -51,7 +53,7 @@ def test_binned_scatter(B, O, wrap, n):
     orho = O.cic_scatter(np.zeros((n, n, n), np.float32), ox, oy, oz, w, bs, bm, wrap)
     gx, gy, gz = (dev(p) for p in pos)
     rho = torch.zeros((n, n, n), dtype=torch.float32, device="cuda")
-    with options(B, bin_min_particles=0):
+    with options(B, bin_min_particles=0, scatter_tiles=tiles % 2, unified_sort=int(tiles == 2)):
         B.cic(rho, gx, gy, gz, dev(w), bs, bm, wrap=wrap)
     assert maxabs(rho.cpu().numpy(), orho) <= 2e-5 * max(1.0, float(orho.max()))
     for g, o in zip((gx, gy, gz), (ox, oy, oz)):       # wrapped positions written back
@@ -66,12 +68,13 @@ def test_binned_scatter_out_of_box(B):
     y = (rng.random(1000) * L).astype(np.float32)
     z = (rng.random(1000) * L).astype(np.float32)
     x[7], z[11], y[500] = -3.0, 420.0, np.nan
-    rho = torch.zeros((n, n, n), dtype=torch.float32, device="cuda")
-    with options(B, bin_min_particles=0):
-        with pytest.raises(B.OutOfBoxError) as ei:
-            B.cic(rho, dev(x), dev(y), dev(z), dev(np.ones(1000, np.float32)), bs, bm, wrap=True)
-    assert "3 particle(s)" in str(ei.value)
-    assert abs(float(rho.sum()) - 997.0) < 1e-2       # the others were deposited
+    for tiles in (0, 1, 2):
+        rho = torch.zeros((n, n, n), dtype=torch.float32, device="cuda")
+        with options(B, bin_min_particles=0, scatter_tiles=tiles % 2, unified_sort=int(tiles == 2)):
+            with pytest.raises(B.OutOfBoxError) as ei:
+                B.cic(rho, dev(x), dev(y), dev(z), dev(np.ones(1000, np.float32)), bs, bm, wrap=True)
+        assert "3 particle(s)" in str(ei.value)
+        assert abs(float(rho.sum()) - 997.0) < 1e-2       # the others were deposited
 
 
 @pytest.mark.parametrize("mas", ["cic", "tsc"])
@@ -102,6 +105,8 @@ def test_binned_tsc_scatter(B, O):
 @pytest.mark.parametrize("opts", [dict(bin_min_particles=0, fuse_kspace=1), dict(bin_min_particles=0, fuse_kspace=0),
                                   dict(bin_min_particles=0, fuse_kspace=1, own_fft=1),
                                   dict(bin_min_particles=0, fuse_kspace=1, fft_split_planes=8),
+                                  dict(bin_min_particles=0, fuse_kspace=1, scatter_tiles=1, unified_sort=0),
+                                  dict(bin_min_particles=0, fuse_kspace=1, unified_sort=0),
                                   dict(bin_min_particles=0, fuse_kspace=0, fft_split_planes=24),
                                   dict(bin_min_particles=0, fuse_kspace=0, own_fft=1, gather_tiles=0),
                                   dict(bin_min_particles=1 << 40, fuse_kspace=0),
@@ -278,3 +283,61 @@ def test_displacement_meshes_are_reused_across_catalogs(B, O, algo):
     B.reconstructed_positions(rec, *d, field="sum")
     _, f7 = ctx.launch_counts()
     assert f7 - f6 >= 3
+
+
+def test_unified_sort_is_reused_only_for_the_same_unmodified_catalog(B, O):
+    """run! sorts the catalog once into the gather's tile order; read_shifts on the same position
+    arrays (same pointers, same content by 64-bit hash, wrapped positions included) reuses that sort.
+    Anything else -- other arrays, arrays edited in place, another catalog scattered in between --
+    sorts again.  Results agree with the oracle either way."""
+    n, L, N = 64, 1000.0, 300_000
+    pos, w = clustered_box(N, L, seed=41)
+    pos[0][:60] += np.float32(L)                 # exercised: wrap + write-back, hash of the wrapped positions
+    kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=np.full(3, L, np.float32),
+              box_min=np.zeros(3, np.float32), los=(0.0, 0.0, 1.0), n_iter=3)
+    orec = O.IterativeRecon(**kw)
+    opos = [p.copy() for p in pos]
+    omesh = O.run(orec, (n, n, n), *opos, w)
+    oshift = O.read_shifts(orec, *opos, omesh, "sum")
+
+    def check(s, ref):
+        for a in range(3):
+            assert rel_rms(s[a].cpu().numpy() if hasattr(s[a], "cpu") else s[a], ref[a]) < 1e-4
+            assert maxabs(s[a].cpu().numpy() if hasattr(s[a], "cpu") else s[a], ref[a]) < 1e-3
+
+    with options(B, bin_min_particles=0):
+        ctx = B.Context.get(0)
+        d = [dev(p) for p in pos]
+        rec = B.IterativeRecon(**kw)
+        mesh = B.run(rec, (n, n, n), *d, dev(w))
+        c0 = ctx.sort_reuse_count()
+        s = B.read_shifts(rec, *d, mesh, field="sum")
+        assert ctx.sort_reuse_count() == c0 + 1
+        check(s, oshift)
+        s = B.read_shifts(rec, *d, mesh, field="sum")                  # the kept sort survives a reuse
+        assert ctx.sort_reuse_count() == c0 + 2
+        check(s, oshift)
+        clones = [t.clone() for t in d]                                 # same content, other arrays: sorted again
+        s = B.read_shifts(rec, *clones, mesh, field="sum")
+        assert ctx.sort_reuse_count() == c0 + 2
+        check(s, oshift)
+        # edited in place after run!: the hash no longer matches
+        mesh = B.run(rec, (n, n, n), *d, dev(w))
+        c1 = ctx.sort_reuse_count()
+        d[1].add_(3.0).remainder_(L)
+        moved = [t.cpu().numpy() for t in d]
+        s = B.read_shifts(rec, *d, mesh, field="sum")
+        assert ctx.sort_reuse_count() == c1
+        check(s, O.read_shifts(orec, *moved, omesh, "sum"))
+        # host pipeline: the read-back catalog is uploaded to the arrays run! used
+        rec_h = B.IterativeRecon(**kw)
+        hp = [p.copy() for p in pos]
+        B.run(rec_h, (n, n, n), *hp, w)
+        c2 = ctx.sort_reuse_count()
+        sh = B.read_shifts(rec_h, *hp, None, field="sum")
+        assert ctx.sort_reuse_count() == c2 + 1
+        check(sh, oshift)
+        other, _ = clustered_box(N, L, seed=43)
+        sh = B.read_shifts(rec_h, *other, None, field="sum")           # same size, different catalog
+        assert ctx.sort_reuse_count() == c2 + 1
+        check(sh, O.read_shifts(orec, *other, omesh, "sum"))
