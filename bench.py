@@ -169,6 +169,8 @@ def algorithmic_bytes(name, M, Mc, N):
 NCU_TRAFFIC_BYTES_C4 = {
     "gather_tile_kernel<3>": 14.502e9 + 1.598e9,
     "scatter_sorted_kernel": 5.851e9 + 4.100e9,      # z-slab order (option unified_sort=0)
+    "scatter_records_kernel": 5.849e9 + 4.096e9,     # profiles/r1_ncu_full_unified_sort.csv
+    "usort_reorder_kernel": 3.509e9 + 3.308e9,
     "tile_reorder_kernel": 3.090e9 + 3.300e9,
     "bin_reorder_kernel": 1.645e9 + 1.587e9,
     "unsort_kernel": 7.531e9 + 1.195e9,
