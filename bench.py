@@ -186,12 +186,26 @@ def ncu_traffic(name, n, N, world):
     return None
 
 
-def cpu_reference(mesh_n, n_part, reps, warm):
-    """BAOrec.jl's CPU path, restated (oracle/baorec_oracle.py; NOT the Julia binary): run! +
-    read_shifts(:sum) on a bounded sample: a (mesh_n)^3 sub-volume with the same cell size and
-    particle density as the 1024^3 workload.  Returns seconds per sample reconstruction."""
+def cpu_oracle():
+    """The CPU stand-in for BAOrec.jl's threaded CPU path: the oracle with compiled loops
+    (oracle/baorec_oracle_c.c: serial scatter like the reference's, OpenMP gather / k-space loops,
+    scipy.fft on all host threads) when oracle/_c/ was built, else the pure-numpy port."""
     sys.path.insert(0, str(ROOT / "oracle"))
+    import baorec_oracle_fast as fast
+    if fast.available():
+        O = fast.load()
+        return O, (f"C/OpenMP port of the reference's CPU methods ({O.threads} threads; scatter serial like the "
+                   "reference, src/mas.jl:5) + scipy.fft on all host threads")
     import baorec_oracle as O
+    return O, ("numpy port of the reference's CPU methods: scipy.fft on all host threads, scatter serial like the "
+               "reference (src/mas.jl:5), gather/k-space loops single-threaded numpy")
+
+
+def cpu_reference(mesh_n, n_part, reps, warm):
+    """BAOrec.jl's CPU path, restated (oracle/; NOT the Julia binary): run! + read_shifts(:sum) on a
+    bounded sample: a (mesh_n)^3 sub-volume with the same cell size and particle density as the
+    1024^3 workload.  Returns (seconds per sample reconstruction, description of the port)."""
+    O, what = cpu_oracle()
     L = BOX_L * mesh_n / 1024.0
     rng = np.random.default_rng(42)
     pos = [(rng.random(n_part, dtype=np.float32) * np.float32(L)) for _ in range(3)]
@@ -207,7 +221,7 @@ def cpu_reference(mesh_n, n_part, reps, warm):
         dt = time.perf_counter() - t0
         if i >= warm:
             times.append(dt)
-    return times
+    return times, what
 
 
 def run_reference_arm(args, rank, world):
@@ -216,14 +230,12 @@ def run_reference_arm(args, rank, world):
     mesh_n = args.ref_mesh
     scale = (1024 // mesh_n) ** 3
     n_part = int(args.particles) // scale
-    times = cpu_reference(mesh_n, n_part, args.steps, args.warmup)
+    times, what = cpu_reference(mesh_n, n_part, args.steps, args.warmup)
     ms_sample = 1e3 * float(np.mean(times))
     value = ms_sample * scale
     cores = os.cpu_count() or 1
     sample = (f"{mesh_n}^3 mesh / {n_part} particles sub-volume (same cell size and density), "
-              f"{ms_sample:.0f} ms per sample reconstruction, scaled x{scale} (linear) to 1024^3 / 1e8; numpy port of "
-              "the reference's CPU methods: scipy.fft on all host threads, scatter serial like the reference "
-              "(src/mas.jl:5), gather/k-space loops single-threaded numpy")
+              f"{ms_sample:.0f} ms per sample reconstruction, scaled x{scale} (linear) to 1024^3 / 1e8; {what}")
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_sample, "higher_is_better": False,
@@ -244,7 +256,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mesh", type=int, default=1024)
     ap.add_argument("--particles", type=float, default=1e8)
-    ap.add_argument("--ref-mesh", type=int, default=256, help="mesh size of the CPU sample")
+    ap.add_argument("--ref-mesh", type=int, default=512, help="mesh size of the CPU sample (sub-volume of the workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -424,15 +436,13 @@ def main():
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
-        mesh_n = args.ref_mesh
+        mesh_n = min(args.ref_mesh, n)
         scale = (n // mesh_n) ** 3
-        times = cpu_reference(mesh_n, max(1, N // scale), reps=3, warm=1)
+        times, what = cpu_reference(mesh_n, max(1, N // scale), reps=2, warm=1)
         ms_sample = 1e3 * float(np.mean(times))
         cpu_baseline = {"value": ms_sample * scale, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                         "sample": f"{mesh_n}^3 mesh / {N // scale} particles sub-volume (same cell size and density): "
-                                  f"{ms_sample:.0f} ms per sample reconstruction, scaled x{scale}; numpy port of the "
-                                  "reference's CPU methods: scipy.fft on all host threads, scatter serial like the "
-                                  "reference (src/mas.jl:5), gather/k-space loops single-threaded numpy"}
+                                  f"{ms_sample:.0f} ms per sample reconstruction, scaled x{scale}; {what}"}
 
     out = {
         "metric": METRIC, "value": ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
