@@ -6,15 +6,17 @@ The directory name carries a dot, so load it with `__graft_entry__.load_package(
   lib/         built libbaorec_b200.so (git-ignored)
   lib_loader   ctypes binding (fails loudly if the library is missing)
   host         mirror of the reference's Julia API on top of the C ABI
+  catalog      cosmology tables + sky <-> Cartesian, FKP weights, periodic re-wrap (src/cosmo.jl, examples/lightcone.jl)
   julia/       the ccall shim a BAOrec.jl maintainer would add
 """
 from . import lib_loader
-from .lib_loader import BaorecError, OutOfBoxError
+from .lib_loader import BaorecError, OutOfBoxError, OutOfRangeError
 from .host import (Context, FFTPlan, IterativeRecon, MultigridRecon, setup_fft, k_vec, x_vec, setup_box, smooth, cic,
                    read_cic, cic_cells, gather_cells, setup_overdensity, iterate, reconstructed_overdensity,
                    reconstructed_potential, run, compute_displacements, displacement_meshes, read_shifts,
                    reconstructed_positions, jacobi, residual, reduce, prolong, vcycle, fmg)
 
 from . import dist
+from .catalog import Cosmology, DESICosmology, sky_to_cartesian, cartesian_to_sky, fkp_weights, wrap_positions
 
 lib_loader.load()   # no library -> ImportError; there is no fallback path

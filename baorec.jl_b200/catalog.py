@@ -1,0 +1,131 @@
+"""Catalog pre/post-processing on the device: the host-side mirror of src/cosmo.jl and of the helper
+functions every lightcone example of the reference defines around `run!`
+(examples/lightcone.jl:30-82, identical in lightcone_gpu.jl / lightcone_mg*.jl) -- same names, same
+argument order -- on top of the C ABI (baorec_cosmo_set, baorec_sky_to_cartesian_f32,
+baorec_cartesian_to_sky_f32, baorec_fkp_weights_f32, baorec_wrap_positions_f32).
+
+`Cosmology` is a parameter bag: its derived densities are scalar set-up arithmetic done here exactly
+as the reference's `@with_kw` struct does them (Float32 fields, Float64 intermediates); the
+comoving-distance table, the interpolations and all per-particle work happen in the CUDA library.
+Catalog columns are contiguous 1-D float32 CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import lib_loader as L
+from .host import Context, _chk_vec, _ptr, _stream
+
+_f32 = np.float32
+
+# src/cosmo.jl:11-21
+_MPC, _C_KM_S, _G, _HBAR, _EVC2, _KB = 3.085677581491367e22, 299792.458, 6.67408e-11, 6.582119514e-16, 1.782661907e-36, 8.6173303e-5
+
+
+@dataclass
+class Cosmology:
+    """`BAOrec.Cosmology(; kwargs...)` src/cosmo.jl:22-64 (keyword names transliterated:
+    ω_b -> omega_b, Ω_k₀ -> Omega_k0, ...)."""
+    omega_b: float = 0.0225
+    omega_c: float = 0.12
+    h: float = 0.67
+    Neff: float = 3.044
+    Omega_k0: float = 0.0
+    T_cmb: float = 2.725
+    w0: float = -1.0
+    wa: float = 0.0
+    ns: float = 0.96
+    z_tab_min: float = 0
+    z_tab_max: float = 3
+    z_tab_num: int = 100000
+
+    def __post_init__(self):
+        T = _f32
+        for k in ("omega_b", "omega_c", "h", "Neff", "Omega_k0", "T_cmb", "w0", "wa", "ns"):
+            setattr(self, k, T(getattr(self, k)))
+        self.h2 = T(self.h * self.h)
+        self.H0 = T(self.h * T(100))
+        rho_g0 = T(3 * 100 ** 2 / (8 * np.pi * _G) * _HBAR ** 3 * (1.0 / (1e-3 * _MPC)) ** 2 * (1.0 / _EVC2) * (_C_KM_S * 1e3) ** 3)
+        self.Omega_g0 = T((np.pi ** 2 / 15) * (2.725 * _KB) ** 4 / float(rho_g0) * (float(self.T_cmb) / 2.725) ** 4 / float(self.h2))
+        self.Omega_nu0 = T(float(self.Neff) * (7 / 8 * (4 / 11) ** (4 / 3)) * float(self.Omega_g0))
+        self.Omega_b0 = T(self.omega_b / self.h2)
+        self.Omega_c0 = T(self.omega_c / self.h2)
+        self.Omega_L0 = T(T(T(T(T(T(1) - self.Omega_k0) - self.Omega_b0) - self.Omega_c0) - self.Omega_nu0) - self.Omega_g0)
+        self.Omega_m0 = T(self.Omega_b0 + self.Omega_c0)
+        self._bound = {}        # device -> True once the tables of THIS cosmology are the context's
+
+    def _params(self) -> L.CosmologyParams:
+        return L.CosmologyParams(float(self.h), float(self.Omega_b0), float(self.Omega_c0), float(self.Omega_nu0),
+                                 float(self.Omega_g0), float(self.Omega_k0), float(self.Omega_L0), float(self.w0),
+                                 float(self.wa), float(self.z_tab_min), float(self.z_tab_max), int(self.z_tab_num))
+
+    def bind(self, ctx: Optional[Context] = None) -> Context:
+        """Builds the comoving-distance table in the library (the `cache` of src/cosmo.jl:86-91) if the
+        context does not hold this cosmology's yet."""
+        ctx = ctx or Context.get()
+        if getattr(ctx, "cosmology", None) is not self:
+            p = self._params()
+            L.check(ctx.lib.baorec_cosmo_set(ctx.handle, C.byref(p)))
+            ctx.cosmology = self
+        return ctx
+
+    def tables(self, ctx: Optional[Context] = None):
+        """(z, r) of the cache as float64 numpy arrays (parity probe)."""
+        ctx = self.bind(ctx)
+        n = int(self.z_tab_num)
+        z, r = np.empty(n, np.float64), np.empty(n, np.float64)
+        L.check(ctx.lib.baorec_cosmo_tables(ctx.handle, z.ctypes.data_as(C.POINTER(C.c_double)),
+                                            r.ctypes.data_as(C.POINTER(C.c_double)), n))
+        return z, r
+
+
+def DESICosmology(**kwargs) -> Cosmology:
+    """src/cosmo.jl:66-68."""
+    base = dict(omega_b=0.02237, omega_c=0.1200, h=0.6736, ns=0.9649, Neff=float(_f32(_f32(2.0328) + _f32(1))), w0=-1.0, wa=0.0)
+    base.update(kwargs)
+    return Cosmology(**base)
+
+
+def sky_to_cartesian(data_cat_ra, data_cat_dec, data_cat_red, cosmo: Cosmology):
+    """examples/lightcone.jl:30-49: (ra, dec [deg], redshift) -> (x, y, z) [Mpc/h], three new tensors."""
+    n = _chk_vec(data_cat_ra, data_cat_dec, data_cat_red)
+    ctx = cosmo.bind(Context.get(data_cat_ra.device.index))
+    out = tuple(torch.empty_like(data_cat_ra) for _ in range(3))
+    h = float(_f32(cosmo.H0 / _f32(100)))
+    L.check(ctx.lib.baorec_sky_to_cartesian_f32(ctx.handle, _ptr(data_cat_ra), _ptr(data_cat_dec), _ptr(data_cat_red), n, h,
+                                                _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _stream()))
+    return out
+
+
+def cartesian_to_sky(data_x, data_y, data_z, cosmo: Cosmology):
+    """examples/lightcone.jl:51-80: (x, y, z) [Mpc/h] -> (ra, dec [deg], redshift); ra in (-360, 0] like the reference."""
+    n = _chk_vec(data_x, data_y, data_z)
+    ctx = cosmo.bind(Context.get(data_x.device.index))
+    out = tuple(torch.empty_like(data_x) for _ in range(3))
+    L.check(ctx.lib.baorec_cartesian_to_sky_f32(ctx.handle, _ptr(data_x), _ptr(data_y), _ptr(data_z), n, float(cosmo.h),
+                                                _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _stream()))
+    return out
+
+
+def fkp_weights(nz, P0):
+    """fkp_weights.(nz, Ref(P0)) examples/lightcone.jl:82,90-91."""
+    n = _chk_vec(nz)
+    ctx = Context.get(nz.device.index)
+    w = torch.empty_like(nz)
+    L.check(ctx.lib.baorec_fkp_weights_f32(ctx.handle, _ptr(nz), n, float(_f32(P0)), _ptr(w), _stream()))
+    return w
+
+
+def wrap_positions(pos_x, pos_y, pos_z, box_size, box_min=(0.0, 0.0, 0.0)):
+    """In-place periodic re-wrap of (reconstructed) positions into [box_min, box_min + box_size):
+    `(pos + box_size) % box_size` of test_helpers/simulation.py:38,51-52, for any box origin."""
+    n = _chk_vec(pos_x, pos_y, pos_z)
+    ctx = Context.get(pos_x.device.index)
+    L.check(ctx.lib.baorec_wrap_positions_f32(ctx.handle, _ptr(pos_x), _ptr(pos_y), _ptr(pos_z), n, L.f3(np.broadcast_to(box_size, 3)),
+                                              L.f3(np.broadcast_to(box_min, 3)), _stream()))
+    return pos_x, pos_y, pos_z

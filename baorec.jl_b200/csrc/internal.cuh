@@ -231,6 +231,11 @@ struct baorec_ctx {
   int opt_a2a_chunks = 4;
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_chunk[8] = {}, ev_a2a[8] = {};
+  // catalog pre/post-processing (catalog.cu): comoving-distance table r(z) on uniform z knots
+  double* d_cosmo_r = nullptr;
+  std::vector<double> h_cosmo_r;
+  int64_t cosmo_n = 0;
+  double cosmo_z0 = 0.0, cosmo_z1 = 0.0, cosmo_dz = 0.0;
 };
 
 namespace baorec {

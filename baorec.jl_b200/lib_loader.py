@@ -12,7 +12,7 @@ HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "lib" / "libbaorec_b200.so"
 
 OK = 0
-ERR_INVALID, ERR_CUDA, ERR_CUFFT, ERR_NCCL, ERR_OUT_OF_BOX, ERR_NOT_PLANNED, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7
+ERR_INVALID, ERR_CUDA, ERR_CUFFT, ERR_NCCL, ERR_OUT_OF_BOX, ERR_NOT_PLANNED, ERR_NOMEM, ERR_OUT_OF_RANGE = -1, -2, -3, -4, -5, -6, -7, -8
 MAS_CIC, MAS_TSC = 0, 1
 FIELD_DISP, FIELD_RSD, FIELD_SUM = 0, 1, 2
 ITERATIVE, MULTIGRID = 0, 1
@@ -30,6 +30,10 @@ class OutOfBoxError(BaorecError):
     pass
 
 
+class OutOfRangeError(BaorecError):
+    """A redshift / distance outside the cosmology tables (reference: Interpolations.jl BoundsError)."""
+
+
 class Params(C.Structure):
     """struct baorec_params."""
     _fields_ = [
@@ -38,6 +42,13 @@ class Params(C.Structure):
         ("jacobi_damping_factor", C.c_float), ("jacobi_niterations", C.c_int32),
         ("vcycle_niterations", C.c_int32), ("mas", C.c_int32), ("ran_min", C.c_float), ("box_pad", C.c_float),
     ]
+
+
+class CosmologyParams(C.Structure):
+    """struct baorec_cosmology."""
+    _fields_ = [("h", C.c_double), ("Omega_b0", C.c_double), ("Omega_c0", C.c_double), ("Omega_nu0", C.c_double),
+                ("Omega_g0", C.c_double), ("Omega_k0", C.c_double), ("Omega_L0", C.c_double), ("w0", C.c_double),
+                ("wa", C.c_double), ("z_tab_min", C.c_double), ("z_tab_max", C.c_double), ("z_tab_num", C.c_int64)]
 
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
@@ -95,6 +106,13 @@ SIGNATURES = {
     "baorec_run_host_f32": [_vp, _pp, _i, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _f3, _f3],
     "baorec_read_host_f32": [_vp, _pp, _i, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp],
     "baorec_result_cache": [_vp],
+    "baorec_cosmo_set": [_vp, C.POINTER(CosmologyParams)],
+    "baorec_cosmo_build_table": [C.POINTER(CosmologyParams), C.POINTER(C.c_double), C.POINTER(C.c_double)],
+    "baorec_cosmo_tables": [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), _i64],
+    "baorec_sky_to_cartesian_f32": [_vp, _vp, _vp, _vp, _i64, _f, _vp, _vp, _vp, _vp],
+    "baorec_cartesian_to_sky_f32": [_vp, _vp, _vp, _vp, _i64, _f, _vp, _vp, _vp, _vp],
+    "baorec_fkp_weights_f32": [_vp, _vp, _i64, _f, _vp, _vp],
+    "baorec_wrap_positions_f32": [_vp, _vp, _vp, _vp, _i64, _f3, _f3, _vp],
     "baorec_host_alloc": [C.POINTER(_vp), _i64],
     "baorec_host_free": [_vp],
 }
@@ -127,6 +145,8 @@ def check(code: int):
     msg = load().baorec_last_error().decode("utf-8", "replace")
     if code == ERR_OUT_OF_BOX:
         raise OutOfBoxError(code, msg)
+    if code == ERR_OUT_OF_RANGE:
+        raise OutOfRangeError(code, msg)
     raise BaorecError(code, msg)
 
 

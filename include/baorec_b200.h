@@ -45,7 +45,9 @@ enum {
   BAOREC_ERR_OUT_OF_BOX = -5,  /* particle outside the mesh (reference: BoundsError /
                                   out-of-bounds atomic, src/mas.jl:33-49, 82-97) */
   BAOREC_ERR_NOT_PLANNED = -6, /* baorec_plan has not been called */
-  BAOREC_ERR_NOMEM = -7
+  BAOREC_ERR_NOMEM = -7,
+  BAOREC_ERR_OUT_OF_RANGE = -8 /* redshift / distance outside the cosmology tables (reference:
+                                  Interpolations.jl BoundsError) */
 };
 
 enum { BAOREC_MAS_CIC = 0, BAOREC_MAS_TSC = 1 };             /* TSC is an extension */
@@ -283,6 +285,44 @@ int baorec_read_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm,
                          int shifts_only, float* h_ox, float* h_oy, float* h_oz);
 /* Device pointer of the cached result mesh (recon.result_cache), or NULL. */
 float* baorec_result_cache(baorec_ctx* ctx);
+
+/* ---- catalog pre/post-processing (the callers either side of the path) ------ */
+/* The density parameters of `Cosmology` (src/cosmo.jl:22-64) after its Float32 derivations, widened
+ * to double, and the table range (`z_tab_min`, `z_tab_max`, `z_tab_num`). */
+typedef struct baorec_cosmology {
+  double h;                               /* Float32(h) */
+  double Omega_b0, Omega_c0, Omega_nu0, Omega_g0, Omega_k0, Omega_L0;
+  double w0, wa;
+  double z_tab_min, z_tab_max;
+  int64_t z_tab_num;
+} baorec_cosmology;
+/* Replaces the cache built by comoving_distance_interp / redshift_interp (src/cosmo.jl:86-103):
+ * r(z) = c * int_0^z dz'/H(z') [Mpc] on z = range(z_tab_min, z_tab_max, length = z_tab_num), Float64,
+ * by 7-point Gauss-Legendre quadrature per knot interval (the reference: quadgk, rtol 1e-8), kept on
+ * the host and uploaded to the device.  Needs no baorec_plan. */
+int baorec_cosmo_set(baorec_ctx* ctx, const baorec_cosmology* c);
+/* The same table on the host only (no context, no device): h_r[z_tab_num] (and the knots in h_z unless
+ * NULL).  Set-up arithmetic like k_vec / x_vec; lets a caller inspect or cache the table. */
+int baorec_cosmo_build_table(const baorec_cosmology* c, double* h_z, double* h_r);
+/* Host copy of the tables (parity probe); either output may be NULL; cap >= z_tab_num. */
+int baorec_cosmo_tables(const baorec_ctx* ctx, double* h_z, double* h_r, int64_t cap);
+/* sky_to_cartesian (examples/lightcone.jl:30-49): ra, dec [deg], redshift -> x, y, z [Mpc/h];
+ * dist = comoving_distance_interp(redshift), h = Float32(cosmo.H0 / 100).  Outputs may alias inputs.
+ * Synchronises `stream`; BAOREC_ERR_OUT_OF_RANGE if a redshift lies outside the table (outputs NaN). */
+int baorec_sky_to_cartesian_f32(baorec_ctx* ctx, const float* d_ra, const float* d_dec, const float* d_red, int64_t n,
+                                float h, float* d_x, float* d_y, float* d_z, baorec_stream stream);
+/* cartesian_to_sky (examples/lightcone.jl:51-80): x, y, z [Mpc/h] -> ra, dec [deg], redshift =
+ * redshift_interp(|p| / h) with h = cosmo.h.  The right ascension is left in (-360, 0] exactly like
+ * the reference's `(lon - 360) % 360`.  Synchronises `stream`; BAOREC_ERR_OUT_OF_RANGE as above. */
+int baorec_cartesian_to_sky_f32(baorec_ctx* ctx, const float* d_x, const float* d_y, const float* d_z, int64_t n,
+                                float h, float* d_ra, float* d_dec, float* d_red, baorec_stream stream);
+/* fkp_weights.(nz, P0) (examples/lightcone.jl:82): w = 1 / (1 + nz * P0), Float32, bit-exact. */
+int baorec_fkp_weights_f32(baorec_ctx* ctx, const float* d_nz, int64_t n, float P0, float* d_w, baorec_stream stream);
+/* Periodic re-wrap of reconstructed positions, in place: p = min + mod(p - min + L, L) (floored
+ * modulo; test_helpers/simulation.py:38,51-52 with min = 0).  reconstructed_positions itself does not
+ * re-wrap (src/recon.jl:366-388). */
+int baorec_wrap_positions_f32(baorec_ctx* ctx, float* d_x, float* d_y, float* d_z, int64_t n, const float box_size[3],
+                              const float box_min[3], baorec_stream stream);
 
 /* Pinned host memory helpers for callers without their own (Julia: CUDA.Mem.alloc(HostBuffer)). */
 int baorec_host_alloc(void** out, int64_t bytes);

@@ -1,0 +1,171 @@
+"""CPU checks of the catalog pre/post-processing that need no GPU:
+  * the product's host-side comoving-distance table (baorec_cosmo_build_table) against the oracle;
+  * the `Cosmology` mirror's derived densities against the oracle's restatement of src/cosmo.jl;
+  * the per-particle arithmetic the CUDA kernels execute (baorec.jl_b200/csrc/catalog_math.cuh),
+    compiled as plain C++ by tests/hostcheck/ and run on the CPU, against the oracle -- bit-exact for
+    the Float32-only formulas (FKP weights, re-wrap), within 1 ulp otherwise.
+The same comparisons run on the device in tests/test_gpu_zz_catalog.py."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import catalog_oracle as CO
+
+ROOT = Path(__file__).resolve().parent.parent
+f32 = np.float32
+_F, _D = C.POINTER(C.c_float), C.POINTER(C.c_double)
+
+
+def fp(a):
+    return a.ctypes.data_as(_F)
+
+
+@pytest.fixture(scope="module")
+def HC():
+    out = ROOT / "tests" / "_build" / "libcatalog_hostcheck.so"
+    src = ROOT / "tests" / "hostcheck" / "catalog_hostcheck.cpp"
+    hdr = ROOT / "baorec.jl_b200" / "csrc" / "catalog_math.cuh"
+    if not out.exists() or out.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime):
+        out.parent.mkdir(exist_ok=True)
+        gxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
+        subprocess.run([gxx, "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(out), str(src)], check=True)
+    lib = C.CDLL(str(out))
+    i64, d, f = C.c_int64, C.c_double, C.c_float
+    lib.hc_sky_to_cartesian.restype = i64
+    lib.hc_sky_to_cartesian.argtypes = [_F, _F, _F, i64, f, _D, d, d, d, i64, _F, _F, _F]
+    lib.hc_cartesian_to_sky.restype = i64
+    lib.hc_cartesian_to_sky.argtypes = [_F, _F, _F, i64, f, _D, d, d, i64, _F, _F, _F]
+    lib.hc_fkp_weights.restype = None
+    lib.hc_fkp_weights.argtypes = [_F, i64, f, _F]
+    lib.hc_wrap_positions.restype = None
+    lib.hc_wrap_positions.argtypes = [_F, _F, _F, i64, _F, _F]
+    lib.hc_coarse_layout.restype = None
+    lib.hc_coarse_layout.argtypes = [i64, C.POINTER(i64), C.POINTER(C.c_int)]
+    return lib
+
+
+def product_table(B, cosmo):
+    p = cosmo._params()
+    n = int(cosmo.z_tab_num)
+    z, r = np.empty(n), np.empty(n)
+    B.lib_loader.check(B.lib_loader.load().baorec_cosmo_build_table(C.byref(p), z.ctypes.data_as(_D), r.ctypes.data_as(_D)))
+    return z, r
+
+
+def ulps(a, b):
+    a, b = np.asarray(a, f32), np.asarray(b, f32)
+    return np.abs(a.astype(np.float64) - b.astype(np.float64)) / np.spacing(np.maximum(np.abs(a), np.abs(b)).astype(f32))
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(z_tab_max=10), dict(z_tab_min=0.4, z_tab_max=1.6, z_tab_num=4097),
+                                dict(h=0.6736, omega_b=0.02237, Neff=3.0328, z_tab_num=1000), dict(w0=-0.9, wa=0.1, z_tab_max=2)])
+def test_cosmology_mirror_and_distance_table(B, kw):
+    mine, ref = B.Cosmology(**kw), CO.Cosmology(**kw)
+    for k in ("h", "h2", "H0", "Omega_b0", "Omega_c0", "Omega_g0", "Omega_nu0", "Omega_k0", "Omega_L0", "Omega_m0", "w0", "wa"):
+        assert f32(getattr(mine, k)) == f32(getattr(ref, k)), k
+    z, r = product_table(B, mine)
+    zo, ro = CO.tables(ref)
+    assert np.abs(z - zo).max() < 1e-14 * max(1.0, zo[-1])
+    assert np.abs(r[1:] / ro[1:] - 1).max() < 1e-12 and abs(r[0] - ro[0]) < 1e-9 * max(1.0, ro[0])
+    i = len(z) // 3
+    assert abs(r[i] / CO.comoving_distance(ref, z[i]) - 1) < 1e-9            # vs adaptive quadrature (quadgk's rtol is 1e-8)
+
+
+def test_desi_cosmology_mirror(B):
+    a, b = B.DESICosmology(z_tab_max=4), CO.DESICosmology(z_tab_max=4)
+    for k in ("h", "Neff", "Omega_b0", "Omega_c0", "Omega_g0", "Omega_nu0", "Omega_L0"):
+        assert f32(getattr(a, k)) == f32(getattr(b, k)), k
+
+
+def test_bad_cosmology_is_an_error(B):
+    lib = B.lib_loader.load()
+    r = np.empty(8)
+    p = B.Cosmology(z_tab_num=8)._params()
+    assert lib.baorec_cosmo_build_table(C.byref(p), None, None) == B.lib_loader.ERR_INVALID
+    p.z_tab_num = 1
+    assert lib.baorec_cosmo_build_table(C.byref(p), None, r.ctypes.data_as(_D)) == B.lib_loader.ERR_INVALID
+    p.z_tab_num, p.z_tab_max = 8, -1.0
+    assert lib.baorec_cosmo_build_table(C.byref(p), None, r.ctypes.data_as(_D)) == B.lib_loader.ERR_INVALID
+    assert b"z_tab" in lib.baorec_last_error()
+
+
+@pytest.mark.parametrize("ntab", [2, 3, 2047, 2048, 2049, 4095, 100000, 1 << 20])
+def test_coarse_table_layout_covers_every_knot(HC, ntab):
+    s, nc = C.c_int64(), C.c_int()
+    HC.hc_coarse_layout(ntab, C.byref(s), C.byref(nc))
+    assert 2 <= nc.value <= 2048 and s.value >= 1
+    assert (nc.value - 1) * s.value >= ntab - 1 > (nc.value - 2) * s.value
+
+
+def sky_catalog(n, seed, zmax):
+    rng = np.random.default_rng(seed)
+    ra, dec = (360 * rng.random(n)).astype(f32), (180 * rng.random(n) - 90).astype(f32)
+    red = (zmax * rng.random(n)).astype(f32)
+    ra[:4], dec[:4] = f32([0, 90, 180, 359.99]), f32([0, -90, 90, 45])
+    red[:3] = f32([0, zmax, zmax / 2])
+    return ra, dec, red
+
+
+@pytest.mark.parametrize("kw", [dict(z_tab_max=3), dict(z_tab_max=10), dict(z_tab_max=2, z_tab_num=1500)])
+def test_device_arithmetic_of_sky_to_cartesian(HC, B, kw):
+    cosmo, ref = B.Cosmology(**kw), CO.Cosmology(**kw)
+    z, r = product_table(B, cosmo)
+    ra, dec, red = sky_catalog(50000, 3, float(kw["z_tab_max"]))
+    x, y, zz = (np.empty_like(ra) for _ in range(3))
+    h = f32(cosmo.H0 / f32(100))
+    bad = HC.hc_sky_to_cartesian(fp(ra), fp(dec), fp(red), len(ra), h, r.ctypes.data_as(_D), z[0], z[-1], (z[-1] - z[0]) / (len(z) - 1), len(z), fp(x), fp(y), fp(zz))
+    assert bad == 0
+    ox, oy, oz = CO.sky_to_cartesian(ra, dec, red, ref)
+    scale = np.sqrt(ox.astype(float) ** 2 + oy.astype(float) ** 2 + oz.astype(float) ** 2).astype(f32)
+    for a, b in ((x, ox), (y, oy), (zz, oz)):
+        assert (np.abs(a.astype(float) - b.astype(float)) <= 1.01 * np.spacing(scale)).all()     # <= 1 ulp of |p|
+        assert (a == b).mean() > 0.99
+
+
+def test_device_arithmetic_of_cartesian_to_sky_and_round_trip(HC, B):
+    kw = dict(z_tab_max=3)
+    cosmo, ref = B.Cosmology(**kw), CO.Cosmology(**kw)
+    z, r = product_table(B, cosmo)
+    ra, dec, red = sky_catalog(50000, 4, 2.95)
+    red = np.maximum(red, f32(0.01))
+    x, y, zz = CO.sky_to_cartesian(ra, dec, red, ref)
+    a, d, q = (np.empty_like(ra) for _ in range(3))
+    bad = HC.hc_cartesian_to_sky(fp(x), fp(y), fp(zz), len(x), f32(cosmo.h), r.ctypes.data_as(_D), z[0], (z[-1] - z[0]) / (len(z) - 1), len(z), fp(a), fp(d), fp(q))
+    assert bad == 0
+    oa, od, oq = CO.cartesian_to_sky(x, y, zz, ref)
+    assert ulps(a, oa).max() <= 1 and ulps(d, od).max() <= 1 and ulps(q, oq).max() <= 1
+    assert (a <= 0).all() and (a > -360).all()
+    assert np.abs(((a - ra + 180) % 360) - 180)[np.abs(dec) < 89].max() < 2e-4 and np.abs(q / red - 1).max() < 3e-6
+
+
+def test_out_of_table_is_counted_and_nan(HC, B):
+    cosmo = B.Cosmology(z_tab_max=1, z_tab_num=101)
+    z, r = product_table(B, cosmo)
+    ra, dec, red = f32([10, 20, 30, 40]), f32([1, 2, 3, 4]), f32([0.5, 1.0000001, -0.1, np.nan])
+    x, y, zz = (np.empty_like(ra) for _ in range(3))
+    bad = HC.hc_sky_to_cartesian(fp(ra), fp(dec), fp(red), 4, f32(0.67), r.ctypes.data_as(_D), z[0], z[-1], (z[-1] - z[0]) / (len(z) - 1), len(z), fp(x), fp(y), fp(zz))
+    assert bad == 3 and np.isfinite(x[0]) and np.isnan(x[1:]).all() and np.isnan(zz[1:]).all()
+    far = f32([r[-1] * 0.67 * 1.01, 100.0])
+    a, d, q = (np.empty_like(far) for _ in range(3))
+    bad = HC.hc_cartesian_to_sky(fp(far), fp(f32([0, 0])), fp(f32([0, 0])), 2, f32(0.67), r.ctypes.data_as(_D), z[0], (z[-1] - z[0]) / (len(z) - 1), len(z), fp(a), fp(d), fp(q))
+    assert bad == 1 and np.isnan(q[0]) and np.isfinite(q[1]) and np.isfinite(a).all()
+
+
+def test_fkp_and_wrap_bit_exact(HC):
+    rng = np.random.default_rng(5)
+    nz = (1e-3 * rng.random(10000)).astype(f32)
+    w = np.empty_like(nz)
+    HC.hc_fkp_weights(fp(nz), len(nz), f32(5e3), fp(w))
+    assert np.array_equal(w.view(np.uint32), CO.fkp_weights(nz, f32(5e3)).view(np.uint32))
+    for L, mn in (((1000.0,) * 3, (0.0,) * 3), ((500.0, 750.0, 1250.0), (-250.0, 10.0, 1e3))):
+        pos = [(m - 0.3 * l + 1.6 * l * rng.random(20000)).astype(f32) for l, m in zip(L, mn)]
+        pos[0][:5] = f32([mn[0], mn[0] + L[0], mn[0] - L[0], mn[0] + 1e-6, mn[0] - 1e-6])
+        ref = CO.wrap_positions(*pos, L, mn)
+        got = [p.copy() for p in pos]
+        HC.hc_wrap_positions(fp(got[0]), fp(got[1]), fp(got[2]), len(got[0]), fp(f32(L)), fp(f32(mn)))
+        for g, o, l, m in zip(got, ref, L, mn):
+            assert np.array_equal(g.view(np.uint32), o.view(np.uint32))
+            assert (g >= f32(m)).all() and (g <= f32(m) + f32(l)).all()
