@@ -193,6 +193,7 @@ int baorec_set_option(baorec_ctx* ctx, const char* name, int64_t value) {
   else if (s == "a2a_chunks") ctx->opt_a2a_chunks = (int)value;
   else if (s == "mg_coarse") ctx->opt_mg_coarse = (int)value;
   else if (s == "mg_bulk") ctx->opt_mg_bulk = (int)value;
+  else if (s == "catalog_corr") ctx->opt_catalog_corr = (int)value;   // test hook (catalog.cu): -1 = measured value
   else if (s == "mg_slab_min_cells") {
     ctx->opt_mg_slab_min_cells = value;
     ctx->dlevels.clear();

@@ -400,6 +400,7 @@ int baorec_destroy(baorec_ctx* ctx) {
   if (ctx->d_hash) cudaFree(ctx->d_hash);
   if (ctx->d_minmax) cudaFree(ctx->d_minmax);
   if (ctx->d_cosmo_r) cudaFree(ctx->d_cosmo_r);
+  if (ctx->d_cosmo_g) cudaFree(ctx->d_cosmo_g);
   for (int i = 0; i < 8; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (auto& r : ctx->prof) {

@@ -236,6 +236,10 @@ struct baorec_ctx {
   std::vector<double> h_cosmo_r;
   int64_t cosmo_n = 0;
   double cosmo_z0 = 0.0, cosmo_z1 = 0.0, cosmo_dz = 0.0;
+  double* d_cosmo_g = nullptr;   // guess table of the inverse interpolation (catalog_math.cuh)
+  double cosmo_inv_h = 0.0;
+  int cosmo_corr = 1;            // +-1 correction steps after the guess, measured when the table is built
+  int opt_catalog_corr = -1;     // test hook: >= 0 overrides it (0 forces the bisection path for every miss)
 };
 
 namespace baorec {

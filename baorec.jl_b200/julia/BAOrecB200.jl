@@ -294,6 +294,64 @@ function fmg(f1h::CuArray{Float32,3}, v1h::Union{CuArray{Float32,3},Nothing}, bo
     v1h
 end
 
+# ---- catalog pre/post-processing on the device (SURVEY.md 8f N1) ------------------------------------
+# The lightcone examples define sky_to_cartesian / cartesian_to_sky / fkp_weights themselves and run
+# them on CPU threads (examples/lightcone.jl:30-82); with CuVector columns these methods do the same
+# work on the device.  The comoving-distance table replaces the `cache` of
+# comoving_distance_interp / redshift_interp (src/cosmo.jl:86-103).
+struct CosmologyParams            # struct baorec_cosmology
+    h::Cdouble
+    Omega_b0::Cdouble; Omega_c0::Cdouble; Omega_nu0::Cdouble; Omega_g0::Cdouble; Omega_k0::Cdouble; Omega_L0::Cdouble
+    w0::Cdouble; wa::Cdouble
+    z_tab_min::Cdouble; z_tab_max::Cdouble
+    z_tab_num::Int64
+end
+CosmologyParams(c) = CosmologyParams(c.h, c.Ω_b₀, c.Ω_c₀, c.Ω_ν₀, c.Ω_γ₀, c.Ω_k₀, c.Ω_Λ₀, c.w0, c.wa,
+                                     c.z_tab_min, c.z_tab_max, c.z_tab_num)
+
+const BOUND_COSMO = Dict{Ptr{Cvoid},Any}()      # context -> the Cosmology whose table it holds
+function bind_cosmology!(cosmo)
+    ctx = context()
+    if get(BOUND_COSMO, ctx, nothing) !== cosmo
+        check(ccall((:baorec_cosmo_set, libbaorec), Cint, (Ptr{Cvoid}, Ref{CosmologyParams}), ctx, CosmologyParams(cosmo)))
+        BOUND_COSMO[ctx] = cosmo
+    end
+    ctx
+end
+
+function sky_to_cartesian(ra::CuVector{Float32}, dec::CuVector{Float32}, red::CuVector{Float32}, cosmo)
+    ctx = bind_cosmology!(cosmo)
+    x, y, z = similar(ra), similar(ra), similar(ra)
+    check(ccall((:baorec_sky_to_cartesian_f32, libbaorec), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cfloat, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                ctx, ptr(ra), ptr(dec), ptr(red), length(ra), Float32(cosmo.H₀ / 100), ptr(x), ptr(y), ptr(z), stream()))
+    x, y, z                        # the examples' 3 x N matrix, as three columns
+end
+
+function cartesian_to_sky(x::CuVector{Float32}, y::CuVector{Float32}, z::CuVector{Float32}, cosmo)
+    ctx = bind_cosmology!(cosmo)
+    ra, dec, red = similar(x), similar(x), similar(x)
+    check(ccall((:baorec_cartesian_to_sky_f32, libbaorec), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cfloat, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                ctx, ptr(x), ptr(y), ptr(z), length(x), Float32(cosmo.h), ptr(ra), ptr(dec), ptr(red), stream()))
+    ra, dec, red
+end
+
+function fkp_weights(nz::CuVector{Float32}, P0)
+    w = similar(nz)
+    check(ccall((:baorec_fkp_weights_f32, libbaorec), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cfloat, Ptr{Cvoid}, Ptr{Cvoid}),
+                context(), ptr(nz), length(nz), Float32(P0), ptr(w), stream()))
+    w
+end
+
+# (pos + L) % L of test_helpers/simulation.py:38, in place, for a box starting at box_min
+function wrap_positions!(x::CuVector{Float32}, y::CuVector{Float32}, z::CuVector{Float32}, box_size, box_min = (0f0, 0f0, 0f0))
+    check(ccall((:baorec_wrap_positions_f32, libbaorec), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cvoid}),
+                context(), ptr(x), ptr(y), ptr(z), length(x), f3(box_size), f3(box_min), stream()))
+    x, y, z
+end
+
 # run! needs no override: the reference's run! (src/recon.jl:134-261) allocates a CuArray mesh when
 # data_x isa CuArray and calls setup_fft!, setup_box and reconstructed_*! -- all of which dispatch
 # to the methods above.

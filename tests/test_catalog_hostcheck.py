@@ -37,13 +37,15 @@ def HC():
     lib.hc_sky_to_cartesian.restype = i64
     lib.hc_sky_to_cartesian.argtypes = [_F, _F, _F, i64, f, _D, d, d, d, i64, _F, _F, _F]
     lib.hc_cartesian_to_sky.restype = i64
-    lib.hc_cartesian_to_sky.argtypes = [_F, _F, _F, i64, f, _D, d, d, i64, _F, _F, _F]
+    lib.hc_cartesian_to_sky.argtypes = [_F, _F, _F, i64, f, _D, d, d, i64, _F, _F, _F, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    lib.hc_sincos.restype = None
+    lib.hc_sincos.argtypes = [_F, i64, _D, _D]
     lib.hc_fkp_weights.restype = None
     lib.hc_fkp_weights.argtypes = [_F, i64, f, _F]
     lib.hc_wrap_positions.restype = None
     lib.hc_wrap_positions.argtypes = [_F, _F, _F, i64, _F, _F]
-    lib.hc_coarse_layout.restype = None
-    lib.hc_coarse_layout.argtypes = [i64, C.POINTER(i64), C.POINTER(C.c_int)]
+    lib.hc_atan2.restype = None
+    lib.hc_atan2.argtypes = [_D, _D, i64, _D]
     return lib
 
 
@@ -92,14 +94,6 @@ def test_bad_cosmology_is_an_error(B):
     assert b"z_tab" in lib.baorec_last_error()
 
 
-@pytest.mark.parametrize("ntab", [2, 3, 2047, 2048, 2049, 4095, 100000, 1 << 20])
-def test_coarse_table_layout_covers_every_knot(HC, ntab):
-    s, nc = C.c_int64(), C.c_int()
-    HC.hc_coarse_layout(ntab, C.byref(s), C.byref(nc))
-    assert 2 <= nc.value <= 2048 and s.value >= 1
-    assert (nc.value - 1) * s.value >= ntab - 1 > (nc.value - 2) * s.value
-
-
 def sky_catalog(n, seed, zmax):
     rng = np.random.default_rng(seed)
     ra, dec = (360 * rng.random(n)).astype(f32), (180 * rng.random(n) - 90).astype(f32)
@@ -125,23 +119,74 @@ def test_device_arithmetic_of_sky_to_cartesian(HC, B, kw):
         assert (a == b).mean() > 0.99
 
 
-def test_device_arithmetic_of_cartesian_to_sky_and_round_trip(HC, B):
-    kw = dict(z_tab_max=3)
+def test_reduced_sincos_is_accurate_enough_to_round_correctly(HC):
+    rng = np.random.default_rng(11)
+    x = np.concatenate([(4 * np.pi * rng.random(200000) - 2 * np.pi), 1e4 * rng.standard_normal(50000),
+                        [0.0, np.pi / 2, np.pi, -np.pi / 4, 7e4, -9.9e4, 1e5, 3e7, -1e30]]).astype(f32)
+    s, c = np.empty(len(x)), np.empty(len(x))
+    HC.hc_sincos(fp(x), len(x), s.ctypes.data_as(_D), c.ctypes.data_as(_D))
+    xs = x.astype(np.float64)
+    small = np.abs(xs) < 1e5
+    # Cody-Waite + Taylor path: absolute error ~1e-16 (the library path beyond 1e5 is the platform's own sincos)
+    assert np.abs(s - np.sin(xs))[small].max() < 4e-16 and np.abs(c - np.cos(xs))[small].max() < 4e-16
+    assert np.abs(s - np.sin(xs))[~small].max() < 1e-15
+    # after the single rounding to Float32 the result is the correctly rounded one (here: always)
+    assert np.array_equal(s.astype(f32), np.sin(xs).astype(f32)) and np.array_equal(c.astype(f32), np.cos(xs).astype(f32))
+    bad = f32([np.nan, np.inf])
+    HC.hc_sincos(fp(bad), 2, s.ctypes.data_as(_D), c.ctypes.data_as(_D))
+    assert np.isnan(s[:2]).all() and np.isnan(c[:2]).all()
+
+
+def test_polynomial_atan2(HC):
+    rng = np.random.default_rng(12)
+    n = 300000
+    y, x = rng.standard_normal(n) * 10.0 ** rng.integers(-3, 4, n), rng.standard_normal(n) * 10.0 ** rng.integers(-3, 4, n)
+    sp_y = np.array([0.0, -0.0, 0.0, -0.0, 1.0, -1.0, 1.0, -1.0, 0.0, 0.0, 1.0, -1.0, np.inf, -np.inf, np.inf, np.inf, 1.0, 1e-300, 1.0])
+    sp_x = np.array([0.0, 0.0, -0.0, -0.0, 0.0, 0.0, -0.0, -0.0, 1.0, -1.0, 1.0, -1.0, np.inf, np.inf, -np.inf, 1.0, np.inf, 1e-300, -np.inf])
+    y, x = np.concatenate([y, sp_y]), np.concatenate([x, sp_x])
+    out = np.empty(len(y))
+    HC.hc_atan2(y.ctypes.data_as(_D), x.ctypes.data_as(_D), len(y), out.ctypes.data_as(_D))
+    ref = np.arctan2(y, x)
+    assert np.abs(out - ref).max() < 2e-15
+    assert np.array_equal(np.signbit(out), np.signbit(ref))                       # signed zeros: atan2(-0, +1) = -0 ...
+    assert np.array_equal(out.astype(f32), ref.astype(f32))                       # the rounded Float32 is the correctly rounded one
+    small = np.abs(ref) < 1e-3
+    sel = small & (ref != 0)
+    assert (np.abs(out[sel] / ref[sel] - 1) < 3e-15).all()              # relative accuracy near zero
+    nan = np.array([np.nan, 1.0, np.nan])
+    HC.hc_atan2(nan.ctypes.data_as(_D), np.array([1.0, np.nan, np.nan]).ctypes.data_as(_D), 3, out.ctypes.data_as(_D))
+    assert np.isnan(out[:3]).all()
+
+
+@pytest.mark.parametrize("vec4,corr", [(0, -1), (1, -1), (1, 0), (0, 3)])
+@pytest.mark.parametrize("kw", [dict(z_tab_max=3), dict(z_tab_max=3, z_tab_num=37), dict(z_tab_max=3, z_tab_num=2049),
+                                dict(z_tab_max=10), dict(z_tab_max=3, z_tab_num=1 << 20), dict(z_tab_min=0.4, z_tab_max=1.6, z_tab_num=3)])
+def test_device_arithmetic_of_cartesian_to_sky_and_round_trip(HC, B, kw, vec4, corr):
+    """corr = -1: the correction steps measured from the table (the product's setting); 0: every guess that misses its
+    interval falls through to the bisection; 3: more steps than needed.  All give the same answer."""
     cosmo, ref = B.Cosmology(**kw), CO.Cosmology(**kw)
     z, r = product_table(B, cosmo)
-    ra, dec, red = sky_catalog(50000, 4, 2.95)
-    red = np.maximum(red, f32(0.01))
+    zmin, zmax = float(kw.get("z_tab_min", 0.0)), float(kw["z_tab_max"])
+    ra, dec, red = sky_catalog(50001, 4, 1.0)
+    red = (zmin + (zmax - zmin) * np.clip(red, 0.003, 0.9999)).astype(f32)
+    if zmin == 0:
+        red[8] = f32(0.0)                                 # the first knot itself
     x, y, zz = CO.sky_to_cartesian(ra, dec, red, ref)
     a, d, q = (np.empty_like(ra) for _ in range(3))
-    bad = HC.hc_cartesian_to_sky(fp(x), fp(y), fp(zz), len(x), f32(cosmo.h), r.ctypes.data_as(_D), z[0], (z[-1] - z[0]) / (len(z) - 1), len(z), fp(a), fp(d), fp(q))
-    assert bad == 0
+    measured = C.c_int(-1)
+    bad = HC.hc_cartesian_to_sky(fp(x), fp(y), fp(zz), len(x), f32(cosmo.h), r.ctypes.data_as(_D), z[0], (z[-1] - z[0]) / (len(z) - 1), len(z), fp(a), fp(d), fp(q), vec4, corr, C.byref(measured))
+    assert bad == 0 and (measured.value == 1 or len(z) > 200000 or len(z) < 100)
     oa, od, oq = CO.cartesian_to_sky(x, y, zz, ref)
     assert ulps(a, oa).max() <= 1 and ulps(d, od).max() <= 1 and ulps(q, oq).max() <= 1
     assert (a <= 0).all() and (a > -360).all()
-    assert np.abs(((a - ra + 180) % 360) - 180)[np.abs(dec) < 89].max() < 2e-4 and np.abs(q / red - 1).max() < 3e-6
+    sel = (np.abs(dec) < 89) & (red > 0)
+    coarse_tab = len(z) < 1000          # linear interpolation error of a 37-knot table dominates there
+    assert np.abs(((a - ra + 180) % 360) - 180)[sel].max() < 2e-4
+    assert np.abs(q[red > 0] / red[red > 0] - 1).max() < (2e-3 if coarse_tab else 3e-6)
 
 
-def test_out_of_table_is_counted_and_nan(HC, B):
+@pytest.mark.parametrize("vec4", [0, 1])
+def test_out_of_table_is_counted_and_nan(HC, B, vec4):
     cosmo = B.Cosmology(z_tab_max=1, z_tab_num=101)
     z, r = product_table(B, cosmo)
     ra, dec, red = f32([10, 20, 30, 40]), f32([1, 2, 3, 4]), f32([0.5, 1.0000001, -0.1, np.nan])
@@ -150,7 +195,7 @@ def test_out_of_table_is_counted_and_nan(HC, B):
     assert bad == 3 and np.isfinite(x[0]) and np.isnan(x[1:]).all() and np.isnan(zz[1:]).all()
     far = f32([r[-1] * 0.67 * 1.01, 100.0])
     a, d, q = (np.empty_like(far) for _ in range(3))
-    bad = HC.hc_cartesian_to_sky(fp(far), fp(f32([0, 0])), fp(f32([0, 0])), 2, f32(0.67), r.ctypes.data_as(_D), z[0], (z[-1] - z[0]) / (len(z) - 1), len(z), fp(a), fp(d), fp(q))
+    bad = HC.hc_cartesian_to_sky(fp(far), fp(f32([0, 0])), fp(f32([0, 0])), 2, f32(0.67), r.ctypes.data_as(_D), z[0], (z[-1] - z[0]) / (len(z) - 1), len(z), fp(a), fp(d), fp(q), vec4, -1, None)
     assert bad == 1 and np.isnan(q[0]) and np.isfinite(q[1]) and np.isfinite(a).all()
 
 
