@@ -1,0 +1,91 @@
+// Cell / weight arithmetic of the mass-assignment kernels (mas.cu): cic! (src/mas.jl:7-35), read_cic!
+// (src/mas.jl:224-255 CPU formula, :274-306 GPU formula) and the TSC extension, as the device functions every
+// scatter / gather kernel calls.  Coordinate arithmetic uses the explicit round-to-nearest intrinsics so that
+// nvcc never contracts it into FMAs: indices and weights are bit-identical to the reference's Float32 CPU
+// arithmetic.  The product only runs these on the device; the header also compiles as plain C++
+// (-ffp-contract=off, the intrinsics mapped to the plain operators below) so that tests/hostcheck/ can run the
+// very same statements on the CPU of the build container against the CPU checker.
+#pragma once
+#include <math.h>
+
+#if !defined(__CUDACC__)
+#define __device__
+#define __forceinline__ inline
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+#endif
+
+namespace baorec {
+
+// ---- CIC scatter cell (src/mas.jl:13-35) -------------------------------------------------
+__device__ __forceinline__ float wrap_pos(float p, float mn0, float L0) {
+  // src/mas.jl:8-10 -- note: axis-1 box_min/box_size for every axis (reference quirk, kept).
+  return (__fsub_rn(p, mn0) > L0) ? __fsub_rn(p, L0) : p;
+}
+
+__device__ __forceinline__ bool cic_axis(float p, float mn, float L, int n, bool wrap, int& i0, int& i1,
+                                         float& w0, float& w1) {
+  float g = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(p, mn), (float)n), L), 1.0f);
+  if (!(g >= 1.0f && g < (float)(n + 2))) return false;
+  float f0 = floorf(g);
+  int c0 = (int)f0;  // 1-based, as in the reference
+  w1 = __fsub_rn(g, f0);
+  w0 = __fsub_rn(1.0f, w1);
+  if (c0 == n + 1) c0 = 1;
+  int c1;
+  if (c0 == n) {
+    if (!wrap) return false;  // reference: index n+1 -> BoundsError / OOB atomic
+    c1 = 1;
+  } else {
+    c1 = c0 + 1;
+  }
+  i0 = c0 - 1;
+  i1 = c1 - 1;
+  return true;
+}
+
+// ---- CIC gather cell (src/mas.jl:224-255 CPU formula; :274-306 GPU formula) ----------------
+__device__ __forceinline__ bool gather_axis(float p, float mn, float L, float cell, int n, bool gpu_formula,
+                                            int& id, int& iu, float& wd, float& wu) {
+  float d = gpu_formula ? __fdiv_rn(__fmul_rn(__fsub_rn(p, mn), (float)n), L) : __fdiv_rn(__fsub_rn(p, mn), cell);
+  if (!(d >= 0.0f && d < (float)(2 * n))) return false;
+  float f = floorf(d);
+  wu = __fsub_rn(d, f);
+  wd = __fsub_rn(1.0f, wu);
+  int i = (int)f + 1;  // 1-based
+  if (i > n) i -= n;
+  int j = i + 1;
+  if (j > n) j -= n;
+  id = i - 1;
+  iu = j - 1;
+  return true;
+}
+
+// ---- TSC (extension; same grid convention as cic!: mesh points at min + i*cell) -------------
+__device__ __forceinline__ bool tsc_axis(float p, float mn, float L, int n, bool wrap, int idx[3], float w[3]) {
+  float g = __fdiv_rn(__fmul_rn(__fsub_rn(p, mn), (float)n), L);
+  if (!(g >= -1.0f && g <= (float)(n + 1))) return false;
+  float c = floorf(__fadd_rn(g, 0.5f));
+  float d = __fsub_rn(g, c);
+  float hm = __fsub_rn(0.5f, d), hp = __fadd_rn(0.5f, d);
+  w[0] = __fmul_rn(0.5f, __fmul_rn(hm, hm));
+  w[1] = __fsub_rn(0.75f, __fmul_rn(d, d));
+  w[2] = __fmul_rn(0.5f, __fmul_rn(hp, hp));
+  int ic = (int)c;
+#pragma unroll
+  for (int o = 0; o < 3; o++) {
+    int i = ic + o - 1;
+    if (wrap) {
+      i = i < 0 ? i + n : (i >= n ? i - n : i);
+      if (i < 0 || i >= n) return false;
+    } else if (i < 0 || i >= n) {
+      return false;
+    }
+    idx[o] = i;
+  }
+  return true;
+}
+
+}  // namespace baorec
