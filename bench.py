@@ -257,6 +257,9 @@ def main():
     ap.add_argument("--mesh", type=int, default=1024)
     ap.add_argument("--particles", type=float, default=1e8)
     ap.add_argument("--ref-mesh", type=int, default=512, help="mesh size of the CPU sample (sub-volume of the workload)")
+    ap.add_argument("--catalog", default="uniform", choices=["uniform", "lognormal"],
+                    help="synthetic catalog (SURVEY.md 8d C4): uniform (the default workload) or lognormal "
+                         "(sigma = 1 on a 512^3 generation mesh + linear RSD shift, generated on the device; --gpus 1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -290,10 +293,20 @@ def main():
 
     ctx = B.Context.get(local_rank)
     rec = B.IterativeRecon(**kw)
-    if world == 1:
+    if world == 1 and args.catalog == "lognormal":
+        sys.path.insert(0, str(ROOT / "benchmarks"))
+        import catalogs
+        dpos, dwt = catalogs.lognormal_box(N, L, seed=42, device=dev, n_gen=min(n, 512), sigma=1.0, f_rsd=PARAMS["f"])
+        hx, hy, hz, hw = (torch.empty(N, dtype=torch.float32, pin_memory=True).copy_(t) for t in (*dpos, dwt))
+        del dpos, dwt
+        torch.cuda.empty_cache()
+        n_loc = N
+    elif world == 1:
         (hx, hy, hz), hw = make_catalog(N, L, seed=42, pinned=True)
         n_loc = N
     else:
+        if args.catalog != "uniform":
+            raise SystemExit("--catalog lognormal is implemented for --gpus 1 only")
         # strong scaling: the same 1e8-particle workload, sharded by z slab (each rank draws its
         # N/P particles inside its own slab; ownership re-checked with the library's own rule)
         B.dist.init_comm(ctx)
@@ -449,7 +462,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": False,
         "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"IterativeRecon periodic box, {n}^3 mesh, {N:.0e} particles (uniform, seed 42), CIC, "
+        "config": {"workload": f"IterativeRecon periodic box, {n}^3 mesh, {N:.0e} particles ({args.catalog}, seed 42), CIC, "
                                f"n_iter=3, R=15 Mpc/h, L={L:g} Mpc/h, los=(0,0,1): run! + read_shifts(:sum)",
                    "l2_policy": "inputs larger than L2 (4 GiB meshes, 1.6 GB catalog vs 126 MB L2)",
                    "ffts_per_step": (f1 - f0) / args.steps},
