@@ -9,12 +9,18 @@ from __future__ import annotations
 
 import math
 
+import numpy as np
 import torch
+
+
+def _below(L):
+    """Largest float32 below L (positions are kept strictly inside [0, L))."""
+    return float(np.nextafter(np.float32(L), np.float32(0)))
 
 
 def uniform_box(N, L, seed=42, device="cpu"):
     g = torch.Generator(device=device).manual_seed(seed)
-    top = math.nextafter(float(torch.tensor(L, dtype=torch.float32)), 0.0)
+    top = _below(L)
     pos = [(torch.rand(N, generator=g, device=device, dtype=torch.float32) * L).clamp_(max=top) for _ in range(3)]
     return pos, torch.ones(N, dtype=torch.float32, device=device)
 
@@ -59,7 +65,7 @@ def lognormal_box(N, L, seed=42, device="cpu", n_gen=256, sigma=1.0, f_rsd=0.0):
     iy = (cells // n_gen) % n_gen
     ix = cells % n_gen
     cell = L / n_gen
-    top = math.nextafter(float(torch.tensor(L, dtype=torch.float32)), 0.0)
+    top = _below(L)
     pos = []
     for idx in (ix, iy, iz):
         jitter = torch.rand(N, generator=g, device=device, dtype=torch.float32)
