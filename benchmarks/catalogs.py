@@ -58,9 +58,9 @@ def lognormal_box(N, L, seed=42, device="cpu", n_gen=256, sigma=1.0, f_rsd=0.0):
     cells = cells[perm]                                        # random order, then fix the count
     if total >= N:
         cells = cells[:N]
-    else:                                                      # top up with draws from the same density
-        extra = torch.multinomial(rho.float(), N - total, replacement=True, generator=g)
-        cells = torch.cat([cells, extra])[torch.randperm(N, generator=g, device=device)]
+    else:                                                      # top up from the same density: the cells of randomly chosen
+        pick = torch.randint(0, total, (N - total,), generator=g, device=device)   # particles already drawn (torch.multinomial
+        cells = torch.cat([cells, cells[pick]])[torch.randperm(N, generator=g, device=device)]  # stops at 2^24 categories)
     iz = cells // (n_gen * n_gen)
     iy = (cells // n_gen) % n_gen
     ix = cells % n_gen
