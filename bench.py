@@ -193,7 +193,7 @@ def cpu_oracle():
     sys.path.insert(0, str(ROOT / "oracle"))
     import baorec_oracle_fast as fast
     if fast.available():
-        O = fast.load()
+        O = fast.load(threads=os.cpu_count() or 1)      # torchrun sets OMP_NUM_THREADS=1; this leg runs on rank 0 alone
         return O, (f"C/OpenMP port of the reference's CPU methods ({O.threads} threads; scatter serial like the "
                    "reference, src/mas.jl:5) + scipy.fft on all host threads")
     import baorec_oracle as O

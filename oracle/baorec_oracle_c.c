@@ -27,6 +27,15 @@
 
 #define EXPORT __attribute__((visibility("default")))
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline runs on rank 0 alone and wants the host's cores */
+EXPORT void oc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 EXPORT int oc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

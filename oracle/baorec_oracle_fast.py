@@ -39,6 +39,8 @@ def _f32c(a):
 def _bind(lib):
     i, i64, f = C.c_int, C.c_int64, C.c_float
     lib.oc_max_threads.restype = i
+    lib.oc_set_num_threads.restype = None
+    lib.oc_set_num_threads.argtypes = [i]
     lib.oc_cic_scatter_f32.restype = i64
     lib.oc_cic_scatter_f32.argtypes = [_F, i, i, i, _F, _F, _F, _F, i64, _F, _F, i]
     lib.oc_read_cic_f32.restype = i64
@@ -66,11 +68,14 @@ def available() -> bool:
     return LIB_PATH.exists()
 
 
-def load():
-    """A private copy of the numpy oracle with its Float32 loops rebound to the C library."""
+def load(threads=None):
+    """A private copy of the numpy oracle with its Float32 loops rebound to the C library.
+    threads: OpenMP threads for the loops (default: the runtime's own choice, i.e. OMP_NUM_THREADS or all cores)."""
     if not LIB_PATH.exists():
         raise FileNotFoundError(f"{LIB_PATH} is missing: run `make -C oracle` (or __graft_entry__.build())")
     lib = _bind(C.CDLL(str(LIB_PATH)))
+    if threads:
+        lib.oc_set_num_threads(int(threads))
     spec = importlib.util.spec_from_file_location("baorec_oracle_fastcopy", HERE / "baorec_oracle.py")
     O = importlib.util.module_from_spec(spec)
     sys.modules[spec.name] = O          # dataclasses look their module up while the class body runs
