@@ -169,11 +169,11 @@ struct baorec_ctx {
   int64_t n_kernels = 0, n_fft = 0;
   bool cache_valid = false;
   bool kcache_valid = false;   // BUF_CKCACHE holds the unnormalised R2C of the cached result mesh
-  bool want_kcache = false;
+  bool want_kcache = false;    // set by the host pipeline around the solve
   const float* kcache_mesh = nullptr;  // the result mesh delta_k belongs to
-  int opt_keep_delta_k = 1;    // device API: keep delta_k of the last reconstructed_overdensity! result    // set by the host pipeline around the solve
+  int opt_keep_delta_k = 1;    // device API: keep delta_k of the last reconstructed_overdensity! result
   int64_t opt_bin_min_particles = 1 << 18;  // catalogs at least this large are z-binned first
-  int opt_fuse_kspace = 1;
+  int opt_fuse_kspace = 1;     // fixed-LOS iterations folded into one k-space pass
   int opt_scatter_tiles = 0;   // scatter: (z, y/8, x/128) tile order instead of z slabs
   // Unified sort: run! sorts the catalog ONCE into the gather's tile order (records x,y,z,w + inverse
   // permutation + a 64-bit content hash of the wrapped positions); the scatter deposits in that order
@@ -187,7 +187,7 @@ struct baorec_ctx {
   unsigned long long* d_hash = nullptr;  // [0] hash at sort time, [1] hash at read time, [2] match flag
   int64_t n_sort_reuse = 0;              // read-backs that reused the run!'s sort (diagnostics)
   int opt_gather_tiles = 1;    // gather: fine (z, y/8, x/128) tile binning instead of z slabs
-  int opt_zg_scatter = 0, opt_zg_gather = 0;  // z planes per bin (0 = auto)     // fixed-LOS iterations folded into one k-space pass
+  int opt_zg_scatter = 0, opt_zg_gather = 0;  // z planes per bin (0 = auto)
   int64_t last_wrapped = 0;  // particles whose position cic! wrapped in the last scatter
   // per-launch profiling (baorec_profile_*)
   bool prof_on = false;
