@@ -3,19 +3,10 @@
 // scatter / gather kernel calls.  Coordinate arithmetic uses the explicit round-to-nearest intrinsics so that
 // nvcc never contracts it into FMAs: indices and weights are bit-identical to the reference's Float32 CPU
 // arithmetic.  The product only runs these on the device; the header also compiles as plain C++
-// (-ffp-contract=off, the intrinsics mapped to the plain operators below) so that tests/hostcheck/ can run the
+// (-ffp-contract=off, the intrinsics mapped to the plain operators by host_shim.cuh) so that tests/hostcheck/ can run the
 // very same statements on the CPU of the build container against the CPU checker.
 #pragma once
-#include <math.h>
-
-#if !defined(__CUDACC__)
-#define __device__
-#define __forceinline__ inline
-static inline float __fadd_rn(float a, float b) { return a + b; }
-static inline float __fsub_rn(float a, float b) { return a - b; }
-static inline float __fmul_rn(float a, float b) { return a * b; }
-static inline float __fdiv_rn(float a, float b) { return a / b; }
-#endif
+#include "host_shim.cuh"
 
 namespace baorec {
 
