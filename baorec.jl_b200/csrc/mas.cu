@@ -16,16 +16,6 @@
 
 namespace baorec {
 
-struct BoxGeom {
-  float mn[3];
-  float L[3];
-  float cell[3];
-  int n[3];
-  // slab decomposition (multi-GPU): the mesh buffer holds nzp planes; global plane z maps to local
-  // plane (z - z_lo + zoff) (periodic); slab == 0 -> the whole mesh, planes wrap at n[2]
-  int slab, z_lo, zoff, nzp;
-};
-
 static BoxGeom geom_of(const baorec_ctx* ctx) {
   BoxGeom g;
   for (int a = 0; a < 3; a++) {
@@ -41,22 +31,6 @@ static BoxGeom geom_of(const baorec_ctx* ctx) {
   g.zoff = ctx->slab_mode == 2 ? 1 : 0;  // gather slabs carry one halo plane below and two above
   g.nzp = ctx->slab_mode == 1 ? ctx->nz_loc + 1 : (ctx->slab_mode == 2 ? ctx->nz_loc + 3 : ctx->nz);
   return g;
-}
-
-// Global plane indices (lower, upper-wrapped) -> plane indices in the local buffer.
-__device__ __forceinline__ bool local_planes(const BoxGeom& g, int z0, int z1, int& l0, int& l1) {
-  if (!g.slab) {
-    l0 = z0;
-    l1 = z1;
-    return true;
-  }
-  const int nz = g.n[2];
-  int dz = z0 - g.z_lo;          // in (-nz, nz)
-  if (dz < 0) dz += nz;          // periodic distance above the slab base, in [0, nz)
-  if (dz + g.zoff > g.nzp - 2) dz -= nz;  // not reachable from below: it is a plane under the slab
-  l0 = dz + g.zoff;
-  l1 = l0 + 1;
-  return l0 >= 0 && l1 < g.nzp;
 }
 
 // ---- per-particle bodies ---------------------------------------------------------------------

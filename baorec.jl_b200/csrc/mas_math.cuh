@@ -10,6 +10,16 @@
 
 namespace baorec {
 
+struct BoxGeom {
+  float mn[3];
+  float L[3];
+  float cell[3];
+  int n[3];
+  // slab decomposition (multi-GPU): the mesh buffer holds nzp planes; global plane z maps to local
+  // plane (z - z_lo + zoff) (periodic); slab == 0 -> the whole mesh, planes wrap at n[2]
+  int slab, z_lo, zoff, nzp;
+};
+
 // ---- CIC scatter cell (src/mas.jl:13-35) -------------------------------------------------
 __device__ __forceinline__ float wrap_pos(float p, float mn0, float L0) {
   // src/mas.jl:8-10 -- note: axis-1 box_min/box_size for every axis (reference quirk, kept).
@@ -77,6 +87,22 @@ __device__ __forceinline__ bool tsc_axis(float p, float mn, float L, int n, bool
     idx[o] = i;
   }
   return true;
+}
+
+// Global plane indices (lower, upper-wrapped) -> plane indices in the local buffer.
+__device__ __forceinline__ bool local_planes(const BoxGeom& g, int z0, int z1, int& l0, int& l1) {
+  if (!g.slab) {
+    l0 = z0;
+    l1 = z1;
+    return true;
+  }
+  const int nz = g.n[2];
+  int dz = z0 - g.z_lo;          // in (-nz, nz)
+  if (dz < 0) dz += nz;          // periodic distance above the slab base, in [0, nz)
+  if (dz + g.zoff > g.nzp - 2) dz -= nz;  // not reachable from below: it is a plane under the slab
+  l0 = dz + g.zoff;
+  l1 = l0 + 1;
+  return l0 >= 0 && l1 < g.nzp;
 }
 
 }  // namespace baorec
