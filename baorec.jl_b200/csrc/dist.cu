@@ -676,10 +676,41 @@ int baorec_dist_c2r_f32(baorec_ctx* ctx, float* d_kslab_t, float* d_slab, baorec
   return dist_c2r(ctx, (float2*)d_kslab_t, d_slab, (cudaStream_t)stream);
 }
 
+// TSC scatter on slabs.  The 27-point stencil of a particle owned by this slab (owner = slab of its cic! base
+// plane, the same sharding as CIC) reaches one plane below the slab and two above it, so the deposit goes into a
+// scratch buffer of (nz_loc + 3) planes with the real planes at 1 .. nz_loc (slab_mode 3 = the gather's halo
+// layout).  Then the boundary-cell exchange: the plane below goes to the previous rank and is added to its last
+// real plane, the two planes above go to the next rank and are added to its first two; finally the real planes
+// are copied to `loc` (planes 0 .. nz_loc-1), where the transform expects them.
+static int dist_scatter_tsc(baorec_ctx* ctx, float* loc, float* x, float* y, float* z, const float* w, int64_t n,
+                            int wrap, cudaStream_t st) {
+  const int P = ctx->nranks, nzl = ctx->nz_loc;
+  const size_t plane = (size_t)ctx->ny * ctx->nx;
+  const int next = (ctx->rank + 1) % P, prev = (ctx->rank + P - 1) % P;
+  BR_REQUIRE(nzl >= 2, "TSC on slabs needs at least two planes per rank");
+  float* buf;
+  BR_TRY(need_t(ctx, BUF_HALO, (size_t)(nzl + 5) * plane, &buf));
+  float* halo = buf + (size_t)(nzl + 3) * plane;  // two planes of receive space
+  BR_CUDA(cudaMemsetAsync(buf, 0, (size_t)(nzl + 3) * plane * sizeof(float), st));
+  ctx->slab_mode = 3;
+  int s = scatter(ctx, buf, x, y, z, w, n, wrap, BAOREC_MAS_TSC, st);
+  ctx->slab_mode = 0;
+  if (s != BAOREC_OK) return s;
+  // plane 0 (below the slab) -> previous rank; what arrives from the next rank belongs to our last real plane
+  BR_TRY(ring_exchange(ctx, buf, prev, halo, next, plane, st));
+  BR_LAUNCH(ctx, add_plane_kernel, cdiv(plane, 256), 256, 0, st, buf + (size_t)nzl * plane, halo, plane);
+  // planes nz_loc+1, nz_loc+2 (above the slab) -> next rank; what arrives from the previous rank belongs to our first two
+  BR_TRY(ring_exchange(ctx, buf + (size_t)(nzl + 1) * plane, next, halo, prev, 2 * plane, st));
+  BR_LAUNCH(ctx, add_plane_kernel, cdiv(2 * plane, 256), 256, 0, st, buf + plane, halo, 2 * plane);
+  BR_CUDA(cudaMemcpyAsync(loc, buf + plane, (size_t)nzl * plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return BAOREC_OK;
+}
+
 // Scatter this rank's particles into `loc` ((nz_loc+1) planes, zero-filled here); the ghost plane
 // (global plane z_lo + nz_loc) belongs to the next rank: send it, add what arrives from below.
 static int dist_scatter(baorec_ctx* ctx, float* loc, float* x, float* y, float* z, const float* w, int64_t n,
                         int wrap, int mas, cudaStream_t st) {
+  if (mas == BAOREC_MAS_TSC) return dist_scatter_tsc(ctx, loc, x, y, z, w, n, wrap, st);
   const int P = ctx->nranks, nzl = ctx->nz_loc;
   const size_t plane = (size_t)ctx->ny * ctx->nx;
   float* halo;
@@ -756,10 +787,7 @@ int baorec_run_dist_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, 
   BR_REQUIRE(n_local >= 0 && (n_local == 0 || (d_x && d_y && d_z && d_w)), "particle arrays");
   BR_REQUIRE(n_ran_local >= 0 && (n_ran_local == 0 || (d_rx && d_ry && d_rz && d_rw)), "randoms arrays");
   BR_REQUIRE(has_randoms || n_ran_local == 0, "randoms passed with has_randoms == 0");
-  if (p->mas != BAOREC_MAS_CIC) {
-    set_error("baorec_run_dist_f32: the slab-decomposed path supports CIC only (TSC needs two ghost planes)");
-    return BAOREC_ERR_INVALID;
-  }
+  BR_REQUIRE(p->mas == BAOREC_MAS_CIC || p->mas == BAOREC_MAS_TSC, "unknown mass-assignment scheme");
   cudaStream_t st = (cudaStream_t)stream;
   const int nzl = ctx->nz_loc;
   const size_t plane = (size_t)ctx->ny * ctx->nx;

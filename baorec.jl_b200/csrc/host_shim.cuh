@@ -19,4 +19,9 @@ struct float2 {
   float x, y;
 };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline float atomicAdd(float* p, float v) {   // the host check runs one particle at a time
+  const float old = *p;
+  *p = old + v;
+  return old;
+}
 #endif

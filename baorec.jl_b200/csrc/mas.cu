@@ -28,60 +28,11 @@ static BoxGeom geom_of(const baorec_ctx* ctx) {
   g.n[2] = ctx->nz;
   g.slab = ctx->slab_mode != 0;
   g.z_lo = g.slab ? ctx->z0 : 0;
-  g.zoff = ctx->slab_mode == 2 ? 1 : 0;  // gather slabs carry one halo plane below and two above
-  g.nzp = ctx->slab_mode == 1 ? ctx->nz_loc + 1 : (ctx->slab_mode == 2 ? ctx->nz_loc + 3 : ctx->nz);
+  // slab_mode 1: CIC scatter (one ghost plane above); 2: gather (one halo plane below, two above);
+  // 3: TSC scatter (one ghost plane below, two above -- the same layout as the gather's)
+  g.zoff = ctx->slab_mode >= 2 ? 1 : 0;
+  g.nzp = ctx->slab_mode == 1 ? ctx->nz_loc + 1 : (ctx->slab_mode >= 2 ? ctx->nz_loc + 3 : ctx->nz);
   return g;
-}
-
-// ---- per-particle bodies ---------------------------------------------------------------------
-// Deposit one (already wrapped) particle.  Returns false if it is outside the mesh.
-template <int MAS>
-__device__ __forceinline__ bool deposit(float* __restrict__ rho, float px, float py, float pz, float ww,
-                                        const BoxGeom& g, bool wrap) {
-  const size_t nx = g.n[0], ny = g.n[1];
-  if (MAS == BAOREC_MAS_CIC) {
-    int x0, x1, y0, y1, z0, z1;
-    float wx0, wx1, wy0, wy1, wz0, wz1;
-    bool ok = cic_axis(px, g.mn[0], g.L[0], g.n[0], wrap, x0, x1, wx0, wx1);
-    ok = cic_axis(py, g.mn[1], g.L[1], g.n[1], wrap, y0, y1, wy0, wy1) && ok;
-    ok = cic_axis(pz, g.mn[2], g.L[2], g.n[2], wrap, z0, z1, wz0, wz1) && ok;
-    if (!ok || !local_planes(g, z0, z1, z0, z1)) return false;
-    wx0 = __fmul_rn(wx0, ww);
-    wx1 = __fmul_rn(wx1, ww);
-    size_t r00 = ((size_t)z0 * ny + y0) * nx, r10 = ((size_t)z0 * ny + y1) * nx;
-    size_t r01 = ((size_t)z1 * ny + y0) * nx, r11 = ((size_t)z1 * ny + y1) * nx;
-    float a00 = __fmul_rn(wx0, wy0), a10 = __fmul_rn(wx1, wy0), a01 = __fmul_rn(wx0, wy1),
-          a11 = __fmul_rn(wx1, wy1);
-    atomicAdd(rho + r00 + x0, __fmul_rn(a00, wz0));
-    atomicAdd(rho + r00 + x1, __fmul_rn(a10, wz0));
-    atomicAdd(rho + r10 + x0, __fmul_rn(a01, wz0));
-    atomicAdd(rho + r01 + x0, __fmul_rn(a00, wz1));
-    atomicAdd(rho + r10 + x1, __fmul_rn(a11, wz0));
-    atomicAdd(rho + r01 + x1, __fmul_rn(a10, wz1));
-    atomicAdd(rho + r11 + x0, __fmul_rn(a01, wz1));
-    atomicAdd(rho + r11 + x1, __fmul_rn(a11, wz1));
-    return true;
-  } else {
-    int ix[3], iy[3], iz[3];
-    float wx[3], wy[3], wz[3];
-    bool ok = tsc_axis(px, g.mn[0], g.L[0], g.n[0], wrap, ix, wx);
-    ok = tsc_axis(py, g.mn[1], g.L[1], g.n[1], wrap, iy, wy) && ok;
-    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], wrap, iz, wz) && ok;
-    if (!ok || g.slab) return false;  // TSC slabs (two ghost planes) are not implemented
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-#pragma unroll
-      for (int b = 0; b < 3; b++) {
-        size_t row = ((size_t)iz[c] * ny + iy[b]) * nx;
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-          float v = __fmul_rn(__fmul_rn(__fmul_rn(wx[a], ww), wy[b]), wz[c]);
-          atomicAdd(rho + row + ix[a], v);
-        }
-      }
-    }
-    return true;
-  }
 }
 
 struct GatherArgs {
@@ -198,7 +149,11 @@ __device__ __forceinline__ bool gather_one(const GatherArgs& a, const BoxGeom& g
     float wx[3], wy[3], wz[3];
     ok = tsc_axis(px, g.mn[0], g.L[0], g.n[0], true, ix, wx);
     ok = tsc_axis(py, g.mn[1], g.L[1], g.n[1], true, iy, wy) && ok;
-    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], true, iz, wz) && ok && !g.slab;
+    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], true, iz, wz) && ok;
+    if (ok && g.slab) {  // slab layout (multi-GPU): halo planes below / above the slab
+#pragma unroll
+      for (int c = 0; c < 3; c++) ok = local_plane1(g, iz[c], iz[c]) && ok;
+    }
     if (ok) {
 #pragma unroll
       for (int c = 0; c < NF; c++) val[c] = 0.f;
@@ -291,8 +246,12 @@ __device__ __forceinline__ int bin_key(float& px, float& py, float& pz, const Bo
     bool wr = MODE == BIN_GATHER ? true : (wrap != 0);
     ok = tsc_axis(px, g.mn[0], g.L[0], g.n[0], wr, idx, w);
     ok = tsc_axis(py, g.mn[1], g.L[1], g.n[1], wr, idx, w) && ok;
-    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], wr, idx, w) && ok && !g.slab;
+    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], wr, idx, w) && ok;
     zb = idx[1];
+    if (ok && g.slab) {  // bins are planes of the local buffer: the centre plane, provided the whole stencil is local
+      int lo, hi;
+      ok = local_plane1(g, idx[0], lo) && local_plane1(g, idx[2], hi) && local_plane1(g, idx[1], zb);
+    }
   } else {
     int id, iu;
     float wd, wu;
@@ -502,8 +461,12 @@ __device__ __forceinline__ unsigned tile_key(float px, float py, float pz, const
     ix = idx[1];
     ok = tsc_axis(py, g.mn[1], g.L[1], g.n[1], true, idx, w) && ok;
     iy = idx[1];
-    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], true, idx, w) && ok && !g.slab;
+    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], true, idx, w) && ok;
     iz = idx[1];
+    if (ok && g.slab) {  // tiles are planes of the local buffer: the centre plane, provided the whole stencil is local
+      int lo, hi;
+      ok = local_plane1(g, idx[0], lo) && local_plane1(g, idx[2], hi) && local_plane1(g, idx[1], iz);
+    }
   } else {
     int iu;
     float wd, wu;

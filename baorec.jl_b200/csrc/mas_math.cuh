@@ -6,6 +6,9 @@
 // (-ffp-contract=off, the intrinsics mapped to the plain operators by host_shim.cuh) so that tests/hostcheck/ can run the
 // very same statements on the CPU of the build container against the CPU checker.
 #pragma once
+#include <stddef.h>
+
+#include "baorec_b200.h"
 #include "host_shim.cuh"
 
 namespace baorec {
@@ -103,6 +106,79 @@ __device__ __forceinline__ bool local_planes(const BoxGeom& g, int z0, int z1, i
   l0 = dz + g.zoff;
   l1 = l0 + 1;
   return l0 >= 0 && l1 < g.nzp;
+}
+
+// One global plane index (already wrapped into [0, nz)) -> its plane in the local buffer.  The TSC stencil of a
+// particle owned by this slab (owner = slab of its cic! base plane floor(g), the same sharding as CIC) reaches
+// from one plane below the slab to two above it: both TSC slab layouts carry (nz_loc + 3) planes with the real
+// planes at 1 .. nz_loc.
+__device__ __forceinline__ bool local_plane1(const BoxGeom& g, int z, int& l) {
+  if (!g.slab) {
+    l = z;
+    return true;
+  }
+  const int nz = g.n[2];
+  int dz = z - g.z_lo;
+  if (dz < 0) dz += nz;                   // periodic distance above the slab base, in [0, nz)
+  if (dz + g.zoff > g.nzp - 1) dz -= nz;  // not reachable from below: it is a plane under the slab
+  l = dz + g.zoff;
+  return l >= 0 && l < g.nzp;
+}
+
+// ---- per-particle bodies ---------------------------------------------------------------------
+// Deposit one (already wrapped) particle.  Returns false if it is outside the mesh.
+template <int MAS>
+__device__ __forceinline__ bool deposit(float* __restrict__ rho, float px, float py, float pz, float ww,
+                                        const BoxGeom& g, bool wrap) {
+  const size_t nx = g.n[0], ny = g.n[1];
+  if (MAS == BAOREC_MAS_CIC) {
+    int x0, x1, y0, y1, z0, z1;
+    float wx0, wx1, wy0, wy1, wz0, wz1;
+    bool ok = cic_axis(px, g.mn[0], g.L[0], g.n[0], wrap, x0, x1, wx0, wx1);
+    ok = cic_axis(py, g.mn[1], g.L[1], g.n[1], wrap, y0, y1, wy0, wy1) && ok;
+    ok = cic_axis(pz, g.mn[2], g.L[2], g.n[2], wrap, z0, z1, wz0, wz1) && ok;
+    if (!ok || !local_planes(g, z0, z1, z0, z1)) return false;
+    wx0 = __fmul_rn(wx0, ww);
+    wx1 = __fmul_rn(wx1, ww);
+    size_t r00 = ((size_t)z0 * ny + y0) * nx, r10 = ((size_t)z0 * ny + y1) * nx;
+    size_t r01 = ((size_t)z1 * ny + y0) * nx, r11 = ((size_t)z1 * ny + y1) * nx;
+    float a00 = __fmul_rn(wx0, wy0), a10 = __fmul_rn(wx1, wy0), a01 = __fmul_rn(wx0, wy1),
+          a11 = __fmul_rn(wx1, wy1);
+    atomicAdd(rho + r00 + x0, __fmul_rn(a00, wz0));
+    atomicAdd(rho + r00 + x1, __fmul_rn(a10, wz0));
+    atomicAdd(rho + r10 + x0, __fmul_rn(a01, wz0));
+    atomicAdd(rho + r01 + x0, __fmul_rn(a00, wz1));
+    atomicAdd(rho + r10 + x1, __fmul_rn(a11, wz0));
+    atomicAdd(rho + r01 + x1, __fmul_rn(a10, wz1));
+    atomicAdd(rho + r11 + x0, __fmul_rn(a01, wz1));
+    atomicAdd(rho + r11 + x1, __fmul_rn(a11, wz1));
+    return true;
+  } else {
+    int ix[3], iy[3], iz[3];
+    float wx[3], wy[3], wz[3];
+    bool ok = tsc_axis(px, g.mn[0], g.L[0], g.n[0], wrap, ix, wx);
+    ok = tsc_axis(py, g.mn[1], g.L[1], g.n[1], wrap, iy, wy) && ok;
+    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], wrap, iz, wz) && ok;
+    if (!ok) return false;
+    if (g.slab) {  // slab layout (multi-GPU): the three stencil planes in the local (nz_loc + 3)-plane buffer
+#pragma unroll
+      for (int c = 0; c < 3; c++) ok = local_plane1(g, iz[c], iz[c]) && ok;
+      if (!ok) return false;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+#pragma unroll
+      for (int b = 0; b < 3; b++) {
+        size_t row = ((size_t)iz[c] * ny + iy[b]) * nx;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          float v = __fmul_rn(__fmul_rn(__fmul_rn(wx[a], ww), wy[b]), wz[c]);
+          atomicAdd(rho + row + ix[a], v);
+        }
+      }
+    }
+    return true;
+  }
 }
 
 }  // namespace baorec

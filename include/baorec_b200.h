@@ -160,7 +160,10 @@ int baorec_dist_c2r_f32(baorec_ctx* ctx, float* d_kslab_t /* destroyed */, float
  *   MultigridRecon: fmg (src/multigrid.jl:722-752) on slabs, one halo-plane exchange with both
  *   ring neighbours after every Jacobi sweep / residual / prolongation; levels smaller than
  *   option "mg_slab_min_cells" (default 2^22 cells: 128^3 and below) are all-gathered and solved on every rank.
- * delta_k (phi_k) is kept, transposed, for baorec_read_shifts_dist_f32.  CIC only. */
+ * delta_k (phi_k) is kept, transposed, for baorec_read_shifts_dist_f32.
+ * p->mas = BAOREC_MAS_TSC: the 27-point stencil reaches one plane below the slab and two above it; the deposit goes
+ * into a (nz_loc + 3)-plane scratch and the boundary planes are exchanged with both ring neighbours and added
+ * (needs nz_loc >= 2).  Particles are sharded exactly as for CIC (baorec_slab_owner_f32). */
 int baorec_run_dist_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, float* d_x, float* d_y, float* d_z,
                         const float* d_w, int64_t n_local, float* d_rx, float* d_ry, float* d_rz, const float* d_rw,
                         int64_t n_ran_local, int has_randoms, float* d_mesh_slab, baorec_stream stream);

@@ -66,4 +66,75 @@ void hc_tsc_cells(const float* x, const float* y, const float* z, int64_t n, con
   }
 }
 
+static BoxGeom make_geom(const int* ng, const float* L, const float* mn, int slab, int z_lo, int zoff, int nzp) {
+  BoxGeom g;
+  for (int a = 0; a < 3; a++) {
+    g.mn[a] = mn[a];
+    g.L[a] = L[a];
+    g.cell[a] = L[a] / (float)ng[a];
+    g.n[a] = ng[a];
+  }
+  g.slab = slab;
+  g.z_lo = z_lo;
+  g.zoff = zoff;
+  g.nzp = nzp;
+  return g;
+}
+
+// The product's deposit<MAS> (mas_math.cuh) for a list of particles into a local buffer of nzp planes, exactly as
+// scatter_direct_kernel calls it (cic! wraps the position first).  slab = 0: whole mesh (nzp = nz); slab = 1 with
+// (zoff, nzp) = (0, nz_loc + 1): CIC slab scatter; (1, nz_loc + 3): TSC slab scatter.  Returns the rejected count.
+int64_t hc_deposit(int mas, float* buf, const float* x, const float* y, const float* z, const float* w, int64_t n, const int* ng,
+                   const float* L, const float* mn, int wrap, int slab, int z_lo, int zoff, int nzp) {
+  const BoxGeom g = make_geom(ng, L, mn, slab, z_lo, zoff, nzp);
+  int64_t bad = 0;
+  for (int64_t i = 0; i < n; i++) {
+    float px = x[i], py = y[i], pz = z[i];
+    bool ok;
+    if (mas == BAOREC_MAS_CIC) {
+      if (wrap) {
+        px = wrap_pos(px, g.mn[0], g.L[0]);
+        py = wrap_pos(py, g.mn[0], g.L[0]);
+        pz = wrap_pos(pz, g.mn[0], g.L[0]);
+      }
+      ok = deposit<BAOREC_MAS_CIC>(buf, px, py, pz, w[i], g, wrap != 0);
+    } else {
+      ok = deposit<BAOREC_MAS_TSC>(buf, px, py, pz, w[i], g, wrap != 0);
+    }
+    if (!ok) bad++;
+  }
+  return bad;
+}
+
+// TSC gather from a halo'd slab buffer (slab_mode 2: zoff = 1, nzp = nz_loc + 3): the loop of gather_one<1, TSC>
+// in mas.cu, with the product's tsc_axis and local_plane1 doing the index work.  Returns the rejected count.
+int64_t hc_tsc_gather(const float* buf, const float* x, const float* y, const float* z, int64_t n, const int* ng, const float* L,
+                      const float* mn, int slab, int z_lo, int zoff, int nzp, float* out) {
+  const BoxGeom g = make_geom(ng, L, mn, slab, z_lo, zoff, nzp);
+  const size_t nx = g.n[0], ny = g.n[1];
+  int64_t bad = 0;
+  for (int64_t i = 0; i < n; i++) {
+    int ix[3], iy[3], iz[3];
+    float wx[3], wy[3], wz[3];
+    bool ok = tsc_axis(x[i], g.mn[0], g.L[0], g.n[0], true, ix, wx);
+    ok = tsc_axis(y[i], g.mn[1], g.L[1], g.n[1], true, iy, wy) && ok;
+    ok = tsc_axis(z[i], g.mn[2], g.L[2], g.n[2], true, iz, wz) && ok;
+    if (ok && g.slab)
+      for (int c = 0; c < 3; c++) ok = local_plane1(g, iz[c], iz[c]) && ok;
+    float val = 0.f;
+    if (ok) {
+      for (int oz = 0; oz < 3; oz++)
+        for (int oy = 0; oy < 3; oy++) {
+          const size_t row = ((size_t)iz[oz] * ny + iy[oy]) * nx;
+          for (int ox = 0; ox < 3; ox++)
+            val = __fadd_rn(val, __fmul_rn(__fmul_rn(__fmul_rn(buf[row + ix[ox]], wx[ox]), wy[oy]), wz[oz]));
+        }
+    } else {
+      bad++;
+    }
+    out[i] = val;
+  }
+  return bad;
+}
+
 }  // extern "C"

@@ -102,6 +102,35 @@ def more_modes(B, ctx, rank, world, quick=False):
     return ok
 
 
+def tsc_modes(B, ctx, rank, world):
+    """IterativeRecon with TSC on slabs: periodic box (wrap across the last / first slab) and a radial line of sight."""
+    ok = True
+    n, L, N = 64, 1000.0, 400_000
+    if n % (2 * world):
+        return ok
+    for los, lo in (((0.0, 0.0, 1.0), 0.0), (None, 700.0)):
+        pos, w = clustered_box(N, L, seed=13, lo=lo)
+        kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=np.full(3, L, np.float32),
+                  box_min=np.full(3, lo, np.float32), los=los, n_iter=3)
+        orec = O.IterativeRecon(mas="tsc", **kw)
+        omesh = O.run(orec, (n, n, n), *[p.copy() for p in pos], w)
+        oshift = O.read_shifts(orec, *pos, omesh, "sum")
+        mine = B.dist.owner_of_z(pos[2], lo, L, n, world) == rank
+        d = [torch.from_numpy(np.ascontiguousarray(p[mine])).cuda() for p in pos]
+        rec = B.IterativeRecon(mas="tsc", **kw)
+        mesh = B.dist.run_dist(rec, (n, n, n), *d, torch.from_numpy(np.ascontiguousarray(w[mine])).cuda(), ctx=ctx)
+        z_lo, nzl = B.dist.slab_range(ctx)
+        s = B.dist.read_shifts_dist(rec, *d, field="sum")
+        e_mesh = rel_rms(mesh.cpu().numpy(), omesh[z_lo:z_lo + nzl])
+        e_rms = max(rel_rms(s[a].cpu().numpy(), oshift[a][mine]) for a in range(3))
+        e_max = max(maxabs(s[a].cpu().numpy(), oshift[a][mine]) for a in range(3))
+        good = e_mesh < 1e-4 and e_rms < 1e-4 and e_max < 1e-3
+        ok &= good
+        print(f"[rank {rank}/{world}] TSC los={los}: mesh rel.rms={e_mesh:.2e} shift rel.rms={e_rms:.2e} max={e_max:.2e} "
+              f"{'OK' if good else 'FAIL'}", flush=True)
+    return ok
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -139,6 +168,8 @@ def main():
               f"mesh rel.rms={e_mesh:.2e} shift rel.rms={e_rms:.2e} max={e_max:.2e} {'OK' if good else 'FAIL'}",
               flush=True)
     ok &= more_modes(B, ctx, rank, world, quick)
+    if os.environ.get("MGC_TSC") == "1":                 # TSC on slabs (boundary-cell exchange: 1 ghost plane below, 2 above);
+        ok &= tsc_modes(B, ctx, rank, world)             # opt-in until it has run on hardware once
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

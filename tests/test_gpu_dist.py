@@ -84,13 +84,10 @@ def test_run_dist_matches_single_gpu_and_oracle(B, O, dctx, los):
         assert maxabs(newpos[a].cpu().numpy(), opos[a] - oshift[a]) < 1e-3
 
 
-def test_run_dist_rejects_unsupported_modes(B, dctx):
-    n, L = 32, 100.0
-    e = torch.zeros(4, dtype=torch.float32, device="cuda") + 5
-    rec = B.IterativeRecon(bias=2.0, f=0.5, smoothing_radius=5.0, box_size=np.full(3, L, np.float32),
-                           box_min=np.zeros(3, np.float32), los=(0.0, 0.0, 1.0), mas="tsc")
-    with pytest.raises(B.BaorecError):
-        B.dist.run_dist(rec, (n, n, n), e, e, e, e, ctx=dctx)
+def test_read_shifts_dist_needs_a_run_first(B):
+    """(TSC on slabs used to be rejected here; it is supported now: tests/test_gpu_zzzz_dist_tsc.py.)"""
+    lib = B.lib_loader.load()
+    assert lib.baorec_read_shifts_dist_f32(None, None, None, None, None, 0, 0, 0, None, None, None, None) == B.lib_loader.ERR_INVALID
 
 
 def filled_box(n_data, n_rand, L, lo, n, seed):

@@ -30,11 +30,12 @@ def ip(a):
 def HC():
     out = ROOT / "tests" / "_build" / "libmas_hostcheck.so"
     src = ROOT / "tests" / "hostcheck" / "mas_hostcheck.cpp"
-    hdr = ROOT / "baorec.jl_b200" / "csrc" / "mas_math.cuh"
-    if not out.exists() or out.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime):
+    hdrs = [ROOT / "baorec.jl_b200" / "csrc" / h for h in ("mas_math.cuh", "host_shim.cuh")]
+    if not out.exists() or out.stat().st_mtime < max(p.stat().st_mtime for p in [src] + hdrs):
         out.parent.mkdir(exist_ok=True)
         gxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
-        subprocess.run([gxx, "-O2", "-ffp-contract=off", "-Wno-unknown-pragmas", "-shared", "-fPIC", "-o", str(out), str(src)], check=True)
+        subprocess.run([gxx, "-O2", "-ffp-contract=off", "-Wno-unknown-pragmas", "-I", str(ROOT / "include"), "-shared", "-fPIC",
+                        "-o", str(out), str(src)], check=True)
     lib = C.CDLL(str(out))
     i64, i = C.c_int64, C.c_int
     lib.hc_cic_cells.restype = None
@@ -43,6 +44,10 @@ def HC():
     lib.hc_gather_cells.argtypes = [_F, _F, _F, i64, _I, _F, _F, _F, i, _I, _I, _F, _F]
     lib.hc_tsc_cells.restype = None
     lib.hc_tsc_cells.argtypes = [_F, _F, _F, i64, _I, _F, _F, i, _I, _F, _I]
+    lib.hc_deposit.restype = i64
+    lib.hc_deposit.argtypes = [i, _F, _F, _F, _F, _F, i64, _I, _F, _F, i, i, i, i, i]
+    lib.hc_tsc_gather.restype = i64
+    lib.hc_tsc_gather.argtypes = [_F, _F, _F, _F, i64, _I, _F, _F, i, i, i, i, _F]
     return lib
 
 
@@ -124,3 +129,116 @@ def test_tsc_cells_bit_exact(HC, n, L, lo):
             assert np.array_equal(idx[a, o], np.mod(ic[a] + o - 1, n).astype(np.int32))
             assert np.array_equal(u32(w[a, o]), u32(wref))
         assert np.abs(w[a].sum(axis=0) - 1).max() < 3e-7                      # partition of unity
+
+
+# ---- the slab-decomposed (multi-GPU) scatter / gather schemes, emulated rank by rank on the CPU -------------------
+# Each "rank" runs the product's own deposit<MAS> / tsc_axis / local_plane(s) on its particles into a local buffer
+# with ghost planes; numpy then performs the boundary-cell exchange exactly as dist.cu's dist_scatter /
+# dist_scatter_tsc do (ring_exchange + add_plane), and the assembled mesh must be the oracle's global one.
+CIC, TSC = 0, 1
+
+
+def shard(B, pos, w, lo, L, nz, P):
+    own = B.dist.owner_of_z(pos[2], lo, L, nz, P)
+    assert (own >= 0).all()
+    return [([np.ascontiguousarray(p[own == r]) for p in pos], np.ascontiguousarray(w[own == r])) for r in range(P)]
+
+
+def slab_catalog(n, L, lo, seed, wrap):
+    rng = np.random.default_rng(seed)
+    pos, w = [], (0.5 + rng.random(30000)).astype(f32)
+    for a in range(3):
+        frac = rng.random(30000) if wrap else 0.15 + 0.65 * rng.random(30000)     # wrap = false: stencils stay inside the mesh
+        p = (lo + L[a] * frac).astype(f32)
+        if wrap:                                                                    # include both faces and cell boundaries
+            p[:4] = f32([lo, np.nextafter(f32(lo + L[a]), f32(lo)), lo + L[a] / n[a] * 3, lo + L[a] * 0.5])
+        np.clip(p, f32(lo), np.nextafter(f32(lo + L[a]), f32(lo)), out=p)
+        pos.append(p)
+    return pos, w
+
+
+@pytest.mark.parametrize("P", [1, 2, 4, 8])
+@pytest.mark.parametrize("mas,wrap", [(CIC, True), (TSC, True), (TSC, False), (CIC, False)])
+def test_slab_scatter_scheme_reassembles_the_global_mesh(HC, B, P, mas, wrap):
+    n = (12, 10, 16)                                   # (nx, ny, nz); nz divisible by every P with >= 2 planes per rank
+    L, lo = f32([300.0, 250.0, 400.0]), -50.0
+    bs, bm = L, np.full(3, lo, f32)
+    pos, w = slab_catalog(n, L, lo, 21 + P, wrap)
+    if wrap and mas == CIC:                            # cic! wraps with the axis-1 box (quirk): keep the catalog inside it
+        pos = [np.minimum(p, np.nextafter(f32(lo + L[0] * 0.83), f32(lo))) if a == 2 else p for a, p in enumerate(pos)]
+        pos[1] = np.minimum(pos[1], np.nextafter(f32(lo + L[1]), f32(lo)))
+    ref = np.zeros((n[2], n[1], n[0]), f32)
+    if mas == CIC:
+        O.cic_scatter(ref, *[p.copy() for p in pos], w, bs, bm, wrap)
+    else:
+        O.tsc_scatter(ref, *[p.copy() for p in pos], w, bs, bm, wrap)
+    nzl, plane = n[2] // P, n[1] * n[0]
+    ghosts_below, ghosts_above = (0, 1) if mas == CIC else (1, 2)
+    nzp = nzl + ghosts_below + ghosts_above
+    ng = np.asarray(n, np.int32)
+    bufs = []
+    for r, ((px, py, pz), pw) in enumerate(shard(B, pos, w, lo, float(L[2]), n[2], P)):
+        buf = np.zeros((nzp, n[1], n[0]), f32)
+        bad = HC.hc_deposit(mas, fp(buf), fp(px), fp(py), fp(pz), fp(pw), len(px), ip(ng), fp(bs), fp(bm), int(wrap), 1, r * nzl,
+                            ghosts_below, nzp)
+        assert bad == 0                                  # every owned particle finds its whole stencil in the local buffer
+        bufs.append(buf)
+    out = [b.copy() for b in bufs]
+    for r in range(P):                                   # the exchange of dist_scatter (CIC) / dist_scatter_tsc
+        nxt, prv = (r + 1) % P, (r - 1) % P
+        if mas == CIC:
+            out[r][0] += bufs[prv][nzl]                  # ghost plane above -> next rank's first plane
+        else:
+            out[r][nzl] += bufs[nxt][0]                  # plane below the slab -> previous rank's last real plane
+            out[r][1:3] += bufs[prv][nzl + 1:nzl + 3]    # two planes above -> next rank's first two real planes
+    got = np.concatenate([o[ghosts_below:ghosts_below + nzl] for o in out])
+    assert np.abs(got - ref).max() <= 5e-6 * float(ref.max())                       # summation order only
+    assert abs(float(got.sum(dtype=np.float64)) - float(w.sum(dtype=np.float64))) < 1e-2
+
+
+@pytest.mark.parametrize("P", [1, 2, 4, 8])
+def test_tsc_slab_gather_scheme(HC, B, P):
+    n = (12, 10, 16)
+    L, lo = f32([300.0, 250.0, 400.0]), -50.0
+    bs, bm = L, np.full(3, lo, f32)
+    pos, _ = slab_catalog(n, L, lo, 31 + P, True)
+    fld = np.random.default_rng(5).standard_normal((n[2], n[1], n[0])).astype(f32)
+    ref = O.read_tsc(fld, *pos, bs, bm, True)
+    nzl = n[2] // P
+    own = B.dist.owner_of_z(pos[2], lo, float(L[2]), n[2], P)
+    ng = np.asarray(n, np.int32)
+    for r in range(P):
+        # the halo layout read_shifts_dist builds: plane 0 <- previous rank's last, planes nzl+1, nzl+2 <- next rank's first two
+        planes = [(r * nzl - 1 + k) % n[2] for k in range(nzl + 3)]
+        buf = np.ascontiguousarray(fld[planes])
+        sel = own == r
+        px, py, pz = (np.ascontiguousarray(p[sel]) for p in pos)
+        out = np.empty(len(px), f32)
+        bad = HC.hc_tsc_gather(fp(buf), fp(px), fp(py), fp(pz), len(px), ip(ng), fp(bs), fp(bm), 1, r * nzl, 1, nzl + 3, fp(out))
+        assert bad == 0
+        assert np.array_equal(u32(out), u32(ref[sel]))                              # bit-exact, like the single-GPU gather
+    # a particle of another slab is rejected (counted out-of-box), never read from the wrong plane
+    if P > 2:
+        other = own == 2
+        out = np.empty(int(other.sum()), f32)
+        buf = np.ascontiguousarray(fld[[(0 * nzl - 1 + k) % n[2] for k in range(nzl + 3)]])
+        px, py, pz = (np.ascontiguousarray(p[other]) for p in pos)
+        assert HC.hc_tsc_gather(fp(buf), fp(px), fp(py), fp(pz), len(px), ip(ng), fp(bs), fp(bm), 1, 0, 1, nzl + 3, fp(out)) > 0
+
+
+def test_single_gpu_deposit_matches_the_oracle(HC):
+    """slab = 0: the whole-mesh deposit<CIC> in catalog order IS the reference's serial loop (bit-identical); the
+    oracle's TSC scatter sums stencil offset by stencil offset, so deposit<TSC> agrees to summation order."""
+    n = (12, 10, 16)
+    L, lo = f32([300.0, 250.0, 400.0]), -50.0
+    bs, bm = L, np.full(3, lo, f32)
+    pos, w = slab_catalog(n, L, lo, 41, False)
+    ng = np.asarray(n, np.int32)
+    for mas, fn in ((CIC, O.cic_scatter), (TSC, O.tsc_scatter)):
+        ref = fn(np.zeros((n[2], n[1], n[0]), f32), *[p.copy() for p in pos], w, bs, bm, False)
+        buf = np.zeros_like(ref)
+        assert HC.hc_deposit(mas, fp(buf), fp(pos[0]), fp(pos[1]), fp(pos[2]), fp(w), len(w), ip(ng), fp(bs), fp(bm), 0, 0, 0, 0, n[2]) == 0
+        if mas == CIC:
+            assert np.array_equal(u32(buf), u32(ref))
+        else:
+            assert np.abs(buf - ref).max() <= 5e-6 * float(ref.max())
