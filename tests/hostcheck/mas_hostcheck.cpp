@@ -137,4 +137,38 @@ int64_t hc_tsc_gather(const float* buf, const float* x, const float* y, const fl
   return bad;
 }
 
+// CIC gather from a halo'd slab buffer (slab_mode 2): the index work of gather_one<1, CIC> in mas.cu (gather_axis with
+// the CPU formula + local_planes) and its sum of eight products in the reference's order (src/mas.jl:258-265).
+int64_t hc_cic_gather(const float* buf, const float* x, const float* y, const float* z, int64_t n, const int* ng, const float* L,
+                      const float* mn, int slab, int z_lo, int zoff, int nzp, float* out) {
+  const BoxGeom g = make_geom(ng, L, mn, slab, z_lo, zoff, nzp);
+  const size_t nx = g.n[0], ny = g.n[1];
+  int64_t bad = 0;
+  for (int64_t i = 0; i < n; i++) {
+    int xd, xu, yd, yu, zd, zu;
+    float dx, ux, dy, uy, dz, uz;
+    bool ok = gather_axis(x[i], g.mn[0], g.L[0], g.cell[0], g.n[0], false, xd, xu, dx, ux);
+    ok = gather_axis(y[i], g.mn[1], g.L[1], g.cell[1], g.n[1], false, yd, yu, dy, uy) && ok;
+    ok = gather_axis(z[i], g.mn[2], g.L[2], g.cell[2], g.n[2], false, zd, zu, dz, uz) && ok;
+    ok = ok && local_planes(g, zd, zu, zd, zu);
+    float v = 0.f;
+    if (ok) {
+      const size_t rdd = ((size_t)zd * ny + yd) * nx, rdu = ((size_t)zu * ny + yd) * nx;
+      const size_t rud = ((size_t)zd * ny + yu) * nx, ruu = ((size_t)zu * ny + yu) * nx;
+      v = __fmul_rn(__fmul_rn(__fmul_rn(buf[rdd + xd], dx), dy), dz);
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(buf[rdu + xd], dx), dy), uz));
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(buf[rud + xd], dx), uy), dz));
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(buf[ruu + xd], dx), uy), uz));
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(buf[rdd + xu], ux), dy), dz));
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(buf[rdu + xu], ux), dy), uz));
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(buf[rud + xu], ux), uy), dz));
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(buf[ruu + xu], ux), uy), uz));
+    } else {
+      bad++;
+    }
+    out[i] = v;
+  }
+  return bad;
+}
+
 }  // extern "C"

@@ -48,6 +48,8 @@ def HC():
     lib.hc_deposit.argtypes = [i, _F, _F, _F, _F, _F, i64, _I, _F, _F, i, i, i, i, i]
     lib.hc_tsc_gather.restype = i64
     lib.hc_tsc_gather.argtypes = [_F, _F, _F, _F, i64, _I, _F, _F, i, i, i, i, _F]
+    lib.hc_cic_gather.restype = i64
+    lib.hc_cic_gather.argtypes = [_F, _F, _F, _F, i64, _I, _F, _F, i, i, i, i, _F]
     return lib
 
 
@@ -194,6 +196,31 @@ def test_slab_scatter_scheme_reassembles_the_global_mesh(HC, B, P, mas, wrap):
     got = np.concatenate([o[ghosts_below:ghosts_below + nzl] for o in out])
     assert np.abs(got - ref).max() <= 5e-6 * float(ref.max())                       # summation order only
     assert abs(float(got.sum(dtype=np.float64)) - float(w.sum(dtype=np.float64))) < 1e-2
+
+
+@pytest.mark.parametrize("P", [1, 2, 4, 8])
+@pytest.mark.parametrize("n,Lz", [((12, 10, 16), 400.0), ((12, 10, 48), 431.7)])
+def test_cic_slab_gather_scheme(HC, B, P, n, Lz):
+    """The halo layout of read_shifts_dist (one plane below the slab, two above) is enough for every owned particle --
+    including those whose gather coordinate (p - min)/cell rounds into the cell below or above the scatter's
+    (p - min) n / L (src/mas.jl:13 vs :224) -- and the result is the oracle's read_cic! bit for bit."""
+    L, lo = f32([300.0, 250.0, Lz]), -50.0
+    bs, bm = L, np.full(3, lo, f32)
+    pos, _ = slab_catalog(n, L, lo, 51 + P, True)
+    cellz = f32(L[2] / f32(n[2]))
+    pos[2][4:4 + n[2]] = (lo + cellz * np.arange(n[2])).astype(f32)           # exactly on the planes: the last-bit cases
+    fld = np.random.default_rng(6).standard_normal((n[2], n[1], n[0])).astype(f32)
+    ref = O.read_cic(fld, *pos, bs, bm, True, "cpu")
+    nzl = n[2] // P
+    own = B.dist.owner_of_z(pos[2], lo, float(L[2]), n[2], P)
+    ng = np.asarray(n, np.int32)
+    for r in range(P):
+        buf = np.ascontiguousarray(fld[[(r * nzl - 1 + k) % n[2] for k in range(nzl + 3)]])
+        sel = own == r
+        px, py, pz = (np.ascontiguousarray(p[sel]) for p in pos)
+        out = np.empty(len(px), f32)
+        assert HC.hc_cic_gather(fp(buf), fp(px), fp(py), fp(pz), len(px), ip(ng), fp(bs), fp(bm), 1, r * nzl, 1, nzl + 3, fp(out)) == 0
+        assert np.array_equal(u32(out), u32(ref[sel]))
 
 
 @pytest.mark.parametrize("P", [1, 2, 4, 8])
