@@ -7,6 +7,7 @@
 // very same statements on the CPU of the build container against the CPU checker.
 #pragma once
 #include <stddef.h>
+#include <stdint.h>
 
 #include "baorec_b200.h"
 #include "host_shim.cuh"
@@ -179,6 +180,70 @@ __device__ __forceinline__ bool deposit(float* __restrict__ rho, float px, float
     }
     return true;
   }
+}
+
+// ---- read_shifts / reconstructed_positions epilogue -----------------------------------------------------------
+struct GatherArgs {
+  const float* f[3];
+  const float* x;
+  const float* y;
+  const float* z;
+  float* o[3];
+  int64_t n;
+  int field;      // BAOREC_FIELD_*
+  int positions;  // write pos - shift
+  int has_los;
+  float los[3];
+  float fgrowth;
+  float4* sorted_out;  // if non-null: write (s0,s1,s2,0) at the record's sorted position instead of o[c][idx]
+};
+
+// read_shifts epilogue (src/recon.jl:277-304 / kernels :308-330) and optionally pos - shift (:376-378)
+template <int NF>
+__device__ __forceinline__ void shifts_epilogue(const GatherArgs& a, const float (&val)[NF], float px, float py,
+                                                float pz, int64_t out_idx, int64_t sorted_pos = -1) {
+  if (NF == 1) {
+    a.o[0][out_idx] = val[0];
+    return;
+  }
+  float s0 = val[0], s1 = val[NF > 1 ? 1 : 0], s2 = val[NF > 2 ? 2 : 0];
+  if (a.field != BAOREC_FIELD_DISP) {
+    float lx, ly, lz;
+    if (a.has_los) {
+      lx = a.los[0];
+      ly = a.los[1];
+      lz = a.los[2];
+    } else {
+      float dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
+      lx = __fdiv_rn(px, dist);
+      ly = __fdiv_rn(py, dist);
+      lz = __fdiv_rn(pz, dist);
+    }
+    float dot = __fadd_rn(__fadd_rn(__fmul_rn(s0, lx), __fmul_rn(s1, ly)), __fmul_rn(s2, lz));
+    float fd = __fmul_rn(a.fgrowth, dot);
+    float r0 = __fmul_rn(fd, lx), r1 = __fmul_rn(fd, ly), r2 = __fmul_rn(fd, lz);
+    if (a.field == BAOREC_FIELD_RSD) {
+      s0 = r0;
+      s1 = r1;
+      s2 = r2;
+    } else {
+      s0 = __fadd_rn(s0, r0);
+      s1 = __fadd_rn(s1, r1);
+      s2 = __fadd_rn(s2, r2);
+    }
+  }
+  if (a.positions) {
+    s0 = __fsub_rn(px, s0);
+    s1 = __fsub_rn(py, s1);
+    s2 = __fsub_rn(pz, s2);
+  }
+  if (a.sorted_out && sorted_pos >= 0) {
+    a.sorted_out[sorted_pos] = make_float4(s0, s1, s2, 0.f);  // coalesced; un-permuted by unsort_kernel
+    return;
+  }
+  a.o[0][out_idx] = s0;
+  if (NF > 1) a.o[1][out_idx] = s1;
+  if (NF > 2) a.o[2][out_idx] = s2;
 }
 
 }  // namespace baorec

@@ -171,4 +171,26 @@ int64_t hc_cic_gather(const float* buf, const float* x, const float* y, const fl
   return bad;
 }
 
+// The product's shifts_epilogue<3> (read_shifts: :disp / :rsd / :sum, fixed or per-particle line of sight; with
+// positions != 0 reconstructed_positions' pos - shift) applied to given displacement values.
+void hc_shifts_epilogue(const float* px, const float* py, const float* pz, const float* dx, const float* dy, const float* dz,
+                        int64_t n, int field, int positions, int has_los, const float* los, float fgrowth, float* ox, float* oy,
+                        float* oz) {
+  GatherArgs a;
+  a.f[0] = a.f[1] = a.f[2] = nullptr;
+  a.x = px, a.y = py, a.z = pz;
+  a.o[0] = ox, a.o[1] = oy, a.o[2] = oz;
+  a.n = n;
+  a.field = field;
+  a.positions = positions;
+  a.has_los = has_los;
+  for (int c = 0; c < 3; c++) a.los[c] = has_los ? los[c] : 0.f;
+  a.fgrowth = fgrowth;
+  a.sorted_out = nullptr;
+  for (int64_t i = 0; i < n; i++) {
+    const float val[3] = {dx[i], dy[i], dz[i]};
+    shifts_epilogue<3>(a, val, px[i], py[i], pz[i], i);
+  }
+}
+
 }  // extern "C"

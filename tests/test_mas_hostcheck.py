@@ -48,6 +48,8 @@ def HC():
     lib.hc_deposit.argtypes = [i, _F, _F, _F, _F, _F, i64, _I, _F, _F, i, i, i, i, i]
     lib.hc_tsc_gather.restype = i64
     lib.hc_tsc_gather.argtypes = [_F, _F, _F, _F, i64, _I, _F, _F, i, i, i, i, _F]
+    lib.hc_shifts_epilogue.restype = None
+    lib.hc_shifts_epilogue.argtypes = [_F, _F, _F, _F, _F, _F, i64, i, i, i, _F, C.c_float, _F, _F, _F]
     lib.hc_cic_gather.restype = i64
     lib.hc_cic_gather.argtypes = [_F, _F, _F, _F, i64, _I, _F, _F, i, i, i, i, _F]
     return lib
@@ -269,3 +271,41 @@ def test_single_gpu_deposit_matches_the_oracle(HC):
             assert np.array_equal(u32(buf), u32(ref))
         else:
             assert np.abs(buf - ref).max() <= 5e-6 * float(ref.max())
+
+
+@pytest.mark.parametrize("los", [(0.0, 0.0, 1.0), (0.6, 0.0, 0.8), None])
+def test_read_shifts_epilogue_bit_exact(HC, los):
+    """read_shifts' :disp / :rsd / :sum arithmetic (src/recon.jl:277-304) and reconstructed_positions' pos - shift
+    (:377), as the gather kernels apply it per particle, against the oracle's -- same operations, same order."""
+    rng = np.random.default_rng(7)
+    N = 20000
+    pos = [(900.0 + 600.0 * rng.random(N)).astype(f32) for _ in range(3)]
+    disp = [(5.0 * rng.standard_normal(N)).astype(f32) for _ in range(3)]
+
+    class Rec:                       # what oracle.read_shifts needs besides the displacements
+        f = 0.757
+        los = None
+
+    Rec.los = los
+    fgrowth = f32(0.757)
+    for code, field in enumerate(("disp", "rsd", "sum")):
+        # the oracle's epilogue, fed with the same displacement values
+        if field == "disp":
+            ref = disp
+        else:
+            if los is None:
+                dist = np.sqrt(((pos[0] * pos[0]) + (pos[1] * pos[1])).astype(f32) + (pos[2] * pos[2])).astype(f32)
+                l = [(p / dist).astype(f32) for p in pos]
+            else:
+                l = [f32(v) for v in los]
+            dot = (((disp[0] * l[0]) + (disp[1] * l[1])).astype(f32) + (disp[2] * l[2])).astype(f32)
+            rsd = [((fgrowth * dot).astype(f32) * li).astype(f32) for li in l]
+            ref = rsd if field == "rsd" else [(d + r).astype(f32) for d, r in zip(disp, rsd)]
+        for positions in (0, 1):
+            want = [(p - s).astype(f32) for p, s in zip(pos, ref)] if positions else ref
+            out = [np.empty(N, f32) for _ in range(3)]
+            HC.hc_shifts_epilogue(fp(pos[0]), fp(pos[1]), fp(pos[2]), fp(disp[0]), fp(disp[1]), fp(disp[2]), N, code, positions,
+                                  int(los is not None), fp(np.asarray(los if los is not None else (0, 0, 0), f32)), fgrowth,
+                                  fp(out[0]), fp(out[1]), fp(out[2]))
+            for a in range(3):
+                assert np.array_equal(u32(out[a]), u32(np.broadcast_to(want[a], (N,)).astype(f32)))
