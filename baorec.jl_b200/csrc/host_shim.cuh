@@ -19,6 +19,11 @@ struct float2 {
   float x, y;
 };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
+  const unsigned long long old = *p;
+  *p = old + v;
+  return old;
+}
 struct float4 {
   float x, y, z, w;
 };

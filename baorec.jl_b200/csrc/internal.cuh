@@ -84,6 +84,7 @@ enum BufId {
   BUF_A2A_RECV2,
   BUF_HALO,
   BUF_MGD,      // multigrid level hierarchy of the slab-decomposed solver
+  BUF_DET,      // 64-bit fixed-point accumulator of the deterministic scatter
   BUF_COUNT
 };
 
@@ -175,6 +176,7 @@ struct baorec_ctx {
   int64_t opt_bin_min_particles = 1 << 18;  // catalogs at least this large are z-binned first
   int opt_fuse_kspace = 1;     // fixed-LOS iterations folded into one k-space pass
   int opt_scatter_tiles = 0;   // scatter: (z, y/8, x/128) tile order instead of z slabs
+  int opt_det_scatter = 0;     // CIC scatter through 64-bit fixed-point integer reductions: bit-reproducible meshes
   // Unified sort: run! sorts the catalog ONCE into the gather's tile order (records x,y,z,w + inverse
   // permutation + a 64-bit content hash of the wrapped positions); the scatter deposits in that order
   // and a read-back of the same, unmodified position arrays (same pointers, same count, same hash --

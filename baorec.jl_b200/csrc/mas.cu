@@ -500,6 +500,50 @@ scatter_records_kernel(float* __restrict__ rho, const float4* __restrict__ rec, 
   if (!deposit<BAOREC_MAS_CIC>(rho, p.x, p.y, p.z, p.w, g, wrap != 0)) atomicAdd(oob, 1ULL);
 }
 
+// ---- deterministic scatter (option "deterministic_scatter"; see deposit_fixed in mas_math.cuh) -------------------
+__global__ void __launch_bounds__(256)
+scatter_records_fixed_kernel(unsigned long long* __restrict__ acc, const float4* __restrict__ rec, int64_t n, BoxGeom g,
+                             int wrap, unsigned long long* __restrict__ oob) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = rec[i];
+  if (!deposit_fixed(acc, p.x, p.y, p.z, p.w, g, wrap != 0)) atomicAdd(oob, 1ULL);
+}
+
+// catalog order (small catalogs, or unified_sort off); wraps and writes back like scatter_direct_kernel
+__global__ void __launch_bounds__(256)
+scatter_direct_fixed_kernel(unsigned long long* __restrict__ acc, float* __restrict__ x, float* __restrict__ y,
+                            float* __restrict__ z, const float* __restrict__ w, int64_t n, BoxGeom g, int wrap,
+                            unsigned long long* oob) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float px = x[i], py = y[i], pz = z[i];
+  if (wrap) {
+    float qx = wrap_pos(px, g.mn[0], g.L[0]);
+    float qy = wrap_pos(py, g.mn[0], g.L[0]);
+    float qz = wrap_pos(pz, g.mn[0], g.L[0]);
+    if (qx != px) x[i] = qx;  // write-back like the reference (src/mas.jl:57-59)
+    if (qy != py) y[i] = qy;
+    if (qz != pz) z[i] = qz;
+    if (qx != px || qy != py || qz != pz) atomicAdd(oob + 1, 1ULL);
+    px = qx;
+    py = qy;
+    pz = qz;
+  }
+  if (!deposit_fixed(acc, px, py, pz, w[i], g, wrap != 0)) atomicAdd(oob, 1ULL);
+}
+
+// rho += Float32(sum): the one rounding of the deterministic scatter (cic! accumulates into rho)
+__global__ void __launch_bounds__(256)
+fixed_to_float_kernel(float* __restrict__ rho, const unsigned long long* __restrict__ acc, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const unsigned long long a = acc[i];
+    if (a) rho[i] = __fadd_rn(rho[i], from_fixed(a));
+  }
+}
+
 template <int MAS>
 __global__ void __launch_bounds__(256)
 tile_count_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z, int64_t n,
@@ -912,6 +956,25 @@ int scatter(baorec_ctx* ctx, float* rho, float* x, float* y, float* z, const flo
   if (n == 0) return BAOREC_OK;
   BoxGeom g = geom_of(ctx);
   const bool tsc = mas == BAOREC_MAS_TSC;
+  if (ctx->opt_det_scatter && !tsc && ctx->slab_mode == 0) {
+    // bit-reproducible CIC: 64-bit fixed-point integer reductions, one rounding to Float32 at the end
+    unsigned long long* acc;
+    BR_TRY(need_t(ctx, BUF_DET, ctx->M, &acc));
+    BR_CUDA(cudaMemsetAsync(acc, 0, ctx->M * sizeof(unsigned long long), st));
+    if (use_binning(ctx, n) && ctx->opt_unified_sort && ctx->opt_gather_tiles) {
+      BinResult b;
+      BR_TRY(unified_sort(ctx, x, y, z, w, n, wrap, st, &b));  // same sort (and the read-back reuses it)
+      BR_LAUNCH(ctx, scatter_records_fixed_kernel, cdiv((size_t)n, 256), 256, 0, st, acc, b.rec, n, g, wrap, ctx->d_oob);
+    } else {
+      ctx->sortc_valid = false;
+      BR_LAUNCH(ctx, scatter_direct_fixed_kernel, cdiv((size_t)n, 256), 256, 0, st, acc, x, y, z, w, n, g, wrap,
+                ctx->d_oob);
+    }
+    size_t blocks = cdiv(ctx->M, 256);
+    if (blocks > (size_t)148 * 32) blocks = (size_t)148 * 32;
+    BR_LAUNCH(ctx, fixed_to_float_kernel, (unsigned)blocks, 256, 0, st, rho, acc, ctx->M);
+    return BAOREC_OK;
+  }
   if (use_binning(ctx, n) && ctx->opt_unified_sort && !tsc && ctx->slab_mode == 0 && ctx->opt_gather_tiles) {
     BinResult b;
     BR_TRY(unified_sort(ctx, x, y, z, w, n, wrap, st, &b));

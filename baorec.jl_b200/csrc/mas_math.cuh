@@ -182,6 +182,52 @@ __device__ __forceinline__ bool deposit(float* __restrict__ rho, float px, float
   }
 }
 
+// ---- deterministic deposit (option "deterministic_scatter") -------------------------------------------------------
+// Float additions do not commute, so a mesh accumulated with float reductions differs from run to run in the last
+// bits (and with it the cells that sit on the `ran > threshold` cut).  Integer additions do
+// commute: every Float32 deposit value is converted to 2^-40 fixed point -- exactly, unless it is below 2^-17, where
+// the bits under 2^-40 are rounded away -- and accumulated with 64-bit integer reductions; the sum is then rounded to
+// Float32 ONCE.  Bit-reproducible whatever the order, and closer to the exact sum than any Float32 summation order.
+constexpr float kFixedScale = 1099511627776.0f;          // 2^40
+constexpr double kFixedInv = 1.0 / 1099511627776.0;
+
+__device__ __forceinline__ unsigned long long to_fixed(float v) {
+#if defined(__CUDA_ARCH__)
+  return (unsigned long long)__float2ll_rn(__fmul_rn(v, kFixedScale));
+#else
+  return (unsigned long long)llrintf(v * kFixedScale);
+#endif
+}
+
+__device__ __forceinline__ float from_fixed(unsigned long long a) { return (float)((double)(long long)a * kFixedInv); }
+
+// cic! for one (already wrapped) particle into the fixed-point accumulator: the cells, weights and the eight
+// products are deposit<CIC>'s, only the accumulation differs.  Whole mesh only (no slab layout).
+__device__ __forceinline__ bool deposit_fixed(unsigned long long* __restrict__ acc, float px, float py, float pz, float ww,
+                                              const BoxGeom& g, bool wrap) {
+  const size_t nx = g.n[0], ny = g.n[1];
+  int x0, x1, y0, y1, z0, z1;
+  float wx0, wx1, wy0, wy1, wz0, wz1;
+  bool ok = cic_axis(px, g.mn[0], g.L[0], g.n[0], wrap, x0, x1, wx0, wx1);
+  ok = cic_axis(py, g.mn[1], g.L[1], g.n[1], wrap, y0, y1, wy0, wy1) && ok;
+  ok = cic_axis(pz, g.mn[2], g.L[2], g.n[2], wrap, z0, z1, wz0, wz1) && ok;
+  if (!ok) return false;
+  wx0 = __fmul_rn(wx0, ww);
+  wx1 = __fmul_rn(wx1, ww);
+  const size_t r00 = ((size_t)z0 * ny + y0) * nx, r10 = ((size_t)z0 * ny + y1) * nx;
+  const size_t r01 = ((size_t)z1 * ny + y0) * nx, r11 = ((size_t)z1 * ny + y1) * nx;
+  const float a00 = __fmul_rn(wx0, wy0), a10 = __fmul_rn(wx1, wy0), a01 = __fmul_rn(wx0, wy1), a11 = __fmul_rn(wx1, wy1);
+  atomicAdd(acc + r00 + x0, to_fixed(__fmul_rn(a00, wz0)));
+  atomicAdd(acc + r00 + x1, to_fixed(__fmul_rn(a10, wz0)));
+  atomicAdd(acc + r10 + x0, to_fixed(__fmul_rn(a01, wz0)));
+  atomicAdd(acc + r01 + x0, to_fixed(__fmul_rn(a00, wz1)));
+  atomicAdd(acc + r10 + x1, to_fixed(__fmul_rn(a11, wz0)));
+  atomicAdd(acc + r01 + x1, to_fixed(__fmul_rn(a10, wz1)));
+  atomicAdd(acc + r11 + x0, to_fixed(__fmul_rn(a01, wz1)));
+  atomicAdd(acc + r11 + x1, to_fixed(__fmul_rn(a11, wz1)));
+  return true;
+}
+
 // ---- read_shifts / reconstructed_positions epilogue -----------------------------------------------------------
 struct GatherArgs {
   const float* f[3];

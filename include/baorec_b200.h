@@ -98,6 +98,10 @@ int baorec_set_box(baorec_ctx* ctx, const float box_size[3], const float box_min
  *       smoothing, normalisation and all n_iter iterations into ONE k-space pass between one
  *       R2C and one C2R (iterate! is linear and diagonal in k for a constant LOS); 0 = run the
  *       reference's sequence of iterate! calls (2 + 2 n_iter transforms).
+ *   "deterministic_scatter" (default 0): 1 = the CIC scatter (single GPU) accumulates 2^-40 fixed-point values with
+ *       64-bit integer reductions and rounds to Float32 once: meshes, `ran > threshold` masks and everything after
+ *       them are bit-reproducible from run to run and independent of the particle order (float reductions are not);
+ *       costs an 8-byte-per-cell scratch mesh and one conversion pass.
  *   "mg_slab_min_cells" (default 4194304): slab-decomposed multigrid levels with fewer cells are
  *       replicated on every rank instead of exchanging halos. */
 int baorec_set_option(baorec_ctx* ctx, const char* name, int64_t value);

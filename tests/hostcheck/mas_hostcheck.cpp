@@ -137,6 +137,28 @@ int64_t hc_tsc_gather(const float* buf, const float* x, const float* y, const fl
   return bad;
 }
 
+// The deterministic scatter (option "deterministic_scatter"): the product's deposit_fixed for a list of particles in
+// the given order into a 64-bit fixed-point accumulator, then from_fixed per cell (fixed_to_float_kernel: rho += ...).
+int64_t hc_deposit_fixed(float* rho, unsigned long long* acc, const float* x, const float* y, const float* z, const float* w,
+                         int64_t n, const int* ng, const float* L, const float* mn, int wrap) {
+  const BoxGeom g = make_geom(ng, L, mn, 0, 0, 0, ng[2]);
+  const size_t M = (size_t)ng[0] * ng[1] * ng[2];
+  for (size_t i = 0; i < M; i++) acc[i] = 0;
+  int64_t bad = 0;
+  for (int64_t i = 0; i < n; i++) {
+    float px = x[i], py = y[i], pz = z[i];
+    if (wrap) {
+      px = wrap_pos(px, g.mn[0], g.L[0]);
+      py = wrap_pos(py, g.mn[0], g.L[0]);
+      pz = wrap_pos(pz, g.mn[0], g.L[0]);
+    }
+    if (!deposit_fixed(acc, px, py, pz, w[i], g, wrap != 0)) bad++;
+  }
+  for (size_t i = 0; i < M; i++)
+    if (acc[i]) rho[i] = __fadd_rn(rho[i], from_fixed(acc[i]));
+  return bad;
+}
+
 // CIC gather from a halo'd slab buffer (slab_mode 2): the index work of gather_one<1, CIC> in mas.cu (gather_axis with
 // the CPU formula + local_planes) and its sum of eight products in the reference's order (src/mas.jl:258-265).
 int64_t hc_cic_gather(const float* buf, const float* x, const float* y, const float* z, int64_t n, const int* ng, const float* L,

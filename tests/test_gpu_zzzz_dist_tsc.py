@@ -71,3 +71,32 @@ def test_multigrid_tsc_on_slabs_matches_the_oracle(B, O, dctx):
     for a in range(3):
         assert rel_rms(s[a].cpu().numpy(), ref[a]) < 1e-4
         assert maxabs(s[a].cpu().numpy(), ref[a]) < 1e-3
+
+
+# ---- option "deterministic_scatter" (64-bit fixed-point integer reductions; csrc/mas_math.cuh: deposit_fixed) --------
+# Same status as above: arithmetic validated on the CPU (tests/test_mas_hostcheck.py), kernels not yet run on hardware.
+@pytest.mark.parametrize("N", [50_000, 400_000])          # catalog-order kernel / unified sort + records kernel
+def test_deterministic_scatter_is_bit_reproducible(B, O, N):
+    n, L = 64, 1000.0
+    pos, w = clustered_box(N, L, seed=17)
+    bs, bm = np.full(3, L, np.float32), np.zeros(3, np.float32)
+    ctx = B.Context.get(0)
+    ref = O.cic_scatter(np.zeros((n, n, n), np.float32), *[p.copy() for p in pos], w, bs, bm, True)
+    perm = np.random.default_rng(1).permutation(N)
+    try:
+        ctx.set_option("deterministic_scatter", 1)
+        meshes = []
+        for order in (np.arange(N), np.arange(N), perm):
+            rho = torch.zeros((n, n, n), dtype=torch.float32, device="cuda")
+            B.cic(rho, *(dev(p[order]) for p in pos), dev(w[order]), bs, bm, wrap=True)
+            meshes.append(rho)
+        assert torch.equal(meshes[0], meshes[1]) and torch.equal(meshes[0], meshes[2])      # any order, same bits
+        assert maxabs(meshes[0].cpu().numpy(), ref) <= 2e-6 * float(ref.max())
+        kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=bs, box_min=bm, los=(0.0, 0.0, 1.0), n_iter=3)
+        runs = [B.run(B.IterativeRecon(**kw), (n, n, n), *(dev(p) for p in pos), dev(w)) for _ in range(2)]
+        assert torch.equal(runs[0], runs[1])                                                 # the whole reconstruction
+    finally:
+        ctx.set_option("deterministic_scatter", 0)
+    rho = torch.zeros((n, n, n), dtype=torch.float32, device="cuda")
+    B.cic(rho, *(dev(p) for p in pos), dev(w), bs, bm, wrap=True)
+    assert maxabs(rho.cpu().numpy(), meshes[0].cpu().numpy()) <= 2e-6 * float(ref.max())     # default path: same to rounding

@@ -48,6 +48,8 @@ def HC():
     lib.hc_deposit.argtypes = [i, _F, _F, _F, _F, _F, i64, _I, _F, _F, i, i, i, i, i]
     lib.hc_tsc_gather.restype = i64
     lib.hc_tsc_gather.argtypes = [_F, _F, _F, _F, i64, _I, _F, _F, i, i, i, i, _F]
+    lib.hc_deposit_fixed.restype = i64
+    lib.hc_deposit_fixed.argtypes = [_F, C.POINTER(C.c_uint64), _F, _F, _F, _F, i64, _I, _F, _F, i]
     lib.hc_shifts_epilogue.restype = None
     lib.hc_shifts_epilogue.argtypes = [_F, _F, _F, _F, _F, _F, i64, i, i, i, _F, C.c_float, _F, _F, _F]
     lib.hc_cic_gather.restype = i64
@@ -309,3 +311,47 @@ def test_read_shifts_epilogue_bit_exact(HC, los):
                                   fp(out[0]), fp(out[1]), fp(out[2]))
             for a in range(3):
                 assert np.array_equal(u32(out[a]), u32(np.broadcast_to(want[a], (N,)).astype(f32)))
+
+
+@pytest.mark.parametrize("wrap", [True, False])
+def test_deterministic_scatter_is_order_independent_and_correctly_rounded(HC, wrap):
+    """Option "deterministic_scatter": 2^-40 fixed-point integer accumulation + ONE rounding to Float32.  Any particle
+    order gives the same bits; the result is the correctly rounded sum of the reference's Float32 deposit values
+    (all but never off by the bits dropped below 2^-40), hence within summation-order distance of the serial loop."""
+    n = (12, 10, 16)
+    L, lo = f32([300.0, 250.0, 400.0]), -50.0
+    bs, bm = L, np.full(3, lo, f32)
+    pos, w = slab_catalog(n, L, lo, 61, False)
+    w = (w * f32(3.7)).astype(f32)
+    ng = np.asarray(n, np.int32)
+    M = n[0] * n[1] * n[2]
+
+    def run(order):
+        rho, acc = np.zeros(M, f32), np.zeros(M, np.uint64)
+        p = [np.ascontiguousarray(a[order]) for a in pos]
+        bad = HC.hc_deposit_fixed(fp(rho), acc.ctypes.data_as(C.POINTER(C.c_uint64)), fp(p[0]), fp(p[1]), fp(p[2]),
+                                  fp(np.ascontiguousarray(w[order])), len(w), ip(ng), fp(bs), fp(bm), int(wrap))
+        assert bad == 0
+        return rho.reshape(n[2], n[1], n[0])
+
+    N = len(w)
+    a = run(np.arange(N))
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        assert np.array_equal(u32(run(rng.permutation(N))), u32(a))          # bit-reproducible in any order
+    ref = O.cic_scatter(np.zeros((n[2], n[1], n[0]), f32), *[p.copy() for p in pos], w, bs, bm, wrap)
+    assert np.abs(a - ref).max() <= 2e-6 * float(ref.max())
+    # exact sum of the very same Float32 deposit values, in Float64, rounded once
+    _, i0, i1, w0, w1 = O.cic_cells(*[p.copy() for p in pos], n, bs, bm, wrap)
+    exact = np.zeros(M, np.float64)
+    wx = ((w0[0] * w).astype(f32), (w1[0] * w).astype(f32))
+    ix, iy, iz = (i0[0], i1[0]), (i0[1], i1[1]), (i0[2], i1[2])
+    wy, wz = (w0[1], w1[1]), (w0[2], w1[2])
+    for cx in (0, 1):
+        for cy in (0, 1):
+            for cz in (0, 1):
+                v = ((wx[cx] * wy[cy]).astype(f32) * wz[cz]).astype(f32)
+                np.add.at(exact, (iz[cz] * n[1] + iy[cy]) * n[0] + ix[cx], v.astype(np.float64))
+    exact32 = exact.astype(f32).reshape(a.shape)
+    assert (a == exact32).mean() > 0.999 and np.abs(a - exact32).max() <= np.spacing(exact32.max())
+    assert abs(float(a.sum(dtype=np.float64)) - float(w.sum(dtype=np.float64))) < 2e-3
