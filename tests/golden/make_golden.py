@@ -28,6 +28,7 @@ sys.path.insert(0, str(ROOT / "oracle"))
 sys.path.insert(0, str(ROOT / "tests"))
 
 import baorec_oracle as O  # noqa: E402
+import catalog_oracle as CO  # noqa: E402
 from util import clustered_box, lightcone  # noqa: E402
 
 PARAMS = dict(bias=2.2, f=0.757, smoothing_radius=15.0)
@@ -141,6 +142,24 @@ def multigrid_ops_case(n, L, seed):
     return out
 
 
+def catalog_case(n, seed):
+    """Catalog pre/post-processing (src/cosmo.jl, examples/lightcone.jl:30-82): cosmology tables (every 1000th knot),
+    sky -> Cartesian -> sky, FKP weights, periodic re-wrap."""
+    rng = np.random.default_rng(seed)
+    c = CO.Cosmology(z_tab_max=3)
+    ra, dec = (360 * rng.random(n)).astype(np.float32), (180 * rng.random(n) - 90).astype(np.float32)
+    red = (0.01 + 2.9 * rng.random(n)).astype(np.float32)
+    nz = (1e-3 * rng.random(n)).astype(np.float32)
+    zt, rt = CO.tables(c)
+    x, y, z = CO.sky_to_cartesian(ra, dec, red, c)
+    ra2, dec2, red2 = CO.cartesian_to_sky(x, y, z, c)
+    box = (np.float32([1500.0, 2000.0, 2500.0]), np.float32([-700.0, 0.0, 100.0]))
+    wx, wy, wz = CO.wrap_positions(x, y, z, *box)
+    dens = {k: np.float32(getattr(c, k)) for k in ("h", "H0", "Omega_b0", "Omega_c0", "Omega_g0", "Omega_nu0", "Omega_L0")}
+    return dict(ra=ra, dec=dec, red=red, nz=nz, z_tab=zt[::1000], r_tab=rt[::1000], x=x, y=y, z=z, ra2=ra2, dec2=dec2, red2=red2,
+                fkp=CO.fkp_weights(nz, np.float32(5e3)), wrap_box_size=box[0], wrap_box_min=box[1], wx=wx, wy=wy, wz=wz, **dens)
+
+
 CASES = {
     "iterative_box_32": lambda: box_case("iterative", 32, 431.7, 6000, (0.0, 0.0, 1.0), 101),
     "multigrid_box_32": lambda: box_case("multigrid", 32, 431.7, 6000, (0.0, 0.0, 1.0), 102),
@@ -148,6 +167,7 @@ CASES = {
     "multigrid_lightcone_48": lambda: lightcone_case("multigrid", 48, 4000, 30000, 104),
     "mas_24": lambda: mas_case(24, 300.0, 5000, 105),
     "multigrid_ops_32": lambda: multigrid_ops_case(32, 500.0, 106),
+    "catalog_4000": lambda: catalog_case(4000, 107),
 }
 
 

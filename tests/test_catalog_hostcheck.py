@@ -214,3 +214,30 @@ def test_fkp_and_wrap_bit_exact(HC):
         for g, o, l, m in zip(got, ref, L, mn):
             assert np.array_equal(g.view(np.uint32), o.view(np.uint32))
             assert (g >= f32(m)).all() and (g <= f32(m) + f32(l)).all()
+
+
+def test_device_arithmetic_against_the_golden_fixture(HC, B):
+    """The committed catalog fixture (tests/golden/catalog_4000.npz) against the kernels' arithmetic, no oracle run."""
+    with np.load(ROOT / "tests" / "golden" / "catalog_4000.npz") as zf:
+        g = {k: zf[k] for k in zf.files}
+    cosmo = B.Cosmology(z_tab_max=3)
+    z, r = product_table(B, cosmo)
+    assert np.abs(r[::1000][1:] / g["r_tab"][1:] - 1).max() < 1e-12
+    n = len(g["ra"])
+    x, y, zz = (np.empty(n, f32) for _ in range(3))
+    assert HC.hc_sky_to_cartesian(fp(g["ra"]), fp(g["dec"]), fp(g["red"]), n, f32(cosmo.H0 / f32(100)), r.ctypes.data_as(_D), z[0], z[-1],
+                                  (z[-1] - z[0]) / (len(z) - 1), len(z), fp(x), fp(y), fp(zz)) == 0
+    scale = np.sqrt(g["x"].astype(float) ** 2 + g["y"].astype(float) ** 2 + g["z"].astype(float) ** 2).astype(f32)
+    for a, b in ((x, g["x"]), (y, g["y"]), (zz, g["z"])):
+        assert (np.abs(a.astype(float) - b.astype(float)) <= 1.01 * np.spacing(scale)).all() and (a == b).mean() > 0.99
+    a, d, q = (np.empty(n, f32) for _ in range(3))
+    assert HC.hc_cartesian_to_sky(fp(g["x"]), fp(g["y"]), fp(g["z"]), n, f32(cosmo.h), r.ctypes.data_as(_D), z[0],
+                                  (z[-1] - z[0]) / (len(z) - 1), len(z), fp(a), fp(d), fp(q), 1, -1, None) == 0
+    assert ulps(a, g["ra2"]).max() <= 1 and ulps(d, g["dec2"]).max() <= 1 and ulps(q, g["red2"]).max() <= 1
+    w = np.empty(n, f32)
+    HC.hc_fkp_weights(fp(g["nz"]), n, f32(5e3), fp(w))
+    assert np.array_equal(w.view(np.uint32), g["fkp"].view(np.uint32))
+    p = [g[k].copy() for k in "xyz"]
+    HC.hc_wrap_positions(fp(p[0]), fp(p[1]), fp(p[2]), n, fp(g["wrap_box_size"]), fp(g["wrap_box_min"]))
+    for got, k in zip(p, ("wx", "wy", "wz")):
+        assert np.array_equal(got.view(np.uint32), g[k].view(np.uint32))
