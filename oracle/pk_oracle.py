@@ -1,0 +1,86 @@
+"""TEST INFRASTRUCTURE (CPU oracle) -- power-spectrum multipoles of a density mesh.
+
+The reference validates a reconstruction by eye, through the power-spectrum multipoles of the catalogs
+before and after (test_helpers/simulation.py:56-75, test_helpers/pyrecon_simulation.py:70-86: pypowspec
+`compute_auto_box` on a 512^3 mesh, CIC, line of sight along z, multipoles 0/2/4, linear k bins).  pypowspec is a
+third-party C library that is not under /root/reference; what it computes for a periodic box is the textbook
+FFT estimator restated here (parity unpinned: no reference vectors exist for it; pinned by the analytic
+known-answer tests in tests/test_pk_oracle.py -- plane waves, Poisson shot noise, the Kaiser quadrupole):
+
+    delta(x)  = rho(x) / mean(rho) - 1                       on the mesh, rho from cic! (or TSC)
+    delta_k   = sum_x delta(x) exp(-i k x)                   unnormalised forward transform (src/recon.jl:36)
+    P(k)      = V |delta_k|^2 / M^2 / W(k)^2                 V = Lx Ly Lz, M = nx ny nz,
+                W(k) = prod_a sinc(k_a h_a / 2)^p            mass-assignment window (p = 2 CIC, 3 TSC, 0 = none)
+    P_l(k_i)  = (2l+1) <P(k) L_l(mu)>_{k in bin i} - [l == 0] shot     mu = k . los / |k|
+
+Every mode of the full (Hermitian) mesh counts once: on the half mesh the planes kx = 0 and kx = Nyquist have
+weight 1, the others weight 2.  k = 0 is excluded.  Bins are [kmin + i dk, kmin + (i+1) dk), i < nbins.
+Only tests/ (and the product's parity tests) may import this module."""
+from __future__ import annotations
+
+import numpy as np
+import scipy.fft
+
+import baorec_oracle as O
+
+
+def mode_table(shape_zyx, box_size, los, mas_power=2):
+    """Per-mode |k| (from the reference's Float32 k_vec tables, src/utils.jl:3-10, combined in Float64), mu, window
+    and Hermitian weight on the half mesh [nz][ny][nx/2+1]."""
+    nz, ny, nx = shape_zyx
+    L = np.asarray(box_size, np.float32)
+    f32 = np.float32
+    kx, ky, kz = O.k_vec((nx, ny, nz), L, f32)          # the tables the device context holds (src/utils.jl:3-10)
+    KX, KY, KZ = kx[None, None, :], ky[None, :, None], kz[:, None, None]
+    KX, KY, KZ = KX.astype(np.float64), KY.astype(np.float64), KZ.astype(np.float64)
+    k = np.sqrt(KX * KX + KY * KY + KZ * KZ)             # Float64 arithmetic on the Float32 table values
+    lv = np.asarray(los, np.float64)
+    lv = lv / np.sqrt((lv * lv).sum())
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mu = (KX * lv[0] + KY * lv[1] + KZ * lv[2]) / k
+    mu[0, 0, 0] = 0.0
+    h = L.astype(np.float64) / np.array([nx, ny, nz], np.float64)
+
+    def sinc(k1, h1):   # sin(x)/x with x = k h / 2
+        x = k1.astype(np.float64) * h1 / 2
+        return np.where(x == 0, 1.0, np.sin(x) / np.where(x == 0, 1.0, x))
+
+    W = (sinc(KX, h[0]) * sinc(KY, h[1]) * sinc(KZ, h[2])) ** mas_power if mas_power else np.ones_like(k)
+    wt = np.full(k.shape, 2.0)
+    wt[:, :, 0] = 1.0
+    if nx % 2 == 0:
+        wt[:, :, -1] = 1.0
+    wt[0, 0, 0] = 0.0
+    return k, mu, W, wt
+
+
+def power_multipoles(rho, box_size, los=(0.0, 0.0, 1.0), kmin=0.0, dk=None, nbins=None, mas_power=2, shot=0.0):
+    """Multipoles l = 0, 2, 4 of the density mesh `rho` ([nz][ny][nx], any normalisation; Float32 or Float64).
+    Returns dict(k=<mean k per bin>, nmodes, p0, p2, p4); empty bins hold NaN."""
+    rho = np.asarray(rho)
+    nz, ny, nx = rho.shape
+    L = np.asarray(box_size, np.float64)
+    if dk is None:
+        dk = 2 * np.pi / float(L.max())
+    if nbins is None:
+        nbins = int((np.pi * min(nx / L[0], ny / L[1], nz / L[2]) - kmin) / dk)
+    rk = scipy.fft.rfftn(rho, workers=-1)
+    a0 = float(rk[0, 0, 0].real)
+    k, mu, W, wt = mode_table(rho.shape, box_size, los, mas_power)
+    V = float(L.prod())
+    p = (rk.real.astype(np.float64) ** 2 + rk.imag.astype(np.float64) ** 2) * (V / (a0 * a0)) / (W * W)
+    b = np.floor((k - kmin) / dk).astype(np.int64)
+    ok = (b >= 0) & (b < nbins) & (wt > 0)
+    b, w = b[ok], wt[ok]
+    p, mu, kk = p[ok], mu[ok], k[ok]
+    mu2 = mu * mu
+    l2 = 1.5 * mu2 - 0.5
+    l4 = (35.0 * mu2 * mu2 - 30.0 * mu2 + 3.0) / 8.0
+    cnt = np.bincount(b, w, nbins)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        out = dict(nmodes=cnt,
+                   k=np.bincount(b, w * kk, nbins) / cnt,
+                   p0=np.bincount(b, w * p, nbins) / cnt - shot,
+                   p2=5.0 * np.bincount(b, w * p * l2, nbins) / cnt,
+                   p4=9.0 * np.bincount(b, w * p * l4, nbins) / cnt)
+    return out

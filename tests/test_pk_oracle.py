@@ -1,0 +1,104 @@
+"""CPU: known-answer tests of the power-spectrum multipole oracle (oracle/pk_oracle.py), and -- through it -- a
+physics known-answer test of the reconstruction oracle itself.
+
+The reference ships no assertion about its results: it validates by eye, plotting P_0/P_2 before and after
+(test_helpers/simulation.py:56-75).  The last test below turns that into numbers: a lognormal box with a linear
+redshift-space shift shows the Kaiser quadrupole; IterativeRecon + reconstructed positions with field = :rsd
+(src/recon.jl:366-388) must remove it and bring the monopole back to its real-space value.  A sign error anywhere
+in the chain (overdensity normalisation, the RSD recurrence, -ik/k^2, the shift epilogue) makes the quadrupole
+grow instead."""
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import baorec_oracle as O
+import baorec_oracle_fast as fast
+import pk_oracle as PK
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "benchmarks"))
+f32 = np.float32
+
+
+def test_plane_wave_lands_in_its_bin_with_the_right_amplitude():
+    n, L, A, m = 32, np.array([100.0, 100.0, 100.0]), 0.1, 3
+    x = np.arange(n) * L[0] / n
+    wave = 1 + A * np.cos(2 * np.pi * m * x / L[0])
+    kf = 2 * np.pi / 100.0
+    for axis, los, l2, l4 in ((2, (0, 0, 1), -0.5, 0.375), (2, (1, 0, 0), 1.0, 1.0), (0, (0, 0, 1), 1.0, 1.0)):
+        shape = [1, 1, 1]
+        shape[axis] = n
+        rho = np.ones((n, n, n)) * wave.reshape(shape)
+        r = PK.power_multipoles(rho, L, los=los, kmin=0.5 * kf, dk=kf, nbins=8, mas_power=0)
+        b = m - 1                                            # bins are centred on the multiples of kf
+        # two modes (+-k0) of power V A^2 / 4 each among the modes of the bin
+        assert np.isclose(r["p0"][b], L.prod() * A * A / 4 * 2 / r["nmodes"][b], rtol=1e-10)
+        assert np.isclose(r["p2"][b] / r["p0"][b], 5 * l2, rtol=1e-6) and np.isclose(r["p4"][b] / r["p0"][b], 9 * l4, rtol=1e-6)
+        others = np.delete(np.arange(8), b)
+        assert np.abs(r["p0"][others]).max() < 1e-20 * r["p0"][b] + 1e-12
+
+
+def test_every_mode_is_counted_once():
+    for shape, L in (((16, 16, 16), (50.0, 50.0, 50.0)), ((12, 10, 14), (30.0, 25.0, 35.0)), ((8, 8, 9), (20.0, 20.0, 20.0))):
+        rho = np.random.default_rng(0).random(shape)
+        r = PK.power_multipoles(rho, L, kmin=0.0, dk=0.05, nbins=400, mas_power=2)
+        assert r["nmodes"].sum() == np.prod(shape) - 1       # all of the Hermitian mesh but k = 0
+        k, mu, W, wt = PK.mode_table(shape, L, (0, 0, 1))
+        assert np.abs(mu).max() <= 1 + 1e-12 and W.min() > 0 and W.max() == 1.0
+
+
+def test_poisson_catalog_has_only_shot_noise():
+    n, L, N = 64, 500.0, 200_000
+    rng = np.random.default_rng(3)
+    pos = [(L * rng.random(N)).astype(f32) for _ in range(3)]
+    bs, bm = np.full(3, L, f32), np.zeros(3, f32)
+    rho = O.cic_scatter(np.zeros((n, n, n), f32), *pos, np.ones(N, f32), bs, bm, True)
+    shot = L ** 3 / N
+    r = PK.power_multipoles(rho, bs, kmin=0.0, dk=0.02, nbins=8, mas_power=2, shot=shot)   # up to 0.4 of Nyquist
+    err = shot * np.sqrt(2.0 / r["nmodes"])
+    assert np.all(np.abs(r["p0"][1:]) < 5 * err[1:] + 0.03 * shot)      # compensated CIC: aliasing stays below 3 % there
+    assert np.all(np.abs(r["p2"][1:]) < 5 * np.sqrt(5.0) * err[1:] + 0.03 * shot)
+
+
+@pytest.fixture(scope="module")
+def F():
+    if not fast.available():
+        subprocess.run(["make", "-C", str(ROOT / "oracle"), "-s"], check=True)
+    return fast.load()
+
+
+def test_reconstruction_removes_the_kaiser_quadrupole(F):
+    import catalogs as Cat
+    L, n, N, f, R = 1000.0, 64, 2_000_000, 0.757, 10.0
+    red, w = Cat.lognormal_box(N, L, seed=5, n_gen=64, sigma=0.8, f_rsd=f)
+    real, _ = Cat.lognormal_box(N, L, seed=5, n_gen=64, sigma=0.8, f_rsd=0.0)     # same particles, no RSD shift
+    red, real, w = [p.numpy() for p in red], [p.numpy() for p in real], w.numpy()
+    bs, bm = np.full(3, L, f32), np.zeros(3, f32)
+
+    def multipoles(p):
+        rho = F.cic_scatter(np.zeros((n, n, n), f32), *[q.copy() for q in p], w, bs, bm, True)
+        return PK.power_multipoles(rho, bs, los=(0, 0, 1), kmin=0.0, dk=0.02, nbins=4, mas_power=2, shot=L ** 3 / N)
+
+    r_real, r_red = multipoles(real), multipoles(red)
+    b = 1                                                    # 0.02 <= k < 0.04 h/Mpc: ~1000 modes, exp(-k^2 R^2 / 2) = 0.95
+    beta = f                                                 # the tracer is the field itself: bias 1
+    kaiser_q = (4 * beta / 3 + 4 * beta ** 2 / 7) / (1 + 2 * beta / 3 + beta ** 2 / 5)      # 0.826
+    q_real, q_red = r_real["p2"][b] / r_real["p0"][b], r_red["p2"][b] / r_red["p0"][b]
+    assert abs(q_real) < 0.15                                # isotropic up to the sample variance of ~1000 modes
+    assert abs(q_red - q_real - kaiser_q) < 0.2              # measured: +0.68
+    assert 1.3 < r_red["p0"][b] / r_real["p0"][b] < 1.8      # Kaiser monopole boost 1.62 (linear theory)
+    rec = F.IterativeRecon(bias=1.0, f=f, smoothing_radius=R, box_size=bs, box_min=bm, los=(0.0, 0.0, 1.0), n_iter=3)
+    mesh = F.run(rec, (n, n, n), *[q.copy() for q in red], w)
+    new = F.reconstructed_positions(rec, *red, mesh, field="rsd")
+    top = np.nextafter(f32(L), f32(0))
+    new = [np.clip(np.mod(q, f32(L)), 0, top).astype(f32) for q in new]
+    r_new = multipoles(new)
+    assert abs(r_new["p2"][b] / r_new["p0"][b] - q_real) < 0.12   # the quadrupole is back at its real-space value (measured: -0.08) ...
+    assert abs(r_new["p0"][b] / r_real["p0"][b] - 1) < 0.15  # ... and so is the monopole (measured: 0.967)
+    # the displacement itself points the right way: removing it as well (field = :sum) lowers the large-scale power
+    both = F.reconstructed_positions(rec, *red, mesh, field="sum")
+    both = [np.clip(np.mod(q, f32(L)), 0, top).astype(f32) for q in both]
+    assert multipoles(both)["p0"][b] < 0.2 * r_real["p0"][b]     # measured: ~0 (k R << 1: the smoothed field is the field)
