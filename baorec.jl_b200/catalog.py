@@ -129,3 +129,27 @@ def wrap_positions(pos_x, pos_y, pos_z, box_size, box_min=(0.0, 0.0, 0.0)):
     L.check(ctx.lib.baorec_wrap_positions_f32(ctx.handle, _ptr(pos_x), _ptr(pos_y), _ptr(pos_z), n, L.f3(np.broadcast_to(box_size, 3)),
                                               L.f3(np.broadcast_to(box_min, 3)), _stream()))
     return pos_x, pos_y, pos_z
+
+
+def power_multipoles(rho, box_size, los=(0.0, 0.0, 1.0), kmin=0.0, dk=None, nbins=None, mas="cic", shot=0.0,
+                     box_min=(0.0, 0.0, 0.0)):
+    """P_0, P_2, P_4 of the density mesh `rho` (device tensor [nz][ny][nx] from `cic`; not modified) for a periodic
+    box: the before / after check of test_helpers/simulation.py:56-75 (pypowspec compute_auto_box), on the device.
+    mas: "cic" / "tsc" / None selects the window the estimate is compensated for; `shot` (e.g. V / N) is subtracted
+    from the monopole.  Defaults: dk = the fundamental 2 pi / max(L), bins up to the Nyquist frequency.
+    Returns dict(k, nmodes, p0, p2, p4) of numpy Float64 arrays (NaN in empty bins)."""
+    from .host import _chk_mesh, _plan_for
+    nx, ny, nz = _chk_mesh(rho)
+    Lb = np.broadcast_to(np.asarray(box_size, np.float64), 3)
+    if dk is None:
+        dk = 2 * np.pi / float(Lb.max())
+    if nbins is None:
+        nbins = int((np.pi * min(nx / Lb[0], ny / Lb[1], nz / Lb[2]) - kmin) / dk)
+    nbins = max(1, min(int(nbins), 1024))
+    ctx = _plan_for(rho, box_size, box_min)
+    out = [np.empty(nbins, np.float64) for _ in range(5)]
+    dp = [o.ctypes.data_as(C.POINTER(C.c_double)) for o in out]
+    power = {None: 0, "none": 0, "ngp": 1, "cic": 2, "tsc": 3}[mas]
+    L.check(ctx.lib.baorec_power_multipoles_f32(ctx.handle, _ptr(rho), L.f3(np.asarray(los, np.float32)), float(kmin), float(dk),
+                                                nbins, power, float(shot), *dp, _stream()))
+    return dict(k=out[0], nmodes=out[1], p0=out[2], p2=out[3], p4=out[4])

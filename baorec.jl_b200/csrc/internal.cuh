@@ -85,6 +85,7 @@ enum BufId {
   BUF_HALO,
   BUF_MGD,      // multigrid level hierarchy of the slab-decomposed solver
   BUF_DET,      // 64-bit fixed-point accumulator of the deterministic scatter
+  BUF_PK,       // multipole estimator: window tables + per-bin Float64 sums
   BUF_COUNT
 };
 

@@ -1,0 +1,189 @@
+// Power-spectrum multipoles P_0, P_2, P_4 of a density mesh on the device: the check the
+// reference makes by eye on every reconstruction (test_helpers/simulation.py:56-75, pypowspec compute_auto_box on
+// the catalogs before / after), as one R2C and ONE pass over the half mesh.
+//
+// pk_kernel: HBM-bound reduction, algorithmic bytes 8 Mc (every mode read once; the result is 5 * nbins doubles).
+// Persistent grid (a multiple of the SM count), each block walks chunks of PK_THREADS * PK_UNROLL modes of one z
+// plane with coalesced float2 loads issued back to back, bins them into a shared-memory histogram of Float64
+// sums -- after a segmented shuffle reduction over the warp's runs of equal bins (|k| is monotonic along a row, so
+// a warp holds a handful of runs): shared Float64 atomics are compare-and-swap loops on sm_100a
+// (ATOMS.CAST.SPIN.64), one per run instead of one per lane keeps them conflict-free -- and flushes its histogram
+// to global memory once at the end (REDG.ADD.F64).
+#include <math.h>
+
+#include <vector>
+
+#include "internal.cuh"
+#include "pk_ops.cuh"
+
+namespace baorec {
+
+constexpr int PK_THREADS = 256;
+constexpr int PK_UNROLL = 4;
+constexpr int PK_MAX_BINS = 1024;  // 5 * 1024 doubles = 40 KB of shared memory
+
+__global__ void __launch_bounds__(PK_THREADS)
+pk_kernel(PkGeom g, const float* __restrict__ tkx, const float* __restrict__ tky, const float* __restrict__ tkz, int ny,
+          unsigned chunks_per_plane, unsigned nchunks, const float2* __restrict__ in, double* __restrict__ acc) {
+  extern __shared__ double s_acc[];  // [5][nbins]
+  const int nb = g.nbins;
+  for (int t = threadIdx.x; t < 5 * nb; t += blockDim.x) s_acc[t] = 0.0;
+  __syncthreads();
+  const unsigned plane = (unsigned)g.xh * (unsigned)ny;
+  const int lane = threadIdx.x & 31;
+  for (unsigned chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {  // block-uniform trip count
+    const unsigned iz = chunk / chunks_per_plane;
+    const unsigned base = (chunk - iz * chunks_per_plane) * (PK_THREADS * PK_UNROLL) + threadIdx.x;
+    const size_t off = (size_t)iz * plane;
+    const float kz = __ldg(tkz + iz);
+    float2 v[PK_UNROLL];
+#pragma unroll
+    for (int u = 0; u < PK_UNROLL; u++) {
+      const unsigned p = base + u * PK_THREADS;
+      v[u] = p < plane ? in[off + p] : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < PK_UNROLL; u++) {
+      const unsigned p = base + u * PK_THREADS;
+      int bin = -1;
+      double c[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      if (p < plane) {
+        const unsigned iy = p / (unsigned)g.xh;
+        const unsigned ix = p - iy * (unsigned)g.xh;
+        bin = pk_mode(g, v[u], __ldg(tkx + ix), __ldg(tky + iy), kz, (int)ix, (int)iy, (int)iz, c);
+      }
+      // Segmented reduction over the warp's runs of equal bins (|k| is monotonic along a row, so equal bins sit in
+      // consecutive lanes): run id = number of run heads up to this lane; five shuffle steps leave the sum of each
+      // run in its head lane, which issues the only atomics (two lanes of one instruction meet on an address only where a
+      // row boundary inside the warp repeats a bin).
+      const int prev = __shfl_up_sync(0xffffffffu, bin, 1);
+      const bool head = lane == 0 || prev != bin;
+      const unsigned heads = __ballot_sync(0xffffffffu, head);
+      const int run = __popc(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int r = __shfl_down_sync(0xffffffffu, run, d);
+        const bool take = lane + d < 32 && r == run;
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+          const double t = __shfl_down_sync(0xffffffffu, c[q], d);
+          if (take) c[q] += t;
+        }
+      }
+      if (head && bin >= 0) {
+#pragma unroll
+        for (int q = 0; q < 5; q++) atomicAdd(&s_acc[q * nb + bin], c[q]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 5 * nb; t += blockDim.x) {
+    const double s = s_acc[t];
+    if (s != 0.0) atomicAdd(acc + t, s);
+  }
+}
+
+static double sinc_pow(double x, int p) {
+  const double s = x == 0.0 ? 1.0 : sin(x) / x;
+  double r = 1.0;
+  for (int i = 0; i < p; i++) r *= s;
+  return r;
+}
+
+int power_multipoles(baorec_ctx* ctx, const float* rho, const float los[3], double kmin, double dk, int nbins,
+                     int mas_power, double shot, double* h_k, double* h_nmodes, double* h_p0, double* h_p2,
+                     double* h_p4, cudaStream_t st) {
+  const int n[3] = {ctx->nx, ctx->ny, ctx->nz};
+  const int len[3] = {ctx->xh, ctx->ny, ctx->nz};
+  const size_t ntab = (size_t)len[0] + len[1] + len[2];
+  // window tables from the context's own k tables: W_a = sinc(k_a h_a / 2)^p in Float64
+  std::vector<float> kt(ntab);
+  std::vector<double> wt(ntab);
+  size_t o = 0;
+  for (int a = 0; a < 3; a++) {
+    BR_CUDA(cudaMemcpyAsync(kt.data() + o, ctx->d_k[a], sizeof(float) * len[a], cudaMemcpyDeviceToHost, st));
+    o += len[a];
+  }
+  BR_CUDA(cudaStreamSynchronize(st));
+  o = 0;
+  for (int a = 0; a < 3; a++) {
+    const double h = (double)ctx->L[a] / (double)n[a];
+    for (int i = 0; i < len[a]; i++) wt[o + i] = sinc_pow((double)kt[o + i] * h / 2.0, mas_power);
+    o += len[a];
+  }
+  double* d;
+  BR_TRY(need_t(ctx, BUF_PK, ntab + (size_t)5 * nbins, &d));
+  double* acc = d + ntab;
+  BR_CUDA(cudaMemcpyAsync(d, wt.data(), sizeof(double) * ntab, cudaMemcpyHostToDevice, st));
+  BR_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 5 * nbins, st));
+  float2* ck0;
+  BR_TRY(need_t(ctx, BUF_CK0, ctx->Mc, &ck0));
+  BR_TRY(fft_r2c(ctx, rho, ck0, st));
+  PkGeom g;
+  g.wx = d;
+  g.wy = d + len[0];
+  g.wz = d + len[0] + len[1];
+  const double ln = sqrt((double)los[0] * los[0] + (double)los[1] * los[1] + (double)los[2] * los[2]);
+  for (int a = 0; a < 3; a++) g.los[a] = (double)los[a] / ln;
+  g.kmin = kmin;
+  g.dk = dk;
+  g.nbins = nbins;
+  g.xh = ctx->xh;
+  g.nyq_x = (ctx->nx % 2 == 0) ? ctx->nx / 2 : -1;
+  const size_t plane = (size_t)ctx->xh * ctx->ny;
+  const unsigned cpp = cdiv(plane, PK_THREADS * PK_UNROLL);
+  const size_t nchunks = (size_t)cpp * ctx->nz;
+  BR_REQUIRE(nchunks < ((size_t)1 << 32), "mesh too large for the multipole kernel's chunk index");
+  // persistent grid: SM count x resident blocks per SM (74 registers -> 3 blocks of 256 threads)
+  int sms = 148, occ = 1;
+  BR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+  BR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pk_kernel, PK_THREADS, sizeof(double) * 5 * nbins));
+  unsigned grid = (unsigned)sms * (unsigned)(occ > 0 ? occ : 1);
+  if (grid > nchunks) grid = (unsigned)nchunks;
+  BR_LAUNCH(ctx, pk_kernel, grid, PK_THREADS, sizeof(double) * 5 * nbins, st, g, ctx->d_k[0], ctx->d_k[1],
+            ctx->d_k[2], ctx->ny, cpp, (unsigned)nchunks, ck0, acc);
+  std::vector<double> h((size_t)5 * nbins);
+  float2 dc;
+  BR_CUDA(cudaMemcpyAsync(h.data(), acc, sizeof(double) * 5 * nbins, cudaMemcpyDeviceToHost, st));
+  BR_CUDA(cudaMemcpyAsync(&dc, ck0, sizeof(float2), cudaMemcpyDeviceToHost, st));
+  BR_CUDA(cudaStreamSynchronize(st));
+  if (!(dc.x != 0.f)) {
+    set_error("baorec_power_multipoles_f32: the mesh sums to zero (pass the density, not the overdensity)");
+    return BAOREC_ERR_INVALID;
+  }
+  const double V = (double)ctx->L[0] * (double)ctx->L[1] * (double)ctx->L[2];
+  const double norm = V / ((double)dc.x * (double)dc.x);  // P = V |rho_k|^2 / rho_0^2 = V |delta_k|^2 / M^2
+  const double nan = ::nan("");
+  for (int b = 0; b < nbins; b++) {
+    const double cnt = h[b];
+    h_nmodes[b] = cnt;
+    if (cnt > 0.0) {
+      h_k[b] = h[nbins + b] / cnt;
+      h_p0[b] = h[2 * nbins + b] / cnt * norm - shot;
+      h_p2[b] = 5.0 * h[3 * nbins + b] / cnt * norm;
+      h_p4[b] = 9.0 * h[4 * nbins + b] / cnt * norm;
+    } else {
+      h_k[b] = h_p0[b] = h_p2[b] = h_p4[b] = nan;
+    }
+  }
+  return BAOREC_OK;
+}
+
+}  // namespace baorec
+
+using namespace baorec;
+
+extern "C" int baorec_power_multipoles_f32(baorec_ctx* ctx, const float* d_rho, const float los[3], double kmin,
+                                           double dk, int nbins, int mas_power, double shot, double* h_k,
+                                           double* h_nmodes, double* h_p0, double* h_p2, double* h_p4,
+                                           baorec_stream stream) {
+  BR_NEED_PLAN(ctx);
+  BR_REQUIRE(d_rho != nullptr && los != nullptr, "NULL mesh / line of sight");
+  BR_REQUIRE(h_k && h_nmodes && h_p0 && h_p2 && h_p4, "NULL output array");
+  BR_REQUIRE(nbins >= 1 && nbins <= PK_MAX_BINS, "nbins must be in 1..1024");
+  BR_REQUIRE(dk > 0.0 && kmin >= 0.0, "kmin >= 0 and dk > 0");
+  BR_REQUIRE(mas_power >= 0 && mas_power <= 4, "mas_power (window exponent) must be in 0..4");
+  BR_REQUIRE(los[0] != 0.f || los[1] != 0.f || los[2] != 0.f, "line of sight is the zero vector");
+  return power_multipoles(ctx, d_rho, los, kmin, dk, nbins, mas_power, shot, h_k, h_nmodes, h_p0, h_p2, h_p4,
+                          (cudaStream_t)stream);
+}

@@ -70,7 +70,7 @@ GENERIC = {"$(QuoteNode(sym))": re.findall(r"\(:\w+!?, :(baorec_\w+)\)", SHIM), 
 
 def test_every_ccall_matches_its_prototype():
     protos, calls = c_prototypes(), shim_ccalls()
-    assert len(protos) == 58 and len(calls) >= 25
+    assert len(protos) == 59 and len(calls) >= 25
     seen = set()
     for sym, ret, types, line in calls:
         if sym.startswith(":"):
@@ -99,7 +99,7 @@ def test_every_ccall_matches_its_prototype():
                  "baorec_reconstructed_positions_f32", "baorec_setup_box_f32", "baorec_mg_jacobi_f32", "baorec_mg_residual_f32",
                  "baorec_mg_restrict_f32", "baorec_mg_prolong_f32", "baorec_mg_vcycle_f32", "baorec_mg_fmg_f32",
                  "baorec_cosmo_set", "baorec_sky_to_cartesian_f32", "baorec_cartesian_to_sky_f32", "baorec_fkp_weights_f32",
-                 "baorec_wrap_positions_f32"):
+                 "baorec_wrap_positions_f32", "baorec_power_multipoles_f32"):
         assert must in seen, must
 
 
