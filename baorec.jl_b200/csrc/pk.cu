@@ -83,11 +83,12 @@ pk_kernel(PkGeom g, const float* __restrict__ tkx, const float* __restrict__ tky
   }
 }
 
-static double sinc_pow(double x, int p) {
+// 1 / sinc(x)^(2p): the inverse squared window of one axis
+static double inv_window2(double x, int p) {
   const double s = x == 0.0 ? 1.0 : sin(x) / x;
   double r = 1.0;
   for (int i = 0; i < p; i++) r *= s;
-  return r;
+  return 1.0 / (r * r);
 }
 
 int power_multipoles(baorec_ctx* ctx, const float* rho, const float los[3], double kmin, double dk, int nbins,
@@ -96,7 +97,7 @@ int power_multipoles(baorec_ctx* ctx, const float* rho, const float los[3], doub
   const int n[3] = {ctx->nx, ctx->ny, ctx->nz};
   const int len[3] = {ctx->xh, ctx->ny, ctx->nz};
   const size_t ntab = (size_t)len[0] + len[1] + len[2];
-  // window tables from the context's own k tables: W_a = sinc(k_a h_a / 2)^p in Float64
+  // window tables from the context's own k tables: 1 / W_a^2, W_a = sinc(k_a h_a / 2)^p, in Float64
   std::vector<float> kt(ntab);
   std::vector<double> wt(ntab);
   size_t o = 0;
@@ -108,7 +109,7 @@ int power_multipoles(baorec_ctx* ctx, const float* rho, const float los[3], doub
   o = 0;
   for (int a = 0; a < 3; a++) {
     const double h = (double)ctx->L[a] / (double)n[a];
-    for (int i = 0; i < len[a]; i++) wt[o + i] = sinc_pow((double)kt[o + i] * h / 2.0, mas_power);
+    for (int i = 0; i < len[a]; i++) wt[o + i] = inv_window2((double)kt[o + i] * h / 2.0, mas_power);
     o += len[a];
   }
   double* d;
@@ -126,7 +127,7 @@ int power_multipoles(baorec_ctx* ctx, const float* rho, const float los[3], doub
   const double ln = sqrt((double)los[0] * los[0] + (double)los[1] * los[1] + (double)los[2] * los[2]);
   for (int a = 0; a < 3; a++) g.los[a] = (double)los[a] / ln;
   g.kmin = kmin;
-  g.dk = dk;
+  g.inv_dk = 1.0 / dk;
   g.nbins = nbins;
   g.xh = ctx->xh;
   g.nyq_x = (ctx->nx % 2 == 0) ? ctx->nx / 2 : -1;
@@ -134,7 +135,7 @@ int power_multipoles(baorec_ctx* ctx, const float* rho, const float los[3], doub
   const unsigned cpp = cdiv(plane, PK_THREADS * PK_UNROLL);
   const size_t nchunks = (size_t)cpp * ctx->nz;
   BR_REQUIRE(nchunks < ((size_t)1 << 32), "mesh too large for the multipole kernel's chunk index");
-  // persistent grid: SM count x resident blocks per SM (74 registers -> 3 blocks of 256 threads)
+  // persistent grid: SM count x resident blocks per SM (64 registers -> 4 blocks of 256 threads)
   int sms = 148, occ = 1;
   BR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
   BR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pk_kernel, PK_THREADS, sizeof(double) * 5 * nbins));

@@ -9,11 +9,11 @@
 namespace baorec {
 
 struct PkGeom {
-  const double* wx;  // per-axis mass-assignment window sinc(k_a h_a / 2)^p, Float64, tabulated on the host
+  const double* wx;  // per-axis inverse squared mass-assignment window 1 / sinc(k_a h_a / 2)^(2p), Float64, tabulated on the host
   const double* wy;
   const double* wz;
   double los[3];     // unit line of sight
-  double kmin, dk;
+  double kmin, inv_dk;  // bin = floor((|k| - kmin) * inv_dk), inv_dk = 1 / dk rounded once (the oracle does the same)
   int nbins;
   int xh;            // nx/2 + 1
   int nyq_x;         // index of the x-Nyquist plane (nx even), or -1
@@ -30,12 +30,12 @@ __device__ __forceinline__ int pk_mode(const PkGeom& g, float2 v, float kx, floa
   const double k2 = x * x + y * y + z * z;
   if (!(k2 > 0.0)) return -1;
   const double k = sqrt(k2);
-  const double fb = floor((k - g.kmin) / g.dk);
+  const double fb = floor((k - g.kmin) * g.inv_dk);
   if (!(fb >= 0.0 && fb < (double)g.nbins)) return -1;
   const double mu = (x * g.los[0] + y * g.los[1] + z * g.los[2]) / k;
   const double mu2 = mu * mu;
-  const double W = __ldg(g.wx + ix) * __ldg(g.wy + iy) * __ldg(g.wz + iz);
-  const double p = ((double)v.x * (double)v.x + (double)v.y * (double)v.y) / (W * W);
+  const double iw2 = __ldg(g.wx + ix) * __ldg(g.wy + iy) * __ldg(g.wz + iz);
+  const double p = ((double)v.x * (double)v.x + (double)v.y * (double)v.y) * iw2;
   const double w = (ix == 0 || ix == g.nyq_x) ? 1.0 : 2.0;
   const double wp = w * p;
   c[0] = w;

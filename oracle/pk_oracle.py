@@ -14,7 +14,8 @@ known-answer tests in tests/test_pk_oracle.py -- plane waves, Poisson shot noise
     P_l(k_i)  = (2l+1) <P(k) L_l(mu)>_{k in bin i} - [l == 0] shot     mu = k . los / |k|
 
 Every mode of the full (Hermitian) mesh counts once: on the half mesh the planes kx = 0 and kx = Nyquist have
-weight 1, the others weight 2.  k = 0 is excluded.  Bins are [kmin + i dk, kmin + (i+1) dk), i < nbins.
+weight 1, the others weight 2.  k = 0 is excluded.  Bins are [kmin + i dk, kmin + (i+1) dk), i < nbins
+(index = floor((|k| - kmin) * (1/dk)) in Float64).
 Only tests/ (and the product's parity tests) may import this module."""
 from __future__ import annotations
 
@@ -69,7 +70,7 @@ def power_multipoles(rho, box_size, los=(0.0, 0.0, 1.0), kmin=0.0, dk=None, nbin
     k, mu, W, wt = mode_table(rho.shape, box_size, los, mas_power)
     V = float(L.prod())
     p = (rk.real.astype(np.float64) ** 2 + rk.imag.astype(np.float64) ** 2) * (V / (a0 * a0)) / (W * W)
-    b = np.floor((k - kmin) / dk).astype(np.int64)
+    b = np.floor((k - kmin) * (1.0 / dk)).astype(np.int64)     # 1/dk rounded once, like the device kernel
     ok = (b >= 0) & (b < nbins) & (wt > 0)
     b, w = b[ok], wt[ok]
     p, mu, kk = p[ok], mu[ok], k[ok]

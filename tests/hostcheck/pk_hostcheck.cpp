@@ -20,7 +20,7 @@ int64_t hc_pk(const float* rk, const float* kx, const float* ky, const float* kz
   g.wz = wz;
   for (int a = 0; a < 3; a++) g.los[a] = los[a];
   g.kmin = kmin;
-  g.dk = dk;
+  g.inv_dk = 1.0 / dk;
   g.nbins = nbins;
   g.xh = nx / 2 + 1;
   g.nyq_x = nx % 2 == 0 ? nx / 2 : -1;

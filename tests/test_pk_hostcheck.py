@@ -49,7 +49,7 @@ def device_estimate(HC, rho, bs, los, kmin, dk, nbins, power, shot):
         r = np.ones_like(s)
         for _ in range(power):
             r = r * s
-        return np.ascontiguousarray(r)
+        return np.ascontiguousarray(1.0 / (r * r))               # csrc/pk.cu: inv_window2
 
     wt = [window(kv[a], h[a]) for a in range(3)]
     lv = np.asarray(los, f32).astype(np.float64)
