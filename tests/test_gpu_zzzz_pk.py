@@ -60,3 +60,39 @@ def test_plane_wave_and_errors(B):
         B.power_multipoles(torch.zeros((n, n, n), dtype=torch.float32, device="cuda"), np.full(3, L, f32))
     with pytest.raises(B.BaorecError):
         B.power_multipoles(rho, np.full(3, L, f32), los=(0.0, 0.0, 0.0))
+
+
+@pytest.mark.parametrize("algorithm", ["iterative", "multigrid"])
+def test_reconstruction_removes_the_kaiser_quadrupole_on_the_device(B, algorithm):
+    """The physics known-answer test of tests/test_pk_oracle.py with the product instead of the oracle, end to end on
+    the device and 8x the volume: lognormal box with a linear redshift-space shift -> run! ->
+    reconstructed_positions(field = :rsd) -> re-wrap -> P_0, P_2 from baorec_power_multipoles_f32."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "benchmarks"))
+    import catalogs as Cat
+    L, n, N, f, R = 2000.0, 128, 16_000_000, 0.757, 10.0
+    red, w = Cat.lognormal_box(N, L, seed=5, device="cuda", n_gen=128, sigma=0.8, f_rsd=f)
+    real, _ = Cat.lognormal_box(N, L, seed=5, device="cuda", n_gen=128, sigma=0.8, f_rsd=0.0)
+    bs, bm = np.full(3, L, f32), np.zeros(3, f32)
+
+    def multipoles(p):
+        rho = torch.zeros((n, n, n), dtype=torch.float32, device="cuda")
+        B.cic(rho, *[q.clone() for q in p], w, bs, bm, wrap=True)
+        return B.power_multipoles(rho, bs, los=(0.0, 0.0, 1.0), kmin=0.0, dk=0.02, nbins=4, mas="cic", shot=L ** 3 / N)
+
+    r_real, r_red = multipoles(real), multipoles(red)
+    b = 1                                                    # 0.02 <= k < 0.04 h/Mpc: ~8000 modes
+    kaiser_q = (4 * f / 3 + 4 * f ** 2 / 7) / (1 + 2 * f / 3 + f ** 2 / 5)
+    q_real, q_red = r_real["p2"][b] / r_real["p0"][b], r_red["p2"][b] / r_red["p0"][b]
+    assert abs(q_real) < 0.15 and abs(q_red - q_real - kaiser_q) < 0.25
+    assert 1.3 < r_red["p0"][b] / r_real["p0"][b] < 1.8
+    kw = dict(bias=1.0, f=f, smoothing_radius=R, box_size=bs, box_min=bm, los=(0.0, 0.0, 1.0))
+    rec = B.IterativeRecon(n_iter=3, **kw) if algorithm == "iterative" else B.MultigridRecon(**kw)
+    pos = [q.clone() for q in red]
+    B.run(rec, (n, n, n), *pos, w)
+    new = list(B.reconstructed_positions(rec, *pos, field="rsd"))
+    B.wrap_positions(*new, bs, bm)
+    r_new = multipoles(new)
+    assert abs(r_new["p2"][b] / r_new["p0"][b] - q_real) < 0.12
+    assert abs(r_new["p0"][b] / r_real["p0"][b] - 1) < 0.15
