@@ -13,7 +13,7 @@ from . import lib_loader
 from .lib_loader import BaorecError, OutOfBoxError, OutOfRangeError
 from .host import (Context, FFTPlan, IterativeRecon, MultigridRecon, setup_fft, k_vec, x_vec, setup_box, smooth, cic,
                    read_cic, cic_cells, gather_cells, setup_overdensity, iterate, reconstructed_overdensity,
-                   reconstructed_potential, run, compute_displacements, displacement_meshes, read_shifts,
+                   reconstructed_potential, run, run_batch, compute_displacements, displacement_meshes, read_shifts,
                    reconstructed_positions, jacobi, residual, reduce, prolong, vcycle, fmg)
 
 from . import dist

@@ -351,4 +351,118 @@ int baorec_read_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm,
   return BAOREC_OK;
 }
 
+// ---- many catalogs per process: the host pipeline, software-pipelined over a batch --------------------------------
+// README.md:11 of the reference: "one process, many reconstructions" (the examples loop over mocks).  For each
+// catalog this is baorec_run_host_f32 followed by baorec_read_host_f32 on the same catalog -- periodic box, no
+// randoms -- but the PCIe transfers of neighbouring catalogs overlap the solve: the upload of catalog i+1 (copy
+// stream) and the download of the results of catalog i-1 (download stream) run while catalog i is reconstructed
+// (main stream); catalogs and results are double-buffered on the device, the read-back uses the positions
+// already resident (no second upload) and the tile sort run! made (same device arrays -> hash hit).
+int baorec_batch_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, int n_catalogs, float* const* h_x,
+                          float* const* h_y, float* const* h_z, const float* const* h_w, const int64_t* n, int field,
+                          int shifts_only, float* const* h_ox, float* const* h_oy, float* const* h_oz) {
+  BR_NEED_PLAN(ctx);
+  BR_TRY(check_params(p));
+  BR_REQUIRE(algorithm == BAOREC_ITERATIVE || algorithm == BAOREC_MULTIGRID, "unknown algorithm");
+  BR_REQUIRE(field >= BAOREC_FIELD_DISP && field <= BAOREC_FIELD_SUM, "unknown field");
+  BR_REQUIRE(n_catalogs >= 1 && h_x && h_y && h_z && h_w && n && h_ox && h_oy && h_oz, "batch arrays");
+  int64_t nmax = 0;
+  for (int i = 0; i < n_catalogs; i++) {
+    BR_REQUIRE(n[i] > 0 && h_x[i] && h_y[i] && h_z[i] && h_w[i] && h_ox[i] && h_oy[i] && h_oz[i], "catalog arrays");
+    if (n[i] > nmax) nmax = n[i];
+  }
+  cudaStream_t st = ctx->own_stream, up = ctx->copy_stream;
+  float *part[2], *out, *mesh, *px, *py, *pz;
+  BR_TRY(need_t(ctx, BUF_PART, (size_t)nmax * 4, &part[0]));
+  BR_TRY(need_t(ctx, BUF_PART2, (size_t)nmax * 4, &part[1]));
+  BR_TRY(need_t(ctx, BUF_OUT, (size_t)nmax * 6, &out));
+  BR_TRY(need_t(ctx, BUF_CACHE, ctx->M, &mesh));
+  BR_TRY(need_t(ctx, BUF_RX, ctx->M, &px));
+  BR_TRY(need_t(ctx, BUF_RY, ctx->M, &py));
+  BR_TRY(need_t(ctx, BUF_RZ, ctx->M, &pz));
+  float* outb[2] = {out, out + (size_t)nmax * 3};
+  cudaStream_t dn = nullptr;
+  cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_gather[2] = {nullptr, nullptr}, ev_dn[2] = {nullptr, nullptr};
+  BR_CUDA(cudaStreamCreateWithFlags(&dn, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; b++) {
+    BR_CUDA(cudaEventCreateWithFlags(&ev_up[b], cudaEventDisableTiming));
+    BR_CUDA(cudaEventCreateWithFlags(&ev_gather[b], cudaEventDisableTiming));
+    BR_CUDA(cudaEventCreateWithFlags(&ev_dn[b], cudaEventDisableTiming));
+  }
+  ctx->cache_valid = false;
+  ctx->kcache_valid = false;
+  ctx->disp_valid = false;
+  auto upload = [&](int i) -> int {  // catalog i -> part[i & 1] (x, y, z, w at stride n[i]) on the copy stream
+    const int b = i & 1;
+    const float* src[4] = {h_x[i], h_y[i], h_z[i], h_w[i]};
+    for (int c = 0; c < 4; c++)
+      BR_CUDA(cudaMemcpyAsync(part[b] + (size_t)c * n[i], src[c], (size_t)n[i] * sizeof(float), cudaMemcpyHostToDevice, up));
+    BR_CUDA(cudaEventRecord(ev_up[b], up));
+    return BAOREC_OK;
+  };
+  auto body = [&]() -> int {
+    // everything queued on the main stream so far (an earlier call's work on these buffers) precedes the first upload
+    BR_CUDA(cudaEventRecord(ev_gather[0], st));
+    BR_CUDA(cudaStreamWaitEvent(up, ev_gather[0], 0));
+    BR_TRY(upload(0));
+    for (int i = 0; i < n_catalogs; i++) {
+      const int b = i & 1;
+      const int64_t ni = n[i];
+      float *dx = part[b], *dy = part[b] + ni, *dz = part[b] + 2 * ni, *dw = part[b] + 3 * ni;
+      if (i + 1 < n_catalogs) {
+        // part[b ^ 1] was last read by the gather of catalog i-1, which has completed (check_oob synchronises the
+        // main stream); the event keeps the order explicit on the device as well
+        if (i >= 1) BR_CUDA(cudaStreamWaitEvent(up, ev_gather[b ^ 1], 0));
+        BR_TRY(upload(i + 1));
+      }
+      BR_CUDA(cudaStreamWaitEvent(st, ev_up[b], 0));
+      BR_CUDA(cudaMemsetAsync(mesh, 0, ctx->M * sizeof(float), st));
+      ctx->want_kcache = true;
+      int s = algorithm == BAOREC_MULTIGRID
+                  ? reconstructed_potential(ctx, p, mesh, dx, dy, dz, dw, ni, nullptr, nullptr, nullptr, nullptr, 0, st)
+                  : reconstructed_overdensity(ctx, p, mesh, dx, dy, dz, dw, ni, nullptr, nullptr, nullptr, nullptr, 0, st);
+      ctx->want_kcache = false;
+      if (s != BAOREC_OK) return s;
+      if (ctx->last_wrapped > 0) {  // cic!(wrap = true) mutates the caller's positions (src/mas.jl:8-10)
+        float* hdst[3] = {h_x[i], h_y[i], h_z[i]};
+        for (int c = 0; c < 3; c++)
+          BR_CUDA(cudaMemcpyAsync(hdst[c], part[b] + (size_t)c * ni, (size_t)ni * sizeof(float), cudaMemcpyDeviceToHost, st));
+      }
+      ctx->disp_valid = false;
+      BR_TRY(displacement_meshes(ctx, mesh, algorithm, px, py, pz, st, /*use_kcache=*/true));
+      if (i >= 2) BR_CUDA(cudaStreamWaitEvent(st, ev_dn[b], 0));  // outb[b] still holds the results of catalog i-2
+      BR_TRY(reset_oob(ctx, st));
+      BR_TRY(gather3(ctx, px, py, pz, dx, dy, dz, ni, outb[b], outb[b] + ni, outb[b] + 2 * ni, p->mas, field, p->f,
+                     p->has_los, p->los, shifts_only ? 0 : 1, st));
+      BR_CUDA(cudaEventRecord(ev_gather[b], st));
+      BR_TRY(check_oob(ctx, st, "read_shifts"));
+      BR_CUDA(cudaStreamWaitEvent(dn, ev_gather[b], 0));
+      float* hdst[3] = {h_ox[i], h_oy[i], h_oz[i]};
+      for (int c = 0; c < 3; c++)
+        BR_CUDA(cudaMemcpyAsync(hdst[c], outb[b] + (size_t)c * ni, (size_t)ni * sizeof(float), cudaMemcpyDeviceToHost, dn));
+      BR_CUDA(cudaEventRecord(ev_dn[b], dn));
+    }
+    BR_CUDA(cudaStreamSynchronize(dn));
+    BR_CUDA(cudaStreamSynchronize(st));
+    return BAOREC_OK;
+  };
+  const int status = body();
+  if (status != BAOREC_OK) {  // drain whatever is in flight before the buffers are reused
+    cudaStreamSynchronize(up);
+    cudaStreamSynchronize(dn);
+    cudaStreamSynchronize(st);
+  }
+  for (int b = 0; b < 2; b++) {
+    cudaEventDestroy(ev_up[b]);
+    cudaEventDestroy(ev_gather[b]);
+    cudaEventDestroy(ev_dn[b]);
+  }
+  cudaStreamDestroy(dn);
+  ctx->sortc_valid = false;  // the sort belongs to a staging buffer the next call overwrites
+  ctx->cache_valid = status == BAOREC_OK;
+  ctx->disp_valid = false;
+  return status;
+}
+
+
 }  // extern "C"

@@ -476,6 +476,34 @@ def run(recon: AbstractRecon, grid_size, data_x, data_y, data_z, data_w, *rand, 
     return mesh_out if mesh_out is not None else recon.result_cache
 
 
+def run_batch(recon: AbstractRecon, grid_size, catalogs, field="disp", positions=True, out=None):
+    """Many catalogs per process (the reference's README: "one process, many reconstructions"; its examples loop over
+    mocks): for every (x, y, z, w) in `catalogs` -- HOST float32 arrays, periodic box, no randoms -- `run!` followed by
+    `reconstructed_positions` (or `read_shifts` with positions=False) of that catalog, with the PCIe transfers of
+    neighbouring catalogs overlapping the solve (baorec_batch_host_f32).  Use pinned arrays (torch `pin_memory`
+    + `.numpy()`, or baorec_host_alloc) for the overlap to happen.  `out`: optional list of 3-tuples of host arrays that
+    receive the results.  Returns the list of (ox, oy, oz)."""
+    nx, ny, nz = (int(v) for v in grid_size)
+    K = len(catalogs)
+    ns = [_chk_np(*cat) for cat in catalogs]
+    if out is None:
+        out = [tuple(np.empty(n, dtype=np.float32) for _ in range(3)) for n in ns]
+    for n, o in zip(ns, out):
+        assert _chk_np(*o) == n
+    if recon.box_size is None:
+        raise RuntimeError("recon.box_size / recon.box_min are not set")
+    setup_fft(recon, (nx, ny, nz))
+    ctx = recon._ctx(grid_size=(nx, ny, nz))
+    p = recon._params()
+    col = lambda arrs: (C.c_void_p * K)(*[a.ctypes.data for a in arrs])
+    L.check(ctx.lib.baorec_batch_host_f32(
+        ctx.handle, C.byref(p), recon.algorithm, K, col([c[0] for c in catalogs]), col([c[1] for c in catalogs]),
+        col([c[2] for c in catalogs]), col([c[3] for c in catalogs]), (C.c_int64 * K)(*ns), L.FIELDS[field],
+        0 if positions else 1, col([o[0] for o in out]), col([o[1] for o in out]), col([o[2] for o in out])))
+    recon.result_cache = ("device-cache", ctx)
+    return out
+
+
 def compute_displacements(mesh, data_x, data_y, data_z, recon: AbstractRecon):
     """compute_displacements src/iterative.jl:229-250 / src/multigrid.jl:781-799."""
     n = _chk_vec(data_x, data_y, data_z)

@@ -363,6 +363,29 @@ function power_multipoles(rho::CuArray{Float32,3}, los = (0f0, 0f0, 1f0); kmin =
     (k = k, nmodes = nmodes, p0 = p0, p2 = p2, p4 = p4)
 end
 
+# Many mocks per process (the reference's README: "one process, many reconstructions"): run! + reconstructed_positions
+# (or read_shifts with positions = false) for every HOST catalog (x, y, z, w) of a periodic box, the PCIe transfers of
+# neighbouring catalogs overlapping the solve.  Returns one (x, y, z) tuple of Vectors per catalog.
+function run_batch(recon::AbstractRecon, grid_size::NTuple{3,Int}, catalogs::Vector{<:NTuple{4,Vector{Float32}}};
+                   field = :disp, positions::Bool = true)
+    ctx = context()
+    check(ccall((:baorec_plan, libbaorec), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cfloat}, Ptr{Cfloat}),
+                ctx, grid_size[1], grid_size[2], grid_size[3], f3(recon.box_size), f3(recon.box_min)))
+    n = Int64[length(c[1]) for c in catalogs]
+    out = [Tuple(Vector{Float32}(undef, k) for _ in 1:3) for k in n]
+    col(arrs) = Ptr{Cvoid}[Ptr{Cvoid}(pointer(a)) for a in arrs]
+    p = Ref(Params(recon))
+    GC.@preserve catalogs out begin
+        check(ccall((:baorec_batch_host_f32, libbaorec), Cint,
+                    (Ptr{Cvoid}, Ptr{Params}, Cint, Cint, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Int64},
+                     Cint, Cint, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}),
+                    ctx, p, algorithm(recon), length(catalogs), col(c[1] for c in catalogs), col(c[2] for c in catalogs),
+                    col(c[3] for c in catalogs), col(c[4] for c in catalogs), n, FIELD[field], positions ? 0 : 1,
+                    col(o[1] for o in out), col(o[2] for o in out), col(o[3] for o in out)))
+    end
+    out
+end
+
 # run! needs no override: the reference's run! (src/recon.jl:134-261) allocates a CuArray mesh when
 # data_x isa CuArray and calls setup_fft!, setup_box and reconstructed_*! -- all of which dispatch
 # to the methods above.

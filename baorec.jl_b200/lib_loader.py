@@ -105,6 +105,7 @@ SIGNATURES = {
     "baorec_displacement_meshes_f32": [_vp, _vp, _i, _vp, _vp, _vp, _vp],
     "baorec_run_host_f32": [_vp, _pp, _i, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _f3, _f3],
     "baorec_read_host_f32": [_vp, _pp, _i, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp],
+    "baorec_batch_host_f32": [_vp, _pp, _i, _i] + [C.POINTER(_vp)] * 4 + [C.POINTER(_i64), _i, _i] + [C.POINTER(_vp)] * 3,
     "baorec_result_cache": [_vp],
     "baorec_cosmo_set": [_vp, C.POINTER(CosmologyParams)],
     "baorec_cosmo_build_table": [C.POINTER(CosmologyParams), C.POINTER(C.c_double), C.POINTER(C.c_double)],

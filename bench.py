@@ -262,6 +262,9 @@ def main():
                          "(sigma = 1 on a 512^3 generation mesh + linear RSD shift, generated on the device; --gpus 1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-batch", type=int, default=0,
+                    help="K > 0 (one GPU): additionally time the batched host pipeline (baorec_batch_host_f32) over K catalogs "
+                         "and report it as e2e['batched'] -- off by default until it has run on hardware once")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -420,6 +423,28 @@ def main():
                             "h2d_pos+disp_meshes": stage[3], "gather": stage[4], "d2h_shifts": stage[5]}
                if (len(stage) >= 6 and world == 1) else None,
                "checksum_abs_mean_shift_z": float(np.abs(outs[2][: 1 << 20]).mean())}
+
+    # ---- optional: the batched host pipeline (transfers of neighbouring catalogs overlap the solve) -----------
+    if e2e is not None and args.e2e_batch > 0 and world == 1:
+        K = args.e2e_batch
+        (gx, gy, gz), gw = make_catalog(N, L, seed=43, pinned=True)          # a second catalog: the batch alternates
+        two = [(ax, ay, az, aw), tuple(t.numpy() for t in (gx, gy, gz, gw))]
+        outs2_t = [torch.empty(n_loc, dtype=torch.float32, pin_memory=True) for _ in range(3)]
+        two_out = [tuple(outs), tuple(t.numpy() for t in outs2_t)]
+        cats = [two[i & 1] for i in range(K)]
+        bouts = [two_out[i & 1] for i in range(K)]
+        rec_b = B.IterativeRecon(**kw)
+        B.run_batch(rec_b, grid, cats[:2], field="sum", positions=False, out=bouts[:2])     # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        B.run_batch(rec_b, grid, cats, field="sum", positions=False, out=bouts)
+        torch.cuda.synchronize()
+        dtb = (time.perf_counter() - t0) * 1e3 / K
+        e2e["batched"] = {"value": dtb, "unit": UNIT, "catalogs": K,
+                          "h2d_bytes_per_catalog": 16 * N, "d2h_bytes_per_catalog": 12 * N,
+                          "what": "baorec_batch_host_f32: run! + read_shifts(:sum) per catalog, upload of catalog i+1 and "
+                                  "download of catalog i-1 overlapping the reconstruction of catalog i",
+                          "checksum_abs_mean_shift_z": float(np.abs(bouts[-1][2][: 1 << 20]).mean())}
 
     if rank != 0:
         if world > 1:

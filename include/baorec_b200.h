@@ -290,6 +290,17 @@ int baorec_run_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm,
 int baorec_read_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, const float* h_mesh_or_null,
                          const float* h_x, const float* h_y, const float* h_z, int64_t n, int field,
                          int shifts_only, float* h_ox, float* h_oy, float* h_oz);
+/* Many catalogs per process (README.md:11 "one process, many reconstructions"; the examples loop over mocks):
+ * for every catalog i < n_catalogs, run! (periodic box, no randoms; src/recon.jl:134-180 / 215-261) followed by
+ * reconstructed_positions / read_shifts of THAT catalog (src/recon.jl:333-388) -- baorec_run_host_f32 +
+ * baorec_read_host_f32 per catalog, software-pipelined: the upload of catalog i+1 and the download of the results of
+ * catalog i-1 overlap the reconstruction of catalog i (catalogs and results double-buffered on the device; the
+ * read-back uses the resident positions and the tile sort run! made).  h_x[i] ... are HOST arrays of n[i] floats
+ * (pinned memory for the overlap to happen); wrapped positions are written back to h_x/h_y/h_z like cic!.
+ * shifts_only != 0 -> read_shifts.  Afterwards the context's result cache is the mesh of the last catalog. */
+int baorec_batch_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, int n_catalogs, float* const* h_x,
+                          float* const* h_y, float* const* h_z, const float* const* h_w, const int64_t* n, int field,
+                          int shifts_only, float* const* h_ox, float* const* h_oy, float* const* h_oz);
 /* Device pointer of the cached result mesh (recon.result_cache), or NULL. */
 float* baorec_result_cache(baorec_ctx* ctx);
 
