@@ -17,6 +17,8 @@ done
 run test_validated python -m pytest tests -q -m gpu -x --ignore tests/test_gpu_zzz_fullsize.py --ignore-glob='tests/test_gpu_zzzz_*' --ignore tests/test_gpu_zzz_golden_catalog.py
 # 3. the bench with the batched host pipeline next to the one-at-a-time e2e
 run bench_batch python bench.py --steps 5 --warmup 3 --e2e-batch 4
+# 3b. the secondary configs, TSC included (BASELINE configs[1] names TSC; only CIC was measured in round 1)
+run secondary python benchmarks/secondary.py c2 c2tsc c3
 # 4. option A/B on the bench workload, uniform and lognormal
 run ab_uniform python benchmarks/ab_options.py --steps 3
 run ab_lognormal python benchmarks/ab_options.py --steps 3 --catalog lognormal

@@ -29,6 +29,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 import baorec_oracle as O  # noqa: E402
 import catalog_oracle as CO  # noqa: E402
+import pk_oracle as PK  # noqa: E402
 from util import clustered_box, lightcone  # noqa: E402
 
 PARAMS = dict(bias=2.2, f=0.757, smoothing_radius=15.0)
@@ -160,6 +161,26 @@ def catalog_case(n, seed):
                 fkp=CO.fkp_weights(nz, np.float32(5e3)), wrap_box_size=box[0], wrap_box_min=box[1], wx=wx, wy=wy, wz=wz, **dens)
 
 
+def pk_case(shape_xyz, L, N, seed):
+    """Power-spectrum multipoles (oracle/pk_oracle.py) of a CIC density mesh: the mesh itself is the input."""
+    nx, ny, nz = shape_xyz
+    bs = np.asarray(L, np.float32)
+    rng = np.random.default_rng(seed)
+    centres = rng.random((40, 3))
+    p = (centres[rng.integers(0, 40, N)] + 0.05 * rng.standard_normal((N, 3))) % 1.0
+    pos = [np.minimum((bs[a] * p[:, a]).astype(np.float32), np.nextafter(bs[a], np.float32(0))) for a in range(3)]
+    w = (0.5 + rng.random(N)).astype(np.float32)
+    rho = O.cic_scatter(np.zeros((nz, ny, nx), np.float32), *pos, w, bs, np.zeros(3, np.float32), True)
+    los = np.float32([0.2, -0.4, 0.9])
+    shot = float(np.prod(bs.astype(np.float64))) * float((w.astype(np.float64) ** 2).sum()) / float(w.sum(dtype=np.float64)) ** 2
+    out = dict(rho=rho, box_size=bs, los=los, kmin=np.float64(0.004), dk=np.float64(0.011), nbins=np.int64(30), shot=np.float64(shot))
+    for power, tag in ((2, "cic"), (0, "raw")):
+        r = PK.power_multipoles(rho, bs, los=los, kmin=0.004, dk=0.011, nbins=30, mas_power=power, shot=shot)
+        for k, v in r.items():
+            out[f"{tag}_{k}"] = np.asarray(v, np.float64)
+    return out
+
+
 CASES = {
     "iterative_box_32": lambda: box_case("iterative", 32, 431.7, 6000, (0.0, 0.0, 1.0), 101),
     "multigrid_box_32": lambda: box_case("multigrid", 32, 431.7, 6000, (0.0, 0.0, 1.0), 102),
@@ -168,12 +189,17 @@ CASES = {
     "mas_24": lambda: mas_case(24, 300.0, 5000, 105),
     "multigrid_ops_32": lambda: multigrid_ops_case(32, 500.0, 106),
     "catalog_4000": lambda: catalog_case(4000, 107),
+    "pk_40": lambda: pk_case((40, 36, 44), (400.0, 360.0, 440.0), 50000, 108),
 }
 
 
 def main():
-    manifest = {}
+    only = sys.argv[1:]                      # `make_golden.py pk_40` regenerates one fixture and keeps the others' entries
+    mf = HERE / "MANIFEST.json"
+    manifest = json.loads(mf.read_text()) if (only and mf.exists()) else {}
     for name, fn in CASES.items():
+        if only and name not in only:
+            continue
         data = fn()
         path = HERE / f"{name}.npz"
         np.savez_compressed(path, **data)

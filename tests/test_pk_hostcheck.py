@@ -98,3 +98,16 @@ def test_plane_wave_through_the_device_arithmetic(HC):
     r = device_estimate(HC, rho, np.full(3, L, f32), (0.0, 0.0, 1.0), 0.5 * kf, kf, 8, 0, 0.0)
     assert np.isclose(r["p0"][m - 1], L ** 3 * A * A / 4 * 2 / r["nmodes"][m - 1], rtol=1e-5)
     assert np.isclose(r["p2"][m - 1] / r["p0"][m - 1], -2.5, rtol=1e-6)
+
+
+def test_device_arithmetic_against_the_golden_fixture(HC):
+    """No oracle run: the committed fixture tests/golden/pk_40.npz (anisotropic 40 x 36 x 44 mesh, oblique line of sight)."""
+    with np.load(ROOT / "tests" / "golden" / "pk_40.npz") as zf:
+        g = {k: zf[k] for k in zf.files}
+    for power, tag in ((2, "cic"), (0, "raw")):
+        got = device_estimate(HC, g["rho"], g["box_size"], g["los"], float(g["kmin"]), float(g["dk"]), int(g["nbins"]), power, float(g["shot"]))
+        assert np.array_equal(got["nmodes"], g[f"{tag}_nmodes"])
+        ok = got["nmodes"] > 0
+        scale = np.abs(g[f"{tag}_p0"][ok] + float(g["shot"])).max()
+        for key in ("p0", "p2", "p4"):
+            assert np.abs(got[key][ok] - g[f"{tag}_{key}"][ok]).max() < 2e-6 * scale
