@@ -132,11 +132,12 @@ def wrap_positions(pos_x, pos_y, pos_z, box_size, box_min=(0.0, 0.0, 0.0)):
 
 
 def power_multipoles(rho, box_size, los=(0.0, 0.0, 1.0), kmin=0.0, dk=None, nbins=None, mas="cic", shot=0.0,
-                     box_min=(0.0, 0.0, 0.0)):
+                     box_min=(0.0, 0.0, 0.0), randoms=None):
     """P_0, P_2, P_4 of the density mesh `rho` (device tensor [nz][ny][nx] from `cic`; not modified) for a periodic
     box: the before / after check of test_helpers/simulation.py:56-75 (pypowspec compute_auto_box), on the device.
     mas: "cic" / "tsc" / None selects the window the estimate is compensated for; `shot` (e.g. V / N) is subtracted
-    from the monopole.  Defaults: dk = the fundamental 2 pi / max(L), bins up to the Nyquist frequency.
+    from the monopole.  `randoms`: optional density mesh of a shifted random catalog -> the spectrum of "data minus
+    shifted randoms" (compute_auto_box_rand in the reference's helpers: RecIso / RecSym).  Defaults: dk = the fundamental 2 pi / max(L), bins up to the Nyquist frequency.
     Returns dict(k, nmodes, p0, p2, p4) of numpy Float64 arrays (NaN in empty bins)."""
     from .host import _chk_mesh, _plan_for
     nx, ny, nz = _chk_mesh(rho)
@@ -146,10 +147,12 @@ def power_multipoles(rho, box_size, los=(0.0, 0.0, 1.0), kmin=0.0, dk=None, nbin
     if nbins is None:
         nbins = int((np.pi * min(nx / Lb[0], ny / Lb[1], nz / Lb[2]) - kmin) / dk)
     nbins = max(1, min(int(nbins), 1024))
+    if randoms is not None and _chk_mesh(randoms) != (nx, ny, nz):
+        raise ValueError("the randoms mesh must have the shape of the data mesh")
     ctx = _plan_for(rho, box_size, box_min)
     out = [np.empty(nbins, np.float64) for _ in range(5)]
     dp = [o.ctypes.data_as(C.POINTER(C.c_double)) for o in out]
     power = {None: 0, "none": 0, "ngp": 1, "cic": 2, "tsc": 3}[mas]
-    L.check(ctx.lib.baorec_power_multipoles_f32(ctx.handle, _ptr(rho), L.f3(np.asarray(los, np.float32)), float(kmin), float(dk),
+    L.check(ctx.lib.baorec_power_multipoles_f32(ctx.handle, _ptr(rho), _ptr(randoms) if randoms is not None else None, L.f3(np.asarray(los, np.float32)), float(kmin), float(dk),
                                                 nbins, power, float(shot), *dp, _stream()))
     return dict(k=out[0], nmodes=out[1], p0=out[2], p2=out[3], p4=out[4])

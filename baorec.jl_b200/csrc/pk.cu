@@ -2,7 +2,8 @@
 // reference makes by eye on every reconstruction (test_helpers/simulation.py:56-75, pypowspec compute_auto_box on
 // the catalogs before / after), as one R2C and ONE pass over the half mesh.
 //
-// pk_kernel: HBM-bound reduction, algorithmic bytes 8 Mc (every mode read once; the result is 5 * nbins doubles).
+// pk_kernel: HBM-bound reduction, algorithmic bytes 8 Mc (16 Mc with a randoms mesh): every mode read once; the
+// result is 5 * nbins doubles.
 // Persistent grid (a multiple of the SM count), each block walks chunks of PK_THREADS * PK_UNROLL modes of one z
 // plane with coalesced float2 loads issued back to back, bins them into a shared-memory histogram of Float64
 // sums -- after a segmented shuffle reduction over the warp's runs of equal bins (|k| is monotonic along a row, so
@@ -24,7 +25,8 @@ constexpr int PK_MAX_BINS = 1024;  // 5 * 1024 doubles = 40 KB of shared memory
 
 __global__ void __launch_bounds__(PK_THREADS)
 pk_kernel(PkGeom g, const float* __restrict__ tkx, const float* __restrict__ tky, const float* __restrict__ tkz, int ny,
-          unsigned chunks_per_plane, unsigned nchunks, const float2* __restrict__ in, double* __restrict__ acc) {
+          unsigned chunks_per_plane, unsigned nchunks, const float2* __restrict__ in, const float2* __restrict__ in2,
+          double sa, double sb, double* __restrict__ acc) {
   extern __shared__ double s_acc[];  // [5][nbins]
   const int nb = g.nbins;
   for (int t = threadIdx.x; t < 5 * nb; t += blockDim.x) s_acc[t] = 0.0;
@@ -36,11 +38,12 @@ pk_kernel(PkGeom g, const float* __restrict__ tkx, const float* __restrict__ tky
     const unsigned base = (chunk - iz * chunks_per_plane) * (PK_THREADS * PK_UNROLL) + threadIdx.x;
     const size_t off = (size_t)iz * plane;
     const float kz = __ldg(tkz + iz);
-    float2 v[PK_UNROLL];
+    float2 v[PK_UNROLL], v2[PK_UNROLL];
 #pragma unroll
     for (int u = 0; u < PK_UNROLL; u++) {
       const unsigned p = base + u * PK_THREADS;
       v[u] = p < plane ? in[off + p] : make_float2(0.f, 0.f);
+      v2[u] = (in2 != nullptr && p < plane) ? in2[off + p] : make_float2(0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < PK_UNROLL; u++) {
@@ -50,7 +53,10 @@ pk_kernel(PkGeom g, const float* __restrict__ tkx, const float* __restrict__ tky
       if (p < plane) {
         const unsigned iy = p / (unsigned)g.xh;
         const unsigned ix = p - iy * (unsigned)g.xh;
-        bin = pk_mode(g, v[u], __ldg(tkx + ix), __ldg(tky + iy), kz, (int)ix, (int)iy, (int)iz, c);
+        // field of the mode: rho_k / rho_0 (minus ran_k / ran_0: "data minus shifted randoms")
+        const double re = (double)v[u].x * sa - (double)v2[u].x * sb;
+        const double im = (double)v[u].y * sa - (double)v2[u].y * sb;
+        bin = pk_mode(g, re, im, __ldg(tkx + ix), __ldg(tky + iy), kz, (int)ix, (int)iy, (int)iz, c);
       }
       // Segmented reduction over the warp's runs of equal bins (|k| is monotonic along a row, so equal bins sit in
       // consecutive lanes): run id = number of run heads up to this lane; five shuffle steps leave the sum of each
@@ -91,7 +97,7 @@ static double inv_window2(double x, int p) {
   return 1.0 / (r * r);
 }
 
-int power_multipoles(baorec_ctx* ctx, const float* rho, const float los[3], double kmin, double dk, int nbins,
+int power_multipoles(baorec_ctx* ctx, const float* rho, const float* ran, const float los[3], double kmin, double dk, int nbins,
                      int mas_power, double shot, double* h_k, double* h_nmodes, double* h_p0, double* h_p2,
                      double* h_p4, cudaStream_t st) {
   const int n[3] = {ctx->nx, ctx->ny, ctx->nz};
@@ -117,9 +123,22 @@ int power_multipoles(baorec_ctx* ctx, const float* rho, const float los[3], doub
   double* acc = d + ntab;
   BR_CUDA(cudaMemcpyAsync(d, wt.data(), sizeof(double) * ntab, cudaMemcpyHostToDevice, st));
   BR_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 5 * nbins, st));
-  float2* ck0;
+  float2 *ck0, *ck1 = nullptr;
   BR_TRY(need_t(ctx, BUF_CK0, ctx->Mc, &ck0));
   BR_TRY(fft_r2c(ctx, rho, ck0, st));
+  float2 dc = make_float2(0.f, 0.f), dc2 = make_float2(1.f, 0.f);
+  BR_CUDA(cudaMemcpyAsync(&dc, ck0, sizeof(float2), cudaMemcpyDeviceToHost, st));
+  if (ran) {
+    BR_TRY(need_t(ctx, BUF_CK1, ctx->Mc, &ck1));
+    BR_TRY(fft_r2c(ctx, ran, ck1, st));
+    BR_CUDA(cudaMemcpyAsync(&dc2, ck1, sizeof(float2), cudaMemcpyDeviceToHost, st));
+  }
+  BR_CUDA(cudaStreamSynchronize(st));
+  if (!(dc.x != 0.f) || !(dc2.x != 0.f)) {
+    set_error("baorec_power_multipoles_f32: a mesh sums to zero (pass densities, not overdensities)");
+    return BAOREC_ERR_INVALID;
+  }
+  const double sa = 1.0 / (double)dc.x, sb = ran ? 1.0 / (double)dc2.x : 0.0;
   PkGeom g;
   g.wx = d;
   g.wy = d + len[0];
@@ -135,25 +154,18 @@ int power_multipoles(baorec_ctx* ctx, const float* rho, const float los[3], doub
   const unsigned cpp = cdiv(plane, PK_THREADS * PK_UNROLL);
   const size_t nchunks = (size_t)cpp * ctx->nz;
   BR_REQUIRE(nchunks < ((size_t)1 << 32), "mesh too large for the multipole kernel's chunk index");
-  // persistent grid: SM count x resident blocks per SM (64 registers -> 4 blocks of 256 threads)
+  // persistent grid: SM count x resident blocks per SM (76 registers -> 3 blocks of 256 threads)
   int sms = 148, occ = 1;
   BR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
   BR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pk_kernel, PK_THREADS, sizeof(double) * 5 * nbins));
   unsigned grid = (unsigned)sms * (unsigned)(occ > 0 ? occ : 1);
   if (grid > nchunks) grid = (unsigned)nchunks;
   BR_LAUNCH(ctx, pk_kernel, grid, PK_THREADS, sizeof(double) * 5 * nbins, st, g, ctx->d_k[0], ctx->d_k[1],
-            ctx->d_k[2], ctx->ny, cpp, (unsigned)nchunks, ck0, acc);
+            ctx->d_k[2], ctx->ny, cpp, (unsigned)nchunks, ck0, ck1, sa, sb, acc);
   std::vector<double> h((size_t)5 * nbins);
-  float2 dc;
   BR_CUDA(cudaMemcpyAsync(h.data(), acc, sizeof(double) * 5 * nbins, cudaMemcpyDeviceToHost, st));
-  BR_CUDA(cudaMemcpyAsync(&dc, ck0, sizeof(float2), cudaMemcpyDeviceToHost, st));
   BR_CUDA(cudaStreamSynchronize(st));
-  if (!(dc.x != 0.f)) {
-    set_error("baorec_power_multipoles_f32: the mesh sums to zero (pass the density, not the overdensity)");
-    return BAOREC_ERR_INVALID;
-  }
-  const double V = (double)ctx->L[0] * (double)ctx->L[1] * (double)ctx->L[2];
-  const double norm = V / ((double)dc.x * (double)dc.x);  // P = V |rho_k|^2 / rho_0^2 = V |delta_k|^2 / M^2
+  const double norm = (double)ctx->L[0] * (double)ctx->L[1] * (double)ctx->L[2];  // P = V |rho_k / rho_0|^2 = V |delta_k|^2 / M^2
   const double nan = ::nan("");
   for (int b = 0; b < nbins; b++) {
     const double cnt = h[b];
@@ -174,7 +186,7 @@ int power_multipoles(baorec_ctx* ctx, const float* rho, const float los[3], doub
 
 using namespace baorec;
 
-extern "C" int baorec_power_multipoles_f32(baorec_ctx* ctx, const float* d_rho, const float los[3], double kmin,
+extern "C" int baorec_power_multipoles_f32(baorec_ctx* ctx, const float* d_rho, const float* d_ran, const float los[3], double kmin,
                                            double dk, int nbins, int mas_power, double shot, double* h_k,
                                            double* h_nmodes, double* h_p0, double* h_p2, double* h_p4,
                                            baorec_stream stream) {
@@ -185,6 +197,6 @@ extern "C" int baorec_power_multipoles_f32(baorec_ctx* ctx, const float* d_rho, 
   BR_REQUIRE(dk > 0.0 && kmin >= 0.0, "kmin >= 0 and dk > 0");
   BR_REQUIRE(mas_power >= 0 && mas_power <= 4, "mas_power (window exponent) must be in 0..4");
   BR_REQUIRE(los[0] != 0.f || los[1] != 0.f || los[2] != 0.f, "line of sight is the zero vector");
-  return power_multipoles(ctx, d_rho, los, kmin, dk, nbins, mas_power, shot, h_k, h_nmodes, h_p0, h_p2, h_p4,
+  return power_multipoles(ctx, d_rho, d_ran, los, kmin, dk, nbins, mas_power, shot, h_k, h_nmodes, h_p0, h_p2, h_p4,
                           (cudaStream_t)stream);
 }

@@ -20,12 +20,13 @@ struct PkGeom {
 };
 
 // Contributions of one mode of the half mesh.  Returns the bin (or -1: k = 0 / outside the bins) and
-// c[0..4] = w, w k, w P, w P L_2(mu), w P L_4(mu)  with  P = |rho_k|^2 / W(k)^2  (unnormalised: the caller multiplies
-// by V / rho_0^2 once per bin) and w the Hermitian weight (1 on the planes kx = 0 and kx = Nyquist, else 2).
+// c[0..4] = w, w k, w P, w P L_2(mu), w P L_4(mu)  with  P = |f_k|^2 / W(k)^2  for the field value (re, im) of the mode
+// -- rho_k / rho_0, minus ran_k / ran_0 when a randoms mesh is given; the caller multiplies by V once per bin --
+// and w the Hermitian weight (1 on the planes kx = 0 and kx = Nyquist, else 2).
 // Everything in Float64 from the Float32 k tables of the context (src/utils.jl:3-10): the bin index is then
 // identical to the oracle's, value for value.
-__device__ __forceinline__ int pk_mode(const PkGeom& g, float2 v, float kx, float ky, float kz, int ix, int iy, int iz,
-                                       double c[5]) {
+__device__ __forceinline__ int pk_mode(const PkGeom& g, double re, double im, float kx, float ky, float kz, int ix, int iy,
+                                       int iz, double c[5]) {
   const double x = (double)kx, y = (double)ky, z = (double)kz;
   const double k2 = x * x + y * y + z * z;
   if (!(k2 > 0.0)) return -1;
@@ -35,7 +36,7 @@ __device__ __forceinline__ int pk_mode(const PkGeom& g, float2 v, float kx, floa
   const double mu = (x * g.los[0] + y * g.los[1] + z * g.los[2]) / k;
   const double mu2 = mu * mu;
   const double iw2 = __ldg(g.wx + ix) * __ldg(g.wy + iy) * __ldg(g.wz + iz);
-  const double p = ((double)v.x * (double)v.x + (double)v.y * (double)v.y) * iw2;
+  const double p = (re * re + im * im) * iw2;
   const double w = (ix == 0 || ix == g.nyq_x) ? 1.0 : 2.0;
   const double wp = w * p;
   c[0] = w;

@@ -353,13 +353,15 @@ function wrap_positions!(x::CuVector{Float32}, y::CuVector{Float32}, z::CuVector
 end
 
 # P_0, P_2, P_4 of a density mesh (periodic box): the before / after check of test_helpers/simulation.py:56-75
-# (pypowspec compute_auto_box) on the device.  mas_power: 2 = CIC window, 3 = TSC, 0 = none.
-function power_multipoles(rho::CuArray{Float32,3}, los = (0f0, 0f0, 1f0); kmin = 0.0, dk, nbins::Integer, mas_power::Integer = 2, shot = 0.0)
+# (pypowspec compute_auto_box; with `randoms`, the mesh of a shifted random catalog: compute_auto_box_rand) on the device.
+# mas_power: 2 = CIC window, 3 = TSC, 0 = none.
+function power_multipoles(rho::CuArray{Float32,3}, los = (0f0, 0f0, 1f0); kmin = 0.0, dk, nbins::Integer, mas_power::Integer = 2, shot = 0.0,
+                          randoms::Union{CuArray{Float32,3},Nothing} = nothing)
     k, nmodes, p0, p2, p4 = (Vector{Float64}(undef, nbins) for _ in 1:5)
     check(ccall((:baorec_power_multipoles_f32, libbaorec), Cint,
-                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cfloat}, Cdouble, Cdouble, Cint, Cint, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble},
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cfloat}, Cdouble, Cdouble, Cint, Cint, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble},
                  Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cvoid}),
-                context(), ptr(rho), f3(los), kmin, dk, nbins, mas_power, shot, k, nmodes, p0, p2, p4, stream()))
+                context(), ptr(rho), randoms === nothing ? C_NULL : ptr(randoms), f3(los), kmin, dk, nbins, mas_power, shot, k, nmodes, p0, p2, p4, stream()))
     (k = k, nmodes = nmodes, p0 = p0, p2 = p2, p4 = p4)
 end
 

@@ -114,7 +114,7 @@ SIGNATURES = {
     "baorec_cartesian_to_sky_f32": [_vp, _vp, _vp, _vp, _i64, _f, _vp, _vp, _vp, _vp],
     "baorec_fkp_weights_f32": [_vp, _vp, _i64, _f, _vp, _vp],
     "baorec_wrap_positions_f32": [_vp, _vp, _vp, _vp, _i64, _f3, _f3, _vp],
-    "baorec_power_multipoles_f32": [_vp, _vp, _f3, C.c_double, C.c_double, _i, _i, C.c_double] + [C.POINTER(C.c_double)] * 5 + [_vp],
+    "baorec_power_multipoles_f32": [_vp, _vp, _vp, _f3, C.c_double, C.c_double, _i, _i, C.c_double] + [C.POINTER(C.c_double)] * 5 + [_vp],
     "baorec_host_alloc": [C.POINTER(_vp), _i64],
     "baorec_host_free": [_vp],
 }

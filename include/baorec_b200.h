@@ -345,14 +345,16 @@ int baorec_wrap_positions_f32(baorec_ctx* ctx, float* d_x, float* d_y, float* d_
 /* Power-spectrum multipoles of a density mesh (periodic box): what the reference checks by eye on every
  * reconstruction, through the third-party pypowspec (test_helpers/simulation.py:56-75, pyrecon_simulation.py:70-86:
  * compute_auto_box on the catalogs before / after, line of sight along z, l = 0, 2, 4, linear bins).
- *   d_rho: density mesh from baorec_cic_f32 on this context's grid (any normalisation; not modified);
+ *   d_rho: density mesh from baorec_cic_scatter_f32 on this context's grid (any normalisation; not modified);
+ *   d_ran: NULL, or the density mesh of a (shifted) random catalog: the field is then rho/sum(rho) - ran/sum(ran),
+ *          "data minus shifted randoms" (compute_auto_box_rand, test_helpers/simulation.py:52-70: RecIso / RecSym);
  *   P(k) = V |rho_k|^2 / rho_0^2 / W(k)^2, W = prod_a sinc(k_a h_a / 2)^mas_power (2 = CIC, 3 = TSC, 0 = none);
  *   P_l(bin i) = (2l+1) <P L_l(mu)> over the modes with kmin + i dk <= |k| < kmin + (i+1) dk, mu = k.los/|k|,
  *   every mode of the Hermitian mesh counted once, k = 0 excluded; `shot` is subtracted from the monopole.
- * One R2C + one pass over the half mesh (Float64 sums).  Outputs are HOST arrays of nbins doubles (mean k of the
+ * One R2C per mesh + one pass over the half mesh (Float64 sums).  Outputs are HOST arrays of nbins doubles (mean k of the
  * bin, number of modes, P_0, P_2, P_4; NaN where a bin is empty).  nbins <= 1024.  Synchronises `stream`. */
-int baorec_power_multipoles_f32(baorec_ctx* ctx, const float* d_rho, const float los[3], double kmin, double dk,
-                                int nbins, int mas_power, double shot, double* h_k, double* h_nmodes, double* h_p0,
+int baorec_power_multipoles_f32(baorec_ctx* ctx, const float* d_rho, const float* d_ran, const float los[3], double kmin,
+                                double dk, int nbins, int mas_power, double shot, double* h_k, double* h_nmodes, double* h_p0,
                                 double* h_p2, double* h_p4, baorec_stream stream);
 
 /* Pinned host memory helpers for callers without their own (Julia: CUDA.Mem.alloc(HostBuffer)). */

@@ -55,9 +55,11 @@ def mode_table(shape_zyx, box_size, los, mas_power=2):
     return k, mu, W, wt
 
 
-def power_multipoles(rho, box_size, los=(0.0, 0.0, 1.0), kmin=0.0, dk=None, nbins=None, mas_power=2, shot=0.0):
+def power_multipoles(rho, box_size, los=(0.0, 0.0, 1.0), kmin=0.0, dk=None, nbins=None, mas_power=2, shot=0.0, randoms=None):
     """Multipoles l = 0, 2, 4 of the density mesh `rho` ([nz][ny][nx], any normalisation; Float32 or Float64).
-    Returns dict(k=<mean k per bin>, nmodes, p0, p2, p4); empty bins hold NaN."""
+    `randoms`: optional density mesh of a (shifted) random catalog: the field is then rho / sum(rho) - ran / sum(ran),
+    the "data minus shifted randoms" estimate of a reconstructed catalog (test_helpers/simulation.py:52-70,
+    compute_auto_box_rand).  Returns dict(k=<mean k per bin>, nmodes, p0, p2, p4); empty bins hold NaN."""
     rho = np.asarray(rho)
     nz, ny, nx = rho.shape
     L = np.asarray(box_size, np.float64)
@@ -67,9 +69,14 @@ def power_multipoles(rho, box_size, los=(0.0, 0.0, 1.0), kmin=0.0, dk=None, nbin
         nbins = int((np.pi * min(nx / L[0], ny / L[1], nz / L[2]) - kmin) / dk)
     rk = scipy.fft.rfftn(rho, workers=-1)
     a0 = float(rk[0, 0, 0].real)
+    re, im = rk.real.astype(np.float64) * (1.0 / a0), rk.imag.astype(np.float64) * (1.0 / a0)
+    if randoms is not None:
+        sk = scipy.fft.rfftn(np.asarray(randoms), workers=-1)
+        b0 = float(sk[0, 0, 0].real)
+        re, im = re - sk.real.astype(np.float64) * (1.0 / b0), im - sk.imag.astype(np.float64) * (1.0 / b0)
     k, mu, W, wt = mode_table(rho.shape, box_size, los, mas_power)
     V = float(L.prod())
-    p = (rk.real.astype(np.float64) ** 2 + rk.imag.astype(np.float64) ** 2) * (V / (a0 * a0)) / (W * W)
+    p = (re * re + im * im) * V / (W * W)
     b = np.floor((k - kmin) * (1.0 / dk)).astype(np.int64)     # 1/dk rounded once, like the device kernel
     ok = (b >= 0) & (b < nbins) & (wt > 0)
     b, w = b[ok], wt[ok]

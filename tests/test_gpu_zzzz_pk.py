@@ -43,7 +43,16 @@ def test_power_multipoles_match_the_oracle(B, O, shape, L, los, mas):
         for key in ("p0", "p2", "p4"):
             assert np.abs(got[key][ok] - ref[key][ok]).max() <= 1e-5 * scale
         assert np.all(np.isnan(got["p0"][~ok]))
-    assert torch.equal(rho, before)                                       # the mesh is an input
+    ran = torch.zeros((nz, ny, nx), dtype=torch.float32, device="cuda")
+    rp = [(bs[a] * rng.random(N)).astype(f32) for a in range(3)]
+    B.cic(ran, *(dev(p) for p in rp), dev(np.ones(N, f32)), bs, bm, wrap=True, mas=mas or "cic")
+    ref = PK.power_multipoles(hrho, bs, los=los, kmin=0.0, dk=kf, nbins=20, mas_power=power, shot=shot, randoms=ran.cpu().numpy())
+    got = B.power_multipoles(rho, bs, los=los, kmin=0.0, dk=kf, nbins=20, mas=mas, shot=shot, randoms=ran)
+    ok = ref["nmodes"] > 0
+    assert np.array_equal(got["nmodes"], ref["nmodes"])
+    for key in ("p0", "p2", "p4"):
+        assert np.abs(got[key][ok] - ref[key][ok]).max() <= 1e-5 * float(np.abs(ref["p0"][ok] + shot).max())
+    assert torch.equal(rho, before)                                       # the meshes are inputs
 
 
 def test_power_multipoles_match_the_golden_fixture(B):
@@ -92,10 +101,21 @@ def test_reconstruction_removes_the_kaiser_quadrupole_on_the_device(B, algorithm
     real, _ = Cat.lognormal_box(N, L, seed=5, device="cuda", n_gen=128, sigma=0.8, f_rsd=0.0)
     bs, bm = np.full(3, L, f32), np.zeros(3, f32)
 
-    def multipoles(p):
+    NR = 2 * N
+    g = torch.Generator(device="cuda").manual_seed(9)
+    top = float(np.nextafter(f32(L), f32(0)))
+    ran = [(torch.rand(NR, device="cuda", generator=g) * L).clamp_(max=top) for _ in range(3)]
+    wr = torch.ones(NR, device="cuda")
+
+    def mesh(p, ww):
         rho = torch.zeros((n, n, n), dtype=torch.float32, device="cuda")
-        B.cic(rho, *[q.clone() for q in p], w, bs, bm, wrap=True)
-        return B.power_multipoles(rho, bs, los=(0.0, 0.0, 1.0), kmin=0.0, dk=0.02, nbins=4, mas="cic", shot=L ** 3 / N)
+        B.cic(rho, *[q.clone() for q in p], ww, bs, bm, wrap=True)
+        return rho
+
+    def multipoles(p, r=None):
+        shot = L ** 3 / N * (1 + (N / NR if r is not None else 0))
+        return B.power_multipoles(mesh(p, w), bs, los=(0.0, 0.0, 1.0), kmin=0.0, dk=0.02, nbins=4, mas="cic", shot=shot,
+                                  randoms=None if r is None else mesh(r, wr))
 
     r_real, r_red = multipoles(real), multipoles(red)
     b = 1                                                    # 0.02 <= k < 0.04 h/Mpc: ~8000 modes
@@ -112,3 +132,15 @@ def test_reconstruction_removes_the_kaiser_quadrupole_on_the_device(B, algorithm
     r_new = multipoles(new)
     assert abs(r_new["p2"][b] / r_new["p0"][b] - q_real) < 0.12
     assert abs(r_new["p0"][b] / r_real["p0"][b] - 1) < 0.15
+    # the reference's own check (test_helpers/simulation.py:48-70): data displaced with :sum, randoms with :sum ("sym":
+    # the redshift-space clustering is kept on large scales) or :disp ("iso": the real-space one comes back)
+    def moved(cat, field):
+        out = list(B.reconstructed_positions(rec, *cat, field=field))
+        B.wrap_positions(*out, bs, bm)
+        return out
+
+    d_sum = moved(pos, "sum")
+    sym, iso = multipoles(d_sum, moved(ran, "sum")), multipoles(d_sum, moved(ran, "disp"))
+    q = lambda r: r["p2"][b] / r["p0"][b]
+    assert abs(sym["p0"][b] / r_red["p0"][b] - 1) < 0.05 and abs(q(sym) - q_red) < 0.05
+    assert abs(iso["p0"][b] / r_real["p0"][b] - 1) < 0.1 and abs(q(iso) - q_real) < 0.12

@@ -31,15 +31,18 @@ def HC():
         subprocess.run([gxx, "-O2", "-ffp-contract=off", "-Wno-unknown-pragmas", "-shared", "-fPIC", "-o", str(out), str(src)], check=True)
     lib = C.CDLL(str(out))
     lib.hc_pk.restype = C.c_int64
-    lib.hc_pk.argtypes = [_F, _F, _F, _F, C.c_int, C.c_int, C.c_int, _D, _D, _D, _D, C.c_double, C.c_double, C.c_int, _D]
+    lib.hc_pk.argtypes = [_F, _F, C.c_double, C.c_double, _F, _F, _F, C.c_int, C.c_int, C.c_int, _D, _D, _D, _D, C.c_double, C.c_double, C.c_int, _D]
     return lib
 
 
-def device_estimate(HC, rho, bs, los, kmin, dk, nbins, power, shot):
+def device_estimate(HC, rho, bs, los, kmin, dk, nbins, power, shot, randoms=None):
     """csrc/pk.cu with the kernel's mode loop on the CPU: R2C (complex64, like cuFFT), window tables from the
     context's k tables, pk_mode per mode, then the host-side finish."""
     nz, ny, nx = rho.shape
     rk = np.ascontiguousarray(scipy.fft.rfftn(rho.astype(f32)).astype(np.complex64))
+    sk = None if randoms is None else np.ascontiguousarray(scipy.fft.rfftn(randoms.astype(f32)).astype(np.complex64))
+    sa = 1.0 / float(rk[0, 0, 0].real)
+    sb = 0.0 if sk is None else 1.0 / float(sk[0, 0, 0].real)
     kv = [np.ascontiguousarray(k, f32) for k in O.k_vec((nx, ny, nz), bs, f32)]
     h = np.asarray(bs, f32).astype(np.float64) / np.array([nx, ny, nz], np.float64)
 
@@ -56,11 +59,10 @@ def device_estimate(HC, rho, bs, los, kmin, dk, nbins, power, shot):
     lv = np.ascontiguousarray(lv / np.sqrt((lv * lv).sum()))
     acc = np.zeros(5 * nbins, np.float64)
     fp, dp = (lambda a: a.ctypes.data_as(_F)), (lambda a: a.ctypes.data_as(_D))
-    HC.hc_pk(fp(rk.view(f32)), fp(kv[0]), fp(kv[1]), fp(kv[2]), nx, ny, nz, dp(wt[0]), dp(wt[1]), dp(wt[2]), dp(lv),
+    HC.hc_pk(fp(rk.view(f32)), None if sk is None else fp(sk.view(f32)), sa, sb, fp(kv[0]), fp(kv[1]), fp(kv[2]), nx, ny, nz, dp(wt[0]), dp(wt[1]), dp(wt[2]), dp(lv),
              float(kmin), float(dk), nbins, dp(acc))
     acc = acc.reshape(5, nbins)
-    a0 = float(rk[0, 0, 0].real)
-    norm = float(np.prod(np.asarray(bs, f32).astype(np.float64))) / (a0 * a0)
+    norm = float(np.prod(np.asarray(bs, f32).astype(np.float64)))
     with np.errstate(invalid="ignore", divide="ignore"):
         cnt = acc[0]
         return dict(nmodes=cnt, k=acc[1] / cnt, p0=acc[2] / cnt * norm - shot, p2=5 * acc[3] / cnt * norm, p4=9 * acc[4] / cnt * norm)
@@ -111,3 +113,22 @@ def test_device_arithmetic_against_the_golden_fixture(HC):
         scale = np.abs(g[f"{tag}_p0"][ok] + float(g["shot"])).max()
         for key in ("p0", "p2", "p4"):
             assert np.abs(got[key][ok] - g[f"{tag}_{key}"][ok]).max() < 2e-6 * scale
+
+
+def test_data_minus_shifted_randoms(HC):
+    """The second mesh of the estimator (compute_auto_box_rand of the reference's helpers)."""
+    n, L = 32, 400.0
+    bs = np.full(3, L, f32)
+    pos, w = clustered_box(80_000, L, seed=4)
+    rng = np.random.default_rng(5)
+    ran = [(L * rng.random(200_000)).astype(f32) for _ in range(3)]
+    rho = O.cic_scatter(np.zeros((n, n, n), f32), *pos, w, bs, np.zeros(3, f32), True)
+    rmesh = O.cic_scatter(np.zeros((n, n, n), f32), *ran, np.ones(200_000, f32), bs, np.zeros(3, f32), True)
+    ref = PK.power_multipoles(rho, bs, los=(0.0, 0.6, 0.8), kmin=0.0, dk=0.02, nbins=12, mas_power=2, shot=3.0, randoms=rmesh)
+    got = device_estimate(HC, rho, bs, (0.0, 0.6, 0.8), 0.0, 0.02, 12, 2, 3.0, randoms=rmesh)
+    assert np.array_equal(got["nmodes"], ref["nmodes"])
+    ok = ref["nmodes"] > 0
+    for key in ("p0", "p2", "p4"):
+        assert np.abs(got[key][ok] - ref[key][ok]).max() <= 2e-6 * np.abs(ref["p0"][ok]).max()
+    plain = PK.power_multipoles(rho, bs, los=(0.0, 0.6, 0.8), kmin=0.0, dk=0.02, nbins=12, mas_power=2, shot=3.0)
+    assert np.abs(ref["p0"][ok] - plain["p0"][ok]).max() > 1e-3 * np.abs(plain["p0"][ok]).max()      # the randoms do enter

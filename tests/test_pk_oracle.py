@@ -104,3 +104,46 @@ def test_reconstruction_removes_the_kaiser_quadrupole(F, algorithm):
     both = F.reconstructed_positions(rec, *red, mesh, field="sum")
     both = [np.clip(np.mod(q, f32(L)), 0, top).astype(f32) for q in both]
     assert multipoles(both)["p0"][b] < 0.2 * r_real["p0"][b]     # measured: ~0 (k R << 1: the smoothed field is the field)
+
+
+@pytest.mark.parametrize("algorithm", ["iterative", "multigrid"])
+def test_rec_sym_keeps_and_rec_iso_removes_the_kaiser_boost(F, algorithm):
+    """The reference's own post-reconstruction check (test_helpers/simulation.py:48-70): data displaced with
+    field = :sum, randoms displaced with :sum ("sym") or :disp ("iso"), power spectrum of data minus shifted randoms.
+    Linear theory: RecSym keeps the redshift-space clustering on large scales (Kaiser boost and quadrupole unchanged),
+    RecIso returns the real-space one (no quadrupole).  Exercises read_shifts on a second catalog and the sign of Psi:
+    with the wrong sign the shifted data and the shifted randoms do not cancel and the large-scale power is lost."""
+    import catalogs as Cat
+    L, n, N, f, R = 1000.0, 64, 2_000_000, 0.757, 10.0
+    red, w = Cat.lognormal_box(N, L, seed=5, n_gen=64, sigma=0.8, f_rsd=f)
+    real, _ = Cat.lognormal_box(N, L, seed=5, n_gen=64, sigma=0.8, f_rsd=0.0)
+    red, real, w = [p.numpy() for p in red], [p.numpy() for p in real], w.numpy()
+    bs, bm = np.full(3, L, f32), np.zeros(3, f32)
+    rng = np.random.default_rng(9)
+    NR = 4 * N
+    ran, wr = [(L * rng.random(NR)).astype(f32) for _ in range(3)], np.ones(NR, f32)
+    top = np.nextafter(f32(L), f32(0))
+
+    def wrap(ps):
+        return [np.clip(np.mod(q, f32(L)), 0, top).astype(f32) for q in ps]
+
+    def mesh(p, ww):
+        return F.cic_scatter(np.zeros((n, n, n), f32), *[q.copy() for q in p], ww, bs, bm, True)
+
+    def multipoles(p, r=None):
+        shot = L ** 3 / N * (1 + (N / NR if r is not None else 0))
+        return PK.power_multipoles(mesh(p, w), bs, los=(0, 0, 1), kmin=0.0, dk=0.02, nbins=4, mas_power=2, shot=shot,
+                                   randoms=None if r is None else mesh(r, wr))
+
+    b = 1
+    r_real, r_red = multipoles(real), multipoles(red)
+    assert abs(multipoles(red, ran)["p0"][b] / r_red["p0"][b] - 1) < 0.03      # unshifted randoms carry no signal
+    kw = dict(bias=1.0, f=f, smoothing_radius=R, box_size=bs, box_min=bm, los=(0.0, 0.0, 1.0))
+    rec = F.IterativeRecon(n_iter=3, **kw) if algorithm == "iterative" else F.MultigridRecon(**kw)
+    m = F.run(rec, (n, n, n), *[q.copy() for q in red], w)
+    d_sum = wrap(F.reconstructed_positions(rec, *red, m, field="sum"))
+    sym = multipoles(d_sum, wrap(F.reconstructed_positions(rec, *ran, m, field="sum")))
+    iso = multipoles(d_sum, wrap(F.reconstructed_positions(rec, *ran, m, field="disp")))
+    q = lambda r: r["p2"][b] / r["p0"][b]
+    assert abs(sym["p0"][b] / r_red["p0"][b] - 1) < 0.05 and abs(q(sym) - q(r_red)) < 0.05     # measured: 0.995, +0.010
+    assert abs(iso["p0"][b] / r_real["p0"][b] - 1) < 0.1 and abs(q(iso) - q(r_real)) < 0.12    # measured: 0.958, -0.083
