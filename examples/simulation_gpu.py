@@ -31,12 +31,16 @@ def timed(label, fn):
     return out
 
 
-def multipoles(label, pos, w, grid_size, box_size, box_min):
-    """P_0 / P_2 of a catalog -- what test_helpers/simulation.py:56-75 plots with pypowspec, here on the device."""
-    rho = torch.zeros(grid_size[::-1], dtype=torch.float32, device="cuda")
-    BAOrec.cic(rho, *[p.clone() for p in pos], w, box_size, box_min, wrap=True)
-    pk = BAOrec.power_multipoles(rho, box_size, los=(0.0, 0.0, 1.0), kmin=0.0, dk=0.01, nbins=10, mas="cic",
-                                 shot=float(np.prod(box_size)) / len(w))
+def multipoles(label, pos, w, grid_size, box_size, box_min, randoms=None):
+    """P_0 / P_2 of a catalog (minus shifted randoms) -- what test_helpers/simulation.py:36-70 plots with pypowspec
+    (compute_auto_box / compute_auto_box_rand), here on the device."""
+    def mesh(cat, ww):
+        rho = torch.zeros(grid_size[::-1], dtype=torch.float32, device="cuda")
+        BAOrec.cic(rho, *[p.clone() for p in cat], ww, box_size, box_min, wrap=True)
+        return rho
+    shot = float(np.prod(box_size)) / len(w) * (1 + (len(w) / len(randoms[0]) if randoms is not None else 0))
+    pk = BAOrec.power_multipoles(mesh(pos, w), box_size, los=(0.0, 0.0, 1.0), kmin=0.0, dk=0.01, nbins=10, mas="cic", shot=shot,
+                                 randoms=None if randoms is None else mesh(randoms, torch.ones_like(randoms[0])))
     print(f"{label}: k = {np.round(pk['k'][1:6], 3)}  P0 = {np.round(pk['p0'][1:6], 0)}  P2/P0 = {np.round(pk['p2'][1:6] / pk['p0'][1:6], 2)}")
 
 
@@ -58,7 +62,7 @@ def main():
         data_cat_pos, _ = catalogs.lognormal_box(int(args.particles), 1000.0, seed=42, device="cuda", n_gen=256, f_rsd=0.757)
     data_cat_w = torch.zeros_like(data_cat_pos[0]) + 1
 
-    multipoles("pre-recon data", data_cat_pos, data_cat_w, grid_size, box_size, box_min)
+    multipoles("Pre", data_cat_pos, data_cat_w, grid_size, box_size, box_min)
     for name, cls, extra in (("iterative", BAOrec.IterativeRecon, dict(n_iter=3)), ("multigrid", BAOrec.MultigridRecon, {})):
         recon = cls(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=box_size, box_min=box_min, los=los, **extra)
         print(f"Run {name}")
@@ -71,7 +75,8 @@ def main():
         # the reference's helper scripts re-wrap before measuring P(k) (test_helpers/simulation.py:51-52); here on the device
         for cat in (new_pos, new_rand_sym, new_rand_iso):
             BAOrec.wrap_positions(*cat, box_size, box_min)
-        multipoles(f"{name}: reconstructed data", new_pos, data_cat_w, grid_size, box_size, box_min)
+        multipoles(f"{name}: Iso", new_pos, data_cat_w, grid_size, box_size, box_min, randoms=new_rand_iso)
+        multipoles(f"{name}: Sym", new_pos, data_cat_w, grid_size, box_size, box_min, randoms=new_rand_sym)
         if args.out:
             out = Path(args.out)
             out.mkdir(parents=True, exist_ok=True)
