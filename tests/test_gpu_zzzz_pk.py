@@ -144,3 +144,40 @@ def test_reconstruction_removes_the_kaiser_quadrupole_on_the_device(B, algorithm
     q = lambda r: r["p2"][b] / r["p0"][b]
     assert abs(sym["p0"][b] / r_red["p0"][b] - 1) < 0.05 and abs(q(sym) - q_red) < 0.05
     assert abs(iso["p0"][b] / r_real["p0"][b] - 1) < 0.1 and abs(q(iso) - q_real) < 0.12
+
+
+@pytest.mark.parametrize("algorithm", ["iterative", "multigrid"])
+def test_lightcone_mode_removes_a_radial_kaiser_quadrupole_on_the_device(B, algorithm):
+    """tests/test_pk_oracle.py::test_lightcone_mode_removes_a_radial_kaiser_quadrupole with the product: radial line of
+    sight + randoms (setup_box, threshold mask, radial iteration / radial multigrid stencil, per-particle line of sight
+    in the epilogue), then the multipoles on the device."""
+    from util import lognormal_radial
+    L, ng, f, R = 1000.0, 64, 0.757, 10.0
+    obs = np.array([500.0, 500.0, -3000.0])
+    real, red = lognormal_radial(2_000_000, L, ng, 0.8, f, obs, 5)
+    N = len(real)
+    bs, bm, w = np.full(3, L, f32), np.zeros(3, f32), torch.ones(N, device="cuda")
+    top = np.nextafter(f32(L), f32(0))
+
+    def multipoles(a):
+        p = [dev(np.clip(np.mod(a[:, i].astype(f32), f32(L)), 0, top).astype(f32)) for i in range(3)]
+        rho = torch.zeros((ng, ng, ng), dtype=torch.float32, device="cuda")
+        B.cic(rho, *p, w, bs, bm, wrap=True)
+        return B.power_multipoles(rho, bs, los=(0.0, 0.0, 1.0), kmin=0.0, dk=0.02, nbins=4, mas="cic", shot=L ** 3 / N)
+
+    b = 1
+    q = lambda r: r["p2"][b] / r["p0"][b]
+    r_real, r_red = multipoles(real), multipoles(red)
+    assert abs(q(r_real)) < 0.1 and abs(q(r_red) - q(r_real) - 0.826) < 0.2
+    NR = 4 * N
+    ran = np.random.default_rng(11).random((NR, 3)) * L
+    cat = lambda a: [dev((a[:, i] - obs[i]).astype(f32)) for i in range(3)]
+    d, r_ = cat(red), cat(ran)
+    kw = dict(bias=1.0, f=f, smoothing_radius=R, los=None)
+    rec = B.IterativeRecon(n_iter=3, **kw) if algorithm == "iterative" else B.MultigridRecon(**kw)
+    B.run(rec, (128, 128, 128), *d, w, *r_, torch.ones(NR, device="cuda"))
+    assert np.allclose(np.asarray(rec.box_size), 1500.0, rtol=1e-3)
+    new = B.reconstructed_positions(rec, *d, field="rsd")
+    r_new = multipoles(np.stack([new[i].cpu().numpy().astype(np.float64) + obs[i] for i in range(3)], 1))
+    assert abs(q(r_new) - q(r_real)) < 0.1
+    assert abs(r_new["p0"][b] / r_real["p0"][b] - 1) < 0.1

@@ -58,3 +58,33 @@ def rel_rms(a, b):
 
 def maxabs(a, b):
     return float(np.max(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))))
+
+
+def lognormal_radial(N, L, ng, sigma, f, observer, seed):
+    """Periodic lognormal box [0, L)^3 (numpy only) with the linear redshift-space shift f (Psi . rhat) rhat seen
+    from `observer` (a point outside the box).  Returns (real-space positions, redshift-space positions), (n, 3) Float64."""
+    rng = np.random.default_rng(seed)
+    wk = np.fft.rfftn(rng.standard_normal((ng, ng, ng)))
+    kf = 2 * np.pi / L
+    kx, ky = np.fft.rfftfreq(ng, 1.0 / ng) * kf, np.fft.fftfreq(ng, 1.0 / ng) * kf
+    KX, KY, KZ = kx[None, None, :], ky[None, :, None], ky[:, None, None]
+    k2 = KX ** 2 + KY ** 2 + KZ ** 2
+    k = np.sqrt(k2)
+    pk = k / (1 + (k / 0.05) ** 2) ** 1.25
+    pk[0, 0, 0] = 0
+    dk = wk * np.sqrt(pk)
+    axes = (0, 1, 2)
+    delta = np.fft.irfftn(dk, s=(ng,) * 3, axes=axes)
+    scale = sigma / delta.std()
+    delta, dk = delta * scale, dk * scale
+    k2s = np.where(k2 > 0, k2, 1.0)
+    psi = [np.fft.irfftn(1j * K * dk / k2s, s=(ng,) * 3, axes=axes) for K in (KX, KY, KZ)]      # -div Psi = delta
+    rho = np.exp(delta - 0.5 * delta.var())
+    cells = np.repeat(np.arange(ng ** 3), rng.poisson(rho * (N / rho.sum())).ravel())
+    rng.shuffle(cells)
+    idx = (cells % ng, (cells // ng) % ng, cells // (ng * ng))
+    pos = np.stack([(i + rng.random(len(cells))) * (L / ng) for i in idx], 1)
+    P = np.stack([p.ravel()[cells] for p in psi], 1)
+    r = pos - np.asarray(observer, np.float64)[None, :]
+    rhat = r / np.linalg.norm(r, axis=1)[:, None]
+    return pos, pos + f * (P * rhat).sum(1)[:, None] * rhat
