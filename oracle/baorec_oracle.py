@@ -10,7 +10,13 @@ no golden vector whose inputs are available (test/bchmk_*.csv were produced
 from DESI mocks that are not shipped) and Julia is not installed here, so the
 reference itself cannot be run.  The oracle is instead pinned by analytic
 known-answer tests in tests/test_oracle_kat.py (plane waves, mass
-conservation, beta=0 identities, spectral-vs-finite-difference agreement).
+conservation, beta=0 identities, spectral-vs-finite-difference agreement)
+and by physics known-answer tests of whole reconstructions in
+tests/test_pk_oracle.py (the reference's own by-eye validation,
+test_helpers/simulation.py:36-70, as numbers: the Kaiser quadrupole of a
+lognormal redshift-space box is removed, RecSym keeps and RecIso removes the
+Kaiser boost, and the radial-line-of-sight + randoms mode does the same for a
+radially shifted box -- for IterativeRecon and MultigridRecon).
 
 Every function cites the reference file:line it follows (paths relative to
 /root/reference).  Array convention: a Julia `Array{T,3}` A[ix,iy,iz]
