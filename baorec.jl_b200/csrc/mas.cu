@@ -637,7 +637,12 @@ tile_reorder_kernel(const float* __restrict__ x, const float* __restrict__ y, co
 // values from shared memory.  Same arithmetic and order as gather_one -> identical results.
 constexpr int TILE_WXP = TILE_X + 4;  // padded row length in shared memory
 
-template <int NF>
+// STAGE selects how the fast path issues its cp.async rows: 0 = rows dealt round-robin over a fully unrolled loop
+// (the version measured in round 1: 1719 of its 2700 SASS instructions are integer address arithmetic, and every warp
+// steps over all 54 row predicates); 1 = each warp owns rows py = warp, warp + 4 (, 8) of every (field, plane):
+// one plane base pointer per (field, plane), one multiply-add per row, compile-time shared-memory offsets
+// (option "gather_stage", off until it has been measured).  Identical shared-memory contents either way.
+template <int NF, int STAGE>
 __global__ void __launch_bounds__(128)
 gather_tile_kernel(GatherArgs a, const float4* __restrict__ rec, const unsigned* __restrict__ starts, BoxGeom g,
                    TileGeom t) {
@@ -655,7 +660,35 @@ gather_tile_kernel(GatherArgs a, const float4* __restrict__ rec, const unsigned*
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool fast = (wx == TILE_X) && (wy == TILE_Y) && (nx % 4 == 0) &&
                     ((((uintptr_t)a.f[0] | (uintptr_t)a.f[NF > 1 ? 1 : 0] | (uintptr_t)a.f[NF > 2 ? 2 : 0]) & 15) == 0);
-  if (fast) {
+  if (fast && STAGE == 1) {
+    int xe = x0 + TILE_X;
+    if (xe >= nx) xe -= nx;
+    const int z1 = g.slab ? iz + 1 : (iz + 1 >= nz ? 0 : iz + 1);
+    int y8 = y0 + TILE_Y;  // only the last row of the window can wrap: the tile is full, so y0 + TILE_Y - 1 < ny
+    if (y8 >= ny) y8 -= ny;
+    const size_t plane_elems = (size_t)ny * nx;
+    const unsigned s_lane = (unsigned)__cvta_generic_to_shared(&sm[0][0][0][0]) + 16u * lane;
+    const unsigned s_edge = (unsigned)__cvta_generic_to_shared(&sm[0][0][0][0]) + 4u * TILE_X;
+#pragma unroll
+    for (int p = 0; p < NF * 2; p++) {  // p = field * 2 + plane
+      const int f = p >> 1;
+      const float* fld = f == 0 ? a.f[0] : (f == 1 ? a.f[NF > 1 ? 1 : 0] : a.f[NF > 2 ? 2 : 0]);
+      const float* base = fld + (size_t)((p & 1) ? z1 : iz) * plane_elems + x0;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const int py = warp + 4 * k;  // rows warp, warp + 4 and -- warp 0 only -- TILE_Y
+        if (py <= TILE_Y) {
+          const int yy = py == TILE_Y ? y8 : y0 + py;
+          const float* src = base + (size_t)yy * nx;
+          const unsigned row = (unsigned)((p * (TILE_Y + 1) + py) * TILE_WXP) * 4u;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_lane + row), "l"(src + 4 * lane));
+          if (lane == 0)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_edge + row), "l"(src - x0 + xe));
+        }
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (fast) {
     // One warp per row, rows dealt round-robin to the 4 warps with compile-time indices (no
     // integer division); each lane issues one 16-byte cp.async (LDGSTS) per row straight into
     // shared memory -- no register staging, all of a warp's rows in flight at once.
@@ -1098,18 +1131,20 @@ int gather3(baorec_ctx* ctx, const float* fx, const float* fy, const float* fz, 
       t.ntiles = b.ntiles;
       static bool carve = false;
       if (!carve) {
-        cudaFuncSetAttribute(gather_tile_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(gather_tile_kernel<3, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(gather_tile_kernel<3, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         carve = true;
       }
       if (one) {
-        BR_LAUNCH(ctx, gather_tile_kernel<1>, b.ntiles, 128, 0, st, a, b.rec, b.starts, g, t);
+        BR_LAUNCH_NAMED(ctx, "gather_tile_kernel<1>", (gather_tile_kernel<1, 0>), b.ntiles, 128, 0, st, a, b.rec, b.starts, g, t);
       } else {
         // results land in sorted order (coalesced), then one un-permute pass: the 3 x 4 B scattered
         // stores of the direct version cost three random DRAM read-modify-writes per particle
         float4* so;
         BR_TRY(need_t(ctx, BUF_BINOUT, (size_t)n, &so));
         a.sorted_out = so;
-        BR_LAUNCH(ctx, gather_tile_kernel<3>, b.ntiles, 128, 0, st, a, b.rec, b.starts, g, t);
+        if (ctx->opt_gather_stage) BR_LAUNCH_NAMED(ctx, "gather_tile_kernel<3> [stage=1]", (gather_tile_kernel<3, 1>), b.ntiles, 128, 0, st, a, b.rec, b.starts, g, t);
+        else BR_LAUNCH_NAMED(ctx, "gather_tile_kernel<3>", (gather_tile_kernel<3, 0>), b.ntiles, 128, 0, st, a, b.rec, b.starts, g, t);
         BR_LAUNCH(ctx, unsort_kernel, cdiv((size_t)n, 256), 256, 0, st, a, so, b.inv, n, b.n_valid);
         return BAOREC_OK;
       }

@@ -10,7 +10,7 @@ mkdir -p gpurun_out
 run() { local name=$1; shift; echo "== $name" | tee -a gpurun_out/r2_first.log; ( time timeout 600 "$@" ) > "gpurun_out/r2_$name.log" 2>&1; echo "   rc=$?" | tee -a gpurun_out/r2_first.log; tail -3 "gpurun_out/r2_$name.log" >> gpurun_out/r2_first.log; }
 
 # 1. the GPU tests that have never run, one file at a time
-for f in zzz_golden_catalog zzzz_pk zzzz_batch zzzz_tsc_slabs_deterministic zzz_fullsize; do
+for f in zzz_golden_catalog zzzz_gather_stage zzzz_pk zzzz_batch zzzz_tsc_slabs_deterministic zzz_fullsize; do
   run "test_$f" python -m pytest "tests/test_gpu_$f.py" -q -m gpu
 done
 # 2. everything that had passed before (regression: mas.o's TSC kernels changed for the slab layout)

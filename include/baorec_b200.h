@@ -98,6 +98,9 @@ int baorec_set_box(baorec_ctx* ctx, const float box_size[3], const float box_min
  *       smoothing, normalisation and all n_iter iterations into ONE k-space pass between one
  *       R2C and one C2R (iterate! is linear and diagonal in k for a constant LOS); 0 = run the
  *       reference's sequence of iterate! calls (2 + 2 n_iter transforms).
+ *   "gather_stage" (default 0): 1 = the tile gather issues its shared-memory staging with one base pointer per
+ *       (field, plane) and one multiply-add per row (half the instructions of the default kernel); bit-identical
+ *       results; off until it has been measured.
  *   "deterministic_scatter" (default 0): 1 = the CIC scatter (single GPU) accumulates 2^-40 fixed-point values with
  *       64-bit integer reductions and rounds to Float32 once: meshes, `ran > threshold` masks and everything after
  *       them are bit-reproducible from run to run and independent of the particle order (float reductions are not);

@@ -1,0 +1,46 @@
+"""GPU: option "gather_stage" = 1 -- the tile gather with the strength-reduced cp.async staging
+(gather_tile_kernel<3, 1>, csrc/mas.cu: each warp owns rows py = warp, warp + 4 (, 8) of every (field, plane); half the
+SASS instructions of the measured version, profiles/r1_sass_census.csv).  Same shared-memory contents, same
+arithmetic: the shifts must be bit-identical to the default kernel's.  Written after this round's GPU budget was
+spent: NOT YET RUN ON HARDWARE (file name sorts last)."""
+import numpy as np
+import pytest
+
+from util import clustered_box, maxabs
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("n,los", [(128, (0.0, 0.0, 1.0)), (256, None)])     # one / two full tiles along x; fixed and radial epilogue
+def test_staged_variant_is_bit_identical(B, O, n, los):
+    L, N = 1000.0, 400_000                                                    # >= 2^18 particles: the tile-sorted gather
+    lo = 0.0 if los is not None else 600.0
+    pos, w = clustered_box(N, L, seed=31, lo=lo)
+    kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=np.full(3, L, f32), box_min=np.full(3, lo, f32), los=los, n_iter=3)
+    ctx = B.Context.get(0)
+    d = [dev(p) for p in pos]
+    rec = B.IterativeRecon(**kw)
+    mesh = B.run(rec, (n, n, n), *d, dev(w))
+    other = [dev(p[::-1].copy()) for p in pos]                               # a second catalog: no reuse of run!'s sort
+    ref = [B.read_shifts(rec, *cat, mesh, field="sum") for cat in (d, other)]
+    k0, _ = ctx.launch_counts()
+    try:
+        ctx.set_option("gather_stage", 1)
+        got = [B.read_shifts(rec, *cat, mesh, field="sum") for cat in (d, other)]
+    finally:
+        ctx.set_option("gather_stage", 0)
+    for r, g in zip(ref, got):
+        for a in range(3):
+            assert torch.equal(r[a], g[a])
+    if n == 128 and los is not None:                                          # and the oracle agrees
+        orec = O.IterativeRecon(**kw)
+        omesh = O.run(orec, (n, n, n), *[p.copy() for p in pos], w)
+        oref = O.read_shifts(orec, *pos, omesh, "sum")
+        for a in range(3):
+            assert maxabs(got[0][a].cpu().numpy(), oref[a]) < 1e-3
