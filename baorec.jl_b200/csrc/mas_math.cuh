@@ -182,6 +182,56 @@ __device__ __forceinline__ bool deposit(float* __restrict__ rho, float px, float
   }
 }
 
+// ---- paired deposit (option "scatter_pairs") ---------------------------------------------------------------------
+// The eight cells of cic! are four rows of two x-neighbours.  When x0 is even (and the mesh row length is, and the
+// pair does not straddle the periodic wrap) the two cells of a row are one 8-byte aligned pair, and sm_90+ has a
+// vector reduction for exactly that: red.global.add.v2.f32 -- one L2 reduction instead of two.  Half of the particles
+// qualify, so a catalog issues 6 reductions per particle on average instead of 8, in a kernel that is bound by L2
+// reduction throughput.  Same cells, same Float32 values; only the grouping differs.
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+#else
+  p[0] += a;
+  p[1] += b;
+#endif
+}
+
+// cic! for one (already wrapped) particle, pairs where possible.  `rho` must be 8-byte aligned.
+__device__ __forceinline__ bool deposit_pairs(float* __restrict__ rho, float px, float py, float pz, float ww,
+                                              const BoxGeom& g, bool wrap) {
+  const size_t nx = g.n[0], ny = g.n[1];
+  int x0, x1, y0, y1, z0, z1;
+  float wx0, wx1, wy0, wy1, wz0, wz1;
+  bool ok = cic_axis(px, g.mn[0], g.L[0], g.n[0], wrap, x0, x1, wx0, wx1);
+  ok = cic_axis(py, g.mn[1], g.L[1], g.n[1], wrap, y0, y1, wy0, wy1) && ok;
+  ok = cic_axis(pz, g.mn[2], g.L[2], g.n[2], wrap, z0, z1, wz0, wz1) && ok;
+  if (!ok || !local_planes(g, z0, z1, z0, z1)) return false;
+  wx0 = __fmul_rn(wx0, ww);
+  wx1 = __fmul_rn(wx1, ww);
+  const size_t r00 = ((size_t)z0 * ny + y0) * nx, r10 = ((size_t)z0 * ny + y1) * nx;
+  const size_t r01 = ((size_t)z1 * ny + y0) * nx, r11 = ((size_t)z1 * ny + y1) * nx;
+  const float a00 = __fmul_rn(wx0, wy0), a10 = __fmul_rn(wx1, wy0), a01 = __fmul_rn(wx0, wy1), a11 = __fmul_rn(wx1, wy1);
+  const float v000 = __fmul_rn(a00, wz0), v100 = __fmul_rn(a10, wz0), v010 = __fmul_rn(a01, wz0), v110 = __fmul_rn(a11, wz0);
+  const float v001 = __fmul_rn(a00, wz1), v101 = __fmul_rn(a10, wz1), v011 = __fmul_rn(a01, wz1), v111 = __fmul_rn(a11, wz1);
+  if (((x0 | g.n[0]) & 1) == 0 && x1 == x0 + 1) {  // rows start at even offsets (nx even), x0 even: aligned pairs
+    red_add_v2(rho + r00 + x0, v000, v100);
+    red_add_v2(rho + r10 + x0, v010, v110);
+    red_add_v2(rho + r01 + x0, v001, v101);
+    red_add_v2(rho + r11 + x0, v011, v111);
+  } else {
+    atomicAdd(rho + r00 + x0, v000);
+    atomicAdd(rho + r00 + x1, v100);
+    atomicAdd(rho + r10 + x0, v010);
+    atomicAdd(rho + r01 + x0, v001);
+    atomicAdd(rho + r10 + x1, v110);
+    atomicAdd(rho + r01 + x1, v101);
+    atomicAdd(rho + r11 + x0, v011);
+    atomicAdd(rho + r11 + x1, v111);
+  }
+  return true;
+}
+
 // ---- deterministic deposit (option "deterministic_scatter") -------------------------------------------------------
 // Float additions do not commute, so a mesh accumulated with float reductions differs from run to run in the last
 // bits (and with it the cells that sit on the `ran > threshold` cut).  Integer additions do

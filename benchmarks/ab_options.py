@@ -5,7 +5,7 @@ one gpurun call answers "does option X pay off?" (ms per reconstruction + the fi
     python benchmarks/ab_options.py [--mesh 1024] [--particles 1e8] [--catalog uniform|lognormal] [--steps 5]
                                     [--set name=value ...]      # extra configurations, e.g. --set deterministic_scatter=1
 
-Default configurations: baseline; unified_sort=0; gather_tiles=0; deterministic_scatter=1; fuse_kspace=0; gather_stage=1.
+Default configurations: baseline; unified_sort=0; gather_tiles=0; deterministic_scatter=1; fuse_kspace=0; gather_stage=1; scatter_pairs=1.
 Not run on hardware yet (written after round 1's GPU budget was spent)."""
 import argparse
 import json
@@ -22,7 +22,7 @@ import __graft_entry__ as G  # noqa: E402
 import catalogs  # noqa: E402
 
 B = G.load_package()
-DEFAULTS = {"unified_sort": 1, "gather_tiles": 1, "deterministic_scatter": 0, "fuse_kspace": 1, "gather_stage": 0}
+DEFAULTS = {"unified_sort": 1, "gather_tiles": 1, "deterministic_scatter": 0, "fuse_kspace": 1, "gather_stage": 0, "scatter_pairs": 0}
 
 
 def main():

@@ -98,6 +98,9 @@ int baorec_set_box(baorec_ctx* ctx, const float box_size[3], const float box_min
  *       smoothing, normalisation and all n_iter iterations into ONE k-space pass between one
  *       R2C and one C2R (iterate! is linear and diagonal in k for a constant LOS); 0 = run the
  *       reference's sequence of iterate! calls (2 + 2 n_iter transforms).
+ *   "scatter_pairs" (default 0): 1 = the tile-ordered CIC scatter deposits the two x-neighbours of a row with one
+ *       vector reduction (red.global.add.v2.f32) when they form an aligned pair -- same cells, same values, 6 instead
+ *       of 8 L2 reductions per particle on average; off until it has been measured.
  *   "gather_stage" (default 0): 1 = the tile gather issues its shared-memory staging with one base pointer per
  *       (field, plane) and one multiply-add per row (half the instructions of the default kernel); bit-identical
  *       results; off until it has been measured.

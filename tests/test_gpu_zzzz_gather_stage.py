@@ -44,3 +44,30 @@ def test_staged_variant_is_bit_identical(B, O, n, los):
         oref = O.read_shifts(orec, *pos, omesh, "sum")
         for a in range(3):
             assert maxabs(got[0][a].cpu().numpy(), oref[a]) < 1e-3
+
+
+def test_paired_scatter_matches_the_oracle(B, O):
+    """Option "scatter_pairs" = 1: aligned x pairs of cic! through red.global.add.v2.f32 (csrc/mas_math.cuh:
+    deposit_pairs; arithmetic checked on the CPU in tests/test_mas_hostcheck.py).  Same cells and values as the default
+    kernel: the mesh differs from the oracle's serial sum only by the order of the Float32 additions."""
+    n, L, N = 128, 1000.0, 400_000
+    pos, w = clustered_box(N, L, seed=33)
+    pos[0][:50] += f32(L)                                                     # wrapped by cic!, written back
+    bs, bm = np.full(3, L, f32), np.zeros(3, f32)
+    opos = [p.copy() for p in pos]
+    ref = O.cic_scatter(np.zeros((n, n, n), f32), *opos, w, bs, bm, True)
+    ctx = B.Context.get(0)
+    meshes = []
+    for on in (0, 1):
+        try:
+            ctx.set_option("scatter_pairs", on)
+            rho = torch.zeros((n, n, n), dtype=torch.float32, device="cuda")
+            d = [dev(p) for p in pos]
+            B.cic(rho, *d, dev(w), bs, bm, wrap=True)
+        finally:
+            ctx.set_option("scatter_pairs", 0)
+        for g, o in zip(d, opos):
+            assert np.array_equal(g.cpu().numpy().view(np.uint32), o.view(np.uint32))
+        meshes.append(rho.cpu().numpy())
+        assert maxabs(meshes[-1], ref) <= 2e-6 * float(ref.max())
+    assert abs(float(meshes[1].sum(dtype=np.float64)) / float(w.sum(dtype=np.float64)) - 1) < 1e-6
