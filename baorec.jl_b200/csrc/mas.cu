@@ -501,13 +501,14 @@ scatter_records_kernel(float* __restrict__ rho, const float4* __restrict__ rec, 
 }
 
 // option "scatter_pairs": the tile-ordered scatter with vector reductions (deposit_pairs in mas_math.cuh)
+template <int MODE>
 __global__ void __launch_bounds__(256)
 scatter_records_pairs_kernel(float* __restrict__ rho, const float4* __restrict__ rec, int64_t n, BoxGeom g, int wrap,
                              unsigned long long* __restrict__ oob) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p = rec[i];
-  if (!deposit_pairs(rho, p.x, p.y, p.z, p.w, g, wrap != 0)) atomicAdd(oob, 1ULL);
+  if (!deposit_pairs<MODE>(rho, p.x, p.y, p.z, p.w, g, wrap != 0)) atomicAdd(oob, 1ULL);
 }
 
 // ---- deterministic scatter (option "deterministic_scatter"; see deposit_fixed in mas_math.cuh) -------------------
@@ -1021,8 +1022,10 @@ int scatter(baorec_ctx* ctx, float* rho, float* x, float* y, float* z, const flo
   if (use_binning(ctx, n) && ctx->opt_unified_sort && !tsc && ctx->slab_mode == 0 && ctx->opt_gather_tiles) {
     BinResult b;
     BR_TRY(unified_sort(ctx, x, y, z, w, n, wrap, st, &b));
-    if (ctx->opt_scatter_pairs && ((uintptr_t)rho & 7) == 0)
-      BR_LAUNCH(ctx, scatter_records_pairs_kernel, cdiv((size_t)n, 256), 256, 0, st, rho, b.rec, n, g, wrap, ctx->d_oob);
+    if (ctx->opt_scatter_pairs >= 2 && ((uintptr_t)rho & 15) == 0)
+      BR_LAUNCH(ctx, scatter_records_pairs_kernel<2>, cdiv((size_t)n, 256), 256, 0, st, rho, b.rec, n, g, wrap, ctx->d_oob);
+    else if (ctx->opt_scatter_pairs && ((uintptr_t)rho & 7) == 0)
+      BR_LAUNCH(ctx, scatter_records_pairs_kernel<1>, cdiv((size_t)n, 256), 256, 0, st, rho, b.rec, n, g, wrap, ctx->d_oob);
     else
       BR_LAUNCH(ctx, scatter_records_kernel, cdiv((size_t)n, 256), 256, 0, st, rho, b.rec, n, g, wrap, ctx->d_oob);
     return BAOREC_OK;

@@ -197,7 +197,22 @@ __device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
 #endif
 }
 
-// cic! for one (already wrapped) particle, pairs where possible.  `rho` must be 8-byte aligned.
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+#else
+  p[0] += a;
+  p[1] += b;
+  p[2] += c;
+  p[3] += d;
+#endif
+}
+
+// cic! for one (already wrapped) particle, pairs where possible.  `rho` must be 8-byte aligned (MODE 1) / 16-byte
+// aligned (MODE 2).  MODE 2 additionally covers x0 = 1 (mod 4), where the two cells are the middle of one aligned
+// 16-byte block: one red.global.add.v4.f32 of {0, a, b, 0} (adding +0 leaves a cell as it is) -- 5 reductions per
+// particle on average instead of 6 (MODE 1) or 8.
+template <int MODE>
 __device__ __forceinline__ bool deposit_pairs(float* __restrict__ rho, float px, float py, float pz, float ww,
                                               const BoxGeom& g, bool wrap) {
   const size_t nx = g.n[0], ny = g.n[1];
@@ -219,6 +234,11 @@ __device__ __forceinline__ bool deposit_pairs(float* __restrict__ rho, float px,
     red_add_v2(rho + r10 + x0, v010, v110);
     red_add_v2(rho + r01 + x0, v001, v101);
     red_add_v2(rho + r11 + x0, v011, v111);
+  } else if (MODE == 2 && (g.n[0] & 3) == 0 && (x0 & 3) == 1) {  // x1 = x0 + 1 < nx follows; block = cells x0-1 .. x0+2
+    red_add_v4(rho + r00 + x0 - 1, 0.f, v000, v100, 0.f);
+    red_add_v4(rho + r10 + x0 - 1, 0.f, v010, v110, 0.f);
+    red_add_v4(rho + r01 + x0 - 1, 0.f, v001, v101, 0.f);
+    red_add_v4(rho + r11 + x0 - 1, 0.f, v011, v111, 0.f);
   } else {
     atomicAdd(rho + r00 + x0, v000);
     atomicAdd(rho + r00 + x1, v100);

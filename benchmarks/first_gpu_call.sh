@@ -20,7 +20,7 @@ run bench_batch python bench.py --steps 5 --warmup 3 --e2e-batch 4
 # 3b. the secondary configs, TSC included (BASELINE configs[1] names TSC; only CIC was measured in round 1)
 run secondary python benchmarks/secondary.py c2 c2tsc c3
 # 4. option A/B on the bench workload, uniform and lognormal
-run ab_uniform python benchmarks/ab_options.py --steps 3
+run ab_uniform python benchmarks/ab_options.py --steps 3 --set scatter_pairs=2
 run ab_lognormal python benchmarks/ab_options.py --steps 3 --catalog lognormal
 # 5. ncu: launch list of one multipole estimate + catalog kernels, full capture of pk_kernel and the two conversions
 cat > /tmp/pk_probe.py <<'PY'

@@ -109,7 +109,7 @@ int64_t hc_deposit(int mas, float* buf, const float* x, const float* y, const fl
 // Option "scatter_pairs": the product's deposit_pairs (aligned x pairs through one vector reduction) for a list of
 // particles in the given order; on the host the pair is two plain additions, so the result must equal hc_deposit's
 // (every cell receives the same values in the same particle order).  Returns (rejected count, pairs used) packed.
-int64_t hc_deposit_pairs(float* buf, const float* x, const float* y, const float* z, const float* w, int64_t n, const int* ng,
+int64_t hc_deposit_pairs(int mode, float* buf, const float* x, const float* y, const float* z, const float* w, int64_t n, const int* ng,
                          const float* L, const float* mn, int wrap, int64_t* n_paired) {
   const BoxGeom g = make_geom(ng, L, mn, 0, 0, 0, ng[2]);
   int64_t bad = 0, paired = 0;
@@ -120,12 +120,12 @@ int64_t hc_deposit_pairs(float* buf, const float* x, const float* y, const float
       py = wrap_pos(py, g.mn[0], g.L[0]);
       pz = wrap_pos(pz, g.mn[0], g.L[0]);
     }
-    if (!deposit_pairs(buf, px, py, pz, w[i], g, wrap != 0)) bad++;
+    if (!(mode == 2 ? deposit_pairs<2>(buf, px, py, pz, w[i], g, wrap != 0) : deposit_pairs<1>(buf, px, py, pz, w[i], g, wrap != 0))) bad++;
     else {
       int x0, x1;
       float w0, w1;
       cic_axis(px, g.mn[0], g.L[0], g.n[0], wrap != 0, x0, x1, w0, w1);
-      if (((x0 | g.n[0]) & 1) == 0 && x1 == x0 + 1) paired++;
+      if ((((x0 | g.n[0]) & 1) == 0 && x1 == x0 + 1) || (mode == 2 && (g.n[0] & 3) == 0 && (x0 & 3) == 1)) paired++;
     }
   }
   *n_paired = paired;

@@ -47,7 +47,8 @@ def test_staged_variant_is_bit_identical(B, O, n, los):
 
 
 def test_paired_scatter_matches_the_oracle(B, O):
-    """Option "scatter_pairs" = 1: aligned x pairs of cic! through red.global.add.v2.f32 (csrc/mas_math.cuh:
+    """Option "scatter_pairs" = 1 / 2: aligned x pairs (and, 2, aligned quads {0, a, b, 0}) of cic! through
+    red.global.add.v2.f32 / .v4.f32 (csrc/mas_math.cuh:
     deposit_pairs; arithmetic checked on the CPU in tests/test_mas_hostcheck.py).  Same cells and values as the default
     kernel: the mesh differs from the oracle's serial sum only by the order of the Float32 additions."""
     n, L, N = 128, 1000.0, 400_000
@@ -58,7 +59,7 @@ def test_paired_scatter_matches_the_oracle(B, O):
     ref = O.cic_scatter(np.zeros((n, n, n), f32), *opos, w, bs, bm, True)
     ctx = B.Context.get(0)
     meshes = []
-    for on in (0, 1):
+    for on in (0, 1, 2):                                                      # scalar; aligned pairs; pairs + aligned quads
         try:
             ctx.set_option("scatter_pairs", on)
             rho = torch.zeros((n, n, n), dtype=torch.float32, device="cuda")
@@ -70,4 +71,5 @@ def test_paired_scatter_matches_the_oracle(B, O):
             assert np.array_equal(g.cpu().numpy().view(np.uint32), o.view(np.uint32))
         meshes.append(rho.cpu().numpy())
         assert maxabs(meshes[-1], ref) <= 2e-6 * float(ref.max())
-    assert abs(float(meshes[1].sum(dtype=np.float64)) / float(w.sum(dtype=np.float64)) - 1) < 1e-6
+    for m in meshes[1:]:
+        assert abs(float(m.sum(dtype=np.float64)) / float(w.sum(dtype=np.float64)) - 1) < 1e-6

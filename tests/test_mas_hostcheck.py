@@ -49,7 +49,7 @@ def HC():
     lib.hc_tsc_gather.restype = i64
     lib.hc_tsc_gather.argtypes = [_F, _F, _F, _F, i64, _I, _F, _F, i, i, i, i, _F]
     lib.hc_deposit_pairs.restype = i64
-    lib.hc_deposit_pairs.argtypes = [_F, _F, _F, _F, _F, i64, _I, _F, _F, i, C.POINTER(i64)]
+    lib.hc_deposit_pairs.argtypes = [i, _F, _F, _F, _F, _F, i64, _I, _F, _F, i, C.POINTER(i64)]
     lib.hc_deposit_fixed.restype = i64
     lib.hc_deposit_fixed.argtypes = [_F, C.POINTER(C.c_uint64), _F, _F, _F, _F, i64, _I, _F, _F, i]
     lib.hc_shifts_epilogue.restype = None
@@ -359,8 +359,9 @@ def test_deterministic_scatter_is_order_independent_and_correctly_rounded(HC, wr
     assert abs(float(a.sum(dtype=np.float64)) - float(w.sum(dtype=np.float64))) < 2e-3
 
 
-@pytest.mark.parametrize("n,wrap", [((12, 10, 16), True), ((12, 10, 16), False), ((13, 8, 8), True)])
-def test_paired_deposit_equals_the_scalar_one(HC, n, wrap):
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("n,wrap", [((12, 10, 16), True), ((12, 10, 16), False), ((13, 8, 8), True), ((14, 8, 8), True)])
+def test_paired_deposit_equals_the_scalar_one(HC, n, wrap, mode):
     """Option "scatter_pairs": the aligned x pairs of cic! through one vector reduction (red.global.add.v2.f32 on the
     device, two additions on the host).  Same cells, same values, same particle order -> the serial result is the
     reference's loop bit for bit; about half of the particles take the paired path on an even mesh, none on an odd one."""
@@ -370,10 +371,9 @@ def test_paired_deposit_equals_the_scalar_one(HC, n, wrap):
     ng = np.asarray(n, np.int32)
     M = n[0] * n[1] * n[2]
     got, paired = np.zeros(M, f32), C.c_int64(0)
-    bad = HC.hc_deposit_pairs(fp(got), fp(pos[0]), fp(pos[1]), fp(pos[2]), fp(w), len(w), ip(ng), fp(bs), fp(bm), int(wrap), C.byref(paired))
+    bad = HC.hc_deposit_pairs(mode, fp(got), fp(pos[0]), fp(pos[1]), fp(pos[2]), fp(w), len(w), ip(ng), fp(bs), fp(bm), int(wrap), C.byref(paired))
     ref = O.cic_scatter(np.zeros((n[2], n[1], n[0]), f32), *[p.copy() for p in pos], w, bs, bm, wrap)
     assert bad == 0 and np.array_equal(u32(got.reshape(ref.shape)), u32(ref))
-    if n[0] % 2 == 0:
-        assert 0.35 * len(w) < paired.value < 0.65 * len(w)
-    else:
-        assert paired.value == 0
+    # share of the particles that take a vector reduction: pairs need an even row, quads (mode 2) a row of 4 k cells
+    want = 0.0 if n[0] % 2 else (0.75 if (mode == 2 and n[0] % 4 == 0) else 0.5)
+    assert abs(paired.value / len(w) - want) < 0.1
