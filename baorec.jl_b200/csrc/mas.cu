@@ -295,6 +295,16 @@ scatter_sorted_kernel(float* __restrict__ rho, const float4* __restrict__ rec, c
   deposit<MAS>(rho, p.x, p.y, p.z, p.w, g, wrap != 0);
 }
 
+// option "scatter_pairs": the binned TSC scatter with vector reductions (deposit_tsc_vec in mas_math.cuh)
+__global__ void __launch_bounds__(256)
+scatter_sorted_tsc_vec_kernel(float* __restrict__ rho, const float4* __restrict__ rec, const unsigned* __restrict__ n_valid,
+                              BoxGeom g, int wrap) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)__ldg(n_valid)) return;
+  float4 p = rec[i];
+  deposit_tsc_vec(rho, p.x, p.y, p.z, p.w, g, wrap != 0);
+}
+
 template <int NF, int MAS>
 __global__ void __launch_bounds__(256)
 gather_sorted_kernel(GatherArgs a, const float4* __restrict__ rec, const unsigned* __restrict__ n_valid, int64_t n,
@@ -1036,7 +1046,9 @@ int scatter(baorec_ctx* ctx, float* rho, float* x, float* y, float* z, const flo
     if (ctx->opt_scatter_tiles && !tsc) BR_TRY(bin_tiles_scatter(ctx, x, y, z, w, n, wrap, st, &b));
     else BR_TRY(bin_particles<BIN_SCATTER>(ctx, x, y, z, w, n, wrap, mas, st, &b));
     unsigned grid = cdiv((size_t)n, 256);
-    if (tsc) BR_LAUNCH(ctx, scatter_sorted_kernel<BAOREC_MAS_TSC>, grid, 256, 0, st, rho, b.rec, b.n_valid, g, wrap);
+    if (tsc && ctx->opt_scatter_pairs && ((uintptr_t)rho & 15) == 0)
+      BR_LAUNCH(ctx, scatter_sorted_tsc_vec_kernel, grid, 256, 0, st, rho, b.rec, b.n_valid, g, wrap);
+    else if (tsc) BR_LAUNCH(ctx, scatter_sorted_kernel<BAOREC_MAS_TSC>, grid, 256, 0, st, rho, b.rec, b.n_valid, g, wrap);
     else BR_LAUNCH(ctx, scatter_sorted_kernel<BAOREC_MAS_CIC>, grid, 256, 0, st, rho, b.rec, b.n_valid, g, wrap);
     return BAOREC_OK;
   }

@@ -209,9 +209,10 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 }
 
 // cic! for one (already wrapped) particle, pairs where possible.  `rho` must be 8-byte aligned (MODE 1) / 16-byte
-// aligned (MODE 2).  MODE 2 additionally covers x0 = 1 (mod 4), where the two cells are the middle of one aligned
-// 16-byte block: one red.global.add.v4.f32 of {0, a, b, 0} (adding +0 leaves a cell as it is) -- 5 reductions per
-// particle on average instead of 6 (MODE 1) or 8.
+// aligned (MODE 2).  MODE 2 is branch-free: every row is ONE red.global.add.v4.f32 on the aligned 16-byte block that
+// holds x0, the two values at the pair's offset in the block and +0 in the other slots (adding +0 leaves a cell as it
+// is), plus a scalar reduction for the quarter of the particles whose pair straddles two blocks -- 5 reductions per
+// particle on average instead of 6 (MODE 1, where the warp also diverges) or 8.
 template <int MODE>
 __device__ __forceinline__ bool deposit_pairs(float* __restrict__ rho, float px, float py, float pz, float ww,
                                               const BoxGeom& g, bool wrap) {
@@ -229,16 +230,26 @@ __device__ __forceinline__ bool deposit_pairs(float* __restrict__ rho, float px,
   const float a00 = __fmul_rn(wx0, wy0), a10 = __fmul_rn(wx1, wy0), a01 = __fmul_rn(wx0, wy1), a11 = __fmul_rn(wx1, wy1);
   const float v000 = __fmul_rn(a00, wz0), v100 = __fmul_rn(a10, wz0), v010 = __fmul_rn(a01, wz0), v110 = __fmul_rn(a11, wz0);
   const float v001 = __fmul_rn(a00, wz1), v101 = __fmul_rn(a10, wz1), v011 = __fmul_rn(a01, wz1), v111 = __fmul_rn(a11, wz1);
-  if (((x0 | g.n[0]) & 1) == 0 && x1 == x0 + 1) {  // rows start at even offsets (nx even), x0 even: aligned pairs
+  if (MODE == 2 && (g.n[0] & 3) == 0) {
+    // every lane: ONE quad on the aligned block that holds x0 (the pair sits at offset o of it; +0 elsewhere), and for
+    // o = 3 -- the pair straddles two blocks, or wraps -- a scalar for the second cell: 1.25 reductions per row
+    const int o = x0 & 3;
+    const size_t xb = (size_t)(x0 - o);
+    const bool s0 = o == 0, s1 = o == 1, s2 = o == 2, s3 = o == 3;
+#define BAOREC_QUAD(row, va, vb)                                                                            \
+  red_add_v4(rho + (row) + xb, s0 ? (va) : 0.f, s0 ? (vb) : (s1 ? (va) : 0.f), s1 ? (vb) : (s2 ? (va) : 0.f), \
+             s2 ? (vb) : (s3 ? (va) : 0.f));                                                                \
+  if (s3) atomicAdd(rho + (row) + x1, (vb));
+    BAOREC_QUAD(r00, v000, v100)
+    BAOREC_QUAD(r10, v010, v110)
+    BAOREC_QUAD(r01, v001, v101)
+    BAOREC_QUAD(r11, v011, v111)
+#undef BAOREC_QUAD
+  } else if (((x0 | g.n[0]) & 1) == 0 && x1 == x0 + 1) {  // rows start at even offsets (nx even), x0 even: aligned pairs
     red_add_v2(rho + r00 + x0, v000, v100);
     red_add_v2(rho + r10 + x0, v010, v110);
     red_add_v2(rho + r01 + x0, v001, v101);
     red_add_v2(rho + r11 + x0, v011, v111);
-  } else if (MODE == 2 && (g.n[0] & 3) == 0 && (x0 & 3) == 1) {  // x1 = x0 + 1 < nx follows; block = cells x0-1 .. x0+2
-    red_add_v4(rho + r00 + x0 - 1, 0.f, v000, v100, 0.f);
-    red_add_v4(rho + r10 + x0 - 1, 0.f, v010, v110, 0.f);
-    red_add_v4(rho + r01 + x0 - 1, 0.f, v001, v101, 0.f);
-    red_add_v4(rho + r11 + x0 - 1, 0.f, v011, v111, 0.f);
   } else {
     atomicAdd(rho + r00 + x0, v000);
     atomicAdd(rho + r00 + x1, v100);
@@ -248,6 +259,59 @@ __device__ __forceinline__ bool deposit_pairs(float* __restrict__ rho, float px,
     atomicAdd(rho + r01 + x1, v101);
     atomicAdd(rho + r11 + x0, v011);
     atomicAdd(rho + r11 + x1, v111);
+  }
+  return true;
+}
+
+// TSC with vector reductions (option "scatter_pairs"): the three x-neighbours of a stencil row lie in ONE aligned
+// 16-byte block (first cell at offset 0 or 1 of the block) or in that block and the first half of the next (offset 2
+// or 3): one quad, plus one pair for half of the particles, +0 in the unused slots -- 13.5 reductions per particle
+// on average instead of 27, and two issued instructions per row instead of three.
+// Rows that touch the periodic wrap, and meshes whose row length is not a multiple of 4, use the scalar reductions.
+__device__ __forceinline__ void red_row3(float* row, int first, float v0, float v1, float v2) {
+  // branch-free: one quad on the aligned block that holds `first` (values at offset o, +0 elsewhere) and, for o >= 2,
+  // one pair on the first half of the next block
+  const int o = first & 3;
+  float* b = row + (first - o);
+  const bool s0 = o == 0, s1 = o == 1, s2 = o == 2, s3 = o == 3;
+  red_add_v4(b, s0 ? v0 : 0.f, s0 ? v1 : (s1 ? v0 : 0.f), s0 ? v2 : (s1 ? v1 : (s2 ? v0 : 0.f)),
+             s1 ? v2 : (s2 ? v1 : (s3 ? v0 : 0.f)));
+  if (o >= 2) red_add_v2(b + 4, s2 ? v2 : v1, s2 ? 0.f : v2);
+}
+
+// deposit<TSC> with vector reductions; `rho` must be 16-byte aligned.  Same cells, same Float32 values.
+__device__ __forceinline__ bool deposit_tsc_vec(float* __restrict__ rho, float px, float py, float pz, float ww,
+                                                const BoxGeom& g, bool wrap) {
+  const size_t nx = g.n[0], ny = g.n[1];
+  int ix[3], iy[3], iz[3];
+  float wx[3], wy[3], wz[3];
+  bool ok = tsc_axis(px, g.mn[0], g.L[0], g.n[0], wrap, ix, wx);
+  ok = tsc_axis(py, g.mn[1], g.L[1], g.n[1], wrap, iy, wy) && ok;
+  ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], wrap, iz, wz) && ok;
+  if (!ok) return false;
+  if (g.slab) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) ok = local_plane1(g, iz[c], iz[c]) && ok;
+    if (!ok) return false;
+  }
+  // the row is contiguous unless the stencil wraps in x; first + 2 < nx and nx = 4 k keep both pairs inside the row
+  const bool vec = (g.n[0] & 3) == 0 && ix[1] == ix[0] + 1 && ix[2] == ix[0] + 2;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+      float* row = rho + ((size_t)iz[c] * ny + iy[b]) * nx;
+      const float v0 = __fmul_rn(__fmul_rn(__fmul_rn(wx[0], ww), wy[b]), wz[c]);
+      const float v1 = __fmul_rn(__fmul_rn(__fmul_rn(wx[1], ww), wy[b]), wz[c]);
+      const float v2 = __fmul_rn(__fmul_rn(__fmul_rn(wx[2], ww), wy[b]), wz[c]);
+      if (vec) {
+        red_row3(row, ix[0], v0, v1, v2);
+      } else {
+        atomicAdd(row + ix[0], v0);
+        atomicAdd(row + ix[1], v1);
+        atomicAdd(row + ix[2], v2);
+      }
+    }
   }
   return true;
 }

@@ -100,8 +100,10 @@ int baorec_set_box(baorec_ctx* ctx, const float box_size[3], const float box_min
  *       reference's sequence of iterate! calls (2 + 2 n_iter transforms).
  *   "scatter_pairs" (default 0): 1 = the tile-ordered CIC scatter deposits the two x-neighbours of a row with one
  *       vector reduction (red.global.add.v2.f32) when they form an aligned pair -- same cells, same values, 6 instead
- *       of 8 L2 reductions per particle on average; 2 = also aligned quads {0, a, b, 0} with red.global.add.v4.f32
- *       (5 on average); off until it has been measured.
+ *       of 8 L2 reductions per particle on average; 2 = one red.global.add.v4.f32 per row on the aligned
+ *       block that holds the pair (+0 in the unused slots) plus a scalar where the pair straddles two blocks (5 on
+ *       average, branch-free).  Either value also switches the binned TSC scatter to one quad (+ one pair for half of
+ *       the particles) per stencil row: 13.5 instead of 27.  Off until it has been measured.
  *   "gather_stage" (default 0): 1 = the tile gather issues its shared-memory staging with one base pointer per
  *       (field, plane) and one multiply-add per row (half the instructions of the default kernel); bit-identical
  *       results; off until it has been measured.

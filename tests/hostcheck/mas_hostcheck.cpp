@@ -125,10 +125,21 @@ int64_t hc_deposit_pairs(int mode, float* buf, const float* x, const float* y, c
       int x0, x1;
       float w0, w1;
       cic_axis(px, g.mn[0], g.L[0], g.n[0], wrap != 0, x0, x1, w0, w1);
-      if ((((x0 | g.n[0]) & 1) == 0 && x1 == x0 + 1) || (mode == 2 && (g.n[0] & 3) == 0 && (x0 & 3) == 1)) paired++;
+      if ((mode == 2 && (g.n[0] & 3) == 0) || (((x0 | g.n[0]) & 1) == 0 && x1 == x0 + 1)) paired++;  // took a vector reduction
     }
   }
   *n_paired = paired;
+  return bad;
+}
+
+// Option "scatter_pairs" for TSC: the product's deposit_tsc_vec (one aligned quad or two aligned pairs per stencil row)
+// against deposit<TSC> -- on the host the vector reductions are plain additions in cell order, the +0 slots included.
+int64_t hc_deposit_tsc_vec(float* buf, const float* x, const float* y, const float* z, const float* w, int64_t n, const int* ng,
+                           const float* L, const float* mn, int wrap, int slab, int z_lo, int zoff, int nzp) {
+  const BoxGeom g = make_geom(ng, L, mn, slab, z_lo, zoff, nzp);
+  int64_t bad = 0;
+  for (int64_t i = 0; i < n; i++)
+    if (!deposit_tsc_vec(buf, x[i], y[i], z[i], w[i], g, wrap != 0)) bad++;
   return bad;
 }
 

@@ -73,3 +73,23 @@ def test_paired_scatter_matches_the_oracle(B, O):
         assert maxabs(meshes[-1], ref) <= 2e-6 * float(ref.max())
     for m in meshes[1:]:
         assert abs(float(m.sum(dtype=np.float64)) / float(w.sum(dtype=np.float64)) - 1) < 1e-6
+
+
+def test_vector_tsc_scatter_matches_the_oracle(B, O):
+    """Option "scatter_pairs" for the binned TSC scatter: one aligned quad or two aligned pairs per stencil row
+    (csrc/mas_math.cuh: deposit_tsc_vec; against the scalar deposit bit for bit on the CPU, tests/test_mas_hostcheck.py)."""
+    n, L, N = 128, 1000.0, 400_000
+    pos, w = clustered_box(N, L, seed=35)
+    bs, bm = np.full(3, L, f32), np.zeros(3, f32)
+    ref = O.tsc_scatter(np.zeros((n, n, n), f32), *pos, w, bs, bm, True)
+    ctx = B.Context.get(0)
+    for on in (0, 1):
+        try:
+            ctx.set_option("scatter_pairs", on)
+            rho = torch.zeros((n, n, n), dtype=torch.float32, device="cuda")
+            B.cic(rho, *(dev(p) for p in pos), dev(w), bs, bm, wrap=True, mas="tsc")
+        finally:
+            ctx.set_option("scatter_pairs", 0)
+        h = rho.cpu().numpy()
+        assert maxabs(h, ref) <= 3e-6 * float(ref.max())
+        assert abs(float(h.sum(dtype=np.float64)) / float(w.sum(dtype=np.float64)) - 1) < 1e-6
