@@ -295,6 +295,16 @@ scatter_sorted_kernel(float* __restrict__ rho, const float4* __restrict__ rec, c
   deposit<MAS>(rho, p.x, p.y, p.z, p.w, g, wrap != 0);
 }
 
+// option "scatter_pairs" on the z-binned path (slab-decomposed scatters, unified_sort = 0): CIC with one quad per row
+__global__ void __launch_bounds__(256)
+scatter_sorted_cic_vec_kernel(float* __restrict__ rho, const float4* __restrict__ rec, const unsigned* __restrict__ n_valid,
+                              BoxGeom g, int wrap) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)__ldg(n_valid)) return;
+  float4 p = rec[i];
+  deposit_pairs<2>(rho, p.x, p.y, p.z, p.w, g, wrap != 0);
+}
+
 // option "scatter_pairs": the binned TSC scatter with vector reductions (deposit_tsc_vec in mas_math.cuh)
 __global__ void __launch_bounds__(256)
 scatter_sorted_tsc_vec_kernel(float* __restrict__ rho, const float4* __restrict__ rec, const unsigned* __restrict__ n_valid,
@@ -1049,6 +1059,8 @@ int scatter(baorec_ctx* ctx, float* rho, float* x, float* y, float* z, const flo
     if (tsc && ctx->opt_scatter_pairs && ((uintptr_t)rho & 15) == 0)
       BR_LAUNCH(ctx, scatter_sorted_tsc_vec_kernel, grid, 256, 0, st, rho, b.rec, b.n_valid, g, wrap);
     else if (tsc) BR_LAUNCH(ctx, scatter_sorted_kernel<BAOREC_MAS_TSC>, grid, 256, 0, st, rho, b.rec, b.n_valid, g, wrap);
+    else if (ctx->opt_scatter_pairs && ((uintptr_t)rho & 15) == 0)
+      BR_LAUNCH(ctx, scatter_sorted_cic_vec_kernel, grid, 256, 0, st, rho, b.rec, b.n_valid, g, wrap);
     else BR_LAUNCH(ctx, scatter_sorted_kernel<BAOREC_MAS_CIC>, grid, 256, 0, st, rho, b.rec, b.n_valid, g, wrap);
     return BAOREC_OK;
   }

@@ -93,3 +93,28 @@ def test_vector_tsc_scatter_matches_the_oracle(B, O):
         h = rho.cpu().numpy()
         assert maxabs(h, ref) <= 3e-6 * float(ref.max())
         assert abs(float(h.sum(dtype=np.float64)) / float(w.sum(dtype=np.float64)) - 1) < 1e-6
+
+
+@pytest.mark.parametrize("mas", ["cic", "tsc"])
+def test_vector_reductions_on_the_slab_path(B, O, mas):
+    """Option "scatter_pairs" on the z-binned scatter of the slab-decomposed path (scatter_sorted_cic_vec_kernel /
+    scatter_sorted_tsc_vec_kernel writing into the ghost-plane layouts): the distributed reconstruction still matches
+    the oracle."""
+    n, L, N = 64, 1000.0, 300_000
+    pos, w = clustered_box(N, L, seed=37)
+    kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=np.full(3, L, f32), box_min=np.zeros(3, f32),
+              los=(0.0, 0.0, 1.0), n_iter=3)
+    orec = O.IterativeRecon(**kw)
+    orec.mas = mas
+    omesh = O.run(orec, (n, n, n), *[p.copy() for p in pos], w)
+    ctx = B.Context.get(0)
+    B.dist.init_comm(ctx)
+    try:
+        ctx.set_option("scatter_pairs", 1)
+        rec = B.IterativeRecon(mas=mas, **kw)
+        mesh = B.dist.run_dist(rec, (n, n, n), *(dev(p) for p in pos), dev(w), ctx=ctx)
+        h = mesh.cpu().numpy()
+    finally:
+        ctx.set_option("scatter_pairs", 0)
+        ctx.plan_key = None
+    assert float(np.sqrt(np.mean((h.astype(np.float64) - omesh) ** 2)) / np.sqrt(np.mean(omesh.astype(np.float64) ** 2))) < 1e-4
