@@ -48,7 +48,7 @@ struct PeerTab {
   float2* p[16];
 };
 __global__ void __launch_bounds__(128)
-rows_p2p_kernel(PeerTab dst, const float2* __restrict__ src, int nzl, int ny, int nyl, int xh, int rank) {
+rows_p2p_kernel(const __grid_constant__ PeerTab dst, const float2* __restrict__ src, int nzl, int ny, int nyl, int xh, int rank) {
   const unsigned row = blockIdx.x;  // zl * ny + y
   const int zl = row / ny, y = row - zl * ny;
   const int peer = y / nyl, yl = y - peer * nyl;
@@ -65,10 +65,14 @@ struct TrGeom {
   size_t src_b0, src_b1, dst_b0, dst_b1;
 };
 
+// (`tab` is __grid_constant__: indexing it with the run-time b0 reads the constant bank; passed by plain value the
+// compiler copied all 16 pointers to every thread's stack first -- 16 local stores per thread, found by
+// benchmarks/sass_census.py.)
 // If `tab` is given, batch b0 (= destination peer) is written into tab.p[b0] + tab_off instead of
 // dst + b0 * dst_b0 (fused transpose + exchange over peer memory).
 __global__ void __launch_bounds__(256)
-transpose_kernel(float2* __restrict__ dst, const float2* __restrict__ src, TrGeom t, PeerTab tab, int use_tab,
+transpose_kernel(float2* __restrict__ dst, const float2* __restrict__ src, TrGeom t, const __grid_constant__ PeerTab tab,
+                 int use_tab,
                  size_t tab_off) {
   __shared__ float2 tile[32][33];
   const int b = blockIdx.z, b0 = b / t.nb1, b1 = b - b0 * t.nb1;

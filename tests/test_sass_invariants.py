@@ -58,12 +58,12 @@ def test_staged_kernels_use_cp_async(K):
 def test_no_register_spills_and_known_local_memory_users(K):
     """No kernel of these objects spills registers except the scalar tail instantiation of cartesian_to_sky (<= 3
     particles per call, 12 bytes).  Local memory is otherwise used only where a kernel indexes a table that arrives by
-    value in its parameters (the compiler copies it to the stack): listed here so that a new one does not go unnoticed."""
+    value in its parameters (the compiler copies it to the stack): listed here so that a new one does not go unnoticed (the slab transpose's peer table was one: 16 local stores per
+    thread until it became __grid_constant__)."""
     spills = {k for k, v in K.items() if v["spill"]}
     assert all("cartesian_to_sky_kernel<1>" in k for k in spills), spills
     local = {k.replace("(anonymous namespace)::", "").split("(")[0].replace("void ", "").replace("baorec::", "") for k, v in K.items() if v["local"]}
     assert local == {"cartesian_to_sky_kernel<1>", "sky_to_cartesian_kernel<1>", "sky_to_cartesian_kernel<4>",   # sincos quadrant table
-                     "transpose_kernel", "rows_p2p_kernel",      # PeerTab (16 pointers by value); transpose_kernel: 16 STL per thread, to fix with __grid_constant__
                      "gather_trash_kernel",                      # GatherArgs.o[c] with a run-time c
                      "mg_coarse_kernel"}, local                  # level table of the single-block coarse V-cycle
 
