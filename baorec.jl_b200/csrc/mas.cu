@@ -671,7 +671,9 @@ constexpr int TILE_WXP = TILE_X + 4;  // padded row length in shared memory
 // STAGE selects how the fast path issues its cp.async rows: 0 = rows dealt round-robin over a fully unrolled loop
 // (the version measured in round 1: 1719 of its 2700 SASS instructions are integer address arithmetic, and every warp
 // steps over all 54 row predicates); 1 = each warp owns rows py = warp, warp + 4 (, 8) of every (field, plane):
-// one plane base pointer per (field, plane), one multiply-add per row, compile-time shared-memory offsets
+// one plane base pointer per (field, plane), one multiply-add per row, compile-time shared-memory offsets; the tile
+// index is decoded with shifts when the tile counts are powers of two; a thread's first record is requested before
+// the window is staged
 // (option "gather_stage", off until it has been measured).  Identical shared-memory contents either way.
 template <int NF, int STAGE>
 __global__ void __launch_bounds__(128)
@@ -682,15 +684,25 @@ gather_tile_kernel(GatherArgs a, const float4* __restrict__ rec, const unsigned*
   const unsigned beg = starts[tile], end = starts[tile + 1];
   if (beg == end) return;
   const int nx = g.n[0], ny = g.n[1], nz = g.n[2];
-  const int tx = tile % t.nxc;
-  const unsigned r = tile / t.nxc;
-  const int ty = r % t.nyc;
-  const int iz = r / t.nyc;
+  int tx, ty, iz;
+  if (STAGE == 1 && ((t.nxc & (t.nxc - 1)) | (t.nyc & (t.nyc - 1))) == 0) {  // power-of-two tile counts: shifts, no division
+    const int sx = __ffs(t.nxc) - 1, sy = __ffs(t.nyc) - 1;
+    tx = (int)(tile & (unsigned)(t.nxc - 1));
+    ty = (int)((tile >> sx) & (unsigned)(t.nyc - 1));
+    iz = (int)(tile >> (sx + sy));
+  } else {
+    tx = tile % t.nxc;
+    const unsigned r = tile / t.nxc;
+    ty = r % t.nyc;
+    iz = r / t.nyc;
+  }
   const int x0 = tx * TILE_X, y0 = ty * TILE_Y;
   const int wx = min(TILE_X, nx - x0), wy = min(TILE_Y, ny - y0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool fast = (wx == TILE_X) && (wy == TILE_Y) && (nx % 4 == 0) &&
                     ((((uintptr_t)a.f[0] | (uintptr_t)a.f[NF > 1 ? 1 : 0] | (uintptr_t)a.f[NF > 2 ? 2 : 0]) & 15) == 0);
+  float4 p_first = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (STAGE == 1 && beg + threadIdx.x < end) p_first = rec[beg + threadIdx.x];  // in flight while the window is staged
   if (fast && STAGE == 1) {
     int xe = x0 + TILE_X;
     if (xe >= nx) xe -= nx;
@@ -768,7 +780,7 @@ gather_tile_kernel(GatherArgs a, const float4* __restrict__ rec, const unsigned*
   }
   __syncthreads();
   for (unsigned i = beg + threadIdx.x; i < end; i += 128) {
-    float4 p = rec[i];
+    float4 p = (STAGE == 1 && i < beg + 128) ? p_first : rec[i];
     const float px = p.x, py = p.y, pz = p.z;
     const int64_t out_idx = (int64_t)__float_as_uint(p.w);
     int xd, xu, yd, yu, zd, zu;

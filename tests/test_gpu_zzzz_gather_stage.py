@@ -1,6 +1,7 @@
 """GPU: option "gather_stage" = 1 -- the tile gather with the strength-reduced cp.async staging
-(gather_tile_kernel<3, 1>, csrc/mas.cu: each warp owns rows py = warp, warp + 4 (, 8) of every (field, plane); half the
-SASS instructions of the measured version, profiles/r1_sass_census.csv).  Same shared-memory contents, same
+(gather_tile_kernel<3, 1>, csrc/mas.cu: each warp owns rows py = warp, warp + 4 (, 8) of every (field, plane), shift
+decode of the tile index, first record prefetched; half the SASS instructions of the measured version,
+profiles/r1_sass_census.csv).  Same shared-memory contents, same
 arithmetic: the shifts must be bit-identical to the default kernel's.  Written after this round's GPU budget was
 spent: NOT YET RUN ON HARDWARE (file name sorts last)."""
 import numpy as np
