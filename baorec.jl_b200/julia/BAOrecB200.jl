@@ -352,6 +352,11 @@ function wrap_positions!(x::CuVector{Float32}, y::CuVector{Float32}, z::CuVector
     x, y, z
 end
 
+# Engine options (include/baorec_b200.h: "fuse_kspace", "unified_sort", "deterministic_scatter", "scatter_pairs",
+# "gather_stage", ...): BAOrecB200.set_option("deterministic_scatter", 1)
+set_option(name::AbstractString, value::Integer) =
+    check(ccall((:baorec_set_option, libbaorec), Cint, (Ptr{Cvoid}, Cstring, Int64), context(), name, value))
+
 # P_0, P_2, P_4 of a density mesh (periodic box): the before / after check of test_helpers/simulation.py:56-75
 # (pypowspec compute_auto_box; with `randoms`, the mesh of a shifted random catalog: compute_auto_box_rand) on the device.
 # mas_power: 2 = CIC window, 3 = TSC, 0 = none.
