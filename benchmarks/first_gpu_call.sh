@@ -10,11 +10,11 @@ mkdir -p gpurun_out
 run() { local name=$1; shift; echo "== $name" | tee -a gpurun_out/r2_first.log; ( time timeout 600 "$@" ) > "gpurun_out/r2_$name.log" 2>&1; echo "   rc=$?" | tee -a gpurun_out/r2_first.log; tail -3 "gpurun_out/r2_$name.log" >> gpurun_out/r2_first.log; }
 
 # 1. the GPU tests that have never run, one file at a time
-for f in zzz_golden_catalog zzzz_gather_stage zzzz_pk zzzz_batch zzzz_tsc_slabs_deterministic zzz_fullsize; do
+for f in zzz1_golden_catalog zzz2_fullsize zzz3_tsc_slabs_deterministic zzz4_pk zzz5_batch zzz6_gather_stage; do
   run "test_$f" python -m pytest "tests/test_gpu_$f.py" -q -m gpu
 done
 # 2. everything that had passed before (regression: mas.o's TSC kernels changed for the slab layout)
-run test_validated python -m pytest tests -q -m gpu -x --ignore tests/test_gpu_zzz_fullsize.py --ignore-glob='tests/test_gpu_zzzz_*' --ignore tests/test_gpu_zzz_golden_catalog.py
+run test_validated python -m pytest tests -q -m gpu -x --ignore-glob='tests/test_gpu_zzz[1-9]_*'
 # 3. the bench with the batched host pipeline next to the one-at-a-time e2e
 run bench_batch python bench.py --steps 5 --warmup 3 --e2e-batch 4
 # 3b. the secondary configs, TSC included (BASELINE configs[1] names TSC; only CIC was measured in round 1)

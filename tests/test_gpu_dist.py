@@ -85,7 +85,7 @@ def test_run_dist_matches_single_gpu_and_oracle(B, O, dctx, los):
 
 
 def test_read_shifts_dist_needs_a_run_first(B):
-    """(TSC on slabs used to be rejected here; it is supported now: tests/test_gpu_zzzz_tsc_slabs_deterministic.py.)"""
+    """(TSC on slabs used to be rejected here; it is supported now: tests/test_gpu_zzz3_tsc_slabs_deterministic.py.)"""
     lib = B.lib_loader.load()
     assert lib.baorec_read_shifts_dist_f32(None, None, None, None, None, 0, 0, 0, None, None, None, None) == B.lib_loader.ERR_INVALID
 
