@@ -132,3 +132,31 @@ def test_data_minus_shifted_randoms(HC):
         assert np.abs(got[key][ok] - ref[key][ok]).max() <= 2e-6 * np.abs(ref["p0"][ok]).max()
     plain = PK.power_multipoles(rho, bs, los=(0.0, 0.6, 0.8), kmin=0.0, dk=0.02, nbins=12, mas_power=2, shot=3.0)
     assert np.abs(ref["p0"][ok] - plain["p0"][ok]).max() > 1e-3 * np.abs(plain["p0"][ok]).max()      # the randoms do enter
+
+
+def test_segmented_warp_reduction_logic():
+    """pk_kernel's accumulation, restated lane by lane: run id = popcount of the head-flag ballot up to the lane, five
+    shuffle-down steps that add only within a run, run heads hold the run totals (csrc/pk.cu).  Checks the algorithm
+    (the compiled kernel is checked on the GPU against the oracle): arbitrary runs, including bins that reappear."""
+    rng = np.random.default_rng(0)
+    for _ in range(500):
+        bins = []
+        while len(bins) < 32:
+            bins += [int(rng.integers(-1, 6))] * int(rng.integers(1, 12))
+        bins, val = np.array(bins[:32]), rng.random(32)
+        head = np.array([1] + [int(bins[i] != bins[i - 1]) for i in range(1, 32)])
+        ballot = sum(int(h) << i for i, h in enumerate(head))
+        run = np.array([bin(ballot & (0xFFFFFFFF >> (31 - lane))).count("1") for lane in range(32)])
+        s = val.copy()
+        d = 1
+        while d < 32:
+            t = np.array([s[i + d] if i + d < 32 else s[i] for i in range(32)])         # __shfl_down: out-of-range lanes read themselves
+            r = np.array([run[i + d] if i + d < 32 else run[i] for i in range(32)])
+            s = np.where((np.arange(32) + d < 32) & (r == run), s + t, s)
+            d *= 2
+        acc = {}
+        for lane in range(32):
+            if head[lane] and bins[lane] >= 0:
+                acc[bins[lane]] = acc.get(bins[lane], 0.0) + s[lane]                    # the atomics of the run heads
+        for b in set(bins[bins >= 0]):
+            assert abs(acc[b] - val[bins == b].sum()) < 1e-12
