@@ -190,7 +190,7 @@ __device__ __forceinline__ bool deposit(float* __restrict__ rho, float px, float
 // reduction throughput.  Same cells, same Float32 values; only the grouping differs.
 __device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
 #if defined(__CUDA_ARCH__)
-  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(__cvta_generic_to_global(p)), "f"(a), "f"(b) : "memory");
 #else
   p[0] += a;
   p[1] += b;
@@ -199,7 +199,8 @@ __device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
 #if defined(__CUDA_ARCH__)
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(p)), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
 #else
   p[0] += a;
   p[1] += b;
