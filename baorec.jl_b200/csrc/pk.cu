@@ -12,6 +12,7 @@
 // to global memory once at the end (REDG.ADD.F64).
 #include <math.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "internal.cuh"
@@ -89,6 +90,50 @@ pk_kernel(PkGeom g, const float* __restrict__ tkx, const float* __restrict__ tky
   }
 }
 
+// Float64 sums of the data (and randoms) mesh: sums[0] = sum rho, sums[1] = sum ran.  4 B/cell per mesh, HBM-bound.
+__global__ void __launch_bounds__(256)
+pk_sum_kernel(const float* __restrict__ rho, const float* __restrict__ ran, size_t n, double* __restrict__ sums) {
+  double a = 0.0, b = 0.0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    a += (double)rho[i];
+    if (ran != nullptr) b += (double)ran[i];
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    a += __shfl_down_sync(0xffffffffu, a, d);
+    b += __shfl_down_sync(0xffffffffu, b, d);
+  }
+  __shared__ double sa[8], sb[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    sa[warp] = a;
+    sb[warp] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++) {
+      a += sa[w];
+      b += sb[w];
+    }
+    atomicAdd(sums, a);
+    if (ran != nullptr) atomicAdd(sums + 1, b);
+  }
+}
+
+// The field whose spectrum is estimated, formed in REAL space so that the Float32 transform never sees the mean:
+// out = rho * (M / sum rho) - 1, or rho * (M / sum rho) - ran * (M / sum ran) with a randoms mesh (compute_auto_box /
+// compute_auto_box_rand of the reference's helpers).  Transforming the raw density instead leaves every mode with
+// the transform's rounding of the DC term (~1e-7 * sum rho), which on a sparse low-k bin is 1e-4 of the signal: the
+// failure of the first hardware run (32 x 32 x 33 mesh).  Float64 arithmetic per cell, rounded once.  12 B/cell.
+__global__ void __launch_bounds__(256)
+pk_contrast_kernel(const float* __restrict__ rho, const float* __restrict__ ran, size_t n, double ca, double cb,
+                   float* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = (float)((double)rho[i] * ca - (ran != nullptr ? (double)ran[i] * cb : 1.0));
+}
+
 // 1 / sinc(x)^(2p): the inverse squared window of one axis
 static double inv_window2(double x, int p) {
   const double s = x == 0.0 ? 1.0 : sin(x) / x;
@@ -123,22 +168,29 @@ int power_multipoles(baorec_ctx* ctx, const float* rho, const float* ran, const 
   double* acc = d + ntab;
   BR_CUDA(cudaMemcpyAsync(d, wt.data(), sizeof(double) * ntab, cudaMemcpyHostToDevice, st));
   BR_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 5 * nbins, st));
-  float2 *ck0, *ck1 = nullptr;
-  BR_TRY(need_t(ctx, BUF_CK0, ctx->Mc, &ck0));
-  BR_TRY(fft_r2c(ctx, rho, ck0, st));
-  float2 dc = make_float2(0.f, 0.f), dc2 = make_float2(1.f, 0.f);
-  BR_CUDA(cudaMemcpyAsync(&dc, ck0, sizeof(float2), cudaMemcpyDeviceToHost, st));
-  if (ran) {
-    BR_TRY(need_t(ctx, BUF_CK1, ctx->Mc, &ck1));
-    BR_TRY(fft_r2c(ctx, ran, ck1, st));
-    BR_CUDA(cudaMemcpyAsync(&dc2, ck1, sizeof(float2), cudaMemcpyDeviceToHost, st));
-  }
+  // sums in Float64 -> contrast in real space -> ONE transform (the randoms are subtracted before it, not after)
+  double* sums = ctx->d_scal + 6;
+  BR_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), st));
+  int sms = 148;
+  BR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+  const unsigned rgrid = (unsigned)std::min<size_t>((size_t)sms * 8, cdiv(ctx->M, 256));
+  BR_LAUNCH(ctx, pk_sum_kernel, rgrid, 256, 0, st, rho, ran, ctx->M, sums);
+  double hs[2] = {0.0, 1.0};
+  BR_CUDA(cudaMemcpyAsync(hs, sums, (ran ? 2 : 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
   BR_CUDA(cudaStreamSynchronize(st));
-  if (!(dc.x != 0.f) || !(dc2.x != 0.f)) {
+  if (!(hs[0] != 0.0) || !(hs[1] != 0.0)) {
     set_error("baorec_power_multipoles_f32: a mesh sums to zero (pass densities, not overdensities)");
     return BAOREC_ERR_INVALID;
   }
-  const double sa = 1.0 / (double)dc.x, sb = ran ? 1.0 / (double)dc2.x : 0.0;
+  float* contrast;
+  float2* ck0;
+  BR_TRY(need_t(ctx, BUF_RS, ctx->M, &contrast));
+  BR_TRY(need_t(ctx, BUF_CK0, ctx->Mc, &ck0));
+  BR_LAUNCH(ctx, pk_contrast_kernel, rgrid, 256, 0, st, rho, ran, ctx->M, (double)ctx->M / hs[0],
+            ran ? (double)ctx->M / hs[1] : 0.0, contrast);
+  BR_TRY(fft_r2c(ctx, contrast, ck0, st));
+  const float2* ck1 = nullptr;
+  const double sa = 1.0 / (double)ctx->M, sb = 0.0;  // delta_k / M  ==  rho_k / rho_0 for k != 0
   PkGeom g;
   g.wx = d;
   g.wy = d + len[0];
@@ -155,8 +207,7 @@ int power_multipoles(baorec_ctx* ctx, const float* rho, const float* ran, const 
   const size_t nchunks = (size_t)cpp * ctx->nz;
   BR_REQUIRE(nchunks < ((size_t)1 << 32), "mesh too large for the multipole kernel's chunk index");
   // persistent grid: SM count x resident blocks per SM (76 registers -> 3 blocks of 256 threads)
-  int sms = 148, occ = 1;
-  BR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+  int occ = 1;
   BR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pk_kernel, PK_THREADS, sizeof(double) * 5 * nbins));
   unsigned grid = (unsigned)sms * (unsigned)(occ > 0 ? occ : 1);
   if (grid > nchunks) grid = (unsigned)nchunks;

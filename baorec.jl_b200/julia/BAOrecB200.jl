@@ -94,7 +94,13 @@ function context()
 end
 
 stream() = CUDA.stream().handle            # the caller's task-local stream
-f3(v) = Ref((Float32(v[1]), Float32(v[2]), Float32(v[3])))
+# a Vector{Float32} converts to Ptr{Cfloat} and is rooted by ccall for the duration of the call (Base defines no
+# unsafe_convert(Ptr{Cfloat}, ::Ref{NTuple{3,Float32}}), so a Ref of a tuple would be a MethodError)
+f3(v) = Float32[v[1], v[2], v[3]]
+# Every method below must be MORE SPECIFIC than the reference's in EVERY argument (an untyped argument where the
+# reference's CuArray method has a typed one makes the call ambiguous): the same argument types with T = Float32.
+const V3 = SVector{3,Float32}
+const Vec3 = Tuple{AbstractVector{Float32},AbstractVector{Float32},AbstractVector{Float32}}   # k_vec / x_vec results
 ptr(a::CuArray{Float32}) = reinterpret(Ptr{Cvoid}, pointer(a))
 ptr(::Nothing) = C_NULL
 
@@ -136,7 +142,7 @@ function smooth!(field::CuArray{Float32,3}, smoothing_radius::Float32, box_size:
     field
 end
 
-function _catalog_call(sym::Symbol, mesh, recon, d, r; extra = ())
+function _catalog_call(mesh, recon, r)
     ctx = plan!(mesh, recon.box_size, recon.box_min)
     p = Ref(Params(recon))
     nr = r === nothing ? 0 : length(r[1])
@@ -146,26 +152,26 @@ end
 
 function setup_overdensity!(δ::CuArray{Float32,3}, recon::AbstractRecon, x::CuArray{Float32}, y::CuArray{Float32},
                             z::CuArray{Float32}, w::CuArray{Float32}, wrap = true)
-    ctx, p, _, rp = _catalog_call(:setup, δ, recon, (x, y, z, w), nothing)
+    ctx, p, _, rp = _catalog_call(δ, recon, nothing)
     check(ccall((:baorec_setup_overdensity_f32, libbaorec), Cint,
                 (Ptr{Cvoid}, Ptr{Params}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64,
                  Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint, Ptr{Cvoid}),
-                ctx, p, ptr(δ), ptr(x), ptr(y), ptr(z), ptr(w), length(x), rp..., 0, wrap, stream()))
+                ctx, p, ptr(δ), ptr(x), ptr(y), ptr(z), ptr(w), length(x), rp[1], rp[2], rp[3], rp[4], 0, wrap, stream()))
     δ
 end
 
 function setup_overdensity!(δ::CuArray{Float32,3}, recon::AbstractRecon, x::CuArray{Float32}, y::CuArray{Float32},
                             z::CuArray{Float32}, w::CuArray{Float32}, rx::CuArray{Float32}, ry::CuArray{Float32},
                             rz::CuArray{Float32}, rw::CuArray{Float32}, ran_min = 0.01)
-    ctx, p, nr, rp = _catalog_call(:setup, δ, recon, (x, y, z, w), (rx, ry, rz, rw))
+    ctx, p, nr, rp = _catalog_call(δ, recon, (rx, ry, rz, rw))
     check(ccall((:baorec_setup_overdensity_f32, libbaorec), Cint,
                 (Ptr{Cvoid}, Ptr{Params}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64,
                  Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint, Ptr{Cvoid}),
-                ctx, p, ptr(δ), ptr(x), ptr(y), ptr(z), ptr(w), length(x), rp..., nr, false, stream()))
+                ctx, p, ptr(δ), ptr(x), ptr(y), ptr(z), ptr(w), length(x), rp[1], rp[2], rp[3], rp[4], nr, false, stream()))
     δ
 end
 
-function iterate!(δ_r::CuArray{Float32,3}, δ_s::CuArray{Float32,3}, k⃗, iter::Int, β::Float32, fft_plan;
+function iterate!(δ_r::CuArray{Float32,3}, δ_s::CuArray{Float32,3}, k⃗::Vec3, iter::Int, β::Float32, fft_plan;
                   r̂ = nothing, x⃗ = nothing)
     # k⃗ / x⃗ are accepted for signature parity; the plan holds the same tables on the device
     los = r̂ === nothing ? C_NULL : f3(r̂)
@@ -175,106 +181,122 @@ function iterate!(δ_r::CuArray{Float32,3}, δ_s::CuArray{Float32,3}, k⃗, iter
     δ_r
 end
 
-for (fn, sym) in ((:reconstructed_overdensity!, :baorec_reconstructed_overdensity_f32),
-                  (:reconstructed_potential!, :baorec_reconstructed_potential_f32))
-    R = fn === :reconstructed_overdensity! ? :IterativeRecon : :MultigridRecon
-    @eval function $fn(mesh::CuArray{Float32,3}, recon::$R, x::CuArray{Float32}, y::CuArray{Float32},
-                       z::CuArray{Float32}, w::CuArray{Float32}, r::CuArray{Float32}...)
-        rr = length(r) == 4 ? r : nothing
-        ctx, p, nr, rp = _catalog_call($(QuoteNode(fn)), mesh, recon, (x, y, z, w), rr)
+# reconstructed_overdensity! (src/recon.jl:93, 111) / reconstructed_potential! (src/recon.jl:184, 197): the two
+# arities of the reference, each strictly more specific than its AbstractArray method (no Vararg: a Vararg method is
+# not a subtype of either fixed-arity signature and would leave the dispatch to the specificity heuristics).
+for (fn, sym, R) in ((:reconstructed_overdensity!, :baorec_reconstructed_overdensity_f32, :IterativeRecon),
+                     (:reconstructed_potential!, :baorec_reconstructed_potential_f32, :MultigridRecon))
+    @eval function $fn(mesh::CuArray{Float32,3}, recon::$R, x::CuVector{Float32}, y::CuVector{Float32},
+                       z::CuVector{Float32}, w::CuVector{Float32})
+        ctx, p, _, rp = _catalog_call(mesh, recon, nothing)
         check(ccall(($(QuoteNode(sym)), libbaorec), Cint,
                     (Ptr{Cvoid}, Ptr{Params}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64,
                      Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}),
-                    ctx, p, ptr(mesh), ptr(x), ptr(y), ptr(z), ptr(w), length(x), rp..., nr, stream()))
+                    ctx, p, ptr(mesh), ptr(x), ptr(y), ptr(z), ptr(w), length(x), rp[1], rp[2], rp[3], rp[4], 0, stream()))
+        mesh
+    end
+    @eval function $fn(mesh::CuArray{Float32,3}, recon::$R, x::CuVector{Float32}, y::CuVector{Float32},
+                       z::CuVector{Float32}, w::CuVector{Float32}, rx::CuVector{Float32}, ry::CuVector{Float32},
+                       rz::CuVector{Float32}, rw::CuVector{Float32})
+        ctx, p, nr, rp = _catalog_call(mesh, recon, (rx, ry, rz, rw))
+        check(ccall(($(QuoteNode(sym)), libbaorec), Cint,
+                    (Ptr{Cvoid}, Ptr{Params}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64,
+                     Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}),
+                    ctx, p, ptr(mesh), ptr(x), ptr(y), ptr(z), ptr(w), length(x), rp[1], rp[2], rp[3], rp[4], nr, stream()))
         mesh
     end
 end
 
-function compute_displacements(mesh::CuArray{Float32,3}, x::CuVector{Float32}, y::CuVector{Float32},
-                               z::CuVector{Float32}, recon::AbstractRecon)
-    ctx = plan!(mesh, recon.box_size, recon.box_min)
-    out = Tuple(similar(x) for _ in 1:3)
-    check(ccall((:baorec_compute_displacements_f32, libbaorec), Cint,
-                (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid},
-                 Ptr{Cvoid}, Cint, Ptr{Cvoid}),
-                ctx, ptr(mesh), algorithm(recon), ptr(x), ptr(y), ptr(z), length(x), ptr(out[1]), ptr(out[2]),
-                ptr(out[3]), 0, stream()))
-    out
+# compute_displacements (src/iterative.jl:229, src/multigrid.jl:781): one method per recon type, as in the reference
+for R in (:IterativeRecon, :MultigridRecon)
+    @eval function compute_displacements(mesh::CuArray{Float32,3}, x::CuVector{Float32}, y::CuVector{Float32},
+                                         z::CuVector{Float32}, recon::$R)
+        ctx = plan!(mesh, recon.box_size, recon.box_min)
+        out = (similar(x), similar(x), similar(x))
+        check(ccall((:baorec_compute_displacements_f32, libbaorec), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid},
+                     Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+                    ctx, ptr(mesh), algorithm(recon), ptr(x), ptr(y), ptr(z), length(x), ptr(out[1]), ptr(out[2]),
+                    ptr(out[3]), 0, stream()))
+        out
+    end
 end
 
-function _read(sym::Symbol, recon, x, y, z, mesh, field)
-    ctx = plan!(mesh, recon.box_size, recon.box_min)
-    out = Tuple(similar(x) for _ in 1:3)
-    p = Ref(Params(recon))
-    if mesh === recon.result_cache
-        # the mesh run! produced: the library kept its delta_k, the forward transform is skipped
-        positions = sym === :baorec_reconstructed_positions_f32
-        check(ccall((:baorec_read_result_cache_f32, libbaorec), Cint,
-                    (Ptr{Cvoid}, Ptr{Params}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint, Cint,
+# read_shifts / reconstructed_positions (src/recon.jl:333-364, 366-388).  The C symbol of a ccall must be a literal
+# (the (name, library) tuple may not reference local variables), so both methods are generated with the symbol
+# interpolated at definition time, like reconstructed_overdensity! / reconstructed_potential! above.
+for (fn, sym, positions) in ((:read_shifts, :baorec_read_shifts_f32, 0),
+                             (:reconstructed_positions, :baorec_reconstructed_positions_f32, 1))
+    @eval function $fn(recon::AbstractRecon, x::CuVector{Float32}, y::CuVector{Float32}, z::CuVector{Float32},
+                       mesh::CuArray{Float32,3}; field = :disp)
+        ctx = plan!(mesh, recon.box_size, recon.box_min)
+        out = (similar(x), similar(x), similar(x))
+        p = Ref(Params(recon))
+        if mesh === recon.result_cache
+            # the mesh run! produced: the library kept its delta_k, the forward transform is skipped
+            check(ccall((:baorec_read_result_cache_f32, libbaorec), Cint,
+                        (Ptr{Cvoid}, Ptr{Params}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint, Cint,
+                         Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                        ctx, p, algorithm(recon), ptr(mesh), ptr(x), ptr(y), ptr(z), length(x), FIELD[field],
+                        $positions, ptr(out[1]), ptr(out[2]), ptr(out[3]), stream()))
+            return out
+        end
+        check(ccall(($(QuoteNode(sym)), libbaorec), Cint,
+                    (Ptr{Cvoid}, Ptr{Params}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint,
                      Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
                     ctx, p, algorithm(recon), ptr(mesh), ptr(x), ptr(y), ptr(z), length(x), FIELD[field],
-                    positions, ptr(out[1]), ptr(out[2]), ptr(out[3]), stream()))
-        return out
+                    ptr(out[1]), ptr(out[2]), ptr(out[3]), stream()))
+        out
     end
-    check(ccall((sym, libbaorec), Cint,
-                (Ptr{Cvoid}, Ptr{Params}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint,
-                 Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
-                ctx, p, algorithm(recon), ptr(mesh), ptr(x), ptr(y), ptr(z), length(x), FIELD[field],
-                ptr(out[1]), ptr(out[2]), ptr(out[3]), stream()))
-    out
 end
 
-read_shifts(recon::AbstractRecon, x::CuVector{Float32}, y::CuVector{Float32}, z::CuVector{Float32},
-            mesh::CuArray{Float32,3}; field = :disp) = _read(:baorec_read_shifts_f32, recon, x, y, z, mesh, field)
-
-reconstructed_positions(recon::AbstractRecon, x::CuVector{Float32}, y::CuVector{Float32}, z::CuVector{Float32},
-                        mesh::CuArray{Float32,3}; field = :disp) =
-    _read(:baorec_reconstructed_positions_f32, recon, x, y, z, mesh, field)
+# reconstructed_positions(recon, x, y, z; field) without a mesh needs no override: the reference's method
+# (src/recon.jl:382-388) forwards recon.result_cache to the method above.
 
 function setup_box(x::CuVector{Float32}, y::CuVector{Float32}, z::CuVector{Float32}, box_pad)
-    bs = Ref((0f0, 0f0, 0f0)); bm = Ref((0f0, 0f0, 0f0))
+    bs = Vector{Float32}(undef, 3); bm = Vector{Float32}(undef, 3)
     check(ccall((:baorec_setup_box_f32, libbaorec), Cint,
                 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cfloat, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cvoid}),
                 context(), ptr(x), ptr(y), ptr(z), length(x), Float32(box_pad), bs, bm, stream()))
-    SVector(bs[]...), SVector(bm[]...)
+    SVector{3,Float32}(bs), SVector{3,Float32}(bm)
 end
 
 # ---- multigrid primitives (src/multigrid.jl) -------------------------------------------------
 _los(los) = los === nothing ? C_NULL : f3(los)
 
-function jacobi!(v::CuArray{Float32,3}, f::CuArray{Float32,3}, x_vec, box_size, box_min, β::Float32,
+function jacobi!(v::CuArray{Float32,3}, f::CuArray{Float32,3}, x_vec::Vec3, box_size::V3, box_min::V3, β::Float32,
                  damping_factor::Float32, niterations::Int; los = nothing)
     ctx = plan!(v, box_size, box_min)
     check(ccall((:baorec_mg_jacobi_f32, libbaorec), Cint,
                 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Cfloat, Cfloat, Cint, Ptr{Cfloat}, Ptr{Cvoid}),
-                ctx, ptr(v), ptr(f), size(v)..., β, damping_factor, niterations, _los(los), stream()))
+                ctx, ptr(v), ptr(f), size(v, 1), size(v, 2), size(v, 3), β, damping_factor, niterations, _los(los), stream()))
     v
 end
 
-function residual!(r::CuArray{Float32,3}, v::CuArray{Float32,3}, f::CuArray{Float32,3}, x_vec, box_size, box_min,
+function residual!(r::CuArray{Float32,3}, v::CuArray{Float32,3}, f::CuArray{Float32,3}, x_vec::Vec3, box_size::V3, box_min::V3,
                    β::Float32, damping_factor::Float32, niterations::Int; los = nothing)
     ctx = plan!(v, box_size, box_min)
     check(ccall((:baorec_mg_residual_f32, libbaorec), Cint,
                 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Cfloat, Ptr{Cfloat}, Ptr{Cvoid}),
-                ctx, ptr(r), ptr(v), ptr(f), size(v)..., β, _los(los), stream()))
+                ctx, ptr(r), ptr(v), ptr(f), size(v, 1), size(v, 2), size(v, 3), β, _los(los), stream()))
     r
 end
 
 function reduce!(v2h::CuArray{Float32,3}, v1h::CuArray{Float32,3})
     check(ccall((:baorec_mg_restrict_f32, libbaorec), Cint,
                 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cvoid}),
-                context(), ptr(v2h), ptr(v1h), size(v1h)..., stream()))
+                context(), ptr(v2h), ptr(v1h), size(v1h, 1), size(v1h, 2), size(v1h, 3), stream()))
     v2h
 end
 
 function prolong!(v1h::CuArray{Float32,3}, v2h::CuArray{Float32,3})
     check(ccall((:baorec_mg_prolong_f32, libbaorec), Cint,
                 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cvoid}),
-                context(), ptr(v1h), ptr(v2h), size(v1h)..., stream()))
+                context(), ptr(v1h), ptr(v2h), size(v1h, 1), size(v1h, 2), size(v1h, 3), stream()))
     v1h
 end
 
-function vcycle!(v::CuArray{Float32,3}, f::CuArray{Float32,3}, box_size, box_min, β::Float32,
+function vcycle!(v::CuArray{Float32,3}, f::CuArray{Float32,3}, box_size::V3, box_min::V3, β::Float32,
                  damping_factor::Float32, niterations::Int; los = nothing)
     ctx = plan!(v, box_size, box_min)
     check(ccall((:baorec_mg_vcycle_f32, libbaorec), Cint,
@@ -283,7 +305,7 @@ function vcycle!(v::CuArray{Float32,3}, f::CuArray{Float32,3}, box_size, box_min
     v
 end
 
-function fmg(f1h::CuArray{Float32,3}, v1h::Union{CuArray{Float32,3},Nothing}, box_size, box_min, β::Float32,
+function fmg(f1h::CuArray{Float32,3}, v1h::Union{CuArray{Float32,3},Nothing}, box_size::V3, box_min::V3, β::Float32,
              jacobi_damping_factor::Float32, jacobi_niterations::Int, vcycle_niterations::Int; los = nothing)
     v1h === nothing && (v1h = CUDA.zeros(Float32, size(f1h)...))
     ctx = plan!(v1h, box_size, box_min)

@@ -67,11 +67,14 @@ def power_multipoles(rho, box_size, los=(0.0, 0.0, 1.0), kmin=0.0, dk=None, nbin
         dk = 2 * np.pi / float(L.max())
     if nbins is None:
         nbins = int((np.pi * min(nx / L[0], ny / L[1], nz / L[2]) - kmin) / dk)
-    rk = scipy.fft.rfftn(rho, workers=-1)
+    # Float64 transform: a Float32 transform of the raw density carries the rounding of its DC term (~1e-7 sum rho)
+    # into every mode, which is 1e-4 of the signal in a sparse low-k bin -- the oracle is the truth, not a second
+    # Float32 estimate
+    rk = scipy.fft.rfftn(np.asarray(rho, np.float64), workers=-1)
     a0 = float(rk[0, 0, 0].real)
     re, im = rk.real.astype(np.float64) * (1.0 / a0), rk.imag.astype(np.float64) * (1.0 / a0)
     if randoms is not None:
-        sk = scipy.fft.rfftn(np.asarray(randoms), workers=-1)
+        sk = scipy.fft.rfftn(np.asarray(randoms, np.float64), workers=-1)
         b0 = float(sk[0, 0, 0].real)
         re, im = re - sk.real.astype(np.float64) * (1.0 / b0), im - sk.imag.astype(np.float64) * (1.0 / b0)
     k, mu, W, wt = mode_table(rho.shape, box_size, los, mas_power)

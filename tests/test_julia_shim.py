@@ -52,31 +52,109 @@ def split_top(s):
     return out
 
 
+CCALL = re.compile(r"ccall\(\(\s*([^,]+?)\s*,\s*libbaorec\)\s*,\s*(\w+)\s*,\s*\(")
+
+
 def shim_ccalls():
+    """(symbol expression, return type, argument types, argument expressions, line) of every ccall into the library"""
     calls = []
-    for m in re.finditer(r"ccall\(\(\s*(:[a-z0-9_]+|sym|\$\(QuoteNode\(sym\)\))\s*,\s*libbaorec\)\s*,\s*(\w+)\s*,\s*\(", SHIM):
+    for m in CCALL.finditer(SHIM):
         i, depth = m.end(), 1
         while depth:
             depth += {"(": 1, ")": -1}.get(SHIM[i], 0)
             i += 1
-        calls.append((m.group(1), m.group(2), split_top(SHIM[m.end():i - 1]), SHIM.count("\n", 0, m.start()) + 1))
+        types = split_top(SHIM[m.end():i - 1])
+        j, depth = i, 1                         # the rest of the ccall( ... ): the argument expressions
+        while depth:
+            depth += {"(": 1, ")": -1}.get(SHIM[j], 0)
+            j += 1
+        args = split_top(SHIM[i:j - 1].lstrip(", \n"))
+        calls.append((m.group(1), m.group(2), types, args, SHIM.count("\n", 0, m.start()) + 1))
     return calls
 
 
-# two call sites name their symbol through a variable: the symbols they are instantiated with, read from the shim itself
-GENERIC = {"$(QuoteNode(sym))": re.findall(r"\(:\w+!?, :(baorec_\w+)\)", SHIM),        # the `for (fn, sym) in (...)` @eval loop
-           "sym": re.findall(r"_read\(:(baorec_\w+),", SHIM)}                            # read_shifts / reconstructed_positions
+def eval_loops():
+    """[(start, end, {loop variable: [values]})] of the `for (...) in (...) @eval function ... end end` blocks"""
+    out = []
+    for m in re.finditer(r"^for (\(?[\w, ]+\)?) in \((.*?)\)\n\s+@eval", SHIM, flags=re.S | re.M):
+        names = [n.strip() for n in m.group(1).strip("()").split(",")]
+        rows = re.findall(r"\(([^()]*)\)", m.group(2)) or [v for v in split_top(m.group(2))]
+        values = {n: [] for n in names}
+        for row in rows:
+            parts = [q.strip() for q in row.split(",")]
+            for n, q in zip(names, parts):
+                values[n].append(q)
+        end = SHIM.index("\nend\n", m.end()) + 5
+        out.append((m.start(), end, values))
+    return out
+
+
+def test_ccall_symbols_are_literals():
+    """Julia lowers ccall((name, lib), ...) only when the tuple is a constant expression: `:literal`, or a symbol
+    interpolated into an @eval'd definition.  A function argument or any other local is a syntax error
+    ("ccall function name and library expression cannot reference local variables") that fails `include`."""
+    loops = eval_loops()
+    assert len(loops) >= 3
+    for m in CCALL.finditer(SHIM):
+        sym, line = m.group(1), SHIM.count("\n", 0, m.start()) + 1
+        if re.fullmatch(r":[a-z0-9_]+", sym):
+            continue
+        im = re.fullmatch(r"\$\(QuoteNode\((\w+)\)\)", sym)
+        assert im, f"line {line}: ccall symbol {sym!r} is neither a literal nor an @eval interpolation"
+        inside = [v for a, b, v in loops if a < m.start() < b]
+        assert inside and im.group(1) in inside[0], f"line {line}: {sym} is not a loop variable of an enclosing @eval loop"
+    assert re.search(r"^const libbaorec\b", SHIM, flags=re.M), "the library name must be a const global"
+
+
+def test_no_splat_and_matching_arity_in_ccalls():
+    """ccall checks the argument count against the type tuple when the call is lowered; a splatted argument cannot
+    be counted.  Every call passes exactly as many expressions as it declares types."""
+    for sym, ret, types, args, line in shim_ccalls():
+        assert not any(a.endswith("...") for a in args), f"line {line}: splatted ccall argument"
+        assert len(args) == len(types), f"line {line}: {len(types)} argument types, {len(args)} arguments"
+
+
+def test_overrides_are_at_least_as_typed_as_the_reference():
+    """An override with an untyped argument where the reference's CuArray method types it (k⃗ / x_vec tuples,
+    SVector boxes, the recon type) is ambiguous with that method instead of more specific."""
+    for name, must in (("iterate!", ["k⃗::Vec3", "β::Float32"]),
+                       ("jacobi!", ["x_vec::Vec3", "box_size::V3", "box_min::V3"]),
+                       ("residual!", ["x_vec::Vec3", "box_size::V3", "box_min::V3"]),
+                       ("vcycle!", ["box_size::V3", "box_min::V3"]),
+                       ("fmg", ["box_size::V3", "box_min::V3"]),
+                       ("smooth!", ["box_size::SVector{3,Float32}"]),
+                       ("cic!", ["box_size::SVector{3,Float32}", "box_min::SVector{3,Float32}"])):
+        mine = [q for q in re.findall(r"function %s\((.*?)\)\n" % re.escape(name), SHIM, flags=re.S)]
+        assert mine, name
+        for q in mine:
+            for need in must:
+                assert need in q, (name, need)
+    # one compute_displacements per recon type; no Vararg reconstructed_* methods
+    assert "compute_displacements(mesh::CuArray{Float32,3}, x::CuVector{Float32}, y::CuVector{Float32},\n" in SHIM
+    assert "recon::$R)" in SHIM and "recon::AbstractRecon)\n    ctx = plan!(mesh" not in SHIM
+    assert "CuArray{Float32}...)" not in SHIM
+    # out-parameters / 3-vectors travel as Vector{Float32} (a Ref of a tuple does not convert to Ptr{Cfloat})
+    assert "Ref((" not in SHIM
+
+
+# loop-generated call sites: the symbols they are instantiated with, read from the loop headers
+def generic_names(pos, var):
+    for a, b, values in eval_loops():
+        if a < pos < b:
+            return [v.lstrip(":") for v in values[var]]
+    raise AssertionError("no enclosing @eval loop")
 
 
 def test_every_ccall_matches_its_prototype():
     protos, calls = c_prototypes(), shim_ccalls()
     assert len(protos) == 60 and len(calls) >= 25
     seen = set()
-    for sym, ret, types, line in calls:
+    starts = [m.start() for m in CCALL.finditer(SHIM)]
+    for (sym, ret, types, args, line), pos in zip(calls, starts):
         if sym.startswith(":"):
             names = [sym[1:]]
         else:
-            names = GENERIC[sym]
+            names = generic_names(pos, re.fullmatch(r"\$\(QuoteNode\((\w+)\)\)", sym).group(1))
             assert len(names) == 2, f"generic ccall at line {line}: expected two instantiations, found {names}"
         for name in names:
             assert name in protos, f"line {line}: {name} is not declared in the header"
