@@ -143,6 +143,69 @@ EXPORT int64_t oc_read_cic_f32(const float *fld, int nx, int ny, int nz, const f
     return bad;
 }
 
+/* ---- TSC (extension, NOT in the reference; same restatement as baorec_oracle.py tsc_cells / tsc_scatter / read_tsc):
+ * g = (p - min) * n / L, centre c = floor(g + 0.5), d = g - c, weights 0.5 (0.5 - d)^2, 0.75 - d^2, 0.5 (0.5 + d)^2.
+ * The scatter is serial over the particles (like cic!); the numpy port loops offset-major instead, so the two meshes
+ * agree to summation order only.  The gather accumulates in the numpy port's order (oz, oy, ox): bit-identical. */
+static inline int tsc_axis(float p, float mn, float L, int n, int wrap, int64_t idx[3], float w[3]) {
+    float g = (p - mn) * (float)n;
+    g = g / L;
+    float c = floorf(g + 0.5f);
+    if (!(c >= -1.0e9f && c <= 1.0e9f)) return 0;
+    float d = g - c;
+    float hm = 0.5f - d, hp = 0.5f + d;
+    w[0] = 0.5f * (hm * hm);
+    w[1] = 0.75f - (d * d);
+    w[2] = 0.5f * (hp * hp);
+    int64_t ic = (int64_t)c;
+    for (int o = 0; o < 3; ++o) {
+        int64_t i = ic + o - 1;
+        if (wrap) { i %= n; if (i < 0) i += n; }
+        else if (i < 0 || i >= n) return 0;
+        idx[o] = i;
+    }
+    return 1;
+}
+
+EXPORT int64_t oc_tsc_scatter_f32(float *rho, int nx, int ny, int nz, const float *x, const float *y, const float *z,
+                                  const float *w, int64_t N, const float *L, const float *mn, int wrap) {
+    int64_t bad = 0;
+    for (int64_t p = 0; p < N; ++p) {
+        int64_t ix[3], iy[3], iz[3];
+        float wx[3], wy[3], wz[3];
+        int ok = tsc_axis(x[p], mn[0], L[0], nx, wrap, ix, wx);
+        ok &= tsc_axis(y[p], mn[1], L[1], ny, wrap, iy, wy);
+        ok &= tsc_axis(z[p], mn[2], L[2], nz, wrap, iz, wz);
+        if (!ok) { ++bad; continue; }
+        for (int oz = 0; oz < 3; ++oz)
+            for (int oy = 0; oy < 3; ++oy)
+                for (int ox = 0; ox < 3; ++ox)
+                    rho[((size_t)iz[oz] * ny + iy[oy]) * nx + ix[ox]] += ((wx[ox] * w[p]) * wy[oy]) * wz[oz];
+    }
+    return bad;
+}
+
+EXPORT int64_t oc_read_tsc_f32(const float *fld, int nx, int ny, int nz, const float *x, const float *y, const float *z,
+                               int64_t N, const float *L, const float *mn, float *out) {
+    int64_t bad = 0;
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+    for (int64_t p = 0; p < N; ++p) {
+        int64_t ix[3], iy[3], iz[3];
+        float wx[3], wy[3], wz[3];
+        int ok = tsc_axis(x[p], mn[0], L[0], nx, 1, ix, wx);
+        ok &= tsc_axis(y[p], mn[1], L[1], ny, 1, iy, wy);
+        ok &= tsc_axis(z[p], mn[2], L[2], nz, 1, iz, wz);
+        if (!ok) { ++bad; out[p] = 0.0f; continue; }
+        float s = 0.0f;
+        for (int oz = 0; oz < 3; ++oz)
+            for (int oy = 0; oy < 3; ++oy)
+                for (int ox = 0; ox < 3; ++ox)
+                    s = s + ((fld[((size_t)iz[oz] * ny + iy[oy]) * nx + ix[ox]] * wx[ox]) * wy[oy]) * wz[oz];
+        out[p] = s;
+    }
+    return bad;
+}
+
 /* ---- k-space passes over a Complex{Float32} half-mesh [nz][ny][nxh] ----------------------------
  * op 0: src/utils.jl:49-52   F *= exp(-0.5 R^2 k^2), exponent / exp / product in Float64 (a = R^2 as Float32)
  * op 1: src/iterative.jl:9-14  F /= k^2 (k^2 == 0 -> 1), F[k=0] = 0

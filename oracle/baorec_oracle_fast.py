@@ -45,6 +45,10 @@ def _bind(lib):
     lib.oc_cic_scatter_f32.argtypes = [_F, i, i, i, _F, _F, _F, _F, i64, _F, _F, i]
     lib.oc_read_cic_f32.restype = i64
     lib.oc_read_cic_f32.argtypes = [_F, i, i, i, _F, _F, _F, i64, _F, _F, i, _F]
+    lib.oc_tsc_scatter_f32.restype = i64
+    lib.oc_tsc_scatter_f32.argtypes = [_F, i, i, i, _F, _F, _F, _F, i64, _F, _F, i]
+    lib.oc_read_tsc_f32.restype = i64
+    lib.oc_read_tsc_f32.argtypes = [_F, i, i, i, _F, _F, _F, i64, _F, _F, _F]
     lib.oc_kspace_c64.restype = None
     lib.oc_kspace_c64.argtypes = [_F, _F, i, i, i, _F, _F, _F, i, i, i, f]
     lib.oc_overdensity_box_f32.restype = None
@@ -80,7 +84,7 @@ def load(threads=None):
     O = importlib.util.module_from_spec(spec)
     sys.modules[spec.name] = O          # dataclasses look their module up while the class body runs
     spec.loader.exec_module(O)
-    N = {k: getattr(O, k) for k in ("cic_scatter", "read_cic", "smooth", "setup_overdensity", "iterate", "jacobi",
+    N = {k: getattr(O, k) for k in ("tsc_scatter", "read_tsc", "cic_scatter", "read_cic", "smooth", "setup_overdensity", "iterate", "jacobi",
                                     "residual", "restrict", "prolong", "displacement_meshes", "read_shifts")}
     f32 = np.float32
 
@@ -111,6 +115,28 @@ def load(threads=None):
                                   0 if formula == "cpu" else 1, _p(out))
         if bad:
             raise O.OutOfBoxError(f"{bad} particle(s) outside the mesh in read_cic")
+        return out
+
+    def tsc_scatter(rho, x, y, z, w, box_size, box_min, wrap=True):
+        if not is32(rho, x, y, z):
+            return N["tsc_scatter"](rho, x, y, z, w, box_size, box_min, wrap)
+        nz, ny, nx = rho.shape
+        w = _f32c(w)
+        L, mn = vec3(box_size), vec3(box_min)
+        bad = lib.oc_tsc_scatter_f32(_p(rho), nx, ny, nz, _p(x), _p(y), _p(z), _p(w), len(x), _p(L), _p(mn), int(bool(wrap)))
+        if bad:
+            raise O.OutOfBoxError(f"{bad} particle(s): TSC stencil leaves the mesh with wrap=False")
+        return rho
+
+    def read_tsc(fld, x, y, z, box_size, box_min, wrap=True):
+        if not is32(fld, x, y, z) or not wrap:
+            return N["read_tsc"](fld, x, y, z, box_size, box_min, wrap)
+        nz, ny, nx = fld.shape
+        out = np.empty(len(x), f32)
+        L, mn = vec3(box_size), vec3(box_min)
+        bad = lib.oc_read_tsc_f32(_p(fld), nx, ny, nz, _p(x), _p(y), _p(z), len(x), _p(L), _p(mn), _p(out))
+        if bad:
+            raise O.OutOfBoxError(f"{bad} particle(s) outside the mesh in read_tsc")
         return out
 
     def kspace(fk, kv, op, axis=0, axis_b=0, a=0.0, out=None):
@@ -239,7 +265,7 @@ def load(threads=None):
         lib.oc_mg_prolong_f32(_p(v1h), _p(v2h), nx, ny, nz)
         return v1h
 
-    for name, fn in dict(cic_scatter=cic_scatter, read_cic=read_cic, smooth=smooth, setup_overdensity=setup_overdensity,
+    for name, fn in dict(tsc_scatter=tsc_scatter, read_tsc=read_tsc, cic_scatter=cic_scatter, read_cic=read_cic, smooth=smooth, setup_overdensity=setup_overdensity,
                          iterate=iterate, displacement_meshes=displacement_meshes, compute_displacements=compute_displacements,
                          compute_displacements_iterative=lambda m, x, y, z, r, formula="cpu": compute_displacements(m, x, y, z, r, formula),
                          compute_displacements_multigrid=lambda m, x, y, z, r, formula="cpu": compute_displacements(m, x, y, z, r, formula),

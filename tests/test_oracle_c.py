@@ -57,6 +57,26 @@ def test_scatter_bit_identical(F, wrap, n, L, lo):
         assert np.array_equal(u32(p), u32(q))        # wrapped positions written back identically
 
 
+@pytest.mark.parametrize("n,L,lo", [(24, 300.0, 0.0), (40, 1373.5, -412.25)])
+def test_tsc_loops(F, n, L, lo):
+    """TSC (extension): the C gather accumulates in the numpy port's order -> identical bits; the C scatter is serial
+    over particles where numpy loops offset-major -> same mesh to summation order, same total to rounding."""
+    pos, w = clustered_box(20000, L, seed=6, lo=lo)
+    bs, bm = np.full(3, L, np.float32), np.full(3, lo, np.float32)
+    ra = O.tsc_scatter(np.zeros((n, n, n), np.float32), *pos, w, bs, bm, True)
+    rb = F.tsc_scatter(np.zeros((n, n, n), np.float32), *pos, w, bs, bm, True)
+    assert rel_rms(rb, ra) < 2e-7 and abs(float(rb.sum(dtype=np.float64)) / float(w.sum(dtype=np.float64)) - 1) < 1e-6
+    fld = np.random.default_rng(3).standard_normal((n, n, n)).astype(np.float32)
+    assert np.array_equal(u32(O.read_tsc(fld, *pos, bs, bm)), u32(F.read_tsc(fld, *pos, bs, bm)))
+    inside = [np.clip(q, lo + 2 * L / n, lo + L - 2 * L / n).astype(np.float32) for q in pos]
+    assert rel_rms(F.tsc_scatter(np.zeros((n, n, n), np.float32), *inside, w, bs, bm, False),
+                   O.tsc_scatter(np.zeros((n, n, n), np.float32), *inside, w, bs, bm, False)) < 2e-7
+    edge = [q.copy() for q in pos]
+    edge[1][0] = np.float32(lo + L - 0.1 * L / n)
+    with pytest.raises(F.OutOfBoxError):
+        F.tsc_scatter(np.zeros((n, n, n), np.float32), *edge, w, bs, bm, False)
+
+
 def test_scatter_out_of_box_raises(F):
     bs, bm = np.full(3, 100.0, np.float32), np.zeros(3, np.float32)
     x, y, z = np.float32([10, -5, 50]), np.float32([10, 20, 50]), np.float32([10, 20, 350])
