@@ -104,7 +104,11 @@ def test_c1_iterative_box_256(B, F, catalog):
         sg = B.read_shifts(rec, *d, mesh, field=fld)
         if fld == "rsd":                                 # x and y components are exactly zero for los = (0, 0, 1)
             assert float(sg[0].abs().max()) == 0.0 and float(sg[1].abs().max()) == 0.0
-            so, sg = so[2:], sg[2:]
+            assert np.abs(so[0]).max() == 0.0 and np.abs(so[1]).max() == 0.0
+            rec_z = {"rel_rms": rel_rms(sg[2].cpu().numpy(), so[2]), "max_abs": maxabs(sg[2].cpu().numpy(), so[2])}
+            REPORT[f"c1_{catalog}_rsd"] = {"z": rec_z}
+            assert rec_z["rel_rms"] < TOL_RMS and rec_z["max_abs"] < TOL_MAX
+            continue
         assert_shifts(f"c1_{catalog}_{fld}", sg, so)
     # the gather alone, same field on both sides: the staged tile branch against read_cic!, bit for bit
     k, f = rec.fft_plan.ctx.launch_counts()
@@ -115,12 +119,23 @@ def test_c1_iterative_box_256(B, F, catalog):
     assert np.array_equal(out.cpu().numpy().view(np.uint32), ref.view(np.uint32))
 
 
-def check_flips_explained(mask_gpu, info, max_frac=2e-5):
+def oracle_mask(delta_gpu, info, max_frac=2e-5):
+    """The threshold decisions the oracle is run with.  The device mesh only shows delta != 0, which is the decision
+    `ran > threshold` EXCEPT in the handful of cells (of 1.3e8) where (dat - alpha ran) rounds to exactly zero.
+    Cells within Float32 noise (2e-3) of the threshold take the device's decision -- those are the legitimate flips;
+    everywhere else the oracle's own decision stands, and a disagreement there must be such an exact zero
+    (device 0, oracle unmasked; checked against the oracle's delta by the caller via the returned index array)."""
     ran, thr = info["ran"].astype(np.float64), info["threshold"]
-    flips = mask_gpu != (ran > thr)
+    mask_gpu = delta_gpu != 0
+    mask_or = ran > thr
+    near = np.abs(ran / thr - 1.0) < 2e-3
+    dis = mask_gpu != mask_or
+    flips = dis & near
+    far = dis & ~near
     assert flips.sum() <= max(40, max_frac * mask_gpu.size), int(flips.sum())
-    assert (np.abs(ran[flips] / thr - 1.0) < 2e-3).all()
-    return int(flips.sum())
+    assert not (far & mask_gpu).any(), "device cell unmasked far below the randoms threshold"
+    assert far.sum() <= 200, int(far.sum())
+    return np.where(near, mask_gpu, mask_or), int(flips.sum()), np.nonzero(far)
 
 
 @pytest.fixture(scope="module")
@@ -143,15 +158,18 @@ def test_c2_iterative_lightcone_512(B, F, lc, mas):
     ds = torch.zeros((n, n, n), dtype=torch.float32, device="cuda")
     B.setup_fft(rec, ds)
     B.setup_overdensity(ds, rec, *gd, gwd, *gr, gwr)
-    mask = ds.cpu().numpy() != 0
+    hds = ds.cpu().numpy()
     orec = F.IterativeRecon(**kw)
     orec.box_size, orec.box_min = F.setup_box(*r, f32(500))
     assert np.array_equal(rec.box_size, orec.box_size) and np.array_equal(rec.box_min, orec.box_min)
     info = {}
     t0 = time.time()
-    ods = F.setup_overdensity(np.zeros((n, n, n), f32), orec, *d, wd, *r, wr, info=info, force_mask=mask)
-    REPORT[f"c2_{mas}_flips"] = check_flips_explained(mask, info)
-    REPORT[f"c2_{mas}_delta_s_rel_rms"] = rel_rms(ds.cpu().numpy(), ods)
+    F.setup_overdensity(np.zeros((n, n, n), f32), orec, *d, wd, *r, wr, info=info)
+    mask, REPORT[f"c2_{mas}_flips"], exact0 = oracle_mask(hds, info)
+    ods = F.setup_overdensity(np.zeros((n, n, n), f32), orec, *d, wd, *r, wr, force_mask=mask)
+    REPORT[f"c2_{mas}_exact_zero_cells"] = int(len(exact0[0]))
+    assert np.abs(ods[exact0]).max(initial=0.0) < 1e-5
+    REPORT[f"c2_{mas}_delta_s_rel_rms"] = rel_rms(hds, ods)
     assert REPORT[f"c2_{mas}_delta_s_rel_rms"] < 2e-4     # 1 / (alpha ran) amplifies Float32 rounding in the sparse edge cells
     odr = ods.copy()
     kv = F.k_vec((n, n, n), orec.box_size, f32)
@@ -193,15 +211,17 @@ def test_c3_multigrid_lightcone_512(B, F, lc):
     delta = torch.zeros((n, n, n), dtype=torch.float32, device="cuda")
     B.setup_fft(rec, delta)
     B.setup_overdensity(delta, rec, *gd, gwd, *gr, gwr)
-    mask = delta.cpu().numpy() != 0
+    hdelta = delta.cpu().numpy()
     orec = F.MultigridRecon(**kw)
     orec.box_size, orec.box_min = F.setup_box(*r, f32(500))
     info = {}
     t0 = time.time()
-    odelta = F.setup_overdensity(np.zeros((n, n, n), f32), orec, *d, wd, *r, wr, info=info, force_mask=mask)
-    REPORT["c3_flips"] = check_flips_explained(mask, info)
+    F.setup_overdensity(np.zeros((n, n, n), f32), orec, *d, wd, *r, wr, info=info)
+    mask, REPORT["c3_flips"], exact0 = oracle_mask(hdelta, info)
+    odelta = F.setup_overdensity(np.zeros((n, n, n), f32), orec, *d, wd, *r, wr, force_mask=mask)
+    assert np.abs(odelta[exact0]).max(initial=0.0) < 1e-5
+    REPORT["c3_delta_rel_rms"] = rel_rms(hdelta, odelta)
     # the solver on the SAME right-hand side (the device's): the 512^3 staged stencil, restriction, prolongation, coarse kernel
-    hdelta = delta.cpu().numpy()
     ophi = F.fmg(hdelta.copy(), np.zeros((n, n, n), f32), orec.box_size, orec.box_min, f32(orec.beta), f32(0.4), 5, 6, None)
     REPORT["c3_oracle_seconds"] = time.time() - t0
     phi = B.fmg(delta, None, rec.box_size, rec.box_min, rec.beta, 0.4, 5, 6, los=None)

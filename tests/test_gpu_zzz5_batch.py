@@ -42,7 +42,9 @@ def test_batch_equals_one_at_a_time(B, O, algorithm, field, positions):
                else B.read_shifts(rec, x, y, z, rec.result_cache, field=field))
         for a in range(3):
             assert np.array_equal(cat[a], (x, y, z)[a])      # same write-back of wrapped positions
-            assert maxabs(got[i][a], ref[a]) < 2e-4           # float reductions of the scatter reorder: rounding only
+            # float reductions of the scatter reorder: rounding only (first hardware run: 2.0e-4 Mpc/h on a multigrid
+            # shift; a reconstructed position additionally carries 2 ulp of a coordinate near L = 1000)
+            assert maxabs(got[i][a], ref[a]) < 5e-4 + (2 * float(np.spacing(f32(L))) if positions else 0.0)
     # and against the oracle for one of them
     x, y, z, w = (a.copy() for a in originals[0])
     orec = (O.IterativeRecon(n_iter=3, **kw) if algorithm == "iterative" else O.MultigridRecon(**kw))
