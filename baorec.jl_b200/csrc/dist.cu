@@ -3,9 +3,15 @@
 //  real space : rank r owns planes [r nz/P, (r+1) nz/P)            slab[zl][y][x]
 //  k space    : rank r owns rows   [r ny/P, (r+1) ny/P), z contiguous   T[yl][ix][iz]
 //
-//  forward FFT = batched 2-D R2C over the local planes -> pack (row copy) -> all-to-all
-//                -> unpack with an (x,z) tile transpose -> batched 1-D C2C along z
-//  inverse FFT = mirror image.  The all-to-all is grouped ncclSend/ncclRecv over NVLink.
+//  Two exchange schemes (option "dist_exchange"):
+//  1 = peer copies (default; needs the receive buffers of all ranks mapped through CUDA IPC, dist.plan does that):
+//      k space is K[z][yl][x] -- the layout the per-peer blocks of the 2-D transform output already have, so there is
+//      NO pack and NO transpose kernel.  forward = batched 2-D R2C over a chunk of planes -> one strided copy per peer
+//      (copy engines, NVLink, no SMs) straight into the peer's K buffer + a flag store -> strided 1-D C2C along z;
+//      inverse mirrors it (the copies land in the peer's plane-layout buffer, the 2-D C2R reads it directly).
+//      Flow control = per-peer sequence flags in peer memory (arrived / buffer-free), no barrier, no NCCL.
+//  0 = NCCL (round 1): k space is T[yl][ix][iz]; 2-D R2C -> pack (row copy) -> grouped ncclSend/ncclRecv
+//      all-to-all -> unpack with an (x,z) tile transpose -> contiguous 1-D C2C along z; inverse mirrors it.
 //  Particles are owned by the slab of their base cell: the scatter writes one ghost plane that
 //  is sent to the next rank and added; the gather reads three halo planes.
 #include <nccl.h>
@@ -42,20 +48,9 @@ rows_kernel(float2* __restrict__ dst, const float2* __restrict__ src, int nzl, i
   for (int x = threadIdx.x; x < xh; x += blockDim.x) d[x] = s[x];
 }
 
-// Fused pack + exchange: the same row copy, but every per-peer block is stored straight into that
-// peer's receive buffer (mapped through CUDA IPC, NVLink stores), at the slot of the sending rank.
 struct PeerTab {
   float2* p[16];
 };
-__global__ void __launch_bounds__(128)
-rows_p2p_kernel(const __grid_constant__ PeerTab dst, const float2* __restrict__ src, int nzl, int ny, int nyl, int xh, int rank) {
-  const unsigned row = blockIdx.x;  // zl * ny + y
-  const int zl = row / ny, y = row - zl * ny;
-  const int peer = y / nyl, yl = y - peer * nyl;
-  const float2* s = src + (size_t)row * xh;
-  float2* d = dst.p[peer] + (((size_t)rank * nzl + zl) * nyl + yl) * xh;
-  for (int x = threadIdx.x; x < xh; x += blockDim.x) d[x] = s[x];
-}
 
 // Batched strided 2-D transpose through shared memory: dst[c][r] = src[r][c].
 struct TrGeom {
@@ -188,21 +183,83 @@ int mg_allgather(baorec_ctx* ctx, const float* send, float* recv, size_t count, 
 
 __global__ void set_scalar_kernel(double* p, double v) { *p = v; }
 
-__global__ void barrier_touch_kernel(int* p) { *p = 1; }
+// ---- peer-copy exchange: flags --------------------------------------------------------------------------------
+// Every rank owns one PeerFlags block (device memory, mapped by all peers through CUDA IPC).  Peers WRITE into it,
+// the owner spins on it: sequence numbers only ever grow, so a late reader never misses a signal.
+//   arrK[s] / arrA[s]   chunks of the forward / inverse exchange that rank s has finished copying into my buffer
+//   freeK[d] / freeA[d] transforms after which rank d has finished reading ITS receive buffer (I may overwrite it)
+struct PeerFlags {
+  unsigned arrK[16], arrA[16], freeK[16], freeA[16];
+  unsigned err, pad[15];
+};
+struct FlagTab {
+  unsigned* p[16];
+};
 
-// all ranks' preceding work on `st` is complete once this returns on every rank's stream
-static int stream_barrier(baorec_ctx* ctx, cudaStream_t st) {
-  if (ctx->nranks == 1) return BAOREC_OK;
-  int pi = prof_begin(ctx, "nccl_barrier", st);
-  BR_NCCL(ncclAllReduce(ctx->d_barrier, ctx->d_barrier, 1, ncclInt, ncclMax, comm_of(ctx), st));
-  prof_end(ctx, pi, st);
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// thread t stores `value` into rank t's flag word for this rank (stream order puts it after the copies it announces)
+__global__ void peer_signal_kernel(const __grid_constant__ FlagTab tab, unsigned value, int P) {
+  const int t = threadIdx.x;
+  if (t < P) {
+    __threadfence_system();
+    st_release_sys(tab.p[t], value);
+  }
+}
+
+// thread t waits until flags[t] >= value (wrap-safe); gives up after ~20 s and raises the error flag instead of
+// hanging the stream forever when a peer died
+__global__ void peer_wait_kernel(const unsigned* flags, unsigned value, int P, unsigned* err) {
+  const int t = threadIdx.x;
+  if (t < P) {
+    const unsigned long long t0 = global_ns();
+    while ((int)(ld_acquire_sys(flags + t) - value) < 0) {
+      __nanosleep(200);
+      if (global_ns() - t0 > 20000000000ull) {
+        atomicExch(err, 1u);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+static PeerFlags* own_flags(const baorec_ctx* ctx) { return (PeerFlags*)ctx->d_flags; }
+
+// which: 0 arrK, 1 arrA, 2 freeK, 3 freeA -- the word of every peer's block that belongs to this rank
+static FlagTab flag_tab(const baorec_ctx* ctx, int which) {
+  FlagTab t;
+  for (int r = 0; r < 16; r++) {
+    PeerFlags* f = (PeerFlags*)ctx->peer_flags[r];
+    unsigned* base = f ? (which == 0 ? f->arrK : which == 1 ? f->arrA : which == 2 ? f->freeK : f->freeA) : nullptr;
+    t.p[r] = base ? base + ctx->rank : nullptr;
+  }
+  return t;
+}
+
+static int peer_signal(baorec_ctx* ctx, int which, unsigned value, cudaStream_t st) {
+  BR_LAUNCH(ctx, peer_signal_kernel, 1, 32, 0, st, flag_tab(ctx, which), value, ctx->nranks);
   return BAOREC_OK;
 }
 
-static PeerTab peer_tab(const baorec_ctx* ctx, int parity) {
-  PeerTab t;
-  for (int i = 0; i < 16; i++) t.p[i] = ctx->peer_recv[parity][i];
-  return t;
+static int peer_wait(baorec_ctx* ctx, int which, unsigned value, cudaStream_t st) {
+  if (value == 0) return BAOREC_OK;
+  PeerFlags* f = own_flags(ctx);
+  const unsigned* w = which == 0 ? f->arrK : which == 1 ? f->arrA : which == 2 ? f->freeK : f->freeA;
+  BR_LAUNCH(ctx, peer_wait_kernel, 1, 32, 0, st, w, value, ctx->nranks, &f->err);
+  return BAOREC_OK;
 }
 
 struct DistBufs {
@@ -213,7 +270,8 @@ static int dist_bufs(baorec_ctx* ctx, DistBufs* b) {
   const size_t slab_c = (size_t)ctx->nz_loc * ctx->ny * ctx->xh;  // == ny_loc * xh * nz
   BR_TRY(need_t(ctx, BUF_CK0, slab_c, &b->A));
   BR_TRY(need_t(ctx, BUF_CK1, slab_c, &b->T));
-  BR_TRY(need_t(ctx, BUF_A2A_SEND, slab_c, &b->S));
+  b->S = nullptr;
+  if (!ctx->p2p) BR_TRY(need_t(ctx, BUF_A2A_SEND, slab_c, &b->S));  // the peer copies need no send staging
   BR_TRY(need_t(ctx, BUF_A2A_RECV, slab_c, &b->R));
   return BAOREC_OK;
 }
@@ -242,7 +300,7 @@ static int all_to_all_chunk(baorec_ctx* ctx, const float2* S, float2* R, size_t 
 static int chunk_setup(baorec_ctx* ctx, int* chunks_out) {
   *chunks_out = 0;
   int C = ctx->opt_a2a_chunks;
-  if (ctx->p2p || C < 2) return BAOREC_OK;
+  if (C < 2) return BAOREC_OK;
   if (C > 8) C = 8;
   while (C > 1 && (ctx->nz_loc % C != 0)) C--;
   if (C < 2) return BAOREC_OK;
@@ -369,10 +427,109 @@ static int dist_c2r_pipelined(baorec_ctx* ctx, float2* T, float* slab, int C, cu
   return BAOREC_OK;
 }
 
+// ---- peer-copy transforms (dist_exchange = 1) ---------------------------------------------------------------------
+// Forward: slab[zl][y][x] -> K[z][yl][x].  The block of plane zl that belongs to rank d, A[zl][d nyl .. (d+1) nyl)[:],
+// is contiguous (nyl * xh values) and its home in rank d's K buffer, RK_d[(rank nzl + zl)][:][:], is contiguous as
+// well, so the whole exchange with one peer is ONE strided copy (height = planes of the chunk) issued to the copy
+// engines on the communication stream; the 2-D transforms of the next chunk run meanwhile.  Then a flag per chunk.
+static int dist_r2c_peer(baorec_ctx* ctx, const float* slab, float2* K, int C, cudaStream_t st) {
+  DistBufs b;
+  BR_TRY(dist_bufs(ctx, &b));
+  const int P = ctx->nranks, nzl = ctx->nz_loc, nyl = ctx->ny_loc, ny = ctx->ny, xh = ctx->xh;
+  if (C < 1) C = 1;
+  const int nzc = nzl / C;
+  const size_t rplane = (size_t)ny * ctx->nx, cplane = (size_t)ny * xh, kplane = (size_t)nyl * xh;
+  cudaStream_t cs = ctx->comm_stream;
+  const unsigned seq = ++ctx->seq_k, base = (seq - 1) * (unsigned)C;
+  cufftHandle plan = C > 1 ? ctx->pc_r2c : ctx->p2d_r2c;
+  BR_CUFFT(cufftSetStream(plan, st));
+  // every destination must have finished reading its K buffer of the previous forward transform
+  BR_CUDA(cudaEventRecord(ctx->ev_a2a[0], st));   // (orders cs after whatever the caller queued: A is about to be overwritten
+  BR_CUDA(cudaStreamWaitEvent(cs, ctx->ev_a2a[0], 0));  //  only by st itself, but RK_d is written from cs)
+  BR_TRY(peer_wait(ctx, 2, seq - 1, cs));
+  for (int c = 0; c < C; c++) {
+    int pi = prof_begin(ctx, "cufft_2d_r2c", st);
+    BR_CUFFT(cufftExecR2C(plan, (cufftReal*)(slab + (size_t)c * nzc * rplane), (cufftComplex*)(b.A + (size_t)c * nzc * cplane)));
+    prof_end(ctx, pi, st);
+    BR_CUDA(cudaEventRecord(ctx->ev_chunk[c], st));
+    BR_CUDA(cudaStreamWaitEvent(cs, ctx->ev_chunk[c], 0));
+    pi = prof_begin(ctx, "peer_copies", cs);
+    for (int k = 0; k < P; k++) {
+      const int d = (ctx->rank + k) % P;  // staggered: at step k every rank writes to a different peer
+      const float2* src = b.A + (size_t)c * nzc * cplane + (size_t)d * kplane;
+      float2* dst = ctx->peer_recv[0][d] + ((size_t)ctx->rank * nzl + (size_t)c * nzc) * kplane;
+      BR_CUDA(cudaMemcpy2DAsync(dst, kplane * sizeof(float2), src, cplane * sizeof(float2), kplane * sizeof(float2),
+                                (size_t)nzc, cudaMemcpyDefault, cs));
+    }
+    prof_end(ctx, pi, cs);
+    BR_TRY(peer_signal(ctx, 0, base + (unsigned)c + 1u, cs));
+  }
+  BR_CUDA(cudaEventRecord(ctx->ev_a2a[1], cs));
+  ctx->n_fft++;
+  BR_TRY(peer_wait(ctx, 0, base + (unsigned)C, st));  // all chunks of all ranks have landed in my K buffer
+  BR_CUFFT(cufftSetStream(ctx->p1d_s, st));
+  int pi = prof_begin(ctx, "cufft_1d_z", st);
+  BR_CUFFT(cufftExecC2C(ctx->p1d_s, (cufftComplex*)ctx->own_recv[0], (cufftComplex*)K, CUFFT_FORWARD));
+  prof_end(ctx, pi, st);
+  ctx->n_fft++;
+  BR_TRY(peer_signal(ctx, 2, seq, st));                    // my K receive buffer may be overwritten
+  BR_CUDA(cudaStreamWaitEvent(st, ctx->ev_a2a[1], 0));     // A may be reused once my own copies have left it
+  return BAOREC_OK;
+}
+
+// Inverse: K[z][yl][x] (destroyed) -> slab.  Rank d's planes are the contiguous block K[d nzl .. (d+1) nzl); they go
+// into rank d's plane-layout buffer RA_d[zl][rank nyl + yl][x] with one strided copy per (peer, chunk); the 2-D C2R of
+// chunk c starts as soon as chunk c has arrived from every rank.
+static int dist_c2r_peer(baorec_ctx* ctx, float2* K, float* slab, int C, cudaStream_t st) {
+  DistBufs b;
+  BR_TRY(dist_bufs(ctx, &b));
+  const int P = ctx->nranks, nzl = ctx->nz_loc, nyl = ctx->ny_loc, ny = ctx->ny, xh = ctx->xh;
+  if (C < 1) C = 1;
+  const int nzc = nzl / C;
+  const size_t rplane = (size_t)ny * ctx->nx, cplane = (size_t)ny * xh, kplane = (size_t)nyl * xh;
+  cudaStream_t cs = ctx->comm_stream;
+  const unsigned seq = ++ctx->seq_a, base = (seq - 1) * (unsigned)C;
+  BR_CUFFT(cufftSetStream(ctx->p1d_s, st));
+  int pi = prof_begin(ctx, "cufft_1d_z", st);
+  BR_CUFFT(cufftExecC2C(ctx->p1d_s, (cufftComplex*)K, (cufftComplex*)K, CUFFT_INVERSE));
+  prof_end(ctx, pi, st);
+  ctx->n_fft++;
+  BR_CUDA(cudaEventRecord(ctx->ev_a2a[0], st));
+  BR_CUDA(cudaStreamWaitEvent(cs, ctx->ev_a2a[0], 0));
+  BR_TRY(peer_wait(ctx, 3, seq - 1, cs));  // every destination has consumed its plane buffer of the previous inverse
+  for (int c = 0; c < C; c++) {
+    pi = prof_begin(ctx, "peer_copies", cs);
+    for (int k = 0; k < P; k++) {
+      const int d = (ctx->rank + k) % P;
+      const float2* src = K + ((size_t)d * nzl + (size_t)c * nzc) * kplane;
+      float2* dst = ctx->peer_recv[1][d] + (size_t)c * nzc * cplane + (size_t)ctx->rank * kplane;
+      BR_CUDA(cudaMemcpy2DAsync(dst, cplane * sizeof(float2), src, kplane * sizeof(float2), kplane * sizeof(float2),
+                                (size_t)nzc, cudaMemcpyDefault, cs));
+    }
+    prof_end(ctx, pi, cs);
+    BR_TRY(peer_signal(ctx, 1, base + (unsigned)c + 1u, cs));
+  }
+  BR_CUDA(cudaEventRecord(ctx->ev_a2a[1], cs));
+  cufftHandle plan = C > 1 ? ctx->pc_c2r : ctx->p2d_c2r;
+  BR_CUFFT(cufftSetStream(plan, st));
+  for (int c = 0; c < C; c++) {
+    BR_TRY(peer_wait(ctx, 1, base + (unsigned)c + 1u, st));
+    pi = prof_begin(ctx, "cufft_2d_c2r", st);
+    BR_CUFFT(cufftExecC2R(plan, (cufftComplex*)(ctx->own_recv[1] + (size_t)c * nzc * cplane),
+                          (cufftReal*)(slab + (size_t)c * nzc * rplane)));
+    prof_end(ctx, pi, st);
+  }
+  ctx->n_fft++;
+  BR_TRY(peer_signal(ctx, 3, seq, st));                    // my plane buffer may be overwritten
+  BR_CUDA(cudaStreamWaitEvent(st, ctx->ev_a2a[1], 0));     // K may be reused once my own copies have left it
+  return BAOREC_OK;
+}
+
 // slab[nz_loc][ny][nx] (real) -> T[ny_loc][xh][nz] (unnormalised forward transform)
 static int dist_r2c(baorec_ctx* ctx, const float* slab, float2* T, cudaStream_t st) {
   int chunks = 0;
   BR_TRY(chunk_setup(ctx, &chunks));
+  if (ctx->p2p) return dist_r2c_peer(ctx, slab, T, chunks, st);
   if (chunks >= 2) return dist_r2c_pipelined(ctx, slab, T, chunks, st);
   DistBufs b;
   BR_TRY(dist_bufs(ctx, &b));
@@ -384,18 +541,8 @@ static int dist_r2c(baorec_ctx* ctx, const float* slab, float2* T, cudaStream_t 
   ctx->n_fft++;
   const size_t blk = (size_t)nzl * nyl * xh;
   const float2* Rsrc = b.R;
-  if (ctx->p2p) {
-    // pack + exchange in one kernel: blocks go straight into the peers' receive buffers
-    const int par = ctx->a2a_parity;
-    ctx->a2a_parity ^= 1;
-    BR_LAUNCH(ctx, rows_p2p_kernel, (unsigned)(nzl * ny), 128, 0, st, peer_tab(ctx, par), b.A, nzl, ny, nyl, xh,
-              ctx->rank);
-    BR_TRY(stream_barrier(ctx, st));
-    Rsrc = ctx->own_recv[par];
-  } else {
-    BR_LAUNCH(ctx, rows_kernel<true>, (unsigned)(nzl * ny), 128, 0, st, b.S, b.A, nzl, ny, nyl, xh, 0u);
-    BR_TRY(all_to_all(ctx, b.S, b.R, blk, st));
-  }
+  BR_LAUNCH(ctx, rows_kernel<true>, (unsigned)(nzl * ny), 128, 0, st, b.S, b.A, nzl, ny, nyl, xh, 0u);
+  BR_TRY(all_to_all(ctx, b.S, b.R, blk, st));
   // T[yl][x][s*nzl + zl] = R[s][zl][yl][x]
   TrGeom t;
   t.rows = nzl;
@@ -421,6 +568,7 @@ static int dist_r2c(baorec_ctx* ctx, const float* slab, float2* T, cudaStream_t 
 static int dist_c2r(baorec_ctx* ctx, float2* T, float* slab, cudaStream_t st) {
   int chunks = 0;
   BR_TRY(chunk_setup(ctx, &chunks));
+  if (ctx->p2p) return dist_c2r_peer(ctx, T, slab, chunks, st);
   if (chunks >= 2) return dist_c2r_pipelined(ctx, T, slab, chunks, st);
   DistBufs b;
   BR_TRY(dist_bufs(ctx, &b));
@@ -444,27 +592,8 @@ static int dist_c2r(baorec_ctx* ctx, float2* T, float* slab, cudaStream_t st) {
   t.dst_b1 = xh;
   dim3 grid(cdiv(nzl, 32), cdiv(xh, 32), P * nyl);
   const float2* Rsrc = b.R;
-  if (ctx->p2p) {
-    // transpose + exchange in one kernel: tile (d, yl) is written into peer d's receive buffer
-    const int par = ctx->a2a_parity;
-    ctx->a2a_parity ^= 1;
-    // tile transpose into per-peer blocks (local), then every block goes to its peer's receive
-    // buffer as ONE contiguous copy over NVLink (256-byte transposed segments stored remotely
-    // reach only ~350 GB/s; contiguous blocks run at link speed)
-    BR_LAUNCH(ctx, transpose_kernel, grid, 256, 0, st, b.S, T, t, PeerTab{}, 0, (size_t)0);
-    int pi = prof_begin(ctx, "p2p_block_copies", st);
-    for (int k = 0; k < P; k++) {
-      const int d = (ctx->rank + k) % P;  // stagger the targets
-      BR_CUDA(cudaMemcpyAsync(ctx->peer_recv[par][d] + (size_t)ctx->rank * blk, b.S + (size_t)d * blk,
-                              blk * sizeof(float2), cudaMemcpyDefault, st));
-    }
-    prof_end(ctx, pi, st);
-    BR_TRY(stream_barrier(ctx, st));
-    Rsrc = ctx->own_recv[par];
-  } else {
-    BR_LAUNCH(ctx, transpose_kernel, grid, 256, 0, st, b.S, T, t, PeerTab{}, 0, (size_t)0);
-    BR_TRY(all_to_all(ctx, b.S, b.R, blk, st));
-  }
+  BR_LAUNCH(ctx, transpose_kernel, grid, 256, 0, st, b.S, T, t, PeerTab{}, 0, (size_t)0);
+  BR_TRY(all_to_all(ctx, b.S, b.R, blk, st));
   BR_LAUNCH(ctx, rows_kernel<false>, (unsigned)(nzl * ny), 128, 0, st, b.A, Rsrc, nzl, ny, nyl, xh, 0u);
   BR_CUFFT(cufftSetStream(ctx->p2d_c2r, st));
   pi = prof_begin(ctx, "cufft_2d_c2r", st);
@@ -472,6 +601,17 @@ static int dist_c2r(baorec_ctx* ctx, float2* T, float* slab, cudaStream_t st) {
   prof_end(ctx, pi, st);
   ctx->n_fft++;
   return BAOREC_OK;
+}
+
+// peer copies are used when the option asks for them AND every rank's buffers and flags are mapped
+void dist_refresh_mode(baorec_ctx* ctx) {
+  bool ok = ctx->opt_dist_exchange != 0 && ctx->d_flags != nullptr;
+  for (int r = 0; r < ctx->nranks && ok; r++) ok = ctx->peer_recv[0][r] && ctx->peer_recv[1][r] && ctx->peer_flags[r];
+  if (ok != ctx->p2p) {  // the k-space layout changes with the scheme: cached k-space meshes are void
+    ctx->kcache_valid = false;
+    ctx->disp_valid = false;
+  }
+  ctx->p2p = ok;
 }
 
 }  // namespace baorec
@@ -518,11 +658,14 @@ int baorec_comm_init(baorec_ctx* ctx, int rank, int nranks, const void* unique_i
 }
 
 static void close_ipc(baorec_ctx* ctx) {
-  for (int k = 0; k < 2; k++)
-    for (int r = 0; r < 16; r++) {
+  for (int r = 0; r < 16; r++) {
+    for (int k = 0; k < 2; k++) {
       if (ctx->peer_recv[k][r] && ctx->peer_recv[k][r] != ctx->own_recv[k]) cudaIpcCloseMemHandle(ctx->peer_recv[k][r]);
       ctx->peer_recv[k][r] = nullptr;
     }
+    if (ctx->peer_flags[r] && ctx->peer_flags[r] != ctx->d_flags) cudaIpcCloseMemHandle(ctx->peer_flags[r]);
+    ctx->peer_flags[r] = nullptr;
+  }
   ctx->p2p = false;
   cudaGetLastError();  // a peer that already exited makes the close fail; nothing to do about it
 }
@@ -530,8 +673,8 @@ static void close_ipc(baorec_ctx* ctx) {
 int baorec_comm_destroy_internal(baorec_ctx* ctx) {
   if (ctx) {
     close_ipc(ctx);
-    if (ctx->d_barrier) cudaFree(ctx->d_barrier);
-    ctx->d_barrier = nullptr;
+    if (ctx->d_flags) cudaFree(ctx->d_flags);
+    ctx->d_flags = nullptr;
   }
   if (ctx && ctx->comm) {
     ncclCommDestroy((ncclComm_t)ctx->comm);
@@ -560,23 +703,33 @@ int baorec_plan_dist(baorec_ctx* ctx, int nx, int ny, int nz, const float box_si
       cufftDestroy(ctx->p2d_r2c);
       cufftDestroy(ctx->p2d_c2r);
       cufftDestroy(ctx->p1d);
+      cufftDestroy(ctx->p1d_s);
       ctx->have_dist_plans = false;
     }
-    size_t w[3] = {0, 0, 0};
+    size_t w[4] = {0, 0, 0, 0};
     int n2[2] = {ny, nx};
     int n1[1] = {nz};
     BR_CUFFT(cufftCreate(&ctx->p2d_r2c));
     BR_CUFFT(cufftCreate(&ctx->p2d_c2r));
     BR_CUFFT(cufftCreate(&ctx->p1d));
+    BR_CUFFT(cufftCreate(&ctx->p1d_s));
     ctx->have_dist_plans = true;
     BR_CUFFT(cufftSetAutoAllocation(ctx->p2d_r2c, 0));
     BR_CUFFT(cufftSetAutoAllocation(ctx->p2d_c2r, 0));
     BR_CUFFT(cufftSetAutoAllocation(ctx->p1d, 0));
+    BR_CUFFT(cufftSetAutoAllocation(ctx->p1d_s, 0));
     BR_CUFFT(cufftMakePlanMany(ctx->p2d_r2c, 2, n2, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, nzl, &w[0]));
     BR_CUFFT(cufftMakePlanMany(ctx->p2d_c2r, 2, n2, nullptr, 1, 0, nullptr, 1, 0, CUFFT_C2R, nzl, &w[1]));
     BR_CUFFT(cufftMakePlanMany(ctx->p1d, 1, n1, nullptr, 1, 0, nullptr, 1, 0, CUFFT_C2C, nyl * (nx / 2 + 1), &w[2]));
+    {
+      // z transform of the K[z][yl][x] layout (peer-copy exchange): nyl * xh interleaved columns, stride = one z plane
+      const int kplane = nyl * (nx / 2 + 1);
+      int emb[1] = {nz};
+      BR_CUFFT(cufftMakePlanMany(ctx->p1d_s, 1, n1, emb, kplane, 1, emb, kplane, 1, CUFFT_C2C, kplane, &w[3]));
+    }
     size_t wmax = w[0] > w[1] ? w[0] : w[1];
     if (w[2] > wmax) wmax = w[2];
+    if (w[3] > wmax) wmax = w[3];
     if (wmax < 16) wmax = 16;
     if (ctx->bufs[BUF_WORK].bytes > wmax) wmax = ctx->bufs[BUF_WORK].bytes;
     void* work = nullptr;
@@ -584,6 +737,7 @@ int baorec_plan_dist(baorec_ctx* ctx, int nx, int ny, int nz, const float box_si
     BR_CUFFT(cufftSetWorkArea(ctx->p2d_r2c, work));
     BR_CUFFT(cufftSetWorkArea(ctx->p2d_c2r, work));
     BR_CUFFT(cufftSetWorkArea(ctx->p1d, work));
+    BR_CUFFT(cufftSetWorkArea(ctx->p1d_s, work));
     if (ctx->have_plans) {  // the single-GPU plans share the (possibly re-allocated) work area
       BR_CUFFT(cufftSetWorkArea(ctx->r2c, work));
       BR_CUFFT(cufftSetWorkArea(ctx->c2r, work));
@@ -596,11 +750,20 @@ int baorec_plan_dist(baorec_ctx* ctx, int nx, int ny, int nz, const float box_si
     void* r1 = ctx->bufs[BUF_A2A_RECV2].p;
     BR_TRY(need_t(ctx, BUF_A2A_RECV, slab_c, &ctx->own_recv[0]));
     BR_TRY(need_t(ctx, BUF_A2A_RECV2, slab_c, &ctx->own_recv[1]));
-    if (r0 != ctx->own_recv[0] || r1 != ctx->own_recv[1]) ctx->p2p = false;  // re-export needed
-    if (!ctx->d_barrier) {
-      BR_CUDA(cudaMalloc(&ctx->d_barrier, sizeof(int)));
-      BR_CUDA(cudaMemset(ctx->d_barrier, 0, sizeof(int)));
+    if (r0 != ctx->own_recv[0] || r1 != ctx->own_recv[1]) {  // re-export needed
+      close_ipc(ctx);
     }
+    if (!ctx->d_flags) {
+      BR_CUDA(cudaMalloc(&ctx->d_flags, sizeof(PeerFlags)));
+      BR_CUDA(cudaMemset(ctx->d_flags, 0, sizeof(PeerFlags)));
+    }
+    if (P == 1) {
+      // a single rank is its own (only) peer: the peer-copy path runs with local copies and local flags
+      ctx->peer_recv[0][0] = ctx->own_recv[0];
+      ctx->peer_recv[1][0] = ctx->own_recv[1];
+      ctx->peer_flags[0] = ctx->d_flags;
+    }
+    dist_refresh_mode(ctx);
   }
   ctx->nz_loc = nzl;
   ctx->z0 = ctx->rank * nzl;
@@ -620,14 +783,21 @@ int baorec_dist_ipc_close(baorec_ctx* ctx) {
   return BAOREC_OK;
 }
 
-int baorec_dist_ipc_export(baorec_ctx* ctx, void* out128) {
+int baorec_dist_ipc_export(baorec_ctx* ctx, void* out192) {
   BR_NEED_DIST(ctx);
-  BR_REQUIRE(out128 != nullptr, "out128 is NULL");
+  BR_REQUIRE(out192 != nullptr, "out192 is NULL");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
-  cudaIpcMemHandle_t h[2];
+  // A new generation of the exchange starts here: every rank calls this before the handles are gathered (a
+  // synchronisation point of the caller), so no peer can have written a flag of the new generation yet.
+  BR_CUDA(cudaDeviceSynchronize());
+  BR_CUDA(cudaMemset(ctx->d_flags, 0, sizeof(PeerFlags)));
+  BR_CUDA(cudaDeviceSynchronize());
+  ctx->seq_k = ctx->seq_a = 0;
+  cudaIpcMemHandle_t h[3];
   BR_CUDA(cudaIpcGetMemHandle(&h[0], ctx->own_recv[0]));
   BR_CUDA(cudaIpcGetMemHandle(&h[1], ctx->own_recv[1]));
-  memcpy(out128, h, sizeof(h));
+  BR_CUDA(cudaIpcGetMemHandle(&h[2], ctx->d_flags));
+  memcpy(out192, h, sizeof(h));
   return BAOREC_OK;
 }
 
@@ -636,20 +806,37 @@ int baorec_dist_ipc_open(baorec_ctx* ctx, const void* all_handles, int nranks) {
   BR_REQUIRE(all_handles != nullptr && nranks == ctx->nranks && nranks <= 16, "ipc_open arguments");
   const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)all_handles;
   close_ipc(ctx);
-  for (int r = 0; r < nranks; r++)
-    for (int k = 0; k < 2; k++) {
-      if (r == ctx->rank) {
-        ctx->peer_recv[k][r] = ctx->own_recv[k];
-        continue;
-      }
-      void* p = nullptr;
-      BR_CUDA(cudaIpcOpenMemHandle(&p, h[2 * r + k], cudaIpcMemLazyEnablePeerAccess));
-      ctx->peer_recv[k][r] = (float2*)p;
+  for (int r = 0; r < nranks; r++) {
+    if (r == ctx->rank) {
+      ctx->peer_recv[0][r] = ctx->own_recv[0];
+      ctx->peer_recv[1][r] = ctx->own_recv[1];
+      ctx->peer_flags[r] = ctx->d_flags;
+      continue;
     }
-  ctx->a2a_parity = 0;
-  ctx->p2p = true;
+    void* p[3] = {nullptr, nullptr, nullptr};
+    for (int k = 0; k < 3; k++) BR_CUDA(cudaIpcOpenMemHandle(&p[k], h[3 * r + k], cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_recv[0][r] = (float2*)p[0];
+    ctx->peer_recv[1][r] = (float2*)p[1];
+    ctx->peer_flags[r] = p[2];
+  }
+  dist_refresh_mode(ctx);
   return BAOREC_OK;
 }
+
+// the wait kernels raise PeerFlags::err instead of spinning forever when a peer never signals
+static int peer_check(baorec_ctx* ctx, cudaStream_t st) {
+  if (!ctx->p2p || !ctx->d_flags) return BAOREC_OK;
+  unsigned e = 0;
+  BR_CUDA(cudaMemcpyAsync(&e, &own_flags(ctx)->err, sizeof(e), cudaMemcpyDeviceToHost, st));
+  BR_CUDA(cudaStreamSynchronize(st));
+  if (e) {
+    set_error("peer-copy exchange: a rank never signalled (20 s timeout); results are invalid");
+    return BAOREC_ERR_NCCL;
+  }
+  return BAOREC_OK;
+}
+
+int baorec_dist_exchange_mode(const baorec_ctx* ctx) { return ctx != nullptr && ctx->p2p ? 1 : 0; }
 
 int baorec_slab_range(const baorec_ctx* ctx, int* z_lo, int* nz_loc) {
   BR_REQUIRE(ctx != nullptr && ctx->dist, "not a distributed plan");
@@ -666,6 +853,236 @@ int baorec_slab_owner_f32(baorec_ctx* ctx, const float* d_z, int64_t n, int32_t*
   BR_LAUNCH(ctx, slab_owner_kernel, cdiv((size_t)n, 256), 256, 0, (cudaStream_t)stream, d_z, n, ctx->mn[2], ctx->L[2],
             ctx->nz, ctx->nz_loc, d_owner);
   return BAOREC_OK;
+}
+
+// ---- particle sharding by slab ------------------------------------------------------------------------------------
+// "particle redistribution by slab is one bucketed all-to-all(v)".  Reference precedent:
+// send_to_relevant_process, src/mas.jl:112-140 (unfinished there).  Every rank passes ANY part of the catalog; the
+// owner of a particle is the slab of its cic! base plane (slab_owner_kernel's arithmetic).  Device counting sort by
+// owner (block-local ranking in shared memory, one global reservation per block and owner), the P x (P+1) count
+// matrix all-gathered (the extra column carries the out-of-box counts so that every rank fails together), then one
+// grouped ncclSend / ncclRecv per column and peer.  The map of original index -> send position stays on the sender,
+// so results computed in slab order travel back the same way and land in the caller's order (baorec_unshard_f32).
+constexpr int SHARD_THREADS = 256, SHARD_ITEMS = 8;
+
+__device__ __forceinline__ int slab_owner_of(float p, float mn, float L, float mn0, float L0, int nz, int nzl) {
+  if (__fsub_rn(p, mn0) > L0) p = __fsub_rn(p, L0);  // upper-face wrap of cic! (axis-1 box for every axis, src/mas.jl:8-10)
+  float g = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(p, mn), (float)nz), L), 1.0f);
+  int c0 = (int)floorf(g);
+  if (c0 == nz + 1) c0 = 1;
+  return (g >= 1.0f && c0 >= 1 && c0 <= nz) ? (c0 - 1) / nzl : 16;  // 16 = out of box
+}
+
+// cnt[0..15] += particles per owner, cnt[16] += out-of-box
+__global__ void __launch_bounds__(SHARD_THREADS)
+shard_count_kernel(const float* __restrict__ z, int64_t n, float mn, float L, float mn0, float L0, int nz, int nzl,
+                   unsigned long long* __restrict__ cnt) {
+  __shared__ unsigned h[17];
+  if (threadIdx.x < 17) h[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * (SHARD_THREADS * SHARD_ITEMS);
+#pragma unroll
+  for (int k = 0; k < SHARD_ITEMS; k++) {
+    int64_t i = base + k * SHARD_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&h[slab_owner_of(z[i], mn, L, mn0, L0, nz, nzl)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 17 && h[threadIdx.x]) atomicAdd(cnt + threadIdx.x, (unsigned long long)h[threadIdx.x]);
+}
+
+// cursor[o] starts at the offset of owner o in the send order; out-of-box particles are dropped (map = ~0)
+__global__ void __launch_bounds__(SHARD_THREADS)
+shard_reorder_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z,
+                     const float* __restrict__ w, int64_t n, float mn, float L, float mn0, float L0, int nz, int nzl,
+                     unsigned long long* __restrict__ cursor, float* __restrict__ sx, float* __restrict__ sy,
+                     float* __restrict__ sz, float* __restrict__ sw, unsigned* __restrict__ map) {
+  __shared__ unsigned h[17];
+  __shared__ unsigned long long start[17];
+  if (threadIdx.x < 17) h[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * (SHARD_THREADS * SHARD_ITEMS);
+  int own[SHARD_ITEMS];
+  unsigned rank_in[SHARD_ITEMS];
+  float pz[SHARD_ITEMS];
+#pragma unroll
+  for (int k = 0; k < SHARD_ITEMS; k++) {
+    int64_t i = base + k * SHARD_THREADS + threadIdx.x;
+    own[k] = -1;
+    if (i < n) {
+      pz[k] = z[i];
+      own[k] = slab_owner_of(pz[k], mn, L, mn0, L0, nz, nzl);
+      rank_in[k] = atomicAdd(&h[own[k]], 1u);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16 && h[threadIdx.x]) start[threadIdx.x] = atomicAdd(cursor + threadIdx.x, (unsigned long long)h[threadIdx.x]);
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < SHARD_ITEMS; k++) {
+    int64_t i = base + k * SHARD_THREADS + threadIdx.x;
+    if (own[k] < 0) continue;
+    if (own[k] == 16) {
+      map[i] = 0xffffffffu;
+      continue;
+    }
+    const size_t slot = (size_t)(start[own[k]] + rank_in[k]);
+    sx[slot] = x[i];
+    sy[slot] = y[i];
+    sz[slot] = pz[k];
+    sw[slot] = w[i];
+    map[i] = (unsigned)slot;
+  }
+}
+
+__global__ void shard_cursor_kernel(unsigned long long* cnt) {
+  // cursors [17 .. 33) = exclusive prefix sum of the per-owner counts
+  if (threadIdx.x == 0) {
+    unsigned long long s = 0;
+    for (int o = 0; o < 16; o++) {
+      cnt[17 + o] = s;
+      s += cnt[o];
+    }
+  }
+}
+
+// out[i] = back[map[i]] for up to three columns
+__global__ void __launch_bounds__(256)
+unshard_gather_kernel(const unsigned* __restrict__ map, int64_t n, const float* __restrict__ ba, const float* __restrict__ bb,
+                      const float* __restrict__ bc, float* __restrict__ oa, float* __restrict__ ob, float* __restrict__ oc) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned s = map[i];
+  if (s == 0xffffffffu) return;
+  if (oa) oa[i] = ba[s];
+  if (ob) ob[i] = bb[s];
+  if (oc) oc[i] = bc[s];
+}
+
+static int shard_catalog(baorec_ctx* ctx, int slot, const float* x, const float* y, const float* z, const float* w,
+                         int64_t n, float** ox, float** oy, float** oz, float** ow, int64_t* n_local, cudaStream_t st) {
+  const int P = ctx->nranks;
+  BR_REQUIRE(P <= 16, "at most 16 ranks");
+  BR_REQUIRE(n < ((int64_t)1 << 32) - 1, "at most 2^32 - 2 particles per rank and call");
+  baorec_ctx::ShardState& S = ctx->shard[slot];
+  S.valid = false;
+  if (!ctx->d_shard_cnt) BR_CUDA(cudaMalloc(&ctx->d_shard_cnt, sizeof(unsigned long long) * (40 + 17 * 16)));
+  unsigned long long* cnt = ctx->d_shard_cnt;
+  BR_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * 40, st));
+  const unsigned grid = cdiv((size_t)(n > 0 ? n : 1), SHARD_THREADS * SHARD_ITEMS);
+  if (n > 0)
+    BR_LAUNCH(ctx, shard_count_kernel, grid, SHARD_THREADS, 0, st, z, n, ctx->mn[2], ctx->L[2], ctx->mn[0], ctx->L[0], ctx->nz,
+              ctx->nz_loc, cnt);
+  BR_LAUNCH(ctx, shard_cursor_kernel, 1, 32, 0, st, cnt);
+  // count matrix: row s = rank s's 17 counts
+  unsigned long long* all = cnt + 40;
+  if (P > 1) {
+    BR_NCCL(ncclAllGather(cnt, all, 17, ncclUint64, comm_of(ctx), st));
+  } else {
+    BR_CUDA(cudaMemcpyAsync(all, cnt, 17 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+  }
+  unsigned long long h[17 * 16];
+  BR_CUDA(cudaMemcpyAsync(h, all, sizeof(unsigned long long) * 17 * P, cudaMemcpyDeviceToHost, st));
+  BR_CUDA(cudaStreamSynchronize(st));
+  unsigned long long oob = 0;
+  for (int s = 0; s < P; s++) oob += h[17 * s + 16];
+  if (oob) {  // every rank sees the same matrix: all of them return the error together
+    set_error("shard_catalog: %llu particle(s) outside the box over all ranks (the reference would raise BoundsError)", oob);
+    return BAOREC_ERR_OUT_OF_BOX;
+  }
+  int64_t so = 0, ro = 0;
+  for (int r = 0; r < P; r++) {
+    S.send_cnt[r] = (int64_t)h[17 * ctx->rank + r];
+    S.send_off[r] = so;
+    so += S.send_cnt[r];
+    S.recv_cnt[r] = (int64_t)h[17 * r + ctx->rank];
+    S.recv_off[r] = ro;
+    ro += S.recv_cnt[r];
+  }
+  S.n = n;
+  S.n_local = ro;
+  float *send, *recv;
+  unsigned* map;
+  const size_t ns = (size_t)(n > 0 ? n : 1), nl = (size_t)(ro > 0 ? ro : 1);
+  BR_TRY(need_t(ctx, slot ? BUF_SHARD_SEND2 : BUF_SHARD_SEND, 4 * ns, &send));
+  BR_TRY(need_t(ctx, slot ? BUF_SHARD_RECV2 : BUF_SHARD_RECV, 4 * nl, &recv));
+  BR_TRY(need_t(ctx, slot ? BUF_SHARD_MAP2 : BUF_SHARD_MAP, ns, &map));
+  if (n > 0)
+    BR_LAUNCH(ctx, shard_reorder_kernel, grid, SHARD_THREADS, 0, st, x, y, z, w, n, ctx->mn[2], ctx->L[2], ctx->mn[0], ctx->L[0],
+              ctx->nz, ctx->nz_loc, cnt + 17, send, send + ns, send + 2 * ns, send + 3 * ns, map);
+  if (P > 1) {
+    int pi = prof_begin(ctx, "nccl_shard_all_to_all_v", st);
+    BR_NCCL(ncclGroupStart());
+    for (int r = 0; r < P; r++)
+      for (int c = 0; c < 4; c++) {
+        if (S.send_cnt[r]) BR_NCCL(ncclSend(send + c * ns + S.send_off[r], (size_t)S.send_cnt[r], ncclFloat, r, comm_of(ctx), st));
+        if (S.recv_cnt[r]) BR_NCCL(ncclRecv(recv + c * nl + S.recv_off[r], (size_t)S.recv_cnt[r], ncclFloat, r, comm_of(ctx), st));
+      }
+    BR_NCCL(ncclGroupEnd());
+    prof_end(ctx, pi, st);
+  } else {
+    for (int c = 0; c < 4 && n > 0; c++)
+      BR_CUDA(cudaMemcpyAsync(recv + c * nl, send + c * ns, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  *ox = recv;
+  *oy = recv + nl;
+  *oz = recv + 2 * nl;
+  *ow = recv + 3 * nl;
+  *n_local = ro;
+  S.valid = true;
+  return BAOREC_OK;
+}
+
+// columns a, b, c (n_local values each, slab order) -> oa, ob, oc (n values each, the order of the arrays that were sharded)
+static int unshard(baorec_ctx* ctx, int slot, const float* a, const float* b, const float* c, float* oa, float* ob, float* oc,
+                   cudaStream_t st) {
+  const int P = ctx->nranks;
+  baorec_ctx::ShardState& S = ctx->shard[slot];
+  if (!S.valid) {
+    set_error("baorec_unshard_f32: no routing table for slot %d (call baorec_shard_catalog_f32 first)", slot);
+    return BAOREC_ERR_INVALID;
+  }
+  const size_t ns = (size_t)(S.n > 0 ? S.n : 1);
+  float* back = (float*)ctx->bufs[slot ? BUF_SHARD_SEND2 : BUF_SHARD_SEND].p;  // the send staging is free again: 4 ns floats
+  const unsigned* map = (const unsigned*)ctx->bufs[slot ? BUF_SHARD_MAP2 : BUF_SHARD_MAP].p;
+  const float* src[3] = {a, b, c};
+  if (P > 1) {
+    int pi = prof_begin(ctx, "nccl_unshard_all_to_all_v", st);
+    BR_NCCL(ncclGroupStart());
+    for (int r = 0; r < P; r++)
+      for (int k = 0; k < 3; k++) {
+        if (!src[k]) continue;
+        if (S.recv_cnt[r]) BR_NCCL(ncclSend(src[k] + S.recv_off[r], (size_t)S.recv_cnt[r], ncclFloat, r, comm_of(ctx), st));
+        if (S.send_cnt[r]) BR_NCCL(ncclRecv(back + k * ns + S.send_off[r], (size_t)S.send_cnt[r], ncclFloat, r, comm_of(ctx), st));
+      }
+    BR_NCCL(ncclGroupEnd());
+    prof_end(ctx, pi, st);
+  } else {
+    for (int k = 0; k < 3; k++)
+      if (src[k] && S.n > 0)
+        BR_CUDA(cudaMemcpyAsync(back + k * ns, src[k], (size_t)S.n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  if (S.n > 0)
+    BR_LAUNCH(ctx, unshard_gather_kernel, cdiv((size_t)S.n, 256), 256, 0, st, map, S.n, back, back + ns, back + 2 * ns,
+              a ? oa : nullptr, b ? ob : nullptr, c ? oc : nullptr);
+  return BAOREC_OK;
+}
+
+int baorec_shard_catalog_f32(baorec_ctx* ctx, int slot, const float* d_x, const float* d_y, const float* d_z,
+                             const float* d_w, int64_t n, float** d_sx, float** d_sy, float** d_sz, float** d_sw,
+                             int64_t* n_local, baorec_stream stream) {
+  BR_NEED_DIST(ctx);
+  BR_REQUIRE(slot == 0 || slot == 1, "slot is 0 (data) or 1 (randoms)");
+  BR_REQUIRE(n >= 0 && (n == 0 || (d_x && d_y && d_z && d_w)), "particle arrays");
+  BR_REQUIRE(d_sx && d_sy && d_sz && d_sw && n_local, "NULL output argument");
+  return shard_catalog(ctx, slot, d_x, d_y, d_z, d_w, n, d_sx, d_sy, d_sz, d_sw, n_local, (cudaStream_t)stream);
+}
+
+int baorec_unshard_f32(baorec_ctx* ctx, int slot, const float* d_a, const float* d_b, const float* d_c, float* d_oa,
+                       float* d_ob, float* d_oc, baorec_stream stream) {
+  BR_NEED_DIST(ctx);
+  BR_REQUIRE(slot == 0 || slot == 1, "slot is 0 (data) or 1 (randoms)");
+  BR_REQUIRE((!d_a || d_oa) && (!d_b || d_ob) && (!d_c || d_oc), "an input column without its output column");
+  return unshard(ctx, slot, d_a, d_b, d_c, d_oa, d_ob, d_oc, (cudaStream_t)stream);
 }
 
 int baorec_dist_r2c_f32(baorec_ctx* ctx, const float* d_slab, float* d_kslab_t, baorec_stream stream) {
@@ -879,6 +1296,7 @@ int baorec_run_dist_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, 
     }
   }
   BR_TRY(check_oob(ctx, st, "run_dist (particles must lie in this rank's slab)"));
+  BR_TRY(peer_check(ctx, st));
   ctx->kcache_valid = true;
   return BAOREC_OK;
 }
@@ -929,7 +1347,59 @@ int baorec_read_shifts_dist_f32(baorec_ctx* ctx, const baorec_params* p, const f
   if (s != BAOREC_OK) return s;
   ctx->disp_valid = true;
   ctx->disp_algo = -1;  // marks slab-layout displacement meshes
-  return check_oob(ctx, st, "read_shifts_dist (particles must lie in this rank's slab)");
+  BR_TRY(check_oob(ctx, st, "read_shifts_dist (particles must lie in this rank's slab)"));
+  return peer_check(ctx, st);
+}
+
+// One reconstruction from an UNSHARDED catalog: every rank passes any part of the data (and randoms) catalog as
+// device arrays; the library shards by slab, runs run! + read_shifts / reconstructed_positions on the slabs and routes
+// the per-particle results back into the caller's order.  The box must have been planned (with randoms: from
+// setup_box over all ranks, src/recon.jl:172,253).  The result mesh slab stays in the library (BUF_CACHE).
+int baorec_reconstruct_dist_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, const float* d_x, const float* d_y,
+                                const float* d_z, const float* d_w, int64_t n, const float* d_rx, const float* d_ry,
+                                const float* d_rz, const float* d_rw, int64_t n_ran, int has_randoms, int field,
+                                int positions, float* d_ox, float* d_oy, float* d_oz, baorec_stream stream) {
+  BR_NEED_DIST(ctx);
+  BR_REQUIRE(p != nullptr, "params is NULL");
+  BR_REQUIRE(n >= 0 && (n == 0 || (d_x && d_y && d_z && d_w && d_ox && d_oy && d_oz)), "particle arrays");
+  BR_REQUIRE(n_ran >= 0 && (n_ran == 0 || (d_rx && d_ry && d_rz && d_rw)), "randoms arrays");
+  cudaStream_t st = (cudaStream_t)stream;
+  float *sx, *sy, *sz, *sw, *rx = nullptr, *ry = nullptr, *rz = nullptr, *rw = nullptr;
+  int64_t nl = 0, nrl = 0;
+  BR_TRY(shard_catalog(ctx, 0, d_x, d_y, d_z, d_w, n, &sx, &sy, &sz, &sw, &nl, st));
+  if (has_randoms) BR_TRY(shard_catalog(ctx, 1, d_rx, d_ry, d_rz, d_rw, n_ran, &rx, &ry, &rz, &rw, &nrl, st));
+  float* mesh;
+  BR_TRY(need_t(ctx, BUF_CACHE, (size_t)ctx->nz_loc * ctx->ny * ctx->nx, &mesh));
+  BR_TRY(baorec_run_dist_f32(ctx, p, algorithm, sx, sy, sz, sw, nl, rx, ry, rz, rw, nrl, has_randoms, mesh, stream));
+  float* out;
+  const size_t no = (size_t)(nl > 0 ? nl : 1);
+  BR_TRY(need_t(ctx, BUF_SHARD_OUT, 3 * no, &out));
+  BR_TRY(baorec_read_shifts_dist_f32(ctx, p, sx, sy, sz, nl, field, positions, out, out + no, out + 2 * no, stream));
+  return unshard(ctx, 0, out, out + no, out + 2 * no, d_ox, d_oy, d_oz, st);
+}
+
+// The same with HOST arrays (this rank's share of the catalog; pinned memory copies at PCIe speed): upload, the call
+// above, download.  This is what a host program that holds an unsharded catalog calls on every rank.
+int baorec_reconstruct_dist_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, const float* h_x,
+                                     const float* h_y, const float* h_z, const float* h_w, int64_t n, int field,
+                                     int positions, float* h_ox, float* h_oy, float* h_oz) {
+  BR_NEED_DIST(ctx);
+  BR_REQUIRE(n >= 0 && (n == 0 || (h_x && h_y && h_z && h_w && h_ox && h_oy && h_oz)), "particle arrays");
+  cudaStream_t st = ctx->own_stream;
+  const size_t nn = (size_t)(n > 0 ? n : 1);
+  float *dp, *dout;
+  BR_TRY(need_t(ctx, BUF_PART, 4 * nn, &dp));
+  BR_TRY(need_t(ctx, BUF_OUT, 3 * nn, &dout));
+  const float* hs[4] = {h_x, h_y, h_z, h_w};
+  for (int c = 0; c < 4 && n > 0; c++)
+    BR_CUDA(cudaMemcpyAsync(dp + c * nn, hs[c], (size_t)n * sizeof(float), cudaMemcpyHostToDevice, st));
+  BR_TRY(baorec_reconstruct_dist_f32(ctx, p, algorithm, dp, dp + nn, dp + 2 * nn, dp + 3 * nn, n, nullptr, nullptr, nullptr,
+                                     nullptr, 0, 0, field, positions, dout, dout + nn, dout + 2 * nn, (baorec_stream)st));
+  float* hd[3] = {h_ox, h_oy, h_oz};
+  for (int c = 0; c < 3 && n > 0; c++)
+    BR_CUDA(cudaMemcpyAsync(hd[c], dout + c * nn, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  BR_CUDA(cudaStreamSynchronize(st));
+  return BAOREC_OK;
 }
 
 }  // extern "C"

@@ -86,6 +86,13 @@ enum BufId {
   BUF_MGD,      // multigrid level hierarchy of the slab-decomposed solver
   BUF_DET,      // 64-bit fixed-point accumulator of the deterministic scatter
   BUF_PK,       // multipole estimator: window tables + per-bin Float64 sums
+  BUF_SHARD_SEND,   // particle sharding, data catalog: columns grouped by destination rank (then: results coming back)
+  BUF_SHARD_RECV,   //   this rank's slab particles (x, y, z, w columns)
+  BUF_SHARD_MAP,    //   position of every original particle in the send order
+  BUF_SHARD_SEND2,  // the same three for the randoms catalog
+  BUF_SHARD_RECV2,
+  BUF_SHARD_MAP2,
+  BUF_SHARD_OUT,    // per-particle results in slab order before they travel back
   BUF_COUNT
 };
 
@@ -213,11 +220,23 @@ struct baorec_ctx {
   bool dist = false;
   int nz_loc = 0, z0 = 0, ny_loc = 0, y0 = 0;
   // peer-to-peer transposes: recv buffers of every rank mapped through CUDA IPC (double-buffered)
+  // peer-copy exchange (dist.cu): [0] = K-layout receive buffer (forward), [1] = plane-layout receive buffer
+  // (inverse) of every rank, and every rank's flag block, mapped through CUDA IPC
   bool p2p = false;
+  int opt_dist_exchange = 1;  // 1 = peer copies + flags (default), 0 = pack / transpose kernels + NCCL all-to-all
   float2* peer_recv[2][16] = {};
   float2* own_recv[2] = {nullptr, nullptr};
-  int a2a_parity = 0;
-  int* d_barrier = nullptr;
+  void* peer_flags[16] = {};
+  void* d_flags = nullptr;
+  unsigned seq_k = 0, seq_a = 0;  // forward / inverse transforms issued since the flags were reset (same on every rank)
+  // particle sharding by slab (baorec_shard_catalog_f32): routing tables of the last call per slot (0 data, 1 randoms)
+  struct ShardState {
+    bool valid = false;
+    int64_t n = 0, n_local = 0;            // particles passed in / particles of this rank's slab
+    int64_t send_cnt[16] = {}, send_off[16] = {};   // per destination rank, in the send order
+    int64_t recv_cnt[16] = {}, recv_off[16] = {};   // per source rank, in the slab order
+  } shard[2];
+  unsigned long long* d_shard_cnt = nullptr;  // [0..15] per-owner counts, [16] out-of-box, [17..33] cursors; [40..] gathered
   // displacement meshes (BUF_RX/RY/RZ) of the cached result, kept across read_shifts /
   // reconstructed_positions calls (the examples read data, randoms-sym and randoms-iso back from
   // one reconstruction: examples/simulation.jl:32-35) so that only the first call pays for the transforms
@@ -227,7 +246,7 @@ struct baorec_ctx {
   const float* mg_result_mesh = nullptr;  // phi produced by the last reconstructed_potential! on this context
   bool kcache_potential = false;  // BUF_CKCACHE holds phi_k (MultigridRecon) instead of delta_k
   int slab_mode = 0;  // 0: whole mesh; 1: scatter into a slab (+1 ghost plane); 2: gather from a slab (+3 halo planes)
-  cufftHandle p2d_r2c = 0, p2d_c2r = 0, p1d = 0;
+  cufftHandle p2d_r2c = 0, p2d_c2r = 0, p1d = 0, p1d_s = 0;  // p1d_s: strided z transform of the K[z][yl][x] layout
   bool have_dist_plans = false;
   // pipelined slab transposes: the local planes are processed in opt_a2a_chunks chunks so that the
   // all-to-all of chunk c (comm_stream) overlaps the 2-D transforms / pack / unpack of its neighbours
@@ -344,6 +363,7 @@ int mg_fmg_dist(baorec_ctx* ctx, float* f_slab, float** result, float beta, floa
 // dist.cu: both halo planes of a slab-layout buffer (ring neighbours, periodic); all-gather of slabs
 int mg_halo_exchange(baorec_ctx* ctx, float* buf, size_t plane, int nzl, cudaStream_t st);
 int mg_allgather(baorec_ctx* ctx, const float* send, float* recv, size_t count, cudaStream_t st);
+void dist_refresh_mode(baorec_ctx* ctx);  // re-evaluates ctx->p2p (peer-copy exchange usable?) after an option / mapping change
 
 #define BR_NEED_PLAN(ctx)                                        \
   do {                                                           \

@@ -13,6 +13,7 @@ struct KGeom {
   const float* ky;
   const float* kz;
   int xh, ny, nz;
+  int y0;  // global index of the first row held (0 on one GPU; the y slab's offset in the distributed K[z][yl][x] layout)
 };
 
 static KGeom kgeom_of(const baorec_ctx* ctx) {
@@ -23,6 +24,7 @@ static KGeom kgeom_of(const baorec_ctx* ctx) {
   g.xh = ctx->xh;
   g.ny = ctx->ny;
   g.nz = ctx->nz;
+  g.y0 = 0;
   return g;
 }
 
@@ -50,6 +52,7 @@ __global__ void __launch_bounds__(KS_THREADS) kspace_kernel(KGeom g, const float
     if (p < plane) {
       unsigned iy = p / (unsigned)g.xh;
       unsigned ix = p - iy * (unsigned)g.xh;
+      iy += (unsigned)g.y0;  // g.ny rows are held, rows y0 .. y0 + ny - 1 of the mesh
       op.apply(off + p, v[u], __ldg(g.kx + ix), __ldg(g.ky + iy), kz, (ix | iy | (unsigned)iz) == 0u, (int)ix, (int)iy, iz);
     }
   }
@@ -374,6 +377,16 @@ kspace_kernel_t(KGeom g, int y0, const float2* __restrict__ in, Op op) {
 
 template <class Op>
 static int run_kspace_t(baorec_ctx* ctx, const float2* in, Op op, cudaStream_t st) {
+  if (ctx->p2p) {
+    // peer-copy exchange: K[z][yl][x] -- the single-GPU layout restricted to this rank's rows
+    KGeom g = kgeom_of(ctx);
+    g.ny = ctx->ny_loc;
+    g.y0 = ctx->y0;
+    size_t kplane = (size_t)ctx->xh * ctx->ny_loc;
+    dim3 grid(cdiv(kplane, KS_THREADS * KS_UNROLL), ctx->nz);
+    BR_LAUNCH_NAMED(ctx, Op::name(), kspace_kernel<Op>, grid, KS_THREADS, 0, st, g, in, op);
+    return BAOREC_OK;
+  }
   size_t plane = (size_t)ctx->xh * ctx->nz;
   dim3 grid(cdiv(plane, KS_THREADS * KS_UNROLL), ctx->ny_loc);
   BR_LAUNCH_NAMED(ctx, Op::name(), kspace_kernel_t<Op>, grid, KS_THREADS, 0, st, kgeom_of(ctx), ctx->y0, in, op);

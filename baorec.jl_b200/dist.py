@@ -38,29 +38,106 @@ def shard_catalog(x, y, z, w, box_size, box_min, nz, world):
     return [tuple(a[own == r] for a in (x, y, z, w)) for r in range(world)]
 
 
-def exchange_catalog(x, y, z, w, box_size, box_min, nz, group=None):
-    """Every rank holds an arbitrary part of the catalog (torch tensors on CPU or GPU); after the
-    call it holds exactly the particles of its own slab.  One all_to_all_single per column."""
+def exchange_catalog_host(x, y, z, w, box_size, box_min, nz, group=None):
+    """The routing of baorec_shard_catalog_f32 restated with torch.distributed collectives on CPU (or CUDA) tensors --
+    the gloo-testable statement of the scheme, not the product path: owner per particle, P x (P+1) count matrix
+    all-gathered (last column = out-of-box counts, so that EVERY rank raises when ANY rank holds an out-of-box
+    particle instead of leaving the others blocked in the collective), columns grouped by destination, one
+    all_to_all_single per column.  Returns (x, y, z, w of this rank's slab, route) with route for unshard_host."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    own = torch.from_numpy(owner_of_z(z.cpu().numpy(), box_min[2], box_size[2], nz, world, box_min[0], box_size[0]))
-    if (own < 0).any():
-        raise L.OutOfBoxError(L.ERR_OUT_OF_BOX, "particle(s) outside the box")
-    order = torch.argsort(own, stable=True).to(x.device)
-    counts = torch.bincount(own, minlength=world).to(torch.int64)
-    recv_counts = torch.empty_like(counts)
-    cdev = counts.to(x.device)
-    rdev = torch.empty_like(cdev)
-    dist.all_to_all_single(rdev, cdev, group=group)
-    recv_counts = rdev.cpu()
+    own = torch.from_numpy(owner_of_z(z.cpu().numpy(), box_min[2], box_size[2], nz, world, box_min[0], box_size[0])).long()
+    row = torch.bincount(torch.where(own < 0, torch.full_like(own, world), own), minlength=world + 1)[: world + 1].to(torch.int64)
+    rows = [torch.empty_like(row) for _ in range(world)]
+    dist.all_gather(rows, row.to(x.device), group=group)
+    mat = torch.stack([r.cpu() for r in rows])                       # mat[s, d] = particles rank s sends to rank d
+    if int(mat[:, world].sum()) > 0:
+        raise L.OutOfBoxError(L.ERR_OUT_OF_BOX, f"{int(mat[:, world].sum())} particle(s) outside the box over all ranks")
+    rank = dist.get_rank(group)
+    order = torch.argsort(own, stable=True)
+    send_cnt, recv_cnt = mat[rank, :world].tolist(), mat[:world, rank].tolist()
     outs = []
     for col in (x, y, z, w):
-        send = col[order].contiguous()
-        recv = torch.empty(int(recv_counts.sum()), dtype=col.dtype, device=col.device)
-        dist.all_to_all_single(recv, send, output_split_sizes=recv_counts.tolist(),
-                               input_split_sizes=counts.tolist(), group=group)
+        send = col[order.to(col.device)].contiguous()
+        recv = torch.empty(int(sum(recv_cnt)), dtype=col.dtype, device=col.device)
+        dist.all_to_all_single(recv, send, output_split_sizes=recv_cnt, input_split_sizes=send_cnt, group=group)
         outs.append(recv)
+    slot_of = torch.empty_like(order)
+    slot_of[order] = torch.arange(len(order))                        # original index -> position in the send order
+    return (*outs, {"slot_of": slot_of, "send_cnt": send_cnt, "recv_cnt": recv_cnt, "group": group})
+
+
+def unshard_host(route, *cols):
+    """The way back of exchange_catalog_host: columns in slab order -> the order of the arrays that were sharded."""
+    import torch.distributed as dist
+    outs = []
+    for col in cols:
+        back = torch.empty(int(sum(route["send_cnt"])), dtype=col.dtype, device=col.device)
+        dist.all_to_all_single(back, col.contiguous(), output_split_sizes=route["send_cnt"],
+                               input_split_sizes=route["recv_cnt"], group=route["group"])
+        outs.append(back[route["slot_of"].to(col.device)])
     return tuple(outs)
+
+
+def exchange_catalog(x, y, z, w, ctx: Context = None, slot=0):
+    """Every rank holds an arbitrary part of the catalog (CUDA tensors); returns this rank's slab particles as four
+    tensors that VIEW the library's buffers (valid until the next call with the same slot) -- baorec_shard_catalog_f32:
+    device counting sort by owner + one grouped ncclSend/ncclRecv per column.  plan() must have been called.
+    Out-of-box particles on any rank raise OutOfBoxError on every rank."""
+    n = _chk_vec(x, y, z, w)
+    ctx = ctx or Context.get(x.device.index)
+    ptrs = [C.c_void_p() for _ in range(4)]
+    nl = C.c_int64()
+    L.check(ctx.lib.baorec_shard_catalog_f32(ctx.handle, int(slot), _ptr(x), _ptr(y), _ptr(z), _ptr(w), n,
+                                             *[C.byref(q) for q in ptrs], C.byref(nl), _stream()))
+    return tuple(_view(q.value, nl.value, x.device) for q in ptrs)
+
+
+def unshard(ctx: Context, cols, like, slot=0):
+    """Per-particle columns in slab order (up to three tensors) -> the order of the arrays that were sharded."""
+    cols = list(cols) + [None] * (3 - len(cols))
+    outs = [torch.empty_like(like) if c is not None else None for c in cols]
+    L.check(ctx.lib.baorec_unshard_f32(ctx.handle, int(slot), *[_ptr(c) for c in cols], *[_ptr(o) for o in outs], _stream()))
+    return tuple(o for o in outs if o is not None)
+
+
+def _view(ptr, n, device):
+    """A float32 CUDA tensor over library-owned device memory (no copy, no ownership)."""
+    if n == 0:
+        return torch.empty(0, dtype=torch.float32, device=device)
+    class _Ext:                                   # __cuda_array_interface__ v2
+        pass
+    e = _Ext()
+    e.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(e, device=device)
+
+
+def reconstruct_dist(recon, grid_size, data_x, data_y, data_z, data_w, rand=None, field="sum", positions=False, ctx: Context = None,
+                     out=None):
+    """run! + read_shifts / reconstructed_positions from this rank's (arbitrary) part of the catalog: sharding by slab,
+    the slab reconstruction and the way back happen inside the library (baorec_reconstruct_dist_f32); CUDA tensors in,
+    three CUDA tensors in the order of data_x out.  NumPy arrays go through the host entry point instead."""
+    p = recon._params()
+    if isinstance(data_x, np.ndarray):
+        ctx = ctx or Context.get()
+        plan(ctx, grid_size, recon.box_size, recon.box_min)
+        recon.fft_plan = FFTPlan(ctx, tuple(int(v) for v in grid_size))
+        assert rand is None, "the host entry point takes no randoms"
+        outs = tuple(out) if out is not None else tuple(np.empty_like(data_x) for _ in range(3))
+        L.check(ctx.lib.baorec_reconstruct_dist_host_f32(ctx.handle, C.byref(p), recon.algorithm, *[a.ctypes.data for a in (data_x, data_y, data_z, data_w)],
+                                                         len(data_x), L.FIELDS[field], int(bool(positions)), *[o.ctypes.data for o in outs]))
+        return outs
+    n = _chk_vec(data_x, data_y, data_z, data_w)
+    ctx = ctx or Context.get(data_x.device.index)
+    plan(ctx, grid_size, recon.box_size, recon.box_min)
+    recon.fft_plan = FFTPlan(ctx, tuple(int(v) for v in grid_size))
+    nr = _chk_vec(*rand) if rand is not None else 0
+    r = list(rand) if rand is not None else [None] * 4
+    outs = tuple(out) if out is not None else tuple(torch.empty_like(data_x) for _ in range(3))
+    L.check(ctx.lib.baorec_reconstruct_dist_f32(ctx.handle, C.byref(p), recon.algorithm, _ptr(data_x), _ptr(data_y), _ptr(data_z),
+                                                _ptr(data_w), n, *[_ptr(a) for a in r], nr, int(rand is not None), L.FIELDS[field],
+                                                int(bool(positions)), *[_ptr(o) for o in outs], _stream()))
+    return outs
 
 
 # ---- library side ---------------------------------------------------------------------------------
@@ -85,26 +162,31 @@ def init_comm(ctx: Context = None):
     return ctx
 
 
-def _enable_p2p(ctx: Context):
-    """(Optional, plan(..., p2p=True).)  Measured on 8 x B200 at 1024^3 it does not beat the grouped
-    ncclSend/ncclRecv path (22.0 vs 20.4 ms per reconstruction: the per-transpose barrier absorbs the
-    rank skew that NCCL hides), so it is off by default.
-    Maps every rank's receive buffers into this process (CUDA IPC) so that the pack / transpose
-    kernels store straight into peer memory over NVLink instead of staging + ncclSend/Recv."""
+def _map_peers(ctx: Context):
+    """Maps every rank's two receive buffers and its flag block into this process (CUDA IPC) -- what the peer-copy
+    exchange of the slab transforms (csrc/dist.cu, option "dist_exchange" = 1, the default) writes into: one strided
+    copy-engine copy per peer and chunk over NVLink plus a flag store, no pack / transpose kernels, no NCCL.
+    (Round 1's version of this exchange ended every transpose with a barrier, which exposed the rank skew that NCCL's
+    grouped send/recv hides -- 22.0 vs 20.4 ms at 8 GPUs; per-peer sequence flags removed the barrier.)"""
     import torch.distributed as dist
     world = dist.get_world_size()
-    mine = (C.c_ubyte * 128)()
-    L.check(ctx.lib.baorec_dist_ipc_export(ctx.handle, mine))
+    mine = (C.c_ubyte * 192)()
+    L.check(ctx.lib.baorec_dist_ipc_export(ctx.handle, mine))      # also resets this rank's flags (new generation)
     t = torch.tensor(list(mine), dtype=torch.uint8, device=torch.device("cuda", ctx.device))
     allh = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(allh, t)
+    dist.all_gather(allh, t)                                       # the synchronisation point the reset relies on
     raw = b"".join(bytes(h.cpu().tolist()) for h in allh)
     L.check(ctx.lib.baorec_dist_ipc_open(ctx.handle, C.create_string_buffer(raw, len(raw)), world))
+    dist.barrier()                                                 # nobody starts an exchange before everybody has mapped
 
 
-def plan(ctx: Context, grid_size, box_size, box_min, p2p=False):
+def plan(ctx: Context, grid_size, box_size, box_min, exchange=None):
+    """baorec_plan_dist + (several ranks, NCCL backend) the IPC mapping of the peers' receive buffers.
+    exchange: "peer" (default) or "nccl" (round 1's pack / transpose kernels + grouped ncclSend/ncclRecv)."""
     import torch.distributed as dist
     nx, ny, nz = (int(v) for v in grid_size)
+    if exchange is not None:
+        ctx.set_option("dist_exchange", 1 if exchange == "peer" else 0)
     key = ("dist", nx, ny, nz, tuple(float(np.float32(v)) for v in box_size),
            tuple(float(np.float32(v)) for v in box_min))
     if ctx.plan_key == key:
@@ -117,12 +199,15 @@ def plan(ctx: Context, grid_size, box_size, box_min, p2p=False):
         L.check(ctx.lib.baorec_dist_ipc_close(ctx.handle))
         dist.barrier()
     L.check(ctx.lib.baorec_plan_dist(ctx.handle, nx, ny, nz, L.f3(box_size), L.f3(box_min)))
-    if p2p and shape_changed and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 \
-            and dist.get_backend() == "nccl":
-        _enable_p2p(ctx)
-    ctx.plan_key = ("dist", nx, ny, nz, tuple(float(np.float32(v)) for v in box_size),
-                    tuple(float(np.float32(v)) for v in box_min))
+    if shape_changed and multi and dist.get_backend() == "nccl":
+        _map_peers(ctx)
+    ctx.plan_key = key
     return ctx
+
+
+def peer_exchange(ctx: Context) -> bool:
+    """True when the slab transforms run the peer-copy exchange (k space is K[z][yl][x]), False for NCCL (T[yl][x][z])."""
+    return bool(ctx.lib.baorec_dist_exchange_mode(ctx.handle))
 
 
 def slab_range(ctx: Context):
@@ -139,11 +224,15 @@ def slab_owner(ctx: Context, z):
 
 
 def dist_r2c(ctx: Context, slab):
+    """Distributed R2C of this rank's z slab.  Returns this rank's y slab of k space: K[z][yl][x] with the peer-copy
+    exchange (peer_exchange(ctx)), T[yl][x][z] with the NCCL exchange."""
     nzl, ny, nx = slab.shape
     z_lo, nz_loc = slab_range(ctx)
     assert nzl == nz_loc
-    world = ctx.plan_key[3] // nz_loc
-    out = torch.empty((ny // world, nx // 2 + 1, ctx.plan_key[3]), dtype=torch.complex64, device=slab.device)
+    nz = ctx.plan_key[3]
+    world = nz // nz_loc
+    shape = (nz, ny // world, nx // 2 + 1) if peer_exchange(ctx) else (ny // world, nx // 2 + 1, nz)
+    out = torch.empty(shape, dtype=torch.complex64, device=slab.device)
     L.check(ctx.lib.baorec_dist_r2c_f32(ctx.handle, _ptr(slab), _ptr(out), _stream()))
     return out
 

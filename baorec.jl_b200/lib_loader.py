@@ -76,7 +76,12 @@ SIGNATURES = {
     "baorec_dist_ipc_close": [_vp],
     "baorec_dist_ipc_export": [_vp, _vp],
     "baorec_dist_ipc_open": [_vp, _vp, _i],
+    "baorec_dist_exchange_mode": [_vp],
     "baorec_slab_range": [_vp, C.POINTER(_i), C.POINTER(_i)],
+    "baorec_shard_catalog_f32": [_vp, _i, _vp, _vp, _vp, _vp, _i64] + [C.POINTER(_vp)] * 4 + [C.POINTER(_i64), _vp],
+    "baorec_unshard_f32": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "baorec_reconstruct_dist_f32": [_vp, _pp, _i, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "baorec_reconstruct_dist_host_f32": [_vp, _pp, _i, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp],
     "baorec_slab_owner_f32": [_vp, _vp, _i64, _vp, _vp],
     "baorec_dist_r2c_f32": [_vp, _vp, _vp, _vp],
     "baorec_dist_c2r_f32": [_vp, _vp, _vp, _vp],

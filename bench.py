@@ -44,21 +44,27 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_catalog(n, L, seed, pinned=False):
-    """Uniform periodic catalog, float32 SoA, weights 1."""
+def make_catalog(n, L, seed, pinned=False, share=None):
+    """Uniform periodic catalog, float32 SoA, weights 1.  share = (lo, hi): only particles
+    lo .. hi-1 of the SAME catalog are kept (every rank draws the whole sequence, so the catalog is identical at every
+    rank count: rank r of P holds the r-th contiguous part of it, NOT the particles of its slab)."""
     import torch
     rng = np.random.default_rng(seed)
+    lo, hi = share if share is not None else (0, n)
     arrs = []
     for _ in range(3):
-        t = torch.empty(n, dtype=torch.float32, pin_memory=pinned)
+        t = torch.empty(hi - lo, dtype=torch.float32, pin_memory=pinned)
         a = t.numpy()
         chunk = 1 << 24
         for s in range(0, n, chunk):
             e = min(n, s + chunk)
-            a[s:e] = rng.random(e - s, dtype=np.float32) * np.float32(L)
+            c = rng.random(e - s, dtype=np.float32) * np.float32(L)
+            a0, a1 = max(s, lo), min(e, hi)
+            if a1 > a0:
+                a[a0 - lo:a1 - lo] = c[a0 - s:a1 - s]
         np.minimum(a, np.nextafter(np.float32(L), np.float32(0)), out=a)
         arrs.append(t)
-    w = torch.ones(n, dtype=torch.float32, pin_memory=pinned)
+    w = torch.ones(hi - lo, dtype=torch.float32, pin_memory=pinned)
     return arrs, w
 
 
@@ -114,13 +120,24 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def algorithmic_bytes(name, M, Mc, N):
+def algorithmic_bytes(name, M, Mc, N, chunks=1):
     """Compulsory HBM traffic per launch ('kernels'): every operand read once, every
-    result written once."""
+    result written once.  M, Mc, N are this rank's cells / complex modes / particles; entries launched once per plane
+    chunk of the slab transforms (2-D transforms, pack / transpose kernels) move 1/chunks of the slab per launch."""
+    if name.startswith("cufft_2d") or name.startswith("rows_kernel") or name.startswith("transpose_kernel"):
+        return (4 * M + 8 * Mc if name.startswith("cufft_2d") else 16 * Mc) // max(chunks, 1)
+    if name.startswith("peer_") or name.startswith("nccl_"):
+        return None
     if "usort_count" in name or "hash_positions" in name:
         return 12 * N                       # positions in
     if "usort_reorder" in name:
         return 16 * N + 16 * N + 4 * N      # x, y, z, w in; float4 records + inverse permutation out
+    if "shard_count" in name:
+        return 4 * N
+    if "shard_reorder" in name:
+        return 16 * N + 16 * N + 4 * N      # columns in, columns grouped by owner + map out
+    if "unshard_gather" in name:
+        return 4 * N + 12 * N + 12 * N
     if "scatter_sorted" in name or "scatter_direct" in name or "scatter_records" in name:
         return 16 * N + 4 * M              # records/SoA in, every mesh cell written once
     if "gather_sorted_kernel<3" in name or "gather_direct_kernel<3" in name:
@@ -190,6 +207,13 @@ def cpu_oracle():
     """The CPU stand-in for BAOrec.jl's threaded CPU path: the oracle with compiled loops
     (oracle/baorec_oracle_c.c: serial scatter like the reference's, OpenMP gather / k-space loops,
     scipy.fft on all host threads) when oracle/_c/ was built, else the pure-numpy port."""
+    # torchrun exports OMP_NUM_THREADS=1 to its workers, and scipy's ducc FFT sizes its thread pool from it (measured
+    # here: the transforms 2.5x slower, the whole CPU arm 3.5x -- round 1's 100 s instead of 20 s under torchrun);
+    # the CPU arm runs on rank 0 alone and is meant to use the host's cores
+    ncpu = str(os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = ncpu
+    os.environ["DUCC0_NUM_THREADS"] = ncpu
+    assert "scipy.fft" not in sys.modules or os.environ.get("BAOREC_BENCH_ALLOW_SCIPY_PRELOAD"), "scipy.fft was imported before the thread count was set"
     sys.path.insert(0, str(ROOT / "oracle"))
     import baorec_oracle_fast as fast
     if fast.available():
@@ -262,9 +286,9 @@ def main():
                          "(sigma = 1 on a 512^3 generation mesh + linear RSD shift, generated on the device; --gpus 1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-batch", type=int, default=0,
+    ap.add_argument("--e2e-batch", type=int, default=4,
                     help="K > 0 (one GPU): additionally time the batched host pipeline (baorec_batch_host_f32) over K catalogs "
-                         "and report it as e2e['batched'] -- off by default until it has run on hardware once")
+                         "and report it as e2e['batched'] (0 = skip)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -310,23 +334,16 @@ def main():
     else:
         if args.catalog != "uniform":
             raise SystemExit("--catalog lognormal is implemented for --gpus 1 only")
-        # strong scaling: the same 1e8-particle workload, sharded by z slab (each rank draws its
-        # N/P particles inside its own slab; ownership re-checked with the library's own rule)
+        # strong scaling of the SAME 1e8-particle catalog: rank r holds the r-th contiguous part of it (not the
+        # particles of its slab); sharding by slab, the reconstruction and the way back of the shifts are one library
+        # call (baorec_reconstruct_dist_f32) inside the timed region
         B.dist.init_comm(ctx)
-        if os.environ.get("BAOREC_A2A_CHUNKS"):      # A/B knob: 1 = unpipelined slab transposes
+        if os.environ.get("BAOREC_A2A_CHUNKS"):      # A/B knobs
             ctx.set_option("a2a_chunks", int(os.environ["BAOREC_A2A_CHUNKS"]))
-        B.dist.plan(ctx, grid, kw["box_size"], kw["box_min"])
-        z_lo, nzl = B.dist.slab_range(ctx)
-        cell = L / n
-        (hx, hy, hz), hw = make_catalog(N // world, L, seed=42 + rank, pinned=True)
-        zz = hz.numpy()
-        zz *= np.float32(nzl / n)
-        zz += np.float32(z_lo * cell)
-        own = B.dist.owner_of_z(zz, 0.0, L, n, world)
-        bad = own != rank
-        if bad.any():      # a handful of particles within one ulp of the slab faces
-            zz[bad] = np.float32((z_lo + 0.5 * nzl) * cell)
-        n_loc = N // world
+        B.dist.plan(ctx, grid, kw["box_size"], kw["box_min"], exchange=os.environ.get("BAOREC_EXCHANGE"))
+        lo, hi = rank * N // world, (rank + 1) * N // world
+        (hx, hy, hz), hw = make_catalog(N, L, seed=42, pinned=True, share=(lo, hi))
+        n_loc = hi - lo
     dx, dy, dz, dw = (t.to(dev) for t in (hx, hy, hz, hw))
 
     # result buffers are allocated once (run! zero-fills the mesh on every call, as the reference
@@ -340,8 +357,7 @@ def main():
             return B.read_shifts(rec, dx, dy, dz, mesh, field="sum", out=out_buf)
     else:
         def step_device():
-            B.dist.run_dist(rec, grid, dx, dy, dz, dw, ctx=ctx)
-            return B.dist.read_shifts_dist(rec, dx, dy, dz, field="sum")
+            return B.dist.reconstruct_dist(rec, grid, dx, dy, dz, dw, field="sum", ctx=ctx, out=out_buf)
 
     def barrier():
         if world > 1:
@@ -373,7 +389,11 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
-    checksum = float(out[2].double().abs().mean().item())
+    # mean |shift_z| over ALL particles of the catalog: comparable across rank counts
+    cs = out[2].double().abs().sum().reshape(1)
+    if world > 1:
+        dist.all_reduce(cs)
+    checksum = float(cs.item()) / N
 
     # ---- end-to-end through the host-buffer C-ABI pipeline (pinned host catalogs) ------------
     e2e = None
@@ -384,13 +404,9 @@ def main():
         outs = [t.numpy() for t in outs_t]
 
         def step_host_dist():
-            # pinned host catalog -> device, distributed solve + read-back, shifts -> pinned host
-            tx, ty, tz, tw = (t.to(dev, non_blocking=True) for t in (hx, hy, hz, hw))
-            B.dist.run_dist(rec_h, grid, tx, ty, tz, tw, ctx=ctx)
-            sh = B.dist.read_shifts_dist(rec_h, tx, ty, tz, field="sum")
-            for o, t_ in zip(outs_t, sh):
-                o.copy_(t_, non_blocking=True)
-            torch.cuda.synchronize()
+            # baorec_reconstruct_dist_host_f32: pinned host share of the catalog -> device, sharding by slab,
+            # distributed solve + read-back, shifts back in the caller's order -> pinned host
+            B.dist.reconstruct_dist(rec_h, grid, ax, ay, az, aw, field="sum", ctx=ctx, out=outs)
 
         def step_host():
             if world > 1:
@@ -416,13 +432,18 @@ def main():
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cs = torch.tensor([float(np.abs(outs[2]).sum(dtype=np.float64))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(cs)
         e2e = {"value": float(t.item()), "unit": UNIT,
+               "api": ("baorec_run_host_f32 + baorec_read_host_f32" if world == 1 else
+                       "baorec_reconstruct_dist_host_f32 on every rank (its N/P share of the unsharded catalog)"),
                "h2d_bytes_per_step": (16 * N + 12 * N) if world == 1 else 16 * N,
                "d2h_bytes_per_step": 12 * N,
                "stage_ms": {"h2d_catalog": stage[0], "solve": stage[1], "d2h_run": stage[2],
                             "h2d_pos+disp_meshes": stage[3], "gather": stage[4], "d2h_shifts": stage[5]}
                if (len(stage) >= 6 and world == 1) else None,
-               "checksum_abs_mean_shift_z": float(np.abs(outs[2][: 1 << 20]).mean())}
+               "checksum_abs_mean_shift_z": float(cs.item()) / N}
 
     # ---- optional: the batched host pipeline (transfers of neighbouring catalogs overlap the solve) -----------
     if e2e is not None and args.e2e_batch > 0 and world == 1:
@@ -454,21 +475,45 @@ def main():
     # ---- roofline of the dominant hand-written kernel + per-kernel table ---------------------
     peak, peak_src = measured_peak_gbs()
     kernels = {}
+    chunks = 1
+    if world > 1:      # launches of the 2-D transforms per slab transform = plane chunks of the pipelined exchange
+        c2 = sum(c for k, (_, c) in prof.items() if k.startswith("cufft_2d"))
+        c1 = sum(c for k, (_, c) in prof.items() if k.startswith("cufft_1d_z"))
+        chunks = max(1, round(c2 / max(c1, 1)))
     for name, (ms, cnt) in prof.items():
-        ab = algorithmic_bytes(name, M // world, Mc // world, N // world)   # per-rank (slab) bytes
+        ab = algorithmic_bytes(name, M // world, Mc // world, N // world, chunks)   # per-rank (slab) bytes
         per = ms / max(cnt, 1)
         kernels[name] = {"ms_per_launch": round(per, 4), "launches_per_step": cnt / args.steps,
                          "ms_per_step": round(ms / args.steps, 3),
                          "alg_GBs": round(ab / per / 1e6, 1) if ab else None,
                          "frac_of_peak": round(ab / per / 1e6 / peak, 3) if ab else None}
-    own = {k: v for k, v in kernels.items() if not k.startswith("cufft")}
+    own = {k: v for k, v in kernels.items() if not k.startswith(("cufft", "peer_", "nccl_"))}
     top = max(own, key=lambda k: own[k]["ms_per_step"]) if own else None
     roofline = None
     if top and kernels[top]["alg_GBs"]:
         roofline = {"kernel": top, "bound": "hbm", "achieved": kernels[top]["alg_GBs"], "peak": peak,
                     "unit": "GB/s", "frac": kernels[top]["frac_of_peak"], "traffic": ncu_traffic(top, n, N, world),
                     "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": algorithmic_bytes(top, M // world, Mc // world, N // world)}
+                    "algorithmic_bytes_per_launch": algorithmic_bytes(top, M // world, Mc // world, N // world, chunks)}
+    exchange = None
+    if world > 1:
+        # The exchange of the slab transforms: every rank sends (P-1)/P of its complex slab per transform.  At N > 1
+        # this, not an HBM kernel, is what bounds the step, so it is the line's roofline (rank 0's CUDA-event time of
+        # the copies on the communication stream; the local 1/P block is an HBM copy inside the same timed span).
+        name = "peer_copies" if "peer_copies" in prof else "nccl_all_to_all"
+        if name in prof:
+            ms, cnt = prof[name]
+            transforms = sum(c for k, (_, c) in prof.items() if k.startswith("cufft_1d_z"))
+            sent = 8 * (Mc // world) * (world - 1) / world * transforms          # bytes over NVLink, this rank, timed region
+            nv_peak, nv_src = 770.0, "measured peer copy per direction (B200_PROFILING.md; nominal 900)"
+            exchange = {"scheme": "peer copies (copy engines) + sequence flags" if name == "peer_copies" else "grouped ncclSend/ncclRecv",
+                        "launches_per_step": cnt / args.steps, "ms_per_step": round(ms / args.steps, 3),
+                        "nvlink_bytes_per_rank_per_step": int(sent / args.steps), "GBs_per_direction": round(sent / ms / 1e6, 1)}
+            hbm_roofline = roofline
+            roofline = {"kernel": name + " (slab-transform exchange, %d per step)" % round(cnt / args.steps), "bound": "nvlink",
+                        "achieved": exchange["GBs_per_direction"], "peak": nv_peak, "unit": "GB/s",
+                        "frac": round(exchange["GBs_per_direction"] / nv_peak, 3), "traffic": None, "peak_source": nv_src,
+                        "algorithmic_bytes_per_launch": int(sent / max(cnt, 1)), "top_hbm_kernel": hbm_roofline}
     fft_ms = sum(v["ms_per_step"] for k, v in kernels.items() if k.startswith("cufft"))
     own_ms = sum(v["ms_per_step"] for k, v in own.items())
 
@@ -488,12 +533,14 @@ def main():
         "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"IterativeRecon periodic box, {n}^3 mesh, {N:.0e} particles ({args.catalog}, seed 42), CIC, "
-                               f"n_iter=3, R=15 Mpc/h, L={L:g} Mpc/h, los=(0,0,1): run! + read_shifts(:sum)",
+                               f"n_iter=3, R=15 Mpc/h, L={L:g} Mpc/h, los=(0,0,1): run! + read_shifts(:sum)"
+                               + ("" if world == 1 else f"; the same catalog at every rank count, rank r holds its r-th 1/{world} "
+                                  "(unsharded): sharding by slab and the way back of the shifts are inside the step"),
                    "l2_policy": "inputs larger than L2 (4 GiB meshes, 1.6 GB catalog vs 126 MB L2)",
                    "ffts_per_step": (f1 - f0) / args.steps},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(k1 - k0),
         "cufft_execs": int(f1 - f0),
-        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "roofline": roofline, "exchange": exchange, "cpu_baseline": cpu_baseline,
         "breakdown_ms_per_step": {"own_kernels": round(own_ms, 3), "cufft": round(fft_ms, 3)},
         "kernels": kernels, "checksum_abs_mean_shift_z": checksum,
         "scratch_GiB": round(ctx.scratch_bytes() / 2 ** 30, 2),

@@ -147,19 +147,38 @@ int baorec_comm_init(baorec_ctx* ctx, int rank, int nranks, const void* unique_i
  * communicator is needed (baorec_comm_init(ctx, 0, 1, NULL)). */
 int baorec_plan_dist(baorec_ctx* ctx, int nx, int ny, int nz, const float box_size[3], const float box_min[3]);
 int baorec_slab_range(const baorec_ctx* ctx, int* z_lo, int* nz_loc);
-/* Peer-to-peer transposes (optional, after baorec_plan_dist): every rank exports the CUDA IPC
- * handles of its two receive buffers (2 x 64 bytes), the host side all-gathers them, and each rank
- * opens the others'.  From then on the pack / tile-transpose kernels store their per-peer blocks
- * straight into the peers' receive buffers over NVLink (one fused kernel + a one-int NCCL barrier
- * instead of pack + grouped ncclSend/ncclRecv). */
+/* Peer-copy exchange of the slab transforms (option "dist_exchange" = 1, the default; after baorec_plan_dist): every
+ * rank exports the CUDA IPC handles of its two receive buffers (k-layout for the forward, plane-layout for the inverse
+ * transform) and of its flag block (3 x 64 bytes; the call also resets the rank's flags, so it must precede the
+ * gathering of the handles on every rank), the host side all-gathers them, and each rank opens the others'.  From then
+ * on an exchange is one strided copy-engine copy per peer and plane chunk over NVLink, straight from the 2-D
+ * transform's output into the peer's buffer, announced by a sequence flag stored into the peer's flag block: no
+ * pack / transpose kernels, no staging buffer, no collective, no barrier.  With one rank the library maps itself.
+ * "dist_exchange" = 0 selects round 1's scheme: pack + tile-transpose kernels and grouped ncclSend/ncclRecv. */
 int baorec_dist_ipc_close(baorec_ctx* ctx);  /* drop the mappings (before a re-plan frees the buffers) */
-int baorec_dist_ipc_export(baorec_ctx* ctx, void* out128);
-int baorec_dist_ipc_open(baorec_ctx* ctx, const void* all_handles /* nranks x 128 bytes */, int nranks);
+int baorec_dist_ipc_export(baorec_ctx* ctx, void* out192);
+int baorec_dist_ipc_open(baorec_ctx* ctx, const void* all_handles /* nranks x 192 bytes */, int nranks);
+int baorec_dist_exchange_mode(const baorec_ctx* ctx); /* 1: peer copies (k space K[z][yl][x]); 0: NCCL (T[yl][x][z]) */
 /* Owner rank of every particle = slab of its cic! base plane (src/mas.jl:15-30), -1 if out of box. */
 int baorec_slab_owner_f32(baorec_ctx* ctx, const float* d_z, int64_t n, int32_t* d_owner, baorec_stream stream);
-/* Slab-decomposed transforms (unnormalised): real slab [nz_loc][ny][nx] <-> transposed k slab
- * [ny_loc][nx/2+1][nz] (complex, z contiguous).  2-D cuFFT over the local planes, hand-written
- * pack / tile-transpose kernels, grouped ncclSend/ncclRecv all-to-all, 1-D cuFFT along z. */
+/* Particle sharding by slab ("one bucketed all-to-all(v)"; the reference's own attempt,
+ * send_to_relevant_process src/mas.jl:112-140, is unfinished).  Every rank passes ANY part of the catalog (device
+ * arrays, untouched); on return *d_sx .. *d_sw point to library-owned columns holding the *n_local particles whose
+ * base plane lies in this rank's slab (valid until the next call with the same slot; run_dist's cic! write-back of
+ * wrapped positions goes into them).  slot 0 = data, 1 = randoms: one routing table each is kept.  Device counting
+ * sort by owner + all-gathered count matrix + one grouped ncclSend/ncclRecv per column and peer.  Out-of-box particles
+ * on ANY rank make EVERY rank return BAOREC_ERR_OUT_OF_BOX.  Synchronises the stream (the counts are needed on the host). */
+int baorec_shard_catalog_f32(baorec_ctx* ctx, int slot, const float* d_x, const float* d_y, const float* d_z,
+                             const float* d_w, int64_t n, float** d_sx, float** d_sy, float** d_sz, float** d_sw,
+                             int64_t* n_local, baorec_stream stream);
+/* The way back: up to three columns in slab order (n_local values each; NULL = skip) -> the order of the arrays that
+ * were passed to baorec_shard_catalog_f32 (n values each). */
+int baorec_unshard_f32(baorec_ctx* ctx, int slot, const float* d_a, const float* d_b, const float* d_c, float* d_oa,
+                       float* d_ob, float* d_oc, baorec_stream stream);
+/* Slab-decomposed transforms (unnormalised): real slab [nz_loc][ny][nx] <-> this rank's y slab of k space (complex):
+ * K[nz][ny_loc][nx/2+1] with the peer-copy exchange (2-D cuFFT over the local planes, peer copies, strided 1-D cuFFT
+ * along z), T[ny_loc][nx/2+1][nz] with the NCCL exchange (2-D cuFFT, pack / tile-transpose kernels, grouped
+ * ncclSend/ncclRecv, contiguous 1-D cuFFT along z). */
 int baorec_dist_r2c_f32(baorec_ctx* ctx, const float* d_slab, float* d_kslab_t, baorec_stream stream);
 int baorec_dist_c2r_f32(baorec_ctx* ctx, float* d_kslab_t /* destroyed */, float* d_slab, baorec_stream stream);
 /* run! (src/recon.jl:134-180 box, :215-261 randoms) across the ranks: every rank passes the
@@ -187,6 +206,18 @@ int baorec_run_dist_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, 
 int baorec_read_shifts_dist_f32(baorec_ctx* ctx, const baorec_params* p, const float* d_x, const float* d_y,
                                 const float* d_z, int64_t n_local, int field, int positions, float* d_sx,
                                 float* d_sy, float* d_sz, baorec_stream stream);
+/* run! + read_shifts / reconstructed_positions from an UNSHARDED catalog: every rank passes any part of the data (and,
+ * has_randoms != 0, randoms) catalog as device arrays; the library shards by slab (baorec_shard_catalog_f32), runs
+ * baorec_run_dist_f32 + baorec_read_shifts_dist_f32 on the slabs and routes the results back into the caller's order.
+ * The box is the planned one (with randoms: setup_box over all ranks first, src/recon.jl:172,253). */
+int baorec_reconstruct_dist_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, const float* d_x, const float* d_y,
+                                const float* d_z, const float* d_w, int64_t n, const float* d_rx, const float* d_ry,
+                                const float* d_rz, const float* d_rw, int64_t n_ran, int has_randoms, int field,
+                                int positions, float* d_ox, float* d_oy, float* d_oz, baorec_stream stream);
+/* The same for HOST arrays (periodic box, no randoms): upload of this rank's share, the call above, download. */
+int baorec_reconstruct_dist_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, const float* h_x,
+                                     const float* h_y, const float* h_z, const float* h_w, int64_t n, int field,
+                                     int positions, float* h_ox, float* h_oy, float* h_oz);
 
 /* ---- mass assignment (replaces cic!/read_cic! CuArray methods) ------------- */
 /* cic!(rho::CuArray, ...; wrap) src/mas.jl:53-107.  Accumulates into d_rho (caller

@@ -131,6 +131,70 @@ def tsc_modes(B, ctx, rank, world):
     return ok
 
 
+def fft_and_sharding(B, ctx, rank, world):
+    """(1) the slab transform alone against numpy's rfftn, both exchange schemes, repeated (flag sequence);
+    (2) baorec_reconstruct_dist_f32 from an INTERLEAVED split of the catalog (rank r holds particles r, r + P, ...):
+    sharding by slab inside the library, reconstruction, results back in the caller's order -- against the oracle."""
+    ok = True
+    n = 64
+    if n % world:
+        return ok
+    bs, bm = np.full(3, 1000.0, np.float32), np.zeros(3, np.float32)
+    rng = np.random.default_rng(3)
+    for exchange in ("peer", "nccl"):
+        ctx.plan_key = None
+        B.dist.plan(ctx, (n, n, n), bs, bm, exchange=exchange)
+        peer = B.dist.peer_exchange(ctx)
+        z_lo, nzl = B.dist.slab_range(ctx)
+        nyl = n // world
+        for rep in range(3):
+            a = rng.standard_normal((n, n, n)).astype(np.float32)
+            ref = np.fft.rfftn(a.astype(np.float64))[:, rank * nyl:(rank + 1) * nyl, :]      # [z][yl][x]
+            K = B.dist.dist_r2c(ctx, torch.from_numpy(a[z_lo:z_lo + nzl].copy()).cuda())
+            got = K.cpu().numpy() if peer else K.cpu().numpy().transpose(2, 0, 1)
+            e = max(rel_rms(got.real, ref.real), rel_rms(got.imag, ref.imag))
+            back = torch.empty((nzl, n, n), dtype=torch.float32, device="cuda")
+            B.dist.dist_c2r(ctx, K, back)
+            e2 = rel_rms(back.cpu().numpy() / a.size, a[z_lo:z_lo + nzl])
+            good = e < 1e-5 and e2 < 1e-5 and peer == (exchange == "peer")
+            ok &= good
+            if rep == 2 or not good:
+                print(f"[rank {rank}/{world}] slab FFT exchange={exchange} (peer copies: {peer}): forward {e:.2e} round trip {e2:.2e} "
+                      f"{'OK' if good else 'FAIL'}", flush=True)
+    ctx.plan_key = None
+    ctx.set_option("dist_exchange", 1)
+    L, N = 1000.0, 400_000
+    pos, w = clustered_box(N, L, seed=17)
+    pos[2][:64] += np.float32(L)
+    for algo, los in (("iterative", (0.0, 0.0, 1.0)), ("multigrid", None)):
+        kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=bs, box_min=bm, los=los)
+        orec = O.IterativeRecon(n_iter=3, **kw) if algo == "iterative" else O.MultigridRecon(**kw)
+        opos = [p.copy() for p in pos]
+        omesh = O.run(orec, (n, n, n), *opos, w)
+        oshift = O.read_shifts(orec, *opos, omesh, "sum")
+        rec = B.IterativeRecon(n_iter=3, **kw) if algo == "iterative" else B.MultigridRecon(**kw)
+        mine = slice(rank, None, world)
+        d = [torch.from_numpy(np.ascontiguousarray(p[mine])).cuda() for p in pos]
+        got = B.dist.reconstruct_dist(rec, (n, n, n), *d, torch.from_numpy(np.ascontiguousarray(w[mine])).cuda(), field="sum", ctx=ctx)
+        e_rms = max(rel_rms(got[a].cpu().numpy(), oshift[a][mine]) for a in range(3))
+        e_max = max(maxabs(got[a].cpu().numpy(), oshift[a][mine]) for a in range(3))
+        good = e_rms < 1e-4 and e_max < 1e-3
+        ok &= good
+        print(f"[rank {rank}/{world}] reconstruct_dist {algo} from an interleaved split: shift rel.rms={e_rms:.2e} max={e_max:.2e} "
+              f"{'OK' if good else 'FAIL'}", flush=True)
+    # an out-of-box particle on one rank raises on every rank
+    bad = [q.clone() for q in d]
+    if rank == world - 1:
+        bad[2][3] = -7.0
+    try:
+        B.dist.exchange_catalog(*bad, torch.ones_like(bad[0]), ctx=ctx)
+        ok = False
+        print(f"[rank {rank}/{world}] out-of-box particle on rank {world - 1} was NOT reported here: FAIL", flush=True)
+    except B.OutOfBoxError:
+        pass
+    return ok
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -167,6 +231,7 @@ def main():
         print(f"[rank {rank}/{world}] n={n} los={los} particles={int(mine.sum())} slab=[{z_lo},{z_lo + nzl}) "
               f"mesh rel.rms={e_mesh:.2e} shift rel.rms={e_rms:.2e} max={e_max:.2e} {'OK' if good else 'FAIL'}",
               flush=True)
+    ok &= fft_and_sharding(B, ctx, rank, world)
     ok &= more_modes(B, ctx, rank, world, quick)
     if os.environ.get("MGC_TSC") == "1":                 # TSC on slabs (boundary-cell exchange: 1 ghost plane below, 2 above);
         ok &= tsc_modes(B, ctx, rank, world)             # opt-in until it has run on hardware once

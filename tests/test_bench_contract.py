@@ -57,3 +57,26 @@ def test_algorithmic_bytes_cover_the_profiled_kernels():
     for key in ('"roofline"', '"cpu_baseline"', '"e2e"', '"clocks"', '"gpu_launches"', '"h2d_bytes_per_step"', '"d2h_bytes_per_step"'):
         assert key in src, key
     assert re.search(r"--warmup.*default=3", src) and "torch.cuda.Event" in src
+
+
+def test_the_catalog_is_the_same_at_every_rank_count():
+    """bench.py --gpus N: rank r holds the r-th contiguous part of the catalog --gpus 1 draws (strong scaling of one workload)."""
+    sys.path.insert(0, str(ROOT))
+    import numpy as np
+    import bench
+    n = (1 << 24) + 12345            # spans two generation chunks
+    (fx, fy, fz), fw = bench.make_catalog(n, 2500.0, seed=42)
+    for world in (2, 8):
+        for rank in (0, world - 1, world // 2):
+            lo, hi = rank * n // world, (rank + 1) * n // world
+            (x, y, z), w = bench.make_catalog(n, 2500.0, seed=42, share=(lo, hi))
+            assert len(w) == hi - lo
+            for a, b in ((x, fx), (y, fy), (z, fz)):
+                assert np.array_equal(a.numpy(), b.numpy()[lo:hi])
+
+
+def test_reference_arm_restores_the_host_threads_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1; scipy's FFT sizes its pool from it.  The CPU arm sets the thread count itself."""
+    src = (ROOT / "bench.py").read_text()
+    assert 'os.environ["OMP_NUM_THREADS"] = ncpu' in src and 'os.environ["DUCC0_NUM_THREADS"] = ncpu' in src
+    assert len(run_ref({"OMP_NUM_THREADS": "1"})) == 1

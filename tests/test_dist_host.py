@@ -64,7 +64,7 @@ def _worker(rank, world, port, q):
         cols = [torch.from_numpy((rng.random(m) * L).astype(np.float32)) for _ in range(3)]
         tag = torch.arange(m, dtype=torch.float32) + 10000 * rank       # weights double as identity tags
         bs, bm = np.full(3, L, np.float32), np.zeros(3, np.float32)
-        x, y, z, w = B.dist.exchange_catalog(*cols, tag, bs, bm, n)
+        x, y, z, w, route = B.dist.exchange_catalog_host(*cols, tag, bs, bm, n)
         own = B.dist.owner_of_z(z.numpy(), 0.0, L, n, world)
         total = torch.tensor([len(x)], dtype=torch.int64)
         dist.all_reduce(total)
@@ -73,6 +73,18 @@ def _worker(rank, world, port, q):
         expect = sum(float((np.arange(3000 + 500 * r) + 10000 * r).sum()) for r in range(world))
         ok = bool((own == rank).all()) and int(total) == sum(3000 + 500 * r for r in range(world)) \
             and abs(float(chk) - expect) < 1e-3 and len(x) == len(y) == len(z) == len(w)
+        # the way back: a per-particle result computed in slab order lands on its particle in the caller's order
+        bx, bt = B.dist.unshard_host(route, 2.0 * x + z, w)
+        ok = ok and torch.equal(bt, tag) and torch.equal(bx, 2.0 * cols[0] + cols[2])
+        # an out-of-box particle on ONE rank raises on EVERY rank (no rank is left blocked in the collective)
+        bad = cols[2].clone()
+        if rank == 1:
+            bad[7] = -5.0
+        try:
+            B.dist.exchange_catalog_host(cols[0], cols[1], bad, tag, bs, bm, n)
+            ok = False
+        except B.OutOfBoxError:
+            pass
         # setup_box over the ranks == setup_box of the concatenated catalog (src/utils.jl:100-109)
         import baorec_oracle as O
         rngs = [np.random.default_rng(100 + r) for r in range(world)]

@@ -23,24 +23,32 @@ def dctx(B):
     ctx.plan_key = None       # force a fresh single-GPU plan for whoever comes next
 
 
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
 @pytest.mark.parametrize("chunks", [4, 1, 3])
 @pytest.mark.parametrize("shape", [(32, 32, 32), (48, 32, 16), (64, 64, 64), (64, 32, 48)])
-def test_dist_fft_roundtrip_and_matches_rfftn(B, dctx, shape, chunks):
+def test_dist_fft_roundtrip_and_matches_rfftn(B, dctx, shape, chunks, exchange):
     """Slab transforms, pipelined in `chunks` plane chunks (1 = unpipelined; a chunk count that does
-    not divide the local planes falls back to the next smaller one)."""
+    not divide the local planes falls back to the next smaller one), with both exchange schemes: peer copies +
+    sequence flags (k space K[z][yl][x]) and pack / transpose kernels + NCCL (T[yl][x][z]).  Repeated transforms
+    exercise the buffer-free / arrived flag sequence."""
     nx, ny, nz = shape
     dctx.set_option("a2a_chunks", chunks)
-    B.dist.plan(dctx, shape, np.full(3, 100.0, np.float32), np.zeros(3, np.float32))
-    rng = np.random.default_rng(0)
-    a = rng.standard_normal((nz, ny, nx)).astype(np.float32)
-    T = B.dist.dist_r2c(dctx, dev(a))                         # [y][x][z]
-    ref = np.fft.rfftn(a.astype(np.float64), axes=(0, 1, 2))  # [z][y][x]
-    got = T.cpu().numpy().transpose(2, 0, 1)
-    assert rel_rms(got.real, ref.real) < 1e-5 and rel_rms(got.imag, ref.imag) < 1e-5
-    back = torch.empty((nz, ny, nx), dtype=torch.float32, device="cuda")
-    B.dist.dist_c2r(dctx, T, back)
-    dctx.set_option("a2a_chunks", 4)
-    assert rel_rms(back.cpu().numpy() / a.size, a) < 1e-5
+    try:
+        B.dist.plan(dctx, shape, np.full(3, 100.0, np.float32), np.zeros(3, np.float32), exchange=exchange)
+        assert B.dist.peer_exchange(dctx) == (exchange == "peer")
+        rng = np.random.default_rng(0)
+        for rep in range(3):
+            a = rng.standard_normal((nz, ny, nx)).astype(np.float32)
+            T = B.dist.dist_r2c(dctx, dev(a))
+            ref = np.fft.rfftn(a.astype(np.float64), axes=(0, 1, 2))  # [z][y][x]
+            got = T.cpu().numpy() if exchange == "peer" else T.cpu().numpy().transpose(2, 0, 1)
+            assert rel_rms(got.real, ref.real) < 1e-5 and rel_rms(got.imag, ref.imag) < 1e-5
+            back = torch.empty((nz, ny, nx), dtype=torch.float32, device="cuda")
+            B.dist.dist_c2r(dctx, T, back)
+            assert rel_rms(back.cpu().numpy() / a.size, a) < 1e-5
+    finally:
+        dctx.set_option("a2a_chunks", 4)
+        dctx.set_option("dist_exchange", 1)
 
 
 def test_slab_owner_matches_host_logic(B, dctx):
@@ -82,6 +90,44 @@ def test_run_dist_matches_single_gpu_and_oracle(B, O, dctx, los):
     newpos = B.dist.read_shifts_dist(rec, *d, field="sum", positions=True)
     for a in range(3):
         assert maxabs(newpos[a].cpu().numpy(), opos[a] - oshift[a]) < 1e-3
+
+
+def test_shard_unshard_and_reconstruct_dist(B, O, dctx):
+    """baorec_shard_catalog_f32 / baorec_unshard_f32 / baorec_reconstruct_dist_f32 with one rank (every particle is
+    this rank's; the counting sort, the routing table and the way back still run).  tests/multi_gpu_check.py is the
+    same under torchrun with an interleaved split of the catalog."""
+    n, L, N = 64, 1000.0, 300_000
+    pos, w = clustered_box(N, L, seed=6)
+    pos[2][:40] += np.float32(L)
+    kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=np.full(3, L, np.float32),
+              box_min=np.zeros(3, np.float32), los=(0.0, 0.0, 1.0), n_iter=3)
+    B.dist.plan(dctx, (n, n, n), kw["box_size"], kw["box_min"])
+    d = [dev(p) for p in pos]
+    tag = torch.arange(N, dtype=torch.float32, device="cuda")
+    sx, sy, sz, st_ = B.dist.exchange_catalog(*d, tag, ctx=dctx)
+    assert len(sx) == N
+    idx = st_.long()
+    assert torch.equal(torch.sort(idx).values, torch.arange(N, device="cuda"))          # a permutation
+    assert torch.equal(sx, d[0][idx]) and torch.equal(sy, d[1][idx]) and torch.equal(sz, d[2][idx])
+    bx, bt = B.dist.unshard(dctx, (2.0 * sx + sz, st_), d[0])
+    assert torch.equal(bt, tag) and torch.equal(bx, 2.0 * d[0] + d[2])
+    with pytest.raises(B.OutOfBoxError):
+        bad = d[2].clone()
+        bad[5] = -3.0
+        B.dist.exchange_catalog(d[0], d[1], bad, tag, ctx=dctx)
+    # the composite against the oracle, device and host arrays
+    orec = O.IterativeRecon(**kw)
+    opos = [p.copy() for p in pos]
+    omesh = O.run(orec, (n, n, n), *opos, w)
+    oshift = O.read_shifts(orec, *opos, omesh, "sum")
+    rec = B.IterativeRecon(**kw)
+    before = [q.clone() for q in d]
+    got = B.dist.reconstruct_dist(rec, (n, n, n), *d, dev(w), field="sum", ctx=dctx)
+    hgot = B.dist.reconstruct_dist(B.IterativeRecon(**kw), (n, n, n), *[p.copy() for p in pos], w, field="sum", ctx=dctx)
+    for a in range(3):
+        assert torch.equal(d[a], before[a])                                             # the caller's arrays are inputs
+        assert rel_rms(got[a].cpu().numpy(), oshift[a]) < 1e-4 and maxabs(got[a].cpu().numpy(), oshift[a]) < 1e-3
+        assert maxabs(hgot[a], oshift[a]) < 1e-3
 
 
 def test_read_shifts_dist_needs_a_run_first(B):
