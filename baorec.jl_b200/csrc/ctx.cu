@@ -367,7 +367,9 @@ int baorec_create(int device, baorec_ctx** out) {
   BR_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   BR_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
   BR_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  BR_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream2, cudaStreamNonBlocking));
   for (int i = 0; i < 8; i++) {
+    BR_CUDA(cudaEventCreateWithFlags(&ctx->ev_local[i], cudaEventDisableTiming));
     BR_CUDA(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
     BR_CUDA(cudaEventCreateWithFlags(&ctx->ev_a2a[i], cudaEventDisableTiming));
   }
@@ -412,7 +414,9 @@ int baorec_destroy(baorec_ctx* ctx) {
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+  if (ctx->comm_stream2) cudaStreamDestroy(ctx->comm_stream2);
   for (int i = 0; i < 8; i++) {
+    if (ctx->ev_local[i]) cudaEventDestroy(ctx->ev_local[i]);
     if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
     if (ctx->ev_a2a[i]) cudaEventDestroy(ctx->ev_a2a[i]);
   }

@@ -439,7 +439,7 @@ static int dist_r2c_peer(baorec_ctx* ctx, const float* slab, float2* K, int C, c
   if (C < 1) C = 1;
   const int nzc = nzl / C;
   const size_t rplane = (size_t)ny * ctx->nx, cplane = (size_t)ny * xh, kplane = (size_t)nyl * xh;
-  cudaStream_t cs = ctx->comm_stream;
+  cudaStream_t cs = ctx->comm_stream, cs2 = ctx->comm_stream2;
   const unsigned seq = ++ctx->seq_k, base = (seq - 1) * (unsigned)C;
   cufftHandle plan = C > 1 ? ctx->pc_r2c : ctx->p2d_r2c;
   BR_CUFFT(cufftSetStream(plan, st));
@@ -447,21 +447,27 @@ static int dist_r2c_peer(baorec_ctx* ctx, const float* slab, float2* K, int C, c
   BR_CUDA(cudaEventRecord(ctx->ev_a2a[0], st));   // (orders cs after whatever the caller queued: A is about to be overwritten
   BR_CUDA(cudaStreamWaitEvent(cs, ctx->ev_a2a[0], 0));  //  only by st itself, but RK_d is written from cs)
   BR_TRY(peer_wait(ctx, 2, seq - 1, cs));
+  BR_CUDA(cudaEventRecord(ctx->ev_a2a[2], cs));
+  BR_CUDA(cudaStreamWaitEvent(cs2, ctx->ev_a2a[2], 0));  // (my own K buffer included: the local copies wait too)
   for (int c = 0; c < C; c++) {
     int pi = prof_begin(ctx, "cufft_2d_r2c", st);
     BR_CUFFT(cufftExecR2C(plan, (cufftReal*)(slab + (size_t)c * nzc * rplane), (cufftComplex*)(b.A + (size_t)c * nzc * cplane)));
     prof_end(ctx, pi, st);
     BR_CUDA(cudaEventRecord(ctx->ev_chunk[c], st));
     BR_CUDA(cudaStreamWaitEvent(cs, ctx->ev_chunk[c], 0));
-    pi = prof_begin(ctx, "peer_copies", cs);
+    // this rank's own block is an HBM copy: second stream, beside the NVLink copies
+    BR_CUDA(cudaStreamWaitEvent(cs2, ctx->ev_chunk[c], 0));
     for (int k = 0; k < P; k++) {
       const int d = (ctx->rank + k) % P;  // staggered: at step k every rank writes to a different peer
       const float2* src = b.A + (size_t)c * nzc * cplane + (size_t)d * kplane;
       float2* dst = ctx->peer_recv[0][d] + ((size_t)ctx->rank * nzl + (size_t)c * nzc) * kplane;
+      if (k == 1) pi = prof_begin(ctx, "peer_copies", cs);
       BR_CUDA(cudaMemcpy2DAsync(dst, kplane * sizeof(float2), src, cplane * sizeof(float2), kplane * sizeof(float2),
-                                (size_t)nzc, cudaMemcpyDefault, cs));
+                                (size_t)nzc, cudaMemcpyDefault, k == 0 ? cs2 : cs));
     }
-    prof_end(ctx, pi, cs);
+    if (P > 1) prof_end(ctx, pi, cs);
+    BR_CUDA(cudaEventRecord(ctx->ev_local[c], cs2));
+    BR_CUDA(cudaStreamWaitEvent(cs, ctx->ev_local[c], 0));
     BR_TRY(peer_signal(ctx, 0, base + (unsigned)c + 1u, cs));
   }
   BR_CUDA(cudaEventRecord(ctx->ev_a2a[1], cs));
@@ -487,7 +493,7 @@ static int dist_c2r_peer(baorec_ctx* ctx, float2* K, float* slab, int C, cudaStr
   if (C < 1) C = 1;
   const int nzc = nzl / C;
   const size_t rplane = (size_t)ny * ctx->nx, cplane = (size_t)ny * xh, kplane = (size_t)nyl * xh;
-  cudaStream_t cs = ctx->comm_stream;
+  cudaStream_t cs = ctx->comm_stream, cs2 = ctx->comm_stream2;
   const unsigned seq = ++ctx->seq_a, base = (seq - 1) * (unsigned)C;
   BR_CUFFT(cufftSetStream(ctx->p1d_s, st));
   int pi = prof_begin(ctx, "cufft_1d_z", st);
@@ -497,16 +503,20 @@ static int dist_c2r_peer(baorec_ctx* ctx, float2* K, float* slab, int C, cudaStr
   BR_CUDA(cudaEventRecord(ctx->ev_a2a[0], st));
   BR_CUDA(cudaStreamWaitEvent(cs, ctx->ev_a2a[0], 0));
   BR_TRY(peer_wait(ctx, 3, seq - 1, cs));  // every destination has consumed its plane buffer of the previous inverse
+  BR_CUDA(cudaEventRecord(ctx->ev_a2a[2], cs));
+  BR_CUDA(cudaStreamWaitEvent(cs2, ctx->ev_a2a[2], 0));  // (my own plane buffer included: the local copies wait too)
   for (int c = 0; c < C; c++) {
-    pi = prof_begin(ctx, "peer_copies", cs);
     for (int k = 0; k < P; k++) {
       const int d = (ctx->rank + k) % P;
       const float2* src = K + ((size_t)d * nzl + (size_t)c * nzc) * kplane;
       float2* dst = ctx->peer_recv[1][d] + (size_t)c * nzc * cplane + (size_t)ctx->rank * kplane;
+      if (k == 1) pi = prof_begin(ctx, "peer_copies", cs);
       BR_CUDA(cudaMemcpy2DAsync(dst, cplane * sizeof(float2), src, kplane * sizeof(float2), kplane * sizeof(float2),
-                                (size_t)nzc, cudaMemcpyDefault, cs));
+                                (size_t)nzc, cudaMemcpyDefault, k == 0 ? cs2 : cs));
     }
-    prof_end(ctx, pi, cs);
+    if (P > 1) prof_end(ctx, pi, cs);
+    BR_CUDA(cudaEventRecord(ctx->ev_local[c], cs2));
+    BR_CUDA(cudaStreamWaitEvent(cs, ctx->ev_local[c], 0));
     BR_TRY(peer_signal(ctx, 1, base + (unsigned)c + 1u, cs));
   }
   BR_CUDA(cudaEventRecord(ctx->ev_a2a[1], cs));

@@ -194,6 +194,7 @@ struct baorec_ctx {
   const float *sortc_x = nullptr, *sortc_y = nullptr, *sortc_z = nullptr;
   int64_t sortc_n = 0;
   unsigned sortc_ntiles = 0;
+  int sortc_slab_mode = 0;  // 0: whole-mesh tiles; 2: tiles of the slab's gather layout (the sort was made by a slab scatter)
   unsigned long long* d_hash = nullptr;  // [0] hash at sort time, [1] hash at read time, [2] match flag
   int64_t n_sort_reuse = 0;              // read-backs that reused the run!'s sort (diagnostics)
   int opt_gather_tiles = 1;    // gather: fine (z, y/8, x/128) tile binning instead of z slabs
@@ -254,7 +255,8 @@ struct baorec_ctx {
   int chunk_planes = 0;  // planes per chunk the chunk plans were made for (0 = none)
   int opt_a2a_chunks = 4;
   cudaStream_t comm_stream = nullptr;
-  cudaEvent_t ev_chunk[8] = {}, ev_a2a[8] = {};
+  cudaStream_t comm_stream2 = nullptr;  // the local 1/P block of a peer-copy exchange (an HBM copy) runs beside the NVLink copies
+  cudaEvent_t ev_chunk[8] = {}, ev_a2a[8] = {}, ev_local[8] = {};
   // catalog pre/post-processing (catalog.cu): comoving-distance table r(z) on uniform z knots
   double* d_cosmo_r = nullptr;
   std::vector<double> h_cosmo_r;

@@ -16,7 +16,7 @@
 
 namespace baorec {
 
-static BoxGeom geom_of(const baorec_ctx* ctx) {
+static BoxGeom geom_for(const baorec_ctx* ctx, int slab_mode) {
   BoxGeom g;
   for (int a = 0; a < 3; a++) {
     g.mn[a] = ctx->mn[a];
@@ -26,14 +26,15 @@ static BoxGeom geom_of(const baorec_ctx* ctx) {
   g.n[0] = ctx->nx;
   g.n[1] = ctx->ny;
   g.n[2] = ctx->nz;
-  g.slab = ctx->slab_mode != 0;
+  g.slab = slab_mode != 0;
   g.z_lo = g.slab ? ctx->z0 : 0;
   // slab_mode 1: CIC scatter (one ghost plane above); 2: gather (one halo plane below, two above);
   // 3: TSC scatter (one ghost plane below, two above -- the same layout as the gather's)
-  g.zoff = ctx->slab_mode >= 2 ? 1 : 0;
-  g.nzp = ctx->slab_mode == 1 ? ctx->nz_loc + 1 : (ctx->slab_mode >= 2 ? ctx->nz_loc + 3 : ctx->nz);
+  g.zoff = slab_mode >= 2 ? 1 : 0;
+  g.nzp = slab_mode == 1 ? ctx->nz_loc + 1 : (slab_mode >= 2 ? ctx->nz_loc + 3 : ctx->nz);
   return g;
 }
+static BoxGeom geom_of(const baorec_ctx* ctx) { return geom_for(ctx, ctx->slab_mode); }
 
 // read_cic! (src/mas.jl:258-265): sum of field*wx*wy*wz, left-associated, in the order
 // ddd,ddu,dud,duu,udd,udu,uud,uuu (letters = x,y,z); then the read_shifts epilogue
@@ -966,7 +967,10 @@ static int tile_scratch(baorec_ctx* ctx, const TileGeom& t, TileScratch* s) {
 static int unified_sort(baorec_ctx* ctx, float* x, float* y, float* z, const float* w, int64_t n, int wrap,
                         cudaStream_t st, BinResult* out) {
   ctx->sortc_valid = false;
-  BoxGeom g = geom_of(ctx);
+  // the key is the GATHER's tile: on a slab that is the gather's halo layout (mode 2: one plane below, two above the
+  // slab), whatever layout the scatter that called us deposits into (mode 1: one ghost plane above)
+  const int key_mode = ctx->slab_mode ? 2 : 0;
+  BoxGeom g = geom_for(ctx, key_mode);
   TileGeom t;
   t.nxc = (ctx->nx + TILE_X - 1) / TILE_X;
   t.nyc = (ctx->ny + TILE_Y - 1) / TILE_Y;
@@ -996,6 +1000,7 @@ static int unified_sort(baorec_ctx* ctx, float* x, float* y, float* z, const flo
   ctx->sortc_z = z;
   ctx->sortc_n = n;
   ctx->sortc_ntiles = t.ntiles;
+  ctx->sortc_slab_mode = key_mode;
   ctx->sortc_valid = true;
   return BAOREC_OK;
 }
@@ -1005,8 +1010,8 @@ static int unified_sort(baorec_ctx* ctx, float* x, float* y, float* z, const flo
 static int sort_cache_hit(baorec_ctx* ctx, const float* x, const float* y, const float* z, int64_t n, cudaStream_t st,
                           bool* hit) {
   *hit = false;
-  if (!ctx->sortc_valid || ctx->slab_mode != 0 || ctx->sortc_x != x || ctx->sortc_y != y || ctx->sortc_z != z ||
-      ctx->sortc_n != n)
+  if (!ctx->sortc_valid || ctx->slab_mode != ctx->sortc_slab_mode || ctx->sortc_x != x || ctx->sortc_y != y ||
+      ctx->sortc_z != z || ctx->sortc_n != n)
     return BAOREC_OK;
   BR_CUDA(cudaMemsetAsync(ctx->d_hash + 1, 0, sizeof(unsigned long long), st));
   unsigned grid = cdiv((size_t)n, 256 * 8);
@@ -1051,7 +1056,7 @@ int scatter(baorec_ctx* ctx, float* rho, float* x, float* y, float* z, const flo
     BR_LAUNCH(ctx, fixed_to_float_kernel, (unsigned)blocks, 256, 0, st, rho, acc, ctx->M);
     return BAOREC_OK;
   }
-  if (use_binning(ctx, n) && ctx->opt_unified_sort && !tsc && ctx->slab_mode == 0 && ctx->opt_gather_tiles) {
+  if (use_binning(ctx, n) && ctx->opt_unified_sort && !tsc && ctx->slab_mode <= 1 && ctx->opt_gather_tiles) {
     BinResult b;
     BR_TRY(unified_sort(ctx, x, y, z, w, n, wrap, st, &b));
     if (ctx->opt_scatter_pairs >= 2 && ((uintptr_t)rho & 15) == 0)
@@ -1089,8 +1094,8 @@ int gather_prebin(baorec_ctx* ctx, const float* x, const float* y, const float* 
   ctx->prebin_valid = false;
   if (!ctx->opt_overlap_sort || n == 0 || !use_binning(ctx, n) || !ctx->opt_gather_tiles || mas == BAOREC_MAS_TSC)
     return BAOREC_OK;
-  if (ctx->sortc_valid && ctx->slab_mode == 0 && ctx->sortc_x == x && ctx->sortc_y == y && ctx->sortc_z == z &&
-      ctx->sortc_n == n)
+  if (ctx->sortc_valid && ctx->slab_mode == ctx->sortc_slab_mode && ctx->sortc_x == x && ctx->sortc_y == y &&
+      ctx->sortc_z == z && ctx->sortc_n == n)
     return BAOREC_OK;  // candidate for the sort run! kept: gather3 validates and reuses it
   ctx->sortc_valid = false;
   BR_CUDA(cudaEventRecord(ctx->ev_fork, st));

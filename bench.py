@@ -499,7 +499,8 @@ def main():
     if world > 1:
         # The exchange of the slab transforms: every rank sends (P-1)/P of its complex slab per transform.  At N > 1
         # this, not an HBM kernel, is what bounds the step, so it is the line's roofline (rank 0's CUDA-event time of
-        # the copies on the communication stream; the local 1/P block is an HBM copy inside the same timed span).
+        # the P-1 remote copies per chunk on the communication stream; the local 1/P block is an HBM copy on a second
+        # stream and is not in the span).
         name = "peer_copies" if "peer_copies" in prof else "nccl_all_to_all"
         if name in prof:
             ms, cnt = prof[name]

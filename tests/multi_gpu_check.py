@@ -35,8 +35,8 @@ def more_modes(B, ctx, rank, world, quick=False):
     def put(a, mine):
         return torch.from_numpy(np.ascontiguousarray(a[mine])).cuda()
 
-    def report(tag, e_mesh, e_rms, e_max):
-        good = e_mesh < 1e-4 and e_rms < 1e-4 and e_max < 1e-3
+    def report(tag, e_mesh, e_rms, e_max, tol_max=1e-3):
+        good = e_mesh < 1e-4 and e_rms < 1e-4 and e_max < tol_max
         print(f"[rank {rank}/{world}] {tag}: mesh rel.rms={e_mesh:.2e} shift rel.rms={e_rms:.2e} "
               f"max={e_max:.2e} {'OK' if good else 'FAIL'}", flush=True)
         return good
@@ -83,6 +83,15 @@ def more_modes(B, ctx, rank, world, quick=False):
                 orec, rec = O.MultigridRecon(**kw), B.MultigridRecon(**kw)
                 omesh = O.reconstructed_potential(np.zeros((n, n, n), np.float32), orec, *dd, wd, *rr, wr)
             oshift = O.read_shifts(orec, *dd, omesh, "sum")
+            # yardstick for max |ds| (as in tests/test_gpu_multigrid.py): 1 / (alpha ran) amplifies Float32 rounding in the
+            # sparse cells and the multigrid solve spreads it, so the Float32 oracle's own distance to the Float64
+            # oracle bounds what any Float32 summation order can promise (first 2-rank run: 0.6 - 1.1e-3 Mpc/h here)
+            d64, r64 = [q.astype(np.float64) for q in dd], [q.astype(np.float64) for q in rr]
+            o64 = (O.IterativeRecon if algo == "iterative" else O.MultigridRecon)(**kw)
+            run64 = O.reconstructed_overdensity if algo == "iterative" else O.reconstructed_potential
+            m64 = run64(np.zeros((n, n, n), np.float64), o64, *d64, wd.astype(np.float64), *r64, wr.astype(np.float64))
+            s64 = O.read_shifts(o64, *d64, m64, "sum")
+            tol_max = max(1e-3, 3 * max(maxabs(oshift[a], s64[a]) for a in range(3)))
             gd = [put(p, md) for p in dd]
             mesh = B.dist.run_dist(rec, (n, n, n), *gd, put(wd, md), *[put(p, mr) for p in rr], put(wr, mr), ctx=ctx)
             z_lo, nzl = B.dist.slab_range(ctx)
@@ -97,7 +106,7 @@ def more_modes(B, ctx, rank, world, quick=False):
             s = B.dist.read_shifts_dist(rec, *gd, field="sum")
             ok &= report(f"{algo} randoms los={los}", e_mesh,
                          max(rel_rms(s[a].cpu().numpy(), oshift[a][md]) for a in range(3)),
-                         max(maxabs(s[a].cpu().numpy(), oshift[a][md]) for a in range(3)))
+                         max(maxabs(s[a].cpu().numpy(), oshift[a][md]) for a in range(3)), tol_max)
     ctx.set_option("mg_slab_min_cells", 1 << 22)
     return ok
 
