@@ -186,23 +186,30 @@ __global__ void set_scalar_kernel(double* p, double v) { *p = v; }
 // ---- peer-copy exchange: flags --------------------------------------------------------------------------------
 // Every rank owns one PeerFlags block (device memory, mapped by all peers through CUDA IPC).  Peers WRITE into it,
 // the owner spins on it: sequence numbers only ever grow, so a late reader never misses a signal.
-//   arrK[s] / arrA[s]   chunks of the forward / inverse exchange that rank s has finished copying into my buffer
-//   freeK[d] / freeA[d] transforms after which rank d has finished reading ITS receive buffer (I may overwrite it)
+//   ARR_*[s]   chunks (or calls) of an exchange that rank s has finished copying into my buffer
+//   FREE_*[d]  transforms (calls) after which rank d has finished reading ITS receive buffer (I may overwrite it)
+// K = k-layout buffer of the forward transform; A0 / A1 = the two plane-layout buffers of the inverse transforms
+// (two, so that the exchange of one displacement field overlaps the transforms of the other).
+enum PeerFlagId { F_ARR_K = 0, F_FREE_K, F_ARR_A0, F_FREE_A0, F_ARR_A1, F_FREE_A1,
+                  F_ARR_S0, F_FREE_S0, F_ARR_B0, F_FREE_B0, F_ARR_S1, F_FREE_S1, F_ARR_B1, F_FREE_B1, F_COUNT = 16 };  // S: sharded catalog, B: results coming back; 0 data, 1 randoms
 struct PeerFlags {
-  unsigned arrK[16], arrA[16], freeK[16], freeA[16];
+  unsigned w[F_COUNT][16];
   unsigned err, pad[15];
 };
 struct FlagTab {
   unsigned* p[16];
 };
 
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+// System-scope RELAXED accesses, no fences: the ordering comes from the stream.  The copies a flag announces are
+// earlier operations of the signalling stream (complete, i.e. performed in the peer's memory, before the flag kernel
+// starts), and whatever consumes the data is a later kernel of the waiting stream.
+__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
@@ -213,10 +220,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // thread t stores `value` into rank t's flag word for this rank (stream order puts it after the copies it announces)
 __global__ void peer_signal_kernel(const __grid_constant__ FlagTab tab, unsigned value, int P) {
   const int t = threadIdx.x;
-  if (t < P) {
-    __threadfence_system();
-    st_release_sys(tab.p[t], value);
-  }
+  if (t < P) st_relaxed_sys(tab.p[t], value);
 }
 
 // thread t waits until flags[t] >= value (wrap-safe); gives up after ~20 s and raises the error flag instead of
@@ -225,7 +229,7 @@ __global__ void peer_wait_kernel(const unsigned* flags, unsigned value, int P, u
   const int t = threadIdx.x;
   if (t < P) {
     const unsigned long long t0 = global_ns();
-    while ((int)(ld_acquire_sys(flags + t) - value) < 0) {
+    while ((int)(ld_relaxed_sys(flags + t) - value) < 0) {
       __nanosleep(200);
       if (global_ns() - t0 > 20000000000ull) {
         atomicExch(err, 1u);
@@ -238,13 +242,12 @@ __global__ void peer_wait_kernel(const unsigned* flags, unsigned value, int P, u
 
 static PeerFlags* own_flags(const baorec_ctx* ctx) { return (PeerFlags*)ctx->d_flags; }
 
-// which: 0 arrK, 1 arrA, 2 freeK, 3 freeA -- the word of every peer's block that belongs to this rank
+// the word of every peer's block that belongs to this rank
 static FlagTab flag_tab(const baorec_ctx* ctx, int which) {
   FlagTab t;
   for (int r = 0; r < 16; r++) {
     PeerFlags* f = (PeerFlags*)ctx->peer_flags[r];
-    unsigned* base = f ? (which == 0 ? f->arrK : which == 1 ? f->arrA : which == 2 ? f->freeK : f->freeA) : nullptr;
-    t.p[r] = base ? base + ctx->rank : nullptr;
+    t.p[r] = f ? f->w[which] + ctx->rank : nullptr;
   }
   return t;
 }
@@ -257,8 +260,7 @@ static int peer_signal(baorec_ctx* ctx, int which, unsigned value, cudaStream_t 
 static int peer_wait(baorec_ctx* ctx, int which, unsigned value, cudaStream_t st) {
   if (value == 0) return BAOREC_OK;
   PeerFlags* f = own_flags(ctx);
-  const unsigned* w = which == 0 ? f->arrK : which == 1 ? f->arrA : which == 2 ? f->freeK : f->freeA;
-  BR_LAUNCH(ctx, peer_wait_kernel, 1, 32, 0, st, w, value, ctx->nranks, &f->err);
+  BR_LAUNCH(ctx, peer_wait_kernel, 1, 32, 0, st, f->w[which], value, ctx->nranks, &f->err);
   return BAOREC_OK;
 }
 
@@ -446,7 +448,7 @@ static int dist_r2c_peer(baorec_ctx* ctx, const float* slab, float2* K, int C, c
   // every destination must have finished reading its K buffer of the previous forward transform
   BR_CUDA(cudaEventRecord(ctx->ev_a2a[0], st));   // (orders cs after whatever the caller queued: A is about to be overwritten
   BR_CUDA(cudaStreamWaitEvent(cs, ctx->ev_a2a[0], 0));  //  only by st itself, but RK_d is written from cs)
-  BR_TRY(peer_wait(ctx, 2, seq - 1, cs));
+  BR_TRY(peer_wait(ctx, F_FREE_K, seq - 1, cs));
   BR_CUDA(cudaEventRecord(ctx->ev_a2a[2], cs));
   BR_CUDA(cudaStreamWaitEvent(cs2, ctx->ev_a2a[2], 0));  // (my own K buffer included: the local copies wait too)
   for (int c = 0; c < C; c++) {
@@ -468,48 +470,66 @@ static int dist_r2c_peer(baorec_ctx* ctx, const float* slab, float2* K, int C, c
     if (P > 1) prof_end(ctx, pi, cs);
     BR_CUDA(cudaEventRecord(ctx->ev_local[c], cs2));
     BR_CUDA(cudaStreamWaitEvent(cs, ctx->ev_local[c], 0));
-    BR_TRY(peer_signal(ctx, 0, base + (unsigned)c + 1u, cs));
+    BR_TRY(peer_signal(ctx, F_ARR_K, base + (unsigned)c + 1u, cs));
   }
   BR_CUDA(cudaEventRecord(ctx->ev_a2a[1], cs));
   ctx->n_fft++;
-  BR_TRY(peer_wait(ctx, 0, base + (unsigned)C, st));  // all chunks of all ranks have landed in my K buffer
+  BR_TRY(peer_wait(ctx, F_ARR_K, base + (unsigned)C, st));  // all chunks of all ranks have landed in my K buffer
   BR_CUFFT(cufftSetStream(ctx->p1d_s, st));
   int pi = prof_begin(ctx, "cufft_1d_z", st);
   BR_CUFFT(cufftExecC2C(ctx->p1d_s, (cufftComplex*)ctx->own_recv[0], (cufftComplex*)K, CUFFT_FORWARD));
   prof_end(ctx, pi, st);
   ctx->n_fft++;
-  BR_TRY(peer_signal(ctx, 2, seq, st));                    // my K receive buffer may be overwritten
+  BR_TRY(peer_signal(ctx, F_FREE_K, seq, st));                  // my K receive buffer may be overwritten
   BR_CUDA(cudaStreamWaitEvent(st, ctx->ev_a2a[1], 0));     // A may be reused once my own copies have left it
   return BAOREC_OK;
 }
 
 // Inverse: K[z][yl][x] (destroyed) -> slab.  Rank d's planes are the contiguous block K[d nzl .. (d+1) nzl); they go
 // into rank d's plane-layout buffer RA_d[zl][rank nyl + yl][x] with one strided copy per (peer, chunk); the 2-D C2R of
-// chunk c starts as soon as chunk c has arrived from every rank.
-static int dist_c2r_peer(baorec_ctx* ctx, float2* K, float* slab, int C, cudaStream_t st) {
-  DistBufs b;
-  BR_TRY(dist_bufs(ctx, &b));
+// chunk c starts as soon as chunk c has arrived from every rank.  Three phases, so that a caller can start the
+// exchange of a second field (buffer slot 1) while the first is in flight:
+//   c2r_peer_send  : z transform, then the copies + one flag per chunk (communication streams)
+//   c2r_peer_wait  : chunk c of `slot` has arrived from every rank (main stream)
+//   c2r_peer_done  : my plane buffer may be overwritten; K may be reused once my own copies have left it
+struct C2RPeer {
+  int slot, C, nzc;
+  unsigned seq, base;
+  size_t cplane, rplane;
+  float2* RA;  // my plane-layout receive buffer of this slot
+};
+
+static int c2r_peer_send(baorec_ctx* ctx, float2* K, int slot, int C, C2RPeer* h, cudaStream_t st) {
   const int P = ctx->nranks, nzl = ctx->nz_loc, nyl = ctx->ny_loc, ny = ctx->ny, xh = ctx->xh;
   if (C < 1) C = 1;
-  const int nzc = nzl / C;
-  const size_t rplane = (size_t)ny * ctx->nx, cplane = (size_t)ny * xh, kplane = (size_t)nyl * xh;
+  h->slot = slot;
+  h->C = C;
+  h->nzc = nzl / C;
+  h->rplane = (size_t)ny * ctx->nx;
+  h->cplane = (size_t)ny * xh;
+  h->RA = ctx->own_recv[1 + slot];
+  const size_t cplane = h->cplane, kplane = (size_t)nyl * xh;
+  const int nzc = h->nzc;
   cudaStream_t cs = ctx->comm_stream, cs2 = ctx->comm_stream2;
-  const unsigned seq = ++ctx->seq_a, base = (seq - 1) * (unsigned)C;
+  h->seq = ++ctx->seq_a[slot];
+  h->base = (h->seq - 1) * (unsigned)C;
+  const int f_arr = slot ? F_ARR_A1 : F_ARR_A0, f_free = slot ? F_FREE_A1 : F_FREE_A0;
+  cudaEvent_t ev_z = ctx->ev_a2a[slot ? 4 : 0], ev_w = ctx->ev_a2a[slot ? 5 : 2];
   BR_CUFFT(cufftSetStream(ctx->p1d_s, st));
   int pi = prof_begin(ctx, "cufft_1d_z", st);
   BR_CUFFT(cufftExecC2C(ctx->p1d_s, (cufftComplex*)K, (cufftComplex*)K, CUFFT_INVERSE));
   prof_end(ctx, pi, st);
   ctx->n_fft++;
-  BR_CUDA(cudaEventRecord(ctx->ev_a2a[0], st));
-  BR_CUDA(cudaStreamWaitEvent(cs, ctx->ev_a2a[0], 0));
-  BR_TRY(peer_wait(ctx, 3, seq - 1, cs));  // every destination has consumed its plane buffer of the previous inverse
-  BR_CUDA(cudaEventRecord(ctx->ev_a2a[2], cs));
-  BR_CUDA(cudaStreamWaitEvent(cs2, ctx->ev_a2a[2], 0));  // (my own plane buffer included: the local copies wait too)
+  BR_CUDA(cudaEventRecord(ev_z, st));
+  BR_CUDA(cudaStreamWaitEvent(cs, ev_z, 0));
+  BR_TRY(peer_wait(ctx, f_free, h->seq - 1, cs));  // every destination has consumed this slot's buffer of the previous inverse
+  BR_CUDA(cudaEventRecord(ev_w, cs));
+  BR_CUDA(cudaStreamWaitEvent(cs2, ev_w, 0));  // (my own plane buffer included: the local copies wait too)
   for (int c = 0; c < C; c++) {
     for (int k = 0; k < P; k++) {
       const int d = (ctx->rank + k) % P;
       const float2* src = K + ((size_t)d * nzl + (size_t)c * nzc) * kplane;
-      float2* dst = ctx->peer_recv[1][d] + (size_t)c * nzc * cplane + (size_t)ctx->rank * kplane;
+      float2* dst = ctx->peer_recv[1 + slot][d] + (size_t)c * nzc * cplane + (size_t)ctx->rank * kplane;
       if (k == 1) pi = prof_begin(ctx, "peer_copies", cs);
       BR_CUDA(cudaMemcpy2DAsync(dst, cplane * sizeof(float2), src, kplane * sizeof(float2), kplane * sizeof(float2),
                                 (size_t)nzc, cudaMemcpyDefault, k == 0 ? cs2 : cs));
@@ -517,22 +537,95 @@ static int dist_c2r_peer(baorec_ctx* ctx, float2* K, float* slab, int C, cudaStr
     if (P > 1) prof_end(ctx, pi, cs);
     BR_CUDA(cudaEventRecord(ctx->ev_local[c], cs2));
     BR_CUDA(cudaStreamWaitEvent(cs, ctx->ev_local[c], 0));
-    BR_TRY(peer_signal(ctx, 1, base + (unsigned)c + 1u, cs));
+    BR_TRY(peer_signal(ctx, f_arr, h->base + (unsigned)c + 1u, cs));
   }
-  BR_CUDA(cudaEventRecord(ctx->ev_a2a[1], cs));
+  BR_CUDA(cudaEventRecord(ctx->ev_a2a[slot ? 3 : 1], cs));
+  return BAOREC_OK;
+}
+
+static int c2r_peer_wait(baorec_ctx* ctx, const C2RPeer& h, int c, cudaStream_t st) {
+  return peer_wait(ctx, h.slot ? F_ARR_A1 : F_ARR_A0, h.base + (unsigned)c + 1u, st);
+}
+
+static int c2r_peer_done(baorec_ctx* ctx, const C2RPeer& h, cudaStream_t st) {
+  BR_TRY(peer_signal(ctx, h.slot ? F_FREE_A1 : F_FREE_A0, h.seq, st));
+  BR_CUDA(cudaStreamWaitEvent(st, ctx->ev_a2a[h.slot ? 3 : 1], 0));
+  return BAOREC_OK;
+}
+
+static int c2r_2d_chunk(baorec_ctx* ctx, int C, float2* in_planes, float* slab, int c, int nzc, size_t cplane, size_t rplane,
+                        cudaStream_t st) {
   cufftHandle plan = C > 1 ? ctx->pc_c2r : ctx->p2d_c2r;
   BR_CUFFT(cufftSetStream(plan, st));
-  for (int c = 0; c < C; c++) {
-    BR_TRY(peer_wait(ctx, 1, base + (unsigned)c + 1u, st));
-    pi = prof_begin(ctx, "cufft_2d_c2r", st);
-    BR_CUFFT(cufftExecC2R(plan, (cufftComplex*)(ctx->own_recv[1] + (size_t)c * nzc * cplane),
-                          (cufftReal*)(slab + (size_t)c * nzc * rplane)));
-    prof_end(ctx, pi, st);
+  int pi = prof_begin(ctx, "cufft_2d_c2r", st);
+  BR_CUFFT(cufftExecC2R(plan, (cufftComplex*)(in_planes + (size_t)c * nzc * cplane), (cufftReal*)(slab + (size_t)c * nzc * rplane)));
+  prof_end(ctx, pi, st);
+  return BAOREC_OK;
+}
+
+static int dist_c2r_peer(baorec_ctx* ctx, float2* K, float* slab, int C, cudaStream_t st) {
+  DistBufs b;
+  BR_TRY(dist_bufs(ctx, &b));
+  C2RPeer h;
+  BR_TRY(c2r_peer_send(ctx, K, 0, C, &h, st));
+  for (int c = 0; c < h.C; c++) {
+    BR_TRY(c2r_peer_wait(ctx, h, c, st));
+    BR_TRY(c2r_2d_chunk(ctx, h.C, h.RA, slab, c, h.nzc, h.cplane, h.rplane, st));
   }
   ctx->n_fft++;
-  BR_TRY(peer_signal(ctx, 3, seq, st));                    // my plane buffer may be overwritten
-  BR_CUDA(cudaStreamWaitEvent(st, ctx->ev_a2a[1], 0));     // K may be reused once my own copies have left it
-  return BAOREC_OK;
+  return c2r_peer_done(ctx, h, st);
+}
+
+// i k_x G and i k_y G of a chunk of planes G[zl][y][x] (plane layout, after the z transform and the exchange):
+// X overwrites G, Y goes to `y_out`.  The multiplications commute with the z transform, so the x and y displacement
+// fields share ONE inverse z transform and ONE exchange (DispGHOp below makes G and the z field H).
+__global__ void __launch_bounds__(256)
+disp_xy_planes_kernel(float2* __restrict__ g_io, float2* __restrict__ y_out, const float* __restrict__ kx,
+                      const float* __restrict__ ky, int xh, int ny, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned row = (unsigned)(i / (unsigned)xh);
+    const unsigned ix = (unsigned)(i - (size_t)row * xh), iy = row % (unsigned)ny;
+    const float2 v = g_io[i];
+    const float kxv = __ldg(kx + ix), kyv = __ldg(ky + iy);
+    g_io[i] = make_float2(__fmul_rn(-v.y, kxv), __fmul_rn(v.x, kxv));
+    y_out[i] = make_float2(__fmul_rn(-v.y, kyv), __fmul_rn(v.x, kyv));
+  }
+}
+
+// The three displacement slabs from the kept delta_k (phi_k): TWO inverse z transforms and TWO exchanges (G for x and
+// y, H for z) instead of three, software-pipelined over the two plane buffers.  psi[c] point at plane 1 of the
+// (nzl + 3)-plane halo buffers.
+static int dist_displacements_peer(baorec_ctx* ctx, const float2* keep, bool potential, float* psi[3], cudaStream_t st) {
+  DistBufs b;
+  BR_TRY(dist_bufs(ctx, &b));
+  const size_t slab_c = (size_t)ctx->nz_loc * ctx->ny * ctx->xh;
+  float2* KH;
+  BR_TRY(need_t(ctx, BUF_CK2, slab_c, &KH));
+  float2* KG = b.T;
+  int C = 0;
+  BR_TRY(chunk_setup(ctx, &C));
+  BR_TRY(kpass_disp_gh(ctx, keep, KG, KH, potential, st));
+  C2RPeer hh, hg;
+  BR_TRY(c2r_peer_send(ctx, KH, 0, C, &hh, st));
+  BR_TRY(c2r_peer_send(ctx, KG, 1, C, &hg, st));   // its z transform runs while H is on the wire
+  for (int c = 0; c < hh.C; c++) {
+    BR_TRY(c2r_peer_wait(ctx, hh, c, st));
+    BR_TRY(c2r_2d_chunk(ctx, hh.C, hh.RA, psi[2], c, hh.nzc, hh.cplane, hh.rplane, st));
+  }
+  ctx->n_fft++;
+  BR_TRY(c2r_peer_done(ctx, hh, st));
+  for (int c = 0; c < hg.C; c++) {
+    BR_TRY(c2r_peer_wait(ctx, hg, c, st));
+    const size_t cnt = (size_t)hg.nzc * hg.cplane;
+    float2* gx = hg.RA + (size_t)c * cnt;
+    float2* gy = b.A + (size_t)c * cnt;
+    BR_LAUNCH(ctx, disp_xy_planes_kernel, 148 * 8, 256, 0, st, gx, gy, ctx->d_k[0], ctx->d_k[1], ctx->xh, ctx->ny, cnt);
+    BR_TRY(c2r_2d_chunk(ctx, hg.C, hg.RA, psi[0], c, hg.nzc, hg.cplane, hg.rplane, st));
+    BR_TRY(c2r_2d_chunk(ctx, hg.C, b.A, psi[1], c, hg.nzc, hg.cplane, hg.rplane, st));
+  }
+  ctx->n_fft += 2;
+  return c2r_peer_done(ctx, hg, st);
 }
 
 // slab[nz_loc][ny][nx] (real) -> T[ny_loc][xh][nz] (unnormalised forward transform)
@@ -616,7 +709,8 @@ static int dist_c2r(baorec_ctx* ctx, float2* T, float* slab, cudaStream_t st) {
 // peer copies are used when the option asks for them AND every rank's buffers and flags are mapped
 void dist_refresh_mode(baorec_ctx* ctx) {
   bool ok = ctx->opt_dist_exchange != 0 && ctx->d_flags != nullptr;
-  for (int r = 0; r < ctx->nranks && ok; r++) ok = ctx->peer_recv[0][r] && ctx->peer_recv[1][r] && ctx->peer_flags[r];
+  for (int r = 0; r < ctx->nranks && ok; r++)
+    ok = ctx->peer_recv[0][r] && ctx->peer_recv[1][r] && ctx->peer_recv[2][r] && ctx->peer_flags[r];
   if (ok != ctx->p2p) {  // the k-space layout changes with the scheme: cached k-space meshes are void
     ctx->kcache_valid = false;
     ctx->disp_valid = false;
@@ -637,6 +731,8 @@ void dist_refresh_mode(baorec_ctx* ctx) {
   } while (0)
 
 extern "C" {
+
+static void shard_close_peers(baorec_ctx* ctx, int slot);
 
 int baorec_comm_unique_id(void* out128) {
   BR_REQUIRE(out128 != nullptr, "out128 is NULL");
@@ -669,7 +765,7 @@ int baorec_comm_init(baorec_ctx* ctx, int rank, int nranks, const void* unique_i
 
 static void close_ipc(baorec_ctx* ctx) {
   for (int r = 0; r < 16; r++) {
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < 3; k++) {
       if (ctx->peer_recv[k][r] && ctx->peer_recv[k][r] != ctx->own_recv[k]) cudaIpcCloseMemHandle(ctx->peer_recv[k][r]);
       ctx->peer_recv[k][r] = nullptr;
     }
@@ -683,6 +779,8 @@ static void close_ipc(baorec_ctx* ctx) {
 int baorec_comm_destroy_internal(baorec_ctx* ctx) {
   if (ctx) {
     close_ipc(ctx);
+    shard_close_peers(ctx, 0);
+    shard_close_peers(ctx, 1);
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     ctx->d_flags = nullptr;
   }
@@ -758,9 +856,11 @@ int baorec_plan_dist(baorec_ctx* ctx, int nx, int ny, int nz, const float box_si
     const size_t slab_c = (size_t)nzl * ny * (nx / 2 + 1);
     void* r0 = ctx->bufs[BUF_A2A_RECV].p;
     void* r1 = ctx->bufs[BUF_A2A_RECV2].p;
+    void* r2 = ctx->bufs[BUF_A2A_RECV3].p;
     BR_TRY(need_t(ctx, BUF_A2A_RECV, slab_c, &ctx->own_recv[0]));
     BR_TRY(need_t(ctx, BUF_A2A_RECV2, slab_c, &ctx->own_recv[1]));
-    if (r0 != ctx->own_recv[0] || r1 != ctx->own_recv[1]) {  // re-export needed
+    BR_TRY(need_t(ctx, BUF_A2A_RECV3, slab_c, &ctx->own_recv[2]));
+    if (r0 != ctx->own_recv[0] || r1 != ctx->own_recv[1] || r2 != ctx->own_recv[2]) {  // re-export needed
       close_ipc(ctx);
     }
     if (!ctx->d_flags) {
@@ -769,8 +869,7 @@ int baorec_plan_dist(baorec_ctx* ctx, int nx, int ny, int nz, const float box_si
     }
     if (P == 1) {
       // a single rank is its own (only) peer: the peer-copy path runs with local copies and local flags
-      ctx->peer_recv[0][0] = ctx->own_recv[0];
-      ctx->peer_recv[1][0] = ctx->own_recv[1];
+      for (int k = 0; k < 3; k++) ctx->peer_recv[k][0] = ctx->own_recv[k];
       ctx->peer_flags[0] = ctx->d_flags;
     }
     dist_refresh_mode(ctx);
@@ -793,21 +892,21 @@ int baorec_dist_ipc_close(baorec_ctx* ctx) {
   return BAOREC_OK;
 }
 
-int baorec_dist_ipc_export(baorec_ctx* ctx, void* out192) {
+int baorec_dist_ipc_export(baorec_ctx* ctx, void* out256) {
   BR_NEED_DIST(ctx);
-  BR_REQUIRE(out192 != nullptr, "out192 is NULL");
+  BR_REQUIRE(out256 != nullptr, "out256 is NULL");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
   // A new generation of the exchange starts here: every rank calls this before the handles are gathered (a
   // synchronisation point of the caller), so no peer can have written a flag of the new generation yet.
   BR_CUDA(cudaDeviceSynchronize());
   BR_CUDA(cudaMemset(ctx->d_flags, 0, sizeof(PeerFlags)));
   BR_CUDA(cudaDeviceSynchronize());
-  ctx->seq_k = ctx->seq_a = 0;
-  cudaIpcMemHandle_t h[3];
-  BR_CUDA(cudaIpcGetMemHandle(&h[0], ctx->own_recv[0]));
-  BR_CUDA(cudaIpcGetMemHandle(&h[1], ctx->own_recv[1]));
-  BR_CUDA(cudaIpcGetMemHandle(&h[2], ctx->d_flags));
-  memcpy(out192, h, sizeof(h));
+  ctx->seq_k = ctx->seq_a[0] = ctx->seq_a[1] = 0;
+  for (int k = 0; k < 2; k++) ctx->seq_shard[k][0] = ctx->seq_shard[k][1] = 0;
+  cudaIpcMemHandle_t h[4];
+  for (int k = 0; k < 3; k++) BR_CUDA(cudaIpcGetMemHandle(&h[k], ctx->own_recv[k]));
+  BR_CUDA(cudaIpcGetMemHandle(&h[3], ctx->d_flags));
+  memcpy(out256, h, sizeof(h));
   return BAOREC_OK;
 }
 
@@ -818,16 +917,14 @@ int baorec_dist_ipc_open(baorec_ctx* ctx, const void* all_handles, int nranks) {
   close_ipc(ctx);
   for (int r = 0; r < nranks; r++) {
     if (r == ctx->rank) {
-      ctx->peer_recv[0][r] = ctx->own_recv[0];
-      ctx->peer_recv[1][r] = ctx->own_recv[1];
+      for (int k = 0; k < 3; k++) ctx->peer_recv[k][r] = ctx->own_recv[k];
       ctx->peer_flags[r] = ctx->d_flags;
       continue;
     }
-    void* p[3] = {nullptr, nullptr, nullptr};
-    for (int k = 0; k < 3; k++) BR_CUDA(cudaIpcOpenMemHandle(&p[k], h[3 * r + k], cudaIpcMemLazyEnablePeerAccess));
-    ctx->peer_recv[0][r] = (float2*)p[0];
-    ctx->peer_recv[1][r] = (float2*)p[1];
-    ctx->peer_flags[r] = p[2];
+    void* p[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < 4; k++) BR_CUDA(cudaIpcOpenMemHandle(&p[k], h[4 * r + k], cudaIpcMemLazyEnablePeerAccess));
+    for (int k = 0; k < 3; k++) ctx->peer_recv[k][r] = (float2*)p[k];
+    ctx->peer_flags[r] = p[3];
   }
   dist_refresh_mode(ctx);
   return BAOREC_OK;
@@ -968,6 +1065,73 @@ unshard_gather_kernel(const unsigned* __restrict__ map, int64_t n, const float* 
   if (oc) oc[i] = bc[s];
 }
 
+// ---- sharding: buffers that peers write into --------------------------------------------------------------------
+// With the peer mappings of the slab transforms in place (ctx->p2p) the catalog columns and the results travel as
+// plain copy-engine copies into the peers' buffers too (NCCL's grouped send/recv moved them at ~200 GB/s).  The
+// receiving buffers grow with the catalog, so their IPC handles are exchanged INSIDE the library whenever any rank has
+// to grow one -- every rank sees the whole count matrix and therefore takes the same decision at the same call.
+static void shard_close_peers(baorec_ctx* ctx, int slot) {
+  for (int r = 0; r < 16; r++)
+    for (int k = 0; k < 2; k++) {
+      void*& q = ctx->shard_peer[slot][k][r];
+      if (q && r != ctx->rank) cudaIpcCloseMemHandle(q);
+      q = nullptr;
+    }
+  cudaGetLastError();
+}
+
+// capacities (particles) every rank's two buffers must have; grows + re-maps when any of them is too small
+static int shard_ensure_peer_buffers(baorec_ctx* ctx, int slot, const int64_t need_recv[16], const int64_t need_send[16],
+                                     cudaStream_t st) {
+  const int P = ctx->nranks;
+  bool grow = false;
+  for (int r = 0; r < P; r++)
+    grow = grow || need_recv[r] > ctx->shard_cap[slot][0][r] || need_send[r] > ctx->shard_cap[slot][1][r] ||
+           !ctx->shard_peer[slot][0][r] || !ctx->shard_peer[slot][1][r];
+  if (!grow) return BAOREC_OK;
+  // (1) nobody frees a buffer a peer still maps: drop the mappings, then a barrier
+  BR_CUDA(cudaStreamSynchronize(st));
+  shard_close_peers(ctx, slot);
+  if (!ctx->d_ipc_stage) BR_CUDA(cudaMalloc(&ctx->d_ipc_stage, 17 * 128));
+  if (P > 1) {
+    BR_NCCL(ncclAllReduce(ctx->d_ipc_stage, ctx->d_ipc_stage, 1, ncclInt, ncclMax, comm_of(ctx), st));
+    BR_CUDA(cudaStreamSynchronize(st));
+  }
+  // (2) new capacities: 25 % headroom so that a slightly different catalog does not grow again
+  for (int r = 0; r < P; r++) {
+    const int64_t nr = need_recv[r] + need_recv[r] / 4 + 1024, ns = need_send[r] + need_send[r] / 4 + 1024;
+    if (need_recv[r] > ctx->shard_cap[slot][0][r]) ctx->shard_cap[slot][0][r] = nr;
+    if (need_send[r] > ctx->shard_cap[slot][1][r]) ctx->shard_cap[slot][1][r] = ns;
+  }
+  float *recv, *send;
+  BR_TRY(need_t(ctx, slot ? BUF_SHARD_RECV2 : BUF_SHARD_RECV, 4 * (size_t)ctx->shard_cap[slot][0][ctx->rank], &recv));
+  BR_TRY(need_t(ctx, slot ? BUF_SHARD_SEND2 : BUF_SHARD_SEND, 4 * (size_t)ctx->shard_cap[slot][1][ctx->rank], &send));
+  // (3) handles: all-gather through device memory, then open
+  cudaIpcMemHandle_t mine[2], all[2 * 16];
+  BR_CUDA(cudaIpcGetMemHandle(&mine[0], recv));
+  BR_CUDA(cudaIpcGetMemHandle(&mine[1], send));
+  char* stage = (char*)ctx->d_ipc_stage;
+  BR_CUDA(cudaMemcpyAsync(stage + 128 * 16, mine, 128, cudaMemcpyHostToDevice, st));
+  if (P > 1) {
+    BR_NCCL(ncclAllGather(stage + 128 * 16, stage, 128, ncclChar, comm_of(ctx), st));
+  } else {
+    BR_CUDA(cudaMemcpyAsync(stage, stage + 128 * 16, 128, cudaMemcpyDeviceToDevice, st));
+  }
+  BR_CUDA(cudaMemcpyAsync(all, stage, 128 * (size_t)P, cudaMemcpyDeviceToHost, st));
+  BR_CUDA(cudaStreamSynchronize(st));
+  for (int r = 0; r < P; r++)
+    for (int k = 0; k < 2; k++) {
+      if (r == ctx->rank) {
+        ctx->shard_peer[slot][k][r] = k == 0 ? (void*)recv : (void*)send;
+        continue;
+      }
+      void* q = nullptr;
+      BR_CUDA(cudaIpcOpenMemHandle(&q, all[2 * r + k], cudaIpcMemLazyEnablePeerAccess));
+      ctx->shard_peer[slot][k][r] = q;
+    }
+  return BAOREC_OK;
+}
+
 static int shard_catalog(baorec_ctx* ctx, int slot, const float* x, const float* y, const float* z, const float* w,
                          int64_t n, float** ox, float** oy, float** oz, float** ow, int64_t* n_local, cudaStream_t st) {
   const int P = ctx->nranks;
@@ -975,6 +1139,10 @@ static int shard_catalog(baorec_ctx* ctx, int slot, const float* x, const float*
   BR_REQUIRE(n < ((int64_t)1 << 32) - 1, "at most 2^32 - 2 particles per rank and call");
   baorec_ctx::ShardState& S = ctx->shard[slot];
   S.valid = false;
+  const bool peer = ctx->p2p;
+  const unsigned seq = peer ? ++ctx->seq_shard[slot][0] : 0;
+  // my receive columns of the previous call are dead once everything queued so far has run: peers may overwrite them
+  if (peer) BR_TRY(peer_signal(ctx, slot ? F_FREE_S1 : F_FREE_S0, seq, st));
   if (!ctx->d_shard_cnt) BR_CUDA(cudaMalloc(&ctx->d_shard_cnt, sizeof(unsigned long long) * (40 + 17 * 16)));
   unsigned long long* cnt = ctx->d_shard_cnt;
   BR_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * 40, st));
@@ -999,7 +1167,7 @@ static int shard_catalog(baorec_ctx* ctx, int slot, const float* x, const float*
     set_error("shard_catalog: %llu particle(s) outside the box over all ranks (the reference would raise BoundsError)", oob);
     return BAOREC_ERR_OUT_OF_BOX;
   }
-  int64_t so = 0, ro = 0;
+  int64_t so = 0, ro = 0, need_recv[16] = {}, need_send[16] = {};
   for (int r = 0; r < P; r++) {
     S.send_cnt[r] = (int64_t)h[17 * ctx->rank + r];
     S.send_off[r] = so;
@@ -1007,19 +1175,54 @@ static int shard_catalog(baorec_ctx* ctx, int slot, const float* x, const float*
     S.recv_cnt[r] = (int64_t)h[17 * r + ctx->rank];
     S.recv_off[r] = ro;
     ro += S.recv_cnt[r];
+    S.off_at_dst[r] = S.off_at_src[r] = 0;
+    for (int q = 0; q < P; q++) {
+      need_recv[r] += (int64_t)h[17 * q + r];
+      need_send[r] += (int64_t)h[17 * r + q];
+      if (q < ctx->rank) {
+        S.off_at_dst[r] += (int64_t)h[17 * q + r];   // where my segment starts in rank r's receive columns
+        S.off_at_src[r] += (int64_t)h[17 * r + q];   // where my results start in rank r's send order
+      }
+    }
   }
   S.n = n;
   S.n_local = ro;
   float *send, *recv;
   unsigned* map;
-  const size_t ns = (size_t)(n > 0 ? n : 1), nl = (size_t)(ro > 0 ? ro : 1);
-  BR_TRY(need_t(ctx, slot ? BUF_SHARD_SEND2 : BUF_SHARD_SEND, 4 * ns, &send));
-  BR_TRY(need_t(ctx, slot ? BUF_SHARD_RECV2 : BUF_SHARD_RECV, 4 * nl, &recv));
-  BR_TRY(need_t(ctx, slot ? BUF_SHARD_MAP2 : BUF_SHARD_MAP, ns, &map));
+  size_t ns = (size_t)(n > 0 ? n : 1), nl = (size_t)(ro > 0 ? ro : 1);
+  if (peer) {
+    BR_TRY(shard_ensure_peer_buffers(ctx, slot, need_recv, need_send, st));
+    ns = (size_t)ctx->shard_cap[slot][1][ctx->rank];   // column strides = the capacities every rank knows
+    nl = (size_t)ctx->shard_cap[slot][0][ctx->rank];
+    send = (float*)ctx->shard_peer[slot][1][ctx->rank];
+    recv = (float*)ctx->shard_peer[slot][0][ctx->rank];
+  } else {
+    BR_TRY(need_t(ctx, slot ? BUF_SHARD_SEND2 : BUF_SHARD_SEND, 4 * ns, &send));
+    BR_TRY(need_t(ctx, slot ? BUF_SHARD_RECV2 : BUF_SHARD_RECV, 4 * nl, &recv));
+  }
+  S.send_stride = (int64_t)ns;
+  S.recv_stride = (int64_t)nl;
+  BR_TRY(need_t(ctx, slot ? BUF_SHARD_MAP2 : BUF_SHARD_MAP, (size_t)(n > 0 ? n : 1), &map));
   if (n > 0)
     BR_LAUNCH(ctx, shard_reorder_kernel, grid, SHARD_THREADS, 0, st, x, y, z, w, n, ctx->mn[2], ctx->L[2], ctx->mn[0], ctx->L[0],
               ctx->nz, ctx->nz_loc, cnt + 17, send, send + ns, send + 2 * ns, send + 3 * ns, map);
-  if (P > 1) {
+  if (peer) {
+    // one copy per (peer, column) straight into the peer's receive columns, after the peer has entered this call
+    BR_TRY(peer_wait(ctx, slot ? F_FREE_S1 : F_FREE_S0, seq, st));
+    int pi = prof_begin(ctx, "peer_shard_copies", st);
+    for (int k = 0; k < P; k++) {
+      const int d = (ctx->rank + k) % P;
+      if (!S.send_cnt[d]) continue;
+      float* dcol = (float*)ctx->shard_peer[slot][0][d];
+      const size_t dstride = (size_t)ctx->shard_cap[slot][0][d];
+      for (int c = 0; c < 4; c++)
+        BR_CUDA(cudaMemcpyAsync(dcol + c * dstride + S.off_at_dst[d], send + c * ns + S.send_off[d],
+                                (size_t)S.send_cnt[d] * sizeof(float), cudaMemcpyDefault, st));
+    }
+    prof_end(ctx, pi, st);
+    BR_TRY(peer_signal(ctx, slot ? F_ARR_S1 : F_ARR_S0, seq, st));
+    BR_TRY(peer_wait(ctx, slot ? F_ARR_S1 : F_ARR_S0, seq, st));
+  } else if (P > 1) {
     int pi = prof_begin(ctx, "nccl_shard_all_to_all_v", st);
     BR_NCCL(ncclGroupStart());
     for (int r = 0; r < P; r++)
@@ -1038,6 +1241,7 @@ static int shard_catalog(baorec_ctx* ctx, int slot, const float* x, const float*
   *oz = recv + 2 * nl;
   *ow = recv + 3 * nl;
   *n_local = ro;
+  S.peer = peer;
   S.valid = true;
   return BAOREC_OK;
 }
@@ -1051,11 +1255,30 @@ static int unshard(baorec_ctx* ctx, int slot, const float* a, const float* b, co
     set_error("baorec_unshard_f32: no routing table for slot %d (call baorec_shard_catalog_f32 first)", slot);
     return BAOREC_ERR_INVALID;
   }
-  const size_t ns = (size_t)(S.n > 0 ? S.n : 1);
-  float* back = (float*)ctx->bufs[slot ? BUF_SHARD_SEND2 : BUF_SHARD_SEND].p;  // the send staging is free again: 4 ns floats
+  const size_t ns = (size_t)S.send_stride;
+  float* back = (float*)ctx->bufs[slot ? BUF_SHARD_SEND2 : BUF_SHARD_SEND].p;  // the send staging is free again: 4 columns
   const unsigned* map = (const unsigned*)ctx->bufs[slot ? BUF_SHARD_MAP2 : BUF_SHARD_MAP].p;
   const float* src[3] = {a, b, c};
-  if (P > 1) {
+  if (S.peer && ctx->p2p) {
+    const unsigned seq = ++ctx->seq_shard[slot][1];
+    const int f_free = slot ? F_FREE_B1 : F_FREE_B0, f_arr = slot ? F_ARR_B1 : F_ARR_B0;
+    BR_TRY(peer_signal(ctx, f_free, seq, st));  // my shard copies have left the staging (stream order): results may land in it
+    BR_TRY(peer_wait(ctx, f_free, seq, st));
+    int pi = prof_begin(ctx, "peer_unshard_copies", st);
+    for (int k = 0; k < P; k++) {
+      const int s = (ctx->rank + k) % P;
+      if (!S.recv_cnt[s]) continue;
+      float* dcol = (float*)ctx->shard_peer[slot][1][s];
+      const size_t dstride = (size_t)ctx->shard_cap[slot][1][s];
+      for (int q = 0; q < 3; q++)
+        if (src[q])
+          BR_CUDA(cudaMemcpyAsync(dcol + q * dstride + S.off_at_src[s], src[q] + S.recv_off[s],
+                                  (size_t)S.recv_cnt[s] * sizeof(float), cudaMemcpyDefault, st));
+    }
+    prof_end(ctx, pi, st);
+    BR_TRY(peer_signal(ctx, f_arr, seq, st));
+    BR_TRY(peer_wait(ctx, f_arr, seq, st));
+  } else if (P > 1) {
     int pi = prof_begin(ctx, "nccl_unshard_all_to_all_v", st);
     BR_NCCL(ncclGroupStart());
     for (int r = 0; r < P; r++)
@@ -1343,9 +1566,15 @@ int baorec_read_shifts_dist_f32(baorec_ctx* ctx, const baorec_params* p, const f
     ctx->slab_mode = 0;
     if (sp != BAOREC_OK) return sp;
   }
+  if (!reuse && ctx->p2p) {
+    float* own[3] = {psi[0] + plane, psi[1] + plane, psi[2] + plane};  // own planes at local index 1 .. nzl
+    BR_TRY(dist_displacements_peer(ctx, keep, ctx->kcache_potential, own, st));
+  }
   for (int c = 0; c < 3 && !reuse; c++) {
-    BR_TRY(kpass_disp_T(ctx, keep, b.T, c, ctx->kcache_potential, st));
-    BR_TRY(dist_c2r(ctx, b.T, psi[c] + plane, st));  // own planes at local index 1 .. nzl
+    if (!ctx->p2p) {
+      BR_TRY(kpass_disp_T(ctx, keep, b.T, c, ctx->kcache_potential, st));
+      BR_TRY(dist_c2r(ctx, b.T, psi[c] + plane, st));  // own planes at local index 1 .. nzl
+    }
     // halo: plane 0 <- previous rank's last plane; planes nzl+1, nzl+2 <- next rank's first two
     BR_TRY(ring_exchange(ctx, psi[c] + (size_t)nzl * plane, next, psi[c], prev, plane, st));
     BR_TRY(ring_exchange(ctx, psi[c] + plane, prev, psi[c] + (size_t)(nzl + 1) * plane, next, 2 * plane, st));

@@ -82,6 +82,7 @@ enum BufId {
   BUF_A2A_SEND, // distributed FFT staging
   BUF_A2A_RECV,
   BUF_A2A_RECV2,
+  BUF_A2A_RECV3,
   BUF_HALO,
   BUF_MGD,      // multigrid level hierarchy of the slab-decomposed solver
   BUF_DET,      // 64-bit fixed-point accumulator of the deterministic scatter
@@ -225,18 +226,27 @@ struct baorec_ctx {
   // (inverse) of every rank, and every rank's flag block, mapped through CUDA IPC
   bool p2p = false;
   int opt_dist_exchange = 1;  // 1 = peer copies + flags (default), 0 = pack / transpose kernels + NCCL all-to-all
-  float2* peer_recv[2][16] = {};
-  float2* own_recv[2] = {nullptr, nullptr};
+  float2* peer_recv[3][16] = {};   // [0] k layout (forward), [1], [2] plane layout (inverse, two slots)
+  float2* own_recv[3] = {nullptr, nullptr, nullptr};
   void* peer_flags[16] = {};
   void* d_flags = nullptr;
-  unsigned seq_k = 0, seq_a = 0;  // forward / inverse transforms issued since the flags were reset (same on every rank)
+  unsigned seq_k = 0, seq_a[2] = {0, 0};  // forward / inverse transforms issued since the flags were reset (same on every rank)
   // particle sharding by slab (baorec_shard_catalog_f32): routing tables of the last call per slot (0 data, 1 randoms)
   struct ShardState {
     bool valid = false;
     int64_t n = 0, n_local = 0;            // particles passed in / particles of this rank's slab
     int64_t send_cnt[16] = {}, send_off[16] = {};   // per destination rank, in the send order
     int64_t recv_cnt[16] = {}, recv_off[16] = {};   // per source rank, in the slab order
+    int64_t off_at_dst[16] = {}, off_at_src[16] = {};  // my segment's offset inside rank r's receive columns / send order
+    int64_t send_stride = 0, recv_stride = 0;       // column strides of the two buffers
+    bool peer = false;                              // routed with peer copies (else NCCL)
   } shard[2];
+  // peer-copy sharding: every rank's receive columns [0] and send staging [1] per slot, mapped through CUDA IPC, with the
+  // capacities (particles per column) all ranks agree on
+  void* shard_peer[2][2][16] = {};
+  int64_t shard_cap[2][2][16] = {};
+  unsigned seq_shard[2][2] = {};   // [slot][0 shard / 1 unshard]
+  void* d_ipc_stage = nullptr;
   unsigned long long* d_shard_cnt = nullptr;  // [0..15] per-owner counts, [16] out-of-box, [17..33] cursors; [40..] gathered
   // displacement meshes (BUF_RX/RY/RZ) of the cached result, kept across read_shifts /
   // reconstructed_positions calls (the examples read data, randoms-sym and randoms-iso back from
@@ -331,6 +341,7 @@ int kpass_fused_T(baorec_ctx* ctx, const float2* in, float2* out_c2r, float2* ke
 int kpass_fused_delta_T(baorec_ctx* ctx, const float2* in, float2* out_c2r, float2* keep, const baorec_params* p,
                         cudaStream_t st);
 int kpass_disp_T(baorec_ctx* ctx, const float2* in, float2* out, int comp, bool potential, cudaStream_t st);
+int kpass_disp_gh(baorec_ctx* ctx, const float2* in, float2* g, float2* h, bool potential, cudaStream_t st);
 int kpass_setup_box_T(baorec_ctx* ctx, const float2* in, float2* out, const baorec_params* p, cudaStream_t st);
 int kpass_gauss_T(baorec_ctx* ctx, const float2* in, float2* out, float R, cudaStream_t st);
 int kpass_iter_pair_T(baorec_ctx* ctx, const float2* in, float2* out, int i, int j, cudaStream_t st);

@@ -412,6 +412,39 @@ struct DispCompOp {  // one component of Psi = i k delta_k / k^2 (src/iterative.
   }
 };
 
+// G = delta_k / (k^2 M) (or phi_k / M) and H = i k_z G: the x and y displacement fields are i k_x G and i k_y G, and those
+// factors commute with the inverse z transform, so they are applied AFTER it (disp_xy_planes_kernel, dist.cu): two
+// distributed inverse transforms per read-back instead of three.  Same Float32 products as DispOp / DispCompOp.
+template <bool POTENTIAL>
+struct DispGHOp {
+  static const char* name() { return POTENTIAL ? "kspace_kernel<DispGHOp<potential>>" : "kspace_kernel<DispGHOp<density>>"; }
+  float2* g;
+  float2* h;
+  float invM;
+  __device__ __forceinline__ void apply(size_t idx, float2 v, float kx, float ky, float kz, bool, int, int, int) const {
+    float s;
+    if (POTENTIAL) {
+      s = invM;
+    } else {
+      float k2 = ksq(kx, ky, kz);
+      s = k2 > 0.f ? __fdiv_rn(invM, k2) : 0.f;
+    }
+    const float gre = __fmul_rn(v.x, s), gim = __fmul_rn(v.y, s);
+    g[idx] = make_float2(gre, gim);
+    h[idx] = make_float2(__fmul_rn(-gim, kz), __fmul_rn(gre, kz));
+  }
+};
+
+int kpass_disp_gh(baorec_ctx* ctx, const float2* in, float2* g, float2* h, bool potential, cudaStream_t st) {
+  const float invM = (float)(1.0 / (double)ctx->M);
+  if (potential) {
+    DispGHOp<true> op{g, h, invM};
+    return run_kspace_t(ctx, in, op, st);
+  }
+  DispGHOp<false> op{g, h, invM};
+  return run_kspace_t(ctx, in, op, st);
+}
+
 int stash_dc(baorec_ctx* ctx, const float2* ck, int slot, double mul, cudaStream_t st) {
   BR_LAUNCH(ctx, stash_dc_kernel, 1, 1, 0, st, ck, ctx->d_scal, slot, mul);
   return BAOREC_OK;
