@@ -374,9 +374,13 @@ int baorec_create(int device, baorec_ctx** out) {
     BR_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     BR_CUDA(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, hi));
     BR_CUDA(cudaStreamCreateWithPriority(&ctx->comm_stream2, cudaStreamNonBlocking, hi));
+    BR_CUDA(cudaStreamCreateWithPriority(&ctx->comm_stream3, cudaStreamNonBlocking, hi));
+    BR_CUDA(cudaStreamCreateWithPriority(&ctx->comm_stream4, cudaStreamNonBlocking, hi));
   }
   for (int i = 0; i < 8; i++) {
     BR_CUDA(cudaEventCreateWithFlags(&ctx->ev_local[i], cudaEventDisableTiming));
+    BR_CUDA(cudaEventCreateWithFlags(&ctx->ev_split[i], cudaEventDisableTiming));
+    BR_CUDA(cudaEventCreateWithFlags(&ctx->ev_split2[i], cudaEventDisableTiming));
     BR_CUDA(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
     BR_CUDA(cudaEventCreateWithFlags(&ctx->ev_a2a[i], cudaEventDisableTiming));
   }
@@ -422,8 +426,12 @@ int baorec_destroy(baorec_ctx* ctx) {
   if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
   if (ctx->comm_stream2) cudaStreamDestroy(ctx->comm_stream2);
+  if (ctx->comm_stream3) cudaStreamDestroy(ctx->comm_stream3);
+  if (ctx->comm_stream4) cudaStreamDestroy(ctx->comm_stream4);
   for (int i = 0; i < 8; i++) {
     if (ctx->ev_local[i]) cudaEventDestroy(ctx->ev_local[i]);
+    if (ctx->ev_split[i]) cudaEventDestroy(ctx->ev_split[i]);
+    if (ctx->ev_split2[i]) cudaEventDestroy(ctx->ev_split2[i]);
     if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
     if (ctx->ev_a2a[i]) cudaEventDestroy(ctx->ev_a2a[i]);
   }

@@ -240,7 +240,52 @@ __global__ void peer_wait_kernel(const unsigned* flags, unsigned value, int P, u
   __syncthreads();
 }
 
+// The remote blocks of one chunk pushed by the SMs, to ALL peers at once: blockIdx.y = peer step k (destination
+// (rank + k) mod P), PUSH_CTAS blocks per destination, 16-byte loads from the local rows and 16-byte stores into the
+// peer's rows over NVLink.  Measured on 8 x B200 (benchmarks/probe/p2p_probe.cu, 16.8 MB per pair): 640 GB/s per
+// direction against 430 GB/s for copy-engine copies in any stream arrangement -- the copy engines cannot keep seven
+// peers busy, 112 thread blocks can.  With 2 - 4 ranks the copy engines are the faster (700 - 755 GB/s) and SM-free.
+constexpr int PUSH_CTAS = 18;  // per destination: 126 blocks with 8 ranks
+struct PushGeom {
+  size_t src_peer_stride;        // source offset per destination rank (float2 elements)
+  size_t src_pitch, dst_pitch;   // row pitches (float2 elements)
+  size_t dst_off;                // offset of this rank's rows in every destination buffer
+  unsigned w4;                   // row width in float4
+  int rows, P, me;
+};
+__global__ void __launch_bounds__(256)
+peer_push_kernel(const __grid_constant__ PeerTab dst, const float2* __restrict__ src, const PushGeom g) {
+  const int d = (g.me + (int)blockIdx.y + 1) % g.P;
+  const float2* s0 = src + (size_t)d * g.src_peer_stride;
+  float2* o0 = dst.p[d] + g.dst_off;
+  for (int row = blockIdx.x; row < g.rows; row += gridDim.x) {
+    const float4* s = (const float4*)(s0 + (size_t)row * g.src_pitch);
+    float4* o = (float4*)(o0 + (size_t)row * g.dst_pitch);
+    unsigned i = threadIdx.x;
+    for (; i + 3 * 256 < g.w4; i += 4 * 256) {
+      const float4 a = s[i], b = s[i + 256], c = s[i + 512], e = s[i + 768];
+      o[i] = a;
+      o[i + 256] = b;
+      o[i + 512] = c;
+      o[i + 768] = e;
+    }
+    for (; i < g.w4; i += 256) o[i] = s[i];
+  }
+}
+
 static PeerFlags* own_flags(const baorec_ctx* ctx) { return (PeerFlags*)ctx->d_flags; }
+
+static PeerTab recv_tab(const baorec_ctx* ctx, int which) {
+  PeerTab t;
+  for (int i = 0; i < 16; i++) t.p[i] = ctx->peer_recv[which][i];
+  return t;
+}
+
+static bool push_with_sms(const baorec_ctx* ctx, size_t kplane, size_t cplane) {
+  const int o = ctx->opt_push_sm;
+  const bool aligned = (kplane % 2 == 0) && (cplane % 2 == 0);   // 16-byte rows
+  return aligned && ctx->nranks > 1 && (o > 0 || (o < 0 && ctx->nranks >= 5));
+}
 
 // the word of every peer's block that belongs to this rank
 static FlagTab flag_tab(const baorec_ctx* ctx, int which) {
@@ -441,7 +486,9 @@ static int dist_r2c_peer(baorec_ctx* ctx, const float* slab, float2* K, int C, c
   if (C < 1) C = 1;
   const int nzc = nzl / C;
   const size_t rplane = (size_t)ny * ctx->nx, cplane = (size_t)ny * xh, kplane = (size_t)nyl * xh;
-  cudaStream_t cs = ctx->comm_stream, cs2 = ctx->comm_stream2;
+  cudaStream_t cs = ctx->comm_stream, cs2 = ctx->comm_stream2, cs3 = ctx->comm_stream3, cs4 = ctx->comm_stream4;
+  const bool split = ctx->opt_comm_split && P > 2;  // two streams of remote copies: two copy engines, two peers at a time
+  const bool sm_push = push_with_sms(ctx, kplane, cplane);
   const unsigned seq = ++ctx->seq_k, base = (seq - 1) * (unsigned)C;
   cufftHandle plan = C > 1 ? ctx->pc_r2c : ctx->p2d_r2c;
   BR_CUFFT(cufftSetStream(plan, st));
@@ -451,6 +498,10 @@ static int dist_r2c_peer(baorec_ctx* ctx, const float* slab, float2* K, int C, c
   BR_TRY(peer_wait(ctx, F_FREE_K, seq - 1, cs));
   BR_CUDA(cudaEventRecord(ctx->ev_a2a[2], cs));
   BR_CUDA(cudaStreamWaitEvent(cs2, ctx->ev_a2a[2], 0));  // (my own K buffer included: the local copies wait too)
+  if (split) {
+    BR_CUDA(cudaStreamWaitEvent(cs3, ctx->ev_a2a[2], 0));
+    BR_CUDA(cudaStreamWaitEvent(cs4, ctx->ev_a2a[2], 0));
+  }
   for (int c = 0; c < C; c++) {
     int pi = prof_begin(ctx, "cufft_2d_r2c", st);
     BR_CUFFT(cufftExecR2C(plan, (cufftReal*)(slab + (size_t)c * nzc * rplane), (cufftComplex*)(b.A + (size_t)c * nzc * cplane)));
@@ -459,15 +510,35 @@ static int dist_r2c_peer(baorec_ctx* ctx, const float* slab, float2* K, int C, c
     BR_CUDA(cudaStreamWaitEvent(cs, ctx->ev_chunk[c], 0));
     // this rank's own block is an HBM copy: second stream, beside the NVLink copies
     BR_CUDA(cudaStreamWaitEvent(cs2, ctx->ev_chunk[c], 0));
-    for (int k = 0; k < P; k++) {
-      const int d = (ctx->rank + k) % P;  // staggered: at step k every rank writes to a different peer
-      const float2* src = b.A + (size_t)c * nzc * cplane + (size_t)d * kplane;
-      float2* dst = ctx->peer_recv[0][d] + ((size_t)ctx->rank * nzl + (size_t)c * nzc) * kplane;
-      if (k == 1) pi = prof_begin(ctx, "peer_copies", cs);
-      BR_CUDA(cudaMemcpy2DAsync(dst, kplane * sizeof(float2), src, cplane * sizeof(float2), kplane * sizeof(float2),
-                                (size_t)nzc, cudaMemcpyDefault, k == 0 ? cs2 : cs));
+    if (split) {
+      BR_CUDA(cudaStreamWaitEvent(cs3, ctx->ev_chunk[c], 0));
+      BR_CUDA(cudaStreamWaitEvent(cs4, ctx->ev_chunk[c], 0));
     }
-    if (P > 1) prof_end(ctx, pi, cs);
+    if (sm_push) {
+      // own block: copy engine; all remote blocks: one kernel
+      BR_CUDA(cudaMemcpy2DAsync(ctx->peer_recv[0][ctx->rank] + ((size_t)ctx->rank * nzl + (size_t)c * nzc) * kplane, kplane * sizeof(float2),
+                                b.A + (size_t)c * nzc * cplane + (size_t)ctx->rank * kplane, cplane * sizeof(float2),
+                                kplane * sizeof(float2), (size_t)nzc, cudaMemcpyDefault, cs2));
+      PushGeom pg{kplane, cplane, kplane, ((size_t)ctx->rank * nzl + (size_t)c * nzc) * kplane, (unsigned)(kplane / 2), nzc, P, ctx->rank};
+      BR_LAUNCH_NAMED(ctx, "peer_copies", peer_push_kernel, dim3(PUSH_CTAS, P - 1), 256, 0, cs, recv_tab(ctx, 0),
+                      b.A + (size_t)c * nzc * cplane, pg);
+    } else {
+      for (int k = 0; k < P; k++) {
+        const int d = (ctx->rank + k) % P;  // staggered: at step k every rank writes to a different peer
+        const float2* src = b.A + (size_t)c * nzc * cplane + (size_t)d * kplane;
+        float2* dst = ctx->peer_recv[0][d] + ((size_t)ctx->rank * nzl + (size_t)c * nzc) * kplane;
+        if (k == 1) pi = prof_begin(ctx, "peer_copies", cs);
+        BR_CUDA(cudaMemcpy2DAsync(dst, kplane * sizeof(float2), src, cplane * sizeof(float2), kplane * sizeof(float2),
+                                  (size_t)nzc, cudaMemcpyDefault, k == 0 ? cs2 : (!split ? cs : (k % 3 == 1 ? cs : (k % 3 == 2 ? cs3 : cs4)))));
+      }
+      if (split) {  // the copies to two thirds of the peers ran on two more streams: join them before the flag
+        BR_CUDA(cudaEventRecord(ctx->ev_split[c], cs3));
+        BR_CUDA(cudaStreamWaitEvent(cs, ctx->ev_split[c], 0));
+        BR_CUDA(cudaEventRecord(ctx->ev_split2[c], cs4));
+        BR_CUDA(cudaStreamWaitEvent(cs, ctx->ev_split2[c], 0));
+      }
+      if (P > 1) prof_end(ctx, pi, cs);
+    }
     BR_CUDA(cudaEventRecord(ctx->ev_local[c], cs2));
     BR_CUDA(cudaStreamWaitEvent(cs, ctx->ev_local[c], 0));
     BR_TRY(peer_signal(ctx, F_ARR_K, base + (unsigned)c + 1u, cs));
@@ -510,7 +581,9 @@ static int c2r_peer_send(baorec_ctx* ctx, float2* K, int slot, int C, C2RPeer* h
   h->RA = ctx->own_recv[1 + slot];
   const size_t cplane = h->cplane, kplane = (size_t)nyl * xh;
   const int nzc = h->nzc;
-  cudaStream_t cs = ctx->comm_stream, cs2 = ctx->comm_stream2;
+  cudaStream_t cs = ctx->comm_stream, cs2 = ctx->comm_stream2, cs3 = ctx->comm_stream3, cs4 = ctx->comm_stream4;
+  const bool split = ctx->opt_comm_split && P > 2;
+  const bool sm_push = push_with_sms(ctx, kplane, cplane);
   h->seq = ++ctx->seq_a[slot];
   h->base = (h->seq - 1) * (unsigned)C;
   const int f_arr = slot ? F_ARR_A1 : F_ARR_A0, f_free = slot ? F_FREE_A1 : F_FREE_A0;
@@ -525,16 +598,36 @@ static int c2r_peer_send(baorec_ctx* ctx, float2* K, int slot, int C, C2RPeer* h
   BR_TRY(peer_wait(ctx, f_free, h->seq - 1, cs));  // every destination has consumed this slot's buffer of the previous inverse
   BR_CUDA(cudaEventRecord(ev_w, cs));
   BR_CUDA(cudaStreamWaitEvent(cs2, ev_w, 0));  // (my own plane buffer included: the local copies wait too)
+  if (split) {
+    BR_CUDA(cudaStreamWaitEvent(cs3, ev_w, 0));
+    BR_CUDA(cudaStreamWaitEvent(cs4, ev_w, 0));
+  }
   for (int c = 0; c < C; c++) {
-    for (int k = 0; k < P; k++) {
-      const int d = (ctx->rank + k) % P;
-      const float2* src = K + ((size_t)d * nzl + (size_t)c * nzc) * kplane;
-      float2* dst = ctx->peer_recv[1 + slot][d] + (size_t)c * nzc * cplane + (size_t)ctx->rank * kplane;
-      if (k == 1) pi = prof_begin(ctx, "peer_copies", cs);
-      BR_CUDA(cudaMemcpy2DAsync(dst, cplane * sizeof(float2), src, kplane * sizeof(float2), kplane * sizeof(float2),
-                                (size_t)nzc, cudaMemcpyDefault, k == 0 ? cs2 : cs));
+    if (sm_push) {
+      BR_CUDA(cudaMemcpy2DAsync(ctx->peer_recv[1 + slot][ctx->rank] + (size_t)c * nzc * cplane + (size_t)ctx->rank * kplane,
+                                cplane * sizeof(float2), K + ((size_t)ctx->rank * nzl + (size_t)c * nzc) * kplane,
+                                kplane * sizeof(float2), kplane * sizeof(float2), (size_t)nzc, cudaMemcpyDefault, cs2));
+      PushGeom pg{(size_t)nzl * kplane, kplane, cplane, (size_t)c * nzc * cplane + (size_t)ctx->rank * kplane, (unsigned)(kplane / 2), nzc, P,
+                  ctx->rank};
+      BR_LAUNCH_NAMED(ctx, "peer_copies", peer_push_kernel, dim3(PUSH_CTAS, P - 1), 256, 0, cs, recv_tab(ctx, 1 + slot),
+                      K + (size_t)c * nzc * kplane, pg);
+    } else {
+      for (int k = 0; k < P; k++) {
+        const int d = (ctx->rank + k) % P;
+        const float2* src = K + ((size_t)d * nzl + (size_t)c * nzc) * kplane;
+        float2* dst = ctx->peer_recv[1 + slot][d] + (size_t)c * nzc * cplane + (size_t)ctx->rank * kplane;
+        if (k == 1) pi = prof_begin(ctx, "peer_copies", cs);
+        BR_CUDA(cudaMemcpy2DAsync(dst, cplane * sizeof(float2), src, kplane * sizeof(float2), kplane * sizeof(float2),
+                                  (size_t)nzc, cudaMemcpyDefault, k == 0 ? cs2 : (!split ? cs : (k % 3 == 1 ? cs : (k % 3 == 2 ? cs3 : cs4)))));
+      }
+      if (split) {
+        BR_CUDA(cudaEventRecord(ctx->ev_split[c], cs3));
+        BR_CUDA(cudaStreamWaitEvent(cs, ctx->ev_split[c], 0));
+        BR_CUDA(cudaEventRecord(ctx->ev_split2[c], cs4));
+        BR_CUDA(cudaStreamWaitEvent(cs, ctx->ev_split2[c], 0));
+      }
+      if (P > 1) prof_end(ctx, pi, cs);
     }
-    if (P > 1) prof_end(ctx, pi, cs);
     BR_CUDA(cudaEventRecord(ctx->ev_local[c], cs2));
     BR_CUDA(cudaStreamWaitEvent(cs, ctx->ev_local[c], 0));
     BR_TRY(peer_signal(ctx, f_arr, h->base + (unsigned)c + 1u, cs));

@@ -266,7 +266,11 @@ struct baorec_ctx {
   int opt_a2a_chunks = 4;
   cudaStream_t comm_stream = nullptr;
   cudaStream_t comm_stream2 = nullptr;  // the local 1/P block of a peer-copy exchange (an HBM copy) runs beside the NVLink copies
-  cudaEvent_t ev_chunk[8] = {}, ev_a2a[8] = {}, ev_local[8] = {};
+  cudaStream_t comm_stream4 = nullptr;
+  cudaStream_t comm_stream3 = nullptr;  // every other remote copy (option "comm_split"): two copy engines, two peers at a time
+  int opt_comm_split = 1;
+  int opt_push_sm = -1;  // remote blocks of the peer exchange pushed by an SM kernel instead of the copy engines: -1 = with 5+ ranks, 0 never, 1 always
+  cudaEvent_t ev_chunk[8] = {}, ev_a2a[8] = {}, ev_local[8] = {}, ev_split[8] = {}, ev_split2[8] = {};
   // catalog pre/post-processing (catalog.cu): comoving-distance table r(z) on uniform z knots
   double* d_cosmo_r = nullptr;
   std::vector<double> h_cosmo_r;

@@ -340,6 +340,10 @@ def main():
         B.dist.init_comm(ctx)
         if os.environ.get("BAOREC_A2A_CHUNKS"):      # A/B knobs
             ctx.set_option("a2a_chunks", int(os.environ["BAOREC_A2A_CHUNKS"]))
+        if os.environ.get("BAOREC_PUSH_SM"):
+            ctx.set_option("push_sm", int(os.environ["BAOREC_PUSH_SM"]))
+        if os.environ.get("BAOREC_COMM_SPLIT"):
+            ctx.set_option("comm_split", int(os.environ["BAOREC_COMM_SPLIT"]))
         B.dist.plan(ctx, grid, kw["box_size"], kw["box_min"], exchange=os.environ.get("BAOREC_EXCHANGE"))
         lo, hi = rank * N // world, (rank + 1) * N // world
         (hx, hy, hz), hw = make_catalog(N, L, seed=42, pinned=True, share=(lo, hi))
@@ -507,7 +511,8 @@ def main():
             transforms = sum(c for k, (_, c) in prof.items() if k.startswith("cufft_1d_z"))
             sent = 8 * (Mc // world) * (world - 1) / world * transforms          # bytes over NVLink, this rank, timed region
             nv_peak, nv_src = 770.0, "measured peer copy per direction (B200_PROFILING.md; nominal 900)"
-            exchange = {"scheme": "peer copies (copy engines) + sequence flags" if name == "peer_copies" else "grouped ncclSend/ncclRecv",
+            exchange = {"scheme": ("peer copies + sequence flags (remote blocks: %s)" % ("one SM kernel per chunk" if world >= 5 and not os.environ.get("BAOREC_PUSH_SM") == "0" else "copy engines"))
+                        if name == "peer_copies" else "grouped ncclSend/ncclRecv",
                         "launches_per_step": cnt / args.steps, "ms_per_step": round(ms / args.steps, 3),
                         "nvlink_bytes_per_rank_per_step": int(sent / args.steps), "GBs_per_direction": round(sent / ms / 1e6, 1)}
             hbm_roofline = roofline

@@ -150,9 +150,10 @@ def fft_and_sharding(B, ctx, rank, world):
         return ok
     bs, bm = np.full(3, 1000.0, np.float32), np.zeros(3, np.float32)
     rng = np.random.default_rng(3)
-    for exchange in ("peer", "nccl"):
+    for exchange in ("peer", "peer+sm", "nccl"):       # peer+sm: the remote blocks pushed by the SM kernel (default with 5+ ranks)
         ctx.plan_key = None
-        B.dist.plan(ctx, (n, n, n), bs, bm, exchange=exchange)
+        ctx.set_option("push_sm", 1 if exchange == "peer+sm" else 0)
+        B.dist.plan(ctx, (n, n, n), bs, bm, exchange=exchange.split("+")[0])
         peer = B.dist.peer_exchange(ctx)
         z_lo, nzl = B.dist.slab_range(ctx)
         nyl = n // world
@@ -165,13 +166,14 @@ def fft_and_sharding(B, ctx, rank, world):
             back = torch.empty((nzl, n, n), dtype=torch.float32, device="cuda")
             B.dist.dist_c2r(ctx, K, back)
             e2 = rel_rms(back.cpu().numpy() / a.size, a[z_lo:z_lo + nzl])
-            good = e < 1e-5 and e2 < 1e-5 and peer == (exchange == "peer")
+            good = e < 1e-5 and e2 < 1e-5 and peer == exchange.startswith("peer")
             ok &= good
             if rep == 2 or not good:
                 print(f"[rank {rank}/{world}] slab FFT exchange={exchange} (peer copies: {peer}): forward {e:.2e} round trip {e2:.2e} "
                       f"{'OK' if good else 'FAIL'}", flush=True)
     ctx.plan_key = None
     ctx.set_option("dist_exchange", 1)
+    ctx.set_option("push_sm", 1 if os.environ.get("MGC_PUSH_SM") == "1" else -1)
     L, N = 1000.0, 400_000
     pos, w = clustered_box(N, L, seed=17)
     pos[2][:64] += np.float32(L)
