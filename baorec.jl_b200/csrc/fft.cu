@@ -3,107 +3,44 @@
 //
 // cuFFT's 3-D R2C/C2R at 1024^3 spends 2 x 2.5 ms in its two strided passes (3.4 TB/s) and the
 // k-space multiplies then cost another read + write of the half-mesh.  Here the x axis stays a
-// batched contiguous cuFFT 1-D transform (already at ~5.3 TB/s) and the y / z axes are our own
-// column kernel:
-//   * a CTA stages a tile of 8 adjacent columns x N rows in shared memory with coalesced
-//     64-byte row segments (the columns are contiguous in memory), one warp per column;
-//   * the warp runs the length-N transform as a 32 x M four-step FFT: an M-point DFT in each
-//     lane's registers, the W_N^(lane*q) twiddle, and a 32-point DFT across the lanes with
-//     __shfl_xor butterflies -- no shared-memory traffic inside the transform;
-//   * the z pass applies the k-space operator while the column sits in registers and runs the
-//     inverse z transform in the same kernel (forward + operator + inverse = ONE read and ONE
-//     write of the half-mesh instead of four passes), optionally emitting three outputs
-//     (the displacement components) from one read.
+// batched contiguous cuFFT 1-D transform and the y / z axes are our own column kernel:
+//   * a CTA owns a tile of 8 adjacent columns (64-byte row segments: the columns are contiguous in memory) and
+//     32 threads per column; thread t of a column loads rows t, t + 32, ... straight into registers;
+//   * the length-N transform is a four-step FFT N = 32 x M (M = N / 32 = 8 .. 64): an M-point transform in each
+//     thread's registers (fft_radix.cuh: generated, fully unrolled radix-2 butterflies with literal twiddles), the
+//     W_N^(t k) twiddles, ONE exchange through shared memory (padded: conflict-free both ways), a 32-point
+//     transform in registers -- ~40 instructions per point instead of the ~110 of the first version, whose 32-point
+//     stage ran across the lanes of a warp with shuffles and made the pass issue-bound (3.2 ms against cuFFT's 2.5);
+//   * the output of a forward transform sits in the registers exactly where the inverse transform wants its input
+//     (thread t holds indices t + 32 j), so the z pass of run! applies the k-space operator in registers and runs the
+//     inverse z transform in the same kernel (forward + operator + inverse = ONE read and ONE write of the
+//     half-mesh instead of four passes), and the read-back emits the three displacement fields from one read.
 #include <math.h>
 
 #include "internal.cuh"
+#include "fft_radix.cuh"
+#include "kspace_ops.cuh"
 
 namespace baorec {
 
 constexpr int FFT_TX = 8;          // columns per tile (8 x 8 B = 64 B row segments)
-constexpr int FFT_THREADS = 256;   // 8 warps = 8 columns
-
-__host__ __device__ constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
-__host__ __device__ constexpr int bitrev(int v, int bits) {
-  int r = 0;
-  for (int i = 0; i < bits; i++) r |= ((v >> i) & 1) << (bits - 1 - i);
-  return r;
-}
+constexpr int FFT_THREADS = 256;   // 8 columns x 32 threads
+// resident CTAs per SM.  The kernels fit 3 (80 registers, 20 bytes of spills at N = 1024), but measured on B200 at 1024^3
+// that is SLOWER (plain pass 3.0 instead of 2.2 ms, fused z pass 9.7 instead of 6.9 ms): a z pass touches every plane
+// of the mesh with ~19 KB per plane in flight whatever the tile shape, so more tiles in flight means more open DRAM
+// rows and less shared memory left for L1 -- two CTAs per SM it is.
+#ifndef FFT_CTAS_1024
+#define FFT_CTAS_1024 2
+#endif
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 template <int DIR>
 __device__ __forceinline__ float2 twd(const float2* __restrict__ tw, int idx) {
   float2 w = __ldg(tw + idx);  // exp(-2 pi i idx / N)
   if (DIR < 0) w.y = -w.y;
   return w;
-}
-
-// Length-N transform of one column held by a warp.
-//   in : lane l holds x[l + 32 j] in v[j], j = 0..M-1      (M = N / 32)
-//   out: lane l holds X[M * bitrev5(l) + q] in v[q], q = 0..M-1
-// tw = exp(-2 pi i k / N), k = 0..N-1.   DIR = +1 forward (e^-), -1 inverse (e^+), unnormalised.
-template <int N, int DIR>
-__device__ __forceinline__ void warp_fft(float2 (&v)[N / 32], const float2* __restrict__ tw, int lane) {
-  constexpr int M = N / 32;
-  constexpr int LM = ilog2(M);
-  // step 1: M-point DIF DFT over j in registers (result in bit-reversed register order)
-#pragma unroll
-  for (int half = M / 2; half >= 1; half >>= 1) {
-#pragma unroll
-    for (int t = 0; t < half; t++) {
-      const float2 w = twd<DIR>(tw, t * (N / (2 * half)));  // W_{2 half}^t
-#pragma unroll
-      for (int g0 = 0; g0 < M; g0 += 2 * half) {
-        float2 a = v[g0 + t], b = v[g0 + t + half];
-        v[g0 + t] = cadd(a, b);
-        float2 d = csub(a, b);
-        v[g0 + t + half] = t == 0 ? d : cmul(d, w);
-      }
-    }
-  }
-  float2 y[M];
-#pragma unroll
-  for (int q = 0; q < M; q++) y[q] = v[bitrev(q, LM)];
-  // step 2: twiddle W_N^(lane q).  Only the log2(M) anchors W_N^(lane 2^b) are loaded (lane-strided
-  // table reads cost one L1 wavefront per distinct line); the other powers are composed from them
-  // along the binary digits of q (at most log2(M)-1 products, <= ~3 ulp).
-  {
-    float2 anchor[LM > 0 ? LM : 1];
-#pragma unroll
-    for (int b = 0; b < LM; b++) anchor[b] = twd<DIR>(tw, (lane << b) & (N - 1));
-#pragma unroll
-    for (int q = 1; q < M; q++) {
-      float2 w = make_float2(1.f, 0.f);
-      bool first = true;
-#pragma unroll
-      for (int b = 0; b < LM; b++) {
-        if (q & (1 << b)) {
-          w = first ? anchor[b] : cmul(w, anchor[b]);
-          first = false;
-        }
-      }
-      y[q] = cmul(y[q], w);
-    }
-  }
-  // step 3: 32-point DIF DFT across lanes (result for output r lands in lane bitrev5(r))
-#pragma unroll
-  for (int half = 16; half >= 1; half >>= 1) {
-    const bool upper = (lane & half) != 0;
-    const float2 w = twd<DIR>(tw, (lane & (half - 1)) * (N / (2 * half)));  // W_{2 half}^(lane mod half)
-#pragma unroll
-    for (int q = 0; q < M; q++) {
-      float2 o;
-      o.x = __shfl_xor_sync(0xffffffffu, y[q].x, half);
-      o.y = __shfl_xor_sync(0xffffffffu, y[q].y, half);
-      y[q] = upper ? cmul(csub(o, y[q]), w) : cadd(y[q], o);
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < M; q++) v[q] = y[q];
 }
 
 struct ColGeom {
@@ -116,88 +53,101 @@ struct ColGeom {
   int outer_is_y;       // 1: outer = y, transform = z (z pass); 0: outer = z, transform = y (y pass)
 };
 
-// shared-memory tile: physical row = f + f/32 (one pad row per 32) so that both the strided
-// per-lane reads (rows l + 32 j) and the per-lane chunk writes (rows M r + q) are conflict-free
+// Exchange buffer of the four-step FFT: per column M rows (k2) of 33 slots (n1; 33 = one pad slot, so that the reads
+// of a row by consecutive threads of a warp fall into different banks) and a column stride that is 16 bytes off a
+// multiple of 128: a half-warp (8 columns x 2 threads, one 8-byte access each) then covers the 32 banks exactly once
+// for the writes (slot t) and for the reads (row t).  (First version: 32 bytes off, columns c and c + 4 collided:
+// ncu counted 2.2 extra wavefronts per shared-memory instruction.)
 template <int N>
-struct Tile {
-  static constexpr int ROWS = N + N / 32;
-  float2 s[ROWS][FFT_TX + 1];
-  __device__ __forceinline__ float2& at(int f, int c) { return s[f + (f >> 5)][c]; }
+struct Xch {
+  static constexpr int M = N / 32;
+  static constexpr int pad() {
+    int p = 0;
+    while (((M * 33 + p) * 8) % 128 != 16) p++;
+    return p;
+  }
+  static constexpr int COL = M * 33 + pad();
+  static constexpr size_t BYTES = (size_t)FFT_TX * COL * sizeof(float2);
 };
 
-// Fills the tile with 8-byte cp.async (LDGSTS): every thread has all of its N/32 row segments in
-// flight at once and no registers are spent on staging.  Call tile_load_wait() before the barrier.
-template <int N>
-__device__ __forceinline__ void tile_load(Tile<N>& T, const float2* __restrict__ src, size_t stride, int ncol) {
-  const int c = threadIdx.x & (FFT_TX - 1), r0 = threadIdx.x / FFT_TX;  // 32 rows x 8 columns per sweep
-  if (c < ncol) {
+// One length-N transform per (column c, 32 threads t): v[j] = x[t + 32 j] in, out[m][r] with
+// out[m][fft_bitrev<32>(k1)] = X[(t + 32 m) + M k1] for the transforms this thread owns in the last step
+// (m < MT = max(1, M / 32); for M < 32 only threads t < M own one).  S = this CTA's exchange buffer.
+template <int N, int DIR>
+__device__ __forceinline__ void fft_column(float2 (&v)[N / 32], float2 (&out)[(N / 32 >= 32 ? N / 1024 : 1)][32],
+                                           float2* __restrict__ S, const float2* __restrict__ tw, int c, int t) {
+  constexpr int M = N / 32, MT = M >= 32 ? M / 32 : 1, COL = Xch<N>::COL;
+  fft_reg<M, DIR>(v);
+  float2* col = S + c * COL;
 #pragma unroll
-    for (int r = r0; r < N; r += FFT_THREADS / FFT_TX) {
-      unsigned d = (unsigned)__cvta_generic_to_shared(&T.at(r, c));
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src + (size_t)r * stride + c));
+  for (int k2 = 0; k2 < M; k2++) {
+    float2 y = v[fft_bitrev<M>(k2)];
+    if (k2) y = cmul(y, twd<DIR>(tw, (t * k2) & (N - 1)));
+    col[k2 * 33 + t] = y;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int m = 0; m < MT; m++) {
+    const int k2 = t + 32 * m;
+    if (M >= 32 || k2 < M) {
+#pragma unroll
+      for (int n1 = 0; n1 < 32; n1++) out[m][n1] = col[k2 * 33 + n1];
+      fft_reg<32, DIR>(out[m]);
     }
   }
-  asm volatile("cp.async.wait_all;" ::: "memory");
 }
+
 template <int N>
-__device__ __forceinline__ void tile_store(Tile<N>& T, float2* __restrict__ dst, size_t stride, int ncol,
-                                           bool drop_imag = false) {
-  const int c = threadIdx.x & (FFT_TX - 1), r0 = threadIdx.x / FFT_TX;
-  if (c < ncol) {
-#pragma unroll 8
-    for (int r = r0; r < N; r += FFT_THREADS / FFT_TX) {
-      float2 v = T.at(r, c);
-      if (drop_imag) v.y = 0.f;
-      dst[(size_t)r * stride + c] = v;
-    }
-  }
-}
-template <int N>
-__device__ __forceinline__ void col_read(Tile<N>& T, int col, int lane, float2 (&v)[N / 32]) {
+__device__ __forceinline__ void load_column(float2 (&v)[N / 32], const float2* __restrict__ src, size_t stride, int t) {
+  const float2* p = src + (size_t)t * stride;
+  const size_t step = 32 * stride;
 #pragma unroll
-  for (int j = 0; j < N / 32; j++) v[j] = T.at(lane + 32 * j, col);
-}
-// after warp_fft lane l holds indices (N/32) * bitrev5(l) + q
-template <int N>
-__device__ __forceinline__ void col_write(Tile<N>& T, int col, int lane, const float2 (&v)[N / 32]) {
-  const int base = (N / 32) * (int)(__brev((unsigned)lane) >> 27);
-#pragma unroll
-  for (int q = 0; q < N / 32; q++) T.at(base + q, col) = v[q];
+  for (int j = 0; j < N / 32; j++) v[j] = p[(size_t)j * step];
 }
 
 // ---- operators applied in the z pass (frequency index f along the transform axis) ----------------
-struct OpNone {
-  static constexpr int NOUT = 1;
-  static constexpr bool HAS_OP = false;
-  __device__ __forceinline__ float2 apply(int, float2 v, float, float, float, bool) const { return v; }
-};
-
-// smoothing + (rho/mean - 1)/bias + all n_iter fixed-LOS iterations (see FusedLosOp in kspace.cu);
-// returns delta_final_k / M; `keep` receives the unnormalised delta_final_k
+// smoothing + (rho/mean - 1)/bias + all n_iter fixed-LOS iterations: FusedLosOp<0> of kspace_ops.cuh, value-returning
+// (same Float32 / Float64 products, Gaussian from the per-axis Float64 tables).  Returns the unnormalised delta_final_k.
 struct OpLosSolve {
-  static constexpr int NOUT = 1;
-  static constexpr bool HAS_OP = true;
-  float R2;
+  GaussTab gt;
   const double* scal;  // scal[8] = M / (A0 bias)
   float los[3];
   float beta;
   int n_iter;
   float invM;
-  __device__ __forceinline__ float2 solve(float2 v, float kx, float ky, float kz, bool is_dc) const {
-    float k2 = __fadd_rn(__fadd_rn(__fmul_rn(kx, kx), __fmul_rn(ky, ky)), __fmul_rn(kz, kz));
-    double s = exp(-0.5 * (double)R2 * (double)k2) * __ldg(scal + 8);
+  // per-column invariants (one thread works on ONE (ix, iy) column): the x-y part of the Gaussian times the
+  // normalisation, the x-y part of the line-of-sight numerator, the first iteration's factor.  (gx gy) gz dc is the
+  // product FusedLosOp forms as ((gx gy) gz) dc -- Float64, the association differs in the last bit only.
+  struct Col {
+    double gxy;
+    float kx, ky, cxy, fac1;
+  };
+  __device__ __forceinline__ Col column(float kx, float ky, int ix, int iy) const {
+    Col c;
+    c.gxy = __ldg(gt.gx + ix) * __ldg(gt.gy + iy);
+    c.kx = kx;
+    c.ky = ky;
+    c.cxy = __fadd_rn(__fmul_rn(__fmul_rn(kx, kx), los[0]), __fmul_rn(__fmul_rn(ky, ky), los[1]));
+    c.fac1 = __fdiv_rn(beta, __fadd_rn(1.0f, beta));
+    return c;
+  }
+  __device__ __forceinline__ float2 solve(float2 v, const Col& c, float kz, double gz_dc, bool is_dc) const {
+    float k2 = ksq(c.kx, c.ky, kz);
+    double s = c.gxy * gz_dc;
     if (is_dc) s = 0.0;
     float dsx = (float)((double)v.x * s), dsy = (float)((double)v.y * s);
-    float c = __fmul_rn(__fmul_rn(kx, kx), los[0]);
-    c = __fadd_rn(c, __fmul_rn(__fmul_rn(ky, ky), los[1]));
-    c = __fadd_rn(c, __fmul_rn(__fmul_rn(kz, kz), los[2]));
-    float mu = k2 > 0.f ? __fdiv_rn(c, k2) : 0.f;
+    float num = __fadd_rn(c.cxy, __fmul_rn(__fmul_rn(kz, kz), los[2]));
+    float mu = k2 > 0.f ? __fdiv_rn(num, k2) : 0.f;
     float drx = dsx, dry = dsy;
-    for (int it = 1; it <= n_iter; it++) {
-      float fac = it == 1 ? __fdiv_rn(beta, __fadd_rn(1.0f, beta)) : beta;
-      float fm = __fmul_rn(fac, mu);
+    if (n_iter >= 1) {
+      float fm = __fmul_rn(c.fac1, mu);
       drx = __fsub_rn(dsx, __fmul_rn(fm, drx));
       dry = __fsub_rn(dsy, __fmul_rn(fm, dry));
+      fm = __fmul_rn(beta, mu);
+      for (int it = 2; it <= n_iter; it++) {
+        drx = __fsub_rn(dsx, __fmul_rn(fm, drx));
+        dry = __fsub_rn(dsy, __fmul_rn(fm, dry));
+      }
     }
     return make_float2(drx, dry);
   }
@@ -212,7 +162,7 @@ struct OpDisp {
     if (potential) {
       s = invM;
     } else {
-      float k2 = __fadd_rn(__fadd_rn(__fmul_rn(kx, kx), __fmul_rn(ky, ky)), __fmul_rn(kz, kz));
+      float k2 = ksq(kx, ky, kz);
       s = k2 > 0.f ? __fdiv_rn(invM, k2) : 0.f;
     }
     float kc = c == 0 ? kx : (c == 1 ? ky : kz);
@@ -221,130 +171,149 @@ struct OpDisp {
 };
 
 // ---- kernels -----------------------------------------------------------------------------------------
-// plain pass: out = FFT_DIR(in) along the strided axis (in place allowed)
+// plain pass: out = FFT_DIR(in) along the strided axis (in place allowed: a CTA reads its whole tile before it writes)
 template <int N, int DIR>
-__global__ void __launch_bounds__(FFT_THREADS)
+__global__ void __launch_bounds__(FFT_THREADS, N >= 2048 ? 1 : FFT_CTAS_1024)
 fft_cols_kernel(const float2* __restrict__ in, float2* __restrict__ out, ColGeom cg, const float2* __restrict__ tw,
                 int hermitian_edges) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Tile<N>& T = *reinterpret_cast<Tile<N>*>(smem_raw);
-  const int x0 = blockIdx.x * FFT_TX;
-  const int ncol = min(FFT_TX, cg.ncols - x0);
-  const size_t base = (size_t)blockIdx.y * cg.outer_stride + x0;
-  tile_load<N>(T, in + base, cg.stride, ncol);
-  __syncthreads();
-  const int lane = threadIdx.x & 31, col = threadIdx.x >> 5;
-  if (col < ncol) {
-    float2 v[N / 32];
-    col_read<N>(T, col, lane, v);
-    warp_fft<N, DIR>(v, tw, lane);
-    __syncwarp();
-    col_write<N>(T, col, lane, v);
+  float2* S = reinterpret_cast<float2*>(smem_raw);
+  constexpr int M = N / 32, MT = M >= 32 ? M / 32 : 1;
+  const int c = threadIdx.x & (FFT_TX - 1), t = threadIdx.x >> 3;
+  const int ix = blockIdx.x * FFT_TX + c;
+  const bool valid = ix < cg.ncols;
+  const size_t base = (size_t)blockIdx.y * cg.outer_stride + ix;
+  float2 v[M], X[MT][32];
+  if (valid) load_column<N>(v, in + base, cg.stride, t);
+  else {
+#pragma unroll
+    for (int j = 0; j < M; j++) v[j] = make_float2(0.f, 0.f);
   }
-  __syncthreads();
+  fft_column<N, DIR>(v, X, S, tw, c, t);
   // Last pass before the C2R along x: the kx = 0 and kx = Nyquist columns must be real there.  FFTW
   // and pocketfft ignore their imaginary part; cuFFT's 1-D C2R does not, so it is dropped here
   // (it is non-zero only for inputs with power at the Nyquist modes, e.g. i k multiplications).
-  const int cme = threadIdx.x & (FFT_TX - 1);
-  const bool drop = hermitian_edges && (x0 + cme == 0 || x0 + cme == cg.ncols - 1);
-  tile_store<N>(T, out + base, cg.stride, ncol, drop);
+  const bool drop = hermitian_edges && (ix == 0 || ix == cg.ncols - 1);
+  if (valid) {
+#pragma unroll
+    for (int m = 0; m < MT; m++) {
+      const int k2 = t + 32 * m;
+      if (M >= 32 || k2 < M) {
+        float2* o = out + base + (size_t)k2 * cg.stride;
+#pragma unroll
+        for (int k1 = 0; k1 < 32; k1++) {
+          float2 r = X[m][fft_bitrev<32>(k1)];
+          if (drop) r.y = 0.f;
+          o[(size_t)k1 * M * cg.stride] = r;
+        }
+      }
+    }
+  }
 }
 
-// z pass of the fused fixed-LOS solve: forward z FFT, operator, inverse z FFT; in place.
+// z pass of the fused fixed-LOS solve (N >= 1024: the forward output is the inverse input, register for register):
+// forward z FFT, operator, [delta_k kept], inverse z FFT; in place.
 template <int N>
-__global__ void __launch_bounds__(FFT_THREADS)
+__global__ void __launch_bounds__(FFT_THREADS, N >= 2048 ? 1 : FFT_CTAS_1024)
 fft_z_solve_kernel(float2* __restrict__ data, float2* __restrict__ keep, ColGeom cg, const float2* __restrict__ tw,
                    OpLosSolve op) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Tile<N>& T = *reinterpret_cast<Tile<N>*>(smem_raw);
-  constexpr int M = N / 32;
-  const int x0 = blockIdx.x * FFT_TX;
-  const int ncol = min(FFT_TX, cg.ncols - x0);
-  const int iy = blockIdx.y;
-  const size_t base = (size_t)iy * cg.outer_stride + x0;
-  tile_load<N>(T, data + base, cg.stride, ncol);
-  __syncthreads();
-  const int lane = threadIdx.x & 31, col = threadIdx.x >> 5;
-  float2 v[M];
-  if (col < ncol) {
-    col_read<N>(T, col, lane, v);
-    warp_fft<N, 1>(v, tw, lane);
-    const int ix = x0 + col;
-    const float kx = __ldg(cg.kx + ix), ky = __ldg(cg.kouter + iy);
-    const int f0 = M * (int)(__brev((unsigned)lane) >> 27);
+  float2* S = reinterpret_cast<float2*>(smem_raw);
+  constexpr int M = N / 32, MT = M / 32;
+  static_assert(M >= 32, "the fused z pass needs N >= 1024");
+  const int c = threadIdx.x & (FFT_TX - 1), t = threadIdx.x >> 3;
+  const int ix = blockIdx.x * FFT_TX + c, iy = blockIdx.y;
+  const bool valid = ix < cg.ncols;
+  const size_t base = (size_t)iy * cg.outer_stride + ix;
+  float2 v[M], X[MT][32];
+  if (valid) load_column<N>(v, data + base, cg.stride, t);
+  else {
 #pragma unroll
-    for (int q = 0; q < M; q++) {
-      const int f = f0 + q;
-      v[q] = op.solve(v[q], kx, ky, __ldg(cg.ktrans + f), (ix | iy | f) == 0);
+    for (int j = 0; j < M; j++) v[j] = make_float2(0.f, 0.f);
+  }
+  fft_column<N, 1>(v, X, S, tw, c, t);
+  const OpLosSolve::Col col = op.column(valid ? __ldg(cg.kx + ix) : 0.f, __ldg(cg.kouter + iy), valid ? ix : 0, iy);
+  const double dc8 = __ldg(op.scal + 8);
+#pragma unroll
+  for (int m = 0; m < MT; m++)
+#pragma unroll
+    for (int k1 = 0; k1 < 32; k1++) {
+      const int f = t + 32 * m + M * k1;      // = t + 32 (m + MT k1): the inverse transform's register m + MT k1
+      float2 d = make_float2(0.f, 0.f);
+      if (valid) {
+        d = op.solve(X[m][fft_bitrev<32>(k1)], col, __ldg(cg.ktrans + f), __ldg(op.gt.gz + f) * dc8, (ix | iy | f) == 0);
+        if (keep != nullptr) keep[base + (size_t)f * cg.stride] = d;
+      }
+      v[m + MT * k1] = make_float2(d.x * op.invM, d.y * op.invM);
     }
-    __syncwarp();
-    col_write<N>(T, col, lane, v);
-  }
-  if (keep != nullptr) {  // uniform branch: delta_final_k for the read-back cache
-    __syncthreads();
-    tile_store<N>(T, keep + base, cg.stride, ncol);
-    __syncthreads();
-  } else {
-    __syncwarp();
-  }
-  if (col < ncol) {
-    col_read<N>(T, col, lane, v);
+  __syncthreads();  // everybody has read the exchange buffer of the forward transform
+  fft_column<N, -1>(v, X, S, tw, c, t);
+  if (valid) {
 #pragma unroll
-    for (int q = 0; q < M; q++) v[q] = make_float2(v[q].x * op.invM, v[q].y * op.invM);
-    warp_fft<N, -1>(v, tw, lane);
-    __syncwarp();
-    col_write<N>(T, col, lane, v);
+    for (int m = 0; m < MT; m++)
+#pragma unroll
+      for (int k1 = 0; k1 < 32; k1++)
+        data[base + (size_t)(t + 32 * m + M * k1) * cg.stride] = X[m][fft_bitrev<32>(k1)];
   }
-  __syncthreads();
-  tile_store<N>(T, data + base, cg.stride, ncol);
 }
 
-// z pass of the displacement read-back: (forward z FFT of `in` unless FROM_K) then for each of the
-// three components operator + inverse z FFT into out[c].  One read, three writes.
-template <int N, bool FROM_K>
-__global__ void __launch_bounds__(FFT_THREADS)
+// z pass of the displacement read-back from a kept delta_k (phi_k).  i k_x and i k_y are constants of a column, so the x
+// and y fields share ONE inverse z transform of G = delta_k / (k^2 M) (phi_k / M); the z field is the inverse transform
+// of H = i k_z G.  Two transforms and three stores per column; delta_k is read twice (the second read of the 64 KB
+// tile comes from L2) so that no copy of it has to stay in registers while a transform runs -- the first version
+// kept it, needed 255 registers (one CTA per SM) and ran three transforms: 11.3 ms at 1024^3.
+template <int N>
+__global__ void __launch_bounds__(FFT_THREADS, N >= 2048 ? 1 : FFT_CTAS_1024)
 fft_z_disp_kernel(const float2* __restrict__ in, float2* __restrict__ o0, float2* __restrict__ o1,
                   float2* __restrict__ o2, ColGeom cg, const float2* __restrict__ tw, OpDisp op) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Tile<N>& T = *reinterpret_cast<Tile<N>*>(smem_raw);
-  constexpr int M = N / 32;
-  const int x0 = blockIdx.x * FFT_TX;
-  const int ncol = min(FFT_TX, cg.ncols - x0);
-  const int iy = blockIdx.y;
-  const size_t base = (size_t)iy * cg.outer_stride + x0;
-  tile_load<N>(T, in + base, cg.stride, ncol);
-  __syncthreads();
-  const int lane = threadIdx.x & 31, col = threadIdx.x >> 5;
-  const int f0 = M * (int)(__brev((unsigned)lane) >> 27);
-  float2 dk[M];  // delta_k (or phi_k) of this column, frequency f0 + q
-  float kx = 0.f, ky = 0.f;
-  if (col < ncol) {
-    if (FROM_K) {
-#pragma unroll
-      for (int q = 0; q < M; q++) dk[q] = T.at(f0 + q, col);
-    } else {
-      col_read<N>(T, col, lane, dk);
-      warp_fft<N, 1>(dk, tw, lane);
-    }
-    kx = __ldg(cg.kx + x0 + col);
-    ky = __ldg(cg.kouter + iy);
-  }
+  float2* S = reinterpret_cast<float2*>(smem_raw);
+  constexpr int M = N / 32, MT = M >= 32 ? M / 32 : 1;
+  const int c = threadIdx.x & (FFT_TX - 1), t = threadIdx.x >> 3;
+  const int ix = blockIdx.x * FFT_TX + c, iy = blockIdx.y;
+  const bool valid = ix < cg.ncols;
+  const size_t base = (size_t)iy * cg.outer_stride + ix;
+  const float kx = valid ? __ldg(cg.kx + ix) : 0.f, ky = __ldg(cg.kouter + iy);
 #pragma unroll 1
-  for (int c = 0; c < 3; c++) {
-    float2* outc = c == 0 ? o0 : (c == 1 ? o1 : o2);
-    __syncthreads();  // previous tile contents fully consumed / stored
-    if (col < ncol) {
-      float2 v[M];
+  for (int pass = 0; pass < 2; pass++) {   // 0: H -> z field;  1: G -> x and y fields
+    float2 v[M], X[MT][32];
+    if (valid) load_column<N>(v, in + base, cg.stride, t);
 #pragma unroll
-      for (int q = 0; q < M; q++) T.at(f0 + q, col) = op.comp(dk[q], kx, ky, __ldg(cg.ktrans + f0 + q), c);
-      __syncwarp();
-      col_read<N>(T, col, lane, v);
-      warp_fft<N, -1>(v, tw, lane);
-      __syncwarp();
-      col_write<N>(T, col, lane, v);
+    for (int j = 0; j < M; j++) {
+      const float kz = __ldg(cg.ktrans + t + 32 * j);
+      float s;
+      if (op.potential) {
+        s = op.invM;
+      } else {
+        float k2 = ksq(kx, ky, kz);
+        s = k2 > 0.f ? __fdiv_rn(op.invM, k2) : 0.f;
+      }
+      const float2 d = valid ? v[j] : make_float2(0.f, 0.f);
+      // the products of DispOp: re = (-v.y s) k, im = (v.x s) k;  G itself for the shared transform
+      v[j] = pass == 0 ? make_float2(__fmul_rn(__fmul_rn(-d.y, s), kz), __fmul_rn(__fmul_rn(d.x, s), kz))
+                       : make_float2(__fmul_rn(d.x, s), __fmul_rn(d.y, s));
     }
-    __syncthreads();
-    tile_store<N>(T, outc + base, cg.stride, ncol);
+    if (pass) __syncthreads();  // the first transform's exchange buffer has been read
+    fft_column<N, -1>(v, X, S, tw, c, t);
+    if (valid) {
+#pragma unroll
+      for (int m = 0; m < MT; m++) {
+        const int k2 = t + 32 * m;
+        if (M >= 32 || k2 < M) {
+#pragma unroll
+          for (int k1 = 0; k1 < 32; k1++) {
+            const size_t o = base + (size_t)(k2 + M * k1) * cg.stride;
+            const float2 r = X[m][fft_bitrev<32>(k1)];
+            if (pass == 0) {
+              o2[o] = r;
+            } else {  // i k g = (-g.y k, g.x k)
+              o0[o] = make_float2(__fmul_rn(-r.y, kx), __fmul_rn(r.x, kx));
+              o1[o] = make_float2(__fmul_rn(-r.y, ky), __fmul_rn(r.x, ky));
+            }
+          }
+        }
+      }
+    }
   }
 }
 
@@ -366,10 +335,17 @@ __global__ void dc_from_xy_kernel(const float2* __restrict__ a, size_t zstride, 
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
-static bool pow2_ok(int n) { return n >= 64 && n <= 2048 && (n & (n - 1)) == 0; }
+static bool pow2_ok(int n) { return n >= 256 && n <= 2048 && (n & (n - 1)) == 0; }
+
+// the fused z pass (forward + operator + inverse in one kernel) needs N >= 1024: below that the last step of the
+// four-step transform leaves its output in 16 (8) of a column's 32 threads, not where the inverse reads its input
+bool own_fft_fused_available(const baorec_ctx* ctx) { return own_fft_available(ctx) && ctx->nz >= 1024; }
 
 bool own_fft_available(const baorec_ctx* ctx) {
-  return ctx->opt_own_fft && ctx->have_x_plans && pow2_ok(ctx->ny) && pow2_ok(ctx->nz) && ctx->d_tw[0] && ctx->d_tw[1];
+  // -1 = auto: on where it was measured faster than cuFFT's 3-D plans (both strided axes a power of two >= 512:
+  // 49.3 vs 52.8 ms per reconstruction at 1024^3, 6.5 vs 6.8 ms of transforms at 512^3; slower at 256^3)
+  const bool want = ctx->opt_own_fft > 0 || (ctx->opt_own_fft < 0 && ctx->ny >= 512 && ctx->nz >= 512);
+  return want && ctx->have_x_plans && pow2_ok(ctx->ny) && pow2_ok(ctx->nz) && ctx->d_tw[0] && ctx->d_tw[1];
 }
 
 // twiddle tables exp(-2 pi i k / n) for the y and z axes, computed in double
@@ -393,12 +369,10 @@ int own_fft_setup(baorec_ctx* ctx) {
 }
 
 template <int N>
-static size_t tile_bytes() { return sizeof(Tile<N>); }
+static size_t tile_bytes() { return Xch<N>::BYTES; }
 
 #define FFT_DISPATCH_N(n, CALL)     \
   switch (n) {                      \
-    case 64: { CALL(64); } break;   \
-    case 128: { CALL(128); } break; \
     case 256: { CALL(256); } break; \
     case 512: { CALL(512); } break; \
     case 1024: { CALL(1024); } break; \
@@ -497,7 +471,7 @@ int own_fused_los_solve(baorec_ctx* ctx, const baorec_params* p, float* mesh, fl
   BR_LAUNCH(ctx, dc_from_xy_kernel, 1, 256, 0, st, work, (size_t)ctx->xh * ctx->ny, ctx->nz, ctx->d_scal, 0,
             (double)ctx->M / (double)p->bias);
   OpLosSolve op;
-  op.R2 = p->smoothing_radius * p->smoothing_radius;
+  BR_TRY(gauss_tables(ctx, p->smoothing_radius, &op.gt.gx, &op.gt.gy, &op.gt.gz, st));
   op.scal = ctx->d_scal;
   for (int a = 0; a < 3; a++) op.los[a] = p->los[a];
   op.beta = p->beta;
@@ -509,7 +483,11 @@ int own_fused_los_solve(baorec_ctx* ctx, const baorec_params* p, float* mesh, fl
   BR_TRY(set_smem(fft_z_solve_kernel<NN>, tile_bytes<NN>()));                                             \
   BR_LAUNCH_NAMED(ctx, "fft_z_solve_kernel", fft_z_solve_kernel<NN>, grid, FFT_THREADS, tile_bytes<NN>(), st, work, \
                   keep, g, ctx->d_tw[1], op);
-  FFT_DISPATCH_N(ctx->nz, CALL)
+  switch (ctx->nz) {
+    case 1024: { CALL(1024); } break;
+    case 2048: { CALL(2048); } break;
+    default: set_error("own FFT: the fused z pass needs nz = 1024 or 2048"); return BAOREC_ERR_INVALID;
+  }
 #undef CALL
   BR_TRY(cols_pass(ctx, work, 1, -1, st, 1));
   return x_c2r(ctx, work, mesh, st);
@@ -524,21 +502,16 @@ int own_displacements(baorec_ctx* ctx, const float* mesh, const float2* from_k, 
   const ColGeom g = geom_z(ctx);
   dim3 grid(cdiv(g.ncols, FFT_TX), ctx->ny);
   const float2* src = from_k;
-  if (!from_k) {
+  if (!from_k) {  // delta_k (phi_k) first: the z kernel starts in k space
     BR_TRY(x_r2c(ctx, mesh, w0, st));
     BR_TRY(cols_pass(ctx, w0, 1, +1, st));
+    BR_TRY(cols_pass(ctx, w0, 2, +1, st));
     src = w0;
   }
 #define CALL(NN)                                                                                               \
-  if (from_k) {                                                                                                \
-    BR_TRY(set_smem(fft_z_disp_kernel<NN, true>, tile_bytes<NN>()));                                           \
-    BR_LAUNCH_NAMED(ctx, "fft_z_disp_kernel<from_k>", (fft_z_disp_kernel<NN, true>), grid, FFT_THREADS,         \
-                    tile_bytes<NN>(), st, src, w0, w1, w2, g, ctx->d_tw[1], op);                                \
-  } else {                                                                                                     \
-    BR_TRY(set_smem(fft_z_disp_kernel<NN, false>, tile_bytes<NN>()));                                          \
-    BR_LAUNCH_NAMED(ctx, "fft_z_disp_kernel<from_mesh>", (fft_z_disp_kernel<NN, false>), grid, FFT_THREADS,     \
-                    tile_bytes<NN>(), st, src, w0, w1, w2, g, ctx->d_tw[1], op);                                \
-  }
+  BR_TRY(set_smem(fft_z_disp_kernel<NN>, tile_bytes<NN>()));                                                   \
+  BR_LAUNCH_NAMED(ctx, "fft_z_disp_kernel", fft_z_disp_kernel<NN>, grid, FFT_THREADS, tile_bytes<NN>(), st, src, w0, \
+                  w1, w2, g, ctx->d_tw[1], op);
   FFT_DISPATCH_N(ctx->nz, CALL)
 #undef CALL
   float2* w[3] = {w0, w1, w2};

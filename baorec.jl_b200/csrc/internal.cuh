@@ -144,7 +144,7 @@ struct baorec_ctx {
   cufftHandle ps_r2c = 0, ps_c2r = 0, ps_z = 0;
   int split_planes_planned = 0;
   int opt_fft_split = 0;
-  int opt_own_fft = 0;  // experimental: correct, but slower than cuFFT's strided passes today
+  int opt_own_fft = -1;  // column FFT kernels of fft.cu instead of cuFFT's 3-D plans: -1 = auto (ny, nz powers of two >= 512), 0 = never, 1 = wherever supported (>= 256)
   size_t work_bytes = 0;
   float* d_k[3] = {nullptr, nullptr, nullptr};  // k tables (xh, ny, nz)
   float* d_xv[3] = {nullptr, nullptr, nullptr}; // cell-centre tables (nx, ny, nz)
@@ -358,6 +358,7 @@ int randoms_combine(baorec_ctx* ctx, float* out, const float* dat, const float* 
 
 // fft.cu
 bool own_fft_available(const baorec_ctx* ctx);
+bool own_fft_fused_available(const baorec_ctx* ctx);
 int own_fft_setup(baorec_ctx* ctx);
 int own_r2c(baorec_ctx* ctx, const float* in, float2* out, cudaStream_t st);
 int own_c2r(baorec_ctx* ctx, float2* in, float* out, cudaStream_t st);

@@ -303,7 +303,7 @@ int reconstructed_overdensity(baorec_ctx* ctx, const baorec_params* p, float* me
     BR_TRY(need_t(ctx, BUF_CK0, ctx->Mc, &ck0));
     float2* keep = nullptr;
     if (ctx->want_kcache || ctx->opt_keep_delta_k) BR_TRY(need_t(ctx, BUF_CKCACHE, ctx->Mc, &keep));
-    if (nr == 0 && own_fft_available(ctx)) {
+    if (nr == 0 && own_fft_fused_available(ctx)) {
       // x: cuFFT 1-D; y: column kernel; z: forward + solve + inverse in one kernel; y; x
       BR_TRY(reset_oob(ctx, st));
       BR_TRY(scatter(ctx, mesh, x, y, z, w, n, 1, p->mas, st));

@@ -169,7 +169,7 @@ def algorithmic_bytes(name, M, Mc, N, chunks=1):
     if name.startswith("fft_cols_kernel"):
         return 16 * Mc
     if name.startswith("fft_z_solve"):
-        return 16 * Mc                      # (+ 8 Mc when delta_k is kept for the read-back)
+        return 24 * Mc                      # column in, column out, delta_k kept for the read-back
     if name.startswith("fft_z_disp"):
         return 8 * Mc + 24 * Mc
     if name.startswith("cufft"):

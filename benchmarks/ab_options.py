@@ -22,7 +22,7 @@ import __graft_entry__ as G  # noqa: E402
 import catalogs  # noqa: E402
 
 B = G.load_package()
-DEFAULTS = {"unified_sort": 1, "gather_tiles": 1, "deterministic_scatter": 0, "fuse_kspace": 1, "gather_stage": 1, "scatter_pairs": 2}
+DEFAULTS = {"unified_sort": 1, "gather_tiles": 1, "deterministic_scatter": 0, "fuse_kspace": 1, "gather_stage": 1, "scatter_pairs": 2, "own_fft": -1}
 
 
 def main():
@@ -43,7 +43,7 @@ def main():
     kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, n_iter=3, los=(0.0, 0.0, 1.0), box_size=np.full(3, L, np.float32),
               box_min=np.zeros(3, np.float32))
     ctx = B.Context.get(0)
-    configs = [{}] + [{k: 0 if v else 1} for k, v in DEFAULTS.items()]
+    configs = [{}] + [{k: 0 if v else 1} for k, v in DEFAULTS.items()]       # (own_fft: auto -> 0 = cuFFT's 3-D plans)
     for item in args.set:
         k, v = item.split("=")
         configs.append({k: int(v)})

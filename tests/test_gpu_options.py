@@ -19,7 +19,7 @@ def dev(a):
 @contextlib.contextmanager
 def options(B, **kw):
     ctx = B.Context.get(0)
-    defaults = {"bin_min_particles": 1 << 18, "fuse_kspace": 1, "own_fft": 0, "gather_tiles": 1,
+    defaults = {"bin_min_particles": 1 << 18, "fuse_kspace": 1, "own_fft": -1, "gather_tiles": 1,
                 "fft_split_planes": 0, "scatter_tiles": 0,
                 "unified_sort": 1}
     try:
@@ -180,9 +180,11 @@ def test_fused_with_randoms_fixed_los(B, O):
 
 
 # ---- own FFT path (cuFFT 1-D along x + column kernels along y/z with fused k-space operators) -----
-@pytest.mark.parametrize("shape", [(64, 64, 64), (128, 64, 256), (64, 512, 128), (96, 128, 64), (64, 1024, 64),
-                                   (64, 64, 2048)])
+@pytest.mark.parametrize("shape", [(64, 256, 256), (128, 512, 256), (40, 256, 1024), (96, 1024, 256), (24, 256, 2048),
+                                   (16, 2048, 512)])
 def test_own_fft_smooth_and_displacements_match_cufft_and_oracle(B, O, shape):
+    """Column kernels of csrc/fft.cu for every supported length (256 ... 2048 along y and z; shorter axes fall back to
+    cuFFT), partial column tiles included (nx/2 + 1 is never a multiple of 8)."""
     nx, ny, nz = shape
     L = 1000.0
     bs, bm = np.full(3, L, np.float32), np.zeros(3, np.float32)
@@ -204,6 +206,35 @@ def test_own_fft_smooth_and_displacements_match_cufft_and_oracle(B, O, shape):
         # path drops the offending imaginary parts like FFTW/pocketfft (= the oracle); cuFFT's C2R
         # does not, so the library path is only compared on the smoothed field above
         assert rel_rms(out[1][1][a], opsi[a]) < 5e-6
+
+
+@pytest.mark.parametrize("los", [(0.0, 0.0, 1.0), (0.0, 1.0, 0.0)])
+def test_own_fft_fused_z_pass_matches_the_oracle(B, O, los):
+    """run! + read_shifts with own_fft = 1 on a mesh with nz = 1024: the z pass is ONE kernel (forward z transform,
+    smoothing + normalisation + all iterations in registers, delta_k kept, inverse z transform) and the read-back emits
+    the three displacement fields from one read of delta_k."""
+    grid, L, N = (32, 256, 1024), 1000.0, 300_000
+    pos, w = clustered_box(N, L, seed=41)
+    kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=np.full(3, L, np.float32),
+              box_min=np.zeros(3, np.float32), los=los, n_iter=3)
+    orec = O.IterativeRecon(**kw)
+    omesh = O.run(orec, grid, *[p.copy() for p in pos], w)
+    oshift = O.read_shifts(orec, *pos, omesh, "sum")
+    d = [dev(p) for p in pos]
+    with options(B, own_fft=1):
+        rec = B.IterativeRecon(**kw)
+        mesh = B.run(rec, grid, *d, dev(w))
+        s = B.read_shifts(rec, *d, mesh, field="sum")
+        names = set()
+        ctx = B.Context.get(0)
+        ctx.profile(True)
+        B.run(rec, grid, *d, dev(w))
+        names = set(ctx.profile_read())
+        ctx.profile(False)
+    assert "fft_z_solve_kernel" in names and not any(k.startswith("cufft_r2c") for k in names), names
+    assert rel_rms(mesh.cpu().numpy(), omesh) < 1e-4
+    for a in range(3):
+        assert rel_rms(s[a].cpu().numpy(), oshift[a]) < 1e-4 and maxabs(s[a].cpu().numpy(), oshift[a]) < 1e-3
 
 
 def test_result_cache_read_skips_forward_transform_and_matches(B, O):

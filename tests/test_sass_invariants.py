@@ -61,11 +61,13 @@ def test_no_register_spills_and_known_local_memory_users(K):
     value in its parameters (the compiler copies it to the stack): listed here so that a new one does not go unnoticed (the slab transpose's peer table was one: 16 local stores per
     thread until it became __grid_constant__)."""
     spills = {k for k, v in K.items() if v["spill"]}
-    assert all("cartesian_to_sky_kernel<1>" in k for k in spills), spills
+    # (peer_push_kernel: ptxas keeps one 4-byte loop-invariant on the stack at 40 registers -- outside the copy loop)
+    assert all("cartesian_to_sky_kernel<1>" in k or "peer_push_kernel" in k for k in spills), spills
     local = {k.replace("(anonymous namespace)::", "").split("(")[0].replace("void ", "").replace("baorec::", "") for k, v in K.items() if v["local"]}
     assert local == {"cartesian_to_sky_kernel<1>", "sky_to_cartesian_kernel<1>", "sky_to_cartesian_kernel<4>",   # sincos quadrant table
                      "gather_trash_kernel",                      # GatherArgs.o[c] with a run-time c
-                     "mg_coarse_kernel"}, local                  # level table of the single-block coarse V-cycle
+                     "mg_coarse_kernel",                         # level table of the single-block coarse V-cycle
+                     "peer_push_kernel"}, local                  # the 4-byte spill above
 
 
 def test_multipole_kernel(K):
