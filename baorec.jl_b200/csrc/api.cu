@@ -201,6 +201,7 @@ int baorec_set_option(baorec_ctx* ctx, const char* name, int64_t value) {
     baorec::dist_refresh_mode(ctx);
   }
   else if (s == "mg_coarse") ctx->opt_mg_coarse = (int)value;
+  else if (s == "mg_remove_mean") ctx->opt_mg_remove_mean = (int)value;
   else if (s == "mg_bulk") ctx->opt_mg_bulk = (int)value;
   else if (s == "catalog_corr") ctx->opt_catalog_corr = (int)value;   // test hook (catalog.cu): -1 = measured value
   else if (s == "mg_slab_min_cells") {

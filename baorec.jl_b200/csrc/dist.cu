@@ -181,6 +181,11 @@ int mg_allgather(baorec_ctx* ctx, const float* send, float* recv, size_t count, 
   return BAOREC_OK;
 }
 
+int mg_allreduce_sum(baorec_ctx* ctx, double* d_value, cudaStream_t st) {
+  if (ctx->nranks > 1) BR_NCCL(ncclAllReduce(d_value, d_value, 1, ncclDouble, ncclSum, comm_of(ctx), st));
+  return BAOREC_OK;
+}
+
 __global__ void set_scalar_kernel(double* p, double v) { *p = v; }
 
 // ---- peer-copy exchange: flags --------------------------------------------------------------------------------

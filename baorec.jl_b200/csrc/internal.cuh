@@ -210,6 +210,7 @@ struct baorec_ctx {
   // multigrid
   std::vector<baorec::MgLevel> levels;
   std::vector<baorec::MgLevel> dlevels;  // slab-decomposed hierarchy (baorec_plan_dist)
+  int opt_mg_remove_mean = 1;  // multigrid solves on f - mean(f) (cubic cells): see mg_fmg in multigrid.cu
   int opt_mg_coarse = 1;  // levels of <= 4096 cells: the bottom of the V-cycle in one thread block
   int opt_mg_bulk = 0;    // staged kernel: row bodies by TMA bulk copies; measured SLOWER than cp.async staging (554 vs 355 us), off
   int opt_mg_ring = 6;    // planes in the staged kernel's shared-memory ring (3 or 6)
@@ -381,6 +382,7 @@ int mg_fmg_dist(baorec_ctx* ctx, float* f_slab, float** result, float beta, floa
 // dist.cu: both halo planes of a slab-layout buffer (ring neighbours, periodic); all-gather of slabs
 int mg_halo_exchange(baorec_ctx* ctx, float* buf, size_t plane, int nzl, cudaStream_t st);
 int mg_allgather(baorec_ctx* ctx, const float* send, float* recv, size_t count, cudaStream_t st);
+int mg_allreduce_sum(baorec_ctx* ctx, double* d_value, cudaStream_t st);  // one double, summed over the ranks in place
 void dist_refresh_mode(baorec_ctx* ctx);  // re-evaluates ctx->p2p (peer-copy exchange usable?) after an option / mapping change
 
 #define BR_NEED_PLAN(ctx)                                        \

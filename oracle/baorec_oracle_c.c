@@ -320,6 +320,15 @@ EXPORT void oc_shifts_f32(float *sx, float *sy, float *sz, const float *x, const
  * One stencil evaluation (jacobi!: :14-135, residual!: :213-326).  mode 0: out = (1-w) v + w * jac,
  * jac = (f + offdiag(v)) / diag; mode 1: out = f - (diag v - offdiag(v)).  xv,yv,zv = cell centres
  * (radial) or NULL with los given.  Periodic neighbours. */
+/* Yardstick hook (tests only): with the flag set the stencil below evaluates the SAME formula with its Float32 sums
+ * associated differently (terms added in reverse order, the damping and the residual written in their other algebraic
+ * form) -- what LoopVectorization's @tturbo (src/multigrid.jl:37...) is free to do, and what any other correct
+ * implementation does somewhere.  The distance between the two results is how sharply the Float32 reference defines
+ * its own answer: on a lightcone the right-hand side has a non-zero mean, the iterate drifts to a constant ~70x the
+ * rms of its fluctuations, and the stencil's cancellation then leaves the potential defined to ~1e-2 only. */
+static int oc_reassociate = 0;
+EXPORT void oc_set_reassociate(int on) { oc_reassociate = on; }
+
 EXPORT void oc_mg_stencil_f32(float *out, const float *v, const float *f, int nx, int ny, int nz, const float *L,
                               const float *xv, const float *yv, const float *zv, const float *los, float beta, float w,
                               int mode) {
@@ -327,6 +336,7 @@ EXPORT void oc_mg_stencil_f32(float *out, const float *v, const float *f, int nx
     const float c2[3] = {cell[0] * cell[0], cell[1] * cell[1], cell[2] * cell[2]};
     const float ic2[3] = {1.0f / c2[0], 1.0f / c2[1], 1.0f / c2[2]};
     const int radial = (los == NULL);
+    const int re = oc_reassociate;
 #pragma omp parallel for schedule(static) collapse(2)
     for (int iz = 0; iz < nz; ++iz)
         for (int iy = 0; iy < ny; ++iy) {
@@ -351,7 +361,14 @@ EXPORT void oc_mg_stencil_f32(float *out, const float *v, const float *f, int nx
                                  pz * (V(zp, iy, ix) - V(zm, iy, ix)));
                 const float diag = 2.0f * ((gx + gy) + gz);
                 const size_t c = ((size_t)iz * ny + iy) * nx + ix;
-                if (mode == 0) out[c] = (1.0f - w) * v[c] + w * ((f[c] + s) / diag);
+                if (re) {   /* the same terms, summed from the other end; see oc_set_reassociate */
+                    float t = gz * (V(zm, iy, ix) + V(zp, iy, ix)) + (gy * (V(iz, ym, ix) + V(iz, yp, ix)) + gx * (V(iz, iy, xm) + V(iz, iy, xp)));
+                    t = (g / 2.0f) * ((py * pz) * cyz + ((px * pz) * cxz + (px * py) * cxy)) + t;
+                    if (radial)
+                        t = g * (pz * (V(zp, iy, ix) - V(zm, iy, ix)) + (py * (V(iz, yp, ix) - V(iz, ym, ix)) + px * (V(iz, iy, xp) - V(iz, iy, xm)))) + t;
+                    if (mode == 0) out[c] = v[c] + w * ((t + f[c]) / diag - v[c]);
+                    else out[c] = (f[c] + t) - diag * v[c];
+                } else if (mode == 0) out[c] = (1.0f - w) * v[c] + w * ((f[c] + s) / diag);
                 else out[c] = f[c] - (diag * v[c] - s);
 #undef V
             }

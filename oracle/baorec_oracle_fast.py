@@ -61,6 +61,8 @@ def _bind(lib):
     lib.oc_shifts_f32.argtypes = [_F, _F, _F, _F, _F, _F, i64, i, f, _F]
     lib.oc_mg_stencil_f32.restype = None
     lib.oc_mg_stencil_f32.argtypes = [_F, _F, _F, i, i, i, _F, _F, _F, _F, _F, f, f, i]
+    lib.oc_set_reassociate.restype = None
+    lib.oc_set_reassociate.argtypes = [i]
     lib.oc_mg_restrict_f32.restype = None
     lib.oc_mg_restrict_f32.argtypes = [_F, _F, i, i, i]
     lib.oc_mg_prolong_f32.restype = None
@@ -271,6 +273,7 @@ def load(threads=None):
                          compute_displacements_multigrid=lambda m, x, y, z, r, formula="cpu": compute_displacements(m, x, y, z, r, formula),
                          read_shifts=read_shifts, jacobi=jacobi, residual=residual, restrict=restrict, prolong=prolong).items():
         setattr(O, name, fn)
+    O.set_reassociate = lambda on: lib.oc_set_reassociate(int(bool(on)))    # tests: a differently associated evaluation of the same stencil
     O.threads = lib.oc_max_threads()
     O.kspace_c = kspace
     O.numpy_loops = N

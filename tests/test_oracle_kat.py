@@ -309,3 +309,31 @@ def test_float32_oracle_tracks_float64():
         out[T] = O.read_shifts(rec, *p, mesh, "sum")
     for a in range(3):
         assert np.abs(out[np.float32][a] - out[np.float64][a]).max() < 1e-3
+
+
+def test_fmg_does_not_feel_the_mean_of_the_right_hand_side_except_through_float32_rounding():
+    """On a periodic cubic mesh the diagonal of the multigrid operator is the same in every cell (2 (3 + beta) / cell^2,
+    src/multigrid.jl:82), so a non-zero mean of the right-hand side only makes the damped-Jacobi iterate drift by a
+    constant (omega mean(f) / diag per sweep): the fluctuating part of the potential -- all that the shifts see -- is the
+    same with and without it.  True in Float64; in Float32 the drifting constant (hundreds of times the rms of the
+    fluctuations) eats the low bits and the reference arithmetic moves away from its own Float64 result, while the same
+    arithmetic on the mean-free right-hand side does not.  tests/test_gpu_a_configs.py relies on this for config 3
+    (a survey's delta has a non-zero mean): the device is held to the Float64-equivalent answer."""
+    import baorec_oracle as O
+    n = 32
+    f32 = np.float32
+    bs, bm = np.full(3, 2798.33, f32), np.array([1400.0, -1400.0, -1400.0], f32)       # observer outside the box: radial LOS
+    rng = np.random.default_rng(4)
+    f = rng.standard_normal((n, n, n)).astype(f32)
+    f = (f - f32(f.mean(dtype=np.float64)) + f32(0.05)).astype(f32)
+    f0 = (f - f32(f.mean(dtype=np.float64))).astype(f32)
+    dm = lambda a: a - a.mean()
+    rel = lambda a, b: float(np.sqrt(np.mean((dm(a) - dm(b)) ** 2)) / dm(b).std())
+    a64 = O.fmg(f.astype(np.float64), np.zeros((n, n, n)), bs.astype(np.float64), bm.astype(np.float64), 0.344, 0.4, 5, 6, None)
+    b64 = O.fmg(f0.astype(np.float64), np.zeros((n, n, n)), bs.astype(np.float64), bm.astype(np.float64), 0.344, 0.4, 5, 6, None)
+    a32 = O.fmg(f.copy(), np.zeros((n, n, n), f32), bs, bm, f32(0.344), f32(0.4), 5, 6, None)
+    b32 = O.fmg(f0.copy(), np.zeros((n, n, n), f32), bs, bm, f32(0.344), f32(0.4), 5, 6, None)
+    assert abs(a64.mean()) > 100 * dm(a64).std()          # the drift
+    assert rel(a64, b64) < 1e-5                           # ... is a pure constant
+    assert rel(b32, a64) < 2e-5                           # Float32 on the mean-free right-hand side: fine
+    assert rel(a32, a64) > 5 * rel(b32, a64)              # Float32 with the drift: visibly worse
