@@ -30,6 +30,13 @@ static int check_catalog(int64_t n, const void* x, const void* y, const void* z,
 static int read_common(baorec_ctx* ctx, const baorec_params* p, int algorithm, const float* mesh, const float* x,
                        const float* y, const float* z, int64_t n, int field, int positions, float* ox, float* oy,
                        float* oz, cudaStream_t st, bool use_kcache = false, bool trusted = false) {
+  if (algorithm == BAOREC_MULTIGRID && ctx->opt_mg_fd_gradient && p->mas == BAOREC_MAS_CIC) {
+    // Psi = grad(phi) by finite differences: one gather over phi, no transforms (src/multigrid.jl:759, commented there)
+    BR_TRY(reset_oob(ctx, st));
+    BR_CUDA(cudaEventRecord(ctx->ev[5], st));
+    BR_TRY(gather_fd(ctx, mesh, x, y, z, n, ox, oy, oz, field, p->f, p->has_los, p->los, positions, st));
+    return check_oob(ctx, st, "read_shifts");
+  }
   float *px, *py, *pz;
   BR_TRY(need_t(ctx, BUF_RX, ctx->M, &px));
   BR_TRY(need_t(ctx, BUF_RY, ctx->M, &py));
@@ -202,6 +209,7 @@ int baorec_set_option(baorec_ctx* ctx, const char* name, int64_t value) {
   }
   else if (s == "mg_coarse") ctx->opt_mg_coarse = (int)value;
   else if (s == "mg_remove_mean") ctx->opt_mg_remove_mean = (int)value;
+  else if (s == "mg_fd_gradient") ctx->opt_mg_fd_gradient = (int)value;
   else if (s == "mg_bulk") ctx->opt_mg_bulk = (int)value;
   else if (s == "catalog_corr") ctx->opt_catalog_corr = (int)value;   // test hook (catalog.cu): -1 = measured value
   else if (s == "mg_slab_min_cells") {

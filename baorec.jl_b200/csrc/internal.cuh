@@ -210,6 +210,7 @@ struct baorec_ctx {
   // multigrid
   std::vector<baorec::MgLevel> levels;
   std::vector<baorec::MgLevel> dlevels;  // slab-decomposed hierarchy (baorec_plan_dist)
+  int opt_mg_fd_gradient = 0;  // MultigridRecon read-back: 1 = finite-difference gradient of phi in ONE gather (no transforms) instead of the reference's spectral gradient
   int opt_mg_remove_mean = 1;  // multigrid solves on f - mean(f) (cubic cells): see mg_fmg in multigrid.cu
   int opt_mg_coarse = 1;  // levels of <= 4096 cells: the bottom of the V-cycle in one thread block
   int opt_mg_bulk = 0;    // staged kernel: row bodies by TMA bulk copies; measured SLOWER than cp.async staging (554 vs 355 us), off
@@ -315,6 +316,11 @@ int gather_prebin(baorec_ctx* ctx, const float* x, const float* y, const float* 
 int gather3(baorec_ctx* ctx, const float* fx, const float* fy, const float* fz, const float* x, const float* y,
             const float* z, int64_t n, float* ox, float* oy, float* oz, int mas, int field, float f, int has_los,
             const float* los, int positions, cudaStream_t st);
+
+// grad(phi) at the particles by finite differences (the reference's commented-out read_grad_cic!, src/mas.jl:388-466)
+// + the read_shifts epilogue; single GPU
+int gather_fd(baorec_ctx* ctx, const float* phi, const float* x, const float* y, const float* z, int64_t n, float* ox,
+              float* oy, float* oz, int field, float f, int has_los, const float* los, int positions, cudaStream_t st);
 
 // kspace.cu
 int smooth(baorec_ctx* ctx, float* mesh, float R, cudaStream_t st);

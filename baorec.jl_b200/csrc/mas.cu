@@ -1230,6 +1230,87 @@ int gather3(baorec_ctx* ctx, const float* fx, const float* fy, const float* fz, 
   return BAOREC_OK;
 }
 
+// ---- finite-difference read-back (fd_gradient in mas_math.cuh) -------------------------------------------------------
+// One thread per particle; in tile order (the unified sort's records) the 32 cells a particle reads are its
+// neighbours' cells too and come from L1 / L2.
+__global__ void __launch_bounds__(256)
+gather_fd_sorted_kernel(GatherArgs a, const float4* __restrict__ rec, const unsigned* __restrict__ n_valid, int64_t n, BoxGeom g) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || i >= (int64_t)__ldg(n_valid)) return;  // the trash bin is zero-filled by unsort_kernel
+  const float4 p = rec[i];
+  float val[3];
+  if (!fd_gradient(a.f[0], g, p.x, p.y, p.z, val)) val[0] = val[1] = val[2] = 0.f;
+  shifts_epilogue<3>(a, val, p.x, p.y, p.z, 0, i);
+}
+__global__ void __launch_bounds__(256)
+gather_fd_direct_kernel(GatherArgs a, BoxGeom g, unsigned long long* __restrict__ oob) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const float px = a.x[i], py = a.y[i], pz = a.z[i];
+  float val[3];
+  if (!fd_gradient(a.f[0], g, px, py, pz, val)) {
+    val[0] = val[1] = val[2] = 0.f;
+    atomicAdd(oob, 1ULL);
+  }
+  shifts_epilogue<3>(a, val, px, py, pz, i);
+}
+
+// grad phi interpolated to the particles by finite differences + the read_shifts epilogue (single GPU)
+int gather_fd(baorec_ctx* ctx, const float* phi, const float* x, const float* y, const float* z, int64_t n, float* ox,
+              float* oy, float* oz, int field, float f, int has_los, const float* los, int positions, cudaStream_t st) {
+  if (ctx->prebin_valid) {
+    BR_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    ctx->prebin_valid = false;
+  }
+  if (n == 0) return BAOREC_OK;
+  BoxGeom g = geom_of(ctx);
+  GatherArgs a;
+  a.f[0] = phi;
+  a.f[1] = a.f[2] = nullptr;
+  a.x = x;
+  a.y = y;
+  a.z = z;
+  a.o[0] = ox;
+  a.o[1] = oy;
+  a.o[2] = oz;
+  a.n = n;
+  a.field = field;
+  a.positions = positions;
+  a.has_los = has_los;
+  for (int c = 0; c < 3; c++) a.los[c] = (has_los && los) ? los[c] : 0.f;
+  a.fgrowth = f;
+  a.sorted_out = nullptr;
+  if (use_binning(ctx, n) && ctx->opt_gather_tiles) {
+    BinResult b;
+    bool reuse = false;
+    BR_TRY(sort_cache_hit(ctx, x, y, z, n, st, &reuse));
+    if (reuse) {
+      TileGeom t;
+      t.nxc = (ctx->nx + TILE_X - 1) / TILE_X;
+      t.nyc = (ctx->ny + TILE_Y - 1) / TILE_Y;
+      t.ntiles = ctx->sortc_ntiles;
+      TileScratch sc;
+      BR_TRY(tile_scratch(ctx, t, &sc));
+      b.rec = (float4*)ctx->bufs[BUF_BINIDX].p;
+      b.n_valid = sc.starts + t.ntiles;
+      b.inv = (unsigned*)ctx->bufs[BUF_BININV].p;
+      BR_LAUNCH(ctx, add_oob_kernel, 1, 1, 0, st, sc.cnt + t.ntiles, ctx->d_oob);
+      ctx->n_sort_reuse++;
+    } else {
+      ctx->sortc_valid = false;
+      BR_TRY(bin_tiles(ctx, x, y, z, n, BAOREC_MAS_CIC, st, &b));
+    }
+    float4* so;
+    BR_TRY(need_t(ctx, BUF_BINOUT, (size_t)n, &so));
+    a.sorted_out = so;
+    BR_LAUNCH(ctx, gather_fd_sorted_kernel, cdiv((size_t)n, 256), 256, 0, st, a, b.rec, b.n_valid, n, g);
+    BR_LAUNCH(ctx, unsort_kernel, cdiv((size_t)n, 256), 256, 0, st, a, so, b.inv, n, b.n_valid);
+    return BAOREC_OK;
+  }
+  BR_LAUNCH(ctx, gather_fd_direct_kernel, cdiv((size_t)n, 256), 256, 0, st, a, g, ctx->d_oob);
+  return BAOREC_OK;
+}
+
 // ---- parity probes -------------------------------------------------------------------------------------
 __global__ void cic_cells_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z,
                                  int64_t n, BoxGeom g, int wrap, int32_t* i0, int32_t* i1, float* w0, float* w1) {

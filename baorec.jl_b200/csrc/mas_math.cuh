@@ -379,6 +379,66 @@ struct GatherArgs {
   float4* sorted_out;  // if non-null: write (s0,s1,s2,0) at the record's sorted position instead of o[c][idx]
 };
 
+// read_grad_cic! -- the finite-difference read-back the reference sketches and leaves commented out
+// (src/mas.jl:388-466; the call site src/multigrid.jl:759, 785): grad phi at the particle = CIC interpolation of the
+// central differences (phi[i+1] - phi[i-1]) at the eight corners, divided by 2 cell.  One gather over phi replaces the
+// 1 R2C + 3 C2R + 3 gathers of the spectral read-back.  Restated with the INTENDED geometry: the sketch computes the
+// particle's cell with the doubled cell size it needs for the difference quotient (dist = (p - min) / (2 L / n)), which
+// would halve every coordinate; here the cell is read_cic!'s (src/mas.jl:221-224: d = (p - min) / T(L / n)) and only the
+// final division uses 2 L / n.  Same accumulation order as the sketch: corners 000, 100, 010, 001, 110, 101, 011, 111
+// (letters = x, y, z upper), weight = (wx wy) wz left to right, sum left to right, one division at the end.
+__device__ __forceinline__ bool fd_axis(float p, float mn, float cell, int n, int idx[4], float& wd, float& wu) {
+  float d = __fdiv_rn(__fsub_rn(p, mn), cell);
+  if (!(d >= 0.0f && d < (float)(2 * n))) return false;
+  float f = floorf(d);
+  wu = __fsub_rn(d, f);
+  wd = __fsub_rn(1.0f, wu);
+  int i = (int)f + 1;  // 1-based like the reference
+  if (i > n) i -= n;
+  int u = i + 1;
+  if (u > n) u -= n;
+  int pp = u + 1;
+  if (pp > n) pp -= n;
+  int m = i - 1;
+  if (m < 1) m += n;
+  idx[0] = m - 1;   // i - 1
+  idx[1] = i - 1;   // i
+  idx[2] = u - 1;   // i + 1
+  idx[3] = pp - 1;  // i + 2
+  return true;
+}
+
+__device__ __forceinline__ bool fd_gradient(const float* __restrict__ phi, const BoxGeom& g, float px, float py, float pz,
+                                            float (&out)[3]) {
+  int X[4], Y[4], Z[4];
+  float wx, dx, wy, dy, wz, dz;  // w = lower weight (1 - u), d = upper weight (u), the sketch's names
+  bool ok = fd_axis(px, g.mn[0], g.cell[0], g.n[0], X, wx, dx);
+  ok = fd_axis(py, g.mn[1], g.cell[1], g.n[1], Y, wy, dy) && ok;
+  ok = fd_axis(pz, g.mn[2], g.cell[2], g.n[2], Z, wz, dz) && ok;
+  if (!ok) return false;
+  const size_t nx = g.n[0], ny = g.n[1];
+#define PHI(ix, iy, iz) __ldg(phi + ((size_t)Z[iz] * ny + Y[iy]) * nx + X[ix])
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    // corner order of the sketch: 000, 100, 010, 001, 110, 101, 011, 111
+    const int cx = (k == 1 || k == 4 || k == 5 || k == 7), cy = (k == 2 || k == 4 || k == 6 || k == 7),
+              cz = (k == 3 || k == 5 || k == 6 || k == 7);
+    const float wt = __fmul_rn(__fmul_rn(cx ? dx : wx, cy ? dy : wy), cz ? dz : wz);
+    const float ax = __fmul_rn(__fsub_rn(PHI(2 + cx, 1 + cy, 1 + cz), PHI(cx, 1 + cy, 1 + cz)), wt);
+    const float ay = __fmul_rn(__fsub_rn(PHI(1 + cx, 2 + cy, 1 + cz), PHI(1 + cx, cy, 1 + cz)), wt);
+    const float az = __fmul_rn(__fsub_rn(PHI(1 + cx, 1 + cy, 2 + cz), PHI(1 + cx, 1 + cy, cz)), wt);
+    gx = k ? __fadd_rn(gx, ax) : ax;
+    gy = k ? __fadd_rn(gy, ay) : ay;
+    gz = k ? __fadd_rn(gz, az) : az;
+  }
+#undef PHI
+  out[0] = __fdiv_rn(gx, __fmul_rn(2.0f, g.cell[0]));
+  out[1] = __fdiv_rn(gy, __fmul_rn(2.0f, g.cell[1]));
+  out[2] = __fdiv_rn(gz, __fmul_rn(2.0f, g.cell[2]));
+  return true;
+}
+
 // read_shifts epilogue (src/recon.jl:277-304 / kernels :308-330) and optionally pos - shift (:376-378)
 template <int NF>
 __device__ __forceinline__ void shifts_epilogue(const GatherArgs& a, const float (&val)[NF], float px, float py,

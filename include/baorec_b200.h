@@ -112,6 +112,19 @@ int baorec_set_box(baorec_ctx* ctx, const float box_size[3], const float box_min
  *       64-bit integer reductions and rounds to Float32 once: meshes, `ran > threshold` masks and everything after
  *       them are bit-reproducible from run to run and independent of the particle order (float reductions are not);
  *       costs an 8-byte-per-cell scratch mesh and one conversion pass.
+ *   "mg_remove_mean" (default 1): MultigridRecon solves on delta - mean(delta) when the cells are cubic.  A survey's
+ *       delta has a non-zero mean; damped Jacobi on a periodic mesh then drifts by a constant that exact arithmetic
+ *       does not feel (the operator's diagonal is uniform, src/multigrid.jl:82) but Float32 does: the reference's
+ *       Float32 arithmetic ends 1e-2 from the reference's own Float64 run at 512^3.  1 = Float64-equivalent shifts
+ *       (the potential comes without the drift constant); 0 = the reference's Float32 arithmetic, drift included.
+ *   "mg_fd_gradient" (default 0): 1 = read_shifts / reconstructed_positions of a MultigridRecon (device API, CIC) take
+ *       Psi = grad(phi) by finite differences in ONE gather over phi -- the read_grad_cic! the reference sketches and
+ *       leaves commented out (src/mas.jl:388-466, src/multigrid.jl:759) -- instead of 1 R2C + 3 C2R + 3 gathers.
+ *       Differs from the reference's spectral gradient by the finite-difference error, hence an option.
+ *   "own_fft" (default -1): -1 = the column FFT kernels of csrc/fft.cu replace cuFFT's 3-D plans where they were
+ *       measured faster (ny, nz powers of two >= 512); 0 = never; 1 = wherever supported (>= 256).
+ *   "dist_exchange" (default 1), "push_sm" (default -1), "comm_split" (default 1): exchange of the slab transforms, see
+ *       baorec_dist_ipc_export below.
  *   "mg_slab_min_cells" (default 4194304): slab-decomposed multigrid levels with fewer cells are
  *       replicated on every rank instead of exchanging halos. */
 int baorec_set_option(baorec_ctx* ctx, const char* name, int64_t value);

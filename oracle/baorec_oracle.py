@@ -533,7 +533,49 @@ def compute_displacements_multigrid(phi, x, y, z, recon, formula="cpu"):
     return out
 
 
+def read_grad_cic(fld, x, y, z, box_size, box_min):
+    """read_grad_cic! -- the finite-difference read-back the reference sketches and leaves commented out
+    (src/mas.jl:388-466; call sites src/multigrid.jl:759, 785): CIC interpolation of the central differences
+    fld[i+1] - fld[i-1] at the eight corners, divided by 2 cell.  Restated with the INTENDED geometry: the sketch
+    locates the particle with the doubled cell size it needs for the difference quotient (dist = (p - min) / (2 L / n)),
+    which would halve every coordinate; here the particle's cell is read_cic!'s (src/mas.jl:221-224) and only the final
+    division uses 2 L / n.  Accumulation order of the sketch: corners 000, 100, 010, 001, 110, 101, 011, 111
+    (x, y, z upper), weight (wx wy) wz, one division at the end.  Always periodic (wrap = true, like every caller)."""
+    T = _T(fld)
+    nz, ny, nx = fld.shape
+    L, mn = _vec3(box_size, T), _vec3(box_min, T)
+    idx, lo, up, cells = [], [], [], []
+    for a, (p, n) in enumerate(zip((x, y, z), (nx, ny, nz))):
+        cell = T(L[a] / T(n))
+        d = ((np.asarray(p, dtype=T) - mn[a]).astype(T) / cell).astype(T)
+        if not ((d >= 0) & (d < 2 * n)).all():
+            raise OutOfBoxError("particle outside the mesh in read_grad_cic")
+        f = np.floor(d)
+        u = (d - f).astype(T)
+        i = f.astype(np.int64) + 1
+        i = np.where(i > n, i - n, i)
+        iu = np.where(i + 1 > n, i + 1 - n, i + 1)
+        ipp = np.where(iu + 1 > n, iu + 1 - n, iu + 1)
+        im = np.where(i - 1 < 1, i - 1 + n, i - 1)
+        idx.append([im - 1, i - 1, iu - 1, ipp - 1])
+        lo.append((T(1) - u).astype(T))
+        up.append(u)
+        cells.append(cell)
+    X, Y, Z = idx
+    phi = lambda ix, iy, iz: fld[Z[iz], Y[iy], X[ix]]
+    g = [None, None, None]
+    for k, (cx, cy, cz) in enumerate(((0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (1, 0, 1), (0, 1, 1), (1, 1, 1))):
+        wt = (((up[0] if cx else lo[0]) * (up[1] if cy else lo[1])).astype(T) * (up[2] if cz else lo[2])).astype(T)
+        terms = (((phi(2 + cx, 1 + cy, 1 + cz) - phi(cx, 1 + cy, 1 + cz)).astype(T) * wt).astype(T),
+                 ((phi(1 + cx, 2 + cy, 1 + cz) - phi(1 + cx, cy, 1 + cz)).astype(T) * wt).astype(T),
+                 ((phi(1 + cx, 1 + cy, 2 + cz) - phi(1 + cx, 1 + cy, cz)).astype(T) * wt).astype(T))
+        g = [t if k == 0 else (acc + t).astype(T) for acc, t in zip(g, terms)]
+    return [(g[a] / (T(2) * cells[a]).astype(T)).astype(T) for a in range(3)]
+
+
 def compute_displacements(mesh, x, y, z, recon, formula="cpu"):
+    if isinstance(recon, MultigridRecon) and getattr(recon, "fd_gradient", False):
+        return read_grad_cic(mesh, x, y, z, recon.box_size, recon.box_min)
     if isinstance(recon, MultigridRecon):
         return compute_displacements_multigrid(mesh, x, y, z, recon, formula)
     return compute_displacements_iterative(mesh, x, y, z, recon, formula)

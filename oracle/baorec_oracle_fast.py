@@ -211,6 +211,8 @@ def load(threads=None):
         return [_f32c(O.irfft(kspace(dk, kv, op, a), mesh.shape)) for a in range(3)]
 
     def compute_displacements(mesh, x, y, z, recon, formula="cpu"):
+        if isinstance(recon, O.MultigridRecon) and getattr(recon, "fd_gradient", False):
+            return O.read_grad_cic(mesh, x, y, z, recon.box_size, recon.box_min)
         return [O._read(recon, m, x, y, z, formula) for m in O.displacement_meshes(mesh, recon)]
 
     def read_shifts(recon, x, y, z, mesh, field="disp", formula="cpu"):

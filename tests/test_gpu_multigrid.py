@@ -182,3 +182,42 @@ def test_kernel_variants_agree(B, O, shape, los, lo):
     for o in outs[1:]:
         assert rel_rms(o, outs[0]) < 1e-4
         assert rel_rms(o - o.mean(), outs[0] - outs[0].mean()) < (2e-5 if nx == ny == nz else 1e-4)   # anisotropic cells amplify rounding
+
+
+@pytest.mark.parametrize("N,n", [(30_000, 48), (400_000, 128)])          # catalog-order kernel; tile-sorted kernel
+@pytest.mark.parametrize("los", [(0.0, 0.0, 1.0), None])
+def test_finite_difference_read_back(B, O, N, n, los):
+    """Option "mg_fd_gradient": Psi = grad(phi) by finite differences in ONE gather (the reference's commented-out
+    read_grad_cic!, src/mas.jl:388-466; call site src/multigrid.jl:759) instead of 1 R2C + 3 C2R + 3 gathers.
+    Same phi on both sides: displacements bit for bit, :sum / positions within rounding; and no transform runs."""
+    L, lo = 1000.0, (0.0 if los is not None else 700.0)
+    pos, w = clustered_box(N, L, seed=23, lo=lo)
+    kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=np.full(3, L, np.float32), box_min=np.full(3, lo, np.float32), los=los)
+    rng = np.random.default_rng(3)
+    phi = (10 * rng.standard_normal((n, n, n))).astype(np.float32)
+    orec = O.MultigridRecon(**kw)
+    orec.fd_gradient = True
+    rec = B.MultigridRecon(**kw)
+    d = [dev(p) for p in pos]
+    gphi = dev(phi)
+    ctx = B.Context.get(0)
+    try:
+        ctx.set_option("mg_fd_gradient", 1)
+        B.setup_fft(rec, gphi)
+        _, f0 = ctx.launch_counts()
+        got = {f: B.read_shifts(rec, *d, gphi, field=f) for f in ("disp", "rsd", "sum")}
+        newpos = B.reconstructed_positions(rec, *d, gphi, field="sum")
+        _, f1 = ctx.launch_counts()
+    finally:
+        ctx.set_option("mg_fd_gradient", 0)
+    assert f1 == f0                                                       # not a single transform
+    for f in ("disp", "rsd", "sum"):
+        ref = O.read_shifts(orec, *pos, phi, f)
+        for a in range(3):
+            g = got[f][a].cpu().numpy()
+            if f == "disp":
+                assert np.array_equal(g.view(np.uint32), ref[a].view(np.uint32))
+            else:
+                assert maxabs(g, ref[a]) <= 4 * np.spacing(np.float32(np.abs(ref[a]).max()))
+    for a in range(3):
+        assert np.array_equal(newpos[a].cpu().numpy(), (d[a] - got["sum"][a]).cpu().numpy())

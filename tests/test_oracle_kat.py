@@ -337,3 +337,42 @@ def test_fmg_does_not_feel_the_mean_of_the_right_hand_side_except_through_float3
     assert rel(a64, b64) < 1e-5                           # ... is a pure constant
     assert rel(b32, a64) < 2e-5                           # Float32 on the mean-free right-hand side: fine
     assert rel(a32, a64) > 5 * rel(b32, a64)              # Float32 with the drift: visibly worse
+
+
+def test_read_grad_cic_known_answers():
+    """The finite-difference read-back (oracle restatement of the reference's commented-out read_grad_cic!,
+    src/mas.jl:388-466, with the intended geometry).  A particle ON a mesh point gets exactly the central difference
+    there; for a plane wave the result is the spectral gradient times sin(kh)/(kh) (the central difference) up to the
+    CIC interpolation; the Float64 and Float32 evaluations agree to rounding."""
+    import baorec_oracle as O
+    n, L = 32, 640.0
+    h = L / n
+    bs, bm = np.full(3, L), np.array([100.0, -50.0, 0.0])
+    rng = np.random.default_rng(1)
+    phi = rng.standard_normal((n, n, n))
+    i, j, k = 5, 31, 0                                       # wraps in y (upper neighbour) and z (lower neighbour)
+    g = O.read_grad_cic(phi, np.array([bm[0] + i * h]), np.array([bm[1] + j * h]), np.array([bm[2] + k * h]), bs, bm)
+    assert np.isclose(g[0][0], (phi[k, j, i + 1] - phi[k, j, i - 1]) / (2 * h), rtol=1e-12)
+    assert np.isclose(g[1][0], (phi[k, 0, i] - phi[k, j - 1, i]) / (2 * h), rtol=1e-12)
+    assert np.isclose(g[2][0], (phi[1, j, i] - phi[n - 1, j, i]) / (2 * h), rtol=1e-12)
+    m = 2
+    kx = 2 * np.pi * m / L
+    xs = bm[0] + h * np.arange(n)
+    wave = np.broadcast_to(np.sin(kx * (xs - bm[0]))[None, None, :], (n, n, n)).copy()
+    N = 2000
+    x, y, z = (bm[a] + L * rng.random(N) for a in range(3))
+    g = O.read_grad_cic(wave, x, y, z, bs, bm)
+    want = kx * np.cos(kx * (x - bm[0])) * np.sin(kx * h) / (kx * h)
+    assert np.abs(g[0] - want).max() < 0.02 * kx and np.abs(g[1]).max() < 1e-12 and np.abs(g[2]).max() < 1e-12
+    g32 = O.read_grad_cic(phi.astype(np.float32), x.astype(np.float32), y.astype(np.float32), z.astype(np.float32),
+                          bs.astype(np.float32), bm.astype(np.float32))
+    g64 = O.read_grad_cic(phi.astype(np.float32).astype(np.float64), x.astype(np.float32).astype(np.float64),
+                          y.astype(np.float32).astype(np.float64), z.astype(np.float32).astype(np.float64), bs, bm)
+    # (the Float32 cell index can differ from Float64's for a particle within rounding of a mesh point: compare the bulk)
+    err = np.abs(g32[0] - g64[0])
+    assert np.median(err) < 1e-6 and np.quantile(err, 0.99) < 1e-4
+    # and the multigrid read-back through it
+    rec = O.MultigridRecon(bias=2.0, f=0.8, smoothing_radius=10.0, box_size=bs.astype(np.float32), box_min=bm.astype(np.float32), los=(0.0, 0.0, 1.0))
+    rec.fd_gradient = True
+    s = O.read_shifts(rec, x.astype(np.float32), y.astype(np.float32), z.astype(np.float32), wave.astype(np.float32), "disp")
+    assert np.allclose(s[0], want, atol=0.02 * kx)
