@@ -203,6 +203,7 @@ int baorec_set_option(baorec_ctx* ctx, const char* name, int64_t value) {
   else if (s == "a2a_chunks") ctx->opt_a2a_chunks = (int)value;
   else if (s == "comm_split") ctx->opt_comm_split = (int)value;
   else if (s == "push_sm") ctx->opt_push_sm = (int)value;
+  else if (s == "peer_halo") ctx->opt_peer_halo = (int)value;
   else if (s == "dist_exchange") {
     ctx->opt_dist_exchange = value != 0;
     baorec::dist_refresh_mode(ctx);

@@ -108,6 +108,11 @@ __global__ void slab_owner_kernel(const float* __restrict__ z, int64_t n, float 
 
 static ncclComm_t comm_of(baorec_ctx* ctx) { return (ncclComm_t)ctx->comm; }
 
+// defined with the peer-copy machinery below
+static bool peer_halos(const baorec_ctx* ctx);
+static int halo_exchange_peer(baorec_ctx* ctx, int nx, const float* const send[2], const int to[2], float* const recv[2],
+                              const int from[2], const size_t count[2], cudaStream_t st);
+
 // blocks of `blk` complex values per peer: S[peer] -> R[peer]
 static int all_to_all(baorec_ctx* ctx, const float2* S, float2* R, size_t blk, cudaStream_t st) {
   const int P = ctx->nranks;
@@ -132,6 +137,13 @@ static int ring_exchange(baorec_ctx* ctx, const float* send, int to, float* recv
   if (ctx->nranks == 1) {
     BR_CUDA(cudaMemcpyAsync(recv, send, count * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return BAOREC_OK;
+  }
+  if (peer_halos(ctx) && count % 4 == 0 && count <= ctx->inbox_slot_floats) {
+    const float* sp[2] = {send, nullptr};
+    float* rp[2] = {recv, nullptr};
+    const int t2[2] = {to, to}, f2[2] = {from, from};
+    const size_t c2[2] = {count, 0};
+    return halo_exchange_peer(ctx, 1, sp, t2, rp, f2, c2, st);
   }
   int pi = prof_begin(ctx, "nccl_halo", st);
   BR_NCCL(ncclGroupStart());
@@ -158,6 +170,13 @@ int mg_halo_exchange(baorec_ctx* ctx, float* buf, size_t plane, int nzl, cudaStr
     return BAOREC_OK;
   }
   const int next = (ctx->rank + 1) % P, prev = (ctx->rank + P - 1) % P;
+  if (peer_halos(ctx) && plane % 4 == 0 && plane <= ctx->inbox_slot_floats) {
+    const float* sp[2] = {last, first};      // last plane -> next rank's plane 0; first plane -> previous rank's plane nzl+1
+    float* rp[2] = {lo, hi};
+    const int t2[2] = {next, prev}, f2[2] = {prev, next};
+    const size_t c2[2] = {plane, plane};
+    return halo_exchange_peer(ctx, 2, sp, t2, rp, f2, c2, st);
+  }
   int pi = prof_begin(ctx, "nccl_mg_halo", st);
   BR_NCCL(ncclGroupStart());
   BR_NCCL(ncclSend(last, plane, ncclFloat, next, comm_of(ctx), st));
@@ -196,7 +215,8 @@ __global__ void set_scalar_kernel(double* p, double v) { *p = v; }
 // K = k-layout buffer of the forward transform; A0 / A1 = the two plane-layout buffers of the inverse transforms
 // (two, so that the exchange of one displacement field overlaps the transforms of the other).
 enum PeerFlagId { F_ARR_K = 0, F_FREE_K, F_ARR_A0, F_FREE_A0, F_ARR_A1, F_FREE_A1,
-                  F_ARR_S0, F_FREE_S0, F_ARR_B0, F_FREE_B0, F_ARR_S1, F_FREE_S1, F_ARR_B1, F_FREE_B1, F_COUNT = 16 };  // S: sharded catalog, B: results coming back; 0 data, 1 randoms
+                  F_ARR_S0, F_FREE_S0, F_ARR_B0, F_FREE_B0, F_ARR_S1, F_FREE_S1, F_ARR_B1, F_FREE_B1,
+                  F_ARR_H0, F_ARR_H1, F_FREE_H, F_COUNT = 20 };  // H: halo / ghost planes through the peers' inboxes  // S: sharded catalog, B: results coming back; 0 data, 1 randoms
 struct PeerFlags {
   unsigned w[F_COUNT][16];
   unsigned err, pad[15];
@@ -278,7 +298,131 @@ peer_push_kernel(const __grid_constant__ PeerTab dst, const float2* __restrict__
   }
 }
 
+// ---- halo / ghost planes through peer memory ------------------------------------------------------------------------
+// A ring exchange (every rank sends `count` floats to one neighbour and receives as many from another) as TWO small
+// kernels instead of a grouped ncclSend / ncclRecv (~100 us each at 8 ranks for a 4 MB plane; a multigrid solve makes
+// 700 of them): the send kernel stores the plane(s) straight into slot (call number mod HALO_SLOTS) of the neighbour's
+// inbox and its last block raises the arrival flag; the receive kernel spins on the flag, copies inbox -> destination
+// and its last block tells both neighbours that the slot is free again.  Up to two transfers per call (the multigrid
+// halo exchange sends to both neighbours).
+constexpr int HALO_SLOTS = 8;
+struct HaloXfer {
+  const float* src;   // send: local source            receive: my inbox slot
+  float* dst;         // send: the neighbour's inbox   receive: local destination
+  unsigned* flag;     // send: the neighbour's ARR_H word for me
+  const unsigned* wait;  // send: my FREE_H word of that neighbour   receive: my ARR_H word of the sender
+  size_t count;       // floats (multiple of 4)
+};
+struct HaloArgs {
+  HaloXfer x[2];
+  int nx;             // transfers in this call (1 or 2)
+  unsigned seq;       // call number
+  unsigned* done;     // block counter (zeroed by the last block)
+  unsigned* free_flag[2];  // receive: the FREE_H words of my two neighbours that belong to me
+  unsigned* err;
+};
+
+__device__ __forceinline__ bool spin_until(const unsigned* p, unsigned value, unsigned* err) {
+  const unsigned long long t0 = global_ns();
+  while ((int)(ld_relaxed_sys(p) - value) < 0) {
+    __nanosleep(100);
+    if (global_ns() - t0 > 20000000000ull) {
+      atomicExch(err, 1u);
+      return false;
+    }
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(256) halo_send_kernel(const __grid_constant__ HaloArgs a) {
+  if (threadIdx.x == 0) {  // the slot must have been consumed HALO_SLOTS calls ago
+    for (int k = 0; k < a.nx; k++)
+      if (a.seq > HALO_SLOTS) spin_until(a.x[k].wait, a.seq - HALO_SLOTS, a.err);
+  }
+  __syncthreads();
+  for (int k = 0; k < a.nx; k++) {
+    const float4* s = reinterpret_cast<const float4*>(a.x[k].src);
+    float4* d = reinterpret_cast<float4*>(a.x[k].dst);
+    const size_t n4 = a.x[k].count >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
+  }
+  __threadfence_system();   // my stores are performed in the neighbour's memory before the flag can be
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(a.done, 1u) == gridDim.x - 1) {
+      *a.done = 0u;
+      __threadfence_system();
+      for (int k = 0; k < a.nx; k++) st_relaxed_sys(a.x[k].flag, a.seq);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) halo_recv_kernel(const __grid_constant__ HaloArgs a) {
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < a.nx; k++) spin_until(a.x[k].wait, a.seq, a.err);
+    __threadfence_system();
+  }
+  __syncthreads();
+  for (int k = 0; k < a.nx; k++) {
+    const float4* s = reinterpret_cast<const float4*>(a.x[k].src);
+    float4* d = reinterpret_cast<float4*>(a.x[k].dst);
+    const size_t n4 = a.x[k].count >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+      d[i] = __ldcg(s + i);   // the inbox was written by a peer: read it from L2, not from a stale L1 line
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(a.done, 1u) == gridDim.x - 1) {
+      *a.done = 0u;
+      st_relaxed_sys(a.free_flag[0], a.seq);
+      st_relaxed_sys(a.free_flag[1], a.seq);
+    }
+  }
+}
+
 static PeerFlags* own_flags(const baorec_ctx* ctx) { return (PeerFlags*)ctx->d_flags; }
+
+static bool peer_halos(const baorec_ctx* ctx) { return ctx->p2p && ctx->nranks > 1 && ctx->opt_peer_halo && ctx->peer_inbox[ctx->rank]; }
+
+// up to two transfers: send[k] -> rank to[k], recv[k] <- rank from[k]; counts in floats
+static int halo_exchange_peer(baorec_ctx* ctx, int nx, const float* const send[2], const int to[2], float* const recv[2],
+                              const int from[2], const size_t count[2], cudaStream_t st) {
+  const int P = ctx->nranks, me = ctx->rank, next = (me + 1) % P, prev = (me + P - 1) % P;
+  const unsigned seq = ++ctx->seq_halo;
+  const size_t slot_floats = ctx->inbox_slot_floats;
+  const size_t slot = (size_t)(seq % HALO_SLOTS) * 2;   // two half-slots per call
+  PeerFlags* mine = own_flags(ctx);
+  HaloArgs sa, ra;
+  sa.nx = ra.nx = nx;
+  sa.seq = ra.seq = seq;
+  sa.done = ctx->d_halo_done;
+  ra.done = ctx->d_halo_done + 1;
+  sa.err = ra.err = &mine->err;
+  sa.free_flag[0] = sa.free_flag[1] = nullptr;
+  ra.free_flag[0] = ((PeerFlags*)ctx->peer_flags[prev])->w[F_FREE_H] + me;
+  ra.free_flag[1] = ((PeerFlags*)ctx->peer_flags[next])->w[F_FREE_H] + me;
+  for (int k = 0; k < nx; k++) {
+    BR_REQUIRE(count[k] % 4 == 0 && count[k] <= slot_floats, "halo plane does not fit an inbox slot");
+    // the two transfers of a call go to different half-slots so that prev == next (two ranks) does not collide
+    sa.x[k].src = send[k];
+    sa.x[k].dst = (float*)ctx->peer_inbox[to[k]] + (slot + k) * slot_floats;
+    sa.x[k].flag = ((PeerFlags*)ctx->peer_flags[to[k]])->w[k ? F_ARR_H1 : F_ARR_H0] + me;
+    sa.x[k].wait = mine->w[F_FREE_H] + to[k];
+    sa.x[k].count = count[k];
+    ra.x[k].src = (const float*)ctx->peer_inbox[me] + (slot + k) * slot_floats;
+    ra.x[k].dst = recv[k];
+    ra.x[k].flag = nullptr;
+    ra.x[k].wait = mine->w[k ? F_ARR_H1 : F_ARR_H0] + from[k];
+    ra.x[k].count = count[k];
+  }
+  const size_t work = (count[0] + (nx > 1 ? count[1] : 0)) / 4;
+  unsigned grid = (unsigned)((work + 2047) / 2048);
+  if (grid > 64) grid = 64;
+  if (grid < 1) grid = 1;
+  BR_LAUNCH(ctx, halo_send_kernel, grid, 256, 0, st, sa);
+  BR_LAUNCH(ctx, halo_recv_kernel, grid, 256, 0, st, ra);
+  return BAOREC_OK;
+}
 
 static PeerTab recv_tab(const baorec_ctx* ctx, int which) {
   PeerTab t;
@@ -869,6 +1013,8 @@ static void close_ipc(baorec_ctx* ctx) {
     }
     if (ctx->peer_flags[r] && ctx->peer_flags[r] != ctx->d_flags) cudaIpcCloseMemHandle(ctx->peer_flags[r]);
     ctx->peer_flags[r] = nullptr;
+    if (ctx->peer_inbox[r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->peer_inbox[r]);
+    ctx->peer_inbox[r] = nullptr;
   }
   ctx->p2p = false;
   cudaGetLastError();  // a peer that already exited makes the close fail; nothing to do about it
@@ -881,6 +1027,8 @@ int baorec_comm_destroy_internal(baorec_ctx* ctx) {
     shard_close_peers(ctx, 1);
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     ctx->d_flags = nullptr;
+    if (ctx->d_halo_done) cudaFree(ctx->d_halo_done);
+    ctx->d_halo_done = nullptr;
   }
   if (ctx && ctx->comm) {
     ncclCommDestroy((ncclComm_t)ctx->comm);
@@ -965,10 +1113,26 @@ int baorec_plan_dist(baorec_ctx* ctx, int nx, int ny, int nz, const float box_si
       BR_CUDA(cudaMalloc(&ctx->d_flags, sizeof(PeerFlags)));
       BR_CUDA(cudaMemset(ctx->d_flags, 0, sizeof(PeerFlags)));
     }
+    if (!ctx->d_halo_done) {
+      BR_CUDA(cudaMalloc(&ctx->d_halo_done, 2 * sizeof(unsigned)));
+      BR_CUDA(cudaMemset(ctx->d_halo_done, 0, 2 * sizeof(unsigned)));
+    }
+    {
+      // halo / ghost planes travel through an inbox the ring neighbours write into: HALO_SLOTS calls in flight, two
+      // transfers of up to two planes each per call
+      const size_t slot = 2 * (size_t)ny * nx;
+      void* old = ctx->bufs[BUF_HALO_INBOX].p;
+      float* inbox;
+      BR_TRY(need_t(ctx, BUF_HALO_INBOX, (size_t)HALO_SLOTS * 2 * slot, &inbox));
+      if (old != (void*)inbox) close_ipc(ctx);
+      ctx->inbox_slot_floats = slot;
+      ctx->own_inbox = inbox;
+    }
     if (P == 1) {
       // a single rank is its own (only) peer: the peer-copy path runs with local copies and local flags
       for (int k = 0; k < 3; k++) ctx->peer_recv[k][0] = ctx->own_recv[k];
       ctx->peer_flags[0] = ctx->d_flags;
+      ctx->peer_inbox[0] = ctx->own_inbox;
     }
     dist_refresh_mode(ctx);
   }
@@ -990,9 +1154,9 @@ int baorec_dist_ipc_close(baorec_ctx* ctx) {
   return BAOREC_OK;
 }
 
-int baorec_dist_ipc_export(baorec_ctx* ctx, void* out256) {
+int baorec_dist_ipc_export(baorec_ctx* ctx, void* out320) {
   BR_NEED_DIST(ctx);
-  BR_REQUIRE(out256 != nullptr, "out256 is NULL");
+  BR_REQUIRE(out320 != nullptr, "out320 is NULL");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
   // A new generation of the exchange starts here: every rank calls this before the handles are gathered (a
   // synchronisation point of the caller), so no peer can have written a flag of the new generation yet.
@@ -1001,10 +1165,12 @@ int baorec_dist_ipc_export(baorec_ctx* ctx, void* out256) {
   BR_CUDA(cudaDeviceSynchronize());
   ctx->seq_k = ctx->seq_a[0] = ctx->seq_a[1] = 0;
   for (int k = 0; k < 2; k++) ctx->seq_shard[k][0] = ctx->seq_shard[k][1] = 0;
-  cudaIpcMemHandle_t h[4];
+  ctx->seq_halo = 0;
+  cudaIpcMemHandle_t h[5];
   for (int k = 0; k < 3; k++) BR_CUDA(cudaIpcGetMemHandle(&h[k], ctx->own_recv[k]));
   BR_CUDA(cudaIpcGetMemHandle(&h[3], ctx->d_flags));
-  memcpy(out256, h, sizeof(h));
+  BR_CUDA(cudaIpcGetMemHandle(&h[4], ctx->own_inbox));
+  memcpy(out320, h, sizeof(h));
   return BAOREC_OK;
 }
 
@@ -1017,12 +1183,14 @@ int baorec_dist_ipc_open(baorec_ctx* ctx, const void* all_handles, int nranks) {
     if (r == ctx->rank) {
       for (int k = 0; k < 3; k++) ctx->peer_recv[k][r] = ctx->own_recv[k];
       ctx->peer_flags[r] = ctx->d_flags;
+      ctx->peer_inbox[r] = ctx->own_inbox;
       continue;
     }
-    void* p[4] = {nullptr, nullptr, nullptr, nullptr};
-    for (int k = 0; k < 4; k++) BR_CUDA(cudaIpcOpenMemHandle(&p[k], h[4 * r + k], cudaIpcMemLazyEnablePeerAccess));
+    void* p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < 5; k++) BR_CUDA(cudaIpcOpenMemHandle(&p[k], h[5 * r + k], cudaIpcMemLazyEnablePeerAccess));
     for (int k = 0; k < 3; k++) ctx->peer_recv[k][r] = (float2*)p[k];
     ctx->peer_flags[r] = p[3];
+    ctx->peer_inbox[r] = p[4];
   }
   dist_refresh_mode(ctx);
   return BAOREC_OK;

@@ -83,6 +83,7 @@ enum BufId {
   BUF_A2A_RECV,
   BUF_A2A_RECV2,
   BUF_A2A_RECV3,
+  BUF_HALO_INBOX,  // halo / ghost planes the ring neighbours store into (mapped by all peers)
   BUF_HALO,
   BUF_MGD,      // multigrid level hierarchy of the slab-decomposed solver
   BUF_DET,      // 64-bit fixed-point accumulator of the deterministic scatter
@@ -232,7 +233,14 @@ struct baorec_ctx {
   float2* own_recv[3] = {nullptr, nullptr, nullptr};
   void* peer_flags[16] = {};
   void* d_flags = nullptr;
-  unsigned seq_k = 0, seq_a[2] = {0, 0};  // forward / inverse transforms issued since the flags were reset (same on every rank)
+  unsigned seq_k = 0, seq_a[2] = {0, 0};
+  // halo / ghost planes through peer memory (halo_send_kernel / halo_recv_kernel in dist.cu)
+  void* peer_inbox[16] = {};
+  float* own_inbox = nullptr;
+  size_t inbox_slot_floats = 0;
+  unsigned seq_halo = 0;
+  unsigned* d_halo_done = nullptr;
+  int opt_peer_halo = 1;  // 0 = grouped ncclSend / ncclRecv for the ring exchanges  // forward / inverse transforms issued since the flags were reset (same on every rank)
   // particle sharding by slab (baorec_shard_catalog_f32): routing tables of the last call per slot (0 data, 1 randoms)
   struct ShardState {
     bool valid = false;

@@ -163,14 +163,14 @@ def init_comm(ctx: Context = None):
 
 
 def _map_peers(ctx: Context):
-    """Maps every rank's three receive buffers and its flag block into this process (CUDA IPC) -- what the peer-copy
+    """Maps every rank's three receive buffers, its halo inbox and its flag block into this process (CUDA IPC) -- what the peer-copy
     exchange of the slab transforms (csrc/dist.cu, option "dist_exchange" = 1, the default) writes into: one strided
     copy-engine copy per peer and chunk over NVLink plus a flag store, no pack / transpose kernels, no NCCL.
     (Round 1's version of this exchange ended every transpose with a barrier, which exposed the rank skew that NCCL's
     grouped send/recv hides -- 22.0 vs 20.4 ms at 8 GPUs; per-peer sequence flags removed the barrier.)"""
     import torch.distributed as dist
     world = dist.get_world_size()
-    mine = (C.c_ubyte * 256)()
+    mine = (C.c_ubyte * 320)()
     L.check(ctx.lib.baorec_dist_ipc_export(ctx.handle, mine))      # also resets this rank's flags (new generation)
     t = torch.tensor(list(mine), dtype=torch.uint8, device=torch.device("cuda", ctx.device))
     allh = [torch.empty_like(t) for _ in range(world)]

@@ -338,6 +338,8 @@ def main():
         B.dist.init_comm(ctx)
         if os.environ.get("BAOREC_A2A_CHUNKS"):      # A/B knobs
             ctx.set_option("a2a_chunks", int(os.environ["BAOREC_A2A_CHUNKS"]))
+        if os.environ.get("BAOREC_PEER_HALO"):
+            ctx.set_option("peer_halo", int(os.environ["BAOREC_PEER_HALO"]))
         if os.environ.get("BAOREC_PUSH_SM"):
             ctx.set_option("push_sm", int(os.environ["BAOREC_PUSH_SM"]))
         if os.environ.get("BAOREC_COMM_SPLIT"):

@@ -162,15 +162,17 @@ int baorec_plan_dist(baorec_ctx* ctx, int nx, int ny, int nz, const float box_si
 int baorec_slab_range(const baorec_ctx* ctx, int* z_lo, int* nz_loc);
 /* Peer-copy exchange of the slab transforms (option "dist_exchange" = 1, the default; after baorec_plan_dist): every
  * rank exports the CUDA IPC handles of its three receive buffers (k-layout for the forward, two plane-layout ones for
- * the inverse transforms, so that two fields can be in flight) and of its flag block (4 x 64 bytes; the call also resets the rank's flags, so it must precede the
+ * the inverse transforms, so that two fields can be in flight), of its halo inbox (ghost / halo planes of the ring
+ * neighbours land there: two small kernels per exchange instead of a grouped ncclSend / ncclRecv; option "peer_halo")
+ * and of its flag block (5 x 64 bytes; the call also resets the rank's flags, so it must precede the
  * gathering of the handles on every rank), the host side all-gathers them, and each rank opens the others'.  From then
  * on an exchange is one strided copy-engine copy per peer and plane chunk over NVLink, straight from the 2-D
  * transform's output into the peer's buffer, announced by a sequence flag stored into the peer's flag block: no
  * pack / transpose kernels, no staging buffer, no collective, no barrier.  With one rank the library maps itself.
  * "dist_exchange" = 0 selects round 1's scheme: pack + tile-transpose kernels and grouped ncclSend/ncclRecv. */
 int baorec_dist_ipc_close(baorec_ctx* ctx);  /* drop the mappings (before a re-plan frees the buffers) */
-int baorec_dist_ipc_export(baorec_ctx* ctx, void* out256);
-int baorec_dist_ipc_open(baorec_ctx* ctx, const void* all_handles /* nranks x 256 bytes */, int nranks);
+int baorec_dist_ipc_export(baorec_ctx* ctx, void* out320);
+int baorec_dist_ipc_open(baorec_ctx* ctx, const void* all_handles /* nranks x 320 bytes */, int nranks);
 int baorec_dist_exchange_mode(const baorec_ctx* ctx); /* 1: peer copies (k space K[z][yl][x]); 0: NCCL (T[yl][x][z]) */
 /* Owner rank of every particle = slab of its cic! base plane (src/mas.jl:15-30), -1 if out of box. */
 int baorec_slab_owner_f32(baorec_ctx* ctx, const float* d_z, int64_t n, int32_t* d_owner, baorec_stream stream);
