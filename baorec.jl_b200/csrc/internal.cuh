@@ -201,7 +201,7 @@ struct baorec_ctx {
   int64_t n_sort_reuse = 0;              // read-backs that reused the run!'s sort (diagnostics)
   int opt_gather_tiles = 1;    // gather: fine (z, y/8, x/128) tile binning instead of z slabs
   int opt_scatter_pairs = 2;   // vector reductions: 1 = red.global.add.v2.f32 for aligned x pairs (6 per particle), 2 = one red.global.add.v4.f32 per CIC row (5 per particle); measured at C4: scatter 3.89 -> 3.51 -> 2.99 ms, default 2
-  int opt_gather_stage = 1;    // tile gather: 1 = strength-reduced cp.async staging (gather_tile_kernel<3, 1>); measured at C4: 5.28 -> 3.54 ms, bit-identical shifts, default
+  int opt_gather_stage = 2;    // tile gather staging: 2 = tensor-map TMA (gather_tile_tma_kernel: six cp.async.bulk.tensor.3d copies per tile; C4: 3.48 -> 2.90 ms = 0.85 of HBM), 1 = strength-reduced cp.async rows (5.28 -> 3.48 ms), 0 = the round-1 loop; bit-identical shifts
   int opt_zg_scatter = 0, opt_zg_gather = 0;  // z planes per bin (0 = auto)
   int64_t last_wrapped = 0;  // particles whose position cic! wrapped in the last scatter
   // per-launch profiling (baorec_profile_*)

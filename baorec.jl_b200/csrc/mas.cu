@@ -9,6 +9,7 @@
 // plane, ZG planes per bin): the scatter's float atomics and the gather's 8x3 loads then
 // walk the mesh one (ZG+1)-plane window at a time, which stays resident in the 126 MB L2,
 // so HBM sees each mesh sector once instead of once per particle.
+#include <cuda.h>
 #include <string.h>
 
 #include "internal.cuh"
@@ -669,6 +670,44 @@ tile_reorder_kernel(const float* __restrict__ x, const float* __restrict__ y, co
 // values from shared memory.  Same arithmetic and order as gather_one -> identical results.
 constexpr int TILE_WXP = TILE_X + 4;  // padded row length in shared memory
 
+// The particle loop of the TMA-staged tile gather (gather_tile_tma_kernel below): every particle of the tile reads its
+// 8 x NF values from the staged window (PLANE floats per (field, plane), rows of TILE_WXP).  The same arithmetic in the
+// same order as the loop of gather_tile_kernel and as gather_one -> identical results.
+template <int NF, int PLANE, bool FIRST>
+__device__ __forceinline__ void tile_particles(const float* __restrict__ sm, const GatherArgs& a,
+                                               const float4* __restrict__ rec, unsigned beg, unsigned end,
+                                               float4 p_first, const BoxGeom& g, int x0, int y0) {
+  const int nx = g.n[0], ny = g.n[1], nz = g.n[2];
+  for (unsigned i = beg + threadIdx.x; i < end; i += 128) {
+    float4 p = (FIRST && i < beg + 128) ? p_first : rec[i];
+    const float px = p.x, py = p.y, pz = p.z;
+    const int64_t out_idx = (int64_t)__float_as_uint(p.w);
+    int xd, xu, yd, yu, zd, zu;
+    float dx, ux, dy, uy, dz, uz;
+    gather_axis(px, g.mn[0], g.L[0], g.cell[0], nx, false, xd, xu, dx, ux);
+    gather_axis(py, g.mn[1], g.L[1], g.cell[1], ny, false, yd, yu, dy, uy);
+    gather_axis(pz, g.mn[2], g.L[2], g.cell[2], nz, false, zd, zu, dz, uz);
+    const float* w00 = sm + (yd - y0) * TILE_WXP + (xd - x0);  // plane 0, row ly, column lx
+    float val[NF];
+#pragma unroll
+    for (int c = 0; c < NF; c++) {
+      const float* q0 = w00 + (2 * c) * PLANE;
+      const float* q1 = q0 + PLANE;
+      float v;
+      v = __fmul_rn(__fmul_rn(__fmul_rn(q0[0], dx), dy), dz);
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(q1[0], dx), dy), uz));
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(q0[TILE_WXP], dx), uy), dz));
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(q1[TILE_WXP], dx), uy), uz));
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(q0[1], ux), dy), dz));
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(q1[1], ux), dy), uz));
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(q0[TILE_WXP + 1], ux), uy), dz));
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fmul_rn(q1[TILE_WXP + 1], ux), uy), uz));
+      val[c] = v;
+    }
+    shifts_epilogue<NF>(a, val, px, py, pz, out_idx, (int64_t)i);
+  }
+}
+
 // STAGE selects how the fast path issues its cp.async rows: 0 = rows dealt round-robin over a fully unrolled loop
 // (the version measured in round 1: 1719 of its 2700 SASS instructions are integer address arithmetic, and every warp
 // steps over all 54 row predicates); 1 = each warp owns rows py = warp, warp + 4 (, 8) of every (field, plane):
@@ -806,6 +845,161 @@ gather_tile_kernel(GatherArgs a, const float4* __restrict__ rec, const unsigned*
     }
     shifts_epilogue<NF>(a, val, px, py, pz, out_idx, (int64_t)i);
   }
+}
+
+// ---- tile gather staged by the TMA engine (option "gather_stage" = 2) ------------------------------------------------
+// One 3-D tensor map per field (x fastest, then y, then the nzp planes of the buffer), box = TILE_WXP x (TILE_Y+1) x 1:
+// ONE thread issues 2 x NF cp.async.bulk.tensor.3d copies (UTMALDG) for the whole window -- the 54 row copies of the
+// cp.async versions with their address arithmetic leave the issue slots -- and the block waits on one mbarrier.
+// The engine fills what lies beyond the mesh with zeros, it does not wrap: the last tile along x takes its column
+// TILE_X from x = 0 and the last tile along y its row TILE_Y from y = 0 with ordinary loads, requested before the wait
+// and stored after it.  The two planes are separate copies, so the periodic z + 1 is just a coordinate.
+// Shared-memory destinations of tensor copies must be 128-byte aligned: each (field, plane) block is padded from
+// 9 x 132 = 1188 floats to 1216.  Tiles that are not full (mesh sizes off the tile grid) stage with plain loads.
+struct alignas(64) GatherMaps {
+  CUtensorMap m[3];
+};
+constexpr int TMA_PLANE = 1216;
+static_assert(TMA_PLANE >= (TILE_Y + 1) * TILE_WXP && (TMA_PLANE * 4) % 128 == 0, "128-byte aligned (field, plane) blocks");
+static_assert((TILE_WXP * 4) % 16 == 0, "the box's inner extent is a multiple of 16 bytes");
+
+template <int NF>
+__global__ void __launch_bounds__(128)
+gather_tile_tma_kernel(const __grid_constant__ GatherMaps maps, GatherArgs a, const float4* __restrict__ rec,
+                       const unsigned* __restrict__ starts, BoxGeom g, TileGeom t) {
+  __shared__ __align__(128) float sm[NF * 2 * TMA_PLANE];
+  __shared__ __align__(8) unsigned long long mbar_store;
+  const unsigned tile = blockIdx.x;
+  const unsigned beg = starts[tile], end = starts[tile + 1];
+  if (beg == end) return;
+  const int nx = g.n[0], ny = g.n[1], nz = g.n[2];
+  int tx, ty, iz;
+  if (((t.nxc & (t.nxc - 1)) | (t.nyc & (t.nyc - 1))) == 0) {
+    const int sx = __ffs(t.nxc) - 1, sy = __ffs(t.nyc) - 1;
+    tx = (int)(tile & (unsigned)(t.nxc - 1));
+    ty = (int)((tile >> sx) & (unsigned)(t.nyc - 1));
+    iz = (int)(tile >> (sx + sy));
+  } else {
+    tx = tile % t.nxc;
+    const unsigned r = tile / t.nxc;
+    ty = r % t.nyc;
+    iz = r / t.nyc;
+  }
+  const int x0 = tx * TILE_X, y0 = ty * TILE_Y;
+  const int wx = min(TILE_X, nx - x0), wy = min(TILE_Y, ny - y0);
+  const int z1 = g.slab ? iz + 1 : (iz + 1 >= nz ? 0 : iz + 1);
+  const int tid = threadIdx.x;
+  float4 p_first = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (beg + tid < end) p_first = rec[beg + tid];  // in flight while the window is staged
+  if (wx == TILE_X && wy == TILE_Y) {
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(&mbar_store);
+    const unsigned s0 = (unsigned)__cvta_generic_to_shared(sm);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      constexpr unsigned BYTES = NF * 2 * (TILE_Y + 1) * TILE_WXP * 4;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(BYTES) : "memory");
+#pragma unroll
+      for (int p = 0; p < NF * 2; p++) {  // p = field * 2 + plane
+        const unsigned long long map = (unsigned long long)(uintptr_t)&maps.m[p >> 1];
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(s0 + (unsigned)(p * TMA_PLANE * 4)), "l"(map), "r"(x0), "r"(y0), "r"((p & 1) ? z1 : iz), "r"(mbar)
+            : "memory");
+      }
+    }
+    // what the engine cannot fetch: the periodic images of column TILE_X (last tile along x) and row TILE_Y (last along y)
+    const bool wrapx = x0 + TILE_X >= nx, wrapy = y0 + TILE_Y >= ny;
+    const size_t plane_elems = (size_t)ny * nx;
+    float ex = 0.f;
+    int ex_at = -1;
+    if (wrapx && tid < NF * 2 * (TILE_Y + 1)) {
+      const int p = tid / (TILE_Y + 1), py = tid - p * (TILE_Y + 1);
+      int yy = y0 + py;
+      if (yy >= ny) yy -= ny;
+      const int f = p >> 1;
+      const float* fld = f == 0 ? a.f[0] : (f == 1 ? a.f[NF > 1 ? 1 : 0] : a.f[NF > 2 ? 2 : 0]);
+      ex = __ldg(fld + (size_t)((p & 1) ? z1 : iz) * plane_elems + (size_t)yy * nx);
+      ex_at = p * TMA_PLANE + py * TILE_WXP + TILE_X;
+    }
+    __syncthreads();  // the barrier is initialised before anyone polls it
+    unsigned done = 0;
+    while (!done) {
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                   : "=r"(done)
+                   : "r"(mbar)
+                   : "memory");
+    }
+    if (wrapx | wrapy) {
+      if (ex_at >= 0) sm[ex_at] = ex;
+      if (wrapy) {
+        for (int idx = tid; idx < NF * 2 * (TILE_X + 1); idx += 128) {
+          const int p = idx / (TILE_X + 1), c = idx - p * (TILE_X + 1);
+          int xx = x0 + c;
+          if (xx >= nx) xx -= nx;
+          const int f = p >> 1;
+          const float* fld = f == 0 ? a.f[0] : (f == 1 ? a.f[NF > 1 ? 1 : 0] : a.f[NF > 2 ? 2 : 0]);
+          sm[p * TMA_PLANE + TILE_Y * TILE_WXP + c] = __ldg(fld + (size_t)((p & 1) ? z1 : iz) * plane_elems + xx);
+        }
+      }
+      __syncthreads();
+    }
+  } else {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nrows = NF * 2 * (wy + 1);
+    for (int row = warp; row < nrows; row += 4) {
+      const int py = row % (wy + 1), p = row / (wy + 1);
+      int yy = y0 + py;
+      if (yy >= ny) yy -= ny;
+      const int f = p >> 1;
+      const float* fld = f == 0 ? a.f[0] : (f == 1 ? a.f[NF > 1 ? 1 : 0] : a.f[NF > 2 ? 2 : 0]);
+      const float* src = fld + ((size_t)((p & 1) ? z1 : iz) * ny + yy) * nx;
+      float* dst = sm + p * TMA_PLANE + py * TILE_WXP;
+      for (int c = lane; c <= wx; c += 32) {
+        int xx = x0 + c;
+        if (xx >= nx) xx -= nx;
+        dst[c] = __ldg(src + xx);
+      }
+    }
+    __syncthreads();
+  }
+  tile_particles<NF, TMA_PLANE, true>(sm, a, rec, beg, end, p_first, g, x0, y0);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point query: no link-time dependency on libcuda
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// The maps of the gather's fields; false when the layout cannot be described (row pitch or base off 16 bytes) or the
+// driver has no tensor maps: the caller stages with cp.async then.
+static bool gather_maps(const GatherArgs& a, int nf, const BoxGeom& g, GatherMaps* out) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc || g.n[0] % 4 != 0) return false;
+  for (int f = 0; f < 3; f++) {
+    const float* base = a.f[f < nf ? f : 0];
+    if (((uintptr_t)base & 15) != 0) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)g.n[0], (cuuint64_t)g.n[1], (cuuint64_t)g.nzp};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.n[0] * 4, (cuuint64_t)g.n[0] * g.n[1] * 4};
+    const cuuint32_t box[3] = {TILE_WXP, TILE_Y + 1, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&out->m[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  }
+  return true;
 }
 
 __global__ void add_oob_kernel(const unsigned* __restrict__ count, unsigned long long* oob) {
@@ -1192,15 +1386,25 @@ int gather3(baorec_ctx* ctx, const float* fx, const float* fy, const float* fz, 
         cudaFuncSetAttribute(gather_tile_kernel<3, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         carve = true;
       }
+      GatherMaps maps;
+      const bool tma = ctx->opt_gather_stage == 2 && gather_maps(a, one ? 1 : 3, g, &maps);
       if (one) {
-        BR_LAUNCH_NAMED(ctx, "gather_tile_kernel<1>", (gather_tile_kernel<1, 0>), b.ntiles, 128, 0, st, a, b.rec, b.starts, g, t);
+        if (tma) BR_LAUNCH_NAMED(ctx, "gather_tile_tma_kernel<1>", gather_tile_tma_kernel<1>, b.ntiles, 128, 0, st, maps, a, b.rec, b.starts, g, t);
+        else BR_LAUNCH_NAMED(ctx, "gather_tile_kernel<1>", (gather_tile_kernel<1, 0>), b.ntiles, 128, 0, st, a, b.rec, b.starts, g, t);
       } else {
         // results land in sorted order (coalesced), then one un-permute pass: the 3 x 4 B scattered
         // stores of the direct version cost three random DRAM read-modify-writes per particle
         float4* so;
         BR_TRY(need_t(ctx, BUF_BINOUT, (size_t)n, &so));
         a.sorted_out = so;
-        if (ctx->opt_gather_stage) BR_LAUNCH_NAMED(ctx, "gather_tile_kernel<3> [stage=1]", (gather_tile_kernel<3, 1>), b.ntiles, 128, 0, st, a, b.rec, b.starts, g, t);
+        if (tma) {
+          static bool carve_tma = false;
+          if (!carve_tma) {
+            cudaFuncSetAttribute(gather_tile_tma_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            carve_tma = true;
+          }
+          BR_LAUNCH_NAMED(ctx, "gather_tile_tma_kernel<3>", gather_tile_tma_kernel<3>, b.ntiles, 128, 0, st, maps, a, b.rec, b.starts, g, t);
+        } else if (ctx->opt_gather_stage) BR_LAUNCH_NAMED(ctx, "gather_tile_kernel<3> [stage=1]", (gather_tile_kernel<3, 1>), b.ntiles, 128, 0, st, a, b.rec, b.starts, g, t);
         else BR_LAUNCH_NAMED(ctx, "gather_tile_kernel<3>", (gather_tile_kernel<3, 0>), b.ntiles, 128, 0, st, a, b.rec, b.starts, g, t);
         BR_LAUNCH(ctx, unsort_kernel, cdiv((size_t)n, 256), 256, 0, st, a, so, b.inv, n, b.n_valid);
         return BAOREC_OK;

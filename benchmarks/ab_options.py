@@ -5,8 +5,7 @@ one gpurun call answers "does option X pay off?" (ms per reconstruction + the fi
     python benchmarks/ab_options.py [--mesh 1024] [--particles 1e8] [--catalog uniform|lognormal] [--steps 5]
                                     [--set name=value ...]      # extra configurations, e.g. --set deterministic_scatter=1
 
-Default configurations: baseline; unified_sort=0; gather_tiles=0; deterministic_scatter=1; fuse_kspace=0; gather_stage=1; scatter_pairs=1.
-Not run on hardware yet (written after round 1's GPU budget was spent)."""
+Default configurations: baseline; unified_sort=0; gather_tiles=0; deterministic_scatter=1; fuse_kspace=0; gather_stage=0 / 1; scatter_pairs=0; own_fft=0."""
 import argparse
 import json
 import sys
@@ -22,7 +21,7 @@ import __graft_entry__ as G  # noqa: E402
 import catalogs  # noqa: E402
 
 B = G.load_package()
-DEFAULTS = {"unified_sort": 1, "gather_tiles": 1, "deterministic_scatter": 0, "fuse_kspace": 1, "gather_stage": 1, "scatter_pairs": 2, "own_fft": -1}
+DEFAULTS = {"unified_sort": 1, "gather_tiles": 1, "deterministic_scatter": 0, "fuse_kspace": 1, "gather_stage": 2, "scatter_pairs": 2, "own_fft": -1}
 
 
 def main():
@@ -33,6 +32,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--set", action="append", default=[], metavar="NAME=VALUE")
+    ap.add_argument("--only-set", action="store_true", help="baseline + the --set configurations only")
     args = ap.parse_args()
     n, N = args.mesh, int(args.particles)
     L = 2500.0 * n / 1024.0
@@ -43,7 +43,7 @@ def main():
     kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, n_iter=3, los=(0.0, 0.0, 1.0), box_size=np.full(3, L, np.float32),
               box_min=np.zeros(3, np.float32))
     ctx = B.Context.get(0)
-    configs = [{}] + [{k: 0 if v else 1} for k, v in DEFAULTS.items()]       # (own_fft: auto -> 0 = cuFFT's 3-D plans)
+    configs = [{}] + ([] if args.only_set else [{k: 0 if v else 1} for k, v in DEFAULTS.items()] + [{"gather_stage": 1}])   # (own_fft: auto -> 0 = cuFFT's 3-D plans)
     for item in args.set:
         k, v = item.split("=")
         configs.append({k: int(v)})

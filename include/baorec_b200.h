@@ -105,9 +105,13 @@ int baorec_set_box(baorec_ctx* ctx, const float box_size[3], const float box_min
  *       average, branch-free).  Either value also switches the binned TSC scatter to one quad (+ one pair for half of
  *       the particles) per stencil row: 13.5 instead of 27.  Measured on B200 at 1024^3 / 1e8 particles: scatter 3.89 ms
  *       (0), 3.51 ms (1), 2.99 ms (2).
- *   "gather_stage" (default 1): 1 = the tile gather issues its shared-memory staging with one base pointer per
- *       (field, plane) and one multiply-add per row (half the instructions of the first kernel, 0); bit-identical
- *       results.  Measured on B200 at 1024^3 / 1e8 particles: gather 5.28 ms (0), 3.54 ms (1).
+ *   "gather_stage" (default 2): how the tile gather stages the 2 x 9 x 129 window of each displacement mesh in shared
+ *       memory.  2 = the TMA engine: one 3-D tensor map per field, six cp.async.bulk.tensor.3d copies per tile issued by
+ *       one thread, one mbarrier (the periodic column / row the engine cannot fetch come from ordinary loads); needs a
+ *       row pitch and base that are multiples of 16 bytes and a driver with cuTensorMapEncodeTiled, else 1 is used.
+ *       1 = cp.async rows with one base pointer per (field, plane) and one multiply-add per row; 0 = the first kernel
+ *       (twice the instructions of 1).  Bit-identical results.  Measured on B200 at 1024^3 / 1e8 particles: gather
+ *       5.28 ms (0), 3.48 ms (1), 2.90 ms (2) = 0.85 of the measured HBM copy rate.
  *   "deterministic_scatter" (default 0): 1 = the CIC scatter (single GPU) accumulates 2^-40 fixed-point values with
  *       64-bit integer reductions and rounds to Float32 once: meshes, `ran > threshold` masks and everything after
  *       them are bit-reproducible from run to run and independent of the particle order (float reductions are not);

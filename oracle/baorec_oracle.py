@@ -334,6 +334,67 @@ def read_tsc(fld, x, y, z, box_size, box_min, wrap=True):
     return out
 
 
+# PCS (piecewise cubic spline; SURVEY.md section 8f N3 -- the fourth assignment scheme of the power-spectrum tool the
+# reference's helpers configure, test_helpers/powspec_auto.conf:117-124; not in src/mas.jl).  Same grid convention as
+# cic! / tsc: mesh points at min + i * cell.  c = floor(g), t = g - c, u = 1 - t; the four points c-1 .. c+2 carry the
+# cubic B-spline  w(-1) = u^3/6,  w(0) = ((3t - 6) t^2 + 4)/6,  w(+1) = ((3u - 6) u^2 + 4)/6,  w(+2) = t^3/6,
+# every operation rounded to T in the order written (the device kernels spell out the same sequence).
+def pcs_cells(x, y, z, n_xyz, box_size, box_min, wrap=True):
+    """Returns (c[3][N] 0-based *unwrapped* floor index, [w(-1), w(0), w(+1), w(+2)] per axis)."""
+    T = _T(x)
+    L = _vec3(box_size, T)
+    mn = _vec3(box_min, T)
+    ic, W = [], []
+    for a, p in enumerate((x, y, z)):
+        n = int(n_xyz[a])
+        p = np.asarray(p, dtype=T)
+        g = (((p - mn[a]).astype(T) * T(n)).astype(T) / L[a]).astype(T)
+        c = np.floor(g)
+        t = (g - c).astype(T)
+        u = (T(1) - t).astype(T)
+        t2 = (t * t).astype(T)
+        u2 = (u * u).astype(T)
+        w_m = ((u2 * u).astype(T) / T(6)).astype(T)
+        w_0 = (((((T(3) * t).astype(T) - T(6)).astype(T) * t2).astype(T) + T(4)).astype(T) / T(6)).astype(T)
+        w_1 = (((((T(3) * u).astype(T) - T(6)).astype(T) * u2).astype(T) + T(4)).astype(T) / T(6)).astype(T)
+        w_2 = ((t2 * t).astype(T) / T(6)).astype(T)
+        W.append((w_m, w_0, w_1, w_2))
+        ic.append(c.astype(np.int64))
+    return ic, W
+
+
+def pcs_scatter(rho, x, y, z, w, box_size, box_min, wrap=True):
+    T = _T(rho)
+    nz, ny, nx = rho.shape
+    ic, W = pcs_cells(x, y, z, (nx, ny, nz), box_size, box_min, wrap)
+    w = np.asarray(w, dtype=T)
+    flat = rho.reshape(-1)
+    for oz in range(4):
+        iz = _tsc_axis_index(ic[2], oz - 1, nz, wrap)
+        for oy in range(4):
+            iy = _tsc_axis_index(ic[1], oy - 1, ny, wrap)
+            for ox in range(4):
+                ix = _tsc_axis_index(ic[0], ox - 1, nx, wrap)
+                val = (((W[0][ox] * w).astype(T) * W[1][oy]).astype(T) * W[2][oz]).astype(T)
+                np.add.at(flat, (iz * ny + iy) * nx + ix, val)
+    return rho
+
+
+def read_pcs(fld, x, y, z, box_size, box_min, wrap=True):
+    T = _T(fld)
+    nz, ny, nx = fld.shape
+    ic, W = pcs_cells(x, y, z, (nx, ny, nz), box_size, box_min, wrap)
+    out = np.zeros(len(x), dtype=T)
+    for oz in range(4):
+        iz = _tsc_axis_index(ic[2], oz - 1, nz, wrap)
+        for oy in range(4):
+            iy = _tsc_axis_index(ic[1], oy - 1, ny, wrap)
+            for ox in range(4):
+                ix = _tsc_axis_index(ic[0], ox - 1, nx, wrap)
+                out = (out + (((fld[iz, iy, ix] * W[0][ox]).astype(T) * W[1][oy]).astype(T) * W[2][oz]).astype(T)).astype(T)
+    return out
+
+
 # --------------------------------------------------------------------------
 # recon.jl : parameter bags and overdensity set-up
 # --------------------------------------------------------------------------
@@ -348,7 +409,7 @@ class IterativeRecon:
     los: Optional[Sequence[float]] = None
     n_iter: int = 3
     beta: Optional[float] = None
-    mas: str = "cic"            # extension ("tsc"); the reference hard-codes cic!
+    mas: str = "cic"            # extension ("tsc", "pcs"); the reference hard-codes cic!
     result_cache: Optional[np.ndarray] = _dcfield(default=None, repr=False)
 
     def __post_init__(self):
@@ -380,6 +441,8 @@ class MultigridRecon:
 def _scatter(recon, rho, x, y, z, w, wrap):
     if getattr(recon, "mas", "cic") == "tsc":
         return tsc_scatter(rho, x, y, z, w, recon.box_size, recon.box_min, wrap)
+    if getattr(recon, "mas", "cic") == "pcs":
+        return pcs_scatter(rho, x, y, z, w, recon.box_size, recon.box_min, wrap)
     return cic_scatter(rho, x, y, z, w, recon.box_size, recon.box_min, wrap)
 
 
@@ -495,6 +558,8 @@ def compute_displacements_iterative(delta, x, y, z, recon, formula="cpu"):
 def _read(recon, fld, x, y, z, formula="cpu"):
     if getattr(recon, "mas", "cic") == "tsc":
         return read_tsc(fld, x, y, z, recon.box_size, recon.box_min, True)
+    if getattr(recon, "mas", "cic") == "pcs":
+        return read_pcs(fld, x, y, z, recon.box_size, recon.box_min, True)
     return read_cic(fld, x, y, z, recon.box_size, recon.box_min, True, formula)
 
 
