@@ -17,6 +17,6 @@ from .host import (Context, FFTPlan, IterativeRecon, MultigridRecon, setup_fft, 
                    reconstructed_positions, jacobi, residual, reduce, prolong, vcycle, fmg)
 
 from . import dist
-from .catalog import Cosmology, DESICosmology, sky_to_cartesian, cartesian_to_sky, fkp_weights, wrap_positions, power_multipoles
+from .catalog import Cosmology, DESICosmology, sky_to_cartesian, cartesian_to_sky, fkp_weights, wrap_positions, power_multipoles, interlace_positions, compute_auto_box
 
 lib_loader.load()   # no library -> ImportError; there is no fallback path

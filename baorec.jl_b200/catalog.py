@@ -131,28 +131,78 @@ def wrap_positions(pos_x, pos_y, pos_z, box_size, box_min=(0.0, 0.0, 0.0)):
     return pos_x, pos_y, pos_z
 
 
-def power_multipoles(rho, box_size, los=(0.0, 0.0, 1.0), kmin=0.0, dk=None, nbins=None, mas="cic", shot=0.0,
-                     box_min=(0.0, 0.0, 0.0), randoms=None):
-    """P_0, P_2, P_4 of the density mesh `rho` (device tensor [nz][ny][nx] from `cic`; not modified) for a periodic
-    box: the before / after check of test_helpers/simulation.py:56-75 (pypowspec compute_auto_box), on the device.
-    mas: "cic" / "tsc" / None selects the window the estimate is compensated for; `shot` (e.g. V / N) is subtracted
-    from the monopole.  `randoms`: optional density mesh of a shifted random catalog -> the spectrum of "data minus
-    shifted randoms" (compute_auto_box_rand in the reference's helpers: RecIso / RecSym).  Defaults: dk = the fundamental 2 pi / max(L), bins up to the Nyquist frequency.
-    Returns dict(k, nmodes, p0, p2, p4) of numpy Float64 arrays (NaN in empty bins)."""
-    from .host import _chk_mesh, _plan_for
-    nx, ny, nz = _chk_mesh(rho)
+MAS_POWER = {None: 0, "none": 0, "ngp": 1, "cic": 2, "tsc": 3, "pcs": 4}
+
+
+def _bins(nx, ny, nz, box_size, kmin, dk, nbins):
     Lb = np.broadcast_to(np.asarray(box_size, np.float64), 3)
     if dk is None:
         dk = 2 * np.pi / float(Lb.max())
     if nbins is None:
         nbins = int((np.pi * min(nx / Lb[0], ny / Lb[1], nz / Lb[2]) - kmin) / dk)
-    nbins = max(1, min(int(nbins), 1024))
-    if randoms is not None and _chk_mesh(randoms) != (nx, ny, nz):
-        raise ValueError("the randoms mesh must have the shape of the data mesh")
+    return float(dk), max(1, min(int(nbins), 1024))
+
+
+def power_multipoles(rho, box_size, los=(0.0, 0.0, 1.0), kmin=0.0, dk=None, nbins=None, mas="cic", shot=0.0,
+                     box_min=(0.0, 0.0, 0.0), randoms=None, rho_shifted=None, randoms_shifted=None):
+    """P_0, P_2, P_4 of the density mesh `rho` (device tensor [nz][ny][nx] from `cic`; not modified) for a periodic
+    box: the before / after check of test_helpers/simulation.py:56-75 (pypowspec compute_auto_box), on the device.
+    mas: "cic" / "tsc" / "pcs" / None selects the window the estimate is compensated for; `shot` (e.g. V / N) is subtracted
+    from the monopole.  `randoms`: optional density mesh of a shifted random catalog -> the spectrum of "data minus
+    shifted randoms" (compute_auto_box_rand in the reference's helpers: RecIso / RecSym).  `rho_shifted` (and
+    `randoms_shifted`): the meshes of the same catalogs painted from `interlace_positions` -> the interlaced estimate
+    (GRID_INTERLACE = T, test_helpers/powspec_auto.conf:125).  Defaults: dk = the fundamental 2 pi / max(L), bins up to
+    the Nyquist frequency.  Returns dict(k, nmodes, p0, p2, p4) of numpy Float64 arrays (NaN in empty bins)."""
+    from .host import _chk_mesh, _plan_for
+    nx, ny, nz = _chk_mesh(rho)
+    dk, nbins = _bins(nx, ny, nz, box_size, kmin, dk, nbins)
+    for m in (randoms, rho_shifted, randoms_shifted):
+        if m is not None and _chk_mesh(m) != (nx, ny, nz):
+            raise ValueError("every mesh must have the shape of the data mesh")
+    if (randoms is None) != (randoms_shifted is None) and rho_shifted is not None:
+        raise ValueError("interlaced estimate with randoms: pass both randoms meshes")
     ctx = _plan_for(rho, box_size, box_min)
     out = [np.empty(nbins, np.float64) for _ in range(5)]
     dp = [o.ctypes.data_as(C.POINTER(C.c_double)) for o in out]
-    power = {None: 0, "none": 0, "ngp": 1, "cic": 2, "tsc": 3}[mas]
-    L.check(ctx.lib.baorec_power_multipoles_f32(ctx.handle, _ptr(rho), _ptr(randoms) if randoms is not None else None, L.f3(np.asarray(los, np.float32)), float(kmin), float(dk),
-                                                nbins, power, float(shot), *dp, _stream()))
+    power = MAS_POWER[mas]
+    opt = lambda t: _ptr(t) if t is not None else None                       # noqa: E731
+    if rho_shifted is None:
+        L.check(ctx.lib.baorec_power_multipoles_f32(ctx.handle, _ptr(rho), opt(randoms), L.f3(np.asarray(los, np.float32)), float(kmin), dk,
+                                                    nbins, power, float(shot), *dp, _stream()))
+    else:
+        L.check(ctx.lib.baorec_power_multipoles_interlaced_f32(ctx.handle, _ptr(rho), opt(randoms), _ptr(rho_shifted), opt(randoms_shifted),
+                                                               L.f3(np.asarray(los, np.float32)), float(kmin), dk, nbins, power, float(shot),
+                                                               *dp, _stream()))
+    return dict(k=out[0], nmodes=out[1], p0=out[2], p2=out[3], p4=out[4])
+
+
+def interlace_positions(pos_x, pos_y, pos_z, grid_size, box_size, box_min=(0.0, 0.0, 0.0)):
+    """The catalog of the interlaced mesh: every position half a cell further along each axis, periodic.  Returns new tensors."""
+    import torch
+    from .host import _plan_grid
+    n = _chk_vec(pos_x, pos_y, pos_z)
+    ctx = _plan_grid(pos_x.device.index, grid_size, box_size, box_min)
+    out = tuple(torch.empty_like(pos_x) for _ in range(3))
+    L.check(ctx.lib.baorec_interlace_positions_f32(ctx.handle, _ptr(pos_x), _ptr(pos_y), _ptr(pos_z), n, *(_ptr(o) for o in out), _stream()))
+    return out
+
+
+def compute_auto_box(data_x, data_y, data_z, data_w, box_size, grid_size=(512, 512, 512), mas="tsc", interlace=True, los=(0.0, 0.0, 1.0),
+                     kmin=0.0, dk=None, nbins=None, shot=0.0, box_min=(0.0, 0.0, 0.0), rand_x=None, rand_y=None, rand_z=None, rand_w=None):
+    """compute_auto_box(x, y, z, w, ...) / compute_auto_box_rand(x, y, z, w, rx, ry, rz, rw, ...) of the reference's
+    helpers (test_helpers/simulation.py:36-70 with test_helpers/powspec_auto.conf: 512^3 grid, TSC, interlaced, line of
+    sight along z, l = 0, 2, 4) in ONE library call on device catalogs: paint, interlace, transform, bin.  The catalogs
+    are not modified.  Returns dict(k, nmodes, p0, p2, p4)."""
+    from .host import _plan_grid
+    n = _chk_vec(data_x, data_y, data_z, data_w)
+    nr = _chk_vec(rand_x, rand_y, rand_z, rand_w) if rand_x is not None else 0
+    nx, ny, nz = (int(v) for v in grid_size)
+    dk, nbins = _bins(nx, ny, nz, box_size, kmin, dk, nbins)
+    ctx = _plan_grid(data_x.device.index, grid_size, box_size, box_min)
+    out = [np.empty(nbins, np.float64) for _ in range(5)]
+    dp = [o.ctypes.data_as(C.POINTER(C.c_double)) for o in out]
+    opt = lambda t: _ptr(t) if t is not None else None                       # noqa: E731
+    L.check(ctx.lib.baorec_compute_auto_box_f32(ctx.handle, _ptr(data_x), _ptr(data_y), _ptr(data_z), _ptr(data_w), n, opt(rand_x), opt(rand_y),
+                                                opt(rand_z), opt(rand_w), nr, L.MAS[mas], int(bool(interlace)), L.f3(np.asarray(los, np.float32)),
+                                                float(kmin), dk, nbins, float(shot), *dp, _stream()))
     return dict(k=out[0], nmodes=out[1], p0=out[2], p2=out[3], p4=out[4])

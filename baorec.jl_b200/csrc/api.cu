@@ -9,7 +9,7 @@ namespace baorec {
 static int check_params(const baorec_params* p) {
   BR_REQUIRE(p != nullptr, "params is NULL");
   BR_REQUIRE(p->bias != 0.f, "bias must be non-zero");
-  BR_REQUIRE(p->mas == BAOREC_MAS_CIC || p->mas == BAOREC_MAS_TSC, "unknown mas");
+  BR_REQUIRE(p->mas == BAOREC_MAS_CIC || p->mas == BAOREC_MAS_TSC || p->mas == BAOREC_MAS_PCS, "unknown mas");
   BR_REQUIRE(p->n_iter >= 0 && p->jacobi_niterations >= 0 && p->vcycle_niterations >= 0, "negative iteration count");
   return BAOREC_OK;
 }

@@ -360,7 +360,7 @@ int baorec_create(int device, baorec_ctx** out) {
   ctx->device = device;
   BR_CUDA(cudaMalloc(&ctx->d_oob, 2 * sizeof(unsigned long long)));  // [0] out-of-box, [1] positions wrapped
   BR_CUDA(cudaMemset(ctx->d_oob, 0, 2 * sizeof(unsigned long long)));
-  BR_CUDA(cudaMalloc(&ctx->d_scal, 16 * sizeof(double)));
+  BR_CUDA(cudaMalloc(&ctx->d_scal, 32 * sizeof(double)));
   BR_CUDA(cudaMalloc(&ctx->d_hash, 4 * sizeof(unsigned long long)));
   BR_CUDA(cudaMalloc(&ctx->d_minmax, 8 * sizeof(float)));
   BR_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));

@@ -1603,7 +1603,7 @@ int baorec_dist_c2r_f32(baorec_ctx* ctx, float* d_kslab_t, float* d_slab, baorec
 // real plane, the two planes above go to the next rank and are added to its first two; finally the real planes
 // are copied to `loc` (planes 0 .. nz_loc-1), where the transform expects them.
 static int dist_scatter_tsc(baorec_ctx* ctx, float* loc, float* x, float* y, float* z, const float* w, int64_t n,
-                            int wrap, cudaStream_t st) {
+                            int wrap, int mas, cudaStream_t st) {
   const int P = ctx->nranks, nzl = ctx->nz_loc;
   const size_t plane = (size_t)ctx->ny * ctx->nx;
   const int next = (ctx->rank + 1) % P, prev = (ctx->rank + P - 1) % P;
@@ -1613,7 +1613,7 @@ static int dist_scatter_tsc(baorec_ctx* ctx, float* loc, float* x, float* y, flo
   float* halo = buf + (size_t)(nzl + 3) * plane;  // two planes of receive space
   BR_CUDA(cudaMemsetAsync(buf, 0, (size_t)(nzl + 3) * plane * sizeof(float), st));
   ctx->slab_mode = 3;
-  int s = scatter(ctx, buf, x, y, z, w, n, wrap, BAOREC_MAS_TSC, st);
+  int s = scatter(ctx, buf, x, y, z, w, n, wrap, mas, st);
   ctx->slab_mode = 0;
   if (s != BAOREC_OK) return s;
   // plane 0 (below the slab) -> previous rank; what arrives from the next rank belongs to our last real plane
@@ -1630,7 +1630,7 @@ static int dist_scatter_tsc(baorec_ctx* ctx, float* loc, float* x, float* y, flo
 // (global plane z_lo + nz_loc) belongs to the next rank: send it, add what arrives from below.
 static int dist_scatter(baorec_ctx* ctx, float* loc, float* x, float* y, float* z, const float* w, int64_t n,
                         int wrap, int mas, cudaStream_t st) {
-  if (mas == BAOREC_MAS_TSC) return dist_scatter_tsc(ctx, loc, x, y, z, w, n, wrap, st);
+  if (mas != BAOREC_MAS_CIC) return dist_scatter_tsc(ctx, loc, x, y, z, w, n, wrap, mas, st);  // TSC and PCS reach the same planes
   const int P = ctx->nranks, nzl = ctx->nz_loc;
   const size_t plane = (size_t)ctx->ny * ctx->nx;
   float* halo;
@@ -1707,7 +1707,7 @@ int baorec_run_dist_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, 
   BR_REQUIRE(n_local >= 0 && (n_local == 0 || (d_x && d_y && d_z && d_w)), "particle arrays");
   BR_REQUIRE(n_ran_local >= 0 && (n_ran_local == 0 || (d_rx && d_ry && d_rz && d_rw)), "randoms arrays");
   BR_REQUIRE(has_randoms || n_ran_local == 0, "randoms passed with has_randoms == 0");
-  BR_REQUIRE(p->mas == BAOREC_MAS_CIC || p->mas == BAOREC_MAS_TSC, "unknown mass-assignment scheme");
+  BR_REQUIRE(p->mas == BAOREC_MAS_CIC || p->mas == BAOREC_MAS_TSC || p->mas == BAOREC_MAS_PCS, "unknown mass-assignment scheme");
   cudaStream_t st = (cudaStream_t)stream;
   const int nzl = ctx->nz_loc;
   const size_t plane = (size_t)ctx->ny * ctx->nx;

@@ -133,11 +133,13 @@ struct OpLosSolve {
   }
   __device__ __forceinline__ float2 solve(float2 v, const Col& c, float kz, double gz_dc, bool is_dc) const {
     float k2 = ksq(c.kx, c.ky, kz);
-    double s = c.gxy * gz_dc;
-    if (is_dc) s = 0.0;
-    float dsx = (float)((double)v.x * s), dsy = (float)((double)v.y * s);
+    // the Gaussian of the three axes and the normalisation multiply in Float64 and are rounded ONCE; the mode is then
+    // scaled in Float32 (FusedLosOp rounds (double) v * s instead: one ulp apart, and four conversions per mode more)
+    float s = (float)(c.gxy * gz_dc);
+    if (is_dc) s = 0.f;
+    float dsx = __fmul_rn(v.x, s), dsy = __fmul_rn(v.y, s);
     float num = __fadd_rn(c.cxy, __fmul_rn(__fmul_rn(kz, kz), los[2]));
-    float mu = k2 > 0.f ? __fdiv_rn(num, k2) : 0.f;
+    float mu = k2 > 0.f ? __fdividef(num, k2) : 0.f;  // 2 ulp; the IEEE division is 12 instructions and a slow-path branch per mode
     float drx = dsx, dry = dsy;
     if (n_iter >= 1) {
       float fm = __fmul_rn(c.fac1, mu);
@@ -286,7 +288,7 @@ fft_z_disp_kernel(const float2* __restrict__ in, float2* __restrict__ o0, float2
         s = op.invM;
       } else {
         float k2 = ksq(kx, ky, kz);
-        s = k2 > 0.f ? __fdiv_rn(op.invM, k2) : 0.f;
+        s = k2 > 0.f ? __fdividef(op.invM, k2) : 0.f;  // MUFU.RCP + FMUL (2 ulp) instead of the ~12-instruction IEEE division
       }
       const float2 d = valid ? v[j] : make_float2(0.f, 0.f);
       // the products of DispOp: re = (-v.y s) k, im = (v.x s) k;  G itself for the shared transform

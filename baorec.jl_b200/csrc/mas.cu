@@ -84,25 +84,26 @@ __device__ __forceinline__ bool gather_one(const GatherArgs& a, const BoxGeom& g
       }
     }
   } else {
-    int ix[3], iy[3], iz[3];
-    float wx[3], wy[3], wz[3];
-    ok = tsc_axis(px, g.mn[0], g.L[0], g.n[0], true, ix, wx);
-    ok = tsc_axis(py, g.mn[1], g.L[1], g.n[1], true, iy, wy) && ok;
-    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], true, iz, wz) && ok;
+    constexpr int SW = MasStencil<MAS>::SW;
+    int ix[4], iy[4], iz[4];
+    float wx[4], wy[4], wz[4];
+    ok = stencil_axis<MAS>(px, g.mn[0], g.L[0], g.n[0], true, ix, wx);
+    ok = stencil_axis<MAS>(py, g.mn[1], g.L[1], g.n[1], true, iy, wy) && ok;
+    ok = stencil_axis<MAS>(pz, g.mn[2], g.L[2], g.n[2], true, iz, wz) && ok;
     if (ok && g.slab) {  // slab layout (multi-GPU): halo planes below / above the slab
 #pragma unroll
-      for (int c = 0; c < 3; c++) ok = local_plane1(g, iz[c], iz[c]) && ok;
+      for (int c = 0; c < SW; c++) ok = local_plane1(g, iz[c], iz[c]) && ok;
     }
     if (ok) {
 #pragma unroll
       for (int c = 0; c < NF; c++) val[c] = 0.f;
 #pragma unroll
-      for (int oz = 0; oz < 3; oz++)
+      for (int oz = 0; oz < SW; oz++)
 #pragma unroll
-        for (int oy = 0; oy < 3; oy++) {
+        for (int oy = 0; oy < SW; oy++) {
           size_t row = ((size_t)iz[oz] * ny + iy[oy]) * nx;
 #pragma unroll
-          for (int ox = 0; ox < 3; ox++)
+          for (int ox = 0; ox < SW; ox++)
 #pragma unroll
             for (int c = 0; c < NF; c++)
               val[c] = __fadd_rn(
@@ -179,17 +180,18 @@ __device__ __forceinline__ int bin_key(float& px, float& py, float& pz, const Bo
     ok = cic_axis(pz, g.mn[2], g.L[2], g.n[2], wrap, i0, i1, w0, w1) && ok;
     ok = ok && local_planes(g, i0, i1, i0, i1);
     zb = i0;
-  } else if (MAS == BAOREC_MAS_TSC) {
-    int idx[3];
-    float w[3];
+  } else if (MAS != BAOREC_MAS_CIC) {
+    constexpr int SW = MasStencil<MAS>::SW;
+    int idx[4];
+    float w[4];
     bool wr = MODE == BIN_GATHER ? true : (wrap != 0);
-    ok = tsc_axis(px, g.mn[0], g.L[0], g.n[0], wr, idx, w);
-    ok = tsc_axis(py, g.mn[1], g.L[1], g.n[1], wr, idx, w) && ok;
-    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], wr, idx, w) && ok;
+    ok = stencil_axis<MAS>(px, g.mn[0], g.L[0], g.n[0], wr, idx, w);
+    ok = stencil_axis<MAS>(py, g.mn[1], g.L[1], g.n[1], wr, idx, w) && ok;
+    ok = stencil_axis<MAS>(pz, g.mn[2], g.L[2], g.n[2], wr, idx, w) && ok;
     zb = idx[1];
-    if (ok && g.slab) {  // bins are planes of the local buffer: the centre plane, provided the whole stencil is local
+    if (ok && g.slab) {  // bins are planes of the local buffer: plane 1 of the stencil, provided the whole stencil is local
       int lo, hi;
-      ok = local_plane1(g, idx[0], lo) && local_plane1(g, idx[2], hi) && local_plane1(g, idx[1], zb);
+      ok = local_plane1(g, idx[0], lo) && local_plane1(g, idx[SW - 1], hi) && local_plane1(g, idx[1], zb);
     }
   } else {
     int id, iu;
@@ -413,18 +415,19 @@ template <int MAS>
 __device__ __forceinline__ unsigned tile_key(float px, float py, float pz, const BoxGeom& g, const TileGeom& t) {
   int ix, iy, iz;
   bool ok;
-  if (MAS == BAOREC_MAS_TSC) {
-    int idx[3];
-    float w[3];
-    ok = tsc_axis(px, g.mn[0], g.L[0], g.n[0], true, idx, w);
+  if (MAS != BAOREC_MAS_CIC) {
+    constexpr int SW = MasStencil<MAS>::SW;
+    int idx[4];
+    float w[4];
+    ok = stencil_axis<MAS>(px, g.mn[0], g.L[0], g.n[0], true, idx, w);
     ix = idx[1];
-    ok = tsc_axis(py, g.mn[1], g.L[1], g.n[1], true, idx, w) && ok;
+    ok = stencil_axis<MAS>(py, g.mn[1], g.L[1], g.n[1], true, idx, w) && ok;
     iy = idx[1];
-    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], true, idx, w) && ok;
+    ok = stencil_axis<MAS>(pz, g.mn[2], g.L[2], g.n[2], true, idx, w) && ok;
     iz = idx[1];
-    if (ok && g.slab) {  // tiles are planes of the local buffer: the centre plane, provided the whole stencil is local
+    if (ok && g.slab) {  // tiles are planes of the local buffer: plane 1 of the stencil, provided the whole stencil is local
       int lo, hi;
-      ok = local_plane1(g, idx[0], lo) && local_plane1(g, idx[2], hi) && local_plane1(g, idx[1], iz);
+      ok = local_plane1(g, idx[0], lo) && local_plane1(g, idx[SW - 1], hi) && local_plane1(g, idx[1], iz);
     }
   } else {
     int iu;
@@ -1051,8 +1054,11 @@ static int bin_particles(baorec_ctx* ctx, float* x, float* y, float* z, const fl
   unsigned grid_c = cdiv((size_t)n, BIN_THREADS * 4);
   if (grid_c > 148 * 8) grid_c = 148 * 8;
   unsigned grid_r = cdiv((size_t)n, BIN_THREADS * BIN_PPT);
-  const bool tsc = mas == BAOREC_MAS_TSC;
-  if (tsc) {
+  const bool tsc = mas != BAOREC_MAS_CIC, pcs = mas == BAOREC_MAS_PCS;  // tsc: a stencil scheme (TSC or PCS)
+  if (pcs) {
+    BR_LAUNCH(ctx, (bin_count_kernel<MODE, BAOREC_MAS_PCS>), grid_c, BIN_THREADS, 0, st, x, y, z, n, g, wrap, zg, nbins,
+              cnt);
+  } else if (tsc) {
     BR_LAUNCH(ctx, (bin_count_kernel<MODE, BAOREC_MAS_TSC>), grid_c, BIN_THREADS, 0, st, x, y, z, n, g, wrap, zg, nbins,
               cnt);
   } else {
@@ -1060,7 +1066,10 @@ static int bin_particles(baorec_ctx* ctx, float* x, float* y, float* z, const fl
               cnt);
   }
   BR_LAUNCH(ctx, bin_scan_kernel, 1, 256, 0, st, cnt, cursor, starts, nbins, ctx->d_oob);
-  if (tsc) {
+  if (pcs) {
+    BR_LAUNCH(ctx, (bin_reorder_kernel<MODE, BAOREC_MAS_PCS>), grid_r, BIN_THREADS, 0, st, x, y, z, w, n, g, wrap, zg,
+              nbins, cursor, rec, ctx->d_oob);
+  } else if (tsc) {
     BR_LAUNCH(ctx, (bin_reorder_kernel<MODE, BAOREC_MAS_TSC>), grid_r, BIN_THREADS, 0, st, x, y, z, w, n, g, wrap, zg,
               nbins, cursor, rec, ctx->d_oob);
   } else {
@@ -1094,14 +1103,16 @@ static int bin_tiles(baorec_ctx* ctx, const float* x, const float* y, const floa
   unsigned* total = sums + nsb;
   BR_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * m, st));
   const unsigned grid = cdiv((size_t)n, 256);
-  const bool tsc = mas == BAOREC_MAS_TSC;
-  if (tsc) BR_LAUNCH(ctx, tile_count_kernel<BAOREC_MAS_TSC>, grid, 256, 0, st, x, y, z, n, g, t, cnt);
+  const bool tsc = mas != BAOREC_MAS_CIC, pcs = mas == BAOREC_MAS_PCS;  // tsc: a stencil scheme (TSC or PCS)
+  if (pcs) BR_LAUNCH(ctx, tile_count_kernel<BAOREC_MAS_PCS>, grid, 256, 0, st, x, y, z, n, g, t, cnt);
+  else if (tsc) BR_LAUNCH(ctx, tile_count_kernel<BAOREC_MAS_TSC>, grid, 256, 0, st, x, y, z, n, g, t, cnt);
   else BR_LAUNCH(ctx, tile_count_kernel<BAOREC_MAS_CIC>, grid, 256, 0, st, x, y, z, n, g, t, cnt);
   BR_LAUNCH(ctx, scan_partial_kernel, nsb, 256, 0, st, cnt, sums, m);
   BR_LAUNCH(ctx, scan_sums_kernel, 1, 32, 0, st, sums, nsb, total);
   BR_LAUNCH(ctx, scan_final_kernel, nsb, 256, 0, st, cnt, sums, cursor, starts, m);
   BR_LAUNCH(ctx, add_oob_kernel, 1, 1, 0, st, cnt + t.ntiles, ctx->d_oob);  // trash-bin size -> out-of-box counter
-  if (tsc) BR_LAUNCH(ctx, tile_reorder_kernel<BAOREC_MAS_TSC>, grid, 256, 0, st, x, y, z, n, g, t, cursor, rec, inv);
+  if (pcs) BR_LAUNCH(ctx, tile_reorder_kernel<BAOREC_MAS_PCS>, grid, 256, 0, st, x, y, z, n, g, t, cursor, rec, inv);
+  else if (tsc) BR_LAUNCH(ctx, tile_reorder_kernel<BAOREC_MAS_TSC>, grid, 256, 0, st, x, y, z, n, g, t, cursor, rec, inv);
   else BR_LAUNCH(ctx, tile_reorder_kernel<BAOREC_MAS_CIC>, grid, 256, 0, st, x, y, z, n, g, t, cursor, rec, inv);
   out->rec = rec;
   out->n_valid = starts + t.ntiles;
@@ -1230,7 +1241,7 @@ int scatter(baorec_ctx* ctx, float* rho, float* x, float* y, float* z, const flo
   }
   if (n == 0) return BAOREC_OK;
   BoxGeom g = geom_of(ctx);
-  const bool tsc = mas == BAOREC_MAS_TSC;
+  const bool tsc = mas != BAOREC_MAS_CIC, pcs = mas == BAOREC_MAS_PCS;  // tsc: a stencil scheme (TSC or PCS)
   if (ctx->opt_det_scatter && !tsc && ctx->slab_mode == 0) {
     // bit-reproducible CIC: 64-bit fixed-point integer reductions, one rounding to Float32 at the end
     unsigned long long* acc;
@@ -1267,7 +1278,8 @@ int scatter(baorec_ctx* ctx, float* rho, float* x, float* y, float* z, const flo
     if (ctx->opt_scatter_tiles && !tsc) BR_TRY(bin_tiles_scatter(ctx, x, y, z, w, n, wrap, st, &b));
     else BR_TRY(bin_particles<BIN_SCATTER>(ctx, x, y, z, w, n, wrap, mas, st, &b));
     unsigned grid = cdiv((size_t)n, 256);
-    if (tsc && ctx->opt_scatter_pairs && ((uintptr_t)rho & 15) == 0)
+    if (pcs) BR_LAUNCH(ctx, scatter_sorted_kernel<BAOREC_MAS_PCS>, grid, 256, 0, st, rho, b.rec, b.n_valid, g, wrap);
+    else if (tsc && ctx->opt_scatter_pairs && ((uintptr_t)rho & 15) == 0)
       BR_LAUNCH(ctx, scatter_sorted_tsc_vec_kernel, grid, 256, 0, st, rho, b.rec, b.n_valid, g, wrap);
     else if (tsc) BR_LAUNCH(ctx, scatter_sorted_kernel<BAOREC_MAS_TSC>, grid, 256, 0, st, rho, b.rec, b.n_valid, g, wrap);
     else if (ctx->opt_scatter_pairs && ((uintptr_t)rho & 15) == 0)
@@ -1276,7 +1288,9 @@ int scatter(baorec_ctx* ctx, float* rho, float* x, float* y, float* z, const flo
     return BAOREC_OK;
   }
   unsigned grid = cdiv((size_t)n, 256);
-  if (tsc) BR_LAUNCH(ctx, scatter_direct_kernel<BAOREC_MAS_TSC>, grid, 256, 0, st, rho, x, y, z, w, n, g, wrap,
+  if (pcs) BR_LAUNCH(ctx, scatter_direct_kernel<BAOREC_MAS_PCS>, grid, 256, 0, st, rho, x, y, z, w, n, g, wrap,
+                     ctx->d_oob);
+  else if (tsc) BR_LAUNCH(ctx, scatter_direct_kernel<BAOREC_MAS_TSC>, grid, 256, 0, st, rho, x, y, z, w, n, g, wrap,
                      ctx->d_oob);
   else BR_LAUNCH(ctx, scatter_direct_kernel<BAOREC_MAS_CIC>, grid, 256, 0, st, rho, x, y, z, w, n, g, wrap,
                  ctx->d_oob);
@@ -1286,7 +1300,7 @@ int scatter(baorec_ctx* ctx, float* rho, float* x, float* y, float* z, const flo
 int gather_prebin(baorec_ctx* ctx, const float* x, const float* y, const float* z, int64_t n, int mas,
                   cudaStream_t st) {
   ctx->prebin_valid = false;
-  if (!ctx->opt_overlap_sort || n == 0 || !use_binning(ctx, n) || !ctx->opt_gather_tiles || mas == BAOREC_MAS_TSC)
+  if (!ctx->opt_overlap_sort || n == 0 || !use_binning(ctx, n) || !ctx->opt_gather_tiles || mas != BAOREC_MAS_CIC)
     return BAOREC_OK;
   if (ctx->sortc_valid && ctx->slab_mode == ctx->sortc_slab_mode && ctx->sortc_x == x && ctx->sortc_y == y &&
       ctx->sortc_z == z && ctx->sortc_n == n)
@@ -1342,7 +1356,7 @@ int gather3(baorec_ctx* ctx, const float* fx, const float* fy, const float* fz, 
   a.fgrowth = f;
   a.sorted_out = nullptr;
   const bool one = (fy == nullptr);
-  const bool tsc = mas == BAOREC_MAS_TSC;
+  const bool tsc = mas != BAOREC_MAS_CIC, pcs = mas == BAOREC_MAS_PCS;  // tsc: a stencil scheme (TSC or PCS)
   if (use_binning(ctx, n)) {
     BinResult b;
     bool reuse = false;
@@ -1413,7 +1427,10 @@ int gather3(baorec_ctx* ctx, const float* fx, const float* fy, const float* fz, 
       BR_LAUNCH(ctx, gather_trash_kernel, cdiv((size_t)n, 256), 256, 0, st, a, b.rec, b.n_valid, n, 1);
     } else {
       unsigned grid = cdiv((size_t)n, 256);
-      if (tsc) {
+      if (pcs) {
+        if (one) BR_LAUNCH(ctx, (gather_sorted_kernel<1, BAOREC_MAS_PCS>), grid, 256, 0, st, a, b.rec, b.n_valid, n, g);
+        else BR_LAUNCH(ctx, (gather_sorted_kernel<3, BAOREC_MAS_PCS>), grid, 256, 0, st, a, b.rec, b.n_valid, n, g);
+      } else if (tsc) {
         if (one) BR_LAUNCH(ctx, (gather_sorted_kernel<1, BAOREC_MAS_TSC>), grid, 256, 0, st, a, b.rec, b.n_valid, n, g);
         else BR_LAUNCH(ctx, (gather_sorted_kernel<3, BAOREC_MAS_TSC>), grid, 256, 0, st, a, b.rec, b.n_valid, n, g);
       } else {
@@ -1424,7 +1441,10 @@ int gather3(baorec_ctx* ctx, const float* fx, const float* fy, const float* fz, 
     return BAOREC_OK;
   }
   unsigned grid = cdiv((size_t)n, 256);
-  if (tsc) {
+  if (pcs) {
+    if (one) BR_LAUNCH(ctx, (gather_direct_kernel<1, BAOREC_MAS_PCS>), grid, 256, 0, st, a, g, ctx->d_oob);
+    else BR_LAUNCH(ctx, (gather_direct_kernel<3, BAOREC_MAS_PCS>), grid, 256, 0, st, a, g, ctx->d_oob);
+  } else if (tsc) {
     if (one) BR_LAUNCH(ctx, (gather_direct_kernel<1, BAOREC_MAS_TSC>), grid, 256, 0, st, a, g, ctx->d_oob);
     else BR_LAUNCH(ctx, (gather_direct_kernel<3, BAOREC_MAS_TSC>), grid, 256, 0, st, a, g, ctx->d_oob);
   } else {
@@ -1634,7 +1654,7 @@ int baorec_cic_scatter_f32(baorec_ctx* ctx, float* d_rho, float* d_x, float* d_y
   BR_NEED_PLAN(ctx);
   BR_REQUIRE(n >= 0, "n < 0");
   BR_REQUIRE(n == 0 || (d_rho && d_x && d_y && d_z && d_w), "NULL device pointer");
-  BR_REQUIRE(mas == BAOREC_MAS_CIC || mas == BAOREC_MAS_TSC, "unknown mas");
+  BR_REQUIRE(mas == BAOREC_MAS_CIC || mas == BAOREC_MAS_TSC || mas == BAOREC_MAS_PCS, "unknown mas");
   cudaStream_t st = (cudaStream_t)stream;
   BR_TRY(reset_oob(ctx, st));
   BR_TRY(scatter(ctx, d_rho, d_x, d_y, d_z, d_w, n, wrap, mas, st));

@@ -93,6 +93,50 @@ __device__ __forceinline__ bool tsc_axis(float p, float mn, float L, int n, bool
   return true;
 }
 
+// ---- PCS (extension, SURVEY.md 8f N3: the piecewise cubic spline of the power-spectrum tool the reference's helpers
+// configure, test_helpers/powspec_auto.conf:117-124).  The coordinate is cic!'s: g = (p - min) n / L + 1, base point
+// c = floor(g) - 1, t = g - floor(g) (cic!'s upper weight), u = 1 - t; the four points c-1 .. c+2 carry the cubic
+// B-spline u^3/6, ((3t-6)t^2+4)/6, ((3u-6)u^2+4)/6, t^3/6 -- every operation rounded to Float32 in the order written,
+// as in the CPU restatement the parity tests compare with.  A particle owned by a slab (owner = slab of cic!'s base
+// plane, the same cell) reaches the same planes as TSC does: one below the slab to two above it.
+__device__ __forceinline__ bool pcs_axis(float p, float mn, float L, int n, bool wrap, int idx[4], float w[4]) {
+  float g = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(p, mn), (float)n), L), 1.0f);  // cic!'s 1-based coordinate
+  if (!(g >= 0.0f && g <= (float)(n + 2))) return false;
+  float c = floorf(g);
+  float t = __fsub_rn(g, c), u = __fsub_rn(1.0f, t);
+  c = c - 1.0f;  // 0-based base point: the cell cic! deposits into, last bit included
+  float t2 = __fmul_rn(t, t), u2 = __fmul_rn(u, u);
+  w[0] = __fdiv_rn(__fmul_rn(u2, u), 6.0f);
+  w[1] = __fdiv_rn(__fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(3.0f, t), 6.0f), t2), 4.0f), 6.0f);
+  w[2] = __fdiv_rn(__fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(3.0f, u), 6.0f), u2), 4.0f), 6.0f);
+  w[3] = __fdiv_rn(__fmul_rn(t2, t), 6.0f);
+  int ic = (int)c;
+#pragma unroll
+  for (int o = 0; o < 4; o++) {
+    int i = ic + o - 1;
+    if (wrap) {
+      i = i < 0 ? i + n : (i >= n ? i - n : i);
+      if (i < 0 || i >= n) return false;
+    } else if (i < 0 || i >= n) {
+      return false;
+    }
+    idx[o] = i;
+  }
+  return true;
+}
+
+// The stencil schemes behind one interface: SW points per axis (arrays are sized for the widest), point 1 is the one
+// the sorts key on (TSC: the nearest grid point; PCS: the base point floor(g)).
+template <int MAS>
+struct MasStencil {
+  static constexpr int SW = MAS == BAOREC_MAS_PCS ? 4 : 3;
+};
+template <int MAS>
+__device__ __forceinline__ bool stencil_axis(float p, float mn, float L, int n, bool wrap, int idx[4], float w[4]) {
+  if (MAS == BAOREC_MAS_PCS) return pcs_axis(p, mn, L, n, wrap, idx, w);
+  return tsc_axis(p, mn, L, n, wrap, idx, w);
+}
+
 // Global plane indices (lower, upper-wrapped) -> plane indices in the local buffer.
 __device__ __forceinline__ bool local_planes(const BoxGeom& g, int z0, int z1, int& l0, int& l1) {
   if (!g.slab) {
@@ -155,24 +199,25 @@ __device__ __forceinline__ bool deposit(float* __restrict__ rho, float px, float
     atomicAdd(rho + r11 + x1, __fmul_rn(a11, wz1));
     return true;
   } else {
-    int ix[3], iy[3], iz[3];
-    float wx[3], wy[3], wz[3];
-    bool ok = tsc_axis(px, g.mn[0], g.L[0], g.n[0], wrap, ix, wx);
-    ok = tsc_axis(py, g.mn[1], g.L[1], g.n[1], wrap, iy, wy) && ok;
-    ok = tsc_axis(pz, g.mn[2], g.L[2], g.n[2], wrap, iz, wz) && ok;
+    constexpr int SW = MasStencil<MAS>::SW;
+    int ix[4], iy[4], iz[4];
+    float wx[4], wy[4], wz[4];
+    bool ok = stencil_axis<MAS>(px, g.mn[0], g.L[0], g.n[0], wrap, ix, wx);
+    ok = stencil_axis<MAS>(py, g.mn[1], g.L[1], g.n[1], wrap, iy, wy) && ok;
+    ok = stencil_axis<MAS>(pz, g.mn[2], g.L[2], g.n[2], wrap, iz, wz) && ok;
     if (!ok) return false;
-    if (g.slab) {  // slab layout (multi-GPU): the three stencil planes in the local (nz_loc + 3)-plane buffer
+    if (g.slab) {  // slab layout (multi-GPU): the stencil planes in the local (nz_loc + 3)-plane buffer
 #pragma unroll
-      for (int c = 0; c < 3; c++) ok = local_plane1(g, iz[c], iz[c]) && ok;
+      for (int c = 0; c < SW; c++) ok = local_plane1(g, iz[c], iz[c]) && ok;
       if (!ok) return false;
     }
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
+    for (int c = 0; c < SW; c++) {
 #pragma unroll
-      for (int b = 0; b < 3; b++) {
+      for (int b = 0; b < SW; b++) {
         size_t row = ((size_t)iz[c] * ny + iy[b]) * nx;
 #pragma unroll
-        for (int a = 0; a < 3; a++) {
+        for (int a = 0; a < SW; a++) {
           float v = __fmul_rn(__fmul_rn(__fmul_rn(wx[a], ww), wy[b]), wz[c]);
           atomicAdd(rho + row + ix[a], v);
         }

@@ -296,6 +296,11 @@ def _plan_for(mesh, box_size, box_min) -> Context:
     return Context.get(mesh.device.index).plan(gs, box_size, box_min)
 
 
+def _plan_grid(device_index, grid_size_xyz, box_size, box_min) -> Context:
+    return Context.get(device_index).plan(grid_size_xyz, np.broadcast_to(np.asarray(box_size, np.float32), 3),
+                                          np.broadcast_to(np.asarray(box_min, np.float32), 3))
+
+
 def smooth(field, smoothing_radius, box_size, fft_plan=None, box_min=(0.0, 0.0, 0.0)):
     """smooth! src/utils.jl:85-96."""
     ctx = _plan_for(field, box_size, box_min)

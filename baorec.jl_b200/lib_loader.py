@@ -13,11 +13,11 @@ LIB_PATH = HERE / "lib" / "libbaorec_b200.so"
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_CUFFT, ERR_NCCL, ERR_OUT_OF_BOX, ERR_NOT_PLANNED, ERR_NOMEM, ERR_OUT_OF_RANGE = -1, -2, -3, -4, -5, -6, -7, -8
-MAS_CIC, MAS_TSC = 0, 1
+MAS_CIC, MAS_TSC, MAS_PCS = 0, 1, 2
 FIELD_DISP, FIELD_RSD, FIELD_SUM = 0, 1, 2
 ITERATIVE, MULTIGRID = 0, 1
 FIELDS = {"disp": FIELD_DISP, "rsd": FIELD_RSD, "sum": FIELD_SUM}
-MAS = {"cic": MAS_CIC, "tsc": MAS_TSC}
+MAS = {"cic": MAS_CIC, "tsc": MAS_TSC, "pcs": MAS_PCS}
 
 
 class BaorecError(RuntimeError):
@@ -120,6 +120,9 @@ SIGNATURES = {
     "baorec_fkp_weights_f32": [_vp, _vp, _i64, _f, _vp, _vp],
     "baorec_wrap_positions_f32": [_vp, _vp, _vp, _vp, _i64, _f3, _f3, _vp],
     "baorec_power_multipoles_f32": [_vp, _vp, _vp, _f3, C.c_double, C.c_double, _i, _i, C.c_double] + [C.POINTER(C.c_double)] * 5 + [_vp],
+    "baorec_power_multipoles_interlaced_f32": [_vp, _vp, _vp, _vp, _vp, _f3, C.c_double, C.c_double, _i, _i, C.c_double] + [C.POINTER(C.c_double)] * 5 + [_vp],
+    "baorec_interlace_positions_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
+    "baorec_compute_auto_box_f32": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _f3, C.c_double, C.c_double, _i, C.c_double] + [C.POINTER(C.c_double)] * 5 + [_vp],
     "baorec_host_alloc": [C.POINTER(_vp), _i64],
     "baorec_host_free": [_vp],
 }

@@ -50,7 +50,7 @@ enum {
                                   Interpolations.jl BoundsError) */
 };
 
-enum { BAOREC_MAS_CIC = 0, BAOREC_MAS_TSC = 1 };             /* TSC is an extension */
+enum { BAOREC_MAS_CIC = 0, BAOREC_MAS_TSC = 1, BAOREC_MAS_PCS = 2 };  /* TSC and PCS are extensions */
 enum { BAOREC_FIELD_DISP = 0, BAOREC_FIELD_RSD = 1, BAOREC_FIELD_SUM = 2 }; /* :disp :rsd :sum */
 enum { BAOREC_ITERATIVE = 0, BAOREC_MULTIGRID = 1 };
 
@@ -408,7 +408,7 @@ int baorec_wrap_positions_f32(baorec_ctx* ctx, float* d_x, float* d_y, float* d_
  *   d_rho: density mesh from baorec_cic_scatter_f32 on this context's grid (any normalisation; not modified);
  *   d_ran: NULL, or the density mesh of a (shifted) random catalog: the field is then rho/sum(rho) - ran/sum(ran),
  *          "data minus shifted randoms" (compute_auto_box_rand, test_helpers/simulation.py:52-70: RecIso / RecSym);
- *   P(k) = V |rho_k|^2 / rho_0^2 / W(k)^2, W = prod_a sinc(k_a h_a / 2)^mas_power (2 = CIC, 3 = TSC, 0 = none);
+ *   P(k) = V |rho_k|^2 / rho_0^2 / W(k)^2, W = prod_a sinc(k_a h_a / 2)^mas_power (2 = CIC, 3 = TSC, 4 = PCS, 0 = none);
  *   P_l(bin i) = (2l+1) <P L_l(mu)> over the modes with kmin + i dk <= |k| < kmin + (i+1) dk, mu = k.los/|k|,
  *   every mode of the Hermitian mesh counted once, k = 0 excluded; `shot` is subtracted from the monopole.
  * One R2C per mesh + one pass over the half mesh (Float64 sums).  Outputs are HOST arrays of nbins doubles (mean k of the
@@ -416,6 +416,31 @@ int baorec_wrap_positions_f32(baorec_ctx* ctx, float* d_x, float* d_y, float* d_
 int baorec_power_multipoles_f32(baorec_ctx* ctx, const float* d_rho, const float* d_ran, const float los[3], double kmin,
                                 double dk, int nbins, int mas_power, double shot, double* h_k, double* h_nmodes, double* h_p0,
                                 double* h_p2, double* h_p4, baorec_stream stream);
+
+/* The same estimator with interlacing (Sefusatti et al. 2016; GRID_INTERLACE = T in the reference's helper configuration,
+ * test_helpers/powspec_auto.conf:125): d_rho_shifted (d_ran_shifted) is the mesh of the same catalog painted half a cell
+ * further along every axis (baorec_interlace_positions_f32); the two transforms are combined per mode as
+ * [f1 + f2 exp(i (k_x h_x + k_y h_y + k_z h_z) / 2)] / 2, which cancels the aliasing images k + 2 k_N m with
+ * m_x + m_y + m_z odd.  mas_power: 2 = CIC, 3 = TSC, 4 = PCS.  Two R2C transforms + one pass over both half meshes. */
+int baorec_power_multipoles_interlaced_f32(baorec_ctx* ctx, const float* d_rho, const float* d_ran, const float* d_rho_shifted,
+                                           const float* d_ran_shifted, const float los[3], double kmin, double dk, int nbins,
+                                           int mas_power, double shot, double* h_k, double* h_nmodes, double* h_p0,
+                                           double* h_p2, double* h_p4, baorec_stream stream);
+
+/* Positions of the interlaced mesh on this context's grid: q = p + (L/n)/2 per axis in Float32, minus L where
+ * q - min >= L.  Output arrays may not alias the inputs. */
+int baorec_interlace_positions_f32(baorec_ctx* ctx, const float* d_x, const float* d_y, const float* d_z, int64_t n, float* d_ox,
+                                   float* d_oy, float* d_oz, baorec_stream stream);
+
+/* compute_auto_box / compute_auto_box_rand of the reference's helpers (test_helpers/simulation.py:36-70, settings of
+ * test_helpers/powspec_auto.conf: TSC + interlacing on a 512^3 grid) in one call on this context's grid and box: paint
+ * the catalog (mas = BAOREC_MAS_CIC / TSC / PCS, periodic; the caller's arrays are not modified), optionally the
+ * randoms (nr > 0: the field is data/sum - randoms/sum, "data minus shifted randoms") and the interlaced meshes
+ * (interlace != 0), then the multipoles as above with the window exponent of the scheme. */
+int baorec_compute_auto_box_f32(baorec_ctx* ctx, const float* d_x, const float* d_y, const float* d_z, const float* d_w, int64_t n,
+                                const float* d_rx, const float* d_ry, const float* d_rz, const float* d_rw, int64_t nr, int mas,
+                                int interlace, const float los[3], double kmin, double dk, int nbins, double shot, double* h_k,
+                                double* h_nmodes, double* h_p0, double* h_p2, double* h_p4, baorec_stream stream);
 
 /* Pinned host memory helpers for callers without their own (Julia: CUDA.Mem.alloc(HostBuffer)). */
 int baorec_host_alloc(void** out, int64_t bytes);

@@ -336,9 +336,12 @@ def read_tsc(fld, x, y, z, box_size, box_min, wrap=True):
 
 # PCS (piecewise cubic spline; SURVEY.md section 8f N3 -- the fourth assignment scheme of the power-spectrum tool the
 # reference's helpers configure, test_helpers/powspec_auto.conf:117-124; not in src/mas.jl).  Same grid convention as
-# cic! / tsc: mesh points at min + i * cell.  c = floor(g), t = g - c, u = 1 - t; the four points c-1 .. c+2 carry the
-# cubic B-spline  w(-1) = u^3/6,  w(0) = ((3t - 6) t^2 + 4)/6,  w(+1) = ((3u - 6) u^2 + 4)/6,  w(+2) = t^3/6,
-# every operation rounded to T in the order written (the device kernels spell out the same sequence).
+# cic! / tsc: mesh points at min + i * cell.  The coordinate is cic!'s own (src/mas.jl:13-19): g = (p - min) n / L + 1
+# (1-based), c = floor(g) - 1 the 0-based base point, t = g - floor(g) -- cic!'s upper weight, so the base point of a
+# particle is the same cell under both schemes, last bit included (the slab decomposition assigns particles by that
+# cell).  u = 1 - t; the four points c-1 .. c+2 carry the cubic B-spline  w(-1) = u^3/6,  w(0) = ((3t - 6) t^2 + 4)/6,
+# w(+1) = ((3u - 6) u^2 + 4)/6,  w(+2) = t^3/6, every operation rounded to T in the order written (the device kernels
+# spell out the same sequence).
 def pcs_cells(x, y, z, n_xyz, box_size, box_min, wrap=True):
     """Returns (c[3][N] 0-based *unwrapped* floor index, [w(-1), w(0), w(+1), w(+2)] per axis)."""
     T = _T(x)
@@ -348,9 +351,10 @@ def pcs_cells(x, y, z, n_xyz, box_size, box_min, wrap=True):
     for a, p in enumerate((x, y, z)):
         n = int(n_xyz[a])
         p = np.asarray(p, dtype=T)
-        g = (((p - mn[a]).astype(T) * T(n)).astype(T) / L[a]).astype(T)
-        c = np.floor(g)
-        t = (g - c).astype(T)
+        g = ((((p - mn[a]).astype(T) * T(n)).astype(T) / L[a]).astype(T) + T(1)).astype(T)
+        f0 = np.floor(g)
+        c = f0 - 1
+        t = (g - f0).astype(T)
         u = (T(1) - t).astype(T)
         t2 = (t * t).astype(T)
         u2 = (u * u).astype(T)

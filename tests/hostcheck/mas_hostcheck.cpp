@@ -98,6 +98,8 @@ int64_t hc_deposit(int mas, float* buf, const float* x, const float* y, const fl
         pz = wrap_pos(pz, g.mn[0], g.L[0]);
       }
       ok = deposit<BAOREC_MAS_CIC>(buf, px, py, pz, w[i], g, wrap != 0);
+    } else if (mas == BAOREC_MAS_PCS) {
+      ok = deposit<BAOREC_MAS_PCS>(buf, px, py, pz, w[i], g, wrap != 0);
     } else {
       ok = deposit<BAOREC_MAS_TSC>(buf, px, py, pz, w[i], g, wrap != 0);
     }
@@ -164,6 +166,57 @@ int64_t hc_tsc_gather(const float* buf, const float* x, const float* y, const fl
         for (int oy = 0; oy < 3; oy++) {
           const size_t row = ((size_t)iz[oz] * ny + iy[oy]) * nx;
           for (int ox = 0; ox < 3; ox++)
+            val = __fadd_rn(val, __fmul_rn(__fmul_rn(__fmul_rn(buf[row + ix[ox]], wx[ox]), wy[oy]), wz[oz]));
+        }
+    } else {
+      bad++;
+    }
+    out[i] = val;
+  }
+  return bad;
+}
+
+// idx / w are [3 axes][4 stencil points][n]
+void hc_pcs_cells(const float* x, const float* y, const float* z, int64_t n, const int* ng, const float* L, const float* mn, int wrap,
+                  int32_t* idx, float* w, int32_t* ok) {
+  const float* p[3] = {x, y, z};
+  for (int64_t i = 0; i < n; i++) {
+    int good = 1;
+    for (int a = 0; a < 3; a++) {
+      int id4[4] = {-1, -1, -1, -1};
+      float w4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!pcs_axis(p[a][i], mn[a], L[a], ng[a], wrap != 0, id4, w4)) good = 0;
+      for (int o = 0; o < 4; o++) {
+        idx[(a * 4 + o) * n + i] = id4[o];
+        w[(a * 4 + o) * n + i] = w4[o];
+      }
+    }
+    ok[i] = good;
+  }
+}
+
+// PCS gather (whole mesh or a halo'd slab buffer, slab_mode 2: zoff = 1, nzp = nz_loc + 3): the loop of
+// gather_one<1, PCS> in mas.cu with the product's stencil_axis and local_plane1.  Returns the rejected count.
+int64_t hc_pcs_gather(const float* buf, const float* x, const float* y, const float* z, int64_t n, const int* ng, const float* L,
+                      const float* mn, int slab, int z_lo, int zoff, int nzp, float* out) {
+  const BoxGeom g = make_geom(ng, L, mn, slab, z_lo, zoff, nzp);
+  const size_t nx = g.n[0], ny = g.n[1];
+  constexpr int SW = MasStencil<BAOREC_MAS_PCS>::SW;
+  int64_t bad = 0;
+  for (int64_t i = 0; i < n; i++) {
+    int ix[4], iy[4], iz[4];
+    float wx[4], wy[4], wz[4];
+    bool ok = stencil_axis<BAOREC_MAS_PCS>(x[i], g.mn[0], g.L[0], g.n[0], true, ix, wx);
+    ok = stencil_axis<BAOREC_MAS_PCS>(y[i], g.mn[1], g.L[1], g.n[1], true, iy, wy) && ok;
+    ok = stencil_axis<BAOREC_MAS_PCS>(z[i], g.mn[2], g.L[2], g.n[2], true, iz, wz) && ok;
+    if (ok && g.slab)
+      for (int c = 0; c < SW; c++) ok = local_plane1(g, iz[c], iz[c]) && ok;
+    float val = 0.f;
+    if (ok) {
+      for (int oz = 0; oz < SW; oz++)
+        for (int oy = 0; oy < SW; oy++) {
+          const size_t row = ((size_t)iz[oz] * ny + iy[oy]) * nx;
+          for (int ox = 0; ox < SW; ox++)
             val = __fadd_rn(val, __fmul_rn(__fmul_rn(__fmul_rn(buf[row + ix[ox]], wx[ox]), wy[oy]), wz[oz]));
         }
     } else {

@@ -131,18 +131,36 @@ def test_read_cic_bit_exact(B, O, n, L, lo):
     assert np.array_equal(out.cpu().numpy().view(np.uint32), ref.view(np.uint32))
 
 
-def test_tsc_scatter_gather(B, O):
-    n, L, N = 48, 500.0, 100_000
+@pytest.mark.parametrize("mas", ["tsc", "pcs"])
+@pytest.mark.parametrize("N", [100_000, 400_000])                             # catalog-order kernels / z-binned kernels
+def test_stencil_scatter_gather(B, O, mas, N):
+    """TSC (27 cells) and PCS (64 cells, the cubic B-spline): the mesh agrees with the oracle's to the order
+    of the Float32 additions, the gather is bit-identical (same cells, same weights, same order)."""
+    n, L = 48, 500.0
     pos, w = clustered_box(N, L, seed=3)
     bs, bm = np.full(3, L, np.float32), np.zeros(3, np.float32)
-    orho = O.tsc_scatter(np.zeros((n, n, n), np.float32), *pos, w, bs, bm, True)
+    scatter, read = (O.tsc_scatter, O.read_tsc) if mas == "tsc" else (O.pcs_scatter, O.read_pcs)
+    orho = scatter(np.zeros((n, n, n), np.float32), *pos, w, bs, bm, True)
     rho = torch.zeros((n, n, n), dtype=torch.float32, device="cuda")
-    B.cic(rho, *(dev(p) for p in pos), dev(w), bs, bm, wrap=True, mas="tsc")
+    B.cic(rho, *(dev(p) for p in pos), dev(w), bs, bm, wrap=True, mas=mas)
     assert maxabs(rho.cpu().numpy(), orho) <= 2e-5 * float(orho.max())
+    assert abs(float(rho.sum(dtype=torch.float64)) / float(w.sum(dtype=np.float64)) - 1) < 2e-6
     fld = np.random.default_rng(1).standard_normal((n, n, n)).astype(np.float32)
-    ref = O.read_tsc(fld, *pos, bs, bm)
+    ref = read(fld, *pos, bs, bm)
     out = torch.empty(N, dtype=torch.float32, device="cuda")
-    B.read_cic(out, dev(fld), *(dev(p) for p in pos), bs, bm, mas="tsc")
+    B.read_cic(out, dev(fld), *(dev(p) for p in pos), bs, bm, mas=mas)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+
+
+def test_pcs_cells_at_the_edges(B, O):
+    """PCS gather at the faces and cell boundaries of the box (edge_positions): bit-identical to the oracle."""
+    n, L, lo = 48, 500.0, -120.5
+    x, y, z = (edge_positions(L, lo, n, s) for s in (16, 17, 18))
+    bs, bm = np.full(3, L, np.float32), np.full(3, lo, np.float32)
+    fld = np.random.default_rng(2).standard_normal((n, n, n)).astype(np.float32)
+    ref = O.read_pcs(fld, x, y, z, bs, bm)
+    out = torch.empty(len(x), dtype=torch.float32, device="cuda")
+    B.read_cic(out, dev(fld), dev(x), dev(y), dev(z), bs, bm, mas="pcs")
     assert np.array_equal(out.cpu().numpy().view(np.uint32), ref.view(np.uint32))
 
 

@@ -181,3 +181,75 @@ def test_lightcone_mode_removes_a_radial_kaiser_quadrupole_on_the_device(B, algo
     r_new = multipoles(np.stack([new[i].cpu().numpy().astype(np.float64) + obs[i] for i in range(3)], 1))
     assert abs(q(r_new) - q(r_real)) < 0.1
     assert abs(r_new["p0"][b] / r_real["p0"][b] - 1) < 0.1
+
+
+# ---- interlacing, PCS, compute_auto_box -----------------------------------------------------------
+@pytest.mark.parametrize("shape,L,lo,mas", [((48, 40, 56), (300.0, 250.0, 350.0), -20.0, "pcs"), ((64, 64, 64), 500.0, 0.0, "tsc")])
+def test_interlaced_estimate_matches_the_oracle(B, O, shape, L, lo, mas):
+    """interlace_positions bit for bit; the interlaced multipoles of the device meshes against the oracle's combination
+    of the same two meshes (with and without a randoms pair)."""
+    nx, ny, nz = shape
+    bs, bm = np.broadcast_to(np.asarray(L, f32), 3).copy(), np.full(3, lo, f32)
+    rng = np.random.default_rng(4)
+    N = 300_000
+    pos = [(bm[a] + bs[a] * rng.random(N)).astype(f32) for a in range(3)]
+    for a in range(3):                                                         # the last half cell wraps; so does the upper face
+        pos[a][:3] = [bm[a], np.nextafter(f32(bm[a] + bs[a]), f32(0)), bm[a] + bs[a] * (1 - 0.25 / shape[a])]
+    w = (0.5 + rng.random(N)).astype(f32)
+    rp = [(bm[a] + bs[a] * rng.random(N)).astype(f32) for a in range(3)]
+    ones = np.ones(N, f32)
+    dpos, drp = [dev(p) for p in pos], [dev(p) for p in rp]
+    sh = B.interlace_positions(*dpos, shape, bs, bm)
+    osh = PK.interlace_positions(*pos, shape, bs, bm)
+    for g, o in zip(sh, osh):
+        assert np.array_equal(g.cpu().numpy().view(np.uint32), o.view(np.uint32))
+    rsh = B.interlace_positions(*drp, shape, bs, bm)
+
+    def paint(p, ww):
+        m = torch.zeros((nz, ny, nx), dtype=torch.float32, device="cuda")
+        B.cic(m, *(q.clone() for q in p), dev(ww), bs, bm, wrap=True, mas=mas)
+        return m
+    m1, m2, r1, r2 = paint(dpos, w), paint(sh, w), paint(drp, ones), paint(rsh, ones)
+    kf = 2 * np.pi / float(bs.max())
+    for rand in (False, True):
+        kw = dict(los=(0.2, -0.4, 0.9), kmin=0.0, dk=kf, nbins=24, shot=0.0)
+        ref = PK.power_multipoles(m1.cpu().numpy(), bs, mas_power=PK.MAS_POWER[mas], rho_shifted=m2.cpu().numpy(),
+                                  randoms=r1.cpu().numpy() if rand else None, randoms_shifted=r2.cpu().numpy() if rand else None, **kw)
+        got = B.power_multipoles(m1, bs, mas=mas, box_min=bm, rho_shifted=m2, randoms=r1 if rand else None,
+                                 randoms_shifted=r2 if rand else None, **kw)
+        ok = ref["nmodes"] > 0
+        assert np.array_equal(got["nmodes"], ref["nmodes"])
+        scale = float(np.abs(ref["p0"][ok]).max())
+        for key in ("p0", "p2", "p4"):
+            assert np.abs(got[key][ok] - ref[key][ok]).max() <= 1e-5 * scale
+
+
+@pytest.mark.parametrize("mas,interlace,rand", [("tsc", True, False), ("pcs", True, True), ("cic", False, False), ("pcs", False, True)])
+def test_compute_auto_box_matches_the_oracle(B, O, mas, interlace, rand):
+    """The one-call mirror of the reference helpers' compute_auto_box / compute_auto_box_rand (paint + interlace +
+    transform + bin) against the oracle's; the catalogs are left untouched.  The meshes differ by the order of the
+    Float32 additions of the scatter, the spectra by 1e-5 of the largest bin."""
+    grid, L, N = (64, 48, 56), np.asarray([500.0, 400.0, 450.0], f32), 400_000
+    rng = np.random.default_rng(9)
+    pos = [(L[a] * rng.random(N)).astype(f32) for a in range(3)]
+    pos[0] += (10.0 * np.sin(2 * np.pi * 3 * pos[0] / L[0])).astype(f32)       # some power above the shot noise
+    pos[0] = np.mod(pos[0], L[0]).astype(f32)
+    w = (0.5 + rng.random(N)).astype(f32)
+    rp = [(L[a] * rng.random(N // 2)).astype(f32) for a in range(3)]
+    rw = np.ones(N // 2, f32)
+    d = [dev(p) for p in pos] + [dev(w)]
+    r = [dev(p) for p in rp] + [dev(rw)]
+    keep = [t.clone() for t in d]
+    kf = 2 * np.pi / float(L.max())
+    kw = dict(mas=mas, interlace=interlace, los=(0.0, 0.0, 1.0), kmin=0.0, dk=kf, nbins=20, shot=0.0)
+    got = B.compute_auto_box(*d, L, grid, rand_x=r[0] if rand else None, rand_y=r[1] if rand else None, rand_z=r[2] if rand else None,
+                             rand_w=r[3] if rand else None, **kw)
+    ref = PK.compute_auto_box(*pos, w, L, grid, rx=rp[0] if rand else None, ry=rp[1] if rand else None, rz=rp[2] if rand else None,
+                              rw=rw if rand else None, **kw)
+    ok = ref["nmodes"] > 0
+    assert np.array_equal(got["nmodes"], ref["nmodes"])
+    scale = float(np.abs(ref["p0"][ok]).max())
+    for key in ("p0", "p2", "p4"):
+        assert np.abs(got[key][ok] - ref[key][ok]).max() <= 2e-5 * scale
+    for a, b in zip(d, keep):
+        assert torch.equal(a, b)

@@ -48,6 +48,10 @@ def HC():
     lib.hc_deposit.argtypes = [i, _F, _F, _F, _F, _F, i64, _I, _F, _F, i, i, i, i, i]
     lib.hc_tsc_gather.restype = i64
     lib.hc_tsc_gather.argtypes = [_F, _F, _F, _F, i64, _I, _F, _F, i, i, i, i, _F]
+    lib.hc_pcs_cells.restype = None
+    lib.hc_pcs_cells.argtypes = [_F, _F, _F, i64, _I, _F, _F, i, _I, _F, _I]
+    lib.hc_pcs_gather.restype = i64
+    lib.hc_pcs_gather.argtypes = [_F, _F, _F, _F, i64, _I, _F, _F, i, i, i, i, _F]
     lib.hc_deposit_pairs.restype = i64
     lib.hc_deposit_pairs.argtypes = [i, _F, _F, _F, _F, _F, i64, _I, _F, _F, i, C.POINTER(i64)]
     lib.hc_deposit_tsc_vec.restype = i64
@@ -141,11 +145,30 @@ def test_tsc_cells_bit_exact(HC, n, L, lo):
         assert np.abs(w[a].sum(axis=0) - 1).max() < 3e-7                      # partition of unity
 
 
+@pytest.mark.parametrize("n,L,lo", [(48, 500.0, 0.0), (96, 1373.5, -412.25)])
+def test_pcs_cells_bit_exact(HC, n, L, lo):
+    """pcs_axis (csrc/mas_math.cuh) against the oracle's pcs_cells: the four indices and the four cubic B-spline weights
+    of every axis, bit for bit, at the faces, the cell boundaries and inside the cells."""
+    x, y, z = (edge_positions(L, lo, n, s) for s in (13, 14, 15))
+    bs, bm = np.full(3, L, f32), np.full(3, lo, f32)
+    N = len(x)
+    ic, W = O.pcs_cells(x, y, z, (n, n, n), bs, bm, True)
+    idx, w, ok = np.empty((3, 4, N), np.int32), np.empty((3, 4, N), f32), np.empty(N, np.int32)
+    HC.hc_pcs_cells(fp(x), fp(y), fp(z), N, ip(np.full(3, n, np.int32)), fp(bs), fp(bm), 1, ip(idx), fp(w), ip(ok))
+    assert ok.all()
+    for a in range(3):
+        for o in range(4):
+            assert np.array_equal(idx[a, o], np.mod(ic[a] + o - 1, n).astype(np.int32))
+            assert np.array_equal(u32(w[a, o]), u32(W[a][o]))
+        assert np.abs(w[a].sum(axis=0) - 1).max() < 4e-7                      # partition of unity
+        assert (w[a] >= 0).all()
+
+
 # ---- the slab-decomposed (multi-GPU) scatter / gather schemes, emulated rank by rank on the CPU -------------------
 # Each "rank" runs the product's own deposit<MAS> / tsc_axis / local_plane(s) on its particles into a local buffer
 # with ghost planes; numpy then performs the boundary-cell exchange exactly as dist.cu's dist_scatter /
 # dist_scatter_tsc do (ring_exchange + add_plane), and the assembled mesh must be the oracle's global one.
-CIC, TSC = 0, 1
+CIC, TSC, PCS = 0, 1, 2
 
 
 def shard(B, pos, w, lo, L, nz, P):
@@ -168,7 +191,7 @@ def slab_catalog(n, L, lo, seed, wrap):
 
 
 @pytest.mark.parametrize("P", [1, 2, 4, 8])
-@pytest.mark.parametrize("mas,wrap", [(CIC, True), (TSC, True), (TSC, False), (CIC, False)])
+@pytest.mark.parametrize("mas,wrap", [(CIC, True), (TSC, True), (TSC, False), (CIC, False), (PCS, True), (PCS, False)])
 def test_slab_scatter_scheme_reassembles_the_global_mesh(HC, B, P, mas, wrap):
     n = (12, 10, 16)                                   # (nx, ny, nz); nz divisible by every P with >= 2 planes per rank
     L, lo = f32([300.0, 250.0, 400.0]), -50.0
@@ -180,6 +203,8 @@ def test_slab_scatter_scheme_reassembles_the_global_mesh(HC, B, P, mas, wrap):
     ref = np.zeros((n[2], n[1], n[0]), f32)
     if mas == CIC:
         O.cic_scatter(ref, *[p.copy() for p in pos], w, bs, bm, wrap)
+    elif mas == PCS:
+        O.pcs_scatter(ref, *[p.copy() for p in pos], w, bs, bm, wrap)                 # PCS reaches the same planes as TSC: same layout, same exchange
     else:
         O.tsc_scatter(ref, *[p.copy() for p in pos], w, bs, bm, wrap)
     nzl, plane = n[2] // P, n[1] * n[0]
@@ -203,7 +228,7 @@ def test_slab_scatter_scheme_reassembles_the_global_mesh(HC, B, P, mas, wrap):
             out[r][1:3] += bufs[prv][nzl + 1:nzl + 3]    # two planes above -> next rank's first two real planes
     got = np.concatenate([o[ghosts_below:ghosts_below + nzl] for o in out])
     assert np.abs(got - ref).max() <= 5e-6 * float(ref.max())                       # summation order only
-    assert abs(float(got.sum(dtype=np.float64)) - float(w.sum(dtype=np.float64))) < 1e-2
+    assert abs(float(got.sum(dtype=np.float64)) - float(w.sum(dtype=np.float64))) < (5e-2 if mas == PCS else 1e-2)   # 64 Float32 products per particle (PCS), 27, 8
 
 
 @pytest.mark.parametrize("P", [1, 2, 4, 8])
@@ -232,13 +257,15 @@ def test_cic_slab_gather_scheme(HC, B, P, n, Lz):
 
 
 @pytest.mark.parametrize("P", [1, 2, 4, 8])
-def test_tsc_slab_gather_scheme(HC, B, P):
+@pytest.mark.parametrize("mas", [TSC, PCS])
+def test_tsc_slab_gather_scheme(HC, B, P, mas):
     n = (12, 10, 16)
     L, lo = f32([300.0, 250.0, 400.0]), -50.0
     bs, bm = L, np.full(3, lo, f32)
     pos, _ = slab_catalog(n, L, lo, 31 + P, True)
     fld = np.random.default_rng(5).standard_normal((n[2], n[1], n[0])).astype(f32)
-    ref = O.read_tsc(fld, *pos, bs, bm, True)
+    ref = (O.read_tsc if mas == TSC else O.read_pcs)(fld, *pos, bs, bm, True)
+    hc_gather = HC.hc_tsc_gather if mas == TSC else HC.hc_pcs_gather
     nzl = n[2] // P
     own = B.dist.owner_of_z(pos[2], lo, float(L[2]), n[2], P)
     ng = np.asarray(n, np.int32)
@@ -249,7 +276,7 @@ def test_tsc_slab_gather_scheme(HC, B, P):
         sel = own == r
         px, py, pz = (np.ascontiguousarray(p[sel]) for p in pos)
         out = np.empty(len(px), f32)
-        bad = HC.hc_tsc_gather(fp(buf), fp(px), fp(py), fp(pz), len(px), ip(ng), fp(bs), fp(bm), 1, r * nzl, 1, nzl + 3, fp(out))
+        bad = hc_gather(fp(buf), fp(px), fp(py), fp(pz), len(px), ip(ng), fp(bs), fp(bm), 1, r * nzl, 1, nzl + 3, fp(out))
         assert bad == 0
         assert np.array_equal(u32(out), u32(ref[sel]))                              # bit-exact, like the single-GPU gather
     # a particle of another slab is rejected (counted out-of-box), never read from the wrong plane
@@ -258,7 +285,7 @@ def test_tsc_slab_gather_scheme(HC, B, P):
         out = np.empty(int(other.sum()), f32)
         buf = np.ascontiguousarray(fld[[(0 * nzl - 1 + k) % n[2] for k in range(nzl + 3)]])
         px, py, pz = (np.ascontiguousarray(p[other]) for p in pos)
-        assert HC.hc_tsc_gather(fp(buf), fp(px), fp(py), fp(pz), len(px), ip(ng), fp(bs), fp(bm), 1, 0, 1, nzl + 3, fp(out)) > 0
+        assert hc_gather(fp(buf), fp(px), fp(py), fp(pz), len(px), ip(ng), fp(bs), fp(bm), 1, 0, 1, nzl + 3, fp(out)) > 0
 
 
 def test_single_gpu_deposit_matches_the_oracle(HC):
@@ -269,7 +296,7 @@ def test_single_gpu_deposit_matches_the_oracle(HC):
     bs, bm = L, np.full(3, lo, f32)
     pos, w = slab_catalog(n, L, lo, 41, False)
     ng = np.asarray(n, np.int32)
-    for mas, fn in ((CIC, O.cic_scatter), (TSC, O.tsc_scatter)):
+    for mas, fn in ((CIC, O.cic_scatter), (TSC, O.tsc_scatter), (PCS, O.pcs_scatter)):
         ref = fn(np.zeros((n[2], n[1], n[0]), f32), *[p.copy() for p in pos], w, bs, bm, False)
         buf = np.zeros_like(ref)
         assert HC.hc_deposit(mas, fp(buf), fp(pos[0]), fp(pos[1]), fp(pos[2]), fp(w), len(w), ip(ng), fp(bs), fp(bm), 0, 0, 0, 0, n[2]) == 0

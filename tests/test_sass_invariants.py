@@ -71,5 +71,7 @@ def test_no_register_spills_and_known_local_memory_users(K):
 
 
 def test_multipole_kernel(K):
-    k = find(K, "pk_kernel")
+    for name in ("pk_kernel<false>", "pk_kernel<true>"):          # plain / interlaced (second half mesh + the phase product)
+        assert find(K, name)["spill"] == 0
+    k = find(K, "pk_kernel<false>")
     assert k["fp64"] > 200 and k["shfl_vote"] > 100 and k["red_global"] == 1 and k["atom_shared"] > 0
