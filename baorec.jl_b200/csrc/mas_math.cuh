@@ -362,6 +362,55 @@ __device__ __forceinline__ bool deposit_tsc_vec(float* __restrict__ rho, float p
   return true;
 }
 
+// Four contiguous cells of a row (PCS): the aligned 16-byte block that holds `first` takes the values at offset o
+// (+0 in the slots before it), the next block the rest -- one quad for a quarter of the particles, two for the others.
+__device__ __forceinline__ void red_row4(float* row, int first, float v0, float v1, float v2, float v3) {
+  const int o = first & 3;
+  float* b = row + (first - o);
+  const bool s0 = o == 0, s1 = o == 1, s2 = o == 2;
+  red_add_v4(b, s0 ? v0 : 0.f, s0 ? v1 : (s1 ? v0 : 0.f), s0 ? v2 : (s1 ? v1 : (s2 ? v0 : 0.f)), s0 ? v3 : (s1 ? v2 : (s2 ? v1 : v0)));
+  if (o != 0) red_add_v4(b + 4, s1 ? v3 : (s2 ? v2 : v1), s1 ? 0.f : (s2 ? v3 : v2), (s1 || s2) ? 0.f : v3, 0.f);
+}
+
+// deposit<PCS> with vector reductions (16 rows of four cells: 16 - 32 quads instead of 64 scalar reductions); `rho` must
+// be 16-byte aligned.  Same cells, same Float32 values.
+__device__ __forceinline__ bool deposit_pcs_vec(float* __restrict__ rho, float px, float py, float pz, float ww,
+                                                const BoxGeom& g, bool wrap) {
+  const size_t nx = g.n[0], ny = g.n[1];
+  int ix[4], iy[4], iz[4];
+  float wx[4], wy[4], wz[4];
+  bool ok = pcs_axis(px, g.mn[0], g.L[0], g.n[0], wrap, ix, wx);
+  ok = pcs_axis(py, g.mn[1], g.L[1], g.n[1], wrap, iy, wy) && ok;
+  ok = pcs_axis(pz, g.mn[2], g.L[2], g.n[2], wrap, iz, wz) && ok;
+  if (!ok) return false;
+  if (g.slab) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) ok = local_plane1(g, iz[c], iz[c]) && ok;
+    if (!ok) return false;
+  }
+  // the row is contiguous unless the stencil wraps in x; first + 3 < nx and nx = 4 k keep both blocks inside the row
+  const bool vec = (g.n[0] & 3) == 0 && ix[3] == ix[0] + 3;
+  const float x0 = __fmul_rn(wx[0], ww), x1 = __fmul_rn(wx[1], ww), x2 = __fmul_rn(wx[2], ww), x3 = __fmul_rn(wx[3], ww);
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      float* row = rho + ((size_t)iz[c] * ny + iy[b]) * nx;
+      const float v0 = __fmul_rn(__fmul_rn(x0, wy[b]), wz[c]), v1 = __fmul_rn(__fmul_rn(x1, wy[b]), wz[c]);
+      const float v2 = __fmul_rn(__fmul_rn(x2, wy[b]), wz[c]), v3 = __fmul_rn(__fmul_rn(x3, wy[b]), wz[c]);
+      if (vec) {
+        red_row4(row, ix[0], v0, v1, v2, v3);
+      } else {
+        atomicAdd(row + ix[0], v0);
+        atomicAdd(row + ix[1], v1);
+        atomicAdd(row + ix[2], v2);
+        atomicAdd(row + ix[3], v3);
+      }
+    }
+  }
+  return true;
+}
+
 // ---- deterministic deposit (option "deterministic_scatter") -------------------------------------------------------
 // Float additions do not commute, so a mesh accumulated with float reductions differs from run to run in the last
 // bits (and with it the cells that sit on the `ran > threshold` cut).  Integer additions do

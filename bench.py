@@ -150,7 +150,7 @@ def algorithmic_bytes(name, M, Mc, N, chunks=1):
         return 16 * N + 16 * N
     if "tile_reorder" in name:
         return 12 * N + 16 * N + 4 * N
-    if "gather_tile_kernel<3" in name:
+    if "gather_tile_kernel<3" in name or "gather_tile_tma_kernel<3" in name:
         return 16 * N + 16 * N + 12 * M    # records in, float4 results out (sorted order), 3 meshes once
     if "unsort" in name:
         return 4 * N + 16 * N + 12 * N
@@ -182,9 +182,13 @@ def algorithmic_bytes(name, M, Mc, N, chunks=1):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of THIS workload
-# (1024^3, 1e8 particles, one GPU; profiles/r1_ncu_full_final_own_kernels.csv, r1_ncu_full_prof_r1_a.csv)
+# (1024^3, 1e8 particles, one GPU; profiles/r1_ncu_full_final_own_kernels.csv, r1_ncu_full_prof_r1_a.csv, r2_ncu_full_*.csv)
 NCU_TRAFFIC_BYTES_C4 = {
     "gather_tile_kernel<3>": 14.502e9 + 1.598e9,
+    "gather_tile_tma_kernel<3>": 14.502e9 + 1.598e9,  # profiles/r2_ncu_full_gather_tma.csv
+    "fft_z_disp_kernel": 4.805e9 + 13.877e9,         # profiles/r2_ncu_full_own_kernels.csv
+    "fft_z_solve_kernel": 4.330e9 + 8.576e9,
+    "fft_cols_kernel": 4.303e9 + 4.251e9,
     "scatter_sorted_kernel": 5.851e9 + 4.100e9,      # z-slab order (option unified_sort=0)
     "scatter_records_kernel": 5.849e9 + 4.096e9,     # profiles/r1_ncu_full_unified_sort.csv
     "usort_reorder_kernel": 3.509e9 + 3.308e9,

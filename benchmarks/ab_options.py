@@ -70,7 +70,7 @@ def main():
         torch.cuda.synchronize()
         prof = ctx.profile_read()
         ctx.profile(False)
-        top = sorted(prof.items(), key=lambda kv: -kv[1][0])[:5]
+        top = sorted(prof.items(), key=lambda kv: -kv[1][0])[:14]
         print(json.dumps({"options": cfg or "defaults", "catalog": args.catalog, "mesh": n, "particles": N,
                           "ms_per_reconstruction": round(e0.elapsed_time(e1) / args.steps, 3),
                           "top_kernels_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in top},

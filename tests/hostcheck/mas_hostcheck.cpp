@@ -134,6 +134,16 @@ int64_t hc_deposit_pairs(int mode, float* buf, const float* x, const float* y, c
   return bad;
 }
 
+// Option "scatter_pairs" for PCS: the product's deposit_pcs_vec (one or two aligned quads per stencil row) against deposit<PCS>.
+int64_t hc_deposit_pcs_vec(float* buf, const float* x, const float* y, const float* z, const float* w, int64_t n, const int* ng,
+                           const float* L, const float* mn, int wrap, int slab, int z_lo, int zoff, int nzp) {
+  const BoxGeom g = make_geom(ng, L, mn, slab, z_lo, zoff, nzp);
+  int64_t bad = 0;
+  for (int64_t i = 0; i < n; i++)
+    if (!deposit_pcs_vec(buf, x[i], y[i], z[i], w[i], g, wrap != 0)) bad++;
+  return bad;
+}
+
 // Option "scatter_pairs" for TSC: the product's deposit_tsc_vec (one aligned quad or two aligned pairs per stencil row)
 // against deposit<TSC> -- on the host the vector reductions are plain additions in cell order, the +0 slots included.
 int64_t hc_deposit_tsc_vec(float* buf, const float* x, const float* y, const float* z, const float* w, int64_t n, const int* ng,

@@ -56,6 +56,8 @@ def HC():
     lib.hc_deposit_pairs.argtypes = [i, _F, _F, _F, _F, _F, i64, _I, _F, _F, i, C.POINTER(i64)]
     lib.hc_deposit_tsc_vec.restype = i64
     lib.hc_deposit_tsc_vec.argtypes = [_F, _F, _F, _F, _F, i64, _I, _F, _F, i, i, i, i, i]
+    lib.hc_deposit_pcs_vec.restype = i64
+    lib.hc_deposit_pcs_vec.argtypes = [_F, _F, _F, _F, _F, i64, _I, _F, _F, i, i, i, i, i]
     lib.hc_deposit_fixed.restype = i64
     lib.hc_deposit_fixed.argtypes = [_F, C.POINTER(C.c_uint64), _F, _F, _F, _F, i64, _I, _F, _F, i]
     lib.hc_shifts_epilogue.restype = None
@@ -422,5 +424,22 @@ def test_vector_tsc_deposit_equals_the_scalar_one(HC, n, wrap):
     TSC = 1
     bad_a = HC.hc_deposit(TSC, fp(a), fp(pos[0]), fp(pos[1]), fp(pos[2]), fp(w), len(w), ip(ng), fp(bs), fp(bm), int(wrap), 0, 0, 0, n[2])
     bad_b = HC.hc_deposit_tsc_vec(fp(b), fp(pos[0]), fp(pos[1]), fp(pos[2]), fp(w), len(w), ip(ng), fp(bs), fp(bm), int(wrap), 0, 0, 0, n[2])
+    assert bad_a == bad_b and np.array_equal(u32(a), u32(b))
+    assert abs(float(b.sum(dtype=np.float64)) / float(w.sum(dtype=np.float64)) - 1) < 1e-5 or bad_b > 0
+
+
+@pytest.mark.parametrize("n,wrap", [((16, 10, 12), True), ((16, 10, 12), False), ((12, 8, 8), True), ((14, 8, 8), True)])
+def test_vector_pcs_deposit_equals_the_scalar_one(HC, n, wrap):
+    """Option "scatter_pairs" for PCS: one or two aligned quads per stencil row (16 - 32 reductions per particle instead
+    of 64).  Against the product's own scalar deposit<PCS> in the same particle order: identical bits (rows that wrap in
+    x, and the 14-cell mesh whose rows are not a multiple of 4, take the scalar path)."""
+    L, lo = f32([300.0, 250.0, 400.0]), -50.0
+    bs, bm = L, np.full(3, lo, f32)
+    pos, w = slab_catalog(n, L, lo, 73, wrap)
+    ng = np.asarray(n, np.int32)
+    M = n[0] * n[1] * n[2]
+    a, b = np.zeros(M, f32), np.zeros(M, f32)
+    bad_a = HC.hc_deposit(PCS, fp(a), fp(pos[0]), fp(pos[1]), fp(pos[2]), fp(w), len(w), ip(ng), fp(bs), fp(bm), int(wrap), 0, 0, 0, n[2])
+    bad_b = HC.hc_deposit_pcs_vec(fp(b), fp(pos[0]), fp(pos[1]), fp(pos[2]), fp(w), len(w), ip(ng), fp(bs), fp(bm), int(wrap), 0, 0, 0, n[2])
     assert bad_a == bad_b and np.array_equal(u32(a), u32(b))
     assert abs(float(b.sum(dtype=np.float64)) / float(w.sum(dtype=np.float64)) - 1) < 1e-5 or bad_b > 0
