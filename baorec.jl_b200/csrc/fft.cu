@@ -36,9 +36,10 @@ constexpr int FFT_THREADS = 256;   // 8 columns x 32 threads
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
-template <int DIR>
-__device__ __forceinline__ float2 twd(const float2* __restrict__ tw, int idx) {
-  float2 w = __ldg(tw + idx);  // exp(-2 pi i idx / N)
+// TWS: the table is the CTA's shared-memory copy (fused z passes) / the global table through L1 (plain passes)
+template <int DIR, bool TWS>
+__device__ __forceinline__ float2 twd(const float2* tw, int idx) {
+  float2 w = TWS ? tw[idx] : __ldg(tw + idx);  // exp(-2 pi i idx / N)
   if (DIR < 0) w.y = -w.y;
   return w;
 }
@@ -70,19 +71,31 @@ struct Xch {
   static constexpr size_t BYTES = (size_t)FFT_TX * COL * sizeof(float2);
 };
 
+// The fused z passes keep the twiddle table and the k_z / Gaussian tables in SHARED memory, after the exchange buffer.
+// Read through L1 (__ldg) the streaming column loads and stores keep evicting them (ncu: L1 hit rate 14 - 21 %) and
+// every twiddle multiply and every k_z^2 waits for L2: a third of the warp-stall samples of fft_z_disp sat on the first
+// use of a k_z value.  Measured at 1024^3: fft_z_solve 6.93 -> 6.17 ms, fft_z_disp 8.41 -> 7.96 ms.  The plain pass
+// (fft_cols_kernel) is better off with __ldg: there the copy and its barrier cost more than they save (2.02 -> 2.24 ms).
+template <int N>
+__device__ __forceinline__ float2* stage_twiddles(float2* S, const float2* __restrict__ tw) {
+  float2* T = S + FFT_TX * Xch<N>::COL;
+  for (int i = threadIdx.x; i < N; i += FFT_THREADS) T[i] = __ldg(tw + i);
+  return T;
+}
+
 // One length-N transform per (column c, 32 threads t): v[j] = x[t + 32 j] in, out[m][r] with
 // out[m][fft_bitrev<32>(k1)] = X[(t + 32 m) + M k1] for the transforms this thread owns in the last step
 // (m < MT = max(1, M / 32); for M < 32 only threads t < M own one).  S = this CTA's exchange buffer.
-template <int N, int DIR>
+template <int N, int DIR, bool TWS>
 __device__ __forceinline__ void fft_column(float2 (&v)[N / 32], float2 (&out)[(N / 32 >= 32 ? N / 1024 : 1)][32],
-                                           float2* __restrict__ S, const float2* __restrict__ tw, int c, int t) {
+                                           float2* __restrict__ S, const float2* tw, int c, int t) {
   constexpr int M = N / 32, MT = M >= 32 ? M / 32 : 1, COL = Xch<N>::COL;
   fft_reg<M, DIR>(v);
   float2* col = S + c * COL;
 #pragma unroll
   for (int k2 = 0; k2 < M; k2++) {
     float2 y = v[fft_bitrev<M>(k2)];
-    if (k2) y = cmul(y, twd<DIR>(tw, (t * k2) & (N - 1)));
+    if (k2) y = cmul(y, twd<DIR, TWS>(tw, (t * k2) & (N - 1)));
     col[k2 * 33 + t] = y;
   }
   __syncthreads();
@@ -191,7 +204,7 @@ fft_cols_kernel(const float2* __restrict__ in, float2* __restrict__ out, ColGeom
 #pragma unroll
     for (int j = 0; j < M; j++) v[j] = make_float2(0.f, 0.f);
   }
-  fft_column<N, DIR>(v, X, S, tw, c, t);
+  fft_column<N, DIR, false>(v, X, S, tw, c, t);
   // Last pass before the C2R along x: the kx = 0 and kx = Nyquist columns must be real there.  FFTW
   // and pocketfft ignore their imaginary part; cuFFT's 1-D C2R does not, so it is dropped here
   // (it is non-zero only for inputs with power at the Nyquist modes, e.g. i k multiplications).
@@ -233,7 +246,15 @@ fft_z_solve_kernel(float2* __restrict__ data, float2* __restrict__ keep, ColGeom
 #pragma unroll
     for (int j = 0; j < M; j++) v[j] = make_float2(0.f, 0.f);
   }
-  fft_column<N, 1>(v, X, S, tw, c, t);
+  float2* T = stage_twiddles<N>(S, tw);
+  double* GZ = reinterpret_cast<double*>(T + N);   // Gaussian of the z axis (Float64), then k_z
+  float* KZ = reinterpret_cast<float*>(GZ + N);
+  for (int i = threadIdx.x; i < N; i += FFT_THREADS) {
+    GZ[i] = __ldg(op.gt.gz + i);
+    KZ[i] = __ldg(cg.ktrans + i);
+  }
+  __syncthreads();
+  fft_column<N, 1, true>(v, X, S, T, c, t);
   const OpLosSolve::Col col = op.column(valid ? __ldg(cg.kx + ix) : 0.f, __ldg(cg.kouter + iy), valid ? ix : 0, iy);
   const double dc8 = __ldg(op.scal + 8);
 #pragma unroll
@@ -243,13 +264,13 @@ fft_z_solve_kernel(float2* __restrict__ data, float2* __restrict__ keep, ColGeom
       const int f = t + 32 * m + M * k1;      // = t + 32 (m + MT k1): the inverse transform's register m + MT k1
       float2 d = make_float2(0.f, 0.f);
       if (valid) {
-        d = op.solve(X[m][fft_bitrev<32>(k1)], col, __ldg(cg.ktrans + f), __ldg(op.gt.gz + f) * dc8, (ix | iy | f) == 0);
+        d = op.solve(X[m][fft_bitrev<32>(k1)], col, KZ[f], GZ[f] * dc8, (ix | iy | f) == 0);
         if (keep != nullptr) keep[base + (size_t)f * cg.stride] = d;
       }
       v[m + MT * k1] = make_float2(d.x * op.invM, d.y * op.invM);
     }
   __syncthreads();  // everybody has read the exchange buffer of the forward transform
-  fft_column<N, -1>(v, X, S, tw, c, t);
+  fft_column<N, -1, true>(v, X, S, T, c, t);
   if (valid) {
 #pragma unroll
     for (int m = 0; m < MT; m++)
@@ -276,13 +297,17 @@ fft_z_disp_kernel(const float2* __restrict__ in, float2* __restrict__ o0, float2
   const bool valid = ix < cg.ncols;
   const size_t base = (size_t)iy * cg.outer_stride + ix;
   const float kx = valid ? __ldg(cg.kx + ix) : 0.f, ky = __ldg(cg.kouter + iy);
+  float2* T = stage_twiddles<N>(S, tw);
+  float* KZ = reinterpret_cast<float*>(T + N);
+  for (int i = threadIdx.x; i < N; i += FFT_THREADS) KZ[i] = __ldg(cg.ktrans + i);
+  __syncthreads();
 #pragma unroll 1
   for (int pass = 0; pass < 2; pass++) {   // 0: H -> z field;  1: G -> x and y fields
     float2 v[M], X[MT][32];
     if (valid) load_column<N>(v, in + base, cg.stride, t);
 #pragma unroll
     for (int j = 0; j < M; j++) {
-      const float kz = __ldg(cg.ktrans + t + 32 * j);
+      const float kz = KZ[t + 32 * j];
       float s;
       if (op.potential) {
         s = op.invM;
@@ -296,7 +321,7 @@ fft_z_disp_kernel(const float2* __restrict__ in, float2* __restrict__ o0, float2
                        : make_float2(__fmul_rn(d.x, s), __fmul_rn(d.y, s));
     }
     if (pass) __syncthreads();  // the first transform's exchange buffer has been read
-    fft_column<N, -1>(v, X, S, tw, c, t);
+    fft_column<N, -1, true>(v, X, S, T, c, t);
     if (valid) {
 #pragma unroll
       for (int m = 0; m < MT; m++) {
@@ -370,8 +395,11 @@ int own_fft_setup(baorec_ctx* ctx) {
   return BAOREC_OK;
 }
 
+// exchange buffer; the fused z passes add their tables (twiddles 8 N, + extra)
 template <int N>
 static size_t tile_bytes() { return Xch<N>::BYTES; }
+template <int N>
+static size_t fused_bytes(size_t extra) { return Xch<N>::BYTES + (size_t)N * sizeof(float2) + extra; }
 
 #define FFT_DISPATCH_N(n, CALL)     \
   switch (n) {                      \
@@ -482,8 +510,8 @@ int own_fused_los_solve(baorec_ctx* ctx, const baorec_params* p, float* mesh, fl
   const ColGeom g = geom_z(ctx);
   dim3 grid(cdiv(g.ncols, FFT_TX), ctx->ny);
 #define CALL(NN)                                                                                          \
-  BR_TRY(set_smem(fft_z_solve_kernel<NN>, tile_bytes<NN>()));                                             \
-  BR_LAUNCH_NAMED(ctx, "fft_z_solve_kernel", fft_z_solve_kernel<NN>, grid, FFT_THREADS, tile_bytes<NN>(), st, work, \
+  BR_TRY(set_smem(fft_z_solve_kernel<NN>, fused_bytes<NN>(NN * 12)));                                             \
+  BR_LAUNCH_NAMED(ctx, "fft_z_solve_kernel", fft_z_solve_kernel<NN>, grid, FFT_THREADS, fused_bytes<NN>(NN * 12), st, work, \
                   keep, g, ctx->d_tw[1], op);
   switch (ctx->nz) {
     case 1024: { CALL(1024); } break;
@@ -511,8 +539,8 @@ int own_displacements(baorec_ctx* ctx, const float* mesh, const float2* from_k, 
     src = w0;
   }
 #define CALL(NN)                                                                                               \
-  BR_TRY(set_smem(fft_z_disp_kernel<NN>, tile_bytes<NN>()));                                                   \
-  BR_LAUNCH_NAMED(ctx, "fft_z_disp_kernel", fft_z_disp_kernel<NN>, grid, FFT_THREADS, tile_bytes<NN>(), st, src, w0, \
+  BR_TRY(set_smem(fft_z_disp_kernel<NN>, fused_bytes<NN>(NN * 4)));                                                   \
+  BR_LAUNCH_NAMED(ctx, "fft_z_disp_kernel", fft_z_disp_kernel<NN>, grid, FFT_THREADS, fused_bytes<NN>(NN * 4), st, src, w0, \
                   w1, w2, g, ctx->d_tw[1], op);
   FFT_DISPATCH_N(ctx->nz, CALL)
 #undef CALL
