@@ -1282,7 +1282,12 @@ int scatter(baorec_ctx* ctx, float* rho, float* x, float* y, float* z, const flo
   if (n == 0) return BAOREC_OK;
   BoxGeom g = geom_of(ctx);
   const bool tsc = mas != BAOREC_MAS_CIC, pcs = mas == BAOREC_MAS_PCS;  // tsc: a stencil scheme (TSC or PCS)
-  if (ctx->opt_det_scatter && !tsc && ctx->slab_mode == 0) {
+  if (ctx->opt_det_scatter && (tsc || ctx->slab_mode != 0)) {
+    set_error("option deterministic_scatter covers the single-GPU CIC scatter only (requested: %s%s); unset it for this call",
+              tsc ? "TSC / PCS" : "CIC", ctx->slab_mode != 0 ? " on slabs" : "");
+    return BAOREC_ERR_INVALID;  // not silently ignored: the caller asked for bit-reproducible meshes
+  }
+  if (ctx->opt_det_scatter) {
     // bit-reproducible CIC: 64-bit fixed-point integer reductions, one rounding to Float32 at the end
     unsigned long long* acc;
     BR_TRY(need_t(ctx, BUF_DET, ctx->M, &acc));

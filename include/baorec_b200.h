@@ -115,7 +115,9 @@ int baorec_set_box(baorec_ctx* ctx, const float box_size[3], const float box_min
  *   "deterministic_scatter" (default 0): 1 = the CIC scatter (single GPU) accumulates 2^-40 fixed-point values with
  *       64-bit integer reductions and rounds to Float32 once: meshes, `ran > threshold` masks and everything after
  *       them are bit-reproducible from run to run and independent of the particle order (float reductions are not);
- *       costs an 8-byte-per-cell scratch mesh and one conversion pass.
+ *       costs an 8-byte-per-cell scratch mesh and one conversion pass.  With the option set, a TSC / PCS scatter or a
+ *       scatter on slabs (multi-GPU) returns BAOREC_ERR_INVALID instead of falling back to float reductions.  A cell may
+ *       accumulate up to 2^23 (8.4e6) in weight before the 2^-40 fixed-point sum wraps.
  *   "mg_remove_mean" (default 1): MultigridRecon solves on delta - mean(delta) when the cells are cubic.  A survey's
  *       delta has a non-zero mean; damped Jacobi on a periodic mesh then drifts by a constant that exact arithmetic
  *       does not feel (the operator's diagonal is uniform, src/multigrid.jl:82) but Float32 does: the reference's

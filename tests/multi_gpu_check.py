@@ -112,21 +112,22 @@ def more_modes(B, ctx, rank, world, quick=False):
 
 
 def tsc_modes(B, ctx, rank, world):
-    """IterativeRecon with TSC on slabs: periodic box (wrap across the last / first slab) and a radial line of sight."""
+    """IterativeRecon with TSC and PCS on slabs (both reach one plane below the slab and two above): periodic box (wrap
+    across the last / first slab) and a radial line of sight."""
     ok = True
     n, L, N = 64, 1000.0, 400_000
     if n % (2 * world):
         return ok
-    for los, lo in (((0.0, 0.0, 1.0), 0.0), (None, 700.0)):
+    for los, lo, mas in (((0.0, 0.0, 1.0), 0.0, "tsc"), (None, 700.0, "tsc"), ((0.0, 0.0, 1.0), 0.0, "pcs"), (None, 700.0, "pcs")):
         pos, w = clustered_box(N, L, seed=13, lo=lo)
         kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=np.full(3, L, np.float32),
                   box_min=np.full(3, lo, np.float32), los=los, n_iter=3)
-        orec = O.IterativeRecon(mas="tsc", **kw)
+        orec = O.IterativeRecon(mas=mas, **kw)
         omesh = O.run(orec, (n, n, n), *[p.copy() for p in pos], w)
         oshift = O.read_shifts(orec, *pos, omesh, "sum")
         mine = B.dist.owner_of_z(pos[2], lo, L, n, world) == rank
         d = [torch.from_numpy(np.ascontiguousarray(p[mine])).cuda() for p in pos]
-        rec = B.IterativeRecon(mas="tsc", **kw)
+        rec = B.IterativeRecon(mas=mas, **kw)
         mesh = B.dist.run_dist(rec, (n, n, n), *d, torch.from_numpy(np.ascontiguousarray(w[mine])).cuda(), ctx=ctx)
         z_lo, nzl = B.dist.slab_range(ctx)
         s = B.dist.read_shifts_dist(rec, *d, field="sum")
@@ -135,7 +136,7 @@ def tsc_modes(B, ctx, rank, world):
         e_max = max(maxabs(s[a].cpu().numpy(), oshift[a][mine]) for a in range(3))
         good = e_mesh < 1e-4 and e_rms < 1e-4 and e_max < 1e-3
         ok &= good
-        print(f"[rank {rank}/{world}] TSC los={los}: mesh rel.rms={e_mesh:.2e} shift rel.rms={e_rms:.2e} max={e_max:.2e} "
+        print(f"[rank {rank}/{world}] {mas.upper()} los={los}: mesh rel.rms={e_mesh:.2e} shift rel.rms={e_rms:.2e} max={e_max:.2e} "
               f"{'OK' if good else 'FAIL'}", flush=True)
     return ok
 

@@ -95,6 +95,8 @@ def test_deterministic_scatter_is_bit_reproducible(B, O, N):
         kw = dict(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=bs, box_min=bm, los=(0.0, 0.0, 1.0), n_iter=3)
         runs = [B.run(B.IterativeRecon(**kw), (n, n, n), *(dev(p) for p in pos), dev(w)) for _ in range(2)]
         assert torch.equal(runs[0], runs[1])                                                 # the whole reconstruction
+        with pytest.raises(B.BaorecError):                                                   # TSC / PCS / slabs: refused, not silently ignored
+            B.cic(torch.zeros((n, n, n), dtype=torch.float32, device="cuda"), *(dev(p) for p in pos), dev(w), bs, bm, wrap=True, mas="tsc")
     finally:
         ctx.set_option("deterministic_scatter", 0)
     rho = torch.zeros((n, n, n), dtype=torch.float32, device="cuda")
