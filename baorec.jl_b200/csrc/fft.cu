@@ -23,8 +23,8 @@
 
 namespace baorec {
 
-constexpr int FFT_TX = 8;          // columns per tile (8 x 8 B = 64 B row segments)
-constexpr int FFT_THREADS = 256;   // 8 columns x 32 threads
+constexpr int FFT_TX = 8;          // columns per tile (8 x 8 B = 64 B row segments): the default; 4 and 16 are instantiated for N = 1024
+                                   // (option "fft_tile_cols") -- 32 threads per column, so 128 / 256 / 512 threads per CTA
 // resident CTAs per SM.  The kernels fit 3 (80 registers, 20 bytes of spills at N = 1024), but measured on B200 at 1024^3
 // that is SLOWER (plain pass 3.0 instead of 2.2 ms, fused z pass 9.7 instead of 6.9 ms): a z pass touches every plane
 // of the mesh with ~19 KB per plane in flight whatever the tile shape, so more tiles in flight means more open DRAM
@@ -59,16 +59,16 @@ struct ColGeom {
 // multiple of 128: a half-warp (8 columns x 2 threads, one 8-byte access each) then covers the 32 banks exactly once
 // for the writes (slot t) and for the reads (row t).  (First version: 32 bytes off, columns c and c + 4 collided:
 // ncu counted 2.2 extra wavefronts per shared-memory instruction.)
-template <int N>
+template <int N, int TX = FFT_TX>
 struct Xch {
   static constexpr int M = N / 32;
-  static constexpr int pad() {
+  static constexpr int pad() {  // column stride = 128 / TX bytes off a multiple of 128 (TX columns x 16 / TX threads per half-warp)
     int p = 0;
-    while (((M * 33 + p) * 8) % 128 != 16) p++;
+    while (((M * 33 + p) * 8) % 128 != 128 / TX) p++;
     return p;
   }
   static constexpr int COL = M * 33 + pad();
-  static constexpr size_t BYTES = (size_t)FFT_TX * COL * sizeof(float2);
+  static constexpr size_t BYTES = (size_t)TX * COL * sizeof(float2);
 };
 
 // The fused z passes keep the twiddle table and the k_z / Gaussian tables in SHARED memory, after the exchange buffer.
@@ -76,20 +76,20 @@ struct Xch {
 // every twiddle multiply and every k_z^2 waits for L2: a third of the warp-stall samples of fft_z_disp sat on the first
 // use of a k_z value.  Measured at 1024^3: fft_z_solve 6.93 -> 6.17 ms, fft_z_disp 8.41 -> 7.96 ms.  The plain pass
 // (fft_cols_kernel) is better off with __ldg: there the copy and its barrier cost more than they save (2.02 -> 2.24 ms).
-template <int N>
+template <int N, int TX>
 __device__ __forceinline__ float2* stage_twiddles(float2* S, const float2* __restrict__ tw) {
-  float2* T = S + FFT_TX * Xch<N>::COL;
-  for (int i = threadIdx.x; i < N; i += FFT_THREADS) T[i] = __ldg(tw + i);
+  float2* T = S + TX * Xch<N, TX>::COL;
+  for (int i = threadIdx.x; i < N; i += 32 * TX) T[i] = __ldg(tw + i);
   return T;
 }
 
 // One length-N transform per (column c, 32 threads t): v[j] = x[t + 32 j] in, out[m][r] with
 // out[m][fft_bitrev<32>(k1)] = X[(t + 32 m) + M k1] for the transforms this thread owns in the last step
 // (m < MT = max(1, M / 32); for M < 32 only threads t < M own one).  S = this CTA's exchange buffer.
-template <int N, int DIR, bool TWS>
+template <int N, int DIR, bool TWS, int TX = FFT_TX>
 __device__ __forceinline__ void fft_column(float2 (&v)[N / 32], float2 (&out)[(N / 32 >= 32 ? N / 1024 : 1)][32],
                                            float2* __restrict__ S, const float2* tw, int c, int t) {
-  constexpr int M = N / 32, MT = M >= 32 ? M / 32 : 1, COL = Xch<N>::COL;
+  constexpr int M = N / 32, MT = M >= 32 ? M / 32 : 1, COL = Xch<N, TX>::COL;
   fft_reg<M, DIR>(v);
   float2* col = S + c * COL;
 #pragma unroll
@@ -187,15 +187,15 @@ struct OpDisp {
 
 // ---- kernels -----------------------------------------------------------------------------------------
 // plain pass: out = FFT_DIR(in) along the strided axis (in place allowed: a CTA reads its whole tile before it writes)
-template <int N, int DIR>
-__global__ void __launch_bounds__(FFT_THREADS, N >= 2048 ? 1 : FFT_CTAS_1024)
+template <int N, int DIR, int TX = FFT_TX>
+__global__ void __launch_bounds__(32 * TX, N >= 2048 ? 1 : (FFT_CTAS_1024 * 8) / TX)
 fft_cols_kernel(const float2* __restrict__ in, float2* __restrict__ out, ColGeom cg, const float2* __restrict__ tw,
                 int hermitian_edges) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* S = reinterpret_cast<float2*>(smem_raw);
   constexpr int M = N / 32, MT = M >= 32 ? M / 32 : 1;
-  const int c = threadIdx.x & (FFT_TX - 1), t = threadIdx.x >> 3;
-  const int ix = blockIdx.x * FFT_TX + c;
+  const int c = threadIdx.x & (TX - 1), t = threadIdx.x / TX;
+  const int ix = blockIdx.x * TX + c;
   const bool valid = ix < cg.ncols;
   const size_t base = (size_t)blockIdx.y * cg.outer_stride + ix;
   float2 v[M], X[MT][32];
@@ -204,7 +204,7 @@ fft_cols_kernel(const float2* __restrict__ in, float2* __restrict__ out, ColGeom
 #pragma unroll
     for (int j = 0; j < M; j++) v[j] = make_float2(0.f, 0.f);
   }
-  fft_column<N, DIR, false>(v, X, S, tw, c, t);
+  fft_column<N, DIR, false, TX>(v, X, S, tw, c, t);
   // Last pass before the C2R along x: the kx = 0 and kx = Nyquist columns must be real there.  FFTW
   // and pocketfft ignore their imaginary part; cuFFT's 1-D C2R does not, so it is dropped here
   // (it is non-zero only for inputs with power at the Nyquist modes, e.g. i k multiplications).
@@ -228,16 +228,16 @@ fft_cols_kernel(const float2* __restrict__ in, float2* __restrict__ out, ColGeom
 
 // z pass of the fused fixed-LOS solve (N >= 1024: the forward output is the inverse input, register for register):
 // forward z FFT, operator, [delta_k kept], inverse z FFT; in place.
-template <int N>
-__global__ void __launch_bounds__(FFT_THREADS, N >= 2048 ? 1 : FFT_CTAS_1024)
+template <int N, int TX = FFT_TX>
+__global__ void __launch_bounds__(32 * TX, N >= 2048 ? 1 : (FFT_CTAS_1024 * 8) / TX)
 fft_z_solve_kernel(float2* __restrict__ data, float2* __restrict__ keep, ColGeom cg, const float2* __restrict__ tw,
                    OpLosSolve op) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* S = reinterpret_cast<float2*>(smem_raw);
   constexpr int M = N / 32, MT = M / 32;
   static_assert(M >= 32, "the fused z pass needs N >= 1024");
-  const int c = threadIdx.x & (FFT_TX - 1), t = threadIdx.x >> 3;
-  const int ix = blockIdx.x * FFT_TX + c, iy = blockIdx.y;
+  const int c = threadIdx.x & (TX - 1), t = threadIdx.x / TX;
+  const int ix = blockIdx.x * TX + c, iy = blockIdx.y;
   const bool valid = ix < cg.ncols;
   const size_t base = (size_t)iy * cg.outer_stride + ix;
   float2 v[M], X[MT][32];
@@ -246,15 +246,15 @@ fft_z_solve_kernel(float2* __restrict__ data, float2* __restrict__ keep, ColGeom
 #pragma unroll
     for (int j = 0; j < M; j++) v[j] = make_float2(0.f, 0.f);
   }
-  float2* T = stage_twiddles<N>(S, tw);
+  float2* T = stage_twiddles<N, TX>(S, tw);
   double* GZ = reinterpret_cast<double*>(T + N);   // Gaussian of the z axis (Float64), then k_z
   float* KZ = reinterpret_cast<float*>(GZ + N);
-  for (int i = threadIdx.x; i < N; i += FFT_THREADS) {
+  for (int i = threadIdx.x; i < N; i += 32 * TX) {
     GZ[i] = __ldg(op.gt.gz + i);
     KZ[i] = __ldg(cg.ktrans + i);
   }
   __syncthreads();
-  fft_column<N, 1, true>(v, X, S, T, c, t);
+  fft_column<N, 1, true, TX>(v, X, S, T, c, t);
   const OpLosSolve::Col col = op.column(valid ? __ldg(cg.kx + ix) : 0.f, __ldg(cg.kouter + iy), valid ? ix : 0, iy);
   const double dc8 = __ldg(op.scal + 8);
 #pragma unroll
@@ -270,7 +270,7 @@ fft_z_solve_kernel(float2* __restrict__ data, float2* __restrict__ keep, ColGeom
       v[m + MT * k1] = make_float2(d.x * op.invM, d.y * op.invM);
     }
   __syncthreads();  // everybody has read the exchange buffer of the forward transform
-  fft_column<N, -1, true>(v, X, S, T, c, t);
+  fft_column<N, -1, true, TX>(v, X, S, T, c, t);
   if (valid) {
 #pragma unroll
     for (int m = 0; m < MT; m++)
@@ -285,21 +285,21 @@ fft_z_solve_kernel(float2* __restrict__ data, float2* __restrict__ keep, ColGeom
 // of H = i k_z G.  Two transforms and three stores per column; delta_k is read twice (the second read of the 64 KB
 // tile comes from L2) so that no copy of it has to stay in registers while a transform runs -- the first version
 // kept it, needed 255 registers (one CTA per SM) and ran three transforms: 11.3 ms at 1024^3.
-template <int N>
-__global__ void __launch_bounds__(FFT_THREADS, N >= 2048 ? 1 : FFT_CTAS_1024)
+template <int N, int TX = FFT_TX>
+__global__ void __launch_bounds__(32 * TX, N >= 2048 ? 1 : (FFT_CTAS_1024 * 8) / TX)
 fft_z_disp_kernel(const float2* __restrict__ in, float2* __restrict__ o0, float2* __restrict__ o1,
                   float2* __restrict__ o2, ColGeom cg, const float2* __restrict__ tw, OpDisp op) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* S = reinterpret_cast<float2*>(smem_raw);
   constexpr int M = N / 32, MT = M >= 32 ? M / 32 : 1;
-  const int c = threadIdx.x & (FFT_TX - 1), t = threadIdx.x >> 3;
-  const int ix = blockIdx.x * FFT_TX + c, iy = blockIdx.y;
+  const int c = threadIdx.x & (TX - 1), t = threadIdx.x / TX;
+  const int ix = blockIdx.x * TX + c, iy = blockIdx.y;
   const bool valid = ix < cg.ncols;
   const size_t base = (size_t)iy * cg.outer_stride + ix;
   const float kx = valid ? __ldg(cg.kx + ix) : 0.f, ky = __ldg(cg.kouter + iy);
-  float2* T = stage_twiddles<N>(S, tw);
+  float2* T = stage_twiddles<N, TX>(S, tw);
   float* KZ = reinterpret_cast<float*>(T + N);
-  for (int i = threadIdx.x; i < N; i += FFT_THREADS) KZ[i] = __ldg(cg.ktrans + i);
+  for (int i = threadIdx.x; i < N; i += 32 * TX) KZ[i] = __ldg(cg.ktrans + i);
   __syncthreads();
 #pragma unroll 1
   for (int pass = 0; pass < 2; pass++) {   // 0: H -> z field;  1: G -> x and y fields
@@ -321,7 +321,7 @@ fft_z_disp_kernel(const float2* __restrict__ in, float2* __restrict__ o0, float2
                        : make_float2(__fmul_rn(d.x, s), __fmul_rn(d.y, s));
     }
     if (pass) __syncthreads();  // the first transform's exchange buffer has been read
-    fft_column<N, -1, true>(v, X, S, T, c, t);
+    fft_column<N, -1, true, TX>(v, X, S, T, c, t);
     if (valid) {
 #pragma unroll
       for (int m = 0; m < MT; m++) {
@@ -396,10 +396,26 @@ int own_fft_setup(baorec_ctx* ctx) {
 }
 
 // exchange buffer; the fused z passes add their tables (twiddles 8 N, + extra)
-template <int N>
-static size_t tile_bytes() { return Xch<N>::BYTES; }
-template <int N>
-static size_t fused_bytes(size_t extra) { return Xch<N>::BYTES + (size_t)N * sizeof(float2) + extra; }
+template <int N, int TX = FFT_TX>
+static size_t tile_bytes() { return Xch<N, TX>::BYTES; }
+template <int N, int TX = FFT_TX>
+static size_t fused_bytes(size_t extra) { return Xch<N, TX>::BYTES + (size_t)N * sizeof(float2) + extra; }
+
+// Columns per tile (option "fft_tile_cols"; the widths 4 and 16 are instantiated for N = 1024 only).  -1 = auto: the
+// z passes of a 1024-point axis -- fused or plain -- take 16 columns (128-byte row segments, one CTA of 512 threads per
+// SM), every other pass 8 (64-byte segments, two CTAs of 256 threads).  Measured at 1024^3
+// (profiles/r2_ab_fft_tile_cols.jsonl, r2_fft_zplain_probe.jsonl): with 16 columns fft_z_solve 6.14 -> 5.00 ms,
+// fft_z_disp 7.91 -> 6.42 ms, the plain z pass 3.0 -> 2.35 ms -- along z consecutive rows of a column are a whole plane
+// (4 MB) apart, every row segment opens its own DRAM page, and a 128-byte segment moves twice the data per activation
+// -- while the y pass loses (2.03 -> 2.21 ms: its rows are 4 KB apart, and one CTA per SM overlaps load, exchange and
+// store worse than two), the 512-point z pass loses slightly (0.55 -> 0.58 ms at 512^3: 1 MB planes) and 4 columns
+// (32-byte segments, four CTAs) lose everywhere (fft_z_disp 13.8 ms).
+static int tile_cols(const baorec_ctx* ctx, int n, bool z_axis) {
+  if (n != 1024) return FFT_TX;
+  const int o = ctx->opt_fft_tile_cols;
+  if (o == 4 || o == 16 || o == 8) return o;
+  return z_axis ? 16 : FFT_TX;
+}
 
 #define FFT_DISPATCH_N(n, CALL)     \
   switch (n) {                      \
@@ -439,14 +455,24 @@ static ColGeom geom_z(const baorec_ctx* ctx) {  // transform along z, tiles over
   return g;
 }
 
+template <int N, int DIR, int TX>
+static int launch_cols_tx(baorec_ctx* ctx, const float2* in, float2* out, const ColGeom& g, int nouter, const float2* tw,
+                          int herm, cudaStream_t st) {
+  BR_TRY(set_smem((fft_cols_kernel<N, DIR, TX>), (tile_bytes<N, TX>())));
+  dim3 grid(cdiv(g.ncols, TX), nouter);
+  BR_LAUNCH_NAMED(ctx, DIR > 0 ? "fft_cols_kernel<fwd>" : "fft_cols_kernel<inv>", (fft_cols_kernel<N, DIR, TX>), grid,
+                  32 * TX, (tile_bytes<N, TX>()), st, in, out, g, tw, herm);
+  return BAOREC_OK;
+}
 template <int N, int DIR>
 static int launch_cols(baorec_ctx* ctx, const float2* in, float2* out, const ColGeom& g, int nouter, const float2* tw,
-                       int herm, cudaStream_t st) {
-  BR_TRY(set_smem(fft_cols_kernel<N, DIR>, tile_bytes<N>()));
-  dim3 grid(cdiv(g.ncols, FFT_TX), nouter);
-  BR_LAUNCH_NAMED(ctx, DIR > 0 ? "fft_cols_kernel<fwd>" : "fft_cols_kernel<inv>", (fft_cols_kernel<N, DIR>), grid,
-                  FFT_THREADS, tile_bytes<N>(), st, in, out, g, tw, herm);
-  return BAOREC_OK;
+                       int herm, bool z_axis, cudaStream_t st) {
+  if (N == 1024) {
+    const int tx = tile_cols(ctx, N, z_axis);
+    if (tx == 4) return launch_cols_tx<1024, DIR, 4>(ctx, in, out, g, nouter, tw, herm, st);
+    if (tx == 16) return launch_cols_tx<1024, DIR, 16>(ctx, in, out, g, nouter, tw, herm, st);
+  }
+  return launch_cols_tx<N, DIR, FFT_TX>(ctx, in, out, g, nouter, tw, herm, st);
 }
 
 static int cols_pass(baorec_ctx* ctx, float2* data, int axis /*1 = y, 2 = z*/, int dir, cudaStream_t st,
@@ -456,8 +482,8 @@ static int cols_pass(baorec_ctx* ctx, float2* data, int axis /*1 = y, 2 = z*/, i
   const int nouter = axis == 1 ? ctx->nz : ctx->ny;
   const float2* tw = ctx->d_tw[axis - 1];
 #define CALL(NN)                                                                    \
-  if (dir > 0) BR_TRY((launch_cols<NN, 1>(ctx, data, data, g, nouter, tw, herm, st)));    \
-  else BR_TRY((launch_cols<NN, -1>(ctx, data, data, g, nouter, tw, herm, st)));
+  if (dir > 0) BR_TRY((launch_cols<NN, 1>(ctx, data, data, g, nouter, tw, herm, axis == 2, st)));    \
+  else BR_TRY((launch_cols<NN, -1>(ctx, data, data, g, nouter, tw, herm, axis == 2, st)));
   FFT_DISPATCH_N(n, CALL)
 #undef CALL
   return BAOREC_OK;
@@ -508,14 +534,19 @@ int own_fused_los_solve(baorec_ctx* ctx, const baorec_params* p, float* mesh, fl
   op.n_iter = p->n_iter;
   op.invM = (float)(1.0 / (double)ctx->M);
   const ColGeom g = geom_z(ctx);
-  dim3 grid(cdiv(g.ncols, FFT_TX), ctx->ny);
-#define CALL(NN)                                                                                          \
-  BR_TRY(set_smem(fft_z_solve_kernel<NN>, fused_bytes<NN>(NN * 12)));                                             \
-  BR_LAUNCH_NAMED(ctx, "fft_z_solve_kernel", fft_z_solve_kernel<NN>, grid, FFT_THREADS, fused_bytes<NN>(NN * 12), st, work, \
-                  keep, g, ctx->d_tw[1], op);
+#define CALL(NN, TX)                                                                                               \
+  {                                                                                                                \
+    dim3 grid(cdiv(g.ncols, TX), ctx->ny);                                                                         \
+    BR_TRY(set_smem((fft_z_solve_kernel<NN, TX>), (fused_bytes<NN, TX>(NN * 12))));                                \
+    BR_LAUNCH_NAMED(ctx, "fft_z_solve_kernel", (fft_z_solve_kernel<NN, TX>), grid, 32 * TX, (fused_bytes<NN, TX>(NN * 12)), st, \
+                    work, keep, g, ctx->d_tw[1], op);                                                              \
+  }
   switch (ctx->nz) {
-    case 1024: { CALL(1024); } break;
-    case 2048: { CALL(2048); } break;
+    case 1024: {
+      const int tx = tile_cols(ctx, 1024, true);
+      if (tx == 4) CALL(1024, 4) else if (tx == 16) CALL(1024, 16) else CALL(1024, FFT_TX)
+    } break;
+    case 2048: CALL(2048, FFT_TX) break;
     default: set_error("own FFT: the fused z pass needs nz = 1024 or 2048"); return BAOREC_ERR_INVALID;
   }
 #undef CALL
@@ -530,7 +561,6 @@ int own_displacements(baorec_ctx* ctx, const float* mesh, const float2* from_k, 
   op.potential = algorithm == BAOREC_MULTIGRID;
   op.invM = (float)(1.0 / (double)ctx->M);
   const ColGeom g = geom_z(ctx);
-  dim3 grid(cdiv(g.ncols, FFT_TX), ctx->ny);
   const float2* src = from_k;
   if (!from_k) {  // delta_k (phi_k) first: the z kernel starts in k space
     BR_TRY(x_r2c(ctx, mesh, w0, st));
@@ -538,12 +568,21 @@ int own_displacements(baorec_ctx* ctx, const float* mesh, const float2* from_k, 
     BR_TRY(cols_pass(ctx, w0, 2, +1, st));
     src = w0;
   }
-#define CALL(NN)                                                                                               \
-  BR_TRY(set_smem(fft_z_disp_kernel<NN>, fused_bytes<NN>(NN * 4)));                                                   \
-  BR_LAUNCH_NAMED(ctx, "fft_z_disp_kernel", fft_z_disp_kernel<NN>, grid, FFT_THREADS, fused_bytes<NN>(NN * 4), st, src, w0, \
-                  w1, w2, g, ctx->d_tw[1], op);
-  FFT_DISPATCH_N(ctx->nz, CALL)
+#define CALL_TX(NN, TX)                                                                                            \
+  {                                                                                                                \
+    dim3 grid_tx(cdiv(g.ncols, TX), ctx->ny);                                                                      \
+    BR_TRY(set_smem((fft_z_disp_kernel<NN, TX>), (fused_bytes<NN, TX>(NN * 4))));                                  \
+    BR_LAUNCH_NAMED(ctx, "fft_z_disp_kernel", (fft_z_disp_kernel<NN, TX>), grid_tx, 32 * TX, (fused_bytes<NN, TX>(NN * 4)), st, \
+                    src, w0, w1, w2, g, ctx->d_tw[1], op);                                                         \
+  }
+#define CALL(NN) CALL_TX(NN, FFT_TX)
+  if (ctx->nz == 1024 && tile_cols(ctx, 1024, true) == 4) CALL_TX(1024, 4)
+  else if (ctx->nz == 1024 && tile_cols(ctx, 1024, true) == 16) CALL_TX(1024, 16)
+  else {
+    FFT_DISPATCH_N(ctx->nz, CALL)
+  }
 #undef CALL
+#undef CALL_TX
   float2* w[3] = {w0, w1, w2};
   float* o[3] = {px, py, pz};
   for (int c = 0; c < 3; c++) {

@@ -20,7 +20,7 @@ def dev(a):
 def options(B, **kw):
     ctx = B.Context.get(0)
     defaults = {"bin_min_particles": 1 << 18, "fuse_kspace": 1, "own_fft": -1, "gather_tiles": 1,
-                "fft_split_planes": 0, "scatter_tiles": 0,
+                "fft_split_planes": 0, "scatter_tiles": 0, "fft_tile_cols": -1,
                 "unified_sort": 1}
     try:
         for k, v in kw.items():
@@ -208,8 +208,8 @@ def test_own_fft_smooth_and_displacements_match_cufft_and_oracle(B, O, shape):
         assert rel_rms(out[1][1][a], opsi[a]) < 5e-6
 
 
-@pytest.mark.parametrize("los", [(0.0, 0.0, 1.0), (0.0, 1.0, 0.0)])
-def test_own_fft_fused_z_pass_matches_the_oracle(B, O, los):
+@pytest.mark.parametrize("los,tile_cols", [((0.0, 0.0, 1.0), 8), ((0.0, 1.0, 0.0), 8), ((0.0, 0.0, 1.0), 4), ((0.0, 0.0, 1.0), 16)])
+def test_own_fft_fused_z_pass_matches_the_oracle(B, O, los, tile_cols):
     """run! + read_shifts with own_fft = 1 on a mesh with nz = 1024: the z pass is ONE kernel (forward z transform,
     smoothing + normalisation + all iterations in registers, delta_k kept, inverse z transform) and the read-back emits
     the three displacement fields from one read of delta_k."""
@@ -221,7 +221,7 @@ def test_own_fft_fused_z_pass_matches_the_oracle(B, O, los):
     omesh = O.run(orec, grid, *[p.copy() for p in pos], w)
     oshift = O.read_shifts(orec, *pos, omesh, "sum")
     d = [dev(p) for p in pos]
-    with options(B, own_fft=1):
+    with options(B, own_fft=1, fft_tile_cols=tile_cols):      # 4 / 16 columns per tile: the experimental widths of the N = 1024 kernels
         rec = B.IterativeRecon(**kw)
         mesh = B.run(rec, grid, *d, dev(w))
         s = B.read_shifts(rec, *d, mesh, field="sum")
