@@ -695,10 +695,14 @@ static int dist_r2c_peer(baorec_ctx* ctx, const float* slab, float2* K, int C, c
   BR_CUDA(cudaEventRecord(ctx->ev_a2a[1], cs));
   ctx->n_fft++;
   BR_TRY(peer_wait(ctx, F_ARR_K, base + (unsigned)C, st));  // all chunks of all ranks have landed in my K buffer
-  BR_CUFFT(cufftSetStream(ctx->p1d_s, st));
-  int pi = prof_begin(ctx, "cufft_1d_z", st);
-  BR_CUFFT(cufftExecC2C(ctx->p1d_s, (cufftComplex*)ctx->own_recv[0], (cufftComplex*)K, CUFFT_FORWARD));
-  prof_end(ctx, pi, st);
+  if (own_slab_z_available(ctx)) {
+    BR_TRY(own_slab_z(ctx, ctx->own_recv[0], K, +1, st));
+  } else {
+    BR_CUFFT(cufftSetStream(ctx->p1d_s, st));
+    int pi = prof_begin(ctx, "cufft_1d_z", st);
+    BR_CUFFT(cufftExecC2C(ctx->p1d_s, (cufftComplex*)ctx->own_recv[0], (cufftComplex*)K, CUFFT_FORWARD));
+    prof_end(ctx, pi, st);
+  }
   ctx->n_fft++;
   BR_TRY(peer_signal(ctx, F_FREE_K, seq, st));                  // my K receive buffer may be overwritten
   BR_CUDA(cudaStreamWaitEvent(st, ctx->ev_a2a[1], 0));     // A may be reused once my own copies have left it
@@ -737,10 +741,15 @@ static int c2r_peer_send(baorec_ctx* ctx, float2* K, int slot, int C, C2RPeer* h
   h->base = (h->seq - 1) * (unsigned)C;
   const int f_arr = slot ? F_ARR_A1 : F_ARR_A0, f_free = slot ? F_FREE_A1 : F_FREE_A0;
   cudaEvent_t ev_z = ctx->ev_a2a[slot ? 4 : 0], ev_w = ctx->ev_a2a[slot ? 5 : 2];
-  BR_CUFFT(cufftSetStream(ctx->p1d_s, st));
-  int pi = prof_begin(ctx, "cufft_1d_z", st);
-  BR_CUFFT(cufftExecC2C(ctx->p1d_s, (cufftComplex*)K, (cufftComplex*)K, CUFFT_INVERSE));
-  prof_end(ctx, pi, st);
+  int pi = 0;
+  if (own_slab_z_available(ctx)) {
+    BR_TRY(own_slab_z(ctx, K, K, -1, st));
+  } else {
+    BR_CUFFT(cufftSetStream(ctx->p1d_s, st));
+    pi = prof_begin(ctx, "cufft_1d_z", st);
+    BR_CUFFT(cufftExecC2C(ctx->p1d_s, (cufftComplex*)K, (cufftComplex*)K, CUFFT_INVERSE));
+    prof_end(ctx, pi, st);
+  }
   ctx->n_fft++;
   BR_CUDA(cudaEventRecord(ev_z, st));
   BR_CUDA(cudaStreamWaitEvent(cs, ev_z, 0));
@@ -1097,6 +1106,7 @@ int baorec_plan_dist(baorec_ctx* ctx, int nx, int ny, int nz, const float box_si
       BR_CUFFT(cufftSetWorkArea(ctx->c2r, work));
     }
   }
+  BR_TRY(own_fft_setup(ctx));  // twiddle tables of the column kernels (the slab z pass uses them where they beat cuFFT's strided plan)
   {
     // receive buffers are allocated here at their final size: their addresses are exported via IPC
     const size_t slab_c = (size_t)nzl * ny * (nx / 2 + 1);

@@ -375,6 +375,8 @@ int randoms_combine(baorec_ctx* ctx, float* out, const float* dat, const float* 
 // fft.cu
 bool own_fft_available(const baorec_ctx* ctx);
 bool own_fft_fused_available(const baorec_ctx* ctx);
+bool own_slab_z_available(const baorec_ctx* ctx);
+int own_slab_z(baorec_ctx* ctx, const float2* in, float2* out, int dir, cudaStream_t st);
 int own_fft_setup(baorec_ctx* ctx);
 int own_r2c(baorec_ctx* ctx, const float* in, float2* out, cudaStream_t st);
 int own_c2r(baorec_ctx* ctx, float2* in, float* out, cudaStream_t st);

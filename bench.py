@@ -496,7 +496,8 @@ def main():
     chunks = 1
     if world > 1:      # launches of the 2-D transforms per slab transform = plane chunks of the pipelined exchange
         c2 = sum(c for k, (_, c) in prof.items() if k.startswith("cufft_2d"))
-        c1 = sum(c for k, (_, c) in prof.items() if k.startswith("cufft_1d_z"))
+        # z passes of the slab transforms: cuFFT's strided plan, or the column kernel (at N > 1 it runs nowhere else)
+        c1 = sum(c for k, (_, c) in prof.items() if k.startswith("cufft_1d_z") or k.startswith("fft_cols_kernel"))
         chunks = max(1, round(c2 / max(c1, 1)))
     for name, (ms, cnt) in prof.items():
         ab = algorithmic_bytes(name, M // world, Mc // world, N // world, chunks)   # per-rank (slab) bytes
@@ -522,7 +523,7 @@ def main():
         name = "peer_copies" if "peer_copies" in prof else "nccl_all_to_all"
         if name in prof:
             ms, cnt = prof[name]
-            transforms = sum(c for k, (_, c) in prof.items() if k.startswith("cufft_1d_z"))
+            transforms = sum(c for k, (_, c) in prof.items() if k.startswith("cufft_1d_z") or k.startswith("fft_cols_kernel"))
             sent = 8 * (Mc // world) * (world - 1) / world * transforms          # bytes over NVLink, this rank, timed region
             nv_peak, nv_src = 770.0, "measured peer copy per direction (B200_PROFILING.md; nominal 900)"
             exchange = {"scheme": ("peer copies + sequence flags (remote blocks: %s)" % ("one SM kernel per chunk" if world >= 5 and not os.environ.get("BAOREC_PUSH_SM") == "0" else "copy engines"))

@@ -206,3 +206,29 @@ def test_run_dist_with_randoms(B, O, dctx, algo, los, lo):
     for a in range(3):
         assert rel_rms(s[a].cpu().numpy(), ref[a]) < 1e-4
         assert maxabs(s[a].cpu().numpy(), ref[a]) < 1e-3
+
+
+@pytest.mark.parametrize("own", [-1, 0])
+def test_slab_z_pass_of_a_1024_point_axis(B, dctx, own):
+    """nz = 1024 on slabs: the z pass of the K[z][yl][x] layout is the column kernel of csrc/fft.cu (16 columns per tile,
+    own_slab_z) instead of cuFFT's strided plan (option own_fft = 0): both match rfftn and invert back."""
+    shape = (40, 16, 1024)
+    nx, ny, nz = shape
+    dctx.set_option("own_fft", own)
+    try:
+        B.dist.plan(dctx, shape, np.full(3, 100.0, np.float32), np.zeros(3, np.float32), exchange="peer")
+        a = np.random.default_rng(3).standard_normal((nz, ny, nx)).astype(np.float32)
+        dctx.profile(True)
+        T = B.dist.dist_r2c(dctx, dev(a))
+        back = torch.empty((nz, ny, nx), dtype=torch.float32, device="cuda")
+        B.dist.dist_c2r(dctx, T.clone(), back)
+        names = set(dctx.profile_read())
+        dctx.profile(False)
+        assert any(k.startswith("fft_cols_kernel") for k in names) == (own != 0), names
+        assert any(k.startswith("cufft_1d_z") for k in names) == (own == 0), names
+        ref = np.fft.rfftn(a.astype(np.float64), axes=(0, 1, 2))
+        got = T.cpu().numpy()
+        assert rel_rms(got.real, ref.real) < 1e-5 and rel_rms(got.imag, ref.imag) < 1e-5
+        assert rel_rms(back.cpu().numpy() / a.size, a) < 1e-5
+    finally:
+        dctx.set_option("own_fft", -1)
