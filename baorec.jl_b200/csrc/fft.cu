@@ -46,6 +46,7 @@ __device__ __forceinline__ float2 twd(const float2* tw, int idx) {
 
 struct ColGeom {
   int ncols;            // length of the contiguous axis (nx/2+1)
+  int nouter;           // z passes: number of rows (y) -- their columns are tiled over the flat index iy * ncols + ix
   size_t stride;        // elements between consecutive points of a transform
   size_t outer_stride;  // elements between consecutive tiles rows (blockIdx.y)
   const float* kx;      // k tables: contiguous axis, outer axis, transform axis
@@ -236,10 +237,13 @@ fft_z_solve_kernel(float2* __restrict__ data, float2* __restrict__ keep, ColGeom
   float2* S = reinterpret_cast<float2*>(smem_raw);
   constexpr int M = N / 32, MT = M / 32;
   static_assert(M >= 32, "the fused z pass needs N >= 1024");
+  // tiles run over the FLAT column index q = iy * xh + ix (the columns of a z pass are contiguous in memory across
+  // rows): every tile is one aligned 64- / 128-byte segment per plane and none is partly empty (xh = nx/2 + 1 is odd)
   const int c = threadIdx.x & (TX - 1), t = threadIdx.x / TX;
-  const int ix = blockIdx.x * TX + c, iy = blockIdx.y;
-  const bool valid = ix < cg.ncols;
-  const size_t base = (size_t)iy * cg.outer_stride + ix;
+  const unsigned q = blockIdx.x * TX + c;
+  const bool valid = q < (unsigned)cg.ncols * (unsigned)cg.nouter;
+  const int iy = valid ? (int)(q / (unsigned)cg.ncols) : 0, ix = valid ? (int)(q - (unsigned)iy * (unsigned)cg.ncols) : 0;
+  const size_t base = q;
   float2 v[M], X[MT][32];
   if (valid) load_column<N>(v, data + base, cg.stride, t);
   else {
@@ -255,7 +259,7 @@ fft_z_solve_kernel(float2* __restrict__ data, float2* __restrict__ keep, ColGeom
   }
   __syncthreads();
   fft_column<N, 1, true, TX>(v, X, S, T, c, t);
-  const OpLosSolve::Col col = op.column(valid ? __ldg(cg.kx + ix) : 0.f, __ldg(cg.kouter + iy), valid ? ix : 0, iy);
+  const OpLosSolve::Col col = op.column(__ldg(cg.kx + ix), __ldg(cg.kouter + iy), ix, iy);
   const double dc8 = __ldg(op.scal + 8);
 #pragma unroll
   for (int m = 0; m < MT; m++)
@@ -293,10 +297,11 @@ fft_z_disp_kernel(const float2* __restrict__ in, float2* __restrict__ o0, float2
   float2* S = reinterpret_cast<float2*>(smem_raw);
   constexpr int M = N / 32, MT = M >= 32 ? M / 32 : 1;
   const int c = threadIdx.x & (TX - 1), t = threadIdx.x / TX;
-  const int ix = blockIdx.x * TX + c, iy = blockIdx.y;
-  const bool valid = ix < cg.ncols;
-  const size_t base = (size_t)iy * cg.outer_stride + ix;
-  const float kx = valid ? __ldg(cg.kx + ix) : 0.f, ky = __ldg(cg.kouter + iy);
+  const unsigned q = blockIdx.x * TX + c;  // flat column index iy * xh + ix (see fft_z_solve_kernel)
+  const bool valid = q < (unsigned)cg.ncols * (unsigned)cg.nouter;
+  const int iy = valid ? (int)(q / (unsigned)cg.ncols) : 0, ix = valid ? (int)(q - (unsigned)iy * (unsigned)cg.ncols) : 0;
+  const size_t base = q;
+  const float kx = __ldg(cg.kx + ix), ky = __ldg(cg.kouter + iy);
   float2* T = stage_twiddles<N, TX>(S, tw);
   float* KZ = reinterpret_cast<float*>(T + N);
   for (int i = threadIdx.x; i < N; i += 32 * TX) KZ[i] = __ldg(cg.ktrans + i);
@@ -435,6 +440,7 @@ static int set_smem(K kernel, size_t bytes) {
 static ColGeom geom_y(const baorec_ctx* ctx) {  // transform along y, tiles over (x, z)
   ColGeom g;
   g.ncols = ctx->xh;
+  g.nouter = ctx->nz;
   g.stride = ctx->xh;
   g.outer_stride = (size_t)ctx->xh * ctx->ny;
   g.kx = ctx->d_k[0];
@@ -446,6 +452,7 @@ static ColGeom geom_y(const baorec_ctx* ctx) {  // transform along y, tiles over
 static ColGeom geom_z(const baorec_ctx* ctx) {  // transform along z, tiles over (x, y)
   ColGeom g;
   g.ncols = ctx->xh;
+  g.nouter = ctx->ny;
   g.stride = (size_t)ctx->xh * ctx->ny;
   g.outer_stride = ctx->xh;
   g.kx = ctx->d_k[0];
@@ -477,9 +484,13 @@ static int launch_cols(baorec_ctx* ctx, const float2* in, float2* out, const Col
 
 static int cols_pass(baorec_ctx* ctx, float2* data, int axis /*1 = y, 2 = z*/, int dir, cudaStream_t st,
                      int herm = 0) {
-  const ColGeom g = axis == 1 ? geom_y(ctx) : geom_z(ctx);
+  ColGeom g = axis == 1 ? geom_y(ctx) : geom_z(ctx);
   const int n = axis == 1 ? ctx->ny : ctx->nz;
-  const int nouter = axis == 1 ? ctx->nz : ctx->ny;
+  int nouter = axis == 1 ? ctx->nz : ctx->ny;
+  if (axis == 2) {  // the columns of a z pass are contiguous across rows: one flat row of xh * ny columns (aligned tiles, none partly empty)
+    g.ncols = ctx->xh * ctx->ny;
+    nouter = 1;
+  }
   const float2* tw = ctx->d_tw[axis - 1];
 #define CALL(NN)                                                                    \
   if (dir > 0) BR_TRY((launch_cols<NN, 1>(ctx, data, data, g, nouter, tw, herm, axis == 2, st)));    \
@@ -497,15 +508,16 @@ bool own_slab_z_available(const baorec_ctx* ctx) {
 }
 int own_slab_z(baorec_ctx* ctx, const float2* in, float2* out, int dir, cudaStream_t st) {
   ColGeom g;
-  g.ncols = ctx->xh;
+  g.ncols = ctx->xh * ctx->ny_loc;  // flat: the nyl * xh columns of the rank are contiguous
+  g.nouter = 1;
   g.stride = (size_t)ctx->xh * ctx->ny_loc;
-  g.outer_stride = ctx->xh;
+  g.outer_stride = 0;
   g.kx = ctx->d_k[0];
   g.kouter = ctx->d_k[1];
   g.ktrans = ctx->d_k[2];
   g.outer_is_y = 1;
-  if (dir > 0) return launch_cols<1024, 1>(ctx, in, out, g, ctx->ny_loc, ctx->d_tw[1], 0, true, st);
-  return launch_cols<1024, -1>(ctx, in, out, g, ctx->ny_loc, ctx->d_tw[1], 0, true, st);
+  if (dir > 0) return launch_cols<1024, 1>(ctx, in, out, g, 1, ctx->d_tw[1], 0, true, st);
+  return launch_cols<1024, -1>(ctx, in, out, g, 1, ctx->d_tw[1], 0, true, st);
 }
 
 static int x_r2c(baorec_ctx* ctx, const float* in, float2* out, cudaStream_t st) {
@@ -555,7 +567,7 @@ int own_fused_los_solve(baorec_ctx* ctx, const baorec_params* p, float* mesh, fl
   const ColGeom g = geom_z(ctx);
 #define CALL(NN, TX)                                                                                               \
   {                                                                                                                \
-    dim3 grid(cdiv(g.ncols, TX), ctx->ny);                                                                         \
+    dim3 grid(cdiv((size_t)g.ncols * g.nouter, TX), 1);                                                            \
     BR_TRY(set_smem((fft_z_solve_kernel<NN, TX>), (fused_bytes<NN, TX>(NN * 12))));                                \
     BR_LAUNCH_NAMED(ctx, "fft_z_solve_kernel", (fft_z_solve_kernel<NN, TX>), grid, 32 * TX, (fused_bytes<NN, TX>(NN * 12)), st, \
                     work, keep, g, ctx->d_tw[1], op);                                                              \
@@ -589,7 +601,7 @@ int own_displacements(baorec_ctx* ctx, const float* mesh, const float2* from_k, 
   }
 #define CALL_TX(NN, TX)                                                                                            \
   {                                                                                                                \
-    dim3 grid_tx(cdiv(g.ncols, TX), ctx->ny);                                                                      \
+    dim3 grid_tx(cdiv((size_t)g.ncols * g.nouter, TX), 1);                                                         \
     BR_TRY(set_smem((fft_z_disp_kernel<NN, TX>), (fused_bytes<NN, TX>(NN * 4))));                                  \
     BR_LAUNCH_NAMED(ctx, "fft_z_disp_kernel", (fft_z_disp_kernel<NN, TX>), grid_tx, 32 * TX, (fused_bytes<NN, TX>(NN * 4)), st, \
                     src, w0, w1, w2, g, ctx->d_tw[1], op);                                                         \

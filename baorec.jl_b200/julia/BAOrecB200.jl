@@ -392,6 +392,46 @@ function power_multipoles(rho::CuArray{Float32,3}, los = (0f0, 0f0, 1f0); kmin =
     (k = k, nmodes = nmodes, p0 = p0, p2 = p2, p4 = p4)
 end
 
+# The helpers' own configuration in ONE call (test_helpers/simulation.py:36-70 with test_helpers/powspec_auto.conf: TSC +
+# interlaced grids): compute_auto_box(x, y, z, w, ...) / compute_auto_box_rand(x, y, z, w, rx, ry, rz, rw, ...) on device
+# catalogs, on the grid and box of the last plan! (mas: 0 = CIC, 1 = TSC, 2 = PCS).  The catalogs are not modified.
+function compute_auto_box(x::CuVector{Float32}, y::CuVector{Float32}, z::CuVector{Float32}, w::CuVector{Float32}, los = (0f0, 0f0, 1f0);
+                          kmin = 0.0, dk, nbins::Integer, mas::Integer = 1, interlace::Bool = true, shot = 0.0,
+                          randoms::Union{NTuple{4,CuVector{Float32}},Nothing} = nothing)
+    k, nmodes, p0, p2, p4 = (Vector{Float64}(undef, nbins) for _ in 1:5)
+    rx, ry, rz, rw = randoms === nothing ? (nothing, nothing, nothing, nothing) : randoms
+    nr = randoms === nothing ? 0 : length(rx)
+    check(ccall((:baorec_compute_auto_box_f32, libbaorec), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint, Cint,
+                 Ptr{Cfloat}, Cdouble, Cdouble, Cint, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cvoid}),
+                context(), ptr(x), ptr(y), ptr(z), ptr(w), length(x), ptr(rx), ptr(ry), ptr(rz), ptr(rw), nr, mas, interlace ? 1 : 0,
+                f3(los), kmin, dk, nbins, shot, k, nmodes, p0, p2, p4, stream()))
+    (k = k, nmodes = nmodes, p0 = p0, p2 = p2, p4 = p4)
+end
+
+# Positions of the interlaced mesh (half a cell further along every axis, periodic) on the grid of the last plan!.
+function interlace_positions(x::CuVector{Float32}, y::CuVector{Float32}, z::CuVector{Float32})
+    ox, oy, oz = similar(x), similar(y), similar(z)
+    check(ccall((:baorec_interlace_positions_f32, libbaorec), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                context(), ptr(x), ptr(y), ptr(z), length(x), ptr(ox), ptr(oy), ptr(oz), stream()))
+    (ox, oy, oz)
+end
+
+# The interlaced estimate from two pairs of meshes (rho / randoms painted from the catalog and from interlace_positions).
+function power_multipoles_interlaced(rho::CuArray{Float32,3}, rho_shifted::CuArray{Float32,3}, los = (0f0, 0f0, 1f0); kmin = 0.0, dk,
+                                     nbins::Integer, mas_power::Integer = 3, shot = 0.0,
+                                     randoms::Union{CuArray{Float32,3},Nothing} = nothing,
+                                     randoms_shifted::Union{CuArray{Float32,3},Nothing} = nothing)
+    k, nmodes, p0, p2, p4 = (Vector{Float64}(undef, nbins) for _ in 1:5)
+    check(ccall((:baorec_power_multipoles_interlaced_f32, libbaorec), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cfloat}, Cdouble, Cdouble, Cint, Cint, Cdouble, Ptr{Cdouble},
+                 Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cvoid}),
+                context(), ptr(rho), ptr(randoms), ptr(rho_shifted), ptr(randoms_shifted), f3(los), kmin, dk, nbins, mas_power, shot,
+                k, nmodes, p0, p2, p4, stream()))
+    (k = k, nmodes = nmodes, p0 = p0, p2 = p2, p4 = p4)
+end
+
 # Many mocks per process (the reference's README: "one process, many reconstructions"): run! + reconstructed_positions
 # (or read_shifts with positions = false) for every HOST catalog (x, y, z, w) of a periodic box, the PCIe transfers of
 # neighbouring catalogs overlapping the solve.  Returns one (x, y, z) tuple of Vectors per catalog.
