@@ -237,13 +237,14 @@ fft_z_solve_kernel(float2* __restrict__ data, float2* __restrict__ keep, ColGeom
   float2* S = reinterpret_cast<float2*>(smem_raw);
   constexpr int M = N / 32, MT = M / 32;
   static_assert(M >= 32, "the fused z pass needs N >= 1024");
-  // tiles run over the FLAT column index q = iy * xh + ix (the columns of a z pass are contiguous in memory across
-  // rows): every tile is one aligned 64- / 128-byte segment per plane and none is partly empty (xh = nx/2 + 1 is odd)
+  // One tile row per y (grid.y = ny; the last tile of a row holds one column: xh = nx/2 + 1 is odd).  The flat tiling of
+  // the other z passes (fft_z_disp_kernel) measured SLOWER here: 5.79 instead of 5.02 ms at 1024^3 -- this kernel
+  // writes two planes-apart streams (delta_k kept, the column) next to the one it reads.
   const int c = threadIdx.x & (TX - 1), t = threadIdx.x / TX;
-  const unsigned q = blockIdx.x * TX + c;
-  const bool valid = q < (unsigned)cg.ncols * (unsigned)cg.nouter;
-  const int iy = valid ? (int)(q / (unsigned)cg.ncols) : 0, ix = valid ? (int)(q - (unsigned)iy * (unsigned)cg.ncols) : 0;
-  const size_t base = q;
+  const int ix0 = blockIdx.x * TX + c, iy = blockIdx.y;
+  const bool valid = ix0 < cg.ncols;
+  const int ix = valid ? ix0 : 0;
+  const size_t base = (size_t)iy * cg.outer_stride + ix0;
   float2 v[M], X[MT][32];
   if (valid) load_column<N>(v, data + base, cg.stride, t);
   else {
@@ -297,7 +298,10 @@ fft_z_disp_kernel(const float2* __restrict__ in, float2* __restrict__ o0, float2
   float2* S = reinterpret_cast<float2*>(smem_raw);
   constexpr int M = N / 32, MT = M >= 32 ? M / 32 : 1;
   const int c = threadIdx.x & (TX - 1), t = threadIdx.x / TX;
-  const unsigned q = blockIdx.x * TX + c;  // flat column index iy * xh + ix (see fft_z_solve_kernel)
+  // tiles run over the FLAT column index q = iy * xh + ix (the columns of a z pass are contiguous in memory across
+  // rows): every tile is one aligned 64- / 128-byte segment per plane and none is partly empty (xh = nx/2 + 1 is odd).
+  // Measured at 1024^3: 6.48 -> 5.70 ms here, the plain z pass 2.35 -> 2.07 ms.
+  const unsigned q = blockIdx.x * TX + c;
   const bool valid = q < (unsigned)cg.ncols * (unsigned)cg.nouter;
   const int iy = valid ? (int)(q / (unsigned)cg.ncols) : 0, ix = valid ? (int)(q - (unsigned)iy * (unsigned)cg.ncols) : 0;
   const size_t base = q;
@@ -567,7 +571,7 @@ int own_fused_los_solve(baorec_ctx* ctx, const baorec_params* p, float* mesh, fl
   const ColGeom g = geom_z(ctx);
 #define CALL(NN, TX)                                                                                               \
   {                                                                                                                \
-    dim3 grid(cdiv((size_t)g.ncols * g.nouter, TX), 1);                                                            \
+    dim3 grid(cdiv(g.ncols, TX), ctx->ny);                                                                         \
     BR_TRY(set_smem((fft_z_solve_kernel<NN, TX>), (fused_bytes<NN, TX>(NN * 12))));                                \
     BR_LAUNCH_NAMED(ctx, "fft_z_solve_kernel", (fft_z_solve_kernel<NN, TX>), grid, 32 * TX, (fused_bytes<NN, TX>(NN * 12)), st, \
                     work, keep, g, ctx->d_tw[1], op);                                                              \
