@@ -189,6 +189,7 @@ int baorec_set_option(baorec_ctx* ctx, const char* name, int64_t value) {
   else if (s == "gather_tiles") ctx->opt_gather_tiles = (int)value;
   else if (s == "gather_stage") ctx->opt_gather_stage = (int)value;
   else if (s == "fft_tile_cols") ctx->opt_fft_tile_cols = (int)value;
+  else if (s == "fft_prefetch") ctx->opt_fft_prefetch = (int)value;
   else if (s == "scatter_pairs") ctx->opt_scatter_pairs = (int)value;
   else if (s == "scatter_tiles") ctx->opt_scatter_tiles = (int)value;
   else if (s == "deterministic_scatter") ctx->opt_det_scatter = (int)value;

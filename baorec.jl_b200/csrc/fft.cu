@@ -53,6 +53,7 @@ struct ColGeom {
   const float* kouter;
   const float* ktrans;
   int outer_is_y;       // 1: outer = y, transform = z (z pass); 0: outer = z, transform = y (y pass)
+  int prefetch;         // > 0: every CTA asks L2 for the tile of the CTA `prefetch` places further on in launch order (option "fft_prefetch")
 };
 
 // Exchange buffer of the four-step FFT: per column M rows (k2) of 33 slots (n1; 33 = one pad slot, so that the reads
@@ -111,12 +112,37 @@ __device__ __forceinline__ void fft_column(float2 (&v)[N / 32], float2 (&out)[(N
   }
 }
 
-template <int N>
+// STREAM: evict-first loads (ld.global.cs).  Measured at 1024^3: together with evict-first stores they help the read-back's
+// z pass (fft_z_disp 5.73 -> 5.53 ms: one read, three write streams), do nothing for fft_z_solve and slow the plain
+// y pass down (2.02 -> 2.21 ms) -- so only fft_z_disp uses them.
+template <int N, bool STREAM = false>
 __device__ __forceinline__ void load_column(float2 (&v)[N / 32], const float2* __restrict__ src, size_t stride, int t) {
   const float2* p = src + (size_t)t * stride;
   const size_t step = 32 * stride;
 #pragma unroll
-  for (int j = 0; j < N / 32; j++) v[j] = p[(size_t)j * step];
+  for (int j = 0; j < N / 32; j++) v[j] = STREAM ? __ldcs(p + (size_t)j * step) : p[(size_t)j * step];
+}
+
+// L2 prefetch of the tile another CTA will load `dist` CTAs later (roughly: when this CTA's slot is free again): the
+// column loads of that CTA then wait for L2 instead of DRAM.  One prefetch at the first and one at the last byte of
+// every row segment (the segments of a y pass are not aligned), rows dealt over the threads of the CTA.
+template <int N, int TX>
+__device__ __forceinline__ void prefetch_tile(const float2* __restrict__ in, const ColGeom& cg, int dist, bool flat) {
+  const unsigned nbx = gridDim.x;
+  const unsigned long long lin = (unsigned long long)blockIdx.y * nbx + blockIdx.x + (unsigned)dist;
+  const unsigned by = (unsigned)(lin / nbx), bx = (unsigned)(lin - (unsigned long long)by * nbx);
+  if (by >= gridDim.y) return;
+  const size_t first = (size_t)by * cg.outer_stride + (size_t)bx * TX;
+  const size_t limit = flat ? (size_t)cg.ncols * cg.nouter : (size_t)by * cg.outer_stride + cg.ncols;  // one past the last column of the row
+  size_t last = first + TX - 1;
+  if (last >= limit) last = limit - 1;
+  if (first >= limit) return;
+  for (int r = threadIdx.x; r < N; r += 32 * TX) {
+    const float2* a = in + first + (size_t)r * cg.stride;
+    const float2* b = in + last + (size_t)r * cg.stride;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(b));
+  }
 }
 
 // ---- operators applied in the z pass (frequency index f along the transform axis) ----------------
@@ -205,6 +231,7 @@ fft_cols_kernel(const float2* __restrict__ in, float2* __restrict__ out, ColGeom
 #pragma unroll
     for (int j = 0; j < M; j++) v[j] = make_float2(0.f, 0.f);
   }
+  if (cg.prefetch > 0) prefetch_tile<N, TX>(in, cg, cg.prefetch, false);
   fft_column<N, DIR, false, TX>(v, X, S, tw, c, t);
   // Last pass before the C2R along x: the kx = 0 and kx = Nyquist columns must be real there.  FFTW
   // and pocketfft ignore their imaginary part; cuFFT's 1-D C2R does not, so it is dropped here
@@ -251,6 +278,7 @@ fft_z_solve_kernel(float2* __restrict__ data, float2* __restrict__ keep, ColGeom
 #pragma unroll
     for (int j = 0; j < M; j++) v[j] = make_float2(0.f, 0.f);
   }
+  if (cg.prefetch > 0) prefetch_tile<N, TX>(data, cg, cg.prefetch, false);
   float2* T = stage_twiddles<N, TX>(S, tw);
   double* GZ = reinterpret_cast<double*>(T + N);   // Gaussian of the z axis (Float64), then k_z
   float* KZ = reinterpret_cast<float*>(GZ + N);
@@ -306,6 +334,7 @@ fft_z_disp_kernel(const float2* __restrict__ in, float2* __restrict__ o0, float2
   const int iy = valid ? (int)(q / (unsigned)cg.ncols) : 0, ix = valid ? (int)(q - (unsigned)iy * (unsigned)cg.ncols) : 0;
   const size_t base = q;
   const float kx = __ldg(cg.kx + ix), ky = __ldg(cg.kouter + iy);
+  if (cg.prefetch > 0) prefetch_tile<N, TX>(in, cg, cg.prefetch, true);
   float2* T = stage_twiddles<N, TX>(S, tw);
   float* KZ = reinterpret_cast<float*>(T + N);
   for (int i = threadIdx.x; i < N; i += 32 * TX) KZ[i] = __ldg(cg.ktrans + i);
@@ -313,7 +342,10 @@ fft_z_disp_kernel(const float2* __restrict__ in, float2* __restrict__ o0, float2
 #pragma unroll 1
   for (int pass = 0; pass < 2; pass++) {   // 0: H -> z field;  1: G -> x and y fields
     float2 v[M], X[MT][32];
-    if (valid) load_column<N>(v, in + base, cg.stride, t);
+    if (valid) {
+      if (pass == 0) load_column<N, false>(v, in + base, cg.stride, t);  // read again by pass 1: stays in L2
+      else load_column<N, true>(v, in + base, cg.stride, t);
+    }
 #pragma unroll
     for (int j = 0; j < M; j++) {
       const float kz = KZ[t + 32 * j];
@@ -341,10 +373,10 @@ fft_z_disp_kernel(const float2* __restrict__ in, float2* __restrict__ o0, float2
             const size_t o = base + (size_t)(k2 + M * k1) * cg.stride;
             const float2 r = X[m][fft_bitrev<32>(k1)];
             if (pass == 0) {
-              o2[o] = r;
+              __stcs(o2 + o, r);
             } else {  // i k g = (-g.y k, g.x k)
-              o0[o] = make_float2(__fmul_rn(-r.y, kx), __fmul_rn(r.x, kx));
-              o1[o] = make_float2(__fmul_rn(-r.y, ky), __fmul_rn(r.x, ky));
+              __stcs(o0 + o, make_float2(__fmul_rn(-r.y, kx), __fmul_rn(r.x, kx)));
+              __stcs(o1 + o, make_float2(__fmul_rn(-r.y, ky), __fmul_rn(r.x, ky)));
             }
           }
         }
@@ -451,6 +483,7 @@ static ColGeom geom_y(const baorec_ctx* ctx) {  // transform along y, tiles over
   g.kouter = ctx->d_k[2];
   g.ktrans = ctx->d_k[1];
   g.outer_is_y = 0;
+  g.prefetch = ctx->opt_fft_prefetch;
   return g;
 }
 static ColGeom geom_z(const baorec_ctx* ctx) {  // transform along z, tiles over (x, y)
@@ -463,6 +496,7 @@ static ColGeom geom_z(const baorec_ctx* ctx) {  // transform along z, tiles over
   g.kouter = ctx->d_k[1];
   g.ktrans = ctx->d_k[2];
   g.outer_is_y = 1;
+  g.prefetch = ctx->opt_fft_prefetch;
   return g;
 }
 
@@ -520,6 +554,7 @@ int own_slab_z(baorec_ctx* ctx, const float2* in, float2* out, int dir, cudaStre
   g.kouter = ctx->d_k[1];
   g.ktrans = ctx->d_k[2];
   g.outer_is_y = 1;
+  g.prefetch = 0;
   if (dir > 0) return launch_cols<1024, 1>(ctx, in, out, g, 1, ctx->d_tw[1], 0, true, st);
   return launch_cols<1024, -1>(ctx, in, out, g, 1, ctx->d_tw[1], 0, true, st);
 }
