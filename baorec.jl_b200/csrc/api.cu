@@ -2,6 +2,10 @@
 // host-buffer pipelines (run! / reconstructed_positions equivalents).
 #include "internal.cuh"
 
+#include <chrono>
+
+#include "batch.cuh"
+
 using namespace baorec;
 
 namespace baorec {
@@ -59,6 +63,144 @@ static int read_common(baorec_ctx* ctx, const baorec_params* p, int algorithm, c
   BR_CUDA(cudaEventRecord(ctx->ev[5], st));
   BR_TRY(gather3(ctx, px, py, pz, x, y, z, n, ox, oy, oz, p->mas, field, p->f, p->has_los, p->los, positions, st));
   return check_oob(ctx, st, "read_shifts");
+}
+
+// ---- many catalogs per process: the host pipeline, software-pipelined over a batch --------------------------------
+// README.md:11 of the reference: "one process, many reconstructions" (the examples loop over mocks).  For each
+// catalog this is baorec_run_host_f32 followed by baorec_read_host_f32 on the same catalog -- periodic box, no
+// randoms -- but the PCIe transfers of neighbouring catalogs overlap the solve: the upload of catalog i+1 (copy
+// stream) and the download of the results of catalog i-1 (download stream) run while catalog i is reconstructed
+// (main stream); catalogs and results are double-buffered on the device, the read-back uses the positions
+// already resident (no second upload) and the tile sort run! made (same device arrays -> hash hit).
+// The catalogs come from `src` (batch.cuh): arrays the caller holds, or files read by an I/O thread.  Sizes need not
+// be known in advance: a staging buffer grows when a larger catalog arrives, at a point where nothing in flight uses it.
+int batch_pipeline(baorec_ctx* ctx, const baorec_params* p, int algorithm, int n_catalogs, int field, int shifts_only,
+                   BatchSource& src) {
+  BR_TRY(check_params(p));
+  BR_REQUIRE(algorithm == BAOREC_ITERATIVE || algorithm == BAOREC_MULTIGRID, "unknown algorithm");
+  BR_REQUIRE(field >= BAOREC_FIELD_DISP && field <= BAOREC_FIELD_SUM, "unknown field");
+  BR_REQUIRE(n_catalogs >= 1, "n_catalogs");
+  cudaStream_t st = ctx->own_stream, up = ctx->copy_stream;
+  const BufId part_id[2] = {BUF_PART, BUF_PART2};
+  float *part[2] = {nullptr, nullptr}, *out = nullptr, *mesh, *px, *py, *pz;
+  int64_t cap_part[2] = {0, 0}, cap_out = 0;
+  BR_TRY(need_t(ctx, BUF_CACHE, ctx->M, &mesh));
+  BR_TRY(need_t(ctx, BUF_RX, ctx->M, &px));
+  BR_TRY(need_t(ctx, BUF_RY, ctx->M, &py));
+  BR_TRY(need_t(ctx, BUF_RZ, ctx->M, &pz));
+  cudaStream_t dn = nullptr;
+  cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_gather[2] = {nullptr, nullptr}, ev_dn[2] = {nullptr, nullptr};
+  BR_CUDA(cudaStreamCreateWithFlags(&dn, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; b++) {
+    BR_CUDA(cudaEventCreateWithFlags(&ev_up[b], cudaEventDisableTiming));
+    BR_CUDA(cudaEventCreateWithFlags(&ev_gather[b], cudaEventDisableTiming));
+    BR_CUDA(cudaEventCreateWithFlags(&ev_dn[b], cudaEventDisableTiming));
+  }
+  ctx->cache_valid = false;
+  ctx->kcache_valid = false;
+  ctx->disp_valid = false;
+  BatchItem item[2];
+  // Device staging for a catalog of n particles in half b.  part[b] was last read by the gather of the catalog two
+  // before, which has completed (check_oob synchronises the main stream); the result halves are re-cut only after
+  // the downloads in flight have drained.  With max_rows() known both happen once, before the first upload.
+  auto reserve = [&](int b, int64_t n) -> int {
+    if (n > cap_part[b]) {
+      const int64_t cap = cap_part[b] == 0 ? n : n + n / 16;
+      BR_TRY(need_t(ctx, part_id[b], (size_t)cap * 4, &part[b]));
+      cap_part[b] = cap;
+    }
+    if (n > cap_out) {
+      BR_CUDA(cudaStreamSynchronize(dn));
+      const int64_t cap = cap_out == 0 ? n : n + n / 16;
+      BR_TRY(need_t(ctx, BUF_OUT, (size_t)cap * 6, &out));
+      cap_out = cap;
+    }
+    return BAOREC_OK;
+  };
+  auto upload = [&](int i) -> int {  // catalog i -> part[i & 1] (x, y, z, w at stride n) on the copy stream
+    const int b = i & 1;
+    BatchItem& it = item[b];
+    BR_TRY(src.acquire(i, &it));
+    BR_REQUIRE(it.n > 0 && it.x && it.y && it.z && it.w && it.ox && it.oy && it.oz, "catalog arrays");
+    BR_TRY(reserve(b, it.n));
+    const float* h[4] = {it.x, it.y, it.z, it.w};
+    for (int c = 0; c < 4; c++)
+      BR_CUDA(cudaMemcpyAsync(part[b] + (size_t)c * it.n, h[c], (size_t)it.n * sizeof(float), cudaMemcpyHostToDevice, up));
+    BR_CUDA(cudaEventRecord(ev_up[b], up));
+    return BAOREC_OK;
+  };
+  auto body = [&]() -> int {
+    if (src.max_rows() > 0) {
+      BR_TRY(reserve(0, src.max_rows()));
+      BR_TRY(reserve(1, src.max_rows()));
+    }
+    // everything queued on the main stream so far (an earlier call's work on these buffers) precedes the first upload
+    BR_CUDA(cudaEventRecord(ev_gather[0], st));
+    BR_CUDA(cudaStreamWaitEvent(up, ev_gather[0], 0));
+    BR_TRY(upload(0));
+    for (int i = 0; i < n_catalogs; i++) {
+      const int b = i & 1;
+      if (i + 1 < n_catalogs) {
+        // part[b ^ 1] was last read by the gather of catalog i-1, which has completed (check_oob synchronises the
+        // main stream); the event keeps the order explicit on the device as well
+        if (i >= 1) BR_CUDA(cudaStreamWaitEvent(up, ev_gather[b ^ 1], 0));
+        BR_TRY(upload(i + 1));
+      }
+      const BatchItem& it = item[b];
+      const int64_t ni = it.n;
+      float *dx = part[b], *dy = part[b] + ni, *dz = part[b] + 2 * ni, *dw = part[b] + 3 * ni;
+      float* ob = out + (size_t)b * 3 * (size_t)cap_out;
+      BR_CUDA(cudaStreamWaitEvent(st, ev_up[b], 0));
+      BR_CUDA(cudaMemsetAsync(mesh, 0, ctx->M * sizeof(float), st));
+      ctx->want_kcache = true;
+      int s = algorithm == BAOREC_MULTIGRID
+                  ? reconstructed_potential(ctx, p, mesh, dx, dy, dz, dw, ni, nullptr, nullptr, nullptr, nullptr, 0, st)
+                  : reconstructed_overdensity(ctx, p, mesh, dx, dy, dz, dw, ni, nullptr, nullptr, nullptr, nullptr, 0, st);
+      ctx->want_kcache = false;
+      if (s != BAOREC_OK) return s;
+      if (ctx->last_wrapped > 0) {  // cic!(wrap = true) mutates the caller's positions (src/mas.jl:8-10)
+        float* hdst[3] = {it.x, it.y, it.z};
+        for (int c = 0; c < 3; c++)
+          BR_CUDA(cudaMemcpyAsync(hdst[c], part[b] + (size_t)c * ni, (size_t)ni * sizeof(float), cudaMemcpyDeviceToHost, st));
+      }
+      ctx->disp_valid = false;
+      BR_TRY(displacement_meshes(ctx, mesh, algorithm, px, py, pz, st, /*use_kcache=*/true));
+      if (i >= 2) BR_CUDA(cudaStreamWaitEvent(st, ev_dn[b], 0));  // this half still holds the results of catalog i-2
+      BR_TRY(reset_oob(ctx, st));
+      BR_TRY(gather3(ctx, px, py, pz, dx, dy, dz, ni, ob, ob + ni, ob + 2 * ni, p->mas, field, p->f, p->has_los, p->los,
+                     shifts_only ? 0 : 1, st));
+      BR_CUDA(cudaEventRecord(ev_gather[b], st));
+      BR_TRY(check_oob(ctx, st, "read_shifts"));
+      BR_CUDA(cudaStreamWaitEvent(dn, ev_gather[b], 0));
+      float* hdst[3] = {it.ox, it.oy, it.oz};
+      for (int c = 0; c < 3; c++)
+        BR_CUDA(cudaMemcpyAsync(hdst[c], ob + (size_t)c * ni, (size_t)ni * sizeof(float), cudaMemcpyDeviceToHost, dn));
+      BR_CUDA(cudaEventRecord(ev_dn[b], dn));
+      if (i >= 1) {  // the download of catalog i-1 ran under this catalog's reconstruction
+        BR_CUDA(cudaEventSynchronize(ev_dn[b ^ 1]));
+        BR_TRY(src.release(i - 1));
+      }
+    }
+    BR_CUDA(cudaStreamSynchronize(dn));
+    BR_CUDA(cudaStreamSynchronize(st));
+    return src.release(n_catalogs - 1);
+  };
+  const int status = body();
+  if (status != BAOREC_OK) {  // drain whatever is in flight before the buffers are reused
+    cudaStreamSynchronize(up);
+    cudaStreamSynchronize(dn);
+    cudaStreamSynchronize(st);
+  }
+  for (int b = 0; b < 2; b++) {
+    cudaEventDestroy(ev_up[b]);
+    cudaEventDestroy(ev_gather[b]);
+    cudaEventDestroy(ev_dn[b]);
+  }
+  cudaStreamDestroy(dn);
+  ctx->sortc_valid = false;  // the sort belongs to a staging buffer the next call overwrites
+  ctx->cache_valid = status == BAOREC_OK;
+  ctx->disp_valid = false;
+  return status;
 }
 
 }  // namespace baorec
@@ -192,6 +334,7 @@ int baorec_set_option(baorec_ctx* ctx, const char* name, int64_t value) {
   else if (s == "fft_prefetch") ctx->opt_fft_prefetch = (int)value;
   else if (s == "scatter_pairs") ctx->opt_scatter_pairs = (int)value;
   else if (s == "scatter_tiles") ctx->opt_scatter_tiles = (int)value;
+  else if (s == "batch_slots") ctx->opt_batch_slots = (int)value;
   else if (s == "deterministic_scatter") ctx->opt_det_scatter = (int)value;
   else if (s == "unified_sort") {
     ctx->opt_unified_sort = (int)value;
@@ -371,118 +514,78 @@ int baorec_read_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm,
   return BAOREC_OK;
 }
 
-// ---- many catalogs per process: the host pipeline, software-pipelined over a batch --------------------------------
-// README.md:11 of the reference: "one process, many reconstructions" (the examples loop over mocks).  For each
-// catalog this is baorec_run_host_f32 followed by baorec_read_host_f32 on the same catalog -- periodic box, no
-// randoms -- but the PCIe transfers of neighbouring catalogs overlap the solve: the upload of catalog i+1 (copy
-// stream) and the download of the results of catalog i-1 (download stream) run while catalog i is reconstructed
-// (main stream); catalogs and results are double-buffered on the device, the read-back uses the positions
-// already resident (no second upload) and the tile sort run! made (same device arrays -> hash hit).
+// ---- many catalogs per process (batch_pipeline above) --------------------------------------------------------------
 int baorec_batch_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, int n_catalogs, float* const* h_x,
                           float* const* h_y, float* const* h_z, const float* const* h_w, const int64_t* n, int field,
                           int shifts_only, float* const* h_ox, float* const* h_oy, float* const* h_oz) {
   BR_NEED_PLAN(ctx);
-  BR_TRY(check_params(p));
-  BR_REQUIRE(algorithm == BAOREC_ITERATIVE || algorithm == BAOREC_MULTIGRID, "unknown algorithm");
-  BR_REQUIRE(field >= BAOREC_FIELD_DISP && field <= BAOREC_FIELD_SUM, "unknown field");
   BR_REQUIRE(n_catalogs >= 1 && h_x && h_y && h_z && h_w && n && h_ox && h_oy && h_oz, "batch arrays");
-  int64_t nmax = 0;
+  struct ArraySource : BatchSource {
+    int count;
+    float* const *x, *const *y, *const *z, *const *ox, *const *oy, *const *oz;
+    const float* const* w;
+    const int64_t* n;
+    int64_t nmax = 0;
+    int acquire(int i, BatchItem* it) override {
+      it->x = x[i], it->y = y[i], it->z = z[i], it->w = w[i], it->n = n[i];
+      it->ox = ox[i], it->oy = oy[i], it->oz = oz[i];
+      return BAOREC_OK;
+    }
+    int release(int) override { return BAOREC_OK; }
+    int64_t max_rows() const override { return nmax; }
+  } src;
+  src.count = n_catalogs;
+  src.x = h_x, src.y = h_y, src.z = h_z, src.w = h_w, src.n = n, src.ox = h_ox, src.oy = h_oy, src.oz = h_oz;
   for (int i = 0; i < n_catalogs; i++) {
     BR_REQUIRE(n[i] > 0 && h_x[i] && h_y[i] && h_z[i] && h_w[i] && h_ox[i] && h_oy[i] && h_oz[i], "catalog arrays");
-    if (n[i] > nmax) nmax = n[i];
+    if (n[i] > src.nmax) src.nmax = n[i];
   }
-  cudaStream_t st = ctx->own_stream, up = ctx->copy_stream;
-  float *part[2], *out, *mesh, *px, *py, *pz;
-  BR_TRY(need_t(ctx, BUF_PART, (size_t)nmax * 4, &part[0]));
-  BR_TRY(need_t(ctx, BUF_PART2, (size_t)nmax * 4, &part[1]));
-  BR_TRY(need_t(ctx, BUF_OUT, (size_t)nmax * 6, &out));
-  BR_TRY(need_t(ctx, BUF_CACHE, ctx->M, &mesh));
-  BR_TRY(need_t(ctx, BUF_RX, ctx->M, &px));
-  BR_TRY(need_t(ctx, BUF_RY, ctx->M, &py));
-  BR_TRY(need_t(ctx, BUF_RZ, ctx->M, &pz));
-  float* outb[2] = {out, out + (size_t)nmax * 3};
-  cudaStream_t dn = nullptr;
-  cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_gather[2] = {nullptr, nullptr}, ev_dn[2] = {nullptr, nullptr};
-  BR_CUDA(cudaStreamCreateWithFlags(&dn, cudaStreamNonBlocking));
-  for (int b = 0; b < 2; b++) {
-    BR_CUDA(cudaEventCreateWithFlags(&ev_up[b], cudaEventDisableTiming));
-    BR_CUDA(cudaEventCreateWithFlags(&ev_gather[b], cudaEventDisableTiming));
-    BR_CUDA(cudaEventCreateWithFlags(&ev_dn[b], cudaEventDisableTiming));
-  }
-  ctx->cache_valid = false;
-  ctx->kcache_valid = false;
-  ctx->disp_valid = false;
-  auto upload = [&](int i) -> int {  // catalog i -> part[i & 1] (x, y, z, w at stride n[i]) on the copy stream
-    const int b = i & 1;
-    const float* src[4] = {h_x[i], h_y[i], h_z[i], h_w[i]};
-    for (int c = 0; c < 4; c++)
-      BR_CUDA(cudaMemcpyAsync(part[b] + (size_t)c * n[i], src[c], (size_t)n[i] * sizeof(float), cudaMemcpyHostToDevice, up));
-    BR_CUDA(cudaEventRecord(ev_up[b], up));
-    return BAOREC_OK;
-  };
-  auto body = [&]() -> int {
-    // everything queued on the main stream so far (an earlier call's work on these buffers) precedes the first upload
-    BR_CUDA(cudaEventRecord(ev_gather[0], st));
-    BR_CUDA(cudaStreamWaitEvent(up, ev_gather[0], 0));
-    BR_TRY(upload(0));
-    for (int i = 0; i < n_catalogs; i++) {
-      const int b = i & 1;
-      const int64_t ni = n[i];
-      float *dx = part[b], *dy = part[b] + ni, *dz = part[b] + 2 * ni, *dw = part[b] + 3 * ni;
-      if (i + 1 < n_catalogs) {
-        // part[b ^ 1] was last read by the gather of catalog i-1, which has completed (check_oob synchronises the
-        // main stream); the event keeps the order explicit on the device as well
-        if (i >= 1) BR_CUDA(cudaStreamWaitEvent(up, ev_gather[b ^ 1], 0));
-        BR_TRY(upload(i + 1));
-      }
-      BR_CUDA(cudaStreamWaitEvent(st, ev_up[b], 0));
-      BR_CUDA(cudaMemsetAsync(mesh, 0, ctx->M * sizeof(float), st));
-      ctx->want_kcache = true;
-      int s = algorithm == BAOREC_MULTIGRID
-                  ? reconstructed_potential(ctx, p, mesh, dx, dy, dz, dw, ni, nullptr, nullptr, nullptr, nullptr, 0, st)
-                  : reconstructed_overdensity(ctx, p, mesh, dx, dy, dz, dw, ni, nullptr, nullptr, nullptr, nullptr, 0, st);
-      ctx->want_kcache = false;
-      if (s != BAOREC_OK) return s;
-      if (ctx->last_wrapped > 0) {  // cic!(wrap = true) mutates the caller's positions (src/mas.jl:8-10)
-        float* hdst[3] = {h_x[i], h_y[i], h_z[i]};
-        for (int c = 0; c < 3; c++)
-          BR_CUDA(cudaMemcpyAsync(hdst[c], part[b] + (size_t)c * ni, (size_t)ni * sizeof(float), cudaMemcpyDeviceToHost, st));
-      }
-      ctx->disp_valid = false;
-      BR_TRY(displacement_meshes(ctx, mesh, algorithm, px, py, pz, st, /*use_kcache=*/true));
-      if (i >= 2) BR_CUDA(cudaStreamWaitEvent(st, ev_dn[b], 0));  // outb[b] still holds the results of catalog i-2
-      BR_TRY(reset_oob(ctx, st));
-      BR_TRY(gather3(ctx, px, py, pz, dx, dy, dz, ni, outb[b], outb[b] + ni, outb[b] + 2 * ni, p->mas, field, p->f,
-                     p->has_los, p->los, shifts_only ? 0 : 1, st));
-      BR_CUDA(cudaEventRecord(ev_gather[b], st));
-      BR_TRY(check_oob(ctx, st, "read_shifts"));
-      BR_CUDA(cudaStreamWaitEvent(dn, ev_gather[b], 0));
-      float* hdst[3] = {h_ox[i], h_oy[i], h_oz[i]};
-      for (int c = 0; c < 3; c++)
-        BR_CUDA(cudaMemcpyAsync(hdst[c], outb[b] + (size_t)c * ni, (size_t)ni * sizeof(float), cudaMemcpyDeviceToHost, dn));
-      BR_CUDA(cudaEventRecord(ev_dn[b], dn));
-    }
-    BR_CUDA(cudaStreamSynchronize(dn));
-    BR_CUDA(cudaStreamSynchronize(st));
-    return BAOREC_OK;
-  };
-  const int status = body();
-  if (status != BAOREC_OK) {  // drain whatever is in flight before the buffers are reused
-    cudaStreamSynchronize(up);
-    cudaStreamSynchronize(dn);
-    cudaStreamSynchronize(st);
-  }
-  for (int b = 0; b < 2; b++) {
-    cudaEventDestroy(ev_up[b]);
-    cudaEventDestroy(ev_gather[b]);
-    cudaEventDestroy(ev_dn[b]);
-  }
-  cudaStreamDestroy(dn);
-  ctx->sortc_valid = false;  // the sort belongs to a staging buffer the next call overwrites
-  ctx->cache_valid = status == BAOREC_OK;
-  ctx->disp_valid = false;
-  return status;
+  return batch_pipeline(ctx, p, algorithm, n_catalogs, field, shifts_only, src);
 }
 
+// The same pipeline fed from catalog FILES (text or NPY by extension) and writing NPY files: a reader thread parses
+// catalog i+1 (and further ahead, as host buffer sets come free) into pinned memory and a writer thread stores the
+// results of catalog i-1 while the device reconstructs catalog i -- examples/simulation.jl:12-40 looped over mocks.
+int baorec_batch_files_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, int n_catalogs,
+                           const char* const* in_paths, char delim, const int cols[4], int field, int shifts_only,
+                           const char* const* out_paths, int n_threads, int64_t* n_rows, double* seconds) {
+  BR_NEED_PLAN(ctx);
+  BR_TRY(check_params(p));
+  BR_REQUIRE(n_catalogs >= 1 && in_paths && cols, "n_catalogs / in_paths / cols");
+  BR_REQUIRE(cols[0] >= 0 && cols[1] >= 0 && cols[2] >= 0, "columns of x, y, z");
+  for (int i = 0; i < n_catalogs; i++) BR_REQUIRE(in_paths[i] != nullptr, "in_paths[i]");
+  FileBatchConfig cfg;
+  cfg.n_catalogs = n_catalogs;
+  cfg.in_paths = in_paths;
+  cfg.out_paths = out_paths;
+  cfg.delim = delim;
+  for (int c = 0; c < 4; c++) cfg.cols[c] = cols[c];
+  cfg.n_threads = n_threads;
+  cfg.n_slots = ctx->opt_batch_slots;
+  HostAllocator al;
+  al.alloc = [](void** out, size_t bytes) -> int { return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? 0 : 1; };
+  al.free = [](void* q) { cudaFreeHost(q); };
+  const auto t0 = std::chrono::steady_clock::now();
+  int status;
+  {
+    FileBatchSource src(cfg, al);
+    status = batch_pipeline(ctx, p, algorithm, n_catalogs, field, shifts_only, src);
+    if (status == BAOREC_OK) status = src.finish();
+    else {
+      const std::string msg = baorec_last_error();  // the abort below may record an I/O message of its own
+      src.finish(true);
+      set_error("%s", msg.c_str());
+    }
+    if (n_rows)
+      for (int i = 0; i < n_catalogs; i++) n_rows[i] = src.rows()[i];
+    if (seconds) {
+      seconds[0] = src.read_seconds();
+      seconds[1] = src.write_seconds();
+      seconds[2] = src.wait_seconds();
+    }
+  }
+  if (seconds) seconds[3] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return status;
+}
 
 }  // extern "C"

@@ -509,6 +509,39 @@ def run_batch(recon: AbstractRecon, grid_size, catalogs, field="disp", positions
     return out
 
 
+def run_batch_files(recon: AbstractRecon, grid_size, in_paths, out_paths=None, columns=(0, 1, 2, -1), delim=" ",
+                    field="disp", positions=True, n_threads=0):
+    """`run_batch` fed from catalog FILES and writing NPY files -- the reference's examples/simulation.jl:12-40 looped
+    over mocks (baorec_batch_files_f32): `in_paths[i]` is a delimited text catalog or an .npy matrix, `columns` the
+    0-based file columns of x, y, z and the weights (-1: weights of one), `out_paths[i]` (or None) receives what
+    `npzwrite(fn, hcat(new_pos...))` stores.  A reader thread parses the next catalogs into pinned memory and a writer
+    thread stores the previous results while the device reconstructs the current one.  Returns a dict: rows per catalog
+    and the seconds spent reading, writing, waiting for the reader, and in total."""
+    import os
+    nx, ny, nz = (int(v) for v in grid_size)
+    K = len(in_paths)
+    if out_paths is not None and len(out_paths) != K:
+        raise ValueError("one output path (or None) per catalog")
+    if len(columns) != 4:
+        raise ValueError("columns = (x, y, z, w); w = -1 for weights of one")
+    if recon.box_size is None:
+        raise RuntimeError("recon.box_size / recon.box_min are not set")
+    setup_fft(recon, (nx, ny, nz))
+    ctx = recon._ctx(grid_size=(nx, ny, nz))
+    p = recon._params()
+    ins = (C.c_char_p * K)(*[os.fsencode(q) for q in in_paths])
+    outs = None if out_paths is None else (C.c_char_p * K)(*[None if q is None else os.fsencode(q) for q in out_paths])
+    rows, secs = (C.c_int64 * K)(), (C.c_double * 4)()
+    d = delim.encode()
+    if len(d) != 1:
+        raise ValueError("delim is one character")
+    L.check(ctx.lib.baorec_batch_files_f32(ctx.handle, C.byref(p), recon.algorithm, K, ins, d,
+                                           (C.c_int * 4)(*[int(c) for c in columns]), L.FIELDS[field], 0 if positions else 1,
+                                           outs, int(n_threads), rows, secs))
+    recon.result_cache = ("device-cache", ctx)
+    return {"rows": list(rows), "read_s": secs[0], "write_s": secs[1], "wait_s": secs[2], "total_s": secs[3]}
+
+
 def compute_displacements(mesh, data_x, data_y, data_z, recon: AbstractRecon):
     """compute_displacements src/iterative.jl:229-250 / src/multigrid.jl:781-799."""
     n = _chk_vec(data_x, data_y, data_z)

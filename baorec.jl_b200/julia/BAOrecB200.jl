@@ -455,6 +455,89 @@ function run_batch(recon::AbstractRecon, grid_size::NTuple{3,Int}, catalogs::Vec
     out
 end
 
+# ---- catalog files either side of the path (what the examples do with CSV.jl and NPZ.jl) --------------------------
+# CSV.File(path, delim = ' ', ignorerepeated = true, header = [...], types = [Float32 ...]) followed by picking columns
+# (examples/simulation.jl:12-15): the 1-based file columns `columns` as Vector{Float32}s, parsed by the library's threads.
+function read_text_catalog(path::AbstractString, columns::Vector{Int}; delim::Char = ' ', nthreads::Integer = 0)
+    n = Ref{Int64}(0)
+    k = Ref{Cint}(0)
+    check(ccall((:baorec_text_catalog_scan, libbaorec), Cint, (Cstring, Cchar, Ptr{Int64}, Ptr{Cint}, Cint),
+                path, Cchar(delim), n, k, nthreads))
+    out = [Vector{Float32}(undef, n[]) for _ in columns]
+    ptrs = Ptr{Cvoid}[Ptr{Cvoid}(pointer(a)) for a in out]
+    got = Ref{Int64}(0)
+    GC.@preserve out begin
+        check(ccall((:baorec_text_catalog_read_f32, libbaorec), Cint,
+                    (Cstring, Cchar, Cint, Ptr{Cint}, Ptr{Ptr{Cvoid}}, Int64, Ptr{Int64}, Cint),
+                    path, Cchar(delim), length(columns), Cint[c - 1 for c in columns], ptrs, n[], got, nthreads))
+    end
+    Tuple(out)
+end
+
+# npzread(path) of an (N, K) matrix, split into Float32 columns (`columns` 1-based; all of them by default).
+function read_npy_catalog(path::AbstractString, columns::Union{Vector{Int},Nothing} = nothing; nthreads::Integer = 0)
+    dtype = Ref{Cint}(0)
+    forder = Ref{Cint}(0)
+    n = Ref{Int64}(0)
+    k = Ref{Int64}(0)
+    check(ccall((:baorec_npy_info, libbaorec), Cint, (Cstring, Ptr{Cint}, Ptr{Cint}, Ptr{Int64}, Ptr{Int64}),
+                path, dtype, forder, n, k))
+    cols = columns === nothing ? collect(1:Int(k[])) : columns
+    out = [Vector{Float32}(undef, n[]) for _ in cols]
+    ptrs = Ptr{Cvoid}[Ptr{Cvoid}(pointer(a)) for a in out]
+    got = Ref{Int64}(0)
+    GC.@preserve out begin
+        check(ccall((:baorec_npy_read_columns_f32, libbaorec), Cint,
+                    (Cstring, Cint, Ptr{Cint}, Ptr{Ptr{Cvoid}}, Int64, Ptr{Int64}, Cint),
+                    path, length(cols), Cint[c - 1 for c in cols], ptrs, n[], got, nthreads))
+    end
+    Tuple(out)
+end
+
+# npzwrite(path, hcat(cols...)) (examples/simulation.jl:38-40) without building the matrix.
+function write_npy(path::AbstractString, cols::Vector{Float32}...)
+    v = collect(cols)
+    ptrs = Ptr{Cvoid}[Ptr{Cvoid}(pointer(a)) for a in v]
+    GC.@preserve v begin
+        check(ccall((:baorec_npy_write_columns_f32, libbaorec), Cint, (Cstring, Cint, Ptr{Ptr{Cvoid}}, Int64),
+                    path, length(v), ptrs, length(v[1])))
+    end
+    nothing
+end
+
+# cat[map(z -> ((z > lo) & (z < hi)), cat.z), :] (examples/lightcone.jl:25-26) on SoA columns: the kept rows, in order.
+function select_rows(cols::Vector{Vector{Float32}}, key::Integer, lo::Real, hi::Real; nthreads::Integer = 0)
+    ptrs = Ptr{Cvoid}[Ptr{Cvoid}(pointer(a)) for a in cols]
+    kept = Ref{Int64}(0)
+    GC.@preserve cols begin
+        check(ccall((:baorec_catalog_select_f32, libbaorec), Cint,
+                    (Cint, Ptr{Ptr{Cvoid}}, Int64, Cint, Cfloat, Cfloat, Ptr{Int64}, Cint),
+                    length(cols), ptrs, length(cols[1]), key - 1, lo, hi, kept, nthreads))
+    end
+    [resize!(a, kept[]) for a in cols]
+end
+
+# run_batch fed from catalog files and writing NPY files (examples/simulation.jl:12-40 looped over mocks): a reader thread
+# parses the next catalogs into pinned memory and a writer thread stores the previous results while the device
+# reconstructs the current one.  `columns` = 1-based file columns of x, y, z and the weights (0: weights of one).
+function run_batch_files(recon::AbstractRecon, grid_size::NTuple{3,Int}, in_paths::Vector{String},
+                         out_paths::Union{Vector{String},Nothing} = nothing; columns::NTuple{4,Int} = (1, 2, 3, 0),
+                         delim::Char = ' ', field = :disp, positions::Bool = true, nthreads::Integer = 0)
+    ctx = context()
+    check(ccall((:baorec_plan, libbaorec), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cfloat}, Ptr{Cfloat}),
+                ctx, grid_size[1], grid_size[2], grid_size[3], f3(recon.box_size), f3(recon.box_min)))
+    p = Ref(Params(recon))
+    rows = Vector{Int64}(undef, length(in_paths))
+    seconds = Vector{Float64}(undef, 4)
+    outs = out_paths === nothing ? C_NULL : out_paths
+    check(ccall((:baorec_batch_files_f32, libbaorec), Cint,
+                (Ptr{Cvoid}, Ptr{Params}, Cint, Cint, Ptr{Cstring}, Cchar, Ptr{Cint}, Cint, Cint, Ptr{Cstring}, Cint, Ptr{Int64},
+                 Ptr{Cdouble}),
+                ctx, p, algorithm(recon), length(in_paths), in_paths, Cchar(delim), Cint[c - 1 for c in columns], FIELD[field],
+                positions ? 0 : 1, outs, nthreads, rows, seconds))
+    (rows = rows, read_s = seconds[1], write_s = seconds[2], wait_s = seconds[3], total_s = seconds[4])
+end
+
 # run! needs no override: the reference's run! (src/recon.jl:134-261) allocates a CuArray mesh when
 # data_x isa CuArray and calls setup_fft!, setup_box and reconstructed_*! -- all of which dispatch
 # to the methods above.

@@ -12,7 +12,8 @@ HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "lib" / "libbaorec_b200.so"
 
 OK = 0
-ERR_INVALID, ERR_CUDA, ERR_CUFFT, ERR_NCCL, ERR_OUT_OF_BOX, ERR_NOT_PLANNED, ERR_NOMEM, ERR_OUT_OF_RANGE = -1, -2, -3, -4, -5, -6, -7, -8
+ERR_INVALID, ERR_CUDA, ERR_CUFFT, ERR_NCCL, ERR_OUT_OF_BOX, ERR_NOT_PLANNED, ERR_NOMEM, ERR_OUT_OF_RANGE, ERR_IO = -1, -2, -3, -4, -5, -6, -7, -8, -9
+DTYPE_F32, DTYPE_F64 = 4, 8
 MAS_CIC, MAS_TSC, MAS_PCS = 0, 1, 2
 FIELD_DISP, FIELD_RSD, FIELD_SUM = 0, 1, 2
 ITERATIVE, MULTIGRID = 0, 1
@@ -32,6 +33,10 @@ class OutOfBoxError(BaorecError):
 
 class OutOfRangeError(BaorecError):
     """A redshift / distance outside the cosmology tables (reference: Interpolations.jl BoundsError)."""
+
+
+class CatalogIOError(BaorecError, OSError):
+    """A catalog file that cannot be opened, read, parsed or written (BAOREC_ERR_IO)."""
 
 
 class Params(C.Structure):
@@ -111,6 +116,8 @@ SIGNATURES = {
     "baorec_run_host_f32": [_vp, _pp, _i, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _f3, _f3],
     "baorec_read_host_f32": [_vp, _pp, _i, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp],
     "baorec_batch_host_f32": [_vp, _pp, _i, _i] + [C.POINTER(_vp)] * 4 + [C.POINTER(_i64), _i, _i] + [C.POINTER(_vp)] * 3,
+    "baorec_batch_files_f32": [_vp, _pp, _i, _i, C.POINTER(C.c_char_p), C.c_char, C.POINTER(_i), _i, _i, C.POINTER(C.c_char_p), _i,
+                               C.POINTER(_i64), C.POINTER(C.c_double)],
     "baorec_result_cache": [_vp],
     "baorec_cosmo_set": [_vp, C.POINTER(CosmologyParams)],
     "baorec_cosmo_build_table": [C.POINTER(CosmologyParams), C.POINTER(C.c_double), C.POINTER(C.c_double)],
@@ -123,6 +130,12 @@ SIGNATURES = {
     "baorec_power_multipoles_interlaced_f32": [_vp, _vp, _vp, _vp, _vp, _f3, C.c_double, C.c_double, _i, _i, C.c_double] + [C.POINTER(C.c_double)] * 5 + [_vp],
     "baorec_interlace_positions_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
     "baorec_compute_auto_box_f32": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _f3, C.c_double, C.c_double, _i, C.c_double] + [C.POINTER(C.c_double)] * 5 + [_vp],
+    "baorec_text_catalog_scan": [C.c_char_p, C.c_char, C.POINTER(_i64), C.POINTER(_i), _i],
+    "baorec_text_catalog_read_f32": [C.c_char_p, C.c_char, _i, C.POINTER(_i), C.POINTER(_vp), _i64, C.POINTER(_i64), _i],
+    "baorec_npy_info": [C.c_char_p, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i64), C.POINTER(_i64)],
+    "baorec_npy_read_columns_f32": [C.c_char_p, _i, C.POINTER(_i), C.POINTER(_vp), _i64, C.POINTER(_i64), _i],
+    "baorec_npy_write_columns_f32": [C.c_char_p, _i, C.POINTER(_vp), _i64],
+    "baorec_catalog_select_f32": [_i, C.POINTER(_vp), _i64, _i, _f, _f, C.POINTER(_i64), _i],
     "baorec_host_alloc": [C.POINTER(_vp), _i64],
     "baorec_host_free": [_vp],
 }
@@ -157,6 +170,8 @@ def check(code: int):
         raise OutOfBoxError(code, msg)
     if code == ERR_OUT_OF_RANGE:
         raise OutOfRangeError(code, msg)
+    if code == ERR_IO:
+        raise CatalogIOError(code, msg)
     raise BaorecError(code, msg)
 
 

@@ -46,8 +46,9 @@ enum {
                                   out-of-bounds atomic, src/mas.jl:33-49, 82-97) */
   BAOREC_ERR_NOT_PLANNED = -6, /* baorec_plan has not been called */
   BAOREC_ERR_NOMEM = -7,
-  BAOREC_ERR_OUT_OF_RANGE = -8 /* redshift / distance outside the cosmology tables (reference:
+  BAOREC_ERR_OUT_OF_RANGE = -8, /* redshift / distance outside the cosmology tables (reference:
                                   Interpolations.jl BoundsError) */
+  BAOREC_ERR_IO = -9            /* a catalog file cannot be opened, read, parsed or written */
 };
 
 enum { BAOREC_MAS_CIC = 0, BAOREC_MAS_TSC = 1, BAOREC_MAS_PCS = 2 };  /* TSC and PCS are extensions */
@@ -363,6 +364,21 @@ int baorec_read_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm,
 int baorec_batch_host_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, int n_catalogs, float* const* h_x,
                           float* const* h_y, float* const* h_z, const float* const* h_w, const int64_t* n, int field,
                           int shifts_only, float* const* h_ox, float* const* h_oy, float* const* h_oz);
+/* The same pipeline fed from catalog FILES and writing files -- examples/simulation.jl:12-40 looped over mocks:
+ *   in_paths[i]  text catalog (fields separated as `delim` says, see baorec_text_catalog_scan) or, by its extension,
+ *                an .npy matrix (N, K); cols[0..2] = the 0-based columns of x, y, z, cols[3] = the column of the
+ *                weights or -1 for weights of one (examples/simulation.jl:16);
+ *   out_paths[i] NPY file of the reconstructed positions (shifts_only != 0: of the shifts) as the (N, 3) Float32
+ *                matrix npzwrite(fn, hcat(new_pos...)) stores; out_paths or any entry may be NULL (nothing written).
+ * A reader thread parses catalog i+1 (and further ahead, as buffer sets come free) into pinned host memory and a
+ * writer thread stores the results of catalog i-1 while the device reconstructs catalog i; the catalogs may differ in
+ * size (staging grows when a larger one arrives).  n_threads: parser threads (<= 0: one per core).  n_rows (NULL or
+ * n_catalogs entries): rows of each catalog.  seconds (NULL or 4 doubles): time the reader spent reading + parsing,
+ * the writer writing, the pipeline waiting for the reader, and the whole call.  Option "batch_slots" (default 4, >= 3)
+ * sets the number of host buffer sets.  Errors: BAOREC_ERR_IO with the file (and line) named. */
+int baorec_batch_files_f32(baorec_ctx* ctx, const baorec_params* p, int algorithm, int n_catalogs,
+                           const char* const* in_paths, char delim, const int cols[4], int field, int shifts_only,
+                           const char* const* out_paths, int n_threads, int64_t* n_rows, double* seconds);
 /* Device pointer of the cached result mesh (recon.result_cache), or NULL. */
 float* baorec_result_cache(baorec_ctx* ctx);
 
@@ -443,6 +459,37 @@ int baorec_compute_auto_box_f32(baorec_ctx* ctx, const float* d_x, const float* 
                                 const float* d_rx, const float* d_ry, const float* d_rz, const float* d_rw, int64_t nr, int mas,
                                 int interlace, const float los[3], double kmin, double dk, int nbins, double shot, double* h_k,
                                 double* h_nmodes, double* h_p0, double* h_p2, double* h_p4, baorec_stream stream);
+
+/* ---- catalog files (the data formats either side of the path) ------------------------------
+ * Host code: none of these needs a context or a GPU.  They fill / read caller-owned SoA Float32 arrays -- the layout
+ * baorec_run_host_f32 and baorec_batch_host_f32 take; give them pinned memory (baorec_host_alloc) and the uploads
+ * that follow are asynchronous.  n_threads <= 0: one thread per host core (never more than one per 4 MiB of work). */
+enum { BAOREC_DTYPE_F32 = 4, BAOREC_DTYPE_F64 = 8 };
+/* Rows and columns of a delimited text catalog -- what CSV.File(fn, delim = ' ', ignorerepeated = true,
+ * header = [...], types = [Float32 ...]) reads (examples/simulation.jl:12-13, examples/lightcone.jl:22-23).
+ * delim == ' ': fields are separated by runs of blanks / tabs (ignorerepeated); any other character separates
+ * exactly, blanks around a field are dropped.  Blank lines and lines starting with '#' are not rows.  n_cols = the
+ * fields of the first row (may be NULL). */
+int baorec_text_catalog_scan(const char* path, char delim, int64_t* n_rows, int* n_cols, int n_threads);
+/* Reads the file columns cols[0..n_out) (0-based) into h_out[j][0..*n_read): correctly rounded Float32 (like
+ * CSV.jl's Float32 parser), `inf` / `nan` accepted.  BAOREC_ERR_INVALID when the file holds more than `capacity`
+ * rows; BAOREC_ERR_IO naming the line when a requested field is missing or not a number. */
+int baorec_text_catalog_read_f32(const char* path, char delim, int n_out, const int* cols, float* const* h_out,
+                                 int64_t capacity, int64_t* n_read, int n_threads);
+/* Header of an NPY file (format 1.0 - 3.0; little-endian f4 / f8; a vector (N,) or a matrix (N, K) in either
+ * memory order; npzread in the reference's scripts).  Any output may be NULL. */
+int baorec_npy_info(const char* path, int* dtype, int* fortran_order, int64_t* n_rows, int64_t* n_cols);
+/* Columns cols[0..n_out) of the (N, K) matrix into h_out[j][0..N) (Float64 data are rounded to Float32). */
+int baorec_npy_read_columns_f32(const char* path, int n_out, const int* cols, float* const* h_out, int64_t capacity,
+                                int64_t* n_read, int n_threads);
+/* npzwrite(fn, hcat(cols...)) (examples/simulation.jl:38-40): the SoA columns written as an (n, n_cols) Float32
+ * matrix with 'fortran_order': True -- byte for byte what NPZ.jl stores for the column-major matrix, and what
+ * numpy.load returns as an (n, n_cols) array.  n_cols == 1 writes a vector (n,). */
+int baorec_npy_write_columns_f32(const char* path, int n_cols, const float* const* h_cols, int64_t n);
+/* data_cat[map(z -> ((z > lo) & (z < hi)), data_cat.z), :] (examples/lightcone.jl:25-26): keeps the rows with
+ * lo < h_cols[key][r] < hi, in order, in place in every column; *n_kept rows remain. */
+int baorec_catalog_select_f32(int n_cols, float* const* h_cols, int64_t n, int key, float lo, float hi, int64_t* n_kept,
+                              int n_threads);
 
 /* Pinned host memory helpers for callers without their own (Julia: CUDA.Mem.alloc(HostBuffer)). */
 int baorec_host_alloc(void** out, int64_t bytes);

@@ -14,9 +14,9 @@ HEADER = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "baorec_b200.h").read_text
 
 # C parameter type -> the set of Julia ccall types that are ABI-compatible with it
 POINTER = {"Ptr{Cvoid}", "Ptr{Cfloat}", "Ptr{Cdouble}", "Ptr{Params}", "Ref{Params}", "Ref{BaorecParams}", "Ptr{Ptr{Cvoid}}",
-           "Ref{CosmologyParams}", "Ptr{CosmologyParams}", "Ptr{Cint}", "Ptr{Int64}", "Cstring", "Ptr{UInt8}"}
+           "Ref{CosmologyParams}", "Ptr{CosmologyParams}", "Ptr{Cint}", "Ptr{Int64}", "Cstring", "Ptr{UInt8}", "Ptr{Cstring}"}
 SCALAR = {"int": {"Cint"}, "int32_t": {"Cint", "Int32"}, "int64_t": {"Int64", "Clonglong"}, "float": {"Cfloat", "Float32"},
-          "double": {"Cdouble", "Float64"}}
+          "double": {"Cdouble", "Float64"}, "char": {"Cchar"}}
 
 
 def c_prototypes():
@@ -147,7 +147,7 @@ def generic_names(pos, var):
 
 def test_every_ccall_matches_its_prototype():
     protos, calls = c_prototypes(), shim_ccalls()
-    assert len(protos) == 68 and len(calls) >= 25
+    assert len(protos) == 75 and len(calls) >= 32
     seen = set()
     starts = [m.start() for m in CCALL.finditer(SHIM)]
     for (sym, ret, types, args, line), pos in zip(calls, starts):
@@ -177,7 +177,9 @@ def test_every_ccall_matches_its_prototype():
                  "baorec_reconstructed_positions_f32", "baorec_setup_box_f32", "baorec_mg_jacobi_f32", "baorec_mg_residual_f32",
                  "baorec_mg_restrict_f32", "baorec_mg_prolong_f32", "baorec_mg_vcycle_f32", "baorec_mg_fmg_f32",
                  "baorec_cosmo_set", "baorec_sky_to_cartesian_f32", "baorec_cartesian_to_sky_f32", "baorec_fkp_weights_f32",
-                 "baorec_wrap_positions_f32", "baorec_power_multipoles_f32"):
+                 "baorec_wrap_positions_f32", "baorec_power_multipoles_f32", "baorec_batch_host_f32", "baorec_batch_files_f32",
+                 "baorec_text_catalog_read_f32", "baorec_npy_read_columns_f32", "baorec_npy_write_columns_f32",
+                 "baorec_catalog_select_f32"):
         assert must in seen, must
 
 
