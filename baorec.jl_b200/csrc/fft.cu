@@ -483,7 +483,9 @@ static ColGeom geom_y(const baorec_ctx* ctx) {  // transform along y, tiles over
   g.kouter = ctx->d_k[2];
   g.ktrans = ctx->d_k[1];
   g.outer_is_y = 0;
-  g.prefetch = ctx->opt_fft_prefetch;
+  // y passes: every CTA asks L2 for the tile of the CTA one wave (148 SMs) further on -- measured at 1024^3: 2.04 -> 1.93 ms
+  // per pass with a distance of 148, 1.94 / 1.98 with 296 / 592 (profiles/r2_ab_fft_prefetch.jsonl)
+  g.prefetch = ctx->opt_fft_prefetch < 0 ? 148 : ctx->opt_fft_prefetch;
   return g;
 }
 static ColGeom geom_z(const baorec_ctx* ctx) {  // transform along z, tiles over (x, y)
@@ -496,7 +498,9 @@ static ColGeom geom_z(const baorec_ctx* ctx) {  // transform along z, tiles over
   g.kouter = ctx->d_k[1];
   g.ktrans = ctx->d_k[2];
   g.outer_is_y = 1;
-  g.prefetch = ctx->opt_fft_prefetch;
+  // z passes: the same prefetch costs time (fft_z_solve 5.03 -> 5.74 ms, fft_z_disp 5.52 -> 6.14 ms: their loads already
+  // keep DRAM busy, the extra requests only thrash the row buffers) -- only when asked for explicitly
+  g.prefetch = ctx->opt_fft_prefetch > 0 ? ctx->opt_fft_prefetch : 0;
   return g;
 }
 

@@ -146,7 +146,7 @@ struct baorec_ctx {
   int split_planes_planned = 0;
   int opt_fft_split = 0;
   int opt_fft_tile_cols = -1;  // columns per tile of the own FFT kernels at N = 1024: -1 = auto (z passes 16, y passes 8), 4 / 8 / 16 = everywhere
-  int opt_fft_prefetch = 0;    // > 0: L2 prefetch distance of the own FFT kernels in CTAs (experiment)
+  int opt_fft_prefetch = -1;   // L2 prefetch distance of the own FFT kernels in CTAs: -1 = auto (y passes 148, z passes none), 0 = none, > 0 = every pass
   int opt_own_fft = -1;  // column FFT kernels of fft.cu instead of cuFFT's 3-D plans: -1 = auto (ny, nz powers of two >= 512), 0 = never, 1 = wherever supported (>= 256)
   size_t work_bytes = 0;
   float* d_k[3] = {nullptr, nullptr, nullptr};  // k tables (xh, ny, nz)
