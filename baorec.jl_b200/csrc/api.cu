@@ -568,7 +568,7 @@ int baorec_batch_files_f32(baorec_ctx* ctx, const baorec_params* p, int algorith
   const auto t0 = std::chrono::steady_clock::now();
   int status;
   {
-    FileBatchSource src(cfg, al);
+    FileBatchSource src(cfg, al, &ctx->batch_host_slots);  // the pinned buffer sets outlive the call
     status = batch_pipeline(ctx, p, algorithm, n_catalogs, field, shifts_only, src);
     if (status == BAOREC_OK) status = src.finish();
     else {

@@ -19,6 +19,7 @@
 
 #include "baorec_b200.h"
 #include "catalog_io.cuh"
+#include "host_slot.cuh"
 
 struct baorec_ctx;
 
@@ -69,9 +70,21 @@ struct FileBatchConfig {
 // acquire / release.  Writer thread: released slot -> NPY file, slot back to the reader.
 class FileBatchSource : public BatchSource {
  public:
-  FileBatchSource(const FileBatchConfig& cfg, HostAllocator al) : cfg_(cfg), al_(al) {
+  FileBatchSource(const FileBatchConfig& cfg, HostAllocator al, std::vector<HostSlot>* keep = nullptr)
+      : cfg_(cfg), al_(al), keep_(keep) {
     if (cfg_.n_slots < 3) cfg_.n_slots = 3;  // acquire(i + 1) happens while i is in flight and i - 1 awaits its release
     slots_.resize(cfg_.n_slots);
+    if (keep_) {  // adopt the buffer sets of an earlier call
+      for (size_t s = 0; s < keep_->size(); s++) {
+        if (s < slots_.size()) {
+          slots_[s].base = (*keep_)[s].base;
+          slots_[s].cap = (*keep_)[s].cap;
+        } else if ((*keep_)[s].base) {
+          al_.free((*keep_)[s].base);
+        }
+      }
+      keep_->clear();
+    }
     slot_of_.assign(cfg_.n_catalogs, -1);
     rows_.assign(cfg_.n_catalogs, 0);
     for (int s = 0; s < cfg_.n_slots; s++) free_.push_back(s);
@@ -80,8 +93,10 @@ class FileBatchSource : public BatchSource {
   }
   ~FileBatchSource() override {
     finish(true);
-    for (auto& s : slots_)
-      if (s.base) al_.free(s.base);
+    for (auto& s : slots_) {
+      if (keep_) keep_->push_back(HostSlot{s.base, s.cap});
+      else if (s.base) al_.free(s.base);
+    }
   }
 
   int acquire(int i, BatchItem* it) override {
@@ -236,7 +251,7 @@ class FileBatchSource : public BatchSource {
       if (path) {
         const auto t0 = clock::now();
         const float* cols[3] = {s.base + 4 * s.cap, s.base + 5 * s.cap, s.base + 6 * s.cap};
-        const int st = io::npy_write(path, 3, cols, s.n);
+        const int st = io::npy_write(path, 3, cols, s.n, cfg_.n_threads);
         if (st != BAOREC_OK) {
           record_failure(st);
           return;
@@ -253,6 +268,7 @@ class FileBatchSource : public BatchSource {
 
   FileBatchConfig cfg_;
   HostAllocator al_;
+  std::vector<HostSlot>* keep_;
   std::vector<Slot> slots_;
   std::vector<int> slot_of_;  // catalog -> slot once read
   std::vector<int64_t> rows_;

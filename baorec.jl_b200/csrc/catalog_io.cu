@@ -358,6 +358,40 @@ int npy_read(const MappedFile& f, const NpyHeader& h, int n_out, const int* cols
     }
   const char* base = f.p + h.data_offset;
   const int T = resolve_threads(n_threads, (size_t)N * (size_t)n_out * (size_t)h.dtype);
+  if (h.dtype == BAOREC_DTYPE_F32 && (h.fortran_order || K == 1) && N > 0) {
+    // the columns lie in the file as they will lie in memory: pread straight into the (pinned) arrays, one row range
+    // per thread -- no page of the file is mapped (mmap + memcpy measured 1.3 GB/s on the first hardware run: one
+    // minor fault per 4 KiB)
+    const int fd = ::open(path, O_RDONLY);
+    if (fd >= 0) {
+      std::vector<int> bad(T, 0);
+      parallel_for(T, [&](int t) {
+        const int64_t r0 = N * t / T, r1 = N * (t + 1) / T;
+        for (int j = 0; j < n_out && !bad[t]; j++) {
+          char* dst = reinterpret_cast<char*>(out[j] + r0);
+          size_t left = (size_t)(r1 - r0) * sizeof(float);
+          off_t off = (off_t)(h.data_offset + ((size_t)cols[j] * (size_t)N + (size_t)r0) * sizeof(float));
+          while (left > 0) {
+            const ssize_t got = pread(fd, dst, std::min<size_t>(left, (size_t)1 << 30), off);
+            if (got < 0 && errno == EINTR) continue;
+            if (got <= 0) {
+              bad[t] = 1;
+              break;
+            }
+            dst += got;
+            off += got;
+            left -= (size_t)got;
+          }
+        }
+      });
+      ::close(fd);
+      bool ok = true;
+      for (int t = 0; t < T; t++) ok &= !bad[t];
+      if (ok) return BAOREC_OK;
+      set_error("reading '%s' failed: %s", path, strerror(errno));
+      return BAOREC_ERR_IO;
+    }
+  }
   parallel_for(T, [&](int t) {
     const int64_t r0 = N * t / T, r1 = N * (t + 1) / T;
     for (int j = 0; j < n_out; j++) {
@@ -387,7 +421,7 @@ static int write_all(int fd, const void* buf, size_t n, const char* path) {
 
 // npzwrite(fn, hcat(cols...)): an (n, n_cols) Float32 matrix in Julia's column-major memory, which NPZ.jl stores as it
 // lies with 'fortran_order': True -- i.e. the SoA columns one after the other.  One column is written as a plain vector.
-int npy_write(const char* path, int n_cols, const float* const* cols, int64_t n) {
+int npy_write(const char* path, int n_cols, const float* const* cols, int64_t n, int n_threads) {
   char dict[160];
   if (n_cols == 1) snprintf(dict, sizeof dict, "{'descr': '<f4', 'fortran_order': False, 'shape': (%lld,), }", (long long)n);
   else snprintf(dict, sizeof dict, "{'descr': '<f4', 'fortran_order': True, 'shape': (%lld, %d), }", (long long)n, n_cols);
@@ -403,7 +437,35 @@ int npy_write(const char* path, int n_cols, const float* const* cols, int64_t n)
   }
   int s = write_all(fd, pre, sizeof pre, path);
   if (s == BAOREC_OK) s = write_all(fd, hd.data(), hd.size(), path);
-  for (int c = 0; c < n_cols && s == BAOREC_OK; c++) s = write_all(fd, cols[c], (size_t)n * sizeof(float), path);
+  // the columns: one row range per thread, each at its place in the file
+  const size_t col_bytes = (size_t)n * sizeof(float);
+  const int T = resolve_threads(n_threads, col_bytes * (size_t)n_cols);
+  std::vector<int> err(T, 0);
+  if (s == BAOREC_OK && n > 0)
+    parallel_for(T, [&](int t) {
+      const int64_t r0 = n * t / T, r1 = n * (t + 1) / T;
+      for (int c = 0; c < n_cols && !err[t]; c++) {
+        const char* src = reinterpret_cast<const char*>(cols[c] + r0);
+        size_t left = (size_t)(r1 - r0) * sizeof(float);
+        off_t off = (off_t)(10 + hd.size() + (size_t)c * col_bytes + (size_t)r0 * sizeof(float));
+        while (left > 0) {
+          const ssize_t w = pwrite(fd, src, std::min<size_t>(left, (size_t)1 << 30), off);
+          if (w < 0 && errno == EINTR) continue;
+          if (w <= 0) {
+            err[t] = errno ? errno : EIO;
+            break;
+          }
+          src += w;
+          off += w;
+          left -= (size_t)w;
+        }
+      }
+    });
+  for (int t = 0; t < T && s == BAOREC_OK; t++)
+    if (err[t]) {
+      set_error("writing '%s' failed: %s", path, strerror(err[t]));
+      s = BAOREC_ERR_IO;
+    }
   if (::close(fd) != 0 && s == BAOREC_OK) {
     set_error("closing '%s' failed: %s", path, strerror(errno));
     s = BAOREC_ERR_IO;
@@ -509,7 +571,7 @@ int baorec_npy_write_columns_f32(const char* path, int n_cols, const float* cons
   BR_REQUIRE(path && h_cols, "path / h_cols");
   BR_REQUIRE(n_cols >= 1 && n_cols <= 64 && n >= 0, "1 <= n_cols <= 64, n >= 0");
   for (int j = 0; j < n_cols; j++) BR_REQUIRE(h_cols[j] != nullptr || n == 0, "column array");
-  return io::npy_write(path, n_cols, h_cols, n);
+  return io::npy_write(path, n_cols, h_cols, n, 0);
 }
 
 int baorec_catalog_select_f32(int n_cols, float* const* h_cols, int64_t n, int key, float lo, float hi, int64_t* n_kept,

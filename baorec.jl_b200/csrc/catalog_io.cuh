@@ -52,7 +52,7 @@ struct NpyHeader {
 int npy_parse(const MappedFile& f, const char* path, NpyHeader* h);
 int npy_read(const MappedFile& f, const NpyHeader& h, int n_out, const int* cols, float* const* out, int64_t capacity,
              int n_threads, const char* path);
-int npy_write(const char* path, int n_cols, const float* const* cols, int64_t n);
+int npy_write(const char* path, int n_cols, const float* const* cols, int64_t n, int n_threads);
 
 // lo < key < hi, stable, in place; returns the rows kept
 int64_t select_rows(int n_cols, float* const* cols, int64_t n, int key, float lo, float hi, int n_threads);

@@ -408,6 +408,9 @@ int baorec_destroy(baorec_ctx* ctx) {
   for (int a = 0; a < 2; a++)
     if (ctx->d_tw[a]) cudaFree(ctx->d_tw[a]);
   if (ctx->d_gauss) cudaFree(ctx->d_gauss);
+  for (auto& hs : ctx->batch_host_slots)
+    if (hs.base) cudaFreeHost(hs.base);
+  ctx->batch_host_slots.clear();
   if (ctx->d_oob) cudaFree(ctx->d_oob);
   if (ctx->d_scal) cudaFree(ctx->d_scal);
   if (ctx->d_hash) cudaFree(ctx->d_hash);

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "baorec_b200.h"
+#include "host_slot.cuh"
 
 namespace baorec {
 
@@ -187,6 +188,7 @@ struct baorec_ctx {
   int opt_keep_delta_k = 1;    // device API: keep delta_k of the last reconstructed_overdensity! result
   int64_t opt_bin_min_particles = 1 << 18;  // catalogs at least this large are z-binned first
   int opt_fuse_kspace = 1;     // fixed-LOS iterations folded into one k-space pass
+  std::vector<baorec::HostSlot> batch_host_slots;  // pinned buffer sets of baorec_batch_files_f32, kept between calls
   int opt_batch_slots = 4;     // baorec_batch_files_f32: host buffer sets (>= 3: reading ahead | uploading + in flight | being written)
   int opt_scatter_tiles = 0;   // scatter: (z, y/8, x/128) tile order instead of z slabs
   int opt_det_scatter = 0;     // CIC scatter through 64-bit fixed-point integer reductions: bit-reproducible meshes
