@@ -5,7 +5,12 @@ neighbouring mocks overlapping the solve (BAOrec.run_batch -> baorec_batch_host_
 reads are not public, so synthetic lognormal boxes stand in (--npy DIR loads DIR/*.npy, one (n, 3) or (n, 4) array
 per mock: x, y, z[, w]).
 
-    python examples/many_mocks.py [--mocks 4] [--grid 512] [--particles 5e6] [--npy DIR] [--out DIR]
+--files DIR is the same loop from catalog FILES to result files, the way the reference's scripts bracket run! with
+CSV.jl and NPZ.jl (examples/simulation.jl:12-40): every DIR/*.dat (text: x y z [w]) or DIR/*.npy is read and parsed by
+the library's reader thread into pinned memory while the device reconstructs its predecessor, and a writer thread
+stores OUT/<name>.rec.npy as npzwrite(fn, hcat(new_pos...)) would (BAOrec.run_batch_files -> baorec_batch_files_f32).
+
+    python examples/many_mocks.py [--mocks 4] [--grid 512] [--particles 5e6] [--npy DIR | --files DIR] [--out DIR]
 """
 import argparse
 import sys
@@ -41,10 +46,23 @@ def main():
     ap.add_argument("--grid", type=int, default=512)
     ap.add_argument("--particles", type=float, default=5e6)
     ap.add_argument("--npy", default=None)
+    ap.add_argument("--files", default=None, help="directory of *.dat / *.npy catalogs: files in, files out")
+    ap.add_argument("--weights-column", type=int, default=-1, help="--files: 0-based column of the weights (-1: ones)")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     L = 1000.0
     box_size, box_min = np.float32([L, L, L]), np.float32([0.0, 0.0, 0.0])
+    if args.files:
+        files = sorted(p for p in Path(args.files).iterdir() if p.suffix in (".dat", ".txt", ".npy"))
+        out = Path(args.out or args.files)
+        out.mkdir(parents=True, exist_ok=True)
+        recon = BAOrec.IterativeRecon(bias=2.2, f=0.757, smoothing_radius=15.0, box_size=box_size, box_min=box_min,
+                                      los=(0.0, 0.0, 1.0), n_iter=3)
+        info = BAOrec.run_batch_files(recon, (args.grid,) * 3, files, [out / f"{f.stem}.rec.npy" for f in files],
+                                      columns=(0, 1, 2, args.weights_column), field="sum", positions=True)
+        print(f"{len(files)} catalogs ({sum(info['rows'])} rows), {args.grid}^3: {1e3 * info['total_s'] / len(files):.1f} ms per catalog "
+              f"(reader {info['read_s']:.2f} s, writer {info['write_s']:.2f} s, device waited {info['wait_s']:.2f} s for input)")
+        return
     if args.npy:
         files = sorted(Path(args.npy).glob("*.npy"))
         mocks = [pinned_columns(np.load(f)) for f in files]
