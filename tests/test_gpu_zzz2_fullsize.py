@@ -3,8 +3,7 @@
 TSC and with the multigrid solver).  What is checked needs no reference run: conservation, invariances and
 linearity of the operators, agreement between independent code paths of the engine (tile-sorted gather vs the
 catalog-order gather; cached vs recomputed read-back), exact identities between the entry points.
-(File name sorts last on purpose: written after this round's GPU budget was spent and NOT YET RUN ON HARDWARE; under
-`pytest -x` everything validated on a B200 earlier runs first.)"""
+(Written at the end of round 1 without GPU time left, hence the file name that sorts late; green on a B200 since round 2.)"""
 import numpy as np
 import pytest
 

@@ -74,7 +74,7 @@ def test_multigrid_tsc_on_slabs_matches_the_oracle(B, O, dctx):
 
 
 # ---- option "deterministic_scatter" (64-bit fixed-point integer reductions; csrc/mas_math.cuh: deposit_fixed) --------
-# Same status as above: arithmetic validated on the CPU (tests/test_mas_hostcheck.py), kernels not yet run on hardware.
+# Arithmetic validated on the CPU (tests/test_mas_hostcheck.py); green on a B200 since round 2 (profiles/r2_gpu_suite_final2.txt).
 @pytest.mark.parametrize("N", [50_000, 400_000])          # catalog-order kernel / unified sort + records kernel
 def test_deterministic_scatter_is_bit_reproducible(B, O, N):
     n, L = 64, 1000.0
