@@ -322,9 +322,10 @@ int npy_parse(const MappedFile& f, const char* path, NpyHeader* h) {
     h->shape[h->ndim++] = v;
   }
   h->data_offset = hoff + hlen;
-  const size_t need = (size_t)h->rows() * (size_t)h->cols() * (size_t)h->dtype;
-  if (h->data_offset + need > f.n) {
-    set_error("'%s': NPY data truncated (%zu bytes needed, %zu present)", path, need, f.n - h->data_offset);
+  // rows * cols * itemsize <= bytes present, without trusting the product not to overflow
+  const size_t avail = f.n - h->data_offset, r = (size_t)h->rows(), c = (size_t)h->cols();
+  if (r != 0 && c != 0 && (c > avail / (size_t)h->dtype || r > avail / (size_t)h->dtype / c)) {
+    set_error("'%s': NPY data truncated (shape (%zu, %zu) of %d-byte items, %zu bytes present)", path, r, c, h->dtype, avail);
     return BAOREC_ERR_IO;
   }
   return BAOREC_OK;

@@ -134,6 +134,12 @@ def test_npy_vector_and_rejections(B, IO, tmp_path):
     (tmp_path / "cut.npy").write_bytes(full[:-8])
     with pytest.raises(OSError, match="truncated"):
         IO.npy_info(tmp_path / "cut.npy")
+    # a header whose shape overflows 64 bits when multiplied out must not pass for "fits"
+    hd = b"{'descr': '<f4', 'fortran_order': True, 'shape': (4611686018427387904, 4), }"
+    hd += b" " * (118 - len(hd) - 1) + b"\n"
+    (tmp_path / "huge.npy").write_bytes(b"\x93NUMPY\x01\x00" + len(hd).to_bytes(2, "little") + hd + b"\0" * 64)
+    with pytest.raises(OSError, match="truncated"):
+        IO.npy_info(tmp_path / "huge.npy")
 
 
 @pytest.mark.parametrize("k,n", [(3, 0), (3, 1), (3, 12_345), (1, 17), (4, 9)])
