@@ -194,3 +194,22 @@ def test_lightcone_example_front_end(B, IO, tmp_path):
     m = (cat[:, 3] > np.float32(0.8)) & (cat[:, 3] < 1)
     assert np.array_equal(ra.numpy(), cat[m, 0]) and np.array_equal(nz.numpy(), cat[m, 4])
     assert np.array_equal(z.numpy(), cat[m, 3]) and np.array_equal(dec.numpy(), cat[m, 1])
+
+
+def test_python_mirror_validates_its_arguments(B, IO, tmp_path):
+    a = torch.arange(6, dtype=torch.float32)
+    with pytest.raises(ValueError, match="different lengths"):
+        IO.write_npy(tmp_path / "x.npy", a, a[:3].clone())
+    with pytest.raises(ValueError, match="at least one"):
+        IO.write_npy(tmp_path / "x.npy")
+    with pytest.raises(TypeError, match="contiguous 1-D float32"):
+        IO.write_npy(tmp_path / "x.npy", a[::2])                     # a strided view
+    with pytest.raises(TypeError, match="contiguous 1-D float32"):
+        IO.write_npy(tmp_path / "x.npy", a.double())
+    with pytest.raises(ValueError, match="different lengths"):
+        IO.select_rows([a, a[:2].clone()], 0, 0.0, 1.0)
+    with pytest.raises(B.BaorecError):
+        IO.select_rows([a], 3, 0.0, 1.0)                              # key column out of range
+    with pytest.raises(ValueError, match="one character"):
+        IO.scan_text_catalog(tmp_path / "x.txt", delim="::")
+    assert not (tmp_path / "x.npy").exists()
