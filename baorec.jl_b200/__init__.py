@@ -20,6 +20,6 @@ from .host import (Context, FFTPlan, IterativeRecon, MultigridRecon, setup_fft, 
 from . import dist
 from . import catalog_io
 from .catalog_io import (scan_text_catalog, read_text_catalog, npy_info, read_npy_catalog, write_npy, select_rows)
-from .catalog import Cosmology, DESICosmology, sky_to_cartesian, cartesian_to_sky, fkp_weights, wrap_positions, power_multipoles, interlace_positions, compute_auto_box
+from .catalog import Cosmology, DESICosmology, E, H, comoving_distance, comoving_distance_interp, redshift_interp, sky_to_cartesian, cartesian_to_sky, fkp_weights, wrap_positions, power_multipoles, interlace_positions, compute_auto_box
 
 lib_loader.load()   # no library -> ImportError; there is no fallback path

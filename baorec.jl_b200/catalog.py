@@ -91,6 +91,76 @@ def DESICosmology(**kwargs) -> Cosmology:
     return Cosmology(**base)
 
 
+# ---- the scalar functions of src/cosmo.jl:70-98 (host set-up arithmetic, Float64 like the reference's quadgk nodes) -------
+def E(c: Cosmology, z):
+    """`E(c, z)` src/cosmo.jl:70-78: sqrt of the density parameters scaled to redshift z (CPL dark energy)."""
+    z = np.asarray(z, np.float64)
+    a1 = 1.0 + z
+    w0, wa = float(c.w0), float(c.wa)
+    fde = -3.0 * (1.0 + w0)
+    if wa != 0.0:
+        a = 1.0 / a1
+        with np.errstate(divide="ignore", invalid="ignore"):
+            fde = fde + 3.0 * wa * ((a - 1.0) / np.log(a) - 1.0)
+    return np.sqrt((float(c.Omega_nu0) + float(c.Omega_g0)) * a1 ** 4 + (float(c.Omega_b0) + float(c.Omega_c0)) * a1 ** 3
+                   + float(c.Omega_k0) * a1 ** 2 + float(c.Omega_L0) * a1 ** (-fde))
+
+
+def H(c: Cosmology, z):
+    """`H(c, z) = c.h * 100 * E(c, z)` src/cosmo.jl:79 [km/s/Mpc]; `c.h * 100` is the Float32 product."""
+    return float(_f32(c.h * _f32(100))) * E(c, z)
+
+
+def _host_table(c: Cosmology, z_min=None, z_max=None, num=None):
+    """The library's host-side comoving-distance table (baorec_cosmo_build_table: 7-point Gauss-Legendre per knot
+    interval); the cosmology's own table range unless another is given."""
+    p = c._params()
+    if z_max is not None:
+        p.z_tab_min, p.z_tab_max, p.z_tab_num = float(z_min), float(z_max), int(num)
+    n = int(p.z_tab_num)
+    z, r = np.empty(n, np.float64), np.empty(n, np.float64)
+    L.check(L.load().baorec_cosmo_build_table(C.byref(p), z.ctypes.data_as(C.POINTER(C.c_double)),
+                                              r.ctypes.data_as(C.POINTER(C.c_double))))
+    return z, r
+
+
+def comoving_distance(c: Cosmology, z):
+    """`comoving_distance(c, z)` src/cosmo.jl:80-82: c * int_0^z dz'/H(z') [Mpc], one redshift (the reference: quadgk,
+    rtol 1e-8; here the library's quadrature over 4096 sub-intervals of [0, z])."""
+    z = float(z)
+    if z == 0.0:
+        return 0.0
+    return float(_host_table(c, 0.0, z, 4097)[1][-1])
+
+
+def _gridded_linear(knots, values, x, what):
+    x = np.asarray(x, np.float64)
+    if x.size and (np.any(~(x >= knots[0])) or np.any(~(x <= knots[-1]))):
+        raise L.OutOfRangeError(L.ERR_OUT_OF_RANGE, f"{what} outside the tabulated range [{knots[0]}, {knots[-1]}]")
+    i = np.clip(np.searchsorted(knots, x, side="right") - 1, 0, len(knots) - 2)
+    t = (x - knots[i]) / (knots[i + 1] - knots[i])
+    return (1.0 - t) * values[i] + t * values[i + 1]
+
+
+def comoving_distance_interp(c: Cosmology):
+    """`comoving_distance_interp(c)` src/cosmo.jl:83-90: the Gridded(Linear()) interpolator r(z) [Mpc] over the cached
+    table, as a host callable (scalars or numpy arrays; the per-particle device path is `sky_to_cartesian`).  Outside the
+    table it raises like Interpolations.jl's BoundsError."""
+    if getattr(c, "_host_cache", None) is None:
+        c._host_cache = _host_table(c)
+    z, r = c._host_cache
+    return lambda x: _gridded_linear(z, r, x, "redshift")
+
+
+def redshift_interp(c: Cosmology):
+    """`redshift_interp(c)` src/cosmo.jl:91-98: the inverse table z(r), r in Mpc (host callable; device path:
+    `cartesian_to_sky`)."""
+    if getattr(c, "_host_cache", None) is None:
+        c._host_cache = _host_table(c)
+    z, r = c._host_cache
+    return lambda x: _gridded_linear(r, z, x, "distance")
+
+
 def sky_to_cartesian(data_cat_ra, data_cat_dec, data_cat_red, cosmo: Cosmology):
     """examples/lightcone.jl:30-49: (ra, dec [deg], redshift) -> (x, y, z) [Mpc/h], three new tensors."""
     n = _chk_vec(data_cat_ra, data_cat_dec, data_cat_red)

@@ -241,3 +241,27 @@ def test_device_arithmetic_against_the_golden_fixture(HC, B):
     HC.hc_wrap_positions(fp(p[0]), fp(p[1]), fp(p[2]), n, fp(g["wrap_box_size"]), fp(g["wrap_box_min"]))
     for got, k in zip(p, ("wx", "wy", "wz")):
         assert np.array_equal(got.view(np.uint32), g[k].view(np.uint32))
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(z_tab_max=10), dict(w0=-0.9, wa=0.1, z_tab_max=2), dict(z_tab_min=0.4, z_tab_max=1.6, z_tab_num=4097)])
+def test_scalar_cosmology_functions_mirror_the_reference(B, kw):
+    """E, H, comoving_distance and the two interpolators of src/cosmo.jl:70-98 as host callables of the product mirror
+    (table from the library's own quadrature) against the oracle's restatement (scipy quad, rtol 1e-10)."""
+    mine, ref = B.Cosmology(**kw), CO.Cosmology(**kw)
+    z = np.array([0.0, 1e-3, 0.5, 0.8754, 1.0, 1.5999])
+    assert np.allclose(B.E(mine, z), CO.E(ref, z), rtol=1e-14, atol=0)
+    assert np.allclose(B.H(mine, z), CO.H(ref, z), rtol=1e-14, atol=0)
+    for zi in (0.0, 0.3, 1.0, 2.5):
+        assert B.comoving_distance(mine, zi) == pytest.approx(CO.comoving_distance(ref, zi), rel=1e-9, abs=0)
+    r_fun, z_fun = B.comoving_distance_interp(mine), B.redshift_interp(mine)
+    r_ref, z_ref = CO.comoving_distance_interp(ref), CO.redshift_interp(ref)
+    zq = np.linspace(max(float(mine.z_tab_min), 0.41), 1.59, 1001)
+    assert np.allclose(r_fun(zq), r_ref(zq), rtol=1e-12, atol=0)
+    rq = np.asarray(r_ref(zq))
+    assert np.allclose(z_fun(rq), z_ref(rq), rtol=1e-11, atol=1e-13)
+    assert np.allclose(z_fun(r_fun(zq)), zq, rtol=0, atol=1e-9)               # the two tables invert each other
+    assert float(r_fun(0.9)) == pytest.approx(float(r_ref(0.9)), rel=1e-12)   # scalars work too
+    with pytest.raises(B.OutOfRangeError):                                    # Interpolations.jl: BoundsError
+        r_fun(float(mine.z_tab_max) + 1.0)
+    with pytest.raises(B.OutOfRangeError):
+        z_fun(-1.0)
