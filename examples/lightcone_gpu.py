@@ -87,8 +87,8 @@ def main():
         if args.out:                                                            # npzwrite("...dat.rec.npy", hcat(new_pos...)) etc.
             out = Path(args.out)
             out.mkdir(parents=True, exist_ok=True)
-            for tag, cat in zip(("dat.rec", "ran.rec.sym", "ran.rec.iso"), sky):
-                BAOrec.write_npy(out / f"{name}.{tag}.npy", *[c.cpu() for c in cat])
+            for tag, cat, nz in zip(("dat.rec", "ran.rec.sym", "ran.rec.iso"), sky, (d_nz, r_nz, r_nz)):
+                BAOrec.write_npy(out / f"{name}.{tag}.npy", *[c.cpu() for c in cat], nz.cpu())   # hcat(new_pos', nz): (N, 4) ra dec z nz
 
 
 if __name__ == "__main__":
