@@ -147,4 +147,6 @@ def test_io_threads_under_sanitizers(tmp_path, sanitizer):
     env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=66", ASAN_OPTIONS="detect_leaks=1 exitcode=66",
                UBSAN_OPTIONS="halt_on_error=1 exitcode=66")
     r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True, env=env, timeout=600)
+    if "unexpected memory mapping" in r.stderr or "Shadow memory range interleaves" in r.stderr:
+        pytest.skip("the sanitizer runtime cannot map its shadow memory on this kernel / ASLR setting")
     assert r.returncode == 0 and "done bad=0" in r.stdout, (r.stdout + r.stderr)[-3000:]
